@@ -1,0 +1,137 @@
+"""Synthetic test matrices of BASELINE.json (lower-triangular CSC, 1-based).
+
+Every generator returns (n, ptr[int64, n+1], row[int32], val[float64]) holding
+the LOWER triangle column by column with 1-based index values, i.e. exactly the
+arrays `ssids_analyse`/`ssids_factor` take (docs/Fortran/ssids.rst, `ptr,row,val`).
+"""
+import numpy as np
+import scipy.sparse as sp
+
+
+def _lower_csc(A):
+    A = sp.tril(sp.csc_matrix(A), format="csc")
+    A.sort_indices()
+    n = A.shape[0]
+    return (n, (A.indptr.astype(np.int64) + 1), (A.indices.astype(np.int32) + 1),
+            A.data.astype(np.float64))
+
+
+def to_scipy(n, ptr, row, val):
+    """Full symmetric scipy CSC from the lower-triangular 1-based arrays."""
+    L = sp.csc_matrix((val, row - 1, ptr - 1), shape=(n, n))
+    return (L + sp.tril(L, -1).T).tocsc()
+
+
+def laplacian_2d_5pt(nx, ny=None):
+    """cfg1: 2-D 5-point Laplacian, diag 4, off-diagonals -1 (posdef)."""
+    ny = ny or nx
+    ex, ey = np.ones(nx), np.ones(ny)
+    Tx = sp.diags([-ex[:-1], 2 * ex, -ex[:-1]], [-1, 0, 1])
+    Ty = sp.diags([-ey[:-1], 2 * ey, -ey[:-1]], [-1, 0, 1])
+    A = sp.kron(sp.eye(ny), Tx) + sp.kron(Ty, sp.eye(nx))
+    return _lower_csc(A)
+
+
+def laplacian_3d_7pt(nx, ny=None, nz=None):
+    """cfg2: 3-D 7-point Laplacian, diag 6, off-diagonals -1 (posdef)."""
+    ny = ny or nx
+    nz = nz or nx
+
+    def T(k):
+        e = np.ones(k)
+        return sp.diags([-e[:-1], 2 * e, -e[:-1]], [-1, 0, 1])
+    A = (sp.kron(sp.eye(nz), sp.kron(sp.eye(ny), T(nx))) +
+         sp.kron(sp.eye(nz), sp.kron(T(ny), sp.eye(nx))) +
+         sp.kron(T(nz), sp.kron(sp.eye(ny), sp.eye(nx))))
+    return _lower_csc(A)
+
+
+def stencil_3d_27pt(nx, ny=None, nz=None, shift=0.0):
+    """cfg3/cfg5: 3-D 27-point stencil, diag 26, all 26 neighbours -1, minus
+    shift*I.  shift=0 is positive semi-definite-ish (diag dominant, posdef);
+    a shift inside the spectrum (e.g. 13) makes it indefinite."""
+    ny = ny or nx
+    nz = nz or nx
+
+    def B(k):   # tridiagonal of ones (incl. diagonal)
+        e = np.ones(k)
+        return sp.diags([e[:-1], e, e[:-1]], [-1, 0, 1])
+    N = sp.kron(B(nz), sp.kron(B(ny), B(nx)))          # 27 ones incl. centre
+    n = nx * ny * nz
+    A = -N + (27.0 - shift) * sp.eye(n)                  # centre: -1 + 27 - shift = 26 - shift
+    return _lower_csc(A)
+
+
+class SpralRandom:
+    """Restatement of the reference's LCG (src/random.f90:15-22,55-80):
+    x <- (1103515245*x + 12345) mod 2^31, default seed 486502."""
+    A, C_, M = 1103515245, 12345, 2 ** 31
+
+    def __init__(self, seed=486502):
+        self.state = seed
+
+    def real(self, positive=False):
+        self.state = (self.A * self.state + self.C_) % self.M
+        if positive:
+            return float(self.state) / float(self.M)
+        return 1.0 - 2.0 * float(self.state) / float(self.M)
+
+    def integer(self, n):
+        self.state = (self.A * self.state + self.C_) % self.M
+        return int(self.state * n // self.M) + 1
+
+
+def kkt_saddle(n, frac_constraints=0.3, nnz_per_row=6, seed=486502):
+    """cfg4: synthetic KKT saddle-point matrix [H B^T; B 0] of order n with
+    m = frac*n zero-diagonal constraint rows.  H is a sparse diagonally dominant
+    SPD block, B a sparse full-row-rank block; entries are drawn with the
+    restated spral_random LCG for scalars and numpy (seeded from it) for bulk
+    patterns, so the matrix is deterministic."""
+    m = int(round(frac_constraints * n))
+    nh = n - m
+    lcg = SpralRandom(seed)
+    rng = np.random.default_rng(lcg.integer(2 ** 30))
+    # H: random symmetric pattern + dominant diagonal
+    k = nnz_per_row // 2
+    r = np.repeat(np.arange(nh), k)
+    c = rng.integers(0, nh, size=nh * k)
+    v = rng.uniform(-1.0, 1.0, size=nh * k)
+    Hoff = sp.coo_matrix((v, (r, c)), shape=(nh, nh)).tocsr()
+    Hoff = sp.tril(Hoff, -1)
+    Hoff = Hoff + Hoff.T
+    d = np.asarray(abs(Hoff).sum(axis=1)).ravel() + 1.0
+    H = Hoff + sp.diags(d)
+    # B: each constraint couples nnz_per_row primal variables; a shifted identity
+    # makes it full row rank
+    rb = np.repeat(np.arange(m), nnz_per_row)
+    cb = rng.integers(0, nh, size=m * nnz_per_row)
+    vb = rng.uniform(-1.0, 1.0, size=m * nnz_per_row)
+    Bm = sp.coo_matrix((vb, (rb, cb)), shape=(m, nh)).tocsr()
+    Bm = Bm + sp.coo_matrix((np.full(m, 2.0), (np.arange(m), np.arange(m) % nh)), shape=(m, nh))
+    K = sp.bmat([[H, Bm.T], [Bm, None]], format="csc")
+    # explicit zero diagonal for the (2,2) block so that pivots are well defined
+    K = K + sp.csc_matrix((np.zeros(m), (np.arange(nh, n), np.arange(nh, n))), shape=(n, n))
+    return _lower_csc_keep_zeros(K)
+
+
+def _lower_csc_keep_zeros(A):
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    n = A.shape[0]
+    ptr = [0]
+    rows, vals = [], []
+    indptr, indices, data = A.indptr, A.indices, A.data
+    keep = np.zeros(len(indices), dtype=bool)
+    col = np.repeat(np.arange(n), np.diff(indptr))
+    keep = indices >= col
+    newcounts = np.bincount(col[keep], minlength=n)
+    ptr = np.concatenate([[0], np.cumsum(newcounts)]).astype(np.int64) + 1
+    return n, ptr, (indices[keep].astype(np.int32) + 1), data[keep].astype(np.float64)
+
+
+def example_5x5():
+    """The matrix of examples/C/ssids.c:18-31 (solution of its rhs is 1..5)."""
+    ptr = np.array([1, 3, 6, 8, 9, 10], dtype=np.int64)
+    row = np.array([1, 2, 2, 3, 5, 3, 4, 4, 5], dtype=np.int32)
+    val = np.array([2.0, 1.0, 4.0, 1.0, 1.0, 3.0, 2.0, -1.0, 2.0])
+    return 5, ptr, row, val
