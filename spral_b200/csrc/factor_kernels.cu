@@ -1,0 +1,734 @@
+/* Panel kernels of the B200 SSIDS numeric engine (sm_100a).
+ *
+ * What they replace in the reference (ralna/spral):
+ *   k_scatter_a        cu_load_nodes[_sc]       src/ssids/gpu/kernels/assemble.cu:41-98
+ *   k_assemble         assemble<>               src/ssids/gpu/kernels/assemble.cu:172-232
+ *   k_delays           add_delays               src/ssids/gpu/kernels/assemble.cu:248-274
+ *   k_diag/k_apply/... cu_multiblock_ldlt/chol + setup + reorder family
+ *                      src/ssids/gpu/kernels/dense_factor.cu:228-334,1092-1122,1350-1373
+ *                      src/ssids/gpu/kernels/reorder.cu
+ *   k_finalize         cu_collect_stats         src/ssids/gpu/kernels/dense_factor.cu:1380-1430
+ * and whose numerical semantics follow the reference CPU kernels (the oracle):
+ *   in-block pivoting  block_ldlt               src/ssids/cpu/kernels/block_ldlt.hxx:289-413
+ *   a-posteriori test  check_threshold          src/ssids/cpu/kernels/ldlt_app.cxx:303-321
+ *   statistics         NumericSubtree ctor      src/ssids/cpu/NumericSubtree.hxx:248-280
+ *
+ * Pivoting state machine (all decisions on the device, see engine.h:Front).
+ * A front's n fully-summed columns are processed in outer panels of PW columns;
+ * each panel in inner steps of BS columns:
+ *   k_diag    advance state; factor the BS x BS diagonal block with full
+ *             pivoting inside the block (1x1 / 2x2), keep L11, L11*D, D^-1, lperm
+ *   k_apply   rows below the block: solve against L11^T, scale by D^-1, write
+ *             the candidate L in place (originals are backed up), record the
+ *             first column that violates |l_ij| <= 1/u
+ *   k_commit  accept the columns before the first failure; restore the failed
+ *             ones from the backup; permute the already-factored rows
+ *   update    (gemm_dmma.cu) trailing update restricted to the panel
+ *   k_swap    move the failed columns to the end of the panel
+ * and at the end of a panel the outer DMMA update of everything right of the
+ * panel, then k_swap(outer) moves the panel's failed columns to the end of the
+ * candidate range.  Failed columns are retried in later passes; what is left
+ * is delayed to the parent.
+ */
+#include "engine.h"
+#include "device_utils.cuh"
+
+namespace b200 {
+
+/* ------------------------------------------------------------------------ */
+/* A scatter (init of a front)                                               */
+/* ------------------------------------------------------------------------ */
+
+constexpr int SCATTER_CHUNK = 1024;
+
+/* lcol(dest) = aval(src) [* scaling]; follows add_a_block
+ * (src/ssids/cpu/kernels/assemble.hxx:50-86): dest is relative to the
+ * undelayed m0 x n0 node, rows >= n0 shift down by ndin. */
+__global__ void __launch_bounds__(256)
+k_scatter_a(Front* fronts, const int2* work, const int64_t* __restrict__ nlist,
+      const int64_t* __restrict__ nptr, const int* __restrict__ node_of_front,
+      const double* __restrict__ aval, const double* __restrict__ scaling) {
+   int2 w = work[blockIdx.x];
+   const Front* f = &fronts[w.x];
+   int node = node_of_front[w.x];
+   int64_t beg = nptr[node] + (int64_t)w.y * SCATTER_CHUNK;
+   int64_t end = min(beg + SCATTER_CHUNK, nptr[node + 1]);
+   int m0 = f->m0, n0 = f->n0, ndin = f->ndin, ldl = f->ldl;
+   double* L = f->L;
+   const int* rows = f->rows;
+   for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      int64_t src = nlist[2 * i] - 1;
+      int64_t dest = nlist[2 * i + 1] - 1;
+      int c = (int)(dest / m0);
+      int r = (int)(dest % m0);
+      double v = aval[src];
+      if (scaling) v = scaling[rows[r] - 1] * v * scaling[rows[c] - 1];
+      if (r >= n0) r += ndin;
+      L[r + (size_t)c * ldl] = v;
+   }
+}
+
+void launch_scatter_a(Front* fronts, const int2* work, int nwork, const int64_t* nlist,
+      const int64_t* nptr, const int* node_of_front, const double* aval,
+      const double* scaling, cudaStream_t s) {
+   if (nwork == 0) return;
+   k_scatter_a<<<nwork, 256, 0, s>>>(fronts, work, nlist, nptr, node_of_front, aval, scaling);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Extend-add                                                                */
+/* ------------------------------------------------------------------------ */
+
+constexpr int ASM_COLS = 8;   // child columns per CTA
+
+/* dest(map(i), map(j)) += C(i,j), i >= j.  Child columns whose image is one
+ * of the parent's own columns go to the parent's L (to_contrib = false, run
+ * before the parent is factorised), the others to the parent's contribution
+ * block (to_contrib = true, run after the parent's Schur complement was
+ * formed).  Follows assemble_expected / assemble_expected_contrib
+ * (src/ssids/cpu/kernels/assemble.hxx:88-139).  Children of one parent are
+ * processed in separate launches (one launch per child rank) so that the
+ * summation order is fixed; ATOMIC is used only for high-degree parents. */
+template <bool ATOMIC>
+__global__ void __launch_bounds__(256)
+k_assemble(Front* fronts, const AsmSrc* srcs, const int2* work, int to_contrib) {
+   int2 w = work[blockIdx.x];
+   const AsmSrc* s = &srcs[w.x];
+   if (!s->C) return;
+   const Front* p = &fronts[s->parent];
+   int cm = s->cm, ldc = s->ldc, npassl = s->npassl;
+   int j0 = w.y * ASM_COLS, j1 = min(j0 + ASM_COLS, cm);
+   if (to_contrib) { j0 = max(j0, npassl); } else { j1 = min(j1, npassl); }
+   if (j0 >= j1) return;
+   const int* __restrict__ map = s->map;
+   const double* __restrict__ C = s->C;
+   int n0 = p->n0, ndin = p->ndin;
+   double* dest;
+   size_t ldd;
+   int roff;
+   if (to_contrib) { dest = p->C; ldd = p->ldc; roff = -n0; }
+   else            { dest = p->L; ldd = p->ldl; roff = 0; }
+   for (int i = j0 + threadIdx.x; i < cm; i += blockDim.x) {
+      int pi = map[i] - 1;
+      int r = to_contrib ? pi - n0 : (pi < n0 ? pi : pi + ndin);
+      int jmax = min(j1, i + 1);
+      for (int j = j0; j < jmax; ++j) {
+         double v = C[i + (size_t)j * ldc];
+         size_t d = (size_t)r + (size_t)(map[j] - 1 + roff) * ldd;
+         if (ATOMIC) atomicAdd(&dest[d], v);
+         else dest[d] += v;
+      }
+   }
+}
+
+void launch_assemble(Front* fronts, const AsmSrc* srcs, const int2* work, int nwork,
+      bool to_contrib, bool use_atomics, cudaStream_t s) {
+   if (nwork == 0) return;
+   if (use_atomics) k_assemble<true><<<nwork, 256, 0, s>>>(fronts, srcs, work, to_contrib);
+   else k_assemble<false><<<nwork, 256, 0, s>>>(fronts, srcs, work, to_contrib);
+}
+int assemble_cols_per_cta() { return ASM_COLS; }
+int scatter_chunk() { return SCATTER_CHUNK; }
+
+/* Delayed columns of a child become extra fully-summed columns of the parent,
+ * placed after its own n0 columns.  Follows assemble_pre
+ * (src/ssids/cpu/kernels/assemble.hxx:244-263): the ndelay x ndelay lower
+ * square goes to the diagonal, the child's contribution rows either below the
+ * new column or, when they are own columns of the parent, transposed into the
+ * new ROW.  work[i] = (src, delayed column). */
+__global__ void __launch_bounds__(128)
+k_delays(Front* fronts, const AsmSrc* srcs, const int2* work) {
+   int2 w = work[blockIdx.x];
+   const AsmSrc* s = &srcs[w.x];
+   const Front* p = &fronts[s->parent];
+   int j = w.y;
+   int nd = s->ndelay, cm = s->cm, ldd = s->lddelay;
+   int pc = s->delay_col + j;
+   size_t ldl = p->ldl;
+   double* L = p->L;
+   const double* __restrict__ src = s->dval + (size_t)j * ldd;
+   if (threadIdx.x == 0) p->perm[pc] = s->dperm[j];
+   for (int i = j + threadIdx.x; i < nd; i += blockDim.x)
+      L[(size_t)(s->delay_col + i) + pc * ldl] = src[i];
+   int n0 = p->n0, ndin = p->ndin;
+   const int* __restrict__ map = s->map;
+   for (int k = threadIdx.x; k < cm; k += blockDim.x) {
+      int pi = map[k] - 1;
+      double v = src[nd + k];
+      if (pi < n0) L[pc + (size_t)pi * ldl] = v;
+      else         L[(size_t)(pi + ndin) + pc * ldl] = v;
+   }
+}
+
+void launch_delays(Front* fronts, const AsmSrc* srcs, const int2* work, int nwork, cudaStream_t s) {
+   if (nwork == 0) return;
+   k_delays<<<nwork, 128, 0, s>>>(fronts, srcs, work);
+}
+
+/* ------------------------------------------------------------------------ */
+/* State machine                                                             */
+/* ------------------------------------------------------------------------ */
+
+/* Accounts the last inner step and opens / closes panels and passes.
+ * Executed by ONE thread per front (first thing in k_diag and k_finalize). */
+__device__ void advance_state(Front* f, bool new_panel) {
+   if (f->finished) return;
+   if (f->step_valid) {
+      int ne = calc_ne(f);
+      f->done += ne;
+      f->pend -= f->bs - ne;
+      f->step_valid = 0;
+   }
+   if (new_panel && f->panel_open) {
+      f->end -= f->pend0 - f->pend;   // failed columns were swapped to the end
+      f->panel_open = 0;
+   }
+   if (!f->panel_open) {
+      if (f->done == f->end) {
+         if (f->first_pass_done < 0) f->first_pass_done = f->done;
+         if (f->end == f->n) f->finished = 1;
+         else if (f->done > f->pass_start) { f->pass_start = f->done; f->end = f->n; }
+         else f->finished = 1;
+      }
+      if (!f->finished) {
+         f->p0 = f->done;
+         f->pend0 = min(f->done + PW, f->end);
+         f->pend = f->pend0;
+         f->panel_open = 1;
+      }
+   }
+   if (f->finished) f->nelim = f->done;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Diagonal block                                                            */
+/* ------------------------------------------------------------------------ */
+
+/* One warp per front; lane r owns row r of the block. */
+template <bool POSDEF>
+__global__ void __launch_bounds__(32)
+k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
+   Front* f = &fronts[flist[blockIdx.x]];
+   const int lane = threadIdx.x;
+   __shared__ double a[BS][BS + 1];
+   __shared__ double ld[BS][BS + 1];
+   __shared__ double dinv[2 * BS];
+   __shared__ int lperm[BS];
+
+   if (lane == 0) {
+      advance_state(f, new_panel != 0);
+      if (!f->finished && f->done < f->pend) {
+         f->bs = min(BS, f->pend - f->done);
+         f->first_fail = f->bs;
+         f->step_valid = 1;
+      } else {
+         f->bs = 0;
+      }
+   }
+   __syncwarp();
+   if (f->finished || f->bs == 0) return;
+   const int bs = f->bs, done = f->done, ldl = f->ldl;
+   double* Ld = f->L + (size_t)done * ldl + done;   // the diagonal block
+   BlockWS* ws = f->ws;
+
+   /* load the lower triangle (coalesced per column), then mirror */
+   for (int c = 0; c < BS; ++c) {
+      double v = 0.0;
+      if (lane < bs && c < bs && lane >= c) v = Ld[lane + (size_t)c * ldl];
+      a[lane][c] = v;
+      ld[lane][c] = 0.0;
+   }
+   __syncwarp();
+   for (int c = lane + 1; c < BS; ++c) a[lane][c] = a[c][lane];
+   lperm[lane] = lane;
+   dinv[2 * lane] = 0.0; dinv[2 * lane + 1] = 0.0;
+   __syncwarp();
+
+   if (POSDEF) {
+      /* Cholesky of the block (cholesky_factor, src/ssids/cpu/kernels/cholesky.cxx:33-187) */
+      bool ok = true;
+      for (int p = 0; p < bs; ++p) {
+         double d = a[p][p];
+         if (!(d > 0.0)) { ok = false; break; }
+         double lpp = sqrt(d);
+         double l = 0.0;
+         if (lane > p && lane < bs) { l = a[lane][p] / lpp; a[lane][p] = l; }
+         if (lane == p) { a[p][p] = lpp; dinv[p] = 1.0 / lpp; }
+         __syncwarp();
+         if (lane > p && lane < bs)
+            for (int c = p + 1; c <= lane; ++c) a[lane][c] -= l * a[c][p];
+         __syncwarp();
+      }
+      if (!ok) {
+         if (lane == 0) { f->flag = SPRAL_SSIDS_ERROR_NOT_POS_DEF; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
+         return;
+      }
+      for (int c = 0; c < bs; ++c) {
+         if (lane < bs && lane >= c) Ld[lane + (size_t)c * ldl] = a[lane][c];
+         ws->l11[lane + c * BS] = (lane < bs && lane >= c) ? a[lane][c] : 0.0;
+      }
+      for (int c = bs; c < BS; ++c) ws->l11[lane + c * BS] = 0.0;
+      ws->dinv[lane] = (lane < bs) ? dinv[lane] : 0.0;
+      return;
+   }
+
+   /* keep the unfactorised block for k_commit */
+   for (int c = 0; c < BS; ++c) ws->a0[lane + c * BS] = a[lane][c];
+
+   int p = 0;
+   while (p < bs) {
+      /* largest remaining entry of the lower triangle: lane r scans its row */
+      double best = -1.0;
+      int bidx = 0;
+      if (lane >= p && lane < bs) {
+         for (int c = p; c <= lane; ++c) {
+            double v = fabs(a[lane][c]);
+            if (v > best) { best = v; bidx = c * BS + lane; }
+         }
+      }
+      #pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+         double ob = __shfl_xor_sync(0xffffffffu, best, off);
+         int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+         if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      }
+      int m = bidx / BS, t = bidx % BS;   // column m <= row t
+
+      if (!(best >= prm.small)) {
+         /* everything left is (numerically) zero: block_ldlt.hxx:303-317 */
+         if (!prm.action) {
+            if (lane == 0) { f->flag = SPRAL_SSIDS_ERROR_SINGULAR; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
+            return;
+         }
+         for (int q = p; q < bs; ++q) {
+            if (lane >= q) a[lane][q] = (lane == q) ? 1.0 : 0.0;
+            ld[lane][q] = 0.0;
+            if (lane == 0) { dinv[2 * q] = 0.0; dinv[2 * q + 1] = 0.0; }
+         }
+         __syncwarp();
+         break;
+      }
+
+      int pivsiz;
+      double a11 = 0, a21 = 0, a22 = 0, detscale = 0, detpiv = 0;
+      if (t == m) {
+         pivsiz = 1;
+      } else {
+         a11 = a[m][m]; a22 = a[t][t]; a21 = a[t][m];
+         detscale = 1.0 / fabs(a21);
+         detpiv = (a11 * detscale) * a22 - fabs(a21);
+         if (fabs(detpiv) >= fabs(a21) / 2) pivsiz = 2;
+         else {
+            pivsiz = 1;
+            if (fabs(a11) > fabs(a22)) t = m; /* a11 as 1x1 */
+            /* else a22 (row/col t) as 1x1 */
+         }
+      }
+      __syncwarp();
+
+      /* symmetric swaps within the block (full storage) */
+      auto swap_sym = [&](int i, int j) {
+         if (i == j) return;
+         double x = a[lane][i]; a[lane][i] = a[lane][j]; a[lane][j] = x;   // columns
+         __syncwarp();
+         x = a[i][lane]; a[i][lane] = a[j][lane]; a[j][lane] = x;          // rows (incl. L part)
+         x = ld[i][lane]; ld[i][lane] = ld[j][lane]; ld[j][lane] = x;
+         if (lane == 0) { int q = lperm[i]; lperm[i] = lperm[j]; lperm[j] = q; }
+         __syncwarp();
+      };
+
+      if (pivsiz == 1) {
+         swap_sym(p, t);
+         double piv = a[p][p];
+         double d11 = 1.0 / piv;
+         double wr = a[lane][p];          // original column (L*D)
+         double lr = wr * d11;
+         __syncwarp();
+         if (lane > p && lane < bs) { ld[lane][p] = wr; a[lane][p] = lr; }
+         if (lane == p) { a[p][p] = 1.0; dinv[2 * p] = d11; dinv[2 * p + 1] = 0.0; }
+         __syncwarp();
+         if (lane > p && lane < bs) {
+            for (int c = p + 1; c < bs; ++c) {
+               /* identical rounding for (r,c) and (c,r) keeps the block symmetric */
+               double upd = (c <= lane) ? lr * ld[c][p] : a[c][p] * wr;
+               a[lane][c] -= upd;
+            }
+         }
+         __syncwarp();
+         p += 1;
+      } else {
+         swap_sym(p, m);
+         swap_sym(p + 1, t);
+         double d11 = (a22 * detscale) / detpiv;
+         double d22 = (a11 * detscale) / detpiv;
+         double d21 = (-a21 * detscale) / detpiv;
+         double w1 = a[lane][p], w2 = a[lane][p + 1];
+         double l1 = d11 * w1 + d21 * w2;
+         double l2 = d21 * w1 + d22 * w2;
+         __syncwarp();
+         if (lane > p + 1 && lane < bs) {
+            ld[lane][p] = w1; ld[lane][p + 1] = w2;
+            a[lane][p] = l1; a[lane][p + 1] = l2;
+         }
+         if (lane == p) {
+            a[p][p] = 1.0; a[p + 1][p] = 0.0; a[p + 1][p + 1] = 1.0;
+            ld[p + 1][p] = 0.0;
+            dinv[2 * p] = d11; dinv[2 * p + 1] = d21;
+            dinv[2 * p + 2] = CUDART_INF; dinv[2 * p + 3] = d22;
+         }
+         __syncwarp();
+         if (lane > p + 1 && lane < bs) {
+            for (int c = p + 2; c < bs; ++c) {
+               double upd = (c <= lane)
+                  ? ld[c][p] * l1 + ld[c][p + 1] * l2
+                  : w1 * a[c][p] + w2 * a[c][p + 1];
+               a[lane][c] -= upd;
+            }
+         }
+         __syncwarp();
+         p += 2;
+      }
+   }
+
+   /* publish L11 (unit lower), L11*D, D^-1 and the local permutation */
+   for (int c = 0; c < BS; ++c) {
+      double l = 0.0, y = 0.0;
+      if (lane < bs && c < bs) {
+         if (lane > c) { l = a[lane][c]; y = ld[lane][c]; }
+         else if (lane == c) l = 1.0;
+      }
+      ws->l11[lane + c * BS] = l;
+      ws->ld11[lane + c * BS] = y;
+   }
+   ws->dinv[2 * lane] = (lane < bs) ? dinv[2 * lane] : 0.0;
+   ws->dinv[2 * lane + 1] = (lane < bs) ? dinv[2 * lane + 1] : 0.0;
+   ws->lperm[lane] = lperm[lane];
+}
+
+void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool new_panel,
+      const FactorParams& prm, cudaStream_t s) {
+   if (count == 0) return;
+   if (posdef) k_diag<true><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
+   else k_diag<false><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Apply the block pivots to the rows below                                  */
+/* ------------------------------------------------------------------------ */
+
+/* One thread per row.  Indefinite: Y = A21(:,lperm) L11^-T, W = Y D^-1, the
+ * a-posteriori threshold test |w| <= 1/u (check_threshold,
+ * src/ssids/cpu/kernels/ldlt_app.cxx:303-321; apply_pivot :332-377).
+ * W overwrites the block column, Y goes to LD, the originals to BK. */
+template <bool POSDEF>
+__global__ void __launch_bounds__(RT)
+k_apply(Front* fronts, const RowTile* work, FactorParams prm) {
+   RowTile w = work[blockIdx.x];
+   Front* f = &fronts[w.front];
+   if (!f->step_valid) return;
+   const int done = f->done, bs = f->bs, m = f->m;
+   const int r0 = w.tile * RT;
+   const int rbeg = done + bs;
+   if (r0 + RT <= rbeg || r0 >= m) return;
+
+   __shared__ double l11[BS][BS + 1];   // l11[j][k]
+   __shared__ double c0[BS], c1[BS], c2[BS];
+   __shared__ int lperm[BS];
+   __shared__ int s_fail;
+   const BlockWS* ws = f->ws;
+   for (int i = threadIdx.x; i < BS * BS; i += RT) l11[i % BS][i / BS] = ws->l11[i];
+   if (threadIdx.x < BS) {
+      int j = threadIdx.x;
+      if (POSDEF) {
+         c0[j] = ws->dinv[j]; c1[j] = 0.0; c2[j] = 0.0; lperm[j] = j;
+      } else {
+         const double* d = ws->dinv;
+         double v0, v1 = 0.0, v2 = 0.0;
+         if (j < bs && isinf(d[2 * j])) { v0 = d[2 * j + 1]; v2 = d[2 * j - 1]; }          // second of a 2x2
+         else if (j + 1 < bs && isinf(d[2 * j + 2])) { v0 = d[2 * j]; v1 = d[2 * j + 1]; } // first of a 2x2
+         else v0 = (j < bs) ? d[2 * j] : 0.0;
+         c0[j] = v0; c1[j] = v1; c2[j] = v2;
+         lperm[j] = ws->lperm[j];
+      }
+   }
+   if (threadIdx.x == 0) s_fail = BS;
+   __syncthreads();
+
+   const int r = r0 + threadIdx.x;
+   const bool active = (r >= rbeg) && (r < m);
+   const size_t ldl = f->ldl;
+   double* Lr = f->L + r + (size_t)done * ldl;
+   double y[BS];
+   #pragma unroll
+   for (int j = 0; j < BS; ++j)
+      y[j] = (active && j < bs) ? Lr[(size_t)lperm[j] * ldl] : 0.0;
+
+   if (POSDEF) {
+      #pragma unroll
+      for (int j = 0; j < BS; ++j) {
+         double s = y[j];
+         #pragma unroll
+         for (int k = 0; k < j; ++k) s -= y[k] * l11[j][k];
+         y[j] = s * c0[j];
+      }
+      if (active) {
+         #pragma unroll
+         for (int j = 0; j < BS; ++j)
+            if (j < bs) Lr[(size_t)j * ldl] = y[j];
+      }
+      return;
+   }
+
+   double* BKr = f->BK + r;
+   double* LDr = f->LD + r + (size_t)done * ldl;
+   if (active) {
+      #pragma unroll
+      for (int j = 0; j < BS; ++j)
+         if (j < bs) BKr[(size_t)j * ldl] = y[j];
+   }
+   #pragma unroll
+   for (int j = 0; j < BS; ++j) {
+      double s = y[j];
+      #pragma unroll
+      for (int k = 0; k < j; ++k) s -= y[k] * l11[j][k];
+      y[j] = s;
+   }
+   int myfail = BS;
+   const double lim = 1.0 / prm.u;
+   if (active) {
+      #pragma unroll
+      for (int j = 0; j < BS; ++j) {
+         if (j < bs) {
+            double wv = c0[j] * y[j];
+            if (j + 1 < BS) wv += c1[j] * y[(j + 1) % BS];
+            if (j > 0) wv += c2[j] * y[(j + BS - 1) % BS];
+            Lr[(size_t)j * ldl] = wv;
+            LDr[(size_t)j * ldl] = y[j];
+            if (!(fabs(wv) <= lim) && myfail == BS) myfail = j;
+         }
+      }
+   }
+   #pragma unroll
+   for (int off = 16; off > 0; off >>= 1)
+      myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
+   if ((threadIdx.x & 31) == 0 && myfail < BS) atomicMin(&s_fail, myfail);
+   __syncthreads();
+   if (threadIdx.x == 0 && s_fail < BS) atomicMin(&f->first_fail, s_fail);
+}
+
+void launch_apply(Front* fronts, const RowTile* work, int nwork, bool posdef,
+      const FactorParams& prm, cudaStream_t s) {
+   if (nwork == 0) return;
+   if (posdef) k_apply<true><<<nwork, RT, 0, s>>>(fronts, work, prm);
+   else k_apply<false><<<nwork, RT, 0, s>>>(fronts, work, prm);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Commit an inner step (indefinite only)                                    */
+/* ------------------------------------------------------------------------ */
+
+__global__ void __launch_bounds__(RT)
+k_commit(Front* fronts, const RowTile* work) {
+   RowTile w = work[blockIdx.x];
+   Front* f = &fronts[w.front];
+   if (!f->step_valid) return;
+   const int done = f->done, bs = f->bs, m = f->m;
+   const int ne = calc_ne(f);
+   const size_t ldl = f->ldl;
+   const int r0 = w.tile * RT;
+   const BlockWS* ws = f->ws;
+   double* L = f->L;
+
+   __shared__ int lperm[BS];
+   __shared__ int s_ident;
+   __shared__ int s_perm[BS];
+   if (threadIdx.x == 0) s_ident = 1;
+   __syncthreads();
+   if (threadIdx.x < BS) {
+      int q = (threadIdx.x < bs) ? ws->lperm[threadIdx.x] : threadIdx.x;
+      lperm[threadIdx.x] = q;
+      if (q != threadIdx.x) s_ident = 0;
+   }
+   __syncthreads();
+
+   /* (1) rows of the block in the already-factored columns c < done: the
+    * block's local permutation is a row permutation of L */
+   if (r0 < done && !s_ident) {
+      int c = r0 + threadIdx.x;
+      if (c < done) {
+         double* col = L + (size_t)c * ldl + done;
+         double v[BS];
+         #pragma unroll
+         for (int i = 0; i < BS; ++i) v[i] = (i < bs) ? col[lperm[i]] : 0.0;
+         #pragma unroll
+         for (int i = 0; i < BS; ++i) if (i < bs) col[i] = v[i];
+      }
+   }
+
+   /* (2) the diagonal block itself, D and perm: one CTA per front */
+   if (w.tile == done / RT) {
+      double* LD = f->LD;
+      for (int e = threadIdx.x; e < BS * BS; e += RT) {
+         int i = e % BS, j = e / BS;
+         if (i < bs && j < bs && i >= j) {
+            double v = (j < ne) ? ws->l11[i + j * BS] : ws->a0[lperm[i] + lperm[j] * BS];
+            L[(size_t)(done + i) + (size_t)(done + j) * ldl] = v;
+            if (j < ne && i >= ne) LD[(size_t)(done + i) + (size_t)(done + j) * ldl] = ws->ld11[i + j * BS];
+         }
+      }
+      if (threadIdx.x < 2 * ne) f->D[2 * done + threadIdx.x] = ws->dinv[threadIdx.x];
+      if (threadIdx.x < bs) s_perm[threadIdx.x] = f->perm[done + lperm[threadIdx.x]];
+      __syncthreads();
+      if (threadIdx.x < bs) f->perm[done + threadIdx.x] = s_perm[threadIdx.x];
+   }
+
+   /* (3) rows below the block: restore the failed columns (permuted originals) */
+   if (ne < bs) {
+      int r = r0 + threadIdx.x;
+      if (r >= done + bs && r < m) {
+         const double* BKr = f->BK + r;
+         double* Lr = L + r + (size_t)done * ldl;
+         for (int j = ne; j < bs; ++j) Lr[(size_t)j * ldl] = BKr[(size_t)j * ldl];
+      }
+   }
+}
+
+void launch_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s) {
+   if (nwork == 0) return;
+   k_commit<<<nwork, RT, 0, s>>>(fronts, work);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Move failed columns out of the way (symmetric swaps, lower storage)       */
+/* ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ double* sym_addr(double* L, size_t ldl, int i, int x) {
+   return (i > x) ? L + i + (size_t)x * ldl : L + x + (size_t)i * ldl;
+}
+
+/* Swaps positions a0+t <-> b0+t, t < nswap (a0+nswap <= b0), of the symmetric
+ * front.  inner: failed columns of the current block go to the end of the
+ * panel; outer: failed columns of the panel go to the end of the candidates. */
+__global__ void __launch_bounds__(RT)
+k_swap(Front* fronts, const RowTile* work, int outer, int slice) {
+   RowTile w = work[blockIdx.x];
+   Front* f = &fronts[w.front];
+   int a0, b0, nswap;
+   if (!outer) {
+      if (!f->step_valid) return;
+      int ne = calc_ne(f);
+      int nfail = f->bs - ne;
+      if (nfail == 0) return;
+      a0 = f->done + ne;
+      int rem = f->pend - (f->done + f->bs);
+      nswap = min(nfail, rem);
+      b0 = f->pend - nswap;
+   } else {
+      if (!f->panel_open || f->finished) return;
+      int pend = f->pend;
+      if (f->step_valid) pend -= f->bs - calc_ne(f);
+      int nf = f->pend0 - pend;
+      if (nf == 0) return;
+      a0 = pend;
+      int rem = f->end - f->pend0;
+      nswap = min(nf, rem);
+      b0 = f->end - nswap;
+   }
+   /* disjoint transpositions commute: the pairs are applied BS at a time */
+   a0 += slice * BS; b0 += slice * BS; nswap = min(BS, nswap - slice * BS);
+   if (nswap <= 0) return;
+   const size_t ldl = f->ldl;
+   const int m = f->m;
+   double* L = f->L;
+   int x = w.tile * RT + threadIdx.x;
+   bool inS = (x >= a0 && x < a0 + nswap) || (x >= b0 && x < b0 + nswap);
+   if (x < m && !inS) {
+      for (int t = 0; t < nswap; ++t) {
+         double* pa = sym_addr(L, ldl, a0 + t, x);
+         double* pb = sym_addr(L, ldl, b0 + t, x);
+         double v = *pa; *pa = *pb; *pb = v;
+      }
+   }
+   if (w.tile == 0) {
+      /* the S x S block: entry (s_k1, s_k2) <- (partner(k1), partner(k2)) */
+      __shared__ double sbuf[2 * BS * 2 * BS];
+      int ns2 = 2 * nswap;
+      for (int e = threadIdx.x; e < ns2 * ns2; e += RT) {
+         int k1 = e % ns2, k2 = e / ns2;
+         if (k1 >= k2) {
+            int s1 = (k1 < nswap) ? a0 + k1 : b0 + k1 - nswap;
+            int s2 = (k2 < nswap) ? a0 + k2 : b0 + k2 - nswap;
+            sbuf[k1 + k2 * ns2] = L[(size_t)s1 + (size_t)s2 * ldl];
+         }
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < ns2 * ns2; e += RT) {
+         int k1 = e % ns2, k2 = e / ns2;
+         if (k1 >= k2) {
+            int s1 = (k1 < nswap) ? a0 + k1 : b0 + k1 - nswap;
+            int s2 = (k2 < nswap) ? a0 + k2 : b0 + k2 - nswap;
+            int q1 = (k1 < nswap) ? k1 + nswap : k1 - nswap;
+            int q2 = (k2 < nswap) ? k2 + nswap : k2 - nswap;
+            double v = (q1 >= q2) ? sbuf[q1 + q2 * ns2] : sbuf[q2 + q1 * ns2];
+            L[(size_t)s1 + (size_t)s2 * ldl] = v;
+         }
+      }
+      int* perm = f->perm;
+      for (int t = threadIdx.x; t < nswap; t += RT) {
+         int q = perm[a0 + t]; perm[a0 + t] = perm[b0 + t]; perm[b0 + t] = q;
+      }
+   }
+}
+
+void launch_swap(Front* fronts, const RowTile* work, int nwork, bool outer, cudaStream_t s) {
+   if (nwork == 0) return;
+   int nslice = outer ? PW / BS : 1;
+   for (int sl = 0; sl < nslice; ++sl)
+      k_swap<<<nwork, RT, 0, s>>>(fronts, work, outer ? 1 : 0, sl);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Finalise a level: close the state machine, collect statistics             */
+/* ------------------------------------------------------------------------ */
+
+template <bool POSDEF>
+__global__ void __launch_bounds__(128)
+k_finalize(Front* fronts, const int* __restrict__ flist) {
+   Front* f = &fronts[flist[blockIdx.x]];
+   if (threadIdx.x == 0) advance_state(f, true);
+   __syncthreads();
+   if (!f->finished || POSDEF) return;
+   __shared__ int s_neg, s_two, s_zero;
+   if (threadIdx.x == 0) { s_neg = 0; s_two = 0; s_zero = 0; }
+   __syncthreads();
+   const int nelim = f->nelim;
+   const double* d = f->D;
+   int neg = 0, two = 0, zero = 0;
+   for (int i = threadIdx.x; i < nelim; i += blockDim.x) {
+      double a11 = d[2 * i];
+      if (isinf(a11)) continue;                       // second column of a 2x2
+      double a21 = d[2 * i + 1];
+      if (i + 1 == nelim || !isinf(d[2 * i + 2])) {   // 1x1 (or zero)
+         if (a11 == 0.0) zero++;
+         if (a11 < 0.0) neg++;
+      } else {
+         double a22 = d[2 * i + 3];
+         two++;
+         double det = a11 * a22 - a21 * a21;
+         double trace = a11 + a22;
+         if (det < 0) neg++;
+         else if (trace < 0) neg += 2;
+      }
+   }
+   atomicAdd(&s_neg, neg); atomicAdd(&s_two, two); atomicAdd(&s_zero, zero);
+   __syncthreads();
+   if (threadIdx.x == 0) { f->num_neg = s_neg; f->num_two = s_two; f->num_zero = s_zero; }
+}
+
+void launch_finalize(Front* fronts, const int* flist, int count, bool posdef, cudaStream_t s) {
+   if (count == 0) return;
+   if (posdef) k_finalize<true><<<count, 128, 0, s>>>(fronts, flist);
+   else k_finalize<false><<<count, 128, 0, s>>>(fronts, flist);
+}
+
+} // namespace b200

@@ -1,0 +1,268 @@
+/* FP64 tensor-core (DMMA) symmetric update kernels of the B200 SSIDS engine.
+ *
+ * One kernel template serves the three dense contractions of a front
+ *   UPD_INNER    A(r,c) -= L(r,K) * LD(c,K)^T   K = columns of the current block
+ *                column, c restricted to the open outer panel
+ *   UPD_OUTER    same with K = all columns eliminated in the panel, c right of it
+ *   UPD_CONTRIB  C(r,c)  = -L(r,K) * LD(c,K)^T  K = all eliminated columns,
+ *                r,c >= n: the Schur complement / contribution block
+ * (lower triangle only, r >= c).  It replaces cu_multisyrk_lc_r4x4 /
+ * cu_multisyrk_r4x4 / cu_syrk_r4x4 (src/ssids/gpu/kernels/syrk.cu:180-600) and
+ * the cublasDgemm calls of src/ssids/gpu/dense_factor.f90:146,672,785,1032;
+ * the mathematics is form_contrib / update of the reference CPU engine
+ * (src/ssids/cpu/kernels/ldlt_app.cxx:1082-1186).
+ *
+ * sm_100a design: tcgen05 has no FP64 kind, so the FP64 tensor path is
+ * mma.sync.m8n8k4 (SASS DMMA).  Operand tiles are staged global -> shared by
+ * the TMA engine with 1-D bulk async copies (cp.async.bulk, SASS UBLKCP): the
+ * fronts are column-major, so a T x BK operand tile is BK contiguous column
+ * segments, each one bulk copy completing on an mbarrier.  Shared tiles are
+ * k-major with a row stride of T+4 doubles, which makes the 8x4 DMMA fragment
+ * loads bank-conflict free.  A 4-stage mbarrier pipeline keeps the copies
+ * ahead of the math.  The accumulator tile is computed transposed (D = B A^T)
+ * so that each thread owns two consecutive ROWS of a column and the epilogue
+ * uses 16-byte accesses on the column-major output.
+ *
+ * Tiles are aligned to absolute front coordinates (multiples of T from row 0),
+ * which keeps every bulk copy 16-byte aligned whatever the pivoting state is.
+ */
+#include "engine.h"
+#include "device_utils.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int BK = 16;       // K columns per pipeline stage
+constexpr int NSTAGE = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+   return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier */
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+   asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+struct Region {
+   const double* A; const double* B; double* C;
+   size_t lda, ldb, ldc;
+   int rows_alloc;        // rows that may be read per column of A/B (ldl, even)
+   int m;                 // row limit of the output
+   int c_lo, c_hi;        // output columns
+   int k0, k1;            // contraction range (columns of A and B)
+   int tj_base;           // absolute tile column of relative tile 0
+   bool accumulate;       // C -= ... (true) or C = -... (false)
+   bool valid;
+};
+
+__device__ __forceinline__ Region make_region(const Front* f, int mode, int T) {
+   Region g;
+   g.valid = false;
+   g.A = f->L; g.B = f->LD; g.lda = g.ldb = (size_t)f->ldl; g.rows_alloc = f->ldl; g.m = f->m;
+   if (mode == UPD_INNER) {
+      if (!f->step_valid) return g;
+      int ne = calc_ne(f);
+      if (ne == 0) return g;
+      g.k0 = f->done; g.k1 = f->done + ne;
+      g.c_lo = f->done + ne; g.c_hi = f->pend0;
+      g.C = f->L; g.ldc = g.lda; g.accumulate = true;
+   } else if (mode == UPD_OUTER) {
+      if (!f->panel_open || f->finished) return g;
+      int done = f->done;
+      if (f->step_valid) done += calc_ne(f);
+      g.k0 = f->p0; g.k1 = done;
+      if (g.k1 <= g.k0) return g;
+      g.c_lo = f->pend0; g.c_hi = f->n;
+      g.C = f->L; g.ldc = g.lda; g.accumulate = true;
+   } else {
+      if (f->m == f->n || !f->C) return g;
+      g.k0 = 0; g.k1 = f->nelim;
+      g.c_lo = f->n; g.c_hi = f->m;
+      g.ldc = (size_t)f->ldc;
+      g.C = f->C - (ptrdiff_t)f->n - (ptrdiff_t)f->n * (ptrdiff_t)g.ldc;   // absolute front coordinates
+      g.accumulate = false;
+   }
+   if (g.c_lo >= g.c_hi) return g;
+   g.tj_base = g.c_lo / T;
+   g.valid = true;
+   return g;
+}
+
+/* T x T output tile per CTA, NWR x NWC warps. */
+template <int T, int NWR, int NWC>
+__global__ void __launch_bounds__(NWR * NWC * 32, 1)
+k_update(Front* fronts, const MatTile* work, int mode) {
+   constexpr int LDS = T + 4;
+   constexpr int WTR = T / NWR, WTC = T / NWC;
+   constexpr int NR = WTR / 8, NC = WTC / 8;
+   constexpr int NTHREADS = NWR * NWC * 32;
+   constexpr int STAGE_DOUBLES = 2 * BK * LDS;
+
+   MatTile w = work[blockIdx.x];
+   const Front* f = &fronts[w.front];
+   const Region g = make_region(f, mode, T);
+   if (!g.valid) return;
+   const int tj = g.tj_base + w.tj;
+   const int ti = tj + w.ti;
+   const int r0 = ti * T, c0 = tj * T;
+   if (c0 >= g.c_hi || r0 >= g.m) return;
+
+   extern __shared__ __align__(128) unsigned char smem_raw[];
+   double* tiles = reinterpret_cast<double*>(smem_raw);
+   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double));
+
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int wr = warp % NWR, wc = warp / NWR;
+   const int rbase = wr * WTR, cbase = wc * WTC;
+   /* a warp whose sub-tile lies strictly above the diagonal has nothing to do */
+   const bool warp_active = (r0 + rbase + WTR > c0 + cbase) && (r0 + rbase < g.m)
+                            && (c0 + cbase < g.c_hi) && (c0 + cbase + WTC > g.c_lo);
+
+   if (tid == 0) {
+      for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+
+   const int klen = g.k1 - g.k0;
+   const int nchunk = (klen + BK - 1) / BK;
+   const int rowsA = min(T, g.rows_alloc - r0);   // even
+   const int rowsB = min(T, g.rows_alloc - c0);
+   const double* Ag = g.A + r0 + (size_t)g.k0 * g.lda;
+   const double* Bg = g.B + c0 + (size_t)g.k0 * g.ldb;
+
+   auto issue = [&](int chunk) {     // executed by warp 0
+      int s = chunk % NSTAGE;
+      int kc = min(BK, klen - chunk * BK);
+      double* st = tiles + (size_t)s * STAGE_DOUBLES;
+      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kc * (rowsA + rowsB) * sizeof(double)));
+      __syncwarp();
+      for (int idx = lane; idx < 2 * kc; idx += 32) {
+         int op = idx >= kc;
+         int col = idx - op * kc;
+         size_t kabs = (size_t)chunk * BK + col;
+         if (op) bulk_g2s(st + BK * LDS + col * LDS, Bg + kabs * g.ldb, rowsB * sizeof(double), &full[s]);
+         else    bulk_g2s(st + col * LDS, Ag + kabs * g.lda, rowsA * sizeof(double), &full[s]);
+      }
+      int kc4 = (kc + 3) & ~3;
+      if (kc4 != kc) {                 // zero the K tail of both operands
+         for (int col = kc; col < kc4; ++col)
+            for (int i = lane; i < T; i += 32) { st[col * LDS + i] = 0.0; st[BK * LDS + col * LDS + i] = 0.0; }
+      }
+   };
+
+   if (warp == 0) {
+      for (int c = 0; c < NSTAGE - 1 && c < nchunk; ++c) issue(c);
+   }
+   __syncthreads();
+
+   double acc[NC][NR][2];
+   #pragma unroll
+   for (int j = 0; j < NC; ++j)
+      #pragma unroll
+      for (int i = 0; i < NR; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+
+   for (int chunk = 0; chunk < nchunk; ++chunk) {
+      if (warp == 0 && chunk + NSTAGE - 1 < nchunk) issue(chunk + NSTAGE - 1);
+      const int s = chunk % NSTAGE;
+      mbar_wait(&full[s], (uint32_t)((chunk / NSTAGE) & 1));
+      if (warp_active) {
+         const int kc4 = (min(BK, klen - chunk * BK) + 3) & ~3;
+         const double* As = tiles + (size_t)s * STAGE_DOUBLES + (lane & 3) * LDS + rbase + (lane >> 2);
+         const double* Bs = As + BK * LDS - rbase + cbase;
+         #pragma unroll
+         for (int kk = 0; kk < BK; kk += 4) {
+            if (kk < kc4) {
+               double af[NR], bf[NC];
+               #pragma unroll
+               for (int i = 0; i < NR; ++i) af[i] = As[kk * LDS + i * 8];
+               #pragma unroll
+               for (int j = 0; j < NC; ++j) bf[j] = Bs[kk * LDS + j * 8];
+               #pragma unroll
+               for (int j = 0; j < NC; ++j)
+                  #pragma unroll
+                  for (int i = 0; i < NR; ++i)
+                     dmma(acc[j][i][0], acc[j][i][1], bf[j], af[i]);
+            }
+         }
+      }
+      __syncthreads();   // everyone is done with stage s before it is refilled
+   }
+
+   if (!warp_active) return;
+   /* epilogue: thread holds rows r, r+1 of column c */
+   #pragma unroll
+   for (int j = 0; j < NC; ++j) {
+      const int c = c0 + cbase + j * 8 + (lane >> 2);
+      if (c < g.c_lo || c >= g.c_hi) continue;
+      double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
+      #pragma unroll
+      for (int i = 0; i < NR; ++i) {
+         const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
+         const bool v0 = (r >= c) && (r < g.m);
+         const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
+         double* p = Cc + r;
+         if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            double2 o;
+            if (g.accumulate) { o = *reinterpret_cast<double2*>(p); o.x -= acc[j][i][0]; o.y -= acc[j][i][1]; }
+            else { o.x = -acc[j][i][0]; o.y = -acc[j][i][1]; }
+            *reinterpret_cast<double2*>(p) = o;
+         } else {
+            if (v0) p[0] = g.accumulate ? p[0] - acc[j][i][0] : -acc[j][i][0];
+            if (v1) p[1] = g.accumulate ? p[1] - acc[j][i][1] : -acc[j][i][1];
+         }
+      }
+   }
+}
+
+template <int T>
+constexpr size_t update_smem_bytes() {
+   return (size_t)NSTAGE * 2 * BK * (T + 4) * sizeof(double) + NSTAGE * sizeof(uint64_t);
+}
+
+} // namespace
+
+int update_tile_size(bool big_tiles) { return big_tiles ? 128 : 64; }
+
+void configure_update_kernels() {
+   cudaFuncSetAttribute(k_update<128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)update_smem_bytes<128>());
+   cudaFuncSetAttribute(k_update<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)update_smem_bytes<64>());
+}
+
+void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
+      bool big_tiles, cudaStream_t s) {
+   if (nwork == 0) return;
+   if (big_tiles)
+      k_update<128, 2, 4><<<nwork, 256, update_smem_bytes<128>(), s>>>(fronts, work, (int)mode);
+   else
+      k_update<64, 2, 2><<<nwork, 128, update_smem_bytes<64>(), s>>>(fronts, work, (int)mode);
+}
+
+} // namespace b200

@@ -1,0 +1,326 @@
+/* Triangular solve kernels of the B200 SSIDS engine (sm_100a), batched over
+ * the fronts of one tree level and over right-hand sides.
+ *
+ * They replace the per-RHS host loop and the kernels of the reference GPU path
+ *   src/ssids/gpu/solve.f90:177-291 (fwd_solve_gpu), :17-56 (bwd), :116-155 (d_solve)
+ *   src/ssids/gpu/kernels/solve.cu:593-735, src/ssids/gpu/kernels/dtrsv.h:462-813
+ * and compute what the reference CPU engine computes node by node
+ *   src/ssids/cpu/NumericSubtree.hxx:286-418 (gather, trsv/gemv or trsm/gemm, scatter)
+ *   src/ssids/cpu/kernels/ldlt_app.cxx:2538-2589, cholesky.cxx:190-213.
+ *
+ * A front of m rows with nelim eliminated columns is processed in column
+ * blocks of SB = 32.  Row i of the front is entry idx(i) of x: perm[i] for
+ * i < n (eliminated and delayed columns), rows[n0 + i - n] below.
+ *
+ * Forward, step s (one launch per step, all fronts of the level):
+ *   every CTA (front, 128-row tile) solves the 32x32 diagonal block of the
+ *   step redundantly in shared memory, then subtracts L(tile, block) * y from
+ *   its rows of x.  Rows >= nelim are shared with sibling fronts -> atomics.
+ *   The final y is parked in `ywork` and flushed to x when the part is done
+ *   (nobody reads an eliminated variable again during the forward sweep).
+ * Backward, step s (two launches): partial L(tile, block)^T x(tile) per tile
+ *   into a scratch, then one warp per front sums the partials in a fixed
+ *   order and solves the transposed diagonal block.
+ */
+#include "engine.h"
+#include <math_constants.h>
+
+namespace b200 {
+
+namespace {
+
+constexpr int SB = 32;    // solve block
+
+__device__ __forceinline__ int row_index(const SolveFront& f, int i) {
+   return (i < f.n ? f.perm[i] : f.rows[f.n0 + i - f.n]) - 1;
+}
+
+/* ---- forward ---------------------------------------------------------- */
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(RT)
+k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
+      double* __restrict__ x, int ldx, double* __restrict__ ywork) {
+   RowTile w = work[blockIdx.x];
+   const SolveFront f = fronts[w.front];
+   const int j0 = step * SB;
+   if (j0 >= f.nelim) return;
+   const int wd = min(SB, f.nelim - j0);
+   const int r0 = w.tile * RT;
+   if (r0 + RT <= j0 || r0 >= f.m) return;
+
+   __shared__ double lkk[SB][SB + 1];
+   __shared__ double xs[SB][NR];
+   __shared__ int gidx[SB];
+   const size_t ldl = f.ldl;
+   const double* Lb = f.L + (size_t)j0 * ldl;     // block column
+   for (int e = threadIdx.x; e < SB * SB; e += RT) {
+      int i = e % SB, j = e / SB;
+      lkk[i][j] = (i < wd && j < wd && i >= j) ? Lb[(size_t)(j0 + i) + j * ldl] : 0.0;
+   }
+   if (threadIdx.x < SB) {
+      int g = (threadIdx.x < wd) ? f.perm[j0 + threadIdx.x] - 1 : -1;
+      gidx[threadIdx.x] = g;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) xs[threadIdx.x][k] = (g >= 0) ? x[g + (size_t)k * ldx] : 0.0;
+   }
+   __syncthreads();
+   if (threadIdx.x < SB) {      // warp 0: forward substitution
+      const int lane = threadIdx.x;
+      for (int j = 0; j < wd; ++j) {
+         if (POSDEF) {
+            if (lane == j) {
+               #pragma unroll
+               for (int k = 0; k < NR; ++k) xs[j][k] /= lkk[j][j];
+            }
+            __syncwarp();
+         }
+         if (lane > j && lane < wd) {
+            double l = lkk[lane][j];
+            #pragma unroll
+            for (int k = 0; k < NR; ++k) xs[lane][k] -= l * xs[j][k];
+         }
+         __syncwarp();
+      }
+   }
+   __syncthreads();
+   /* the CTA owning the block's first row publishes y */
+   if (w.tile == j0 / RT && threadIdx.x < wd) {
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) ywork[gidx[threadIdx.x] + (size_t)k * ldx] = xs[threadIdx.x][k];
+   }
+   const int r = r0 + threadIdx.x;
+   if (r >= j0 + wd && r < f.m) {
+      double acc[NR];
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+      const double* Lr = Lb + r;
+      for (int j = 0; j < wd; ++j) {
+         double l = Lr[j * ldl];
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) acc[k] += l * xs[j][k];
+      }
+      const int g = row_index(f, r);
+      if (r < f.nelim) {
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) x[g + (size_t)k * ldx] -= acc[k];
+      } else {
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) atomicAdd(&x[g + (size_t)k * ldx], -acc[k]);
+      }
+   }
+}
+
+/* x(eliminated variables) <- ywork */
+__global__ void __launch_bounds__(128)
+k_fwd_flush(const SolveFront* fronts, int first, int nrhs, double* __restrict__ x, int ldx,
+      const double* __restrict__ ywork) {
+   const SolveFront f = fronts[first + blockIdx.x];
+   for (int j = threadIdx.x; j < f.nelim; j += blockDim.x) {
+      int g = f.perm[j] - 1;
+      for (int k = 0; k < nrhs; ++k) x[g + (size_t)k * ldx] = ywork[g + (size_t)k * ldx];
+   }
+}
+
+/* ---- diagonal --------------------------------------------------------- */
+/* x <- D^-1 x on the eliminated variables; D^-1 is stored (2 per column,
+ * second column of a 2x2 marked by +Inf), src/ssids/cpu/kernels/ldlt_app.cxx
+ * ldlt_app_solve_diag :2553-2573. */
+__global__ void __launch_bounds__(128)
+k_diag_solve(const SolveFront* fronts, int first, int nrhs, double* __restrict__ x, int ldx) {
+   const SolveFront f = fronts[first + blockIdx.x];
+   const double* d = f.D;
+   for (int j = threadIdx.x; j < f.nelim; j += blockDim.x) {
+      double d11 = d[2 * j];
+      if (isinf(d11)) continue;                 // handled by the first column of the pair
+      int g1 = f.perm[j] - 1;
+      if (j + 1 < f.nelim && isinf(d[2 * j + 2])) {
+         double d21 = d[2 * j + 1], d22 = d[2 * j + 3];
+         int g2 = f.perm[j + 1] - 1;
+         for (int k = 0; k < nrhs; ++k) {
+            double x1 = x[g1 + (size_t)k * ldx], x2 = x[g2 + (size_t)k * ldx];
+            x[g1 + (size_t)k * ldx] = d11 * x1 + d21 * x2;
+            x[g2 + (size_t)k * ldx] = d21 * x1 + d22 * x2;
+         }
+      } else {
+         for (int k = 0; k < nrhs; ++k) x[g1 + (size_t)k * ldx] *= d11;
+      }
+   }
+}
+
+/* ---- backward --------------------------------------------------------- */
+/* block index handled by front f at backward step s (last block first) */
+__device__ __forceinline__ int bwd_block(const SolveFront& f, int step) {
+   int nblk = (f.nelim + SB - 1) / SB;
+   return nblk - 1 - step;
+}
+
+/* partial(t, j, k) = sum over rows r of tile t below the block of L(r, j0+j) * x(r, k) */
+template <int NR>
+__global__ void __launch_bounds__(RT)
+k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
+      const double* __restrict__ x, int ldx, double* __restrict__ pbuf) {
+   RowTile w = work[blockIdx.x];
+   const SolveFront f = fronts[w.front];
+   const int b = bwd_block(f, step);
+   if (b < 0) return;
+   const int j0 = b * SB;
+   const int wd = min(SB, f.nelim - j0);
+   const int r0 = w.tile * RT;
+   if (r0 + RT <= j0 + wd || r0 >= f.m) return;   // no row of this tile below the block
+
+   __shared__ double tile[RT / 32][32][SB + 1];
+   __shared__ double xr[RT][NR];
+   /* red aliases tile once the tile has been consumed (NR <= 8 < SB + 1) */
+   double (*red)[SB][SB + 1] = tile;
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int r = r0 + threadIdx.x;
+   const bool active = (r >= j0 + wd) && (r < f.m);
+   const size_t ldl = f.ldl;
+   {
+      int g = active ? row_index(f, r) : 0;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) xr[threadIdx.x][k] = active ? x[g + (size_t)k * ldx] : 0.0;
+      const double* Lr = f.L + r + (size_t)j0 * ldl;
+      for (int j = 0; j < SB; ++j) tile[warp][lane][j] = (active && j < wd) ? Lr[j * ldl] : 0.0;
+   }
+   __syncthreads();
+   {
+      double acc[NR];
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+      for (int i = 0; i < 32; ++i) {
+         double l = tile[warp][i][lane];
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) acc[k] += l * xr[warp * 32 + i][k];
+      }
+      __syncthreads();
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) red[warp][lane][k] = acc[k];
+   }
+   __syncthreads();
+   if (threadIdx.x < SB) {
+      double* out = pbuf + (size_t)blockIdx.x * SB * NR;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) {
+         double s = 0.0;
+         for (int q = 0; q < RT / 32; ++q) s += red[q][threadIdx.x][k];
+         out[threadIdx.x * NR + k] = s;
+      }
+   }
+}
+
+/* one warp per front: y = x_blk - sum_t partial(t), solve L_kk^T z = y */
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(32)
+k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, int step,
+      double* __restrict__ x, int ldx, const double* __restrict__ pbuf) {
+   const int fi = first + blockIdx.x;
+   const SolveFront f = fronts[fi];
+   const int b = bwd_block(f, step);
+   if (b < 0) return;
+   const int j0 = b * SB;
+   const int wd = min(SB, f.nelim - j0);
+   const int lane = threadIdx.x;
+   __shared__ double lkk[SB][SB + 1];
+   __shared__ double ys[SB][NR];
+   const size_t ldl = f.ldl;
+   for (int j = 0; j < SB; ++j)
+      lkk[lane][j] = (lane < wd && j < wd && lane >= j) ? f.L[(size_t)(j0 + lane) + (size_t)(j0 + j) * ldl] : 0.0;
+   const int g = (lane < wd) ? f.perm[j0 + lane] - 1 : -1;
+   double y[NR];
+   #pragma unroll
+   for (int k = 0; k < NR; ++k) y[k] = (g >= 0) ? x[g + (size_t)k * ldx] : 0.0;
+   /* tiles holding rows below the block, in increasing order */
+   const int ntile = (f.m + RT - 1) / RT;
+   const int t0 = (j0 + wd) / RT;
+   for (int t = t0; t < ntile; ++t) {
+      const double* p = pbuf + (size_t)(wbeg[fi] + t) * SB * NR;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) y[k] -= p[lane * NR + k];
+   }
+   #pragma unroll
+   for (int k = 0; k < NR; ++k) ys[lane][k] = y[k];
+   __syncwarp();
+   for (int j = wd - 1; j >= 0; --j) {
+      if (POSDEF) {
+         if (lane == j) {
+            #pragma unroll
+            for (int k = 0; k < NR; ++k) ys[j][k] /= lkk[j][j];
+         }
+         __syncwarp();
+      }
+      if (lane < j) {
+         double l = lkk[j][lane];
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) ys[lane][k] -= l * ys[j][k];
+      }
+      __syncwarp();
+   }
+   if (g >= 0) {
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) x[g + (size_t)k * ldx] = ys[lane][k];
+   }
+}
+
+template <int NR>
+void fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps, bool posdef,
+      double* x, int ldx, double* ywork, cudaStream_t s) {
+   for (int st = 0; st < nsteps; ++st) {
+      if (posdef) k_fwd_step<NR, true><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork);
+      else k_fwd_step<NR, false><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork);
+   }
+}
+
+template <int NR>
+void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      const int* wbeg, int nsteps, bool posdef, double* x, int ldx, double* pbuf, cudaStream_t s) {
+   for (int st = 0; st < nsteps; ++st) {
+      k_bwd_reduce<NR><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, pbuf);
+      if (posdef) k_bwd_diag<NR, true><<<count, 32, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf);
+      else k_bwd_diag<NR, false><<<count, 32, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf);
+   }
+}
+
+} // namespace
+
+int solve_block() { return SB; }
+
+/* Largest number of right-hand sides one kernel pass handles. */
+int solve_rhs_chunk(int nrhs) { return nrhs >= 8 ? 8 : nrhs >= 4 ? 4 : nrhs >= 2 ? 2 : 1; }
+
+void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps,
+      bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s) {
+   if (nwork == 0 || nsteps == 0) return;
+   switch (nr) {
+   case 8: fwd_level<8>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
+   case 4: fwd_level<4>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
+   case 2: fwd_level<2>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
+   default: fwd_level<1>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
+   }
+}
+
+void launch_fwd_flush(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
+      const double* ywork, cudaStream_t s) {
+   if (count == 0) return;
+   k_fwd_flush<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx, ywork);
+}
+
+void launch_diag_solve(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
+      cudaStream_t s) {
+   if (count == 0) return;
+   k_diag_solve<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx);
+}
+
+void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      const int* wbeg, int nsteps, bool posdef, int nr, double* x, int ldx, double* pbuf,
+      cudaStream_t s) {
+   if (nwork == 0 || nsteps == 0) return;
+   switch (nr) {
+   case 8: bwd_level<8>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
+   case 4: bwd_level<4>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
+   case 2: bwd_level<2>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
+   default: bwd_level<1>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
+   }
+}
+
+} // namespace b200

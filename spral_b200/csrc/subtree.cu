@@ -1,0 +1,1036 @@
+/* Host side of the B200 SSIDS numeric engine: symbolic subtree, level-set
+ * factorisation scheduler, solves, and the C ABI of include/spral_ssids_b200.h.
+ *
+ * Replaces (reference tree, ralna/spral):
+ *   src/ssids/gpu/subtree.f90   construct_gpu_symbolic_subtree :76-160, factor :304-460,
+ *                               build_child_pointers :162-196, build_rlist_direct :204-234,
+ *                               solve_* :555-700, enquire/alter :702-981, get_contrib :522-538
+ *   src/ssids/gpu/factor.f90    parfactor :42-153, subtree_factor_gpu :240-656,
+ *                               assign_nodes_to_levels :824-879, transfer_contrib :155-221
+ *   src/ssids/gpu/solve.f90     setup_gpu_solve :840-1007, fwd/bwd/d_solve_gpu
+ *   driver/cuda_helper_gpu.f90  cuda_init :9-43
+ * Results are defined by the reference CPU engine (src/ssids/cpu/NumericSubtree.hxx).
+ *
+ * Differences by design: the whole part is factorised level by level with ONE
+ * host synchronisation per level (to learn how many columns each front
+ * delayed, which sizes the parents); all pivoting decisions are taken on the
+ * device; contribution blocks never leave HBM; every scratch buffer comes from
+ * a grow-only pool that survives across factorisations.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <stdexcept>
+#include <vector>
+#include "engine.h"
+
+namespace b200 {
+
+struct CudaError { cudaError_t code; };
+#define CUDA_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaError{e_}; } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+/* Grow-only device buffer. */
+struct Buf {
+   void* p = nullptr;
+   size_t cap = 0;
+   /* Makes room for `bytes`; when the buffer has to be re-allocated the stream
+    * is drained first because kernels in flight may still use the old one. */
+   void ensure(size_t bytes, cudaStream_t s) {
+      if (bytes <= cap) return;
+      if (p) { CUDA_TRY(cudaStreamSynchronize(s)); CUDA_TRY(cudaFree(p)); p = nullptr; cap = 0; }
+      size_t want = align_up(bytes + bytes / 8, 256);
+      CUDA_TRY(cudaMalloc(&p, want));
+      cap = want;
+   }
+   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+/* Bump allocator over a Buf. */
+struct Bump {
+   char* base = nullptr; size_t off = 0, cap = 0;
+   void reset(Buf& b) { base = (char*)b.p; off = 0; cap = b.cap; }
+   template <class T> T* take(size_t count) {
+      size_t bytes = align_up(count * sizeof(T), 256);
+      T* r = (T*)(base + off);
+      off += bytes;
+      if (off > cap) throw std::runtime_error("bump overflow");
+      return r;
+   }
+};
+
+/* ------------------------------------------------------------------------ */
+/* Symbolic subtree                                                          */
+/* ------------------------------------------------------------------------ */
+
+struct Symbolic {
+   int device = 0, n = 0, sa = 0, en = 0, nloc = 0;
+   spral_ssids_b200_options options;
+   std::vector<int> n0, m0, parent;   // local parent (or -1)
+   std::vector<char> exported;        // contribution block leaves the part
+   std::vector<int64_t> rptr;         // nloc+1, 0-based offsets into rlist
+   std::vector<int> rlist;            // global 1-based pivot-order indices
+   std::vector<int> rlist_direct;     // 1-based position in the parent's row list
+   std::vector<int> npassl;
+   std::vector<int64_t> nptr;         // nloc+1, 0-based entry offsets into nlist
+   std::vector<int> child_ptr, child_list;     // 0-based local, children in increasing order
+   int nlevels = 0;
+   std::vector<int> level_ptr, level_list;     // reference format: 1-based
+   std::vector<int> front_of_node, node_of_front;
+   std::vector<int> contrib_dest;     // local node per incoming contribution
+   std::vector<std::vector<int>> contribs_of_node;   // incoming contribution indices per node
+   /* device copies */
+   int* d_rlist = nullptr; int* d_rlist_direct = nullptr;
+   int64_t* d_nlist = nullptr; int64_t* d_nptr = nullptr; int* d_node_of_front = nullptr;
+   /* sizes */
+   size_t cbuf_bytes[2] = {0, 0};     // contribution ping-pong
+   size_t ld_estimate = 0;            // doubles of LD scratch for the largest level (no delays)
+   int64_t aval_len = 0;              // entries of aval this part reads: max source index of its nlist slice
+   /* scratch pool shared by the factorisations / solves of this subtree */
+   std::mutex mtx;
+   Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf;
+
+   ~Symbolic() {
+      cudaSetDevice(device);
+      cudaFree(d_rlist); cudaFree(d_rlist_direct); cudaFree(d_nlist); cudaFree(d_nptr);
+      cudaFree(d_node_of_front);
+      b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
+      b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
+      b_y.release(); b_pbuf.release(); b_retry.release();
+   }
+};
+
+static Symbolic* build_symbolic(int device, int n, int sa, int en, const int* sptr,
+      const int* sparent, const int64_t* rptr, const int* rlist, const int64_t* nptr,
+      const int64_t* nlist, int ncontrib, const int* contrib_idx,
+      const spral_ssids_b200_options* options) {
+   auto* S = new Symbolic;
+   S->device = device; S->n = n; S->sa = sa; S->en = en;
+   const int nloc = S->nloc = en - sa;
+   S->options = *options;
+   S->n0.resize(nloc); S->m0.resize(nloc); S->parent.resize(nloc); S->exported.assign(nloc, 0);
+   S->rptr.resize(nloc + 1); S->nptr.resize(nloc + 1);
+   const int64_t rbase = nloc ? rptr[sa - 1] : 1, nbase = nloc ? nptr[sa - 1] : 1;
+   for (int i = 0; i < nloc; ++i) {
+      int node = sa + i;                      // global 1-based
+      S->n0[i] = sptr[node] - sptr[node - 1];
+      S->m0[i] = (int)(rptr[node] - rptr[node - 1]);
+      int p = sparent[node - 1];
+      S->parent[i] = (p < en) ? p - sa : -1;
+      S->exported[i] = (p >= en && S->m0[i] > S->n0[i]);
+      S->rptr[i] = rptr[node - 1] - rbase;
+      S->nptr[i] = nptr[node - 1] - nbase;
+   }
+   S->rptr[nloc] = nloc ? rptr[en - 1] - rbase : 0;
+   S->nptr[nloc] = nloc ? nptr[en - 1] - nbase : 0;
+   S->rlist.assign(rlist + (rbase - 1), rlist + (rbase - 1) + S->rptr[nloc]);
+
+   /* children, in increasing node order (build_child_pointers, gpu/subtree.f90:162-196) */
+   S->child_ptr.assign(nloc + 2, 0);
+   for (int i = 0; i < nloc; ++i) if (S->parent[i] >= 0) S->child_ptr[S->parent[i] + 1]++;
+   for (int i = 0; i < nloc; ++i) S->child_ptr[i + 1] += S->child_ptr[i];
+   S->child_list.resize(nloc);
+   {
+      std::vector<int> pos(S->child_ptr.begin(), S->child_ptr.end() - 1);
+      for (int i = 0; i < nloc; ++i) if (S->parent[i] >= 0) S->child_list[pos[S->parent[i]]++] = i;
+   }
+
+   /* rlist_direct (build_rlist_direct, gpu/subtree.f90:204-234) */
+   S->rlist_direct.assign(S->rlist.size(), 0);
+   S->npassl.assign(nloc, 0);
+   {
+      std::vector<int> map(n + 1, 0);
+      for (int i = 0; i < nloc; ++i) {
+         int p = S->parent[i];
+         if (p < 0) continue;
+         for (int64_t ii = S->rptr[p]; ii < S->rptr[p + 1]; ++ii) map[S->rlist[ii]] = (int)(ii - S->rptr[p] + 1);
+         for (int64_t ii = S->rptr[i]; ii < S->rptr[i + 1]; ++ii) S->rlist_direct[ii] = map[S->rlist[ii]];
+         int cnt = 0;
+         for (int64_t ii = S->rptr[i] + S->n0[i]; ii < S->rptr[i + 1]; ++ii)
+            if (S->rlist_direct[ii] <= S->n0[p]) cnt++;
+         S->npassl[i] = cnt;
+      }
+   }
+
+   /* levels (assign_nodes_to_levels, gpu/factor.f90:824-879): level 1 = deepest */
+   {
+      std::vector<int> level(nloc + 1, 0), lvlcount(nloc + 2, 0);
+      int num_levels = 1;
+      for (int i = nloc - 1; i >= 0; --i) {
+         int j = S->parent[i] >= 0 ? S->parent[i] : nloc;
+         int lvl = level[j] + 1;
+         level[i] = lvl;
+         lvlcount[lvl]++;
+         num_levels = std::max(num_levels, lvl);
+      }
+      S->nlevels = num_levels;
+      S->level_ptr.assign(num_levels + 2, 1);
+      for (int lvl = 2; lvl <= num_levels; ++lvl)
+         S->level_ptr[lvl] = S->level_ptr[lvl - 1] + lvlcount[num_levels - (lvl - 1) + 1];
+      /* level_ptr[k] (0-based k) holds reference lvlptr(k+1) once filled below */
+      std::vector<int> ins(num_levels + 2, 1);
+      ins[1] = 1;
+      for (int lvl = 2; lvl <= num_levels; ++lvl) ins[lvl] = ins[lvl - 1] + lvlcount[num_levels - (lvl - 1) + 1];
+      S->level_list.assign(nloc, 0);
+      std::vector<int> start(ins);
+      for (int i = 0; i < nloc; ++i) {
+         int lvl = num_levels - level[i] + 1;
+         S->level_list[ins[lvl] - 1] = i + 1;
+         ins[lvl]++;
+      }
+      /* reference lvlptr(1..num_levels+1) */
+      for (int lvl = 1; lvl <= num_levels; ++lvl) S->level_ptr[lvl - 1] = start[lvl];
+      S->level_ptr[num_levels] = nloc + 1;
+      S->level_ptr.resize(num_levels + 1);
+   }
+   S->front_of_node.resize(nloc); S->node_of_front.resize(nloc);
+   for (int fi = 0; fi < nloc; ++fi) {
+      int node = S->level_list[fi] - 1;
+      S->node_of_front[fi] = node;
+      S->front_of_node[node] = fi;
+   }
+
+   /* incoming contributions from other parts */
+   S->contribs_of_node.assign(nloc, {});
+   S->contrib_dest.resize(ncontrib);
+   for (int k = 0; k < ncontrib; ++k) {
+      int node = contrib_idx[k] - sa;
+      S->contrib_dest[k] = node;
+      if (node >= 0 && node < nloc) S->contribs_of_node[node].push_back(k);
+   }
+
+   /* static scratch sizes */
+   for (int lev = 0; lev < S->nlevels; ++lev) {
+      size_t cb = 0, ld = 0;
+      for (int fi = S->level_ptr[lev] - 1; fi < S->level_ptr[lev + 1] - 1; ++fi) {
+         int node = S->node_of_front[fi];
+         size_t cm = S->m0[node] - S->n0[node];
+         if (!S->exported[node]) cb += align_up(align_up(cm, 2) * cm * sizeof(double), 256);
+         ld += align_up((size_t)S->m0[node], 2) * S->n0[node] + 32;
+      }
+      S->cbuf_bytes[lev & 1] = std::max(S->cbuf_bytes[lev & 1], cb);
+      S->ld_estimate = std::max(S->ld_estimate, ld);
+   }
+
+   /* device copies */
+   CUDA_TRY(cudaSetDevice(device));
+   auto up = [](auto*& d, const auto& v) {
+      using T = typename std::remove_reference<decltype(v)>::type::value_type;
+      CUDA_TRY(cudaMalloc((void**)&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+      if (!v.empty()) CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+   };
+   up(S->d_rlist, S->rlist);
+   up(S->d_rlist_direct, S->rlist_direct);
+   up(S->d_nptr, S->nptr);
+   up(S->d_node_of_front, S->node_of_front);
+   size_t nent = (size_t)S->nptr[nloc];
+   CUDA_TRY(cudaMalloc((void**)&S->d_nlist, std::max<size_t>(2 * nent, 1) * sizeof(int64_t)));
+   if (nent) CUDA_TRY(cudaMemcpy(S->d_nlist, nlist + 2 * (nbase - 1), 2 * nent * sizeof(int64_t), cudaMemcpyHostToDevice));
+   for (size_t i = 0; i < nent; ++i) S->aval_len = std::max(S->aval_len, nlist[2 * (nbase - 1) + 2 * i]);
+   return S;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Numeric subtree                                                           */
+/* ------------------------------------------------------------------------ */
+
+struct Numeric {
+   Symbolic* S = nullptr;
+   bool posdef = false;
+   cudaStream_t stream = nullptr;
+   std::vector<void*> chunks;          // factor storage (L, D, perm), stream-ordered allocations
+   char* chunk_base = nullptr; size_t chunk_off = 0, chunk_cap = 0;
+   Front* d_fronts = nullptr;          // level order
+   std::vector<Front> h_fronts;
+   SolveFront* d_sfronts = nullptr;
+   RowTile* d_swork = nullptr; int* d_wbeg = nullptr;
+   std::vector<int> swork_ptr, lvl_steps;
+   size_t max_level_work = 0;
+   /* exported contribution */
+   int export_front = -1;
+   double* d_export = nullptr;
+   std::vector<double> h_cval, h_dval; std::vector<int> h_dperm;
+   /* external contribution staging (device copies owned by this object) */
+   std::vector<void*> ext_allocs;
+   double timings[8] = {0};
+
+   ~Numeric() {
+      if (!S) return;
+      cudaSetDevice(S->device);
+      if (stream) cudaStreamSynchronize(stream);
+      for (void* p : chunks) cudaFree(p);
+      for (void* p : ext_allocs) cudaFree(p);
+      cudaFree(d_fronts); cudaFree(d_sfronts); cudaFree(d_swork); cudaFree(d_wbeg); cudaFree(d_export);
+      if (stream) cudaStreamDestroy(stream);
+   }
+
+   /* factor storage: chunked bump allocation */
+   void* falloc(size_t bytes) {
+      bytes = align_up(bytes, 256);
+      if (chunk_off + bytes > chunk_cap) {
+         size_t want = std::max(bytes, (size_t)256 << 20);
+         void* p;
+         CUDA_TRY(cudaMalloc(&p, want));
+         chunks.push_back(p);
+         chunk_base = (char*)p; chunk_off = 0; chunk_cap = want;
+      }
+      void* r = chunk_base + chunk_off;
+      chunk_off += bytes;
+      return r;
+   }
+   void reserve(size_t bytes) {
+      if (chunk_cap - chunk_off >= bytes) return;
+      void* p;
+      CUDA_TRY(cudaMalloc(&p, align_up(bytes, 256)));
+      chunks.push_back(p);
+      chunk_base = (char*)p; chunk_off = 0; chunk_cap = align_up(bytes, 256);
+   }
+};
+
+template <class T>
+static T* upload(Bump& bump, const std::vector<T>& v, cudaStream_t s) {
+   T* d = bump.take<T>(std::max<size_t>(v.size(), 1));
+   if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+   return d;
+}
+
+static bool is_device_pointer(const void* p, int* device) {
+   cudaPointerAttributes at;
+   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+   if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { if (device) *device = at.device; return true; }
+   return false;
+}
+
+/* One schedule of panels/steps over a set of fronts (first pass of a level or
+ * a retry pass over the fronts that still have candidates). */
+struct PassLists {
+   std::vector<int> flist;                 // fronts sorted by remaining columns (descending)
+   std::vector<int> rem;                   // remaining candidate columns per entry of flist
+   std::vector<RowTile> rows; std::vector<int> rows_prefix;
+   std::vector<MatTile> inner; std::vector<int> inner_prefix;
+   std::vector<MatTile> outer; std::vector<int> outer_prefix;
+};
+
+static void build_pass_lists(const std::vector<Front>& F, const std::vector<int>& fronts,
+      const std::vector<int>& remaining, bool big, PassLists& P) {
+   const int T = update_tile_size(big);
+   std::vector<int> ord(fronts.size());
+   for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+   std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return remaining[a] > remaining[b]; });
+   P = PassLists();
+   P.rows_prefix.push_back(0); P.inner_prefix.push_back(0); P.outer_prefix.push_back(0);
+   for (int o : ord) {
+      int fi = fronts[o];
+      const Front& f = F[fi];
+      P.flist.push_back(fi);
+      P.rem.push_back(remaining[o]);
+      int ntr = (f.m + RT - 1) / RT;
+      for (int t = 0; t < ntr; ++t) P.rows.push_back({fi, t});
+      P.rows_prefix.push_back((int)P.rows.size());
+      int mt = (f.m + T - 1) / T, nt = (f.n + T - 1) / T;
+      int ntc_inner = std::min(nt, PW / T + 1);
+      for (int tj = 0; tj < ntc_inner; ++tj)
+         for (int ti = 0; ti < mt; ++ti) P.inner.push_back({fi, ti, tj});
+      P.inner_prefix.push_back((int)P.inner.size());
+      if (f.n > PW) {
+         for (int tj = 0; tj < nt; ++tj)
+            for (int ti = 0; ti < mt - tj; ++ti) P.outer.push_back({fi, ti, tj});
+      }
+      P.outer_prefix.push_back((int)P.outer.size());
+   }
+}
+
+/* Issues the kernels of one pass.  remaining[i] candidates are processed for
+ * front flist[i]: panels of PW, inner steps of BS. */
+static void run_pass(Numeric& N, Front* d_fronts, const PassLists& P, Bump& bump, bool big,
+      const FactorParams& prm) {
+   if (P.flist.empty()) return;
+   cudaStream_t s = N.stream;
+   const bool posdef = N.posdef;
+   int* d_flist = upload(bump, P.flist, s);
+   RowTile* d_rows = upload(bump, P.rows, s);
+   MatTile* d_inner = upload(bump, P.inner, s);
+   MatTile* d_outer = upload(bump, P.outer, s);
+   const int nf = (int)P.flist.size();
+   const int maxrem = P.rem[0];
+   const int npanel = (maxrem + PW - 1) / PW;
+   auto count_gt = [&](int thr) {   // #fronts with rem > thr (rem sorted descending)
+      int lo = 0, hi = nf;
+      while (lo < hi) { int mid = (lo + hi) / 2; if (P.rem[mid] > thr) lo = mid + 1; else hi = mid; }
+      return lo;
+   };
+   for (int p = 0; p < npanel; ++p) {
+      int prem = std::min(PW, maxrem - p * PW);
+      int nsteps = (prem + BS - 1) / BS;
+      for (int st = 0; st < nsteps; ++st) {
+         int na = count_gt(p * PW + st * BS);
+         if (na == 0) break;
+         launch_diag(d_fronts, d_flist, na, posdef, st == 0, prm, s);
+         launch_apply(d_fronts, d_rows, P.rows_prefix[na], posdef, prm, s);
+         if (!posdef) launch_commit(d_fronts, d_rows, P.rows_prefix[na], s);
+         launch_update(d_fronts, d_inner, P.inner_prefix[na], UPD_INNER, big, s);
+         if (!posdef) launch_swap(d_fronts, d_rows, P.rows_prefix[na], false, s);
+      }
+      int no = count_gt((p + 1) * PW);
+      if (no > 0) {
+         launch_update(d_fronts, d_outer, P.outer_prefix[no], UPD_OUTER, big, s);
+         if (!posdef) launch_swap(d_fronts, d_rows, P.rows_prefix[no], true, s);
+      }
+   }
+   launch_finalize(d_fronts, d_flist, nf, posdef, s);
+   CUDA_TRY(cudaGetLastError());
+}
+
+static void factor_subtree(Numeric& N, const double* aval_in, const double* scaling_in,
+      void** child_contrib, const spral_ssids_b200_options* opt, spral_ssids_b200_stats* stats) {
+   Symbolic& S = *N.S;
+   const int nloc = S.nloc;
+   const bool posdef = N.posdef;
+   std::lock_guard<std::mutex> lock(S.mtx);
+   CUDA_TRY(cudaSetDevice(S.device));
+   CUDA_TRY(cudaStreamCreateWithFlags(&N.stream, cudaStreamNonBlocking));
+   cudaStream_t s = N.stream;
+   configure_update_kernels();
+   auto t_begin = std::chrono::steady_clock::now();
+
+   FactorParams prm{opt->u, opt->small, opt->action ? 1 : 0};
+   if (nloc == 0) return;
+
+   /* aval / scaling on the device (the H2D copy of A is part of the factor time,
+    * as in gpu/subtree.f90:375-379) */
+   const double* d_aval = aval_in;
+   const double* d_scal = scaling_in;
+   if (!is_device_pointer(aval_in, nullptr)) {
+      S.b_aval.ensure((size_t)std::max<int64_t>(S.aval_len, 1) * sizeof(double), s);
+      CUDA_TRY(cudaMemcpyAsync(S.b_aval.p, aval_in, (size_t)S.aval_len * sizeof(double), cudaMemcpyHostToDevice, s));
+      d_aval = (const double*)S.b_aval.p;
+   }
+   if (scaling_in && !is_device_pointer(scaling_in, nullptr)) {
+      S.b_scal.ensure((size_t)S.n * sizeof(double), s);
+      CUDA_TRY(cudaMemcpyAsync(S.b_scal.p, scaling_in, (size_t)S.n * sizeof(double), cudaMemcpyHostToDevice, s));
+      d_scal = (const double*)S.b_scal.p;
+   }
+
+   /* fixed-size scratch */
+   S.b_cbuf[0].ensure(std::max<size_t>(S.cbuf_bytes[0], 256), s);
+   S.b_cbuf[1].ensure(std::max<size_t>(S.cbuf_bytes[1], 256), s);
+   CUDA_TRY(cudaMalloc((void**)&N.d_fronts, nloc * sizeof(Front)));
+   N.h_fronts.assign(nloc, Front());
+   std::vector<Front>& F = N.h_fronts;
+
+   /* factor storage estimate: sum over nodes of L + D + perm, times multiplier */
+   {
+      double tot = 0;
+      for (int i = 0; i < nloc; ++i)
+         tot += (double)align_up((size_t)S.m0[i], 2) * S.n0[i] * 8 + 16.0 * S.n0[i] + 4.0 * S.n0[i] + 768;
+      double mult = opt->multiplier > 1.0 ? opt->multiplier : 1.0;
+      N.reserve((size_t)(tot * mult) + (1 << 20));
+   }
+
+   /* external contributions: bring them to this device, compute their maps */
+   struct Ext { AsmSrc src; int node; };
+   std::vector<Ext> ext(S.contrib_dest.size());
+   for (size_t k = 0; k < ext.size(); ++k) {
+      auto* c = static_cast<spral_ssids_b200_contrib*>(child_contrib[k]);
+      while (!c->ready) { /* the producer part sets ready last (fkeep.F90:163-169) */ }
+      int node = S.contrib_dest[k];
+      Ext& e = ext[k];
+      e.node = node;
+      std::memset(&e.src, 0, sizeof(AsmSrc));
+      int cn = c->n, nd = c->ndelay;
+      /* row list -> positions in the destination node's row list */
+      std::vector<int> crl(cn);
+      if (cn) CUDA_TRY(cudaMemcpy(crl.data(), c->rlist, cn * sizeof(int), cudaMemcpyDefault));
+      std::vector<int> map(cn);
+      {
+         std::vector<int> pos(S.n + 1, 0);
+         for (int64_t ii = S.rptr[node]; ii < S.rptr[node + 1]; ++ii) pos[S.rlist[ii]] = (int)(ii - S.rptr[node] + 1);
+         int npl = 0;
+         for (int i = 0; i < cn; ++i) { map[i] = pos[crl[i]]; if (map[i] <= S.n0[node]) npl++; }
+         e.src.npassl = npl;
+      }
+      int* d_map; CUDA_TRY(cudaMalloc((void**)&d_map, std::max(cn, 1) * sizeof(int)));
+      N.ext_allocs.push_back(d_map);
+      if (cn) CUDA_TRY(cudaMemcpyAsync(d_map, map.data(), cn * sizeof(int), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));   // map is a local vector
+      e.src.map = d_map; e.src.cm = cn; e.src.ndelay = nd;
+      bool local = (c->device == S.device);
+      if (!local && c->device >= 0) {      // pull over NVLink: direct P2P when the topology allows it
+         int can = 0;
+         if (cudaDeviceCanAccessPeer(&can, S.device, c->device) == cudaSuccess && can) {
+            cudaError_t pe = cudaDeviceEnablePeerAccess(c->device, 0);
+            if (pe != cudaSuccess) cudaGetLastError();   // already enabled
+         }
+      }
+      if (c->val && cn) {
+         if (local) { e.src.C = c->val; e.src.ldc = c->ldval; }
+         else {
+            double* d; CUDA_TRY(cudaMalloc((void**)&d, (size_t)cn * cn * sizeof(double)));
+            N.ext_allocs.push_back(d);
+            CUDA_TRY(cudaMemcpy2DAsync(d, (size_t)cn * sizeof(double), c->val, (size_t)c->ldval * sizeof(double),
+                                       (size_t)cn * sizeof(double), cn, cudaMemcpyDefault, s));
+            e.src.C = d; e.src.ldc = cn;
+         }
+      }
+      if (nd > 0) {
+         if (local) { e.src.dval = c->delay_val; e.src.lddelay = c->lddelay; e.src.dperm = c->delay_perm; }
+         else {
+            size_t rows = (size_t)nd + cn;
+            double* d; CUDA_TRY(cudaMalloc((void**)&d, rows * nd * sizeof(double)));
+            int* dp; CUDA_TRY(cudaMalloc((void**)&dp, nd * sizeof(int)));
+            N.ext_allocs.push_back(d); N.ext_allocs.push_back(dp);
+            CUDA_TRY(cudaMemcpy2DAsync(d, rows * sizeof(double), c->delay_val, (size_t)c->lddelay * sizeof(double),
+                                       rows * sizeof(double), nd, cudaMemcpyDefault, s));
+            CUDA_TRY(cudaMemcpyAsync(dp, c->delay_perm, nd * sizeof(int), cudaMemcpyDefault, s));
+            e.src.dval = d; e.src.lddelay = (int)rows; e.src.dperm = dp;
+         }
+      }
+   }
+
+   std::vector<int> nelim(nloc, 0), ncol(nloc, 0);   // by node
+   spral_ssids_b200_stats st;
+   std::memset(&st, 0, sizeof(st));
+   const int ASMC = assemble_cols_per_cta();
+   const int SCH = scatter_chunk();
+   const int MAXRANK = 8;
+   double t_sync = 0;
+
+   for (int lev = 0; lev < S.nlevels; ++lev) {
+      const int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
+      const int nfl = f1 - f0;
+      if (nfl == 0) continue;
+
+      /* ---- geometry ---- */
+      size_t lbytes = 0, ldd = 0, bkd = 0;
+      int maxm = 0;
+      for (int fi = f0; fi < f1; ++fi) {
+         int node = S.node_of_front[fi];
+         int ndin = 0;
+         for (int k = S.child_ptr[node]; k < S.child_ptr[node + 1]; ++k) {
+            int c = S.child_list[k];
+            ndin += ncol[c] - nelim[c];
+         }
+         for (int k : S.contribs_of_node[node]) ndin += ext[k].src.ndelay;
+         Front& f = F[fi];
+         std::memset(&f, 0, sizeof(Front));
+         f.m0 = S.m0[node]; f.n0 = S.n0[node]; f.ndin = ndin;
+         f.m = f.m0 + ndin; f.n = f.n0 + ndin;
+         f.ldl = (int)align_up((size_t)f.m, 2);
+         f.end = f.n; f.first_pass_done = -1;
+         ncol[node] = f.n;
+         maxm = std::max(maxm, f.m);
+         lbytes += align_up((size_t)f.ldl * f.n * sizeof(double), 256);
+         if (!posdef) lbytes += align_up((size_t)2 * f.n * sizeof(double), 256);
+         lbytes += align_up((size_t)f.n * sizeof(int), 256);
+         ldd += (size_t)f.ldl * f.n + 32;
+         bkd += (size_t)f.ldl * BS + 32;
+      }
+      const bool big = maxm >= 192;
+      char* lblock = (char*)N.falloc(lbytes);
+      if (!posdef) {
+         S.b_ld.ensure(std::max(ldd, S.ld_estimate) * sizeof(double), s);
+         S.b_bk.ensure(bkd * sizeof(double), s);
+         S.b_ws.ensure((size_t)nfl * sizeof(BlockWS), s);
+      } else {
+         S.b_ws.ensure((size_t)nfl * sizeof(BlockWS), s);
+      }
+      {
+         size_t off = 0, ldo = 0, bko = 0, co = 0;
+         for (int fi = f0; fi < f1; ++fi) {
+            int node = S.node_of_front[fi];
+            Front& f = F[fi];
+            f.L = (double*)(lblock + off); off += align_up((size_t)f.ldl * f.n * sizeof(double), 256);
+            if (!posdef) { f.D = (double*)(lblock + off); off += align_up((size_t)2 * f.n * sizeof(double), 256); }
+            f.perm = (int*)(lblock + off); off += align_up((size_t)f.n * sizeof(int), 256);
+            if (!posdef) {
+               f.LD = (double*)S.b_ld.p + ldo; ldo += align_up((size_t)f.ldl * f.n, 32);
+               f.BK = (double*)S.b_bk.p + bko; bko += align_up((size_t)f.ldl * BS, 32);
+            } else { f.LD = f.L; f.BK = nullptr; }
+            f.ws = (BlockWS*)S.b_ws.p + (fi - f0);
+            f.rows = S.d_rlist + S.rptr[node];
+            int cm = f.m0 - f.n0;
+            f.ldc = (int)align_up((size_t)cm, 2);
+            if (cm > 0) {
+               if (S.exported[node]) {
+                  CUDA_TRY(cudaMalloc((void**)&N.d_export, (size_t)f.ldc * cm * sizeof(double)));
+                  f.C = N.d_export; N.export_front = fi;
+               } else {
+                  f.C = (double*)((char*)S.b_cbuf[lev & 1].p + co);
+                  co += align_up((size_t)f.ldc * cm * sizeof(double), 256);
+               }
+            }
+         }
+      }
+      CUDA_TRY(cudaMemcpyAsync(N.d_fronts + f0, &F[f0], nfl * sizeof(Front), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemsetAsync(lblock, 0, lbytes, s));
+
+      /* ---- per-level work lists ---- */
+      std::vector<int2> scat;
+      std::vector<AsmSrc> srcs;
+      std::vector<std::vector<int2>> pre(MAXRANK + 1), post(MAXRANK + 1);
+      std::vector<int2> dly;
+      std::vector<int> lfronts(nfl), lrem(nfl);
+      for (int fi = f0; fi < f1; ++fi) {
+         int node = S.node_of_front[fi];
+         const Front& f = F[fi];
+         lfronts[fi - f0] = fi; lrem[fi - f0] = f.n;
+         int64_t nent = S.nptr[node + 1] - S.nptr[node];
+         int nch = (int)std::max<int64_t>(1, (nent + SCH - 1) / SCH);
+         for (int c = 0; c < nch; ++c) scat.push_back(make_int2(fi, c));
+         int rank = 0, delay_col = f.n0;
+         auto add_src = [&](const AsmSrc& a) {
+            int si = (int)srcs.size();
+            srcs.push_back(a);
+            AsmSrc& q = srcs.back();
+            q.parent = fi; q.delay_col = delay_col;
+            delay_col += q.ndelay;
+            int r = std::min(rank, MAXRANK);
+            if (q.C) {
+               int t_split = q.npassl / ASMC;   // tile containing the first contribution column
+               int ntile = (q.cm + ASMC - 1) / ASMC;
+               for (int t = 0; t < (q.npassl + ASMC - 1) / ASMC; ++t) pre[r].push_back(make_int2(si, t));
+               for (int t = t_split; t < ntile; ++t) post[r].push_back(make_int2(si, t));
+            }
+            for (int j = 0; j < q.ndelay; ++j) dly.push_back(make_int2(si, j));
+            rank++;
+         };
+         for (int k = S.child_ptr[node]; k < S.child_ptr[node + 1]; ++k) {
+            int c = S.child_list[k];
+            const Front& cf = F[S.front_of_node[c]];
+            AsmSrc a;
+            std::memset(&a, 0, sizeof(a));
+            a.cm = cf.m0 - cf.n0; a.C = cf.C; a.ldc = cf.ldc;
+            a.map = S.d_rlist_direct + S.rptr[c] + cf.n0;
+            a.ndelay = cf.n - cf.nelim;
+            a.dval = cf.L + (size_t)cf.nelim * cf.ldl + cf.nelim; a.lddelay = cf.ldl;
+            a.dperm = cf.perm + cf.nelim;
+            a.npassl = S.npassl[c];
+            add_src(a);
+         }
+         for (int k : S.contribs_of_node[node]) add_src(ext[k].src);
+      }
+      /* one work buffer per level; generous upper bound for the pass lists */
+      PassLists P;
+      build_pass_lists(F, lfronts, lrem, big, P);
+      std::vector<MatTile> ctiles;
+      {
+         const int T = update_tile_size(big);
+         for (int fi = f0; fi < f1; ++fi) {
+            const Front& f = F[fi];
+            if (f.m == f.n) continue;
+            int ntc = (f.m + T - 1) / T - f.n / T;
+            for (int tj = 0; tj < ntc; ++tj)
+               for (int ti = 0; ti < ntc - tj; ++ti) ctiles.push_back({fi, ti, tj});
+         }
+      }
+      size_t wbytes = 4096 + (scat.size() + dly.size()) * sizeof(int2) + srcs.size() * sizeof(AsmSrc)
+                    + (P.flist.size() + 64) * sizeof(int) + P.rows.size() * sizeof(RowTile)
+                    + (P.inner.size() + P.outer.size() + ctiles.size()) * sizeof(MatTile);
+      for (auto& v : pre) wbytes += v.size() * sizeof(int2) + 256;
+      for (auto& v : post) wbytes += v.size() * sizeof(int2) + 256;
+      wbytes += 256 * 32;
+      S.b_work.ensure(2 * wbytes + (1 << 16), s);
+      Bump bump; bump.reset(S.b_work);
+
+      /* ---- init + assemble (fully-summed part) ---- */
+      int2* d_scat = upload(bump, scat, s);
+      launch_scatter_a(N.d_fronts, d_scat, (int)scat.size(), S.d_nlist, S.d_nptr, S.d_node_of_front,
+                       d_aval, d_scal, s);
+      AsmSrc* d_srcs = upload(bump, srcs, s);
+      std::vector<int2*> d_post(MAXRANK + 1, nullptr);
+      for (int r = 0; r <= MAXRANK; ++r) {
+         if (!pre[r].empty()) {
+            int2* d = upload(bump, pre[r], s);
+            launch_assemble(N.d_fronts, d_srcs, d, (int)pre[r].size(), false, r == MAXRANK, s);
+         }
+         if (!post[r].empty()) d_post[r] = upload(bump, post[r], s);
+      }
+      if (!dly.empty()) {
+         int2* d = upload(bump, dly, s);
+         launch_delays(N.d_fronts, d_srcs, d, (int)dly.size(), s);
+      }
+      MatTile* d_ctiles = upload(bump, ctiles, s);
+
+      /* ---- factorise: first pass, then retry passes while fronts have candidates ---- */
+      run_pass(N, N.d_fronts, P, bump, big, prm);
+      for (int iter = 0;; ++iter) {
+         CUDA_TRY(cudaMemcpyAsync(&F[f0], N.d_fronts + f0, nfl * sizeof(Front), cudaMemcpyDeviceToHost, s));
+         auto ts0 = std::chrono::steady_clock::now();
+         CUDA_TRY(cudaStreamSynchronize(s));
+         t_sync += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
+         std::vector<int> uf, urem;
+         int err = 0;
+         for (int fi = f0; fi < f1; ++fi) {
+            if (F[fi].flag < 0) err = err ? std::max(err, F[fi].flag) : F[fi].flag;
+            if (!F[fi].finished) { uf.push_back(fi); urem.push_back(F[fi].n - F[fi].done); }
+         }
+         if (err) { st.flag = err; *stats = st; return; }
+         if (uf.empty()) break;
+         PassLists R;
+         build_pass_lists(F, uf, urem, big, R);
+         size_t rb = 4096 + R.flist.size() * sizeof(int) + R.rows.size() * sizeof(RowTile)
+                   + (R.inner.size() + R.outer.size()) * sizeof(MatTile) + 2048;
+         S.b_retry.ensure(rb, s);             // the stream is idle here: re-use is safe
+         Bump rbump; rbump.reset(S.b_retry);
+         run_pass(N, N.d_fronts, R, rbump, big, prm);
+      }
+
+      /* ---- Schur complement, then the children's contributions to it ---- */
+      launch_update(N.d_fronts, d_ctiles, (int)ctiles.size(), UPD_CONTRIB, big, s);
+      for (int r = 0; r <= MAXRANK; ++r)
+         if (d_post[r]) launch_assemble(N.d_fronts, d_srcs, d_post[r], (int)post[r].size(), true, r == MAXRANK, s);
+      CUDA_TRY(cudaGetLastError());
+
+      /* ---- statistics (cpu/factor.hxx:117-124, NumericSubtree.hxx:248-280) ---- */
+      for (int fi = f0; fi < f1; ++fi) {
+         const Front& f = F[fi];
+         int node = S.node_of_front[fi];
+         nelim[node] = f.nelim;
+         st.num_delay += f.n - f.nelim;
+         for (int64_t j = f.m; j >= (int64_t)f.m - f.nelim + 1; --j) { st.num_factor += j; st.num_flops += j * j; }
+         st.maxfront = std::max(st.maxfront, f.m);
+         st.maxsupernode = std::max(st.maxsupernode, f.n);
+         if (!posdef) {
+            st.num_neg += f.num_neg; st.num_two += f.num_two; st.num_zero += f.num_zero;
+            int fp = f.first_pass_done < 0 ? f.nelim : f.first_pass_done;
+            st.not_first_pass += f.n - fp;
+            st.not_second_pass += f.n - f.nelim;
+         }
+      }
+      /* the next level re-uses b_work / b_ld / ...: its uploads and kernels are
+       * ordered behind this level's kernels on the same stream */
+   }
+   if (st.num_zero > 0) st.flag = SPRAL_SSIDS_WARNING_FACT_SINGULAR;
+
+   /* ---- solve data ---- */
+   {
+      std::vector<SolveFront> sf(nloc);
+      std::vector<RowTile> sw;
+      std::vector<int> wbeg(nloc, 0);
+      N.swork_ptr.assign(S.nlevels + 1, 0);
+      N.lvl_steps.assign(S.nlevels, 0);
+      const int SBk = solve_block();
+      for (int lev = 0; lev < S.nlevels; ++lev) {
+         int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
+         N.swork_ptr[lev] = (int)sw.size();
+         int mx = 0;
+         for (int fi = f0; fi < f1; ++fi) {
+            const Front& f = F[fi];
+            sf[fi] = SolveFront{f.L, f.D, f.perm, f.rows, f.ldl, f.m, f.n, f.n0, f.m0, f.nelim};
+            wbeg[fi] = (int)sw.size() - N.swork_ptr[lev];
+            int nt = (f.m + RT - 1) / RT;
+            for (int t = 0; t < nt; ++t) sw.push_back({fi, t});
+            mx = std::max(mx, f.nelim);
+         }
+         N.lvl_steps[lev] = (mx + SBk - 1) / SBk;
+         N.max_level_work = std::max(N.max_level_work, sw.size() - (size_t)N.swork_ptr[lev]);
+      }
+      N.swork_ptr[S.nlevels] = (int)sw.size();
+      CUDA_TRY(cudaMalloc((void**)&N.d_sfronts, nloc * sizeof(SolveFront)));
+      CUDA_TRY(cudaMalloc((void**)&N.d_swork, std::max<size_t>(sw.size(), 1) * sizeof(RowTile)));
+      CUDA_TRY(cudaMalloc((void**)&N.d_wbeg, nloc * sizeof(int)));
+      CUDA_TRY(cudaMemcpyAsync(N.d_sfronts, sf.data(), nloc * sizeof(SolveFront), cudaMemcpyHostToDevice, s));
+      if (!sw.empty()) CUDA_TRY(cudaMemcpyAsync(N.d_swork, sw.data(), sw.size() * sizeof(RowTile), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(N.d_wbeg, wbeg.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+   }
+   N.timings[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+   N.timings[5] = t_sync;
+   *stats = st;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Solves                                                                    */
+/* ------------------------------------------------------------------------ */
+
+enum SolveJob { JOB_FWD, JOB_DIAG, JOB_DIAG_BWD, JOB_BWD };
+
+static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, int ldx) {
+   Numeric& N = const_cast<Numeric&>(Nc);
+   Symbolic& S = *N.S;
+   if (S.nloc == 0 || nrhs == 0) return 0;
+   try {
+      std::lock_guard<std::mutex> lock(S.mtx);
+      CUDA_TRY(cudaSetDevice(S.device));
+      cudaStream_t s = N.stream;
+      const bool posdef = N.posdef;
+      double* dx = x;
+      bool host_x = !is_device_pointer(x, nullptr);
+      size_t xbytes = (size_t)ldx * nrhs * sizeof(double);
+      if (host_x) {
+         S.b_x.ensure(xbytes, s);
+         dx = (double*)S.b_x.p;
+         CUDA_TRY(cudaMemcpyAsync(dx, x, xbytes, cudaMemcpyHostToDevice, s));
+      }
+      if (job == JOB_FWD) S.b_y.ensure(xbytes, s);
+      if (job == JOB_DIAG_BWD || job == JOB_BWD)
+         S.b_pbuf.ensure(std::max<size_t>(N.max_level_work, 1) * solve_block() * 8 * sizeof(double), s);
+      double* ywork = (double*)S.b_y.p;
+      double* pbuf = (double*)S.b_pbuf.p;
+      for (int r0 = 0; r0 < nrhs;) {
+         int nr = solve_rhs_chunk(nrhs - r0);
+         double* xs = dx + (size_t)r0 * ldx;
+         if (job == JOB_FWD) {
+            for (int lev = 0; lev < S.nlevels; ++lev)
+               launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev],
+                     N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx,
+                     ywork + (size_t)r0 * ldx, s);
+            launch_fwd_flush(N.d_sfronts, 0, S.nloc, nr, xs, ldx, ywork + (size_t)r0 * ldx, s);
+         } else if (job == JOB_DIAG) {
+            if (!posdef) launch_diag_solve(N.d_sfronts, 0, S.nloc, nr, xs, ldx, s);
+         } else {
+            for (int lev = S.nlevels - 1; lev >= 0; --lev) {
+               int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
+               if (job == JOB_DIAG_BWD && !posdef) launch_diag_solve(N.d_sfronts, f0, f1 - f0, nr, xs, ldx, s);
+               launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
+                     N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
+                     xs, ldx, pbuf, s);
+            }
+         }
+         r0 += nr;
+      }
+      CUDA_TRY(cudaGetLastError());
+      if (host_x) CUDA_TRY(cudaMemcpyAsync(x, dx, xbytes, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+   } catch (const CudaError& e) {
+      fprintf(stderr, "spral_ssids_b200: CUDA error %d (%s) in solve\n", (int)e.code, cudaGetErrorString(e.code));
+      return SPRAL_SSIDS_ERROR_CUDA_UNKNOWN;
+   } catch (const std::bad_alloc&) {
+      return SPRAL_SSIDS_ERROR_ALLOCATION;
+   }
+   return 0;
+}
+
+} // namespace b200
+
+/* ------------------------------------------------------------------------ */
+/* C ABI                                                                     */
+/* ------------------------------------------------------------------------ */
+
+using namespace b200;
+
+extern "C" {
+
+int spral_ssids_b200_cuda_init(int* cnt) {
+   int n = 0;
+   cudaError_t e = cudaGetDeviceCount(&n);
+   if (e != cudaSuccess) { *cnt = 0; cudaGetLastError(); return (int)e; }
+   for (int d = 0; d < n; ++d) {
+      if ((e = cudaSetDevice(d)) != cudaSuccess) { *cnt = 0; return (int)e; }
+      void* p = nullptr;
+      if ((e = cudaMalloc(&p, 1 << 20)) != cudaSuccess) { *cnt = 0; return (int)e; }
+      cudaFree(p);
+   }
+   *cnt = n;
+   return 0;
+}
+
+void* spral_ssids_gpu_create_symbolic_subtree(
+      int device, int n, int sa, int en, const int* sptr, const int* sparent,
+      const int64_t* rptr, const int* rlist, const int64_t* nptr,
+      const int64_t* nlist, int ncontrib, const int* contrib_idx,
+      const struct spral_ssids_b200_options* options) {
+   try {
+      return build_symbolic(device, n, sa, en, sptr, sparent, rptr, rlist, nptr, nlist,
+                            ncontrib, contrib_idx, options);
+   } catch (const CudaError& e) {
+      fprintf(stderr, "spral_ssids_b200: CUDA error %d (%s) in symbolic constructor\n",
+              (int)e.code, cudaGetErrorString(e.code));
+   } catch (const std::exception& e) {
+      fprintf(stderr, "spral_ssids_b200: %s in symbolic constructor\n", e.what());
+   }
+   return nullptr;
+}
+
+void spral_ssids_gpu_destroy_symbolic_subtree(void* p) { delete static_cast<Symbolic*>(p); }
+
+void* spral_ssids_gpu_create_num_subtree_dbl(
+      bool posdef, const void* symbolic_subtree, const double* aval,
+      const double* scaling, void** child_contrib,
+      const struct spral_ssids_b200_options* options,
+      struct spral_ssids_b200_stats* stats) {
+   auto* N = new Numeric;
+   N->S = const_cast<Symbolic*>(static_cast<const Symbolic*>(symbolic_subtree));
+   N->posdef = posdef;
+   std::memset(stats, 0, sizeof(*stats));
+   try {
+      factor_subtree(*N, aval, scaling, child_contrib, options, stats);
+   } catch (const CudaError& e) {
+      stats->flag = SPRAL_SSIDS_ERROR_CUDA_UNKNOWN;
+      stats->cuda_error = (int)e.code;
+      fprintf(stderr, "spral_ssids_b200: CUDA error %d (%s) in factor\n", (int)e.code, cudaGetErrorString(e.code));
+   } catch (const std::bad_alloc&) {
+      stats->flag = SPRAL_SSIDS_ERROR_ALLOCATION;
+   } catch (const std::exception& e) {
+      stats->flag = SPRAL_SSIDS_ERROR_ALLOCATION;
+      fprintf(stderr, "spral_ssids_b200: %s in factor\n", e.what());
+   }
+   return N;
+}
+
+void spral_ssids_gpu_destroy_num_subtree_dbl(bool, void* p) { delete static_cast<Numeric*>(p); }
+
+int spral_ssids_gpu_subtree_solve_fwd_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   return solve_subtree(*static_cast<const Numeric*>(p), JOB_FWD, nrhs, x, ldx);
+}
+int spral_ssids_gpu_subtree_solve_diag_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   return solve_subtree(*static_cast<const Numeric*>(p), JOB_DIAG, nrhs, x, ldx);
+}
+int spral_ssids_gpu_subtree_solve_diag_bwd_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   return solve_subtree(*static_cast<const Numeric*>(p), JOB_DIAG_BWD, nrhs, x, ldx);
+}
+int spral_ssids_gpu_subtree_solve_bwd_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   return solve_subtree(*static_cast<const Numeric*>(p), JOB_BWD, nrhs, x, ldx);
+}
+
+/* Format of NumericSubtree::enquire (src/ssids/cpu/NumericSubtree.hxx:424-470):
+ * nodes in node order; posdef: diagonal of L; indefinite: piv_order indexed by
+ * pivot-order variable, 2x2 pivots negative; d two entries per column. */
+void spral_ssids_gpu_subtree_enquire_dbl(bool posdef, const void* p, int* piv_order, double* d) {
+   const Numeric& N = *static_cast<const Numeric*>(p);
+   const Symbolic& S = *N.S;
+   cudaSetDevice(S.device);
+   int piv = 0;
+   std::vector<double> buf; std::vector<int> perm;
+   for (int node = 0; node < S.nloc; ++node) {
+      const Front& f = N.h_fronts[S.front_of_node[node]];
+      if (posdef) {
+         buf.resize(f.nelim);
+         if (f.nelim) cudaMemcpy2D(buf.data(), sizeof(double), f.L, (size_t)(f.ldl + 1) * sizeof(double),
+                                   sizeof(double), f.nelim, cudaMemcpyDeviceToHost);
+         for (int i = 0; i < f.nelim; ++i) *(d++) = buf[i];
+         continue;
+      }
+      buf.resize(2 * (size_t)f.nelim + 2); perm.resize(f.nelim);
+      if (f.nelim) {
+         cudaMemcpy(buf.data(), f.D, 2 * (size_t)f.nelim * sizeof(double), cudaMemcpyDeviceToHost);
+         cudaMemcpy(perm.data(), f.perm, f.nelim * sizeof(int), cudaMemcpyDeviceToHost);
+      }
+      for (int i = 0; i < f.nelim;) {
+         if (i + 1 == f.nelim || std::isfinite(buf[2 * i + 2])) {
+            if (piv_order) piv_order[perm[i] - 1] = (piv++);
+            if (d) { *(d++) = buf[2 * i]; *(d++) = 0.0; }
+            i += 1;
+         } else {
+            if (piv_order) { piv_order[perm[i] - 1] = -(piv++); piv_order[perm[i + 1] - 1] = -(piv++); }
+            if (d) { *(d++) = buf[2 * i]; *(d++) = buf[2 * i + 1]; *(d++) = buf[2 * i + 3]; *(d++) = 0.0; }
+            i += 2;
+         }
+      }
+   }
+}
+
+/* NumericSubtree::alter (src/ssids/cpu/NumericSubtree.hxx:473-497) */
+void spral_ssids_gpu_subtree_alter_dbl(bool posdef, void* p, const double* d) {
+   if (posdef) return;
+   Numeric& N = *static_cast<Numeric*>(p);
+   const Symbolic& S = *N.S;
+   cudaSetDevice(S.device);
+   std::vector<double> buf;
+   for (int node = 0; node < S.nloc; ++node) {
+      const Front& f = N.h_fronts[S.front_of_node[node]];
+      if (!f.nelim) continue;
+      buf.resize(2 * (size_t)f.nelim + 2);
+      cudaMemcpy(buf.data(), f.D, 2 * (size_t)f.nelim * sizeof(double), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < f.nelim;) {
+         if (i + 1 == f.nelim || std::isfinite(buf[2 * i + 2])) { buf[2 * i] = *(d++); d++; i += 1; }
+         else { buf[2 * i] = *(d++); buf[2 * i + 1] = *(d++); buf[2 * i + 3] = *(d++); d++; i += 2; }
+      }
+      cudaMemcpy(f.D, buf.data(), 2 * (size_t)f.nelim * sizeof(double), cudaMemcpyHostToDevice);
+   }
+}
+
+void spral_ssids_gpu_subtree_get_contrib_device_dbl(bool, void* p,
+      int* n, const double** val, int* ldval, const int** rlist, int* ndelay,
+      const int** delay_perm, const double** delay_val, int* lddelay, int* device) {
+   Numeric& N = *static_cast<Numeric*>(p);
+   const Symbolic& S = *N.S;
+   *device = S.device;
+   if (N.export_front < 0) {
+      *n = 0; *val = nullptr; *ldval = 0; *rlist = nullptr; *ndelay = 0;
+      *delay_perm = nullptr; *delay_val = nullptr; *lddelay = 0;
+      return;
+   }
+   const Front& f = N.h_fronts[N.export_front];
+   int node = S.node_of_front[N.export_front];
+   *n = f.m0 - f.n0;
+   *val = f.C; *ldval = f.ldc;
+   *rlist = S.d_rlist + S.rptr[node] + f.n0;
+   *ndelay = f.n - f.nelim;
+   *lddelay = f.ldl;
+   *delay_perm = (*ndelay > 0) ? f.perm + f.nelim : nullptr;
+   *delay_val = (*ndelay > 0) ? f.L + (size_t)f.nelim * (f.ldl + 1) : nullptr;
+}
+
+void spral_ssids_gpu_subtree_get_contrib_dbl(bool posdef, void* p,
+      int* n, const double** val, int* ldval, const int** rlist, int* ndelay,
+      const int** delay_perm, const double** delay_val, int* lddelay) {
+   Numeric& N = *static_cast<Numeric*>(p);
+   const Symbolic& S = *N.S;
+   int dev;
+   const double *dval, *ddel; const int *drl, *dperm;
+   spral_ssids_gpu_subtree_get_contrib_device_dbl(posdef, p, n, &dval, ldval, &drl, ndelay, &dperm, &ddel, lddelay, &dev);
+   if (N.export_front < 0) { *val = nullptr; *rlist = nullptr; *delay_perm = nullptr; *delay_val = nullptr; return; }
+   cudaSetDevice(S.device);
+   const Front& f = N.h_fronts[N.export_front];
+   int node = S.node_of_front[N.export_front];
+   int cn = *n;
+   N.h_cval.resize((size_t)cn * cn);
+   cudaMemcpy2D(N.h_cval.data(), (size_t)cn * sizeof(double), dval, (size_t)f.ldc * sizeof(double),
+                (size_t)cn * sizeof(double), cn, cudaMemcpyDeviceToHost);
+   *val = N.h_cval.data(); *ldval = cn;
+   *rlist = S.rlist.data() + S.rptr[node] + f.n0;
+   int nd = *ndelay;
+   if (nd > 0) {
+      size_t rows = (size_t)nd + cn;
+      N.h_dval.resize(rows * nd); N.h_dperm.resize(nd);
+      cudaMemcpy2D(N.h_dval.data(), rows * sizeof(double), ddel, (size_t)f.ldl * sizeof(double),
+                   rows * sizeof(double), nd, cudaMemcpyDeviceToHost);
+      cudaMemcpy(N.h_dperm.data(), dperm, nd * sizeof(int), cudaMemcpyDeviceToHost);
+      *delay_val = N.h_dval.data(); *lddelay = (int)rows; *delay_perm = N.h_dperm.data();
+   } else { *delay_val = nullptr; *delay_perm = nullptr; }
+}
+
+void spral_ssids_gpu_subtree_free_contrib_dbl(bool, void* p) {
+   Numeric& N = *static_cast<Numeric*>(p);
+   cudaSetDevice(N.S->device);
+   if (N.d_export) { cudaFree(N.d_export); N.d_export = nullptr; }
+   std::vector<double>().swap(N.h_cval);
+   std::vector<double>().swap(N.h_dval);
+}
+
+void spral_ssids_b200_contrib_fill(struct spral_ssids_b200_contrib* c, bool posdef,
+      void* numeric_subtree, bool device_resident) {
+   std::memset((void*)c, 0, sizeof(*c));
+   int dev = -1;
+   if (device_resident)
+      spral_ssids_gpu_subtree_get_contrib_device_dbl(posdef, numeric_subtree, &c->n, &c->val, &c->ldval,
+            &c->rlist, &c->ndelay, &c->delay_perm, &c->delay_val, &c->lddelay, &dev);
+   else
+      spral_ssids_gpu_subtree_get_contrib_dbl(posdef, numeric_subtree, &c->n, &c->val, &c->ldval,
+            &c->rlist, &c->ndelay, &c->delay_perm, &c->delay_val, &c->lddelay);
+   c->owner = 1; c->posdef = posdef; c->owner_ptr = numeric_subtree; c->device = dev;
+   c->ready = 1;
+}
+
+void spral_ssids_gpu_symbolic_get_maps(const void* p, int* rlist_direct, int* num_levels,
+      int* level_ptr, int* level_list) {
+   const Symbolic& S = *static_cast<const Symbolic*>(p);
+   cudaSetDevice(S.device);
+   if (rlist_direct && !S.rlist_direct.empty())
+      cudaMemcpy(rlist_direct, S.d_rlist_direct, S.rlist_direct.size() * sizeof(int), cudaMemcpyDeviceToHost);
+   if (num_levels) *num_levels = S.nlevels;
+   if (level_ptr) std::copy(S.level_ptr.begin(), S.level_ptr.end(), level_ptr);
+   if (level_list) std::copy(S.level_list.begin(), S.level_list.end(), level_list);
+}
+
+void spral_ssids_gpu_subtree_get_timings(const void* p, double* ms, int n) {
+   const Numeric& N = *static_cast<const Numeric*>(p);
+   for (int i = 0; i < n && i < 8; ++i) ms[i] = N.timings[i];
+}
+
+} /* extern "C" */

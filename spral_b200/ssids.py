@@ -226,6 +226,16 @@ def analyse(n, ptr, row, order=None, nemin=32, ngpu=1, devices=None, options=Non
     return Akeep(a, subtrees)
 
 
+def free_contrib(c):
+    """contrib_free (src/ssids/contrib_free.f90:17-31): owner 1 = this engine."""
+    if c is None or not c.owner_ptr:
+        return
+    if c.owner == 1:
+        _lib.load().spral_ssids_gpu_subtree_free_contrib_dbl(bool(c.posdef), c.owner_ptr)
+    elif getattr(c, "_free_hook", None):
+        c._free_hook(c)
+
+
 class Fkeep:
     def __init__(self, akeep, posdef, numeric, inform, scaling):
         self.akeep, self.posdef, self.numeric, self.inform, self.scaling = akeep, posdef, numeric, inform, scaling
@@ -249,6 +259,10 @@ def factor(akeep, posdef, val, options=None, scaling=None, device_contrib=True):
         cc = [slots[i] for i in range(lo, hi)]
         ns = akeep.subtrees[p].factor(posdef, val, cc, options, sc)
         numeric.append(ns)
+        # the consumer releases the contribution blocks it was handed
+        # (spral_ssids_contrib_free_dbl, src/ssids/contrib_free.f90:17-48)
+        for c in cc:
+            free_contrib(c)
         st = ns.stats
         # cpu_copy_stats_out (src/ssids/cpu/cpu_iface.f90:74-94)
         if st.flag < 0:
