@@ -32,6 +32,8 @@ struct BlockWS {
    double a0[BS * BS];    // the diagonal block before factorisation, full symmetric, unpermuted
    double dinv[2 * BS];   // D^-1, reference CPU layout
    int lperm[BS];         // position j of the permuted block holds old position lperm[j]
+   int zfrom;             // columns >= zfrom of the block are tentative zero pivots (BS if none)
+   int pad_[3];
 };
 
 /* One frontal matrix (device resident). */

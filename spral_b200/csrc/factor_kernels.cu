@@ -56,6 +56,8 @@ k_scatter_a(Front* fronts, const int2* work, const int64_t* __restrict__ nlist,
    int m0 = f->m0, n0 = f->n0, ndin = f->ndin, ldl = f->ldl;
    double* L = f->L;
    const int* rows = f->rows;
+   if (w.y == 0)   /* perm of the node's own columns (assemble.hxx:198-200) */
+      for (int i = threadIdx.x; i < n0; i += blockDim.x) f->perm[i] = rows[i];
    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
       int64_t src = nlist[2 * i] - 1;
       int64_t dest = nlist[2 * i + 1] - 1;
@@ -214,6 +216,7 @@ k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams
    __shared__ double ld[BS][BS + 1];
    __shared__ double dinv[2 * BS];
    __shared__ int lperm[BS];
+   int zfrom = BS;      // first column of the block that was declared a zero pivot
 
    if (lane == 0) {
       advance_state(f, new_panel != 0);
@@ -300,6 +303,7 @@ k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams
             if (lane == 0) { f->flag = SPRAL_SSIDS_ERROR_SINGULAR; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
             return;
          }
+         zfrom = p;
          for (int q = p; q < bs; ++q) {
             if (lane >= q) a[lane][q] = (lane == q) ? 1.0 : 0.0;
             ld[lane][q] = 0.0;
@@ -403,6 +407,7 @@ k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams
    ws->dinv[2 * lane] = (lane < bs) ? dinv[2 * lane] : 0.0;
    ws->dinv[2 * lane + 1] = (lane < bs) ? dinv[2 * lane + 1] : 0.0;
    ws->lperm[lane] = lperm[lane];
+   if (lane == 0) ws->zfrom = zfrom;
 }
 
 void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool new_panel,
@@ -453,6 +458,10 @@ k_apply(Front* fronts, const RowTile* work, FactorParams prm) {
    }
    if (threadIdx.x == 0) s_fail = BS;
    __syncthreads();
+   /* columns >= zfrom were declared zero pivots from the diagonal block alone;
+    * they are only zero columns if the rows below are (numerically) zero too
+    * (ldlt_tpp.cxx:179-188 tests the whole column) -- otherwise they fail */
+   const int zfrom = POSDEF ? BS : ws->zfrom;
 
    const int r = r0 + threadIdx.x;
    const bool active = (r >= rbeg) && (r < m);
@@ -504,7 +513,8 @@ k_apply(Front* fronts, const RowTile* work, FactorParams prm) {
             if (j > 0) wv += c2[j] * y[(j + BS - 1) % BS];
             Lr[(size_t)j * ldl] = wv;
             LDr[(size_t)j * ldl] = y[j];
-            if (!(fabs(wv) <= lim) && myfail == BS) myfail = j;
+            bool bad = !(fabs(wv) <= lim) || (j >= zfrom && !(fabs(y[j]) < prm.small));
+            if (bad && myfail == BS) myfail = j;
          }
       }
    }

@@ -375,7 +375,11 @@ static void run_pass(Numeric& N, Front* d_fronts, const PassLists& P, Bump& bump
          launch_update(d_fronts, d_inner, P.inner_prefix[na], UPD_INNER, big, s);
          if (!posdef) launch_swap(d_fronts, d_rows, P.rows_prefix[na], false, s);
       }
-      int no = count_gt((p + 1) * PW);
+      /* Columns right of the panel need the panel's pivots.  Positive definite:
+       * only fronts with columns left.  Indefinite: failed columns of earlier
+       * panels sit at [end, n), so every front wider than one panel takes part
+       * in every one of its panels (the kernel exits when pend0 == n). */
+      int no = posdef ? count_gt((p + 1) * PW) : count_gt(std::max(PW, p * PW));
       if (no > 0) {
          launch_update(d_fronts, d_outer, P.outer_prefix[no], UPD_OUTER, big, s);
          if (!posdef) launch_swap(d_fronts, d_rows, P.rows_prefix[no], true, s);
@@ -1034,3 +1038,17 @@ void spral_ssids_gpu_subtree_get_timings(const void* p, double* ms, int n) {
 }
 
 } /* extern "C" */
+
+/* Debug/introspection (not declared in the public header): copies one front's
+ * factor data to the host.  sizes = {m, n, ldl, nelim, ndin}. */
+extern "C" void spral_ssids_b200_debug_front(const void* p, int node, int* sizes,
+      double* L, double* D, int* perm) {
+   const Numeric& N = *static_cast<const Numeric*>(p);
+   const Symbolic& S = *N.S;
+   cudaSetDevice(S.device);
+   const Front& f = N.h_fronts[S.front_of_node[node]];
+   sizes[0] = f.m; sizes[1] = f.n; sizes[2] = f.ldl; sizes[3] = f.nelim; sizes[4] = f.ndin;
+   if (L) cudaMemcpy(L, f.L, (size_t)f.ldl * f.n * sizeof(double), cudaMemcpyDeviceToHost);
+   if (D && f.D) cudaMemcpy(D, f.D, (size_t)2 * f.n * sizeof(double), cudaMemcpyDeviceToHost);
+   if (perm) cudaMemcpy(perm, f.perm, (size_t)f.n * sizeof(int), cudaMemcpyDeviceToHost);
+}
