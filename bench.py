@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- ssids_factor FP64 GFLOP/s of the B200-native SSIDS engine.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            this engine
+  python bench.py --impl reference ...                     the reference's own CPU
+                                                            engine (oracle/_ref) on host cores
+A "step" is one numeric factorisation (ssids_factor: fkeep%inner_factor over all
+parts) of the BASELINE workload: 3-D 27-point stencil 100^3, shifted indefinite
+(n = 10^6), LDL^T with threshold pivoting u = 0.01, METIS ordering, nemin = 32.
+Analyse (ordering + symbolic) is set-up and is not timed, as in the metric.
+
+value  = num_flops / device time of the factor call with A already resident in HBM
+e2e    = num_flops / wall time of the same call through the C ABI with the HOST
+         value array (pinned) -- H2D of A and D2H of the per-front results inside
+roofline = the Schur-complement DMMA kernel (k_update, UPD_CONTRIB launches):
+         algorithmic flops (m-n)(m-n+1)*nelim per front / CUDA-event time of those
+         launches, against the FP64 tensor-pipe peak measured live on this GPU
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+os.environ.setdefault("OMP_CANCELLATION", "TRUE")
+os.environ.setdefault("OMP_PROC_BIND", "TRUE")
+
+import numpy as np  # noqa: E402
+
+SHIFT = 13.0
+CPU_SAMPLE_GRID = 56      # the CPU arms factor the same stencil on a smaller grid
+
+
+def make_matrix(grid):
+    from spral_b200 import matrices as M
+    return M.stencil_3d_27pt(grid, shift=SHIFT)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_factor(grid, nthreads=0):
+    """The reference's own CPU engine (oracle/_ref, unmodified sources) on the same
+    stencil at `grid`^3; returns (GFLOP/s, seconds, cores, flops)."""
+    import oracle_ref
+    from spral_b200.ssids import Analysis
+    oracle_ref.ensure_env()
+    n, ptr, row, val = make_matrix(grid)
+    a = Analysis(n, ptr, row)
+    cores = nthreads or os.cpu_count()
+    parts, inform, _ = oracle_ref.ref_factor(a, False, val, nthreads=cores)
+    for p in parts:
+        p.close()
+    t = inform["factor_time"]
+    return inform["num_flops"] / t / 1e9, t, cores, inform["num_flops"], a
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import oracle_ref
+    from spral_b200.ssids import Analysis
+    if not oracle_ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libspral_cpu_ref.so was not built"}))
+        return
+    oracle_ref.ensure_env()
+    grid = args.cpu_grid
+    n, ptr, row, val = make_matrix(grid)
+    a = Analysis(n, ptr, row)
+    cores = os.cpu_count()
+    times, flops = [], 0
+    for it in range(args.warmup + args.steps):
+        parts, inform, _ = oracle_ref.ref_factor(a, False, val, nthreads=cores)
+        for p in parts:
+            p.close()
+        flops = inform["num_flops"]
+        if it >= args.warmup:
+            times.append(inform["factor_time"])
+    t = float(np.mean(times))
+    v = flops / t / 1e9
+    sample = f"3-D 27-point {grid}^3 shifted indefinite (n={n}), whole factor, same ordering/options"
+    print(json.dumps({
+        "impl": "reference", "metric": "ssids_factor FP64 GFLOP/s", "value": v, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"ssids_factor 3-D 27-point {args.grid}^3 indefinite (bounded CPU sample: {grid}^3)",
+                   "sample": sample, "engine": "reference CPU engine src/ssids/cpu (OpenMP tasks + OpenBLAS)"},
+        "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=100, help="stencil grid size (BASELINE: 100)")
+    ap.add_argument("--cpu-grid", type=int, default=CPU_SAMPLE_GRID)
+    ap.add_argument("--nrhs", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    import spral_b200 as sb
+    from spral_b200 import _lib, dist as sdist
+    lib = _lib.load()
+
+    # ---- set-up (untimed): matrix, ordering, symbolic analysis, subtree partition ----
+    n, ptr, row, val = make_matrix(args.grid)
+    t0 = time.perf_counter()
+    ctx = sdist.DistContext(world, rank, local_rank)
+    ak = sdist.analyse(ctx, n, ptr, row)
+    t_analyse = time.perf_counter() - t0
+    a = ak.analysis
+    nz = len(val)
+    hval = torch.from_numpy(val).pin_memory()
+    dval = hval.cuda(non_blocking=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def factor_once(values_ptr):
+        """One ssids_factor over all parts; returns (fkeep, wall seconds, device ms of this rank)."""
+        barrier()
+        t = time.perf_counter()
+        fk = sdist.factor(ctx, ak, False, values_ptr)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t
+        dev_ms = sum(float(ns.timings()[1]) for ns in fk.numeric if ns is not None)
+        barrier()
+        return fk, wall, dev_ms
+
+    # ---- warm-up ----
+    fk = None
+    for _ in range(args.warmup):
+        if fk is not None:
+            sdist.free(fk)
+        fk, _, _ = factor_once(dval.data_ptr())
+
+    # ---- timed: A resident in HBM ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    walls, launches = [], 0
+    for _ in range(args.steps):
+        if fk is not None:
+            sdist.free(fk)
+        fk, wall, dev_ms = factor_once(dval.data_ptr())
+        # whole-job time = slowest rank; at N=1 the device-event time of the call
+        t_step = max_over_ranks(dev_ms / 1e3 if world == 1 else wall)
+        walls.append(t_step)
+        launches += int(sum(float(ns.timings()[6]) for ns in fk.numeric if ns is not None))
+    clocks = sampler.stop()
+    inform = sdist.reduce_inform(ctx, fk.inform)
+    flops = inform["num_flops"]
+    t_mean = float(np.mean(walls))
+    value = flops / t_mean / 1e9
+
+    # ---- end to end: host (pinned) values through the C ABI, results read back ----
+    e2e_t = []
+    for _ in range(max(2, min(args.steps, 3))):
+        sdist.free(fk)
+        fk, wall, _ = factor_once(hval.data_ptr())
+        e2e_t.append(max_over_ranks(wall))
+    e2e_value = flops / float(np.mean(e2e_t)) / 1e9
+    front_bytes = 200 * a.nnodes           # sizeof(Front) per front, read back once per level
+
+    # ---- solves (fkeep%inner_solve): 1 and nrhs right-hand sides, device-resident x ----
+    A = None
+    solve_ms, bwd_err = {}, None
+    try:
+        from spral_b200 import matrices as M
+        A = M.to_scipy(n, ptr, row, val)
+        rng = np.random.default_rng(0)
+        for nr in (1, args.nrhs):
+            X = np.asfortranarray(rng.uniform(-1, 1, (n, nr)))
+            X[:, 0] = 1.0
+            B = np.asfortranarray(A @ X)
+            sdist.solve(ctx, fk, B)                               # warm-up
+            barrier()
+            t = time.perf_counter()
+            Xs = sdist.solve(ctx, fk, B)
+            torch.cuda.synchronize()
+            solve_ms[nr] = 1e3 * max_over_ranks(time.perf_counter() - t)
+            if rank == 0 and nr == 1:
+                import oracle_ref
+                bwd_err = float(oracle_ref.backward_error(A, Xs, B))
+                R = B - A @ Xs
+                Xs2 = Xs + sdist.solve(ctx, fk, np.asfortranarray(R))
+                bwd_ref1 = float(oracle_ref.backward_error(A, Xs2, B))
+            elif nr == 1:
+                R = B - A @ Xs
+                sdist.solve(ctx, fk, np.asfortranarray(R))
+    except Exception as e:                                      # solve figures are extra
+        solve_ms["error"] = repr(e)
+        bwd_ref1 = None
+
+    # ---- roofline of the dominant kernel (profiled extra run, not part of the timing) ----
+    roofline = None
+    if world == 1:
+        lib.spral_ssids_b200_set_profile(1)
+        sdist.free(fk)
+        fk, _, _ = factor_once(dval.data_ptr())
+        lib.spral_ssids_b200_set_profile(0)
+        tm = fk.numeric[0].timings()
+        peak = float(lib.spral_ssids_b200_fp64_peak_tflops(local_rank))
+        ach = float(tm[3]) / (float(tm[2]) * 1e-3) / 1e12 if tm[2] > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "k_update<128,2,4> UPD_CONTRIB (Schur complement, FP64 DMMA)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
+                    "traffic": None, "launches": int(tm[4]), "kernel_ms_per_step": float(tm[2]),
+                    "kernel_flops_per_step": float(tm[3]),
+                    "peak_source": "FP64 DMMA issue loop measured live on this GPU "
+                                   "(MEASURED_PEAKS.json has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.9 TF/s on this pool)"}
+
+    out = {
+        "metric": "ssids_factor FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_mean,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"ssids_factor 3-D 27-point {args.grid}^3 shifted (sigma={SHIFT}) indefinite, "
+                               f"n={n}, LDL^T u=0.01, METIS order, nemin=32 (BASELINE configs[4])",
+                   "parallelism": f"subtree-partition x{world}" if world > 1 else "1 GPU",
+                   "nparts": int(a.nparts), "l2": "inputs larger than L2 (factor storage %.1f GB)" % (inform["num_factor"] * 8 / 1e9),
+                   "timer": "CUDA events on the factorisation stream (N=1); wall clock, max over ranks (N>1)"},
+        "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": int(nz * 8),
+                "d2h_bytes_per_step": int(front_bytes)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "inform": {k: int(inform[k]) for k in ("flag", "num_neg", "num_two", "num_delay", "matrix_rank", "num_factor", "num_flops", "maxfront")},
+        "solve_ms": {str(k): v for k, v in solve_ms.items()},
+        "backward_error": bwd_err, "backward_error_after_1_refinement": bwd_ref1 if rank == 0 else None,
+        "analyse_s": t_analyse,
+    }
+    if roofline:
+        out["roofline"] = roofline
+
+    # ---- CPU baseline: the reference engine on a bounded sample (rank 0, N=1 only) ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle_ref
+            if oracle_ref.available():
+                v, t, cores, fl, a2 = cpu_reference_factor(args.cpu_grid)
+                out["cpu_baseline"] = {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
+                                       "sample": f"3-D 27-point {args.cpu_grid}^3 shifted indefinite, whole factor "
+                                                 f"({fl:.3g} flops in {t:.2f} s), same ordering/options"}
+        except Exception as e:
+            out["cpu_baseline"] = {"error": repr(e)}
+    sdist.free(fk)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

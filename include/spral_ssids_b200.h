@@ -187,6 +187,20 @@ void spral_ssids_gpu_subtree_free_contrib_dbl(bool posdef, void* numeric_subtree
 void spral_ssids_b200_contrib_fill(struct spral_ssids_b200_contrib* c,
       bool posdef, void* numeric_subtree, bool device_resident);
 
+/* One process per GPU (torchrun): cross-process hand-over of a part's root
+ * contribution block, replacing transfer_contrib's D2H copy
+ * (src/ssids/gpu/factor.f90:155-221).  The producer packs
+ * [val n*n | delay_val (ndelay+n)*ndelay | delay_perm ndelay ints] into one
+ * device block it keeps owning and returns its 64-byte CUDA IPC handle; the
+ * consumer pulls the block over NVLink into its own memory.  Return 0 or the
+ * raw cudaError_t. */
+int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned char* handle,
+      int* n, int* ndelay, int64_t* bytes, void** device_block);
+int spral_ssids_b200_ipc_pull(const unsigned char* handle, int64_t bytes, void* dst);
+int spral_ssids_b200_copy_to_host(void* dst, const void* src, int64_t bytes);
+void* spral_ssids_b200_device_alloc(int64_t bytes);
+void spral_ssids_b200_device_free(void* p);
+
 /* Introspection used by the parity tests ("bit-exact extend-add index maps
  * and tree scheduling"): copies back the device-side maps built by the
  * symbolic constructor.  rlist_direct has rptr[en]-rptr[sa] entries
@@ -196,9 +210,19 @@ void spral_ssids_b200_contrib_fill(struct spral_ssids_b200_contrib* c,
 void spral_ssids_gpu_symbolic_get_maps(const void* symbolic_subtree,
       int* rlist_direct, int* num_levels, int* level_ptr, int* level_list);
 
-/* Per-phase device timings (ms) of the last factorisation, for profiling:
- * [0] total, [1] init+assemble, [2] factor panels, [3] schur, [4] H2D aval. */
+/* Measurements of the factorisation that built this object (bench.py):
+ * [0] host wall time of the call (ms), [1] device time (ms, CUDA events on the
+ * factorisation's stream), [2] ms spent in the Schur-complement (DMMA) launches,
+ * [3] their algorithmic flops, [4] their count ([2]-[4] only with profiling on),
+ * [5] host ms spent in the per-level synchronisations, [6] kernels launched. */
 void spral_ssids_gpu_subtree_get_timings(const void* numeric_subtree, double* ms, int n);
+
+/* Switches event-bracketing of the Schur-complement launches on or off. */
+void spral_ssids_b200_set_profile(int on);
+
+/* Measured FP64 tensor-pipe (DMMA) peak of `device` in TFLOP/s: a register
+ * resident mma.sync.m8n8k4.f64 issue loop; the roofline denominator. */
+double spral_ssids_b200_fp64_peak_tflops(int device);
 
 /* ------------------------------------------------------------------------ */
 /* Layer 2: host analyse helpers (C restatement of Fortran-only inputs)      */

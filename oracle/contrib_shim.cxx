@@ -57,6 +57,7 @@ void spral_ssids_contrib_free_dbl(void* const contrib) {
    auto* c = static_cast<spral_ssids_b200_contrib*>(contrib);
    switch(c->owner) {
    case 0: spral_ssids_cpu_subtree_free_contrib_dbl(c->posdef, c->owner_ptr); break;
+   case 2: break; /* memory owned by the test harness (a block received from another process) */
    case 1:
       if(gpu_free_contrib_hook) { gpu_free_contrib_hook(c->posdef, c->owner_ptr); break; }
       /* fallthrough */

@@ -14,12 +14,15 @@
  *   the contribution block is (m-n)^2, lower triangle valid.
  */
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <vector>
 #include "spral_ssids_b200.h"
 
 namespace b200 {
+
+extern std::atomic<long> g_launches;   // kernels launched (the gpu_launches figure of bench.py)
 
 constexpr int BS = 32;    // block column width (inner step)
 constexpr int PW = 256;   // outer panel width (a multiple of BS)

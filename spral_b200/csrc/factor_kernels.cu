@@ -34,6 +34,9 @@
 #include "device_utils.cuh"
 
 namespace b200 {
+#ifndef COUNT_LAUNCH
+#define COUNT_LAUNCH() (void)g_launches.fetch_add(1, std::memory_order_relaxed)
+#endif
 
 /* ------------------------------------------------------------------------ */
 /* A scatter (init of a front)                                               */
@@ -74,7 +77,7 @@ void launch_scatter_a(Front* fronts, const int2* work, int nwork, const int64_t*
       const int64_t* nptr, const int* node_of_front, const double* aval,
       const double* scaling, cudaStream_t s) {
    if (nwork == 0) return;
-   k_scatter_a<<<nwork, 256, 0, s>>>(fronts, work, nlist, nptr, node_of_front, aval, scaling);
+   k_scatter_a<<<nwork, 256, 0, s>>>(fronts, work, nlist, nptr, node_of_front, aval, scaling); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -127,7 +130,7 @@ void launch_assemble(Front* fronts, const AsmSrc* srcs, const int2* work, int nw
       bool to_contrib, bool use_atomics, cudaStream_t s) {
    if (nwork == 0) return;
    if (use_atomics) k_assemble<true><<<nwork, 256, 0, s>>>(fronts, srcs, work, to_contrib);
-   else k_assemble<false><<<nwork, 256, 0, s>>>(fronts, srcs, work, to_contrib);
+   else k_assemble<false><<<nwork, 256, 0, s>>>(fronts, srcs, work, to_contrib); COUNT_LAUNCH();
 }
 int assemble_cols_per_cta() { return ASM_COLS; }
 int scatter_chunk() { return SCATTER_CHUNK; }
@@ -164,7 +167,7 @@ k_delays(Front* fronts, const AsmSrc* srcs, const int2* work) {
 
 void launch_delays(Front* fronts, const AsmSrc* srcs, const int2* work, int nwork, cudaStream_t s) {
    if (nwork == 0) return;
-   k_delays<<<nwork, 128, 0, s>>>(fronts, srcs, work);
+   k_delays<<<nwork, 128, 0, s>>>(fronts, srcs, work); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -414,7 +417,7 @@ void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool n
       const FactorParams& prm, cudaStream_t s) {
    if (count == 0) return;
    if (posdef) k_diag<true><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
-   else k_diag<false><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
+   else k_diag<false><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -530,7 +533,7 @@ void launch_apply(Front* fronts, const RowTile* work, int nwork, bool posdef,
       const FactorParams& prm, cudaStream_t s) {
    if (nwork == 0) return;
    if (posdef) k_apply<true><<<nwork, RT, 0, s>>>(fronts, work, prm);
-   else k_apply<false><<<nwork, RT, 0, s>>>(fronts, work, prm);
+   else k_apply<false><<<nwork, RT, 0, s>>>(fronts, work, prm); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -605,7 +608,7 @@ k_commit(Front* fronts, const RowTile* work) {
 
 void launch_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s) {
    if (nwork == 0) return;
-   k_commit<<<nwork, RT, 0, s>>>(fronts, work);
+   k_commit<<<nwork, RT, 0, s>>>(fronts, work); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -694,7 +697,7 @@ void launch_swap(Front* fronts, const RowTile* work, int nwork, bool outer, cuda
    if (nwork == 0) return;
    int nslice = outer ? PW / BS : 1;
    for (int sl = 0; sl < nslice; ++sl)
-      k_swap<<<nwork, RT, 0, s>>>(fronts, work, outer ? 1 : 0, sl);
+      k_swap<<<nwork, RT, 0, s>>>(fronts, work, outer ? 1 : 0, sl); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -738,7 +741,7 @@ k_finalize(Front* fronts, const int* __restrict__ flist) {
 void launch_finalize(Front* fronts, const int* flist, int count, bool posdef, cudaStream_t s) {
    if (count == 0) return;
    if (posdef) k_finalize<true><<<count, 128, 0, s>>>(fronts, flist);
-   else k_finalize<false><<<count, 128, 0, s>>>(fronts, flist);
+   else k_finalize<false><<<count, 128, 0, s>>>(fronts, flist); COUNT_LAUNCH();
 }
 
 } // namespace b200

@@ -30,6 +30,9 @@
 #include "device_utils.cuh"
 
 namespace b200 {
+#ifndef COUNT_LAUNCH
+#define COUNT_LAUNCH() (void)g_launches.fetch_add(1, std::memory_order_relaxed)
+#endif
 
 namespace {
 
@@ -262,7 +265,49 @@ void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mod
    if (big_tiles)
       k_update<128, 2, 4><<<nwork, 256, update_smem_bytes<128>(), s>>>(fronts, work, (int)mode);
    else
-      k_update<64, 2, 2><<<nwork, 128, update_smem_bytes<64>(), s>>>(fronts, work, (int)mode);
+      k_update<64, 2, 2><<<nwork, 128, update_smem_bytes<64>(), s>>>(fronts, work, (int)mode); COUNT_LAUNCH();
 }
 
 } // namespace b200
+
+/* FP64 tensor-pipe peak of the device this runs on: a register-resident DMMA
+ * issue loop (no memory traffic).  Used by bench.py as the roofline
+ * denominator because MEASURED_PEAKS.json holds no FP64 figure. */
+namespace b200 {
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters) {
+   double acc[16][2];
+   for (int i = 0; i < 16; ++i) { acc[i][0] = threadIdx.x * 1e-9; acc[i][1] = i * 1e-9; }
+   double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+   for (int it = 0; it < iters; ++it) {
+      #pragma unroll
+      for (int i = 0; i < 16; ++i)
+         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                      : "+d"(acc[i][0]), "+d"(acc[i][1]) : "d"(a), "d"(b));
+   }
+   double s = 0;
+   for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+} // namespace b200
+
+extern "C" double spral_ssids_b200_fp64_peak_tflops(int device) {
+   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+   cudaDeviceProp p;
+   if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return -1.0;
+   const int blocks = p.multiProcessorCount * 2, iters = 20000;
+   double* out = nullptr;
+   if (cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double)) != cudaSuccess) return -1.0;
+   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+   double best = 0;
+   b200::k_dmma_peak<<<blocks, 256>>>(out, 200);
+   for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      b200::k_dmma_peak<<<blocks, 256>>>(out, iters);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      double tf = (double)blocks * 8 * iters * 16 * 512.0 / ms / 1e9;
+      if (tf > best) best = tf;
+   }
+   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+   return best;
+}

@@ -26,6 +26,9 @@
 #include <math_constants.h>
 
 namespace b200 {
+#ifndef COUNT_LAUNCH
+#define COUNT_LAUNCH() (void)g_launches.fetch_add(1, std::memory_order_relaxed)
+#endif
 
 namespace {
 
@@ -267,7 +270,7 @@ void fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nst
       double* x, int ldx, double* ywork, cudaStream_t s) {
    for (int st = 0; st < nsteps; ++st) {
       if (posdef) k_fwd_step<NR, true><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork);
-      else k_fwd_step<NR, false><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork);
+      else k_fwd_step<NR, false><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork); COUNT_LAUNCH();
    }
 }
 
@@ -275,9 +278,9 @@ template <int NR>
 void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
       const int* wbeg, int nsteps, bool posdef, double* x, int ldx, double* pbuf, cudaStream_t s) {
    for (int st = 0; st < nsteps; ++st) {
-      k_bwd_reduce<NR><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, pbuf);
+      k_bwd_reduce<NR><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, pbuf); COUNT_LAUNCH();
       if (posdef) k_bwd_diag<NR, true><<<count, 32, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf);
-      else k_bwd_diag<NR, false><<<count, 32, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf);
+      else k_bwd_diag<NR, false><<<count, 32, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf); COUNT_LAUNCH();
    }
 }
 
@@ -302,13 +305,13 @@ void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, 
 void launch_fwd_flush(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
       const double* ywork, cudaStream_t s) {
    if (count == 0) return;
-   k_fwd_flush<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx, ywork);
+   k_fwd_flush<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx, ywork); COUNT_LAUNCH();
 }
 
 void launch_diag_solve(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
       cudaStream_t s) {
    if (count == 0) return;
-   k_diag_solve<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx);
+   k_diag_solve<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx); COUNT_LAUNCH();
 }
 
 void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,

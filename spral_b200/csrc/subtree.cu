@@ -18,6 +18,7 @@
  * a grow-only pool that survives across factorisations.
  */
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -30,6 +31,8 @@
 namespace b200 {
 
 struct CudaError { cudaError_t code; };
+static bool g_profile = false;
+std::atomic<long> g_launches{0};      // incremented by every launch wrapper
 #define CUDA_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaError{e_}; } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -257,11 +260,19 @@ struct Numeric {
    /* external contribution staging (device copies owned by this object) */
    std::vector<void*> ext_allocs;
    double timings[8] = {0};
+   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+   /* profiling of the Schur-complement launches (enabled by spral_ssids_b200_set_profile) */
+   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+   double prof_flops = 0;
+   int n_launch = 0;
 
    ~Numeric() {
       if (!S) return;
       cudaSetDevice(S->device);
       if (stream) cudaStreamSynchronize(stream);
+      if (ev_begin) cudaEventDestroy(ev_begin);
+      if (ev_end) cudaEventDestroy(ev_end);
+      for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
       for (void* p : chunks) cudaFree(p);
       for (void* p : ext_allocs) cudaFree(p);
       cudaFree(d_fronts); cudaFree(d_sfronts); cudaFree(d_swork); cudaFree(d_wbeg); cudaFree(d_export);
@@ -400,6 +411,9 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    cudaStream_t s = N.stream;
    configure_update_kernels();
    auto t_begin = std::chrono::steady_clock::now();
+   CUDA_TRY(cudaEventCreate(&N.ev_begin));
+   CUDA_TRY(cudaEventCreate(&N.ev_end));
+   CUDA_TRY(cudaEventRecord(N.ev_begin, s));
 
    FactorParams prm{opt->u, opt->small, opt->action ? 1 : 0};
    if (nloc == 0) return;
@@ -684,6 +698,18 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       }
 
       /* ---- Schur complement, then the children's contributions to it ---- */
+      if (g_profile && !ctiles.empty()) {
+         cudaEvent_t a, b;
+         CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+         CUDA_TRY(cudaEventRecord(a, s));
+         launch_update(N.d_fronts, d_ctiles, (int)ctiles.size(), UPD_CONTRIB, big, s);
+         CUDA_TRY(cudaEventRecord(b, s));
+         N.prof_events.push_back({a, b});
+         for (int fi = f0; fi < f1; ++fi) {
+            double cm = F[fi].m - F[fi].n;
+            N.prof_flops += cm * (cm + 1) * F[fi].nelim;   // lower triangle, 2 flops per fma
+         }
+      } else
       launch_update(N.d_fronts, d_ctiles, (int)ctiles.size(), UPD_CONTRIB, big, s);
       for (int r = 0; r <= MAXRANK; ++r)
          if (d_post[r]) launch_assemble(N.d_fronts, d_srcs, d_post[r], (int)post[r].size(), true, r == MAXRANK, s);
@@ -742,8 +768,21 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       CUDA_TRY(cudaMemcpyAsync(N.d_wbeg, wbeg.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, s));
       CUDA_TRY(cudaStreamSynchronize(s));
    }
+   CUDA_TRY(cudaEventRecord(N.ev_end, s));
+   CUDA_TRY(cudaEventSynchronize(N.ev_end));
+   float ems = 0;
+   CUDA_TRY(cudaEventElapsedTime(&ems, N.ev_begin, N.ev_end));
    N.timings[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-   N.timings[5] = t_sync;
+   N.timings[1] = ems;                 // device time of the whole factorisation (CUDA events on its stream)
+   N.timings[5] = t_sync;              // host time spent waiting in the per-level syncs
+   N.timings[6] = (double)g_launches.exchange(0);   // kernels launched by this factorisation
+   if (g_profile) {
+      double tot = 0;
+      for (auto& e : N.prof_events) { float t = 0; cudaEventElapsedTime(&t, e.first, e.second); tot += t; }
+      N.timings[2] = tot;              // ms inside the Schur-complement (UPD_CONTRIB) launches
+      N.timings[3] = N.prof_flops;     // their algorithmic flops
+      N.timings[4] = (double)N.prof_events.size();
+   }
    *stats = st;
 }
 
@@ -1032,6 +1071,8 @@ void spral_ssids_gpu_symbolic_get_maps(const void* p, int* rlist_direct, int* nu
    if (level_list) std::copy(S.level_list.begin(), S.level_list.end(), level_list);
 }
 
+void spral_ssids_b200_set_profile(int on) { g_profile = (on != 0); }
+
 void spral_ssids_gpu_subtree_get_timings(const void* p, double* ms, int n) {
    const Numeric& N = *static_cast<const Numeric*>(p);
    for (int i = 0; i < n && i < 8; ++i) ms[i] = N.timings[i];
@@ -1052,3 +1093,75 @@ extern "C" void spral_ssids_b200_debug_front(const void* p, int node, int* sizes
    if (D && f.D) cudaMemcpy(D, f.D, (size_t)2 * f.n * sizeof(double), cudaMemcpyDeviceToHost);
    if (perm) cudaMemcpy(perm, f.perm, (size_t)f.n * sizeof(int), cudaMemcpyDeviceToHost);
 }
+
+/* ------------------------------------------------------------------------ */
+/* Cross-process hand-over of a contribution block (one process per GPU):    */
+/* the producer packs [val | delay_val | delay_perm] into one cudaMalloc'd   */
+/* block and publishes its CUDA IPC handle; the consumer maps it and pulls   */
+/* it over NVLink with a peer copy.  Replaces transfer_contrib's D2H copy    */
+/* (src/ssids/gpu/factor.f90:155-221).                                       */
+/* ------------------------------------------------------------------------ */
+extern "C" {
+
+/* Packs the root contribution of `numeric_subtree` into a fresh device block
+ * owned by the numeric object.  Layout (bytes): val n*n doubles (ld n), then
+ * delay_val (ndelay+n)*ndelay doubles (ld ndelay+n), then delay_perm ndelay
+ * ints.  handle receives the 64-byte cudaIpcMemHandle_t.  Returns 0 or the
+ * raw cudaError_t. */
+int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned char* handle,
+      int* n, int* ndelay, int64_t* bytes, void** device_block) {
+   Numeric& N = *static_cast<Numeric*>(numeric_subtree);
+   const Symbolic& S = *N.S;
+   cudaSetDevice(S.device);
+   *n = 0; *ndelay = 0; *bytes = 0; *device_block = nullptr;
+   if (N.export_front < 0) return 0;
+   const Front& f = N.h_fronts[N.export_front];
+   int cn = f.m0 - f.n0, nd = f.n - f.nelim;
+   size_t rows = (size_t)nd + cn;
+   size_t b_val = (size_t)cn * cn * sizeof(double), b_del = rows * nd * sizeof(double);
+   size_t total = b_val + b_del + (size_t)nd * sizeof(int);
+   char* blk = nullptr;
+   cudaError_t e = cudaMalloc((void**)&blk, std::max<size_t>(total, 256));
+   if (e != cudaSuccess) return (int)e;
+   N.ext_allocs.push_back(blk);
+   if (cn) e = cudaMemcpy2D(blk, (size_t)cn * sizeof(double), f.C, (size_t)f.ldc * sizeof(double),
+                            (size_t)cn * sizeof(double), cn, cudaMemcpyDeviceToDevice);
+   if (e == cudaSuccess && nd)
+      e = cudaMemcpy2D(blk + b_val, rows * sizeof(double), f.L + (size_t)f.nelim * (f.ldl + 1),
+                       (size_t)f.ldl * sizeof(double), rows * sizeof(double), nd, cudaMemcpyDeviceToDevice);
+   if (e == cudaSuccess && nd)
+      e = cudaMemcpy(blk + b_val + b_del, f.perm + f.nelim, (size_t)nd * sizeof(int), cudaMemcpyDeviceToDevice);
+   if (e != cudaSuccess) return (int)e;
+   cudaIpcMemHandle_t h;
+   e = cudaIpcGetMemHandle(&h, blk);
+   if (e != cudaSuccess) return (int)e;
+   std::memcpy(handle, &h, sizeof(h));
+   *n = cn; *ndelay = nd; *bytes = (int64_t)total; *device_block = blk;
+   return 0;
+}
+
+/* Consumer side: maps the producer's block and copies `bytes` into dst (a
+ * device pointer of the calling process' current device) over NVLink. */
+int spral_ssids_b200_ipc_pull(const unsigned char* handle, int64_t bytes, void* dst) {
+   cudaIpcMemHandle_t h;
+   std::memcpy(&h, handle, sizeof(h));
+   void* src = nullptr;
+   cudaError_t e = cudaIpcOpenMemHandle(&src, h, cudaIpcMemLazyEnablePeerAccess);
+   if (e != cudaSuccess) return (int)e;
+   e = cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault);
+   cudaError_t e2 = cudaIpcCloseMemHandle(src);
+   return (int)(e != cudaSuccess ? e : e2);
+}
+
+int spral_ssids_b200_copy_to_host(void* dst, const void* src, int64_t bytes) {
+   return (int)cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost);
+}
+
+void* spral_ssids_b200_device_alloc(int64_t bytes) {
+   void* p = nullptr;
+   if (cudaMalloc(&p, (size_t)std::max<int64_t>(bytes, 256)) != cudaSuccess) return nullptr;
+   return p;
+}
+void spral_ssids_b200_device_free(void* p) { if (p) cudaFree(p); }
+
+} /* extern "C" */

@@ -1,0 +1,499 @@
+"""One process per GPU: the part-level scheduler of ssids_factor / ssids_solve.
+
+Mirrors fkeep%inner_factor / inner_solve (src/ssids/fkeep.F90:61-323 of the
+reference), where the reference runs one OpenMP thread per GPU inside one
+process and hands contribution blocks through host memory, this driver runs
+one PROCESS per GPU (torchrun) and
+
+  * every part of the subtree partition (find_subtree_partition, anal.F90:289-464)
+    is owned by exactly one rank; the parts the reference would leave to the CPU
+    ("all-region" parts, exec_loc = -1) are given to the rank of their heaviest
+    child, so the root of the tree is factorised on a GPU too;
+  * a contribution block crosses ranks only where a subtree feeds an ancestor on
+    another GPU: the producer publishes a CUDA IPC handle in the rendezvous
+    store, the consumer pulls the block over NVLink (peer copy) when it reaches
+    the parent part.  Nothing blocks the producer, so the schedule cannot
+    deadlock: every rank walks its parts in increasing (post)order and only ever
+    waits for a lower-numbered part;
+  * the solves exchange, per cross-rank edge, the update a part makes to the
+    rows of its ancestors (forward) and the ancestors' solution on those rows
+    (backward); the final solution is one all-reduce.
+
+The same driver runs on CPU for the world_size-2 gloo tests with the reference
+CPU engine standing in for the GPU engine and the store carrying the payload.
+"""
+import ctypes as C
+import pickle
+
+import numpy as np
+
+from . import _lib
+from ._lib import Contrib, Options
+from .ssids import Analysis, SymbolicSubtree, free_contrib
+
+
+class DistContext:
+    def __init__(self, world=1, rank=0, local_rank=0, engine="gpu", store=None, tag="ssids"):
+        self.world, self.rank, self.local_rank, self.engine = world, rank, local_rank, engine
+        self._store, self.tag, self.epoch = store, tag, 0
+
+    @property
+    def store(self):
+        if self._store is None:
+            import torch.distributed as dist
+            self._store = dist.distributed_c10d._get_default_store()
+        return self._store
+
+
+# --------------------------------------------------------------------------
+# ownership of parts
+# --------------------------------------------------------------------------
+
+def part_graph(a):
+    """consumer[p] = part that receives p's contribution (or -1); children[q]."""
+    nparts = a.nparts
+    consumer = [-1] * nparts
+    for p in range(nparts):
+        idx = int(a.contrib_idx[p])
+        if idx > nparts:
+            continue
+        for q in range(p + 1, nparts):
+            if int(a.contrib_ptr[q]) <= idx < int(a.contrib_ptr[q + 1]):
+                consumer[p] = q
+                break
+    children = [[] for _ in range(nparts)]
+    for p, q in enumerate(consumer):
+        if q >= 0:
+            children[q].append(p)
+    return consumer, children
+
+
+def part_flops(a):
+    fl = np.zeros(a.nparts)
+    for p in range(a.nparts):
+        for node in range(int(a.part[p]), int(a.part[p + 1])):
+            m = int(a.rptr[node] - a.rptr[node - 1])
+            nc = int(a.sptr[node] - a.sptr[node - 1])
+            j = np.arange(nc, dtype=np.float64)
+            fl[p] += float(((m - j) ** 2).sum())
+    return fl
+
+
+def assign_ranks(a, world):
+    """rank_of[p].  Leaf parts: the GPU chosen by the analyse phase (exec_loc,
+    anal.F90:496-501).  All-region parts (exec_loc = -1): the rank of the child
+    whose subtree carries the most flops (it finishes last, so its block never
+    has to travel)."""
+    consumer, children = part_graph(a)
+    fl = part_flops(a)
+    sub = fl.copy()
+    rank_of = [0] * a.nparts
+    for p in range(a.nparts):
+        loc = int(a.exec_loc[p])
+        for c in children[p]:
+            sub[p] += sub[c]
+        if loc >= 2:
+            rank_of[p] = (loc - 2) % world
+        elif children[p]:
+            rank_of[p] = rank_of[max(children[p], key=lambda c: sub[c])]
+        else:
+            rank_of[p] = 0
+    return rank_of
+
+
+class DistAkeep:
+    def __init__(self, analysis, subtrees, rank_of, consumer, children):
+        self.analysis, self.subtrees = analysis, subtrees
+        self.rank_of, self.consumer, self.children = rank_of, consumer, children
+
+
+def analyse(ctx, n, ptr, row, order=None, nemin=32, options=None, **kw):
+    """ssids_analyse on every rank (deterministic, replicated), symbolic subtrees
+    only for the parts this rank owns."""
+    a = Analysis(n, ptr, row, order=order, nemin=nemin, ngpu=ctx.world, **kw)
+    rank_of = assign_ranks(a, ctx.world)
+    consumer, children = part_graph(a)
+    subtrees = []
+    for p in range(a.nparts):
+        if rank_of[p] != ctx.rank:
+            subtrees.append(None)
+        elif ctx.engine == "gpu":
+            subtrees.append(SymbolicSubtree(a, p, device=ctx.local_rank, options=options))
+        else:
+            subtrees.append(("oracle", p))
+    return DistAkeep(a, subtrees, rank_of, consumer, children)
+
+
+# --------------------------------------------------------------------------
+# transport of contribution blocks
+# --------------------------------------------------------------------------
+
+def _key(ctx, kind, p):
+    return f"{ctx.tag}/{ctx.epoch}/{kind}/{p}"
+
+
+def _contrib_rlist(a, p):
+    """Global row indices of part p's root contribution (host, from the replicated analysis)."""
+    root = int(a.part[p + 1]) - 1
+    lo = int(a.rptr[root - 1]) - 1 + int(a.sptr[root] - a.sptr[root - 1])
+    hi = int(a.rptr[root]) - 1
+    return np.ascontiguousarray(a.rlist[lo:hi], dtype=np.int32)
+
+
+def publish_contrib(ctx, ak, p, ns):
+    """Producer side of a cross-rank edge."""
+    if ctx.engine == "gpu":
+        lib = _lib.load()
+        handle = (C.c_ubyte * 64)()
+        n, nd, nbytes, blk = C.c_int(), C.c_int(), C.c_int64(), C.c_void_p()
+        rc = lib.spral_ssids_gpu_subtree_export_contrib_ipc(ns._h, handle, C.byref(n), C.byref(nd),
+                                                            C.byref(nbytes), C.byref(blk))
+        if rc != 0:
+            raise RuntimeError(f"export_contrib_ipc failed: cudaError {rc}")
+        meta = dict(kind="ipc", handle=bytes(handle), n=n.value, ndelay=nd.value, bytes=nbytes.value)
+    else:
+        c = ns.get_contrib()
+        n, nd = c.n, c.ndelay
+
+        def arr(ptr, count, ctype):
+            if not ptr or count == 0:
+                return None
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), (count,)).copy()
+        val = arr(c.val, c.ldval * n, C.c_double)
+        rows = nd + n
+        dval = arr(c.delay_val, c.lddelay * nd, C.c_double)
+        meta = dict(kind="host", n=n, ndelay=nd, ldval=c.ldval, lddelay=c.lddelay, val=val, dval=dval,
+                    dperm=arr(c.delay_perm, nd, C.c_int))
+    ctx.store.set(_key(ctx, "contrib", p), pickle.dumps(meta))
+    return meta
+
+
+class _Fetched:
+    """Keeps the memory behind a fetched Contrib alive / frees the device block."""
+
+    def __init__(self, contrib, keep, block=None):
+        self.contrib, self.keep, self.block = contrib, keep, block
+
+    def release(self):
+        if self.block:
+            _lib.load().spral_ssids_b200_device_free(self.block)
+            self.block = None
+
+
+def fetch_contrib(ctx, ak, p, posdef):
+    """Consumer side: waits for part p's block and brings it to this rank."""
+    key = _key(ctx, "contrib", p)
+    ctx.store.wait([key])
+    meta = pickle.loads(ctx.store.get(key))
+    a = ak.analysis
+    rl = _contrib_rlist(a, p)
+    n, nd = meta["n"], meta["ndelay"]
+    c = Contrib()
+    c.n, c.ndelay, c.posdef, c.owner, c.owner_ptr, c.ready = n, nd, posdef, 2, None, 1
+    c.rlist = rl.ctypes.data
+    if meta["kind"] == "ipc":
+        lib = _lib.load()
+        blk = lib.spral_ssids_b200_device_alloc(meta["bytes"])
+        if not blk:
+            raise MemoryError("device_alloc failed")
+        handle = (C.c_ubyte * 64).from_buffer_copy(meta["handle"])
+        rc = lib.spral_ssids_b200_ipc_pull(handle, meta["bytes"], blk)
+        if rc != 0:
+            raise RuntimeError(f"ipc_pull failed: cudaError {rc}")
+        b_val = n * n * 8
+        rows = nd + n
+        c.val, c.ldval = (blk if n else None), n
+        c.delay_val = blk + b_val if nd else None
+        c.lddelay = rows
+        c.delay_perm = blk + b_val + rows * nd * 8 if nd else None
+        c.device = ctx.local_rank
+        return _Fetched(c, [rl], blk)
+    keep = [rl, meta["val"], meta["dval"], meta["dperm"]]
+    c.val = meta["val"].ctypes.data if meta["val"] is not None else None
+    c.ldval = meta["ldval"]
+    c.delay_val = meta["dval"].ctypes.data if meta["dval"] is not None else None
+    c.lddelay = meta["lddelay"]
+    c.delay_perm = meta["dperm"].ctypes.data if meta["dperm"] is not None else None
+    c.device = -1
+    return _Fetched(c, keep)
+
+
+# --------------------------------------------------------------------------
+# factor
+# --------------------------------------------------------------------------
+
+class DistFkeep:
+    def __init__(self, ak, posdef, numeric, inform, ext_rows, scaling, epoch):
+        self.akeep, self.posdef, self.numeric, self.inform = ak, posdef, numeric, inform
+        self.ext_rows, self.scaling, self.epoch = ext_rows, scaling, epoch
+
+
+def _new_inform(a):
+    return dict(flag=0, num_delay=0, num_factor=0, num_flops=0, num_neg=0, num_two=0, maxfront=0,
+                maxsupernode=0, matrix_rank=0, num_zero=0, not_first_pass=0, not_second_pass=0, cuda_error=0)
+
+
+def _accumulate(inform, st):
+    """cpu_copy_stats_out (src/ssids/cpu/cpu_iface.f90:74-94)."""
+    if st.flag < 0:
+        inform["flag"] = min(inform["flag"], st.flag) if inform["flag"] < 0 else st.flag
+        inform["cuda_error"] = getattr(st, "cuda_error", 0)
+        return
+    if inform["flag"] >= 0:
+        inform["flag"] = max(inform["flag"], st.flag)
+    for k in ("num_delay", "num_factor", "num_flops", "num_neg", "num_two", "num_zero",
+              "not_first_pass", "not_second_pass"):
+        inform[k] += getattr(st, k)
+    inform["maxfront"] = max(inform["maxfront"], st.maxfront)
+    inform["maxsupernode"] = max(inform["maxsupernode"], st.maxsupernode)
+
+
+def factor(ctx, ak, posdef, val, options=None, scaling=None):
+    """fkeep%inner_factor: this rank's parts in postorder; `val` is a numpy array or
+    a raw (host or device) pointer to the values of A."""
+    a = ak.analysis
+    ctx.epoch += 1
+    sc = None
+    if scaling is not None:
+        sc = np.ascontiguousarray(np.asarray(scaling, dtype=np.float64)[a.invp - 1])
+    nparts = a.nparts
+    local = {}                        # part -> Contrib produced on this rank (device resident)
+    numeric = [None] * nparts
+    ext_rows = [None] * nparts        # rows of x outside the part that it touches (solve exchange)
+    inform = _new_inform(a)
+    for p in range(nparts):
+        if ak.rank_of[p] != ctx.rank:
+            continue
+        cc, fetched = [], []
+        for c_part in ak.children[p]:
+            if ak.rank_of[c_part] == ctx.rank:
+                cc.append(local.pop(c_part))
+            else:
+                f = fetch_contrib(ctx, ak, c_part, posdef)
+                fetched.append(f)
+                cc.append(f.contrib)
+        # children[] is ordered by part; the slots contrib_ptr[p].. follow the same order
+        if ctx.engine == "gpu":
+            ns = ak.subtrees[p].factor(posdef, val, cc, options, sc)
+            st = ns.stats
+        else:
+            import oracle_ref
+            ns = oracle_ref.RefSubtree(a, p, posdef, val, cc, options, sc)
+            st = ns.stats
+        numeric[p] = ns
+        for c in cc:
+            if c.owner == 1:
+                free_contrib(c)
+        for f in fetched:
+            f.release()
+        _accumulate(inform, st)
+        if st.flag < 0:
+            break
+        q = ak.consumer[p]
+        if q >= 0:
+            if ctx.engine == "gpu":
+                c = ns.get_contrib(device_resident=True)
+            else:
+                c = ns.get_contrib()
+            rows = [_contrib_rlist(a, p)]
+            if c.ndelay:
+                if c.device >= 0:
+                    dp = np.empty(c.ndelay, dtype=np.int32)
+                    rc = _lib.load().spral_ssids_b200_copy_to_host(dp.ctypes.data, c.delay_perm, 4 * c.ndelay)
+                    if rc != 0:
+                        raise RuntimeError(f"copy_to_host failed: cudaError {rc}")
+                else:
+                    dp = np.ctypeslib.as_array(C.cast(c.delay_perm, C.POINTER(C.c_int)), (c.ndelay,)).copy()
+                rows.append(dp)
+            ext_rows[p] = np.concatenate(rows).astype(np.int64) - 1
+            if ak.rank_of[q] == ctx.rank:
+                local[p] = c
+            else:
+                publish_contrib(ctx, ak, p, ns)
+                ctx.store.set(_key(ctx, "ext_rows", p), pickle.dumps(ext_rows[p]))
+    return DistFkeep(ak, posdef, numeric, finish_inform(a, inform), ext_rows, sc, ctx.epoch)
+
+
+def reduce_inform(ctx, inform):
+    """inform%reduce over ranks (src/ssids/inform.f90:180-215)."""
+    a_rank = None
+    if ctx.world == 1:
+        out = dict(inform)
+    else:
+        import torch
+        import torch.distributed as dist
+        dev = "cuda" if ctx.engine == "gpu" else "cpu"
+        keys_sum = ("num_delay", "num_factor", "num_flops", "num_neg", "num_two", "num_zero",
+                    "not_first_pass", "not_second_pass")
+        t = torch.tensor([inform[k] for k in keys_sum], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        out = dict(inform)
+        for k, v in zip(keys_sum, t.tolist()):
+            out[k] = int(v)
+        t = torch.tensor([inform["maxfront"], inform["maxsupernode"], inform["flag"], -inform["flag"]],
+                         dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mx = t.tolist()
+        out["maxfront"], out["maxsupernode"] = int(mx[0]), int(mx[1])
+        out["flag"] = int(-mx[3]) if mx[3] > 0 else int(mx[2])       # any error wins, else largest warning
+    out["matrix_rank"] = inform.get("n_vars", 0) - out["num_zero"] if "n_vars" in inform else out.get("matrix_rank", 0)
+    return out
+
+
+def finish_inform(a, inform):
+    inform = dict(inform)
+    inform["n_vars"] = int(a.sptr[a.nnodes]) - 1
+    inform["matrix_rank"] = inform["n_vars"] - inform["num_zero"]     # this rank's view; reduce_inform() completes it
+    return inform
+
+
+def free(fk):
+    for ns in fk.numeric:
+        if ns is not None:
+            ns.close()
+    fk.numeric = [None] * len(fk.numeric)
+
+
+# --------------------------------------------------------------------------
+# solve
+# --------------------------------------------------------------------------
+
+def _engine_solve(ctx, ns, which, X, nrhs, n):
+    """X: torch tensor (nrhs, n) contiguous == column-major n x nrhs."""
+    if ctx.engine == "gpu":
+        getattr(ns, f"solve_{which}")(X.data_ptr(), nrhs, n)
+    else:
+        f = getattr(__import__("oracle_ref").load(), f"spral_ssids_cpu_subtree_solve_{which}_dbl")
+        rc = f(ns.posdef, ns.h, nrhs, C.c_void_p(X.data_ptr()), n)
+        assert rc == 0
+
+
+def _send(ctx, kind, p, t):
+    ctx.store.set(_key(ctx, kind, p), pickle.dumps(t.cpu().numpy()))
+
+
+def _recv(ctx, kind, p, dev):
+    import torch
+    key = _key(ctx, kind, p)
+    ctx.store.wait([key])
+    return torch.from_numpy(pickle.loads(ctx.store.get(key))).to(dev)
+
+
+def solve(ctx, fk, x, job=0):
+    """ssids_solve / inner_solve_cpu (src/ssids/fkeep.F90:234-323) across ranks.
+    x: (n,) or (n, nrhs) numpy, same on every rank; returns the solution on every rank."""
+    import torch
+    a = fk.akeep.analysis
+    n = a.n
+    dev = torch.device("cuda", ctx.local_rank) if ctx.engine == "gpu" else torch.device("cpu")
+    x = np.asarray(x, dtype=np.float64)
+    one = x.ndim == 1
+    Xh = np.asfortranarray(x.reshape(n, -1))
+    nrhs = Xh.shape[1]
+    x2 = np.ascontiguousarray(Xh[a.invp - 1, :].T)            # (nrhs, n): pivot order (fkeep.F90:252-266)
+    if fk.scaling is not None and job in (0, 1):
+        x2 *= fk.scaling[None, :]
+    X = solve_pivot_order(ctx, fk, torch.from_numpy(x2).to(dev), job)
+    x2 = X.cpu().numpy()
+    if fk.scaling is not None and job in (0, 3, 4):
+        x2 = x2 * fk.scaling[None, :]
+    out = np.empty((n, nrhs), order="F")
+    out[a.invp - 1, :] = x2.T                                    # fkeep.F90:300-315
+    return out[:, 0] if one else out
+
+
+def solve_pivot_order(ctx, fk, X, job=0):
+    """The part-level sweeps on a resident right-hand side.  X: torch tensor of
+    shape (nrhs, n), contiguous (== column-major n x nrhs), in pivot order and
+    already scaled; on the GPU engine it lives in HBM and never leaves it."""
+    import torch
+    ak = fk.akeep
+    a = ak.analysis
+    n = a.n
+    nrhs = X.shape[0]
+    dev = X.device
+    ctx.epoch += 1
+    nparts = a.nparts
+    mine = [p for p in range(nparts) if ak.rank_of[p] == ctx.rank]
+    ext = {}
+    fkeys = _Epoch(ctx, fk.epoch)
+
+    def rows_of(p):
+        if p not in ext:
+            r = fk.ext_rows[p]
+            if r is None:                                        # produced on another rank
+                key = _key(fkeys, "ext_rows", p)
+                ctx.store.wait([key])
+                r = pickle.loads(ctx.store.get(key))
+                fk.ext_rows[p] = r
+            ext[p] = torch.from_numpy(np.asarray(r, dtype=np.int64)).to(dev)
+        return ext[p]
+
+    delta = {}
+    if job in (0, 1):                                            # forward
+        for p in mine:
+            q = ak.consumer[p]
+            E = rows_of(p) if q >= 0 else None
+            if E is not None:
+                saved = X[:, E].clone()
+                X[:, E] = 0.0
+            for c in ak.children[p]:
+                d = delta.pop(c) if ak.rank_of[c] == ctx.rank else _recv(ctx, "fwd", c, dev)
+                X[:, rows_of(c)] += d
+            _engine_solve(ctx, fk.numeric[p], "fwd", X, nrhs, n)
+            if E is not None:
+                d = X[:, E].clone()
+                X[:, E] = saved
+                if ak.rank_of[q] == ctx.rank:
+                    delta[p] = d
+                else:
+                    _send(ctx, "fwd", p, d)
+    if job == 2:
+        for p in mine:
+            _engine_solve(ctx, fk.numeric[p], "diag", X, nrhs, n)
+    if job in (0, 3, 4):                                         # backward
+        vals = {}
+        which = "bwd" if job == 3 else "diag_bwd"
+        for p in reversed(mine):
+            q = ak.consumer[p]
+            if q >= 0:
+                E = rows_of(p)
+                v = vals.pop(p) if ak.rank_of[q] == ctx.rank else _recv(ctx, "bwd", p, dev)
+                saved = X[:, E].clone()
+                X[:, E] = v
+            _engine_solve(ctx, fk.numeric[p], which, X, nrhs, n)
+            for c in ak.children[p]:
+                v = X[:, rows_of(c)].clone()
+                if ak.rank_of[c] == ctx.rank:
+                    vals[c] = v
+                else:
+                    _send(ctx, "bwd", c, v)
+            if q >= 0:
+                X[:, E] = saved
+    # every rank holds the final values of the variables eliminated in its own parts
+    if ctx.world > 1:
+        import torch.distributed as dist
+        mask = torch.zeros(n, dtype=torch.float64, device=dev)
+        for p in mine:                                           # increasing order
+            lo = int(a.sptr[int(a.part[p]) - 1]) - 1
+            hi = int(a.sptr[int(a.part[p + 1]) - 1]) - 1
+            mask[lo:hi] = 1.0
+            for c in ak.children[p]:                             # delays received are eliminated here
+                mask[rows_of(c)[_ncontrib(a, c):]] = 1.0
+            if ak.consumer[p] >= 0:                              # delays handed on are not
+                mask[rows_of(p)[_ncontrib(a, p):]] = 0.0
+        X = X * mask[None, :]
+        dist.all_reduce(X, op=dist.ReduceOp.SUM)
+    return X
+
+
+def _ncontrib(a, p):
+    root = int(a.part[p + 1]) - 1
+    return int(a.rptr[root] - a.rptr[root - 1]) - int(a.sptr[root] - a.sptr[root - 1])
+
+
+class _Epoch:
+    """A view of the context pinned to another epoch (keys of the factor call)."""
+
+    def __init__(self, ctx, epoch):
+        self.tag, self.epoch = ctx.tag, epoch

@@ -1,0 +1,14 @@
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+# the reference CPU engine needs these before libgomp starts (src/ssids/ssids.f90:1448-1452)
+os.environ.setdefault("OMP_CANCELLATION", "TRUE")
+os.environ.setdefault("OMP_PROC_BIND", "TRUE")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")

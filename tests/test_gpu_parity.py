@@ -1,0 +1,353 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA engine, called through
+the C ABI (include/spral_ssids_b200.h), against the reference's own CPU engine
+(oracle/_ref) on identical matrices and the identical symbolic analysis.
+
+Bars (BASELINE.json north_star):
+  * extend-add index maps and level schedule: bit-exact (vs oracle/index_maps.py)
+  * inertia (num_neg) and matrix rank: identical
+  * num_factor / num_flops: identical whenever neither engine delays a pivot
+  * scaled backward error (driver/spral_ssids.F90:419-480): <= BWD_FACTOR x the
+    reference's own error on the same matrix, and < the reference test-suite's
+    tolerance 5e-11 (tests/ssids/ssids.f90:28); <= 1e-14 after one step of
+    iterative refinement
+  * delayed pivots: |gpu - ref| <= DELAY_ABS + DELAY_REL * ref (the engines
+    choose pivots in different block shapes, so counts are not identical)
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle_ref
+from conftest import ROOT
+import spral_b200 as sb
+from spral_b200 import matrices as M, _lib
+from spral_b200.ssids import Analysis
+
+pytestmark = pytest.mark.gpu
+
+BWD_FACTOR = 10.0
+BWD_ABS = 2e-15
+DELAY_ABS, DELAY_REL = 8, 0.25
+REF_TOL = 5e-11
+
+sys_path_index_maps = os.path.join(ROOT, "oracle")
+import sys
+if sys_path_index_maps not in sys.path:
+    sys.path.insert(0, sys_path_index_maps)
+import index_maps  # noqa: E402
+
+
+def _check(gen, posdef, nrhs=1, options=None, scaling=None, **akw):
+    n, ptr, row, val = gen()
+    ak = sb.analyse(n, ptr, row, options=options, **akw)
+    a = ak.analysis
+    A = M.to_scipy(n, ptr, row, val)
+    rng = np.random.default_rng(5)
+    X = np.asfortranarray(rng.uniform(-1, 1, size=(n, nrhs)))
+    X[:, 0] = 1.0                                   # b = A*1 as driver/spral_ssids.F90:73-85
+    B = np.asfortranarray(A @ X)
+    fk = sb.factor(ak, posdef, val, options=options, scaling=scaling)
+    g = fk.inform
+    assert g["flag"] >= 0, g
+    Xg = sb.solve(fk, B)
+    parts, r, sc = oracle_ref.ref_factor(a, posdef, val, options=options, scaling=scaling)
+    Xr = oracle_ref.ref_solve(a, parts, posdef, B, sc)
+    for p in parts:
+        p.close()
+    bg, br = oracle_ref.backward_error(A, Xg, B), oracle_ref.backward_error(A, Xr, B)
+    assert g["num_neg"] == r["num_neg"]
+    assert g["matrix_rank"] == r["matrix_rank"]
+    assert g["maxfront"] >= a.maxfront
+    if g["num_delay"] == 0 and r["num_delay"] == 0:
+        assert g["num_factor"] == r["num_factor"] == a.num_factor
+        assert g["num_flops"] == r["num_flops"] == a.num_flops
+    assert abs(g["num_delay"] - r["num_delay"]) <= DELAY_ABS + DELAY_REL * r["num_delay"], (g["num_delay"], r["num_delay"])
+    assert bg < REF_TOL
+    assert bg <= BWD_FACTOR * br + BWD_ABS, (bg, br)
+    # one step of iterative refinement reaches 1e-14
+    R = B - A @ Xg
+    Xg2 = Xg + sb.solve(fk, np.asfortranarray(R))
+    assert oracle_ref.backward_error(A, Xg2, B) <= 1e-14
+    return ak, fk, A, g, r
+
+
+CASES = [
+    ("example_5x5", M.example_5x5, False, 1),
+    ("lap2d_100_cfg1", lambda: M.laplacian_2d_5pt(100), True, 1),       # BASELINE config 1
+    ("lap2d_100_indef", lambda: M.laplacian_2d_5pt(100), False, 2),
+    ("lap3d_20", lambda: M.laplacian_3d_7pt(20), True, 9),
+    ("st27_12_s13", lambda: M.stencil_3d_27pt(12, shift=13.0), False, 3),
+    ("st27_20_s13", lambda: M.stencil_3d_27pt(20, shift=13.0), False, 5),
+    ("st27_16_s26", lambda: M.stencil_3d_27pt(16, shift=26.5), False, 1),
+    ("kkt_2000", lambda: M.kkt_saddle(2000), False, 4),
+    ("kkt_6000", lambda: M.kkt_saddle(6000), False, 1),
+    ("lap3d_7x9x30", lambda: M.laplacian_3d_7pt(7, 9, 30), True, 1),    # ragged
+]
+
+
+@pytest.mark.parametrize("name,gen,posdef,nrhs", CASES, ids=[c[0] for c in CASES])
+def test_factor_solve_parity(name, gen, posdef, nrhs):
+    _check(gen, posdef, nrhs)
+
+
+def test_golden_stats_match_gpu():
+    """Committed reference statistics (tests/golden/oracle_stats.json)."""
+    import make_golden
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_stats.json")))
+    for name, exp in gold.items():
+        gen, posdef = make_golden.CASES[name]
+        n, ptr, row, val = gen()
+        ak = sb.analyse(n, ptr, row)
+        fk = sb.factor(ak, posdef, val)
+        g = fk.inform
+        assert ak.analysis.nnodes == exp["nnodes"]
+        assert g["num_neg"] == (0 if posdef else exp["num_neg"])
+        assert g["matrix_rank"] == exp["matrix_rank"]
+        if g["num_delay"] == 0 and exp["num_delay"] == 0:
+            assert (g["num_factor"], g["num_flops"]) == (exp["num_factor"], exp["num_flops"])
+
+
+def _dense(A):
+    n, ptr, row, val = M._lower_csc_keep_zeros(sp.csc_matrix(A))
+    return n, ptr, row, val
+
+
+def _sym(rng, n):
+    A = rng.uniform(-1, 1, (n, n))
+    return (A + A.T) / 2
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 100, 257, 300, 600])
+def test_dense_fronts(n):
+    """One dense front (the reference's kernel tests factor random dense
+    matrices: tests/ssids/kernels/ldlt_app.cxx:373-450): sizes around the block
+    (32) and panel (256) boundaries."""
+    rng = np.random.default_rng(n)
+    A = _sym(rng, n)
+    order = np.arange(1, n + 1, dtype=np.int32)
+    _check(lambda: _dense(A), False, 2, order=order)
+
+
+@pytest.mark.parametrize("kind,n", [("smalllead", 64), ("smalllead", 300), ("smalllead", 600),
+                                    ("saddle", 100), ("saddle", 300), ("saddle", 600),
+                                    ("arrow", 200), ("arrow", 700)])
+def test_doctored_matrices_force_delays(kind, n):
+    """Matrices doctored to make pivots fail (as tests/ssids/kernels/ldlt_app.cxx:104-130)."""
+    rng = np.random.default_rng(7 * n)
+    A = _sym(rng, n)
+    k = n // 3
+    akw = dict(order=np.arange(1, n + 1, dtype=np.int32))
+    if kind == "smalllead":
+        A[:k, :k] *= 1e-6
+    elif kind == "saddle":
+        A[:k, :k] = 0.0
+    else:
+        k = n // 2
+        A[:k, :k] = np.diag(np.diag(A[:k, :k])) * 1e-8
+        akw["nemin"] = 1
+    ak, fk, As, g, r = _check(lambda: _dense(A), False, 1, **akw)
+    assert g["not_first_pass"] > 0          # the failure path was really exercised
+
+
+def test_index_maps_bit_exact():
+    """rlist_direct and the level sets built by the symbolic constructor equal
+    the restated reference algorithms (gpu/subtree.f90:204-234, gpu/factor.f90:824-879)."""
+    n, ptr, row, val = M.stencil_3d_27pt(14, shift=13.0)
+    for ngpu in (1, 4):
+        ak = sb.analyse(n, ptr, row, ngpu=ngpu, devices=[0] * ngpu)
+        a = ak.analysis
+        for p, st in enumerate(ak.subtrees):
+            nn, spar, rp, rl, ncol = index_maps.part_view(a.sptr, a.sparent, a.rptr, a.rlist, st.sa, st.en)
+            rd, lptr, llist = st.maps()
+            exp = index_maps.build_rlist_direct(a.n, nn, spar, rp, rl, ncol)
+            mask = exp >= 0
+            assert np.array_equal(rd[mask], exp[mask])
+            nl, elptr, ellist = index_maps.assign_nodes_to_levels(nn, spar)
+            assert len(lptr) == nl + 1
+            assert np.array_equal(lptr, elptr)
+            assert np.array_equal(llist, ellist)
+
+
+def test_multi_part_contributions_between_parts():
+    """Subtree partition for 2/4/8 'GPUs' (all mapped to device 0): contribution
+    blocks and delays handed part to part, device resident and via host copies."""
+    gen = lambda: M.stencil_3d_27pt(16, shift=13.0)
+    for ngpu in (2, 4, 8):
+        ak, fk, A, g, r = _check(gen, False, 2, ngpu=ngpu, devices=[0] * ngpu)
+        assert ak.analysis.nparts > 1
+    n, ptr, row, val = gen()
+    ak = sb.analyse(n, ptr, row, ngpu=4, devices=[0] * 4)
+    fk = sb.factor(ak, False, val, device_contrib=False)       # reference convention: host contribution blocks
+    A = M.to_scipy(n, ptr, row, val)
+    b = A @ np.ones(n)
+    x = sb.solve(fk, b)
+    assert oracle_ref.backward_error(A, x, b) < 1e-11
+
+
+def test_mixed_cpu_reference_part_feeds_gpu_part():
+    """A leaf part factorised by the reference CPU engine hands its contribution
+    block (host memory, owner=0) to a GPU parent part: the drop-in boundary of
+    fkeep%inner_factor (src/ssids/fkeep.F90:146-169)."""
+    n, ptr, row, val = M.stencil_3d_27pt(14, shift=13.0)
+    ak = sb.analyse(n, ptr, row, ngpu=2, devices=[0, 0])
+    a = ak.analysis
+    assert a.nparts >= 2
+    slots = [None] * (a.nparts + 1)
+    numeric, keep = [], []
+    for p in range(a.nparts):
+        lo, hi = int(a.contrib_ptr[p]) - 1, int(a.contrib_ptr[p + 1]) - 1
+        cc = [slots[i] for i in range(lo, hi)]
+        idx = int(a.contrib_idx[p]) - 1
+        if p == 0:
+            st = oracle_ref.RefSubtree(a, p, False, val, cc)
+            keep.append(st)
+            numeric.append(st)
+            if idx < a.nparts:
+                slots[idx] = st.get_contrib()
+        else:
+            ns = ak.subtrees[p].factor(False, val, cc)
+            assert ns.stats.flag >= 0
+            numeric.append(ns)
+            if idx < a.nparts:
+                slots[idx] = ns.get_contrib(device_resident=True)
+    A = M.to_scipy(n, ptr, row, val)
+    b = A @ np.ones(n)
+    x2 = np.asfortranarray(b[a.invp - 1].reshape(n, 1))
+    for ns in numeric:
+        ns.solve("fwd", x2, 1) if isinstance(ns, oracle_ref.RefSubtree) else ns.solve_fwd(x2, 1, n)
+    for ns in reversed(numeric):
+        ns.solve("diag_bwd", x2, 1) if isinstance(ns, oracle_ref.RefSubtree) else ns.solve_diag_bwd(x2, 1, n)
+    x = np.empty(n)
+    x[a.invp - 1] = x2[:, 0]
+    assert oracle_ref.backward_error(A, x, b) < 1e-11
+
+
+def test_solve_jobs_compose():
+    """job 1 (fwd), 2 (diag), 3 (bwd), 4 (diag+bwd) compose to job 0
+    (ssids_solve, src/ssids/ssids.f90:1140-1250; fkeep.F90:269-297)."""
+    n, ptr, row, val = M.stencil_3d_27pt(10, shift=13.0)
+    ak = sb.analyse(n, ptr, row)
+    fk = sb.factor(ak, False, val)
+    b = np.linspace(-1, 1, n)
+    x0 = sb.solve(fk, b, job=0)
+    x123 = sb.solve(fk, sb.solve(fk, sb.solve(fk, b, job=1), job=2), job=3)
+    x14 = sb.solve(fk, sb.solve(fk, b, job=1), job=4)
+    np.testing.assert_allclose(x123, x0, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(x14, x0, rtol=1e-12, atol=1e-14)
+
+
+def test_scaling_argument():
+    n, ptr, row, val = M.kkt_saddle(1500)
+    A = M.to_scipy(n, ptr, row, val)
+    s = 1.0 / np.sqrt(np.maximum(abs(A).max(axis=1).toarray().ravel(), 1e-8))
+    _check(lambda: (n, ptr, row, val), False, 1, scaling=s)
+
+
+def test_singular_matrix_action():
+    """A structurally rank-deficient matrix: action=true -> warning flag 7 and
+    reduced rank; action=false -> error -5 (src/ssids/datatypes.f90:25-59)."""
+    n = 40
+    rng = np.random.default_rng(3)
+    A = _sym(rng, n)
+    A[:, 5] = 0.0; A[5, :] = 0.0
+    A[:, 17] = 0.0; A[17, :] = 0.0
+    n_, ptr, row, val = _dense(A)
+    order = np.arange(1, n + 1, dtype=np.int32)
+    ak = sb.analyse(n_, ptr, row, order=order)
+    fk = sb.factor(ak, False, val)
+    parts, r, _ = oracle_ref.ref_factor(ak.analysis, False, val)
+    for p in parts:
+        p.close()
+    assert fk.inform["flag"] == 7 == r["flag"]
+    assert fk.inform["matrix_rank"] == n - 2 == r["matrix_rank"]
+    assert fk.inform["num_neg"] == r["num_neg"]
+    opt = _lib.Options.default()
+    opt.action = False
+    fk2 = sb.factor(ak, False, val, options=opt)
+    assert fk2.inform["flag"] == -5
+
+
+def test_not_positive_definite():
+    n, ptr, row, val = M.stencil_3d_27pt(8, shift=13.0)
+    ak = sb.analyse(n, ptr, row)
+    fk = sb.factor(ak, True, val)
+    assert fk.inform["flag"] == -6
+    parts, r, _ = oracle_ref.ref_factor(ak.analysis, True, val)
+    for p in parts:
+        p.close()
+    assert r["flag"] == -6
+
+
+def test_enquire_and_alter():
+    """piv_order / d reporting (NumericSubtree.hxx:424-497) and alter."""
+    n, ptr, row, val = M.stencil_3d_27pt(8, shift=13.0)
+    ak = sb.analyse(n, ptr, row)
+    fk = sb.factor(ak, False, val)
+    ns = fk.numeric[0]
+    piv, d = ns.enquire()
+    assert sorted(abs(piv)) == list(range(n))
+    two = int((piv < 0).sum()) // 2
+    assert abs(two - fk.inform["num_two"]) <= 1      # -0 cannot be told from +0 for pivot 0
+    D = d.reshape(-1, 2)
+    # inertia from the reported D^-1 equals inform%num_neg
+    neg = 0
+    i = 0
+    while i < n:
+        if D[i, 1] != 0.0:
+            M2 = np.array([[D[i, 0], D[i, 1]], [D[i, 1], D[i + 1, 0]]])
+            neg += int((np.linalg.eigvalsh(M2) < 0).sum()); i += 2
+        else:
+            neg += int(D[i, 0] < 0); i += 1
+    assert neg == fk.inform["num_neg"]
+    A = M.to_scipy(n, ptr, row, val)
+    b = A @ np.ones(n)
+    x = sb.solve(fk, b)
+    ns.alter(2.0 * d)                                 # D^-1 doubled -> solution doubled
+    x2 = sb.solve(fk, b)
+    np.testing.assert_allclose(x2, 2.0 * x, rtol=1e-12, atol=1e-13)
+    pd = sb.factor(sb.analyse(*M.laplacian_2d_5pt(12)[:3]), True, M.laplacian_2d_5pt(12)[3])
+    _, dl = pd.numeric[0].enquire()
+    assert (dl > 0).all()
+
+
+def test_device_resident_inputs():
+    """aval and x may already live in HBM (torch tensors): same results."""
+    torch = pytest.importorskip("torch")
+    n, ptr, row, val = M.laplacian_3d_7pt(12)
+    ak = sb.analyse(n, ptr, row)
+    dval = torch.from_numpy(val).cuda()
+    fk = sb.factor(ak, True, dval.data_ptr())
+    A = M.to_scipy(n, ptr, row, val)
+    b = A @ np.ones(n)
+    a = ak.analysis
+    x2 = torch.from_numpy(np.ascontiguousarray(b[a.invp - 1])).cuda()
+    ns = fk.numeric[0]
+    ns.solve_fwd(x2.data_ptr(), 1, n)
+    ns.solve_bwd(x2.data_ptr(), 1, n)
+    torch.cuda.synchronize()
+    x = np.empty(n)
+    x[a.invp - 1] = x2.cpu().numpy()
+    assert oracle_ref.backward_error(A, x, b) < 1e-14
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE config 2 at full size (3-D 7-point 60^3, posdef): size-independent
+    properties -- residual, num_flops == analyse prediction, linearity of the solve."""
+    n, ptr, row, val = M.laplacian_3d_7pt(60)
+    ak = sb.analyse(n, ptr, row)
+    fk = sb.factor(ak, True, val)
+    a = ak.analysis
+    assert fk.inform["flag"] == 0
+    assert fk.inform["num_flops"] == a.num_flops and fk.inform["num_factor"] == a.num_factor
+    A = M.to_scipy(n, ptr, row, val)
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.uniform(-1, 1, (n, 3)))
+    B = np.asfortranarray(A @ X)
+    Xs = sb.solve(fk, B)
+    assert oracle_ref.backward_error(A, Xs, B) <= 1e-14
+    comb = sb.solve(fk, B[:, 0] + 2.0 * B[:, 1])
+    np.testing.assert_allclose(comb, Xs[:, 0] + 2.0 * Xs[:, 1], rtol=1e-9, atol=1e-11)

@@ -62,6 +62,8 @@ if __name__ == "__main__":
         run("lap3d-60", lambda: M.laplacian_3d_7pt(60), True)
     if "cfg3" in which:
         run("27pt-80", lambda: M.stencil_3d_27pt(80, shift=13.0), False, check_ref=False)
+    if "cfg5" in which:
+        run("27pt-100", lambda: M.stencil_3d_27pt(100, shift=13.0), False, check_ref=False)
     if "multi" in which:
         run("27pt-20-2parts", lambda: M.stencil_3d_27pt(20, shift=13.0), False, ngpu=2, devices=[0, 0])
         run("lap3d-20-4parts", lambda: M.laplacian_3d_7pt(20), True, ngpu=4, devices=[0, 0, 0, 0])
