@@ -21,17 +21,29 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <stdexcept>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "engine.h"
 
 namespace b200 {
 
 struct CudaError { cudaError_t code; };
 static bool g_profile = false;
+/* Clears (and, with SPRAL_B200_DEBUG set, reports) a pending non-sticky CUDA
+ * error so that it cannot leak into the host application's own CUDA calls. */
+static void clear_cuda_error(const char* where) {
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess && getenv("SPRAL_B200_DEBUG"))
+      fprintf(stderr, "spral_ssids_b200: pending CUDA error %d (%s) cleared at exit of %s\n",
+              (int)e, cudaGetErrorString(e), where);
+}
+struct AbiExit { const char* w; ~AbiExit() { clear_cuda_error(w); } };
+#define ABI_GUARD() AbiExit abi_guard_{__func__}
 std::atomic<long> g_launches{0};      // incremented by every launch wrapper
 #define CUDA_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaError{e_}; } while (0)
 
@@ -266,9 +278,10 @@ struct Numeric {
    double prof_flops = 0;
    int n_launch = 0;
 
+   int device = 0;                     // copy of S->device: the symbolic object may die first
    ~Numeric() {
       if (!S) return;
-      cudaSetDevice(S->device);
+      cudaSetDevice(device);
       if (stream) cudaStreamSynchronize(stream);
       if (ev_begin) cudaEventDestroy(ev_begin);
       if (ev_end) cudaEventDestroy(ev_end);
@@ -702,7 +715,9 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          cudaEvent_t a, b;
          CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
          CUDA_TRY(cudaEventRecord(a, s));
+         nvtxRangePushA("upd_contrib");
          launch_update(N.d_fronts, d_ctiles, (int)ctiles.size(), UPD_CONTRIB, big, s);
+         nvtxRangePop();
          CUDA_TRY(cudaEventRecord(b, s));
          N.prof_events.push_back({a, b});
          for (int fi = f0; fi < f1; ++fi) {
@@ -859,6 +874,7 @@ using namespace b200;
 extern "C" {
 
 int spral_ssids_b200_cuda_init(int* cnt) {
+   ABI_GUARD();
    int n = 0;
    cudaError_t e = cudaGetDeviceCount(&n);
    if (e != cudaSuccess) { *cnt = 0; cudaGetLastError(); return (int)e; }
@@ -877,6 +893,7 @@ void* spral_ssids_gpu_create_symbolic_subtree(
       const int64_t* rptr, const int* rlist, const int64_t* nptr,
       const int64_t* nlist, int ncontrib, const int* contrib_idx,
       const struct spral_ssids_b200_options* options) {
+   ABI_GUARD();
    try {
       return build_symbolic(device, n, sa, en, sptr, sparent, rptr, rlist, nptr, nlist,
                             ncontrib, contrib_idx, options);
@@ -889,15 +906,18 @@ void* spral_ssids_gpu_create_symbolic_subtree(
    return nullptr;
 }
 
-void spral_ssids_gpu_destroy_symbolic_subtree(void* p) { delete static_cast<Symbolic*>(p); }
+void spral_ssids_gpu_destroy_symbolic_subtree(void* p) {
+   ABI_GUARD(); delete static_cast<Symbolic*>(p); }
 
 void* spral_ssids_gpu_create_num_subtree_dbl(
       bool posdef, const void* symbolic_subtree, const double* aval,
       const double* scaling, void** child_contrib,
       const struct spral_ssids_b200_options* options,
       struct spral_ssids_b200_stats* stats) {
+   ABI_GUARD();
    auto* N = new Numeric;
    N->S = const_cast<Symbolic*>(static_cast<const Symbolic*>(symbolic_subtree));
+   N->device = N->S->device;
    N->posdef = posdef;
    std::memset(stats, 0, sizeof(*stats));
    try {
@@ -915,18 +935,23 @@ void* spral_ssids_gpu_create_num_subtree_dbl(
    return N;
 }
 
-void spral_ssids_gpu_destroy_num_subtree_dbl(bool, void* p) { delete static_cast<Numeric*>(p); }
+void spral_ssids_gpu_destroy_num_subtree_dbl(bool, void* p) {
+   ABI_GUARD(); delete static_cast<Numeric*>(p); }
 
 int spral_ssids_gpu_subtree_solve_fwd_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   ABI_GUARD();
    return solve_subtree(*static_cast<const Numeric*>(p), JOB_FWD, nrhs, x, ldx);
 }
 int spral_ssids_gpu_subtree_solve_diag_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   ABI_GUARD();
    return solve_subtree(*static_cast<const Numeric*>(p), JOB_DIAG, nrhs, x, ldx);
 }
 int spral_ssids_gpu_subtree_solve_diag_bwd_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   ABI_GUARD();
    return solve_subtree(*static_cast<const Numeric*>(p), JOB_DIAG_BWD, nrhs, x, ldx);
 }
 int spral_ssids_gpu_subtree_solve_bwd_dbl(bool, const void* p, int nrhs, double* x, int ldx) {
+   ABI_GUARD();
    return solve_subtree(*static_cast<const Numeric*>(p), JOB_BWD, nrhs, x, ldx);
 }
 
@@ -934,6 +959,7 @@ int spral_ssids_gpu_subtree_solve_bwd_dbl(bool, const void* p, int nrhs, double*
  * nodes in node order; posdef: diagonal of L; indefinite: piv_order indexed by
  * pivot-order variable, 2x2 pivots negative; d two entries per column. */
 void spral_ssids_gpu_subtree_enquire_dbl(bool posdef, const void* p, int* piv_order, double* d) {
+   ABI_GUARD();
    const Numeric& N = *static_cast<const Numeric*>(p);
    const Symbolic& S = *N.S;
    cudaSetDevice(S.device);
@@ -969,6 +995,7 @@ void spral_ssids_gpu_subtree_enquire_dbl(bool posdef, const void* p, int* piv_or
 
 /* NumericSubtree::alter (src/ssids/cpu/NumericSubtree.hxx:473-497) */
 void spral_ssids_gpu_subtree_alter_dbl(bool posdef, void* p, const double* d) {
+   ABI_GUARD();
    if (posdef) return;
    Numeric& N = *static_cast<Numeric*>(p);
    const Symbolic& S = *N.S;
@@ -990,6 +1017,7 @@ void spral_ssids_gpu_subtree_alter_dbl(bool posdef, void* p, const double* d) {
 void spral_ssids_gpu_subtree_get_contrib_device_dbl(bool, void* p,
       int* n, const double** val, int* ldval, const int** rlist, int* ndelay,
       const int** delay_perm, const double** delay_val, int* lddelay, int* device) {
+   ABI_GUARD();
    Numeric& N = *static_cast<Numeric*>(p);
    const Symbolic& S = *N.S;
    *device = S.device;
@@ -1012,6 +1040,7 @@ void spral_ssids_gpu_subtree_get_contrib_device_dbl(bool, void* p,
 void spral_ssids_gpu_subtree_get_contrib_dbl(bool posdef, void* p,
       int* n, const double** val, int* ldval, const int** rlist, int* ndelay,
       const int** delay_perm, const double** delay_val, int* lddelay) {
+   ABI_GUARD();
    Numeric& N = *static_cast<Numeric*>(p);
    const Symbolic& S = *N.S;
    int dev;
@@ -1039,6 +1068,7 @@ void spral_ssids_gpu_subtree_get_contrib_dbl(bool posdef, void* p,
 }
 
 void spral_ssids_gpu_subtree_free_contrib_dbl(bool, void* p) {
+   ABI_GUARD();
    Numeric& N = *static_cast<Numeric*>(p);
    cudaSetDevice(N.S->device);
    if (N.d_export) { cudaFree(N.d_export); N.d_export = nullptr; }
@@ -1048,6 +1078,7 @@ void spral_ssids_gpu_subtree_free_contrib_dbl(bool, void* p) {
 
 void spral_ssids_b200_contrib_fill(struct spral_ssids_b200_contrib* c, bool posdef,
       void* numeric_subtree, bool device_resident) {
+   ABI_GUARD();
    std::memset((void*)c, 0, sizeof(*c));
    int dev = -1;
    if (device_resident)
@@ -1062,6 +1093,7 @@ void spral_ssids_b200_contrib_fill(struct spral_ssids_b200_contrib* c, bool posd
 
 void spral_ssids_gpu_symbolic_get_maps(const void* p, int* rlist_direct, int* num_levels,
       int* level_ptr, int* level_list) {
+   ABI_GUARD();
    const Symbolic& S = *static_cast<const Symbolic*>(p);
    cudaSetDevice(S.device);
    if (rlist_direct && !S.rlist_direct.empty())
@@ -1071,9 +1103,11 @@ void spral_ssids_gpu_symbolic_get_maps(const void* p, int* rlist_direct, int* nu
    if (level_list) std::copy(S.level_list.begin(), S.level_list.end(), level_list);
 }
 
-void spral_ssids_b200_set_profile(int on) { g_profile = (on != 0); }
+void spral_ssids_b200_set_profile(int on) {
+   ABI_GUARD(); g_profile = (on != 0); }
 
 void spral_ssids_gpu_subtree_get_timings(const void* p, double* ms, int n) {
+   ABI_GUARD();
    const Numeric& N = *static_cast<const Numeric*>(p);
    for (int i = 0; i < n && i < 8; ++i) ms[i] = N.timings[i];
 }
@@ -1110,6 +1144,7 @@ extern "C" {
  * raw cudaError_t. */
 int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned char* handle,
       int* n, int* ndelay, int64_t* bytes, void** device_block) {
+   ABI_GUARD();
    Numeric& N = *static_cast<Numeric*>(numeric_subtree);
    const Symbolic& S = *N.S;
    cudaSetDevice(S.device);
@@ -1143,6 +1178,7 @@ int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned c
 /* Consumer side: maps the producer's block and copies `bytes` into dst (a
  * device pointer of the calling process' current device) over NVLink. */
 int spral_ssids_b200_ipc_pull(const unsigned char* handle, int64_t bytes, void* dst) {
+   ABI_GUARD();
    cudaIpcMemHandle_t h;
    std::memcpy(&h, handle, sizeof(h));
    void* src = nullptr;
@@ -1154,14 +1190,17 @@ int spral_ssids_b200_ipc_pull(const unsigned char* handle, int64_t bytes, void* 
 }
 
 int spral_ssids_b200_copy_to_host(void* dst, const void* src, int64_t bytes) {
+   ABI_GUARD();
    return (int)cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost);
 }
 
 void* spral_ssids_b200_device_alloc(int64_t bytes) {
+   ABI_GUARD();
    void* p = nullptr;
    if (cudaMalloc(&p, (size_t)std::max<int64_t>(bytes, 256)) != cudaSuccess) return nullptr;
    return p;
 }
-void spral_ssids_b200_device_free(void* p) { if (p) cudaFree(p); }
+void spral_ssids_b200_device_free(void* p) {
+   ABI_GUARD(); if (p) cudaFree(p); }
 
 } /* extern "C" */

@@ -116,6 +116,19 @@ def _dense(A):
     return n, ptr, row, val
 
 
+def _dense_explicit(A):
+    """Lower triangle of a dense matrix with EVERY entry stored, zeros included."""
+    n = A.shape[0]
+    ptr = np.zeros(n + 1, dtype=np.int64)
+    rows, vals = [], []
+    for j in range(n):
+        ptr[j] = len(rows) + 1
+        rows.extend(range(j + 1, n + 1))
+        vals.extend(A[j:, j])
+    ptr[n] = len(rows) + 1
+    return n, ptr, np.array(rows, dtype=np.int32), np.array(vals, dtype=np.float64)
+
+
 def _sym(rng, n):
     A = rng.uniform(-1, 1, (n, n))
     return (A + A.T) / 2
@@ -236,8 +249,8 @@ def test_solve_jobs_compose():
     x0 = sb.solve(fk, b, job=0)
     x123 = sb.solve(fk, sb.solve(fk, sb.solve(fk, b, job=1), job=2), job=3)
     x14 = sb.solve(fk, sb.solve(fk, b, job=1), job=4)
-    np.testing.assert_allclose(x123, x0, rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(x14, x0, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(x123, x0, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(x14, x0, rtol=1e-9, atol=1e-11)   # atomics reorder the forward sums
 
 
 def test_scaling_argument():
@@ -248,27 +261,32 @@ def test_scaling_argument():
 
 
 def test_singular_matrix_action():
-    """A structurally rank-deficient matrix: action=true -> warning flag 7 and
-    reduced rank; action=false -> error -5 (src/ssids/datatypes.f90:25-59)."""
+    """A rank-deficient matrix (two rows/columns of explicit zeros): action=true
+    -> warning flag 7 and reduced rank; action=false -> error -5
+    (src/ssids/datatypes.f90:25-59; block_ldlt.hxx:303-317, ldlt_tpp.cxx:179-188)."""
     n = 40
     rng = np.random.default_rng(3)
     A = _sym(rng, n)
     A[:, 5] = 0.0; A[5, :] = 0.0
     A[:, 17] = 0.0; A[17, :] = 0.0
-    n_, ptr, row, val = _dense(A)
+    n_, ptr, row, val = _dense_explicit(A)           # the zero rows are PRESENT in the pattern
     order = np.arange(1, n + 1, dtype=np.int32)
     ak = sb.analyse(n_, ptr, row, order=order)
     fk = sb.factor(ak, False, val)
     parts, r, _ = oracle_ref.ref_factor(ak.analysis, False, val)
     for p in parts:
         p.close()
-    assert fk.inform["flag"] == 7 == r["flag"]
+    assert fk.inform["flag"] == 7 and r["flag"] == 7
     assert fk.inform["matrix_rank"] == n - 2 == r["matrix_rank"]
     assert fk.inform["num_neg"] == r["num_neg"]
     opt = _lib.Options.default()
     opt.action = False
     fk2 = sb.factor(ak, False, val, options=opt)
     assert fk2.inform["flag"] == -5
+    parts, r2, _ = oracle_ref.ref_factor(ak.analysis, False, val, options=opt)
+    for p in parts:
+        p.close()
+    assert r2["flag"] == -5
 
 
 def test_not_positive_definite():

@@ -1,0 +1,36 @@
+"""Profiling driver: analyse once, one warm-up factor, then one factor inside
+cudaProfilerStart/Stop (use ncu --profile-from-start off)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import spral_b200 as sb
+from spral_b200 import matrices as M
+
+grid = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+posdef = len(sys.argv) > 2 and sys.argv[2] == "posdef"
+n, ptr, row, val = (M.laplacian_3d_7pt(grid) if posdef else M.stencil_3d_27pt(grid, shift=13.0))
+ak = sb.analyse(n, ptr, row)
+dval = torch.from_numpy(val).cuda()
+fk = sb.factor(ak, posdef, dval.data_ptr())
+for ns in fk.numeric: ns.close()
+torch.cuda.synchronize()
+rt = torch.cuda.cudart()
+from spral_b200 import _lib
+_lib.load().spral_ssids_b200_set_profile(1)      # NVTX range "upd_contrib" + event timing
+rt.cudaProfilerStart()
+t = time.time()
+fk = sb.factor(ak, posdef, dval.data_ptr())
+torch.cuda.synchronize()
+dt = time.time() - t
+rt.cudaProfilerStop()
+print("factor", dt, "s", fk.inform["num_flops"] / dt / 1e9, "GF/s", "timings", fk.numeric[0].timings())
+if len(sys.argv) > 3 and sys.argv[3] == "solve":
+    a = ak.analysis
+    x = torch.ones(n, dtype=torch.float64, device="cuda")
+    rt.cudaProfilerStart()
+    fk.numeric[0].solve_fwd(x.data_ptr(), 1, n)
+    fk.numeric[0].solve_diag_bwd(x.data_ptr(), 1, n)
+    torch.cuda.synchronize()
+    rt.cudaProfilerStop()
