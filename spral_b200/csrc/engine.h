@@ -92,7 +92,7 @@ struct FactorParams {
 
 /* One tile of work for the panel kernels: front index and row-tile index. */
 struct RowTile { int front; int tile; };
-/* One tile of work for the DMMA update kernels. */
+/* One tile of work for the DMMA update kernels: absolute tile row / column of the front. */
 struct MatTile { int front; int ti; int tj; };
 
 /* ---- launch wrappers (factor_kernels.cu) ---- */
@@ -109,6 +109,7 @@ void launch_apply(Front* fronts, const RowTile* work, int nwork, bool posdef,
 void launch_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s);
 void launch_swap(Front* fronts, const RowTile* work, int nwork, bool outer, cudaStream_t s);
 void launch_finalize(Front* fronts, const int* flist, int count, bool posdef, cudaStream_t s);
+void launch_snapshot(Front* fronts, const int* flist, int count, int* snap, cudaStream_t s);
 int assemble_cols_per_cta();
 int scatter_chunk();
 
@@ -117,6 +118,7 @@ enum UpdateMode { UPD_INNER = 0, UPD_OUTER = 1, UPD_CONTRIB = 2 };
 void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
       bool big_tiles, cudaStream_t s);
 int update_tile_size(bool big_tiles);
+int inner_tile_size();
 void configure_update_kernels();   // per device: opt in to > 48 KB dynamic shared memory
 
 /* ---- solve (solve_kernels.cu) ---- */

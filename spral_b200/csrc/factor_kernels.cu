@@ -209,215 +209,233 @@ __device__ void advance_state(Front* f, bool new_panel) {
 /* Diagonal block                                                            */
 /* ------------------------------------------------------------------------ */
 
-/* One warp per front; lane r owns row r of the block. */
+/* One 32x32-thread CTA per front: thread (r, c) owns entry (r, c) of the block,
+ * a warp owns a column.  The block lives in shared memory as a full symmetric
+ * matrix, double buffered: every pivot reads the old buffer (through the
+ * permutation that brings the chosen pivot to the front) and writes the new
+ * one, so a pivot costs two block-wide barriers.  Entry (r,c) and its mirror
+ * (c,r) are computed with the same expression, which keeps the block exactly
+ * symmetric. */
 template <bool POSDEF>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(BS * BS)
 k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
    Front* f = &fronts[flist[blockIdx.x]];
-   const int lane = threadIdx.x;
-   __shared__ double a[BS][BS + 1];
-   __shared__ double ld[BS][BS + 1];
+   const int r = threadIdx.x & 31, c = threadIdx.x >> 5;     // warp == column c
+   __shared__ double A[2][BS][BS + 1];
+   __shared__ double LDm[2][BS][BS + 1];
    __shared__ double dinv[2 * BS];
+   __shared__ double cmax[BS];
+   __shared__ int crow[BS];
    __shared__ int lperm[BS];
-   int zfrom = BS;      // first column of the block that was declared a zero pivot
+   __shared__ int s_go;
+   __shared__ int s_piv_i[4];
+   __shared__ double s_piv_d[4];
 
-   if (lane == 0) {
+   if (threadIdx.x == 0) {
       advance_state(f, new_panel != 0);
       if (!f->finished && f->done < f->pend) {
          f->bs = min(BS, f->pend - f->done);
          f->first_fail = f->bs;
          f->step_valid = 1;
+         s_go = 1;
       } else {
          f->bs = 0;
+         s_go = 0;
       }
    }
-   __syncwarp();
-   if (f->finished || f->bs == 0) return;
+   __syncthreads();
+   if (!s_go) return;
    const int bs = f->bs, done = f->done, ldl = f->ldl;
    double* Ld = f->L + (size_t)done * ldl + done;   // the diagonal block
    BlockWS* ws = f->ws;
 
-   /* load the lower triangle (coalesced per column), then mirror */
-   for (int c = 0; c < BS; ++c) {
+   /* load the lower triangle, mirror it */
+   {
       double v = 0.0;
-      if (lane < bs && c < bs && lane >= c) v = Ld[lane + (size_t)c * ldl];
-      a[lane][c] = v;
-      ld[lane][c] = 0.0;
+      if (r < bs && c < bs && r >= c) v = Ld[r + (size_t)c * ldl];
+      A[0][r][c] = v;
+      LDm[0][r][c] = 0.0; LDm[1][r][c] = 0.0;
+      if (c == 0) { lperm[r] = r; dinv[2 * r] = 0.0; dinv[2 * r + 1] = 0.0; }
    }
-   __syncwarp();
-   for (int c = lane + 1; c < BS; ++c) a[lane][c] = a[c][lane];
-   lperm[lane] = lane;
-   dinv[2 * lane] = 0.0; dinv[2 * lane + 1] = 0.0;
-   __syncwarp();
+   __syncthreads();
+   if (r < c) A[0][r][c] = A[0][c][r];
+   __syncthreads();
+   int cur = 0;
 
    if (POSDEF) {
       /* Cholesky of the block (cholesky_factor, src/ssids/cpu/kernels/cholesky.cxx:33-187) */
-      bool ok = true;
       for (int p = 0; p < bs; ++p) {
-         double d = a[p][p];
-         if (!(d > 0.0)) { ok = false; break; }
+         double d = A[cur][p][p];
+         if (!(d > 0.0)) {
+            if (threadIdx.x == 0) { f->flag = SPRAL_SSIDS_ERROR_NOT_POS_DEF; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
+            return;
+         }
          double lpp = sqrt(d);
-         double l = 0.0;
-         if (lane > p && lane < bs) { l = a[lane][p] / lpp; a[lane][p] = l; }
-         if (lane == p) { a[p][p] = lpp; dinv[p] = 1.0 / lpp; }
-         __syncwarp();
-         if (lane > p && lane < bs)
-            for (int c = p + 1; c <= lane; ++c) a[lane][c] -= l * a[c][p];
-         __syncwarp();
+         const int R = max(r, c), C = min(r, c);
+         double v = A[cur][R][C];
+         if (C == p) v = (R == p) ? lpp : v / lpp;
+         else if (C > p) v -= (A[cur][R][p] / lpp) * (A[cur][C][p] / lpp);
+         A[cur ^ 1][r][c] = v;
+         if (threadIdx.x == 0) dinv[p] = 1.0 / lpp;
+         __syncthreads();
+         cur ^= 1;
       }
-      if (!ok) {
-         if (lane == 0) { f->flag = SPRAL_SSIDS_ERROR_NOT_POS_DEF; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
-         return;
-      }
-      for (int c = 0; c < bs; ++c) {
-         if (lane < bs && lane >= c) Ld[lane + (size_t)c * ldl] = a[lane][c];
-         ws->l11[lane + c * BS] = (lane < bs && lane >= c) ? a[lane][c] : 0.0;
-      }
-      for (int c = bs; c < BS; ++c) ws->l11[lane + c * BS] = 0.0;
-      ws->dinv[lane] = (lane < bs) ? dinv[lane] : 0.0;
+      double l = (r < bs && c < bs && r >= c) ? A[cur][r][c] : 0.0;
+      if (r < bs && c < bs && r >= c) Ld[r + (size_t)c * ldl] = l;
+      ws->l11[r + c * BS] = l;
+      if (c == 0) ws->dinv[r] = (r < bs) ? dinv[r] : 0.0;
       return;
    }
 
    /* keep the unfactorised block for k_commit */
-   for (int c = 0; c < BS; ++c) ws->a0[lane + c * BS] = a[lane][c];
+   ws->a0[r + c * BS] = A[0][r][c];
 
+   int zfrom = BS;
    int p = 0;
    while (p < bs) {
-      /* largest remaining entry of the lower triangle: lane r scans its row */
-      double best = -1.0;
-      int bidx = 0;
-      if (lane >= p && lane < bs) {
-         for (int c = p; c <= lane; ++c) {
-            double v = fabs(a[lane][c]);
-            if (v > best) { best = v; bidx = c * BS + lane; }
+      /* largest remaining entry of the lower triangle (ties: smallest column, then row) */
+      {
+         double v = (r >= c && c >= p && r < bs) ? fabs(A[cur][r][c]) : -1.0;
+         int rr = r;
+         #pragma unroll
+         for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, off);
+            int orr = __shfl_xor_sync(0xffffffffu, rr, off);
+            if (ov > v || (ov == v && orr < rr)) { v = ov; rr = orr; }
+         }
+         if (r == 0) { cmax[c] = v; crow[c] = rr; }
+      }
+      __syncthreads();
+      /* one warp takes the decision and does the divisions; everybody else waits */
+      if (c == 0) {
+         double best = cmax[r];
+         int bidx = r * BS + crow[r];          // lane r looks at column r
+         #pragma unroll
+         for (int off = 16; off > 0; off >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+         }
+         if (r == 0) {
+            int m_ = bidx / BS, t_ = bidx % BS;      // column m <= row t
+            int ps = 1;
+            double e11 = 0, e21 = 0, e22 = 0;
+            if (!(best >= prm.small)) ps = 0;
+            else if (t_ == m_) e11 = 1.0 / A[cur][t_][t_];
+            else {
+               double a11 = A[cur][m_][m_], a22 = A[cur][t_][t_], a21 = A[cur][t_][m_];
+               double detscale = 1.0 / fabs(a21);
+               double detpiv = (a11 * detscale) * a22 - fabs(a21);
+               if (fabs(detpiv) >= fabs(a21) / 2) {
+                  ps = 2;
+                  e11 = (a22 * detscale) / detpiv;
+                  e22 = (a11 * detscale) / detpiv;
+                  e21 = (-a21 * detscale) / detpiv;
+               } else {
+                  if (fabs(a11) > fabs(a22)) t_ = m_;    // a11 as 1x1, else a22 (row/col t)
+                  e11 = 1.0 / A[cur][t_][t_];
+               }
+            }
+            s_piv_i[0] = ps; s_piv_i[1] = t_; s_piv_i[2] = m_;
+            s_piv_d[0] = e11; s_piv_d[1] = e21; s_piv_d[2] = e22;
          }
       }
-      #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-         double ob = __shfl_xor_sync(0xffffffffu, best, off);
-         int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-         if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-      }
-      int m = bidx / BS, t = bidx % BS;   // column m <= row t
+      __syncthreads();
+      const int pivsiz = s_piv_i[0], t = s_piv_i[1], m = s_piv_i[2];
+      const double d11 = s_piv_d[0], d21 = s_piv_d[1], d22 = s_piv_d[2];
 
-      if (!(best >= prm.small)) {
+      if (pivsiz == 0) {
          /* everything left is (numerically) zero: block_ldlt.hxx:303-317 */
          if (!prm.action) {
-            if (lane == 0) { f->flag = SPRAL_SSIDS_ERROR_SINGULAR; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
+            if (threadIdx.x == 0) { f->flag = SPRAL_SSIDS_ERROR_SINGULAR; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
             return;
          }
          zfrom = p;
-         for (int q = p; q < bs; ++q) {
-            if (lane >= q) a[lane][q] = (lane == q) ? 1.0 : 0.0;
-            ld[lane][q] = 0.0;
-            if (lane == 0) { dinv[2 * q] = 0.0; dinv[2 * q + 1] = 0.0; }
-         }
-         __syncwarp();
+         const int R = max(r, c), C = min(r, c);
+         if (C >= p) { A[cur][r][c] = (R == C) ? 1.0 : 0.0; LDm[cur][r][c] = 0.0; }
+         __syncthreads();
          break;
       }
 
-      int pivsiz;
-      double a11 = 0, a21 = 0, a22 = 0, detscale = 0, detpiv = 0;
-      if (t == m) {
-         pivsiz = 1;
-      } else {
-         a11 = a[m][m]; a22 = a[t][t]; a21 = a[t][m];
-         detscale = 1.0 / fabs(a21);
-         detpiv = (a11 * detscale) * a22 - fabs(a21);
-         if (fabs(detpiv) >= fabs(a21) / 2) pivsiz = 2;
-         else {
-            pivsiz = 1;
-            if (fabs(a11) > fabs(a22)) t = m; /* a11 as 1x1 */
-            /* else a22 (row/col t) as 1x1 */
-         }
-      }
-      __syncwarp();
-
-      /* symmetric swaps within the block (full storage) */
-      auto swap_sym = [&](int i, int j) {
-         if (i == j) return;
-         double x = a[lane][i]; a[lane][i] = a[lane][j]; a[lane][j] = x;   // columns
-         __syncwarp();
-         x = a[i][lane]; a[i][lane] = a[j][lane]; a[j][lane] = x;          // rows (incl. L part)
-         x = ld[i][lane]; ld[i][lane] = ld[j][lane]; ld[j][lane] = x;
-         if (lane == 0) { int q = lperm[i]; lperm[i] = lperm[j]; lperm[j] = q; }
-         __syncwarp();
-      };
-
+      const int R = max(r, c), C = min(r, c);
+      const double (*Ao)[BS + 1] = A[cur];
+      const double (*Lo)[BS + 1] = LDm[cur];
+      double vnew, ldnew;
       if (pivsiz == 1) {
-         swap_sym(p, t);
-         double piv = a[p][p];
-         double d11 = 1.0 / piv;
-         double wr = a[lane][p];          // original column (L*D)
-         double lr = wr * d11;
-         __syncwarp();
-         if (lane > p && lane < bs) { ld[lane][p] = wr; a[lane][p] = lr; }
-         if (lane == p) { a[p][p] = 1.0; dinv[2 * p] = d11; dinv[2 * p + 1] = 0.0; }
-         __syncwarp();
-         if (lane > p && lane < bs) {
-            for (int c = p + 1; c < bs; ++c) {
-               /* identical rounding for (r,c) and (c,r) keeps the block symmetric */
-               double upd = (c <= lane) ? lr * ld[c][p] : a[c][p] * wr;
-               a[lane][c] -= upd;
-            }
+         /* new position x holds old position pi(x): swap p <-> t */
+         auto pi = [&](int x) { return x == p ? t : (x == t ? p : x); };
+         const int oR = pi(R), oC = pi(C);
+         if (C < p) { vnew = Ao[oR][C]; ldnew = Lo[oR][C]; }
+         else if (C == p) {
+            double wr = Ao[oR][t];
+            vnew = (R == p) ? 1.0 : wr * d11;
+            ldnew = (R == p) ? 0.0 : wr;
+         } else {
+            vnew = Ao[oR][oC] - (Ao[oR][t] * d11) * Ao[oC][t];
+            ldnew = 0.0;
          }
-         __syncwarp();
-         p += 1;
+         if (threadIdx.x == 0) {
+            dinv[2 * p] = d11; dinv[2 * p + 1] = 0.0;
+            int q = lperm[p]; lperm[p] = lperm[t]; lperm[t] = q;
+         }
       } else {
-         swap_sym(p, m);
-         swap_sym(p + 1, t);
-         double d11 = (a22 * detscale) / detpiv;
-         double d22 = (a11 * detscale) / detpiv;
-         double d21 = (-a21 * detscale) / detpiv;
-         double w1 = a[lane][p], w2 = a[lane][p + 1];
-         double l1 = d11 * w1 + d21 * w2;
-         double l2 = d21 * w1 + d22 * w2;
-         __syncwarp();
-         if (lane > p + 1 && lane < bs) {
-            ld[lane][p] = w1; ld[lane][p + 1] = w2;
-            a[lane][p] = l1; a[lane][p + 1] = l2;
+         /* swap p <-> m, then p+1 <-> t */
+         auto pi1 = [&](int y) { return y == p ? m : (y == m ? p : y); };
+         auto pi = [&](int x) { return x == p + 1 ? pi1(t) : (x == t ? pi1(p + 1) : pi1(x)); };
+         const int oR = pi(R), oC = pi(C);
+         if (C < p) { vnew = Ao[oR][C]; ldnew = Lo[oR][C]; }
+         else if (C <= p + 1) {
+            if (R <= p + 1) {              // the 2x2 diagonal block of L is the identity
+               vnew = (R == C) ? 1.0 : 0.0; ldnew = 0.0;
+            } else {
+               double w1 = Ao[oR][m], w2 = Ao[oR][t];
+               if (C == p) { vnew = d11 * w1 + d21 * w2; ldnew = w1; }
+               else        { vnew = d21 * w1 + d22 * w2; ldnew = w2; }
+            }
+         } else {
+            double w1 = Ao[oR][m], w2 = Ao[oR][t];
+            double l1 = d11 * w1 + d21 * w2, l2 = d21 * w1 + d22 * w2;
+            vnew = Ao[oR][oC] - (Ao[oC][m] * l1 + Ao[oC][t] * l2);
+            ldnew = 0.0;
          }
-         if (lane == p) {
-            a[p][p] = 1.0; a[p + 1][p] = 0.0; a[p + 1][p + 1] = 1.0;
-            ld[p + 1][p] = 0.0;
+         if (threadIdx.x == 0) {
             dinv[2 * p] = d11; dinv[2 * p + 1] = d21;
             dinv[2 * p + 2] = CUDART_INF; dinv[2 * p + 3] = d22;
+            int q = lperm[p]; lperm[p] = lperm[m]; lperm[m] = q;
+            q = lperm[p + 1]; lperm[p + 1] = lperm[t]; lperm[t] = q;
          }
-         __syncwarp();
-         if (lane > p + 1 && lane < bs) {
-            for (int c = p + 2; c < bs; ++c) {
-               double upd = (c <= lane)
-                  ? ld[c][p] * l1 + ld[c][p + 1] * l2
-                  : w1 * a[c][p] + w2 * a[c][p + 1];
-               a[lane][c] -= upd;
-            }
-         }
-         __syncwarp();
-         p += 2;
       }
+      A[cur ^ 1][r][c] = vnew;
+      /* LD is only meaningful strictly below the diagonal of eliminated columns */
+      LDm[cur ^ 1][r][c] = (r > c) ? ldnew : 0.0;
+      __syncthreads();
+      cur ^= 1;
+      p += pivsiz;
    }
 
    /* publish L11 (unit lower), L11*D, D^-1 and the local permutation */
-   for (int c = 0; c < BS; ++c) {
+   {
       double l = 0.0, y = 0.0;
-      if (lane < bs && c < bs) {
-         if (lane > c) { l = a[lane][c]; y = ld[lane][c]; }
-         else if (lane == c) l = 1.0;
+      if (r < bs && c < bs) {
+         if (r > c) { l = A[cur][r][c]; y = LDm[cur][r][c]; }
+         else if (r == c) l = 1.0;
       }
-      ws->l11[lane + c * BS] = l;
-      ws->ld11[lane + c * BS] = y;
+      ws->l11[r + c * BS] = l;
+      ws->ld11[r + c * BS] = y;
+      if (c == 0) {
+         ws->dinv[2 * r] = (r < bs) ? dinv[2 * r] : 0.0;
+         ws->dinv[2 * r + 1] = (r < bs) ? dinv[2 * r + 1] : 0.0;
+         ws->lperm[r] = lperm[r];
+         if (r == 0) ws->zfrom = zfrom;
+      }
    }
-   ws->dinv[2 * lane] = (lane < bs) ? dinv[2 * lane] : 0.0;
-   ws->dinv[2 * lane + 1] = (lane < bs) ? dinv[2 * lane + 1] : 0.0;
-   ws->lperm[lane] = lperm[lane];
-   if (lane == 0) ws->zfrom = zfrom;
 }
 
 void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool new_panel,
       const FactorParams& prm, cudaStream_t s) {
    if (count == 0) return;
-   if (posdef) k_diag<true><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
-   else k_diag<false><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm); COUNT_LAUNCH();
+   if (posdef) k_diag<true><<<count, BS * BS, 0, s>>>(fronts, flist, new_panel, prm);
+   else k_diag<false><<<count, BS * BS, 0, s>>>(fronts, flist, new_panel, prm); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -698,6 +716,33 @@ void launch_swap(Front* fronts, const RowTile* work, int nwork, bool outer, cuda
    int nslice = outer ? PW / BS : 1;
    for (int sl = 0; sl < nslice; ++sl)
       k_swap<<<nwork, RT, 0, s>>>(fronts, work, outer ? 1 : 0, sl); COUNT_LAUNCH();
+}
+
+/* ------------------------------------------------------------------------ */
+/* Panel snapshot for the host                                               */
+/* ------------------------------------------------------------------------ */
+
+/* Accounts the last inner step of the panel and reports the state the host
+ * needs to size the outer update exactly: p0, done, pend, pend0, end,
+ * finished, flag (8 ints per front). */
+__global__ void k_snapshot(Front* fronts, const int* __restrict__ flist, int count, int* __restrict__ snap) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= count) return;
+   Front* f = &fronts[flist[i]];
+   if (!f->finished && f->step_valid) {
+      int ne = calc_ne(f);
+      f->done += ne;
+      f->pend -= f->bs - ne;
+      f->step_valid = 0;
+   }
+   int* o = snap + (size_t)i * 8;
+   o[0] = f->p0; o[1] = f->done; o[2] = f->pend; o[3] = f->pend0; o[4] = f->end;
+   o[5] = f->finished; o[6] = f->flag; o[7] = 0;
+}
+
+void launch_snapshot(Front* fronts, const int* flist, int count, int* snap, cudaStream_t s) {
+   if (count == 0) return;
+   k_snapshot<<<(count + 127) / 128, 128, 0, s>>>(fronts, flist, count, snap); COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */

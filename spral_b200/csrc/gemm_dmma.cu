@@ -26,6 +26,7 @@
  * Tiles are aligned to absolute front coordinates (multiples of T from row 0),
  * which keeps every bulk copy 16-byte aligned whatever the pivoting state is.
  */
+#include <algorithm>
 #include "engine.h"
 #include "device_utils.cuh"
 
@@ -116,156 +117,205 @@ __device__ __forceinline__ Region make_region(const Front* f, int mode, int T) {
    return g;
 }
 
-/* T x T output tile per CTA, NWR x NWC warps. */
-template <int T, int NWR, int NWC>
+/* What one CTA needs to know about one output tile. */
+struct TileJob {
+   Region g;
+   int r0, c0;
+   int nchunk;
+};
+
+template <int T>
+__device__ __forceinline__ bool load_job(const Front* fronts, const MatTile* work, int item, int mode, TileJob& j) {
+   MatTile w = work[item];
+   j.g = make_region(&fronts[w.front], mode, T);
+   if (!j.g.valid) return false;
+   j.r0 = w.ti * T; j.c0 = w.tj * T;          // absolute tile coordinates of the front
+   if (j.c0 + T <= j.g.c_lo) return false;
+   if (j.c0 >= j.g.c_hi || j.r0 >= j.g.m) return false;
+   j.nchunk = (j.g.k1 - j.g.k0 + BK - 1) / BK;
+   return true;
+}
+
+/* Persistent kernel: CTA b processes work items b, b+grid, ... ; T x T output
+ * tile per item, NWR x NWC warps, NS pipeline stages.  The TMA producer (warp
+ * 0) runs NS-1 K-chunks ahead of the math ACROSS tile boundaries, so the
+ * operand loads of the next tile are in flight while the current tile's
+ * epilogue (read-modify-write of C) drains. */
+template <int T, int NWR, int NWC, int NS>
 __global__ void __launch_bounds__(NWR * NWC * 32, 1)
-k_update(Front* fronts, const MatTile* work, int mode) {
+k_update(Front* fronts, const MatTile* work, int nwork, int mode) {
    constexpr int LDS = T + 4;
    constexpr int WTR = T / NWR, WTC = T / NWC;
    constexpr int NR = WTR / 8, NC = WTC / 8;
-   constexpr int NTHREADS = NWR * NWC * 32;
    constexpr int STAGE_DOUBLES = 2 * BK * LDS;
-
-   MatTile w = work[blockIdx.x];
-   const Front* f = &fronts[w.front];
-   const Region g = make_region(f, mode, T);
-   if (!g.valid) return;
-   const int tj = g.tj_base + w.tj;
-   const int ti = tj + w.ti;
-   const int r0 = ti * T, c0 = tj * T;
-   if (c0 >= g.c_hi || r0 >= g.m) return;
 
    extern __shared__ __align__(128) unsigned char smem_raw[];
    double* tiles = reinterpret_cast<double*>(smem_raw);
-   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double));
+   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_DOUBLES * sizeof(double));
 
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int wr = warp % NWR, wc = warp / NWR;
    const int rbase = wr * WTR, cbase = wc * WTC;
-   /* a warp whose sub-tile lies strictly above the diagonal has nothing to do */
-   const bool warp_active = (r0 + rbase + WTR > c0 + cbase) && (r0 + rbase < g.m)
-                            && (c0 + cbase < g.c_hi) && (c0 + cbase + WTC > g.c_lo);
 
    if (tid == 0) {
-      for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+      for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
 
-   const int klen = g.k1 - g.k0;
-   const int nchunk = (klen + BK - 1) / BK;
-   const int rowsA = min(T, g.rows_alloc - r0);   // even
-   const int rowsB = min(T, g.rows_alloc - c0);
-   const double* Ag = g.A + r0 + (size_t)g.k0 * g.lda;
-   const double* Bg = g.B + c0 + (size_t)g.k0 * g.ldb;
-
-   auto issue = [&](int chunk) {     // executed by warp 0
-      int s = chunk % NSTAGE;
-      int kc = min(BK, klen - chunk * BK);
+   /* producer cursor (used by warp 0 only): next (item, chunk) to load */
+   int p_item = blockIdx.x - gridDim.x, p_chunk = 0, p_g = 0;   // p_g: global chunk counter
+   TileJob pj; pj.nchunk = 0;
+   auto produce_one = [&]() -> bool {      // issues the loads of one K chunk; false when out of work
+      while (p_chunk >= pj.nchunk) {
+         p_item += gridDim.x; p_chunk = 0; pj.nchunk = 0;
+         if (p_item >= nwork) return false;
+         if (!load_job<T>(fronts, work, p_item, mode, pj)) pj.nchunk = 0;
+      }
+      const Region& g = pj.g;
+      const int klen = g.k1 - g.k0;
+      const int s = p_g % NS;
+      const int kc = min(BK, klen - p_chunk * BK);
+      const int rowsA = min(T, g.rows_alloc - pj.r0);   // even
+      const int rowsB = min(T, g.rows_alloc - pj.c0);
       double* st = tiles + (size_t)s * STAGE_DOUBLES;
       if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kc * (rowsA + rowsB) * sizeof(double)));
       __syncwarp();
+      const double* Ag = g.A + pj.r0 + (size_t)(g.k0 + p_chunk * BK) * g.lda;
+      const double* Bg = g.B + pj.c0 + (size_t)(g.k0 + p_chunk * BK) * g.ldb;
       for (int idx = lane; idx < 2 * kc; idx += 32) {
          int op = idx >= kc;
          int col = idx - op * kc;
-         size_t kabs = (size_t)chunk * BK + col;
-         if (op) bulk_g2s(st + BK * LDS + col * LDS, Bg + kabs * g.ldb, rowsB * sizeof(double), &full[s]);
-         else    bulk_g2s(st + col * LDS, Ag + kabs * g.lda, rowsA * sizeof(double), &full[s]);
+         if (op) bulk_g2s(st + BK * LDS + col * LDS, Bg + (size_t)col * g.ldb, rowsB * sizeof(double), &full[s]);
+         else    bulk_g2s(st + col * LDS, Ag + (size_t)col * g.lda, rowsA * sizeof(double), &full[s]);
       }
-      int kc4 = (kc + 3) & ~3;
+      const int kc4 = (kc + 3) & ~3;
       if (kc4 != kc) {                 // zero the K tail of both operands
          for (int col = kc; col < kc4; ++col)
             for (int i = lane; i < T; i += 32) { st[col * LDS + i] = 0.0; st[BK * LDS + col * LDS + i] = 0.0; }
       }
+      ++p_chunk; ++p_g;
+      return true;
    };
 
    if (warp == 0) {
-      for (int c = 0; c < NSTAGE - 1 && c < nchunk; ++c) issue(c);
+      for (int q = 0; q < NS - 1; ++q) if (!produce_one()) break;
    }
    __syncthreads();
 
-   double acc[NC][NR][2];
-   #pragma unroll
-   for (int j = 0; j < NC; ++j)
-      #pragma unroll
-      for (int i = 0; i < NR; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+   int c_g = 0;                          // consumer's global chunk counter
+   for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
+      TileJob cj;
+      if (!load_job<T>(fronts, work, item, mode, cj)) continue;
+      const Region& g = cj.g;
+      const int r0 = cj.r0, c0 = cj.c0;
+      /* a warp whose sub-tile lies strictly above the diagonal has nothing to do */
+      const bool warp_active = (r0 + rbase + WTR > c0 + cbase) && (r0 + rbase < g.m)
+                               && (c0 + cbase < g.c_hi) && (c0 + cbase + WTC > g.c_lo);
+      const int klen = g.k1 - g.k0;
 
-   for (int chunk = 0; chunk < nchunk; ++chunk) {
-      if (warp == 0 && chunk + NSTAGE - 1 < nchunk) issue(chunk + NSTAGE - 1);
-      const int s = chunk % NSTAGE;
-      mbar_wait(&full[s], (uint32_t)((chunk / NSTAGE) & 1));
-      if (warp_active) {
-         const int kc4 = (min(BK, klen - chunk * BK) + 3) & ~3;
-         const double* As = tiles + (size_t)s * STAGE_DOUBLES + (lane & 3) * LDS + rbase + (lane >> 2);
-         const double* Bs = As + BK * LDS - rbase + cbase;
+      double acc[NC][NR][2];
+      #pragma unroll
+      for (int j = 0; j < NC; ++j)
          #pragma unroll
-         for (int kk = 0; kk < BK; kk += 4) {
-            if (kk < kc4) {
-               double af[NR], bf[NC];
-               #pragma unroll
-               for (int i = 0; i < NR; ++i) af[i] = As[kk * LDS + i * 8];
-               #pragma unroll
-               for (int j = 0; j < NC; ++j) bf[j] = Bs[kk * LDS + j * 8];
-               #pragma unroll
-               for (int j = 0; j < NC; ++j)
+         for (int i = 0; i < NR; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+
+      for (int chunk = 0; chunk < cj.nchunk; ++chunk, ++c_g) {
+         if (warp == 0) produce_one();            // keeps NS-1 chunks in flight (may belong to the next tile)
+         const int s = c_g % NS;
+         mbar_wait(&full[s], (uint32_t)((c_g / NS) & 1));
+         if (warp_active) {
+            const int kc4 = (min(BK, klen - chunk * BK) + 3) & ~3;
+            const double* As = tiles + (size_t)s * STAGE_DOUBLES + (lane & 3) * LDS + rbase + (lane >> 2);
+            const double* Bs = As + BK * LDS - rbase + cbase;
+            #pragma unroll
+            for (int kk = 0; kk < BK; kk += 4) {
+               if (kk < kc4) {
+                  double af[NR], bf[NC];
                   #pragma unroll
-                  for (int i = 0; i < NR; ++i)
-                     dmma(acc[j][i][0], acc[j][i][1], bf[j], af[i]);
+                  for (int i = 0; i < NR; ++i) af[i] = As[kk * LDS + i * 8];
+                  #pragma unroll
+                  for (int j = 0; j < NC; ++j) bf[j] = Bs[kk * LDS + j * 8];
+                  #pragma unroll
+                  for (int j = 0; j < NC; ++j)
+                     #pragma unroll
+                     for (int i = 0; i < NR; ++i)
+                        dmma(acc[j][i][0], acc[j][i][1], bf[j], af[i]);
+               }
             }
          }
+         __syncthreads();   // everyone is done with stage s before it is refilled
       }
-      __syncthreads();   // everyone is done with stage s before it is refilled
-   }
 
-   if (!warp_active) return;
-   /* epilogue: thread holds rows r, r+1 of column c */
-   #pragma unroll
-   for (int j = 0; j < NC; ++j) {
-      const int c = c0 + cbase + j * 8 + (lane >> 2);
-      if (c < g.c_lo || c >= g.c_hi) continue;
-      double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
+      if (!warp_active) continue;
+      /* epilogue: thread holds rows r, r+1 of column c */
       #pragma unroll
-      for (int i = 0; i < NR; ++i) {
-         const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
-         const bool v0 = (r >= c) && (r < g.m);
-         const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
-         double* p = Cc + r;
-         if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-            double2 o;
-            if (g.accumulate) { o = *reinterpret_cast<double2*>(p); o.x -= acc[j][i][0]; o.y -= acc[j][i][1]; }
-            else { o.x = -acc[j][i][0]; o.y = -acc[j][i][1]; }
-            *reinterpret_cast<double2*>(p) = o;
-         } else {
-            if (v0) p[0] = g.accumulate ? p[0] - acc[j][i][0] : -acc[j][i][0];
-            if (v1) p[1] = g.accumulate ? p[1] - acc[j][i][1] : -acc[j][i][1];
+      for (int j = 0; j < NC; ++j) {
+         const int c = c0 + cbase + j * 8 + (lane >> 2);
+         if (c < g.c_lo || c >= g.c_hi) continue;
+         double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
+         #pragma unroll
+         for (int i = 0; i < NR; ++i) {
+            const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
+            const bool v0 = (r >= c) && (r < g.m);
+            const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
+            double* p = Cc + r;
+            if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+               double2 o;
+               if (g.accumulate) { o = *reinterpret_cast<double2*>(p); o.x -= acc[j][i][0]; o.y -= acc[j][i][1]; }
+               else { o.x = -acc[j][i][0]; o.y = -acc[j][i][1]; }
+               *reinterpret_cast<double2*>(p) = o;
+            } else {
+               if (v0) p[0] = g.accumulate ? p[0] - acc[j][i][0] : -acc[j][i][0];
+               if (v1) p[1] = g.accumulate ? p[1] - acc[j][i][1] : -acc[j][i][1];
+            }
          }
       }
    }
 }
 
-template <int T>
+template <int T, int NS>
 constexpr size_t update_smem_bytes() {
-   return (size_t)NSTAGE * 2 * BK * (T + 4) * sizeof(double) + NSTAGE * sizeof(uint64_t);
+   return (size_t)NS * 2 * BK * (T + 4) * sizeof(double) + NS * sizeof(uint64_t);
 }
 
 } // namespace
 
+/* Tile sizes: the inner (K <= 32) updates always use 64 x 64 tiles with a
+ * 2-stage pipeline (several CTAs per SM hide the latency of the short K loop);
+ * outer / contribution updates use 128 x 128 tiles on large fronts. */
 int update_tile_size(bool big_tiles) { return big_tiles ? 128 : 64; }
+int inner_tile_size() { return 64; }
+
+static int g_num_sms = 0;
 
 void configure_update_kernels() {
-   cudaFuncSetAttribute(k_update<128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)update_smem_bytes<128>());
-   cudaFuncSetAttribute(k_update<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)update_smem_bytes<64>());
+   cudaFuncSetAttribute(k_update<128, 2, 4, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)update_smem_bytes<128, NSTAGE>());
+   cudaFuncSetAttribute(k_update<64, 2, 2, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)update_smem_bytes<64, NSTAGE>());
+   cudaFuncSetAttribute(k_update<64, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)update_smem_bytes<64, 2>());
+   int dev = 0;
+   cudaGetDevice(&dev);
+   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
 void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
       bool big_tiles, cudaStream_t s) {
    if (nwork == 0) return;
-   if (big_tiles)
-      k_update<128, 2, 4><<<nwork, 256, update_smem_bytes<128>(), s>>>(fronts, work, (int)mode);
-   else
-      k_update<64, 2, 2><<<nwork, 128, update_smem_bytes<64>(), s>>>(fronts, work, (int)mode); COUNT_LAUNCH();
+   const int sms = g_num_sms > 0 ? g_num_sms : 148;
+   if (mode == UPD_INNER) {
+      int grid = std::min(nwork, sms * 5);
+      k_update<64, 2, 2, 2><<<grid, 128, update_smem_bytes<64, 2>(), s>>>(fronts, work, nwork, (int)mode);
+   } else if (big_tiles) {
+      int grid = std::min(nwork, sms);
+      k_update<128, 2, 4, NSTAGE><<<grid, 256, update_smem_bytes<128, NSTAGE>(), s>>>(fronts, work, nwork, (int)mode);
+   } else {
+      int grid = std::min(nwork, sms * 3);
+      k_update<64, 2, 2, NSTAGE><<<grid, 128, update_smem_bytes<64, NSTAGE>(), s>>>(fronts, work, nwork, (int)mode);
+   }
+   COUNT_LAUNCH();
 }
 
 } // namespace b200

@@ -272,6 +272,7 @@ struct Numeric {
    /* external contribution staging (device copies owned by this object) */
    std::vector<void*> ext_allocs;
    double timings[8] = {0};
+   double class_ms[16] = {0};          // profiling mode: device ms per kernel class (ProfClass order)
    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
    /* profiling of the Schur-complement launches (enabled by spral_ssids_b200_set_profile) */
    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -315,6 +316,32 @@ struct Numeric {
    }
 };
 
+/* Per-class kernel timing (profiling mode only): CUDA events around every launch. */
+enum ProfClass { PC_DIAG = 0, PC_APPLY, PC_COMMIT, PC_INNER, PC_SWAP, PC_OUTER, PC_CONTRIB, PC_ASSEMBLE, PC_INIT, PC_COUNT };
+struct Prof {
+   struct Rec { int cls; cudaEvent_t a, b; };
+   std::vector<Rec> recs;
+   double ms[PC_COUNT] = {0};
+   cudaEvent_t begin(cudaStream_t s) {
+      if (!g_profile) return nullptr;
+      cudaEvent_t a; cudaEventCreate(&a); cudaEventRecord(a, s); return a;
+   }
+   void end(int cls, cudaEvent_t a, cudaStream_t s) {
+      if (!a) return;
+      cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, s);
+      recs.push_back({cls, a, b});
+   }
+   void collect() {       // call after a stream synchronisation
+      for (auto& r : recs) {
+         float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.cls] += t;
+         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+      }
+      recs.clear();
+   }
+};
+static thread_local Prof* g_prof = nullptr;
+#define PROF(cls, stmt) do { cudaEvent_t pe_ = g_prof ? g_prof->begin(s) : nullptr; stmt; if (pe_) g_prof->end(cls, pe_, s); } while (0)
+
 template <class T>
 static T* upload(Bump& bump, const std::vector<T>& v, cudaStream_t s) {
    T* d = bump.take<T>(std::max<size_t>(v.size(), 1));
@@ -329,88 +356,143 @@ static bool is_device_pointer(const void* p, int* device) {
    return false;
 }
 
-/* One schedule of panels/steps over a set of fronts (first pass of a level or
- * a retry pass over the fronts that still have candidates). */
-struct PassLists {
-   std::vector<int> flist;                 // fronts sorted by remaining columns (descending)
-   std::vector<int> rem;                   // remaining candidate columns per entry of flist
-   std::vector<RowTile> rows; std::vector<int> rows_prefix;
-   std::vector<MatTile> inner; std::vector<int> inner_prefix;
-   std::vector<MatTile> outer; std::vector<int> outer_prefix;
+/* Host mirror of a front's pivoting state at panel boundaries.  The device
+ * takes every pivoting decision; the host only learns, once per outer panel
+ * (k_snapshot + one small D2H), how many columns were eliminated / failed, so
+ * that it can size the next launches exactly (no idle tiles). */
+struct HostState {
+   int fi = 0, m = 0, n = 0;
+   int done = 0, end = 0, pass_start = 0, p0 = 0, pend0 = 0, pend = 0;
+   bool finished = false;
 };
 
-static void build_pass_lists(const std::vector<Front>& F, const std::vector<int>& fronts,
-      const std::vector<int>& remaining, bool big, PassLists& P) {
-   const int T = update_tile_size(big);
-   std::vector<int> ord(fronts.size());
-   for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
-   std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return remaining[a] > remaining[b]; });
-   P = PassLists();
-   P.rows_prefix.push_back(0); P.inner_prefix.push_back(0); P.outer_prefix.push_back(0);
-   for (int o : ord) {
-      int fi = fronts[o];
-      const Front& f = F[fi];
-      P.flist.push_back(fi);
-      P.rem.push_back(remaining[o]);
-      int ntr = (f.m + RT - 1) / RT;
-      for (int t = 0; t < ntr; ++t) P.rows.push_back({fi, t});
-      P.rows_prefix.push_back((int)P.rows.size());
-      int mt = (f.m + T - 1) / T, nt = (f.n + T - 1) / T;
-      int ntc_inner = std::min(nt, PW / T + 1);
-      for (int tj = 0; tj < ntc_inner; ++tj)
-         for (int ti = 0; ti < mt; ++ti) P.inner.push_back({fi, ti, tj});
-      P.inner_prefix.push_back((int)P.inner.size());
-      if (f.n > PW) {
-         for (int tj = 0; tj < nt; ++tj)
-            for (int ti = 0; ti < mt - tj; ++ti) P.outer.push_back({fi, ti, tj});
-      }
-      P.outer_prefix.push_back((int)P.outer.size());
-   }
-}
-
-/* Issues the kernels of one pass.  remaining[i] candidates are processed for
- * front flist[i]: panels of PW, inner steps of BS. */
-static void run_pass(Numeric& N, Front* d_fronts, const PassLists& P, Bump& bump, bool big,
-      const FactorParams& prm) {
-   if (P.flist.empty()) return;
+/* Factorises the n fully-summed columns of every front in `fronts` (indices
+ * into the level-ordered Front array).  Panels of PW columns, inner steps of
+ * BS; failed columns are retried in later passes until a pass eliminates
+ * nothing.  Work buffers come from `wb` (grow-only, re-used panel by panel:
+ * every panel ends with a stream synchronisation). */
+static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& F,
+      const std::vector<int>& fronts, bool big, const FactorParams& prm, Buf& wb, double& t_sync) {
    cudaStream_t s = N.stream;
    const bool posdef = N.posdef;
-   int* d_flist = upload(bump, P.flist, s);
-   RowTile* d_rows = upload(bump, P.rows, s);
-   MatTile* d_inner = upload(bump, P.inner, s);
-   MatTile* d_outer = upload(bump, P.outer, s);
-   const int nf = (int)P.flist.size();
-   const int maxrem = P.rem[0];
-   const int npanel = (maxrem + PW - 1) / PW;
-   auto count_gt = [&](int thr) {   // #fronts with rem > thr (rem sorted descending)
-      int lo = 0, hi = nf;
-      while (lo < hi) { int mid = (lo + hi) / 2; if (P.rem[mid] > thr) lo = mid + 1; else hi = mid; }
-      return lo;
-   };
-   for (int p = 0; p < npanel; ++p) {
-      int prem = std::min(PW, maxrem - p * PW);
-      int nsteps = (prem + BS - 1) / BS;
-      for (int st = 0; st < nsteps; ++st) {
-         int na = count_gt(p * PW + st * BS);
-         if (na == 0) break;
-         launch_diag(d_fronts, d_flist, na, posdef, st == 0, prm, s);
-         launch_apply(d_fronts, d_rows, P.rows_prefix[na], posdef, prm, s);
-         if (!posdef) launch_commit(d_fronts, d_rows, P.rows_prefix[na], s);
-         launch_update(d_fronts, d_inner, P.inner_prefix[na], UPD_INNER, big, s);
-         if (!posdef) launch_swap(d_fronts, d_rows, P.rows_prefix[na], false, s);
+   const int T = update_tile_size(big), Ti = inner_tile_size();
+   std::vector<HostState> H(fronts.size());
+   for (size_t i = 0; i < fronts.size(); ++i) {
+      HostState& h = H[i];
+      const Front& f = F[fronts[i]];
+      h.fi = fronts[i]; h.m = f.m; h.n = f.n;
+      h.done = 0; h.end = f.n; h.pass_start = 0;
+      h.finished = (f.n == 0);
+      h.p0 = 0; h.pend0 = std::min(PW, f.n); h.pend = h.pend0;     // advance_state() opens the same panel
+   }
+   std::vector<int> snap_host;
+   int err = 0;
+   for (;;) {
+      /* active fronts, most candidates first (so that per-step launches use a prefix) */
+      std::vector<int> act;
+      for (size_t i = 0; i < H.size(); ++i) if (!H[i].finished) act.push_back((int)i);
+      if (act.empty()) break;
+      std::stable_sort(act.begin(), act.end(), [&](int a, int b) {
+         return H[a].pend0 - H[a].p0 > H[b].pend0 - H[b].p0; });
+      const int na_all = (int)act.size();
+      std::vector<int> flist(na_all), cand(na_all), rows_prefix(1, 0), inner_prefix(1, 0);
+      std::vector<RowTile> rows;
+      std::vector<MatTile> inner;
+      for (int k = 0; k < na_all; ++k) {
+         const HostState& h = H[act[k]];
+         flist[k] = h.fi; cand[k] = h.pend0 - h.p0;
+         int ntr = (h.m + RT - 1) / RT;
+         for (int t = 0; t < ntr; ++t) rows.push_back({h.fi, t});
+         rows_prefix.push_back((int)rows.size());
+         /* inner updates touch columns [p0, pend0) of rows >= p0 */
+         int mti = (h.m + Ti - 1) / Ti;
+         for (int tj = h.p0 / Ti; tj <= (h.pend0 - 1) / Ti; ++tj)
+            for (int ti = tj; ti < mti; ++ti) inner.push_back({h.fi, ti, tj});
+         inner_prefix.push_back((int)inner.size());
       }
-      /* Columns right of the panel need the panel's pivots.  Positive definite:
-       * only fronts with columns left.  Indefinite: failed columns of earlier
-       * panels sit at [end, n), so every front wider than one panel takes part
-       * in every one of its panels (the kernel exits when pend0 == n). */
-      int no = posdef ? count_gt((p + 1) * PW) : count_gt(std::max(PW, p * PW));
-      if (no > 0) {
-         launch_update(d_fronts, d_outer, P.outer_prefix[no], UPD_OUTER, big, s);
-         if (!posdef) launch_swap(d_fronts, d_rows, P.rows_prefix[no], true, s);
+      size_t need = 8192 + flist.size() * 2 * sizeof(int) * 8 + rows.size() * sizeof(RowTile) + inner.size() * sizeof(MatTile);
+      /* room for the outer list of this panel as well (bounded by all lower tiles) */
+      size_t outer_max = 0;
+      for (int k = 0; k < na_all; ++k) {
+         const HostState& h = H[act[k]];
+         size_t mt = (h.m + T - 1) / T, nt = (h.n + T - 1) / T;
+         outer_max += mt * nt;
+      }
+      need += outer_max * sizeof(MatTile) + rows.size() * sizeof(RowTile);
+      wb.ensure(need, s);
+      Bump bump; bump.reset(wb);
+      int* d_flist = upload(bump, flist, s);
+      RowTile* d_rows = upload(bump, rows, s);
+      MatTile* d_inner = upload(bump, inner, s);
+      int* d_snap = bump.take<int>((size_t)na_all * 8);
+
+      const int maxcand = cand[0];
+      const int nsteps = (maxcand + BS - 1) / BS;
+      auto count_gt = [&](int thr) {
+         int lo = 0, hi = na_all;
+         while (lo < hi) { int mid = (lo + hi) / 2; if (cand[mid] > thr) lo = mid + 1; else hi = mid; }
+         return lo;
+      };
+      for (int st = 0; st < nsteps; ++st) {
+         int na = count_gt(st * BS);
+         if (na == 0) break;
+         PROF(PC_DIAG, launch_diag(d_fronts, d_flist, na, posdef, st == 0, prm, s));
+         PROF(PC_APPLY, launch_apply(d_fronts, d_rows, rows_prefix[na], posdef, prm, s));
+         if (!posdef) PROF(PC_COMMIT, launch_commit(d_fronts, d_rows, rows_prefix[na], s));
+         PROF(PC_INNER, launch_update(d_fronts, d_inner, inner_prefix[na], UPD_INNER, big, s));
+         if (!posdef) PROF(PC_SWAP, launch_swap(d_fronts, d_rows, rows_prefix[na], false, s));
+      }
+      launch_snapshot(d_fronts, d_flist, na_all, d_snap, s);
+      snap_host.resize((size_t)na_all * 8);
+      CUDA_TRY(cudaMemcpyAsync(snap_host.data(), d_snap, snap_host.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+      auto ts0 = std::chrono::steady_clock::now();
+      CUDA_TRY(cudaStreamSynchronize(s));
+      t_sync += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
+      if (g_prof) g_prof->collect();
+
+      /* what happened in the panel; exact outer-update and swap work */
+      std::vector<MatTile> outer;
+      std::vector<RowTile> swap_rows;
+      for (int k = 0; k < na_all; ++k) {
+         HostState& h = H[act[k]];
+         const int* sn = &snap_host[(size_t)k * 8];   // p0, done, pend, pend0, end, finished, flag
+         if (sn[6] < 0) { err = err ? std::max(err, sn[6]) : sn[6]; h.finished = true; continue; }
+         if (sn[0] != h.p0 || sn[3] != h.pend0 || sn[4] != h.end)
+            throw std::runtime_error("host mirror of the pivoting state diverged from the device");
+         h.done = sn[1]; h.pend = sn[2];
+         if (h.done > h.p0 && h.pend0 < h.n) {
+            int mt = (h.m + T - 1) / T, nt = (h.n + T - 1) / T;
+            for (int tj = h.pend0 / T; tj < nt; ++tj)
+               for (int ti = tj; ti < mt; ++ti) outer.push_back({h.fi, ti, tj});
+         }
+         if (!posdef && h.pend0 - h.pend > 0 && h.end - h.pend0 > 0) {
+            int ntr = (h.m + RT - 1) / RT;
+            for (int t = 0; t < ntr; ++t) swap_rows.push_back({h.fi, t});
+         }
+      }
+      if (err) return err;
+      if (!outer.empty()) {
+         MatTile* d_outer = upload(bump, outer, s);
+         PROF(PC_OUTER, launch_update(d_fronts, d_outer, (int)outer.size(), UPD_OUTER, big, s));
+      }
+      if (!swap_rows.empty()) {
+         RowTile* d_sw = upload(bump, swap_rows, s);
+         PROF(PC_SWAP, launch_swap(d_fronts, d_sw, (int)swap_rows.size(), true, s));
+      }
+      /* mirror of advance_state(new_panel = true): close the panel, open the next */
+      for (int k = 0; k < na_all; ++k) {
+         HostState& h = H[act[k]];
+         if (h.finished) continue;
+         h.end -= h.pend0 - h.pend;
+         if (h.done == h.end) {
+            if (h.end == h.n) h.finished = true;
+            else if (h.done > h.pass_start) { h.pass_start = h.done; h.end = h.n; }
+            else h.finished = true;
+         }
+         if (!h.finished) { h.p0 = h.done; h.pend0 = std::min(h.done + PW, h.end); h.pend = h.pend0; }
       }
    }
-   launch_finalize(d_fronts, d_flist, nf, posdef, s);
-   CUDA_TRY(cudaGetLastError());
+   return 0;
 }
 
 static void factor_subtree(Numeric& N, const double* aval_in, const double* scaling_in,
@@ -430,6 +512,8 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
 
    FactorParams prm{opt->u, opt->small, opt->action ? 1 : 0};
    if (nloc == 0) return;
+   Prof prof;
+   struct ProfScope { ProfScope(Prof* p) { g_prof = g_profile ? p : nullptr; } ~ProfScope() { g_prof = nullptr; } } prof_scope(&prof);
 
    /* aval / scaling on the device (the H2D copy of A is part of the factor time,
     * as in gpu/subtree.f90:375-379) */
@@ -597,7 +681,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          }
       }
       CUDA_TRY(cudaMemcpyAsync(N.d_fronts + f0, &F[f0], nfl * sizeof(Front), cudaMemcpyHostToDevice, s));
-      CUDA_TRY(cudaMemsetAsync(lblock, 0, lbytes, s));
+      PROF(PC_INIT, CUDA_TRY(cudaMemsetAsync(lblock, 0, lbytes, s)));
 
       /* ---- per-level work lists ---- */
       std::vector<int2> scat;
@@ -644,39 +728,35 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          }
          for (int k : S.contribs_of_node[node]) add_src(ext[k].src);
       }
-      /* one work buffer per level; generous upper bound for the pass lists */
-      PassLists P;
-      build_pass_lists(F, lfronts, lrem, big, P);
       std::vector<MatTile> ctiles;
       {
          const int T = update_tile_size(big);
          for (int fi = f0; fi < f1; ++fi) {
             const Front& f = F[fi];
             if (f.m == f.n) continue;
-            int ntc = (f.m + T - 1) / T - f.n / T;
-            for (int tj = 0; tj < ntc; ++tj)
-               for (int ti = 0; ti < ntc - tj; ++ti) ctiles.push_back({fi, ti, tj});
+            int mt = (f.m + T - 1) / T;
+            for (int tj = f.n / T; tj < mt; ++tj)
+               for (int ti = tj; ti < mt; ++ti) ctiles.push_back({fi, ti, tj});
          }
       }
       size_t wbytes = 4096 + (scat.size() + dly.size()) * sizeof(int2) + srcs.size() * sizeof(AsmSrc)
-                    + (P.flist.size() + 64) * sizeof(int) + P.rows.size() * sizeof(RowTile)
-                    + (P.inner.size() + P.outer.size() + ctiles.size()) * sizeof(MatTile);
+                    + (lfronts.size() + 64) * sizeof(int) + ctiles.size() * sizeof(MatTile);
       for (auto& v : pre) wbytes += v.size() * sizeof(int2) + 256;
       for (auto& v : post) wbytes += v.size() * sizeof(int2) + 256;
       wbytes += 256 * 32;
-      S.b_work.ensure(2 * wbytes + (1 << 16), s);
+      S.b_work.ensure(wbytes + (1 << 16), s);
       Bump bump; bump.reset(S.b_work);
 
       /* ---- init + assemble (fully-summed part) ---- */
       int2* d_scat = upload(bump, scat, s);
-      launch_scatter_a(N.d_fronts, d_scat, (int)scat.size(), S.d_nlist, S.d_nptr, S.d_node_of_front,
-                       d_aval, d_scal, s);
+      PROF(PC_INIT, launch_scatter_a(N.d_fronts, d_scat, (int)scat.size(), S.d_nlist, S.d_nptr, S.d_node_of_front,
+                       d_aval, d_scal, s));
       AsmSrc* d_srcs = upload(bump, srcs, s);
       std::vector<int2*> d_post(MAXRANK + 1, nullptr);
       for (int r = 0; r <= MAXRANK; ++r) {
          if (!pre[r].empty()) {
             int2* d = upload(bump, pre[r], s);
-            launch_assemble(N.d_fronts, d_srcs, d, (int)pre[r].size(), false, r == MAXRANK, s);
+            PROF(PC_ASSEMBLE, launch_assemble(N.d_fronts, d_srcs, d, (int)pre[r].size(), false, r == MAXRANK, s));
          }
          if (!post[r].empty()) d_post[r] = upload(bump, post[r], s);
       }
@@ -686,28 +766,21 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       }
       MatTile* d_ctiles = upload(bump, ctiles, s);
 
-      /* ---- factorise: first pass, then retry passes while fronts have candidates ---- */
-      run_pass(N, N.d_fronts, P, bump, big, prm);
-      for (int iter = 0;; ++iter) {
+      /* ---- factorise the fully-summed columns (panel by panel, one sync per panel) ---- */
+      {
+         int err = factor_fronts(N, N.d_fronts, F, lfronts, big, prm, S.b_retry, t_sync);
+         if (err) { st.flag = err; *stats = st; return; }
+         int* d_lf = upload(bump, lfronts, s);
+         launch_finalize(N.d_fronts, d_lf, nfl, posdef, s);
          CUDA_TRY(cudaMemcpyAsync(&F[f0], N.d_fronts + f0, nfl * sizeof(Front), cudaMemcpyDeviceToHost, s));
          auto ts0 = std::chrono::steady_clock::now();
          CUDA_TRY(cudaStreamSynchronize(s));
          t_sync += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
-         std::vector<int> uf, urem;
-         int err = 0;
+         prof.collect();
          for (int fi = f0; fi < f1; ++fi) {
-            if (F[fi].flag < 0) err = err ? std::max(err, F[fi].flag) : F[fi].flag;
-            if (!F[fi].finished) { uf.push_back(fi); urem.push_back(F[fi].n - F[fi].done); }
+            if (F[fi].flag < 0) { st.flag = F[fi].flag; *stats = st; return; }
+            if (!F[fi].finished) throw std::runtime_error("front not finished after the panel loop");
          }
-         if (err) { st.flag = err; *stats = st; return; }
-         if (uf.empty()) break;
-         PassLists R;
-         build_pass_lists(F, uf, urem, big, R);
-         size_t rb = 4096 + R.flist.size() * sizeof(int) + R.rows.size() * sizeof(RowTile)
-                   + (R.inner.size() + R.outer.size()) * sizeof(MatTile) + 2048;
-         S.b_retry.ensure(rb, s);             // the stream is idle here: re-use is safe
-         Bump rbump; rbump.reset(S.b_retry);
-         run_pass(N, N.d_fronts, R, rbump, big, prm);
       }
 
       /* ---- Schur complement, then the children's contributions to it ---- */
@@ -716,7 +789,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
          CUDA_TRY(cudaEventRecord(a, s));
          nvtxRangePushA("upd_contrib");
-         launch_update(N.d_fronts, d_ctiles, (int)ctiles.size(), UPD_CONTRIB, big, s);
+         PROF(PC_CONTRIB, launch_update(N.d_fronts, d_ctiles, (int)ctiles.size(), UPD_CONTRIB, big, s));
          nvtxRangePop();
          CUDA_TRY(cudaEventRecord(b, s));
          N.prof_events.push_back({a, b});
@@ -727,7 +800,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       } else
       launch_update(N.d_fronts, d_ctiles, (int)ctiles.size(), UPD_CONTRIB, big, s);
       for (int r = 0; r <= MAXRANK; ++r)
-         if (d_post[r]) launch_assemble(N.d_fronts, d_srcs, d_post[r], (int)post[r].size(), true, r == MAXRANK, s);
+         if (d_post[r]) PROF(PC_ASSEMBLE, launch_assemble(N.d_fronts, d_srcs, d_post[r], (int)post[r].size(), true, r == MAXRANK, s));
       CUDA_TRY(cudaGetLastError());
 
       /* ---- statistics (cpu/factor.hxx:117-124, NumericSubtree.hxx:248-280) ---- */
@@ -797,6 +870,8 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       N.timings[2] = tot;              // ms inside the Schur-complement (UPD_CONTRIB) launches
       N.timings[3] = N.prof_flops;     // their algorithmic flops
       N.timings[4] = (double)N.prof_events.size();
+      prof.collect();
+      for (int i = 0; i < PC_COUNT; ++i) N.class_ms[i] = prof.ms[i];
    }
    *stats = st;
 }
@@ -1110,6 +1185,9 @@ void spral_ssids_gpu_subtree_get_timings(const void* p, double* ms, int n) {
    ABI_GUARD();
    const Numeric& N = *static_cast<const Numeric*>(p);
    for (int i = 0; i < n && i < 8; ++i) ms[i] = N.timings[i];
+   /* entries 8.. : profiling-mode device ms per kernel class: diag, apply, commit,
+    * inner update, swap, outer update, contrib, assemble, init */
+   for (int i = 8; i < n && i < 24; ++i) ms[i] = N.class_ms[i - 8];
 }
 
 } /* extern "C" */

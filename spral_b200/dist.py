@@ -23,7 +23,10 @@ The same driver runs on CPU for the world_size-2 gloo tests with the reference
 CPU engine standing in for the GPU engine and the store carrying the payload.
 """
 import ctypes as C
+import os
 import pickle
+import sys
+import time
 
 import numpy as np
 
@@ -261,9 +264,12 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
     numeric = [None] * nparts
     ext_rows = [None] * nparts        # rows of x outside the part that it touches (solve exchange)
     inform = _new_inform(a)
+    trace = os.environ.get("SPRAL_B200_TRACE")
+    t_start = time.perf_counter()
     for p in range(nparts):
         if ak.rank_of[p] != ctx.rank:
             continue
+        t_p0 = time.perf_counter()
         cc, fetched = [], []
         for c_part in ak.children[p]:
             if ak.rank_of[c_part] == ctx.rank:
@@ -273,6 +279,7 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
                 fetched.append(f)
                 cc.append(f.contrib)
         # children[] is ordered by part; the slots contrib_ptr[p].. follow the same order
+        t_p1 = time.perf_counter()
         if ctx.engine == "gpu":
             ns = ak.subtrees[p].factor(posdef, val, cc, options, sc)
             st = ns.stats
@@ -289,6 +296,7 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
         _accumulate(inform, st)
         if st.flag < 0:
             break
+        t_p2 = time.perf_counter()
         q = ak.consumer[p]
         if q >= 0:
             if ctx.engine == "gpu":
@@ -311,6 +319,11 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
             else:
                 publish_contrib(ctx, ak, p, ns)
                 ctx.store.set(_key(ctx, "ext_rows", p), pickle.dumps(ext_rows[p]))
+        if trace:
+            t_p3 = time.perf_counter()
+            print(f"[trace r{ctx.rank} e{ctx.epoch}] part {p}: start +{1e3*(t_p0-t_start):.1f} ms, fetch {1e3*(t_p1-t_p0):.1f}, "
+                  f"factor {1e3*(t_p2-t_p1):.1f} (dev {float(ns.timings()[1]) if ctx.engine == 'gpu' else 0:.1f}), "
+                  f"publish {1e3*(t_p3-t_p2):.1f} ms, flops {st.num_flops:.3g}", file=sys.stderr, flush=True)
     return DistFkeep(ak, posdef, numeric, finish_inform(a, inform), ext_rows, sc, ctx.epoch)
 
 

@@ -188,8 +188,8 @@ class NumericSubtree:
         return c
 
     def timings(self):
-        ms = np.zeros(8)
-        _lib.load().spral_ssids_gpu_subtree_get_timings(self._h, ms.ctypes.data_as(C.POINTER(C.c_double)), 8)
+        ms = np.zeros(24)
+        _lib.load().spral_ssids_gpu_subtree_get_timings(self._h, ms.ctypes.data_as(C.POINTER(C.c_double)), 24)
         return ms
 
     def close(self):

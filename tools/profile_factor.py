@@ -25,7 +25,10 @@ fk = sb.factor(ak, posdef, dval.data_ptr())
 torch.cuda.synchronize()
 dt = time.time() - t
 rt.cudaProfilerStop()
-print("factor", dt, "s", fk.inform["num_flops"] / dt / 1e9, "GF/s", "timings", fk.numeric[0].timings())
+tm = fk.numeric[0].timings()
+print("factor", dt, "s", fk.inform["num_flops"] / dt / 1e9, "GF/s", "timings", tm[:8])
+names = ["diag", "apply", "commit", "inner", "swap", "outer", "contrib(all)", "assemble", "init"]
+print("class ms:", {k: round(float(v), 2) for k, v in zip(names, tm[8:17])}, "sum", round(float(tm[8:17].sum()), 1))
 if len(sys.argv) > 3 and sys.argv[3] == "solve":
     a = ak.analysis
     x = torch.ones(n, dtype=torch.float64, device="cuda")
