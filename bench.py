@@ -44,39 +44,68 @@ def make_matrix(grid):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs (NVML in
+    process -- spawning nvidia-smi every 200 ms measurably perturbs the run)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.max_mhz, self.reasons = index, [], 0, set()
+        self._stop_evt = threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self._stop_evt.is_set():
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                return int(vis.split(",")[index])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+        return index
+
+    def _sample(self):
+        nv = self.nv
+        if nv is not None:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                              ("hw_thermal_slowdown", 0x40)):
+                if r & bit:
+                    self.reasons.add(name)
+        else:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                  str(self.index)], capture_output=True, text=True, timeout=5).stdout
+            r = [c.strip() for c in out.strip().split(",")]
+            self.sm.append(float(r[0])); self.max_mhz = max(self.max_mhz, float(r[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1 if self.nv is not None else 1.0)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(self.max_mhz) or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def cpu_reference_factor(grid, nthreads=0):
@@ -232,9 +261,10 @@ def main():
     e2e_value = flops / float(np.mean(e2e_t)) / 1e9
     front_bytes = 200 * a.nnodes           # sizeof(Front) per front, read back once per level
 
-    # ---- solves (fkeep%inner_solve): 1 and nrhs right-hand sides, device-resident x ----
-    A = None
-    solve_ms, bwd_err = {}, None
+    # ---- solves (fkeep%inner_solve): 1 and nrhs right-hand sides ----
+    # "device": b and x resident in HBM (CUDA-side permutation, sweeps, un-permutation);
+    # "e2e": host arrays in, host arrays out (adds the H2D / D2H copies of b and x).
+    solve_ms, bwd_err, bwd_ref1 = {}, None, None
     try:
         from spral_b200 import matrices as M
         A = M.to_scipy(n, ptr, row, val)
@@ -243,24 +273,26 @@ def main():
             X = np.asfortranarray(rng.uniform(-1, 1, (n, nr)))
             X[:, 0] = 1.0
             B = np.asfortranarray(A @ X)
-            sdist.solve(ctx, fk, B)                               # warm-up
+            Bd = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()
+            sdist.solve_device(ctx, fk, Bd)                       # warm-up
+            barrier()
+            t = time.perf_counter()
+            Xd = sdist.solve_device(ctx, fk, Bd)
+            torch.cuda.synchronize()
+            solve_ms[f"{nr}_device"] = 1e3 * max_over_ranks(time.perf_counter() - t)
             barrier()
             t = time.perf_counter()
             Xs = sdist.solve(ctx, fk, B)
-            torch.cuda.synchronize()
-            solve_ms[nr] = 1e3 * max_over_ranks(time.perf_counter() - t)
-            if rank == 0 and nr == 1:
-                import oracle_ref
-                bwd_err = float(oracle_ref.backward_error(A, Xs, B))
+            solve_ms[f"{nr}_e2e"] = 1e3 * max_over_ranks(time.perf_counter() - t)
+            if nr == 1:
                 R = B - A @ Xs
                 Xs2 = Xs + sdist.solve(ctx, fk, np.asfortranarray(R))
-                bwd_ref1 = float(oracle_ref.backward_error(A, Xs2, B))
-            elif nr == 1:
-                R = B - A @ Xs
-                sdist.solve(ctx, fk, np.asfortranarray(R))
+                if rank == 0:
+                    import oracle_ref
+                    bwd_err = float(oracle_ref.backward_error(A, Xs, B))
+                    bwd_ref1 = float(oracle_ref.backward_error(A, Xs2, B))
     except Exception as e:                                      # solve figures are extra
         solve_ms["error"] = repr(e)
-        bwd_ref1 = None
 
     # ---- roofline of the dominant kernel (profiled extra run, not part of the timing) ----
     roofline = None
@@ -295,7 +327,7 @@ def main():
         "clocks": clocks,
         "inform": {k: int(inform[k]) for k in ("flag", "num_neg", "num_two", "num_delay", "matrix_rank", "num_factor", "num_flops", "maxfront")},
         "solve_ms": {str(k): v for k, v in solve_ms.items()},
-        "backward_error": bwd_err, "backward_error_after_1_refinement": bwd_ref1 if rank == 0 else None,
+        "backward_error": bwd_err, "backward_error_after_1_refinement": bwd_ref1,
         "analyse_s": t_analyse,
     }
     if roofline:

@@ -128,6 +128,8 @@ struct SolveFront {    // immutable view of a factorised front for the solves
 };
 int solve_block();
 int solve_rhs_chunk(int nrhs);
+int solve_max_chunk();
+void configure_solve_kernels();
 void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps,
       bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s);
 void launch_fwd_flush(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,

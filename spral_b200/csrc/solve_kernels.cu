@@ -67,22 +67,16 @@ k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
       for (int k = 0; k < NR; ++k) xs[threadIdx.x][k] = (g >= 0) ? x[g + (size_t)k * ldx] : 0.0;
    }
    __syncthreads();
-   if (threadIdx.x < SB) {      // warp 0: forward substitution
-      const int lane = threadIdx.x;
-      for (int j = 0; j < wd; ++j) {
-         if (POSDEF) {
-            if (lane == j) {
-               #pragma unroll
-               for (int k = 0; k < NR; ++k) xs[j][k] /= lkk[j][j];
-            }
-            __syncwarp();
+   {  /* forward substitution: lanes are rows, the right-hand sides are dealt to the warps */
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int k = warp; k < NR; k += RT / 32) {
+         double v = xs[lane][k];
+         for (int j = 0; j < wd; ++j) {
+            double yj = __shfl_sync(0xffffffffu, v, j);
+            if (POSDEF) { yj /= lkk[j][j]; if (lane == j) v = yj; }
+            if (lane > j && lane < wd) v -= lkk[lane][j] * yj;
          }
-         if (lane > j && lane < wd) {
-            double l = lkk[lane][j];
-            #pragma unroll
-            for (int k = 0; k < NR; ++k) xs[lane][k] -= l * xs[j][k];
-         }
-         __syncwarp();
+         xs[lane][k] = v;
       }
    }
    __syncthreads();
@@ -171,10 +165,11 @@ k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
    const int r0 = w.tile * RT;
    if (r0 + RT <= j0 + wd || r0 >= f.m) return;   // no row of this tile below the block
 
-   __shared__ double tile[RT / 32][32][SB + 1];
-   __shared__ double xr[RT][NR];
-   /* red aliases tile once the tile has been consumed (NR <= 8 < SB + 1) */
-   double (*red)[SB][SB + 1] = tile;
+   extern __shared__ double smem_dyn[];
+   double (*tile)[32][SB + 1] = reinterpret_cast<double (*)[32][SB + 1]>(smem_dyn);
+   double (*xr)[NR] = reinterpret_cast<double (*)[NR]>(smem_dyn + (RT / 32) * 32 * (SB + 1));
+   /* red aliases tile once the tile has been consumed (NR <= 32 < SB + 1) */
+   double (*red)[32][SB + 1] = tile;
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int r = r0 + threadIdx.x;
    const bool active = (r >= j0 + wd) && (r < f.m);
@@ -212,9 +207,10 @@ k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
    }
 }
 
-/* one warp per front: y = x_blk - sum_t partial(t), solve L_kk^T z = y */
+/* one CTA per front: y = x_blk - sum_t partial(t) (fixed order), solve L_kk^T z = y;
+ * lanes are the block's columns, the right-hand sides are dealt to the warps */
 template <int NR, bool POSDEF>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(RT)
 k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, int step,
       double* __restrict__ x, int ldx, const double* __restrict__ pbuf) {
    const int fi = first + blockIdx.x;
@@ -223,47 +219,33 @@ k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, in
    if (b < 0) return;
    const int j0 = b * SB;
    const int wd = min(SB, f.nelim - j0);
-   const int lane = threadIdx.x;
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    __shared__ double lkk[SB][SB + 1];
-   __shared__ double ys[SB][NR];
    const size_t ldl = f.ldl;
-   for (int j = 0; j < SB; ++j)
-      lkk[lane][j] = (lane < wd && j < wd && lane >= j) ? f.L[(size_t)(j0 + lane) + (size_t)(j0 + j) * ldl] : 0.0;
+   for (int e = threadIdx.x; e < SB * SB; e += RT) {
+      int i = e % SB, j = e / SB;
+      lkk[i][j] = (i < wd && j < wd && i >= j) ? f.L[(size_t)(j0 + i) + (size_t)(j0 + j) * ldl] : 0.0;
+   }
+   __syncthreads();
    const int g = (lane < wd) ? f.perm[j0 + lane] - 1 : -1;
-   double y[NR];
-   #pragma unroll
-   for (int k = 0; k < NR; ++k) y[k] = (g >= 0) ? x[g + (size_t)k * ldx] : 0.0;
    /* tiles holding rows below the block, in increasing order */
    const int ntile = (f.m + RT - 1) / RT;
    const int t0 = (j0 + wd) / RT;
-   for (int t = t0; t < ntile; ++t) {
-      const double* p = pbuf + (size_t)(wbeg[fi] + t) * SB * NR;
-      #pragma unroll
-      for (int k = 0; k < NR; ++k) y[k] -= p[lane * NR + k];
-   }
-   #pragma unroll
-   for (int k = 0; k < NR; ++k) ys[lane][k] = y[k];
-   __syncwarp();
-   for (int j = wd - 1; j >= 0; --j) {
-      if (POSDEF) {
-         if (lane == j) {
-            #pragma unroll
-            for (int k = 0; k < NR; ++k) ys[j][k] /= lkk[j][j];
-         }
-         __syncwarp();
+   const double* pb = pbuf + (size_t)wbeg[fi] * SB * NR;
+   for (int k = warp; k < NR; k += RT / 32) {
+      double v = (g >= 0) ? x[g + (size_t)k * ldx] : 0.0;
+      for (int t = t0; t < ntile; ++t) v -= pb[(size_t)t * SB * NR + lane * NR + k];
+      for (int j = wd - 1; j >= 0; --j) {
+         double zj = __shfl_sync(0xffffffffu, v, j);
+         if (POSDEF) { zj /= lkk[j][j]; if (lane == j) v = zj; }
+         if (lane < j) v -= lkk[j][lane] * zj;
       }
-      if (lane < j) {
-         double l = lkk[j][lane];
-         #pragma unroll
-         for (int k = 0; k < NR; ++k) ys[lane][k] -= l * ys[j][k];
-      }
-      __syncwarp();
-   }
-   if (g >= 0) {
-      #pragma unroll
-      for (int k = 0; k < NR; ++k) x[g + (size_t)k * ldx] = ys[lane][k];
+      if (g >= 0) x[g + (size_t)k * ldx] = v;
    }
 }
+
+template <int NR>
+constexpr size_t reduce_smem() { return ((size_t)(RT / 32) * 32 * (SB + 1) + (size_t)RT * NR) * sizeof(double); }
 
 template <int NR>
 void fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps, bool posdef,
@@ -278,9 +260,9 @@ template <int NR>
 void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
       const int* wbeg, int nsteps, bool posdef, double* x, int ldx, double* pbuf, cudaStream_t s) {
    for (int st = 0; st < nsteps; ++st) {
-      k_bwd_reduce<NR><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, pbuf); COUNT_LAUNCH();
-      if (posdef) k_bwd_diag<NR, true><<<count, 32, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf);
-      else k_bwd_diag<NR, false><<<count, 32, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf); COUNT_LAUNCH();
+      k_bwd_reduce<NR><<<nwork, RT, reduce_smem<NR>(), s>>>(fronts, work, st, x, ldx, pbuf); COUNT_LAUNCH();
+      if (posdef) k_bwd_diag<NR, true><<<count, RT, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf);
+      else k_bwd_diag<NR, false><<<count, RT, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf); COUNT_LAUNCH();
    }
 }
 
@@ -288,13 +270,21 @@ void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* wo
 
 int solve_block() { return SB; }
 
+void configure_solve_kernels() {
+   cudaFuncSetAttribute(k_bwd_reduce<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduce_smem<32>());
+   cudaFuncSetAttribute(k_bwd_reduce<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduce_smem<16>());
+}
+
 /* Largest number of right-hand sides one kernel pass handles. */
-int solve_rhs_chunk(int nrhs) { return nrhs >= 8 ? 8 : nrhs >= 4 ? 4 : nrhs >= 2 ? 2 : 1; }
+int solve_rhs_chunk(int nrhs) { return nrhs >= 32 ? 32 : nrhs >= 16 ? 16 : nrhs >= 8 ? 8 : nrhs >= 4 ? 4 : nrhs >= 2 ? 2 : 1; }
+int solve_max_chunk() { return 32; }
 
 void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps,
       bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s) {
    if (nwork == 0 || nsteps == 0) return;
    switch (nr) {
+   case 32: fwd_level<32>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
+   case 16: fwd_level<16>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
    case 8: fwd_level<8>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
    case 4: fwd_level<4>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
    case 2: fwd_level<2>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
@@ -319,6 +309,8 @@ void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowT
       cudaStream_t s) {
    if (nwork == 0 || nsteps == 0) return;
    switch (nr) {
+   case 32: bwd_level<32>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
+   case 16: bwd_level<16>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
    case 8: bwd_level<8>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
    case 4: bwd_level<4>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
    case 2: bwd_level<2>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;

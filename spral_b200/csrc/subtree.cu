@@ -505,6 +505,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    CUDA_TRY(cudaStreamCreateWithFlags(&N.stream, cudaStreamNonBlocking));
    cudaStream_t s = N.stream;
    configure_update_kernels();
+   configure_solve_kernels();
    auto t_begin = std::chrono::steady_clock::now();
    CUDA_TRY(cudaEventCreate(&N.ev_begin));
    CUDA_TRY(cudaEventCreate(&N.ev_end));
@@ -901,7 +902,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
       }
       if (job == JOB_FWD) S.b_y.ensure(xbytes, s);
       if (job == JOB_DIAG_BWD || job == JOB_BWD)
-         S.b_pbuf.ensure(std::max<size_t>(N.max_level_work, 1) * solve_block() * 8 * sizeof(double), s);
+         S.b_pbuf.ensure(std::max<size_t>(N.max_level_work, 1) * solve_block() * solve_max_chunk() * sizeof(double), s);
       double* ywork = (double*)S.b_y.p;
       double* pbuf = (double*)S.b_pbuf.p;
       for (int r0 = 0; r0 < nrhs;) {

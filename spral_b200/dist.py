@@ -394,25 +394,43 @@ def _recv(ctx, kind, p, dev):
 
 def solve(ctx, fk, x, job=0):
     """ssids_solve / inner_solve_cpu (src/ssids/fkeep.F90:234-323) across ranks.
-    x: (n,) or (n, nrhs) numpy, same on every rank; returns the solution on every rank."""
+    x: (n,) or (n, nrhs) numpy, same on every rank; returns the solution on every rank.
+    The permutation to pivot order and the scaling (fkeep.F90:252-266, 300-315) run on
+    the device that holds the factors."""
     import torch
     a = fk.akeep.analysis
     n = a.n
     dev = torch.device("cuda", ctx.local_rank) if ctx.engine == "gpu" else torch.device("cpu")
     x = np.asarray(x, dtype=np.float64)
     one = x.ndim == 1
-    Xh = np.asfortranarray(x.reshape(n, -1))
-    nrhs = Xh.shape[1]
-    x2 = np.ascontiguousarray(Xh[a.invp - 1, :].T)            # (nrhs, n): pivot order (fkeep.F90:252-266)
-    if fk.scaling is not None and job in (0, 1):
-        x2 *= fk.scaling[None, :]
-    X = solve_pivot_order(ctx, fk, torch.from_numpy(x2).to(dev), job)
-    x2 = X.cpu().numpy()
-    if fk.scaling is not None and job in (0, 3, 4):
-        x2 = x2 * fk.scaling[None, :]
-    out = np.empty((n, nrhs), order="F")
-    out[a.invp - 1, :] = x2.T                                    # fkeep.F90:300-315
-    return out[:, 0] if one else out
+    Xh = x.reshape(n, -1)
+    X = torch.from_numpy(np.ascontiguousarray(Xh.T)).to(dev)         # (nrhs, n), original order
+    out = solve_device(ctx, fk, X, job)
+    res = np.asfortranarray(out.cpu().numpy().T)
+    return res[:, 0] if one else res
+
+
+def solve_device(ctx, fk, X, job=0):
+    """Same with X a torch tensor (nrhs, n) in ORIGINAL variable order on the compute
+    device; returns a tensor of the same shape (device resident end to end)."""
+    import torch
+    a = fk.akeep.analysis
+    dev = X.device
+    cache = getattr(fk, "_perm_cache", None)
+    if cache is None or cache[0].device != dev:
+        invp = torch.from_numpy(np.asarray(a.invp, dtype=np.int64) - 1).to(dev)
+        sc = torch.from_numpy(fk.scaling).to(dev) if fk.scaling is not None else None
+        cache = fk._perm_cache = (invp, sc)
+    invp, sc = cache
+    X2 = X.index_select(1, invp).contiguous()                       # x2(i) = x(invp(i))
+    if sc is not None and job in (0, 1):
+        X2 *= sc[None, :]
+    X2 = solve_pivot_order(ctx, fk, X2, job)
+    if sc is not None and job in (0, 3, 4):
+        X2 = X2 * sc[None, :]
+    out = torch.empty_like(X2)
+    out.index_copy_(1, invp, X2)                                    # x(invp(i)) = x2(i)
+    return out
 
 
 def solve_pivot_order(ctx, fk, X, job=0):

@@ -30,10 +30,17 @@ print("factor", dt, "s", fk.inform["num_flops"] / dt / 1e9, "GF/s", "timings", t
 names = ["diag", "apply", "commit", "inner", "swap", "outer", "contrib(all)", "assemble", "init"]
 print("class ms:", {k: round(float(v), 2) for k, v in zip(names, tm[8:17])}, "sum", round(float(tm[8:17].sum()), 1))
 if len(sys.argv) > 3 and sys.argv[3] == "solve":
+    nrhs = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     a = ak.analysis
-    x = torch.ones(n, dtype=torch.float64, device="cuda")
-    rt.cudaProfilerStart()
-    fk.numeric[0].solve_fwd(x.data_ptr(), 1, n)
-    fk.numeric[0].solve_diag_bwd(x.data_ptr(), 1, n)
-    torch.cuda.synchronize()
-    rt.cudaProfilerStop()
+    x = torch.ones(n * nrhs, dtype=torch.float64, device="cuda")
+    for rep in range(2):
+        if rep == 1:
+            rt.cudaProfilerStart()
+        torch.cuda.synchronize(); t = time.time()
+        fk.numeric[0].solve_fwd(x.data_ptr(), nrhs, n)
+        torch.cuda.synchronize(); t1 = time.time()
+        fk.numeric[0].solve_diag_bwd(x.data_ptr(), nrhs, n)
+        torch.cuda.synchronize(); t2 = time.time()
+        if rep == 1:
+            rt.cudaProfilerStop()
+        print(f"solve nrhs={nrhs}: fwd {1e3*(t1-t):.2f} ms, diag+bwd {1e3*(t2-t1):.2f} ms")
