@@ -39,6 +39,12 @@ namespace {
 
 constexpr int BK = 16;       // K columns per pipeline stage
 constexpr int NSTAGE = 4;
+#ifndef WS_NS
+#define WS_NS 3
+#endif
+#ifndef WS_BK
+#define WS_BK 32
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
    return (uint32_t)__cvta_generic_to_shared(p);
@@ -60,6 +66,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra.uni WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 /* TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier */
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -117,6 +126,44 @@ __device__ __forceinline__ Region make_region(const Front* f, int mode, int T) {
    return g;
 }
 
+/* Epilogue of one warp: thread holds rows r, r+1 of column c for NC x NR
+ * 8x8 sub-tiles.  All loads of a column batch are issued before its stores
+ * (a load after a possibly-aliasing store would serialise on memory latency). */
+template <int NC, int NR>
+__device__ __forceinline__ void store_tile(const Region& g, const double (&acc)[NC][NR][2],
+      int r0, int c0, int rbase, int cbase, int lane) {
+   #pragma unroll
+   for (int j = 0; j < NC; ++j) {
+      const int c = c0 + cbase + j * 8 + (lane >> 2);
+      if (c < g.c_lo || c >= g.c_hi) continue;
+      double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
+      double2 old[NR];
+      #pragma unroll
+      for (int i = 0; i < NR; ++i) {
+         const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
+         const bool v0 = (r >= c) && (r < g.m);
+         const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
+         double* p = Cc + r;
+         old[i].x = 0.0; old[i].y = 0.0;
+         if (g.accumulate) {
+            if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) old[i] = *reinterpret_cast<const double2*>(p);
+            else { if (v0) old[i].x = p[0]; if (v1) old[i].y = p[1]; }
+         }
+      }
+      #pragma unroll
+      for (int i = 0; i < NR; ++i) {
+         const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
+         const bool v0 = (r >= c) && (r < g.m);
+         const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
+         double* p = Cc + r;
+         double2 o;
+         o.x = old[i].x - acc[j][i][0]; o.y = old[i].y - acc[j][i][1];
+         if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) *reinterpret_cast<double2*>(p) = o;
+         else { if (v0) p[0] = o.x; if (v1) p[1] = o.y; }
+      }
+   }
+}
+
 /* What one CTA needs to know about one output tile. */
 struct TileJob {
    Region g;
@@ -124,7 +171,7 @@ struct TileJob {
    int nchunk;
 };
 
-template <int T>
+template <int T, int BKT = BK>
 __device__ __forceinline__ bool load_job(const Front* fronts, const MatTile* work, int item, int mode, TileJob& j) {
    MatTile w = work[item];
    j.g = make_region(&fronts[w.front], mode, T);
@@ -132,7 +179,7 @@ __device__ __forceinline__ bool load_job(const Front* fronts, const MatTile* wor
    j.r0 = w.ti * T; j.c0 = w.tj * T;          // absolute tile coordinates of the front
    if (j.c0 + T <= j.g.c_lo) return false;
    if (j.c0 >= j.g.c_hi || j.r0 >= j.g.m) return false;
-   j.nchunk = (j.g.k1 - j.g.k0 + BK - 1) / BK;
+   j.nchunk = (j.g.k1 - j.g.k0 + BKT - 1) / BKT;
    return true;
 }
 
@@ -248,35 +295,126 @@ k_update(Front* fronts, const MatTile* work, int nwork, int mode) {
       }
 
       if (!warp_active) continue;
-      /* epilogue: thread holds rows r, r+1 of column c */
-      #pragma unroll
-      for (int j = 0; j < NC; ++j) {
-         const int c = c0 + cbase + j * 8 + (lane >> 2);
-         if (c < g.c_lo || c >= g.c_hi) continue;
-         double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
-         #pragma unroll
-         for (int i = 0; i < NR; ++i) {
-            const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
-            const bool v0 = (r >= c) && (r < g.m);
-            const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
-            double* p = Cc + r;
-            if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-               double2 o;
-               if (g.accumulate) { o = *reinterpret_cast<double2*>(p); o.x -= acc[j][i][0]; o.y -= acc[j][i][1]; }
-               else { o.x = -acc[j][i][0]; o.y = -acc[j][i][1]; }
-               *reinterpret_cast<double2*>(p) = o;
-            } else {
-               if (v0) p[0] = g.accumulate ? p[0] - acc[j][i][0] : -acc[j][i][0];
-               if (v1) p[1] = g.accumulate ? p[1] - acc[j][i][1] : -acc[j][i][1];
-            }
-         }
-      }
+      store_tile<NC, NR>(g, acc, r0, c0, rbase, cbase, lane);
    }
 }
 
-template <int T, int NS>
+/* Warp-specialised variant for the large tiles: NWR x NWC consumer warps issue
+ * the DMMAs, one extra producer warp drives the TMA bulk copies.  Stages are
+ * handed back and forth with full[] / empty[] mbarriers, so there is no
+ * block-wide barrier in the main loop: a consumer warp only waits for data, the
+ * producer only for the slowest consumer of the stage it wants to refill, and
+ * it keeps loading across tile boundaries while the consumers run the epilogue. */
+template <int T, int NWR, int NWC, int NS, int BKT>
+__global__ void __launch_bounds__((NWR * NWC + 1) * 32, 1)
+k_update_ws(Front* fronts, const MatTile* work, int nwork, int mode) {
+   constexpr int LDS = T + 4;
+   constexpr int WTR = T / NWR, WTC = T / NWC;
+   constexpr int NR = WTR / 8, NC = WTC / 8;
+   constexpr int NCONS = NWR * NWC;
+   constexpr int STAGE_DOUBLES = 2 * BKT * LDS;
+
+   extern __shared__ __align__(128) unsigned char smem_raw[];
+   double* tiles = reinterpret_cast<double*>(smem_raw);
+   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_DOUBLES * sizeof(double));
+   uint64_t* empty = full + NS;
+
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   if (tid == 0) {
+      for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+
+   if (warp == NCONS) {
+      /* ---------------- producer warp ---------------- */
+      int g = 0;
+      for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
+         TileJob pj;
+         if (!load_job<T, BKT>(fronts, work, item, mode, pj)) continue;
+         const Region& rg = pj.g;
+         const int klen = rg.k1 - rg.k0;
+         const int rowsA = min(T, rg.rows_alloc - pj.r0);   // even
+         const int rowsB = min(T, rg.rows_alloc - pj.c0);
+         for (int chunk = 0; chunk < pj.nchunk; ++chunk, ++g) {
+            const int s = g % NS;
+            if (g >= NS) mbar_wait(&empty[s], (uint32_t)(((g / NS) & 1) ^ 1));
+            const int kc = min(BKT, klen - chunk * BKT);
+            double* st = tiles + (size_t)s * STAGE_DOUBLES;
+            const int kc4 = (kc + 3) & ~3;
+            if (kc4 != kc) {              // zero the K tail of both operands
+               for (int col = kc; col < kc4; ++col)
+                  for (int i = lane; i < T; i += 32) { st[col * LDS + i] = 0.0; st[BKT * LDS + col * LDS + i] = 0.0; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kc * (rowsA + rowsB) * sizeof(double)));
+            __syncwarp();
+            const double* Ag = rg.A + pj.r0 + (size_t)(rg.k0 + chunk * BKT) * rg.lda;
+            const double* Bg = rg.B + pj.c0 + (size_t)(rg.k0 + chunk * BKT) * rg.ldb;
+            for (int idx = lane; idx < 2 * kc; idx += 32) {
+               int op = idx >= kc;
+               int col = idx - op * kc;
+               if (op) bulk_g2s(st + BKT * LDS + col * LDS, Bg + (size_t)col * rg.ldb, rowsB * sizeof(double), &full[s]);
+               else    bulk_g2s(st + col * LDS, Ag + (size_t)col * rg.lda, rowsA * sizeof(double), &full[s]);
+            }
+         }
+      }
+      return;
+   }
+
+   /* ---------------- consumer warps ---------------- */
+   const int wr = warp % NWR, wc = warp / NWR;
+   const int rbase = wr * WTR, cbase = wc * WTC;
+   int g = 0;
+   for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
+      TileJob cj;
+      if (!load_job<T, BKT>(fronts, work, item, mode, cj)) continue;
+      const Region& rg = cj.g;
+      const int r0 = cj.r0, c0 = cj.c0;
+      const bool warp_active = (r0 + rbase + WTR > c0 + cbase) && (r0 + rbase < rg.m)
+                               && (c0 + cbase < rg.c_hi) && (c0 + cbase + WTC > rg.c_lo);
+      const int klen = rg.k1 - rg.k0;
+      double acc[NC][NR][2];
+      #pragma unroll
+      for (int j = 0; j < NC; ++j)
+         #pragma unroll
+         for (int i = 0; i < NR; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+
+      for (int chunk = 0; chunk < cj.nchunk; ++chunk, ++g) {
+         const int s = g % NS;
+         mbar_wait(&full[s], (uint32_t)((g / NS) & 1));
+         if (warp_active) {
+            const int kc4 = (min(BKT, klen - chunk * BKT) + 3) & ~3;
+            const double* As = tiles + (size_t)s * STAGE_DOUBLES + (lane & 3) * LDS + rbase + (lane >> 2);
+            const double* Bs = As + BKT * LDS - rbase + cbase;
+            #pragma unroll
+            for (int kk = 0; kk < BKT; kk += 4) {
+               if (kk < kc4) {
+                  double af[NR], bf[NC];
+                  #pragma unroll
+                  for (int i = 0; i < NR; ++i) af[i] = As[kk * LDS + i * 8];
+                  #pragma unroll
+                  for (int j = 0; j < NC; ++j) bf[j] = Bs[kk * LDS + j * 8];
+                  #pragma unroll
+                  for (int j = 0; j < NC; ++j)
+                     #pragma unroll
+                     for (int i = 0; i < NR; ++i)
+                        dmma(acc[j][i][0], acc[j][i][1], bf[j], af[i]);
+               }
+            }
+         }
+         __syncwarp();
+         if (lane == 0) mbar_arrive(&empty[s]);      // this warp is done with stage s
+      }
+
+      if (!warp_active) continue;
+      store_tile<NC, NR>(rg, acc, r0, c0, rbase, cbase, lane);
+   }
+}
+
+template <int T, int NS, int BKT = BK>
 constexpr size_t update_smem_bytes() {
-   return (size_t)NS * 2 * BK * (T + 4) * sizeof(double) + NS * sizeof(uint64_t);
+   return (size_t)NS * 2 * BKT * (T + 4) * sizeof(double) + 2 * NS * sizeof(uint64_t);
 }
 
 } // namespace
@@ -290,8 +428,8 @@ int inner_tile_size() { return 64; }
 static int g_num_sms = 0;
 
 void configure_update_kernels() {
-   cudaFuncSetAttribute(k_update<128, 2, 4, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)update_smem_bytes<128, NSTAGE>());
+   cudaFuncSetAttribute(k_update_ws<128, 2, 4, WS_NS, WS_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)update_smem_bytes<128, WS_NS, WS_BK>());
    cudaFuncSetAttribute(k_update<64, 2, 2, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                         (int)update_smem_bytes<64, NSTAGE>());
    cudaFuncSetAttribute(k_update<64, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -310,7 +448,7 @@ void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mod
       k_update<64, 2, 2, 2><<<grid, 128, update_smem_bytes<64, 2>(), s>>>(fronts, work, nwork, (int)mode);
    } else if (big_tiles) {
       int grid = std::min(nwork, sms);
-      k_update<128, 2, 4, NSTAGE><<<grid, 256, update_smem_bytes<128, NSTAGE>(), s>>>(fronts, work, nwork, (int)mode);
+      k_update_ws<128, 2, 4, WS_NS, WS_BK><<<grid, 288, update_smem_bytes<128, WS_NS, WS_BK>(), s>>>(fronts, work, nwork, (int)mode);
    } else {
       int grid = std::min(nwork, sms * 3);
       k_update<64, 2, 2, NSTAGE><<<grid, 128, update_smem_bytes<64, NSTAGE>(), s>>>(fronts, work, nwork, (int)mode);

@@ -319,7 +319,8 @@ struct Numeric {
 /* Per-class kernel timing (profiling mode only): CUDA events around every launch. */
 enum ProfClass { PC_DIAG = 0, PC_APPLY, PC_COMMIT, PC_INNER, PC_SWAP, PC_OUTER, PC_CONTRIB, PC_ASSEMBLE, PC_INIT, PC_COUNT };
 struct Prof {
-   struct Rec { int cls; cudaEvent_t a, b; };
+   struct Rec { int cls; cudaEvent_t a, b; double flops; int ntiles; };
+   double next_flops = 0; int next_tiles = 0;   // annotation for the next record (trace output)
    std::vector<Rec> recs;
    double ms[PC_COUNT] = {0};
    cudaEvent_t begin(cudaStream_t s) {
@@ -329,11 +330,15 @@ struct Prof {
    void end(int cls, cudaEvent_t a, cudaStream_t s) {
       if (!a) return;
       cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, s);
-      recs.push_back({cls, a, b});
+      recs.push_back({cls, a, b, next_flops, next_tiles});
+      next_flops = 0; next_tiles = 0;
    }
    void collect() {       // call after a stream synchronisation
       for (auto& r : recs) {
          float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.cls] += t;
+         if (r.flops > 0 && getenv("SPRAL_B200_TRACE"))
+            fprintf(stderr, "[launch] class %d tiles %d flops %.3e ms %.3f -> %.2f TF/s\n", r.cls, r.ntiles, r.flops, t,
+                    r.flops / t / 1e9);
          cudaEventDestroy(r.a); cudaEventDestroy(r.b);
       }
       recs.clear();
@@ -461,6 +466,10 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
             throw std::runtime_error("host mirror of the pivoting state diverged from the device");
          h.done = sn[1]; h.pend = sn[2];
          if (h.done > h.p0 && h.pend0 < h.n) {
+            if (g_prof) {
+               double K = h.done - h.p0, nn = h.n, c0 = h.pend0, mm = h.m;
+               g_prof->next_flops += 2.0 * K * ((nn - c0) * mm - (nn * (nn - 1) - c0 * (c0 - 1)) / 2.0);
+            }
             int mt = (h.m + T - 1) / T, nt = (h.n + T - 1) / T;
             for (int tj = h.pend0 / T; tj < nt; ++tj)
                for (int ti = tj; ti < mt; ++ti) outer.push_back({h.fi, ti, tj});
@@ -473,6 +482,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       if (err) return err;
       if (!outer.empty()) {
          MatTile* d_outer = upload(bump, outer, s);
+         if (g_prof) g_prof->next_tiles = (int)outer.size();
          PROF(PC_OUTER, launch_update(d_fronts, d_outer, (int)outer.size(), UPD_OUTER, big, s));
       }
       if (!swap_rows.empty()) {
