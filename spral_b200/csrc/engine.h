@@ -118,7 +118,7 @@ enum UpdateMode { UPD_INNER = 0, UPD_OUTER = 1, UPD_CONTRIB = 2 };
 void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
       bool big_tiles, cudaStream_t s);
 int update_tile_size(bool big_tiles);
-int inner_tile_size();
+int inner_tile_size(bool big_tiles);
 void configure_update_kernels();   // per device: opt in to > 48 KB dynamic shared memory
 
 /* ---- solve (solve_kernels.cu) ---- */
@@ -127,6 +127,7 @@ struct SolveFront {    // immutable view of a factorised front for the solves
    int ldl, m, n, n0, m0, nelim;
 };
 int solve_block();
+void launch_transpose_rhs(double* x, int ldx, double* xt, int n, int nr, bool to_xt, cudaStream_t s);
 int solve_rhs_chunk(int nrhs);
 int solve_max_chunk();
 void configure_solve_kernels();

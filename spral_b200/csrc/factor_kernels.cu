@@ -113,15 +113,31 @@ k_assemble(Front* fronts, const AsmSrc* srcs, const int2* work, int to_contrib) 
    int roff;
    if (to_contrib) { dest = p->C; ldd = p->ldc; roff = -n0; }
    else            { dest = p->L; ldd = p->ldl; roff = 0; }
+   /* column images of this CTA's child columns */
+   __shared__ int s_col[ASM_COLS];
+   if (threadIdx.x < ASM_COLS) s_col[threadIdx.x] = (j0 + (int)threadIdx.x < j1) ? map[j0 + threadIdx.x] - 1 + roff : 0;
+   __syncthreads();
+   const int nj = j1 - j0;
    for (int i = j0 + threadIdx.x; i < cm; i += blockDim.x) {
       int pi = map[i] - 1;
       int r = to_contrib ? pi - n0 : (pi < n0 ? pi : pi + ndin);
-      int jmax = min(j1, i + 1);
-      for (int j = j0; j < jmax; ++j) {
-         double v = C[i + (size_t)j * ldc];
-         size_t d = (size_t)r + (size_t)(map[j] - 1 + roff) * ldd;
-         if (ATOMIC) atomicAdd(&dest[d], v);
-         else dest[d] += v;
+      /* all loads of the row first, then the stores: a load issued after a
+       * possibly-aliasing store would wait for it */
+      double v[ASM_COLS], old[ASM_COLS];
+      #pragma unroll
+      for (int q = 0; q < ASM_COLS; ++q) {
+         bool on = (q < nj) && (j0 + q <= i);
+         v[q] = on ? C[i + (size_t)(j0 + q) * ldc] : 0.0;
+         if (!ATOMIC) old[q] = on ? dest[(size_t)r + (size_t)s_col[q] * ldd] : 0.0;
+      }
+      #pragma unroll
+      for (int q = 0; q < ASM_COLS; ++q) {
+         bool on = (q < nj) && (j0 + q <= i);
+         if (on) {
+            size_t d = (size_t)r + (size_t)s_col[q] * ldd;
+            if (ATOMIC) atomicAdd(&dest[d], v[q]);
+            else dest[d] = old[q] + v[q];
+         }
       }
    }
 }
@@ -292,19 +308,21 @@ k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams
 
    int zfrom = BS;
    int p = 0;
-   while (p < bs) {
-      /* largest remaining entry of the lower triangle (ties: smallest column, then row) */
-      {
-         double v = (r >= c && c >= p && r < bs) ? fabs(A[cur][r][c]) : -1.0;
-         int rr = r;
-         #pragma unroll
-         for (int off = 16; off > 0; off >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, v, off);
-            int orr = __shfl_xor_sync(0xffffffffu, rr, off);
-            if (ov > v || (ov == v && orr < rr)) { v = ov; rr = orr; }
-         }
-         if (r == 0) { cmax[c] = v; crow[c] = rr; }
+   /* column-wise maxima of the remaining lower triangle (ties: smallest row); the
+    * search for pivot p+1 is folded into the update of pivot p */
+   auto column_max = [&](double val, int pp) {
+      double v = (r >= c && c >= pp && r < bs) ? fabs(val) : -1.0;
+      int rr = r;
+      #pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+         double ov = __shfl_xor_sync(0xffffffffu, v, off);
+         int orr = __shfl_xor_sync(0xffffffffu, rr, off);
+         if (ov > v || (ov == v && orr < rr)) { v = ov; rr = orr; }
       }
+      if (r == 0) { cmax[c] = v; crow[c] = rr; }
+   };
+   column_max(A[cur][r][c], 0);
+   while (p < bs) {
       __syncthreads();
       /* one warp takes the decision and does the divisions; everybody else waits */
       if (c == 0) {
@@ -408,9 +426,9 @@ k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams
       A[cur ^ 1][r][c] = vnew;
       /* LD is only meaningful strictly below the diagonal of eliminated columns */
       LDm[cur ^ 1][r][c] = (r > c) ? ldnew : 0.0;
-      __syncthreads();
       cur ^= 1;
       p += pivsiz;
+      if (p < bs) column_max(vnew, p);      // cmax was consumed before the previous barrier
    }
 
    /* publish L11 (unit lower), L11*D, D^-1 and the local permutation */

@@ -27,6 +27,7 @@
  * which keeps every bulk copy 16-byte aligned whatever the pivoting state is.
  */
 #include <algorithm>
+#include <cstdlib>
 #include "engine.h"
 #include "device_utils.cuh"
 
@@ -160,6 +161,24 @@ __device__ __forceinline__ void store_tile(const Region& g, const double (&acc)[
          o.x = old[i].x - acc[j][i][0]; o.y = old[i].y - acc[j][i][1];
          if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) *reinterpret_cast<double2*>(p) = o;
          else { if (v0) p[0] = o.x; if (v1) p[1] = o.y; }
+      }
+   }
+}
+
+/* L2 prefetch of the warp's part of the output tile (accumulate mode): issued
+ * when the tile starts so that the epilogue's loads hit the L2. */
+template <int NC, int NR>
+__device__ __forceinline__ void prefetch_tile(const Region& g, int r0, int c0, int rbase, int cbase, int lane) {
+   if (!g.accumulate) return;
+   #pragma unroll
+   for (int j = 0; j < NC; ++j) {
+      const int c = c0 + cbase + j * 8 + (lane >> 2);
+      if (c < g.c_lo || c >= g.c_hi) continue;
+      const double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
+      #pragma unroll
+      for (int i = 0; i < NR; i += 2) {      // 8 rows of a column = 64 B: two sub-tiles share a 128-B line
+         const int r = r0 + rbase + i * 8;
+         if ((lane & 3) == 0 && r < g.m) asm volatile("prefetch.global.L2 [%0];" :: "l"(Cc + r));
       }
    }
 }
@@ -374,6 +393,7 @@ k_update_ws(Front* fronts, const MatTile* work, int nwork, int mode) {
       const bool warp_active = (r0 + rbase + WTR > c0 + cbase) && (r0 + rbase < rg.m)
                                && (c0 + cbase < rg.c_hi) && (c0 + cbase + WTC > rg.c_lo);
       const int klen = rg.k1 - rg.k0;
+      if (warp_active) prefetch_tile<NC, NR>(rg, r0, c0, rbase, cbase, lane);
       double acc[NC][NR][2];
       #pragma unroll
       for (int j = 0; j < NC; ++j)
@@ -423,7 +443,7 @@ constexpr size_t update_smem_bytes() {
  * 2-stage pipeline (several CTAs per SM hide the latency of the short K loop);
  * outer / contribution updates use 128 x 128 tiles on large fronts. */
 int update_tile_size(bool big_tiles) { return big_tiles ? 128 : 64; }
-int inner_tile_size() { return 64; }
+int inner_tile_size(bool big_tiles) { return (big_tiles && getenv("SPRAL_B200_INNER128")) ? 128 : 64; }
 
 static int g_num_sms = 0;
 
@@ -443,7 +463,7 @@ void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mod
       bool big_tiles, cudaStream_t s) {
    if (nwork == 0) return;
    const int sms = g_num_sms > 0 ? g_num_sms : 148;
-   if (mode == UPD_INNER) {
+   if (mode == UPD_INNER && inner_tile_size(big_tiles) == 64) {
       int grid = std::min(nwork, sms * 5);
       k_update<64, 2, 2, 2><<<grid, 128, update_smem_bytes<64, 2>(), s>>>(fronts, work, nwork, (int)mode);
    } else if (big_tiles) {

@@ -34,6 +34,11 @@ namespace {
 
 constexpr int SB = 32;    // solve block
 
+/* Inside the sweeps the right-hand sides of a chunk are stored RHS-contiguous
+ * (x^T: entry (g, k) at g*NR + k), so a row of the front touches one 8*NR-byte
+ * segment instead of NR segments ldx apart (the ABI's column-major layout). */
+#define XI(g, k) ((size_t)(g) * NR + (k))
+
 __device__ __forceinline__ int row_index(const SolveFront& f, int i) {
    return (i < f.n ? f.perm[i] : f.rows[f.n0 + i - f.n]) - 1;
 }
@@ -64,26 +69,35 @@ k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
       int g = (threadIdx.x < wd) ? f.perm[j0 + threadIdx.x] - 1 : -1;
       gidx[threadIdx.x] = g;
       #pragma unroll
-      for (int k = 0; k < NR; ++k) xs[threadIdx.x][k] = (g >= 0) ? x[g + (size_t)k * ldx] : 0.0;
+      for (int k = 0; k < NR; ++k) xs[threadIdx.x][k] = (g >= 0) ? x[XI(g, k)] : 0.0;
    }
    __syncthreads();
-   {  /* forward substitution: lanes are rows, the right-hand sides are dealt to the warps */
+   {  /* forward substitution: lanes are rows; every warp takes NR/4 right-hand sides and
+       * advances them together (independent dependency chains hide the shuffle latency) */
+      constexpr int NW = RT / 32;
+      constexpr int NRW = (NR + NW - 1) / NW;
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      for (int k = warp; k < NR; k += RT / 32) {
-         double v = xs[lane][k];
-         for (int j = 0; j < wd; ++j) {
-            double yj = __shfl_sync(0xffffffffu, v, j);
-            if (POSDEF) { yj /= lkk[j][j]; if (lane == j) v = yj; }
-            if (lane > j && lane < wd) v -= lkk[lane][j] * yj;
+      double v[NRW];
+      #pragma unroll
+      for (int q = 0; q < NRW; ++q) { int k = warp * NRW + q; v[q] = (k < NR) ? xs[lane][k] : 0.0; }
+      for (int j = 0; j < wd; ++j) {
+         const double l = (lane > j && lane < wd) ? lkk[lane][j] : 0.0;
+         const double dj = POSDEF ? lkk[j][j] : 1.0;
+         #pragma unroll
+         for (int q = 0; q < NRW; ++q) {
+            double yj = __shfl_sync(0xffffffffu, v[q], j);
+            if (POSDEF) { yj /= dj; if (lane == j) v[q] = yj; }
+            v[q] -= l * yj;
          }
-         xs[lane][k] = v;
       }
+      #pragma unroll
+      for (int q = 0; q < NRW; ++q) { int k = warp * NRW + q; if (k < NR) xs[lane][k] = v[q]; }
    }
    __syncthreads();
    /* the CTA owning the block's first row publishes y */
    if (w.tile == j0 / RT && threadIdx.x < wd) {
       #pragma unroll
-      for (int k = 0; k < NR; ++k) ywork[gidx[threadIdx.x] + (size_t)k * ldx] = xs[threadIdx.x][k];
+      for (int k = 0; k < NR; ++k) ywork[XI(gidx[threadIdx.x], k)] = xs[threadIdx.x][k];
    }
    const int r = r0 + threadIdx.x;
    if (r >= j0 + wd && r < f.m) {
@@ -97,13 +111,11 @@ k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
          for (int k = 0; k < NR; ++k) acc[k] += l * xs[j][k];
       }
       const int g = row_index(f, r);
-      if (r < f.nelim) {
-         #pragma unroll
-         for (int k = 0; k < NR; ++k) x[g + (size_t)k * ldx] -= acc[k];
-      } else {
-         #pragma unroll
-         for (int k = 0; k < NR; ++k) atomicAdd(&x[g + (size_t)k * ldx], -acc[k]);
-      }
+      /* fire-and-forget reductions (RED.ADD.F64): no load latency on the critical
+       * path; rows < nelim are touched by this thread only, rows >= nelim are
+       * shared with sibling fronts */
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) atomicAdd(&x[XI(g, k)], -acc[k]);
    }
 }
 
@@ -111,10 +123,11 @@ k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
 __global__ void __launch_bounds__(128)
 k_fwd_flush(const SolveFront* fronts, int first, int nrhs, double* __restrict__ x, int ldx,
       const double* __restrict__ ywork) {
+   const int NR = nrhs;
    const SolveFront f = fronts[first + blockIdx.x];
    for (int j = threadIdx.x; j < f.nelim; j += blockDim.x) {
       int g = f.perm[j] - 1;
-      for (int k = 0; k < nrhs; ++k) x[g + (size_t)k * ldx] = ywork[g + (size_t)k * ldx];
+      for (int k = 0; k < nrhs; ++k) x[XI(g, k)] = ywork[XI(g, k)];
    }
 }
 
@@ -124,6 +137,7 @@ k_fwd_flush(const SolveFront* fronts, int first, int nrhs, double* __restrict__ 
  * ldlt_app_solve_diag :2553-2573. */
 __global__ void __launch_bounds__(128)
 k_diag_solve(const SolveFront* fronts, int first, int nrhs, double* __restrict__ x, int ldx) {
+   const int NR = nrhs;
    const SolveFront f = fronts[first + blockIdx.x];
    const double* d = f.D;
    for (int j = threadIdx.x; j < f.nelim; j += blockDim.x) {
@@ -134,12 +148,12 @@ k_diag_solve(const SolveFront* fronts, int first, int nrhs, double* __restrict__
          double d21 = d[2 * j + 1], d22 = d[2 * j + 3];
          int g2 = f.perm[j + 1] - 1;
          for (int k = 0; k < nrhs; ++k) {
-            double x1 = x[g1 + (size_t)k * ldx], x2 = x[g2 + (size_t)k * ldx];
-            x[g1 + (size_t)k * ldx] = d11 * x1 + d21 * x2;
-            x[g2 + (size_t)k * ldx] = d21 * x1 + d22 * x2;
+            double x1 = x[XI(g1, k)], x2 = x[XI(g2, k)];
+            x[XI(g1, k)] = d11 * x1 + d21 * x2;
+            x[XI(g2, k)] = d21 * x1 + d22 * x2;
          }
       } else {
-         for (int k = 0; k < nrhs; ++k) x[g1 + (size_t)k * ldx] *= d11;
+         for (int k = 0; k < nrhs; ++k) x[XI(g1, k)] *= d11;
       }
    }
 }
@@ -177,7 +191,7 @@ k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
    {
       int g = active ? row_index(f, r) : 0;
       #pragma unroll
-      for (int k = 0; k < NR; ++k) xr[threadIdx.x][k] = active ? x[g + (size_t)k * ldx] : 0.0;
+      for (int k = 0; k < NR; ++k) xr[threadIdx.x][k] = active ? x[XI(g, k)] : 0.0;
       const double* Lr = f.L + r + (size_t)j0 * ldl;
       for (int j = 0; j < SB; ++j) tile[warp][lane][j] = (active && j < wd) ? Lr[j * ldl] : 0.0;
    }
@@ -232,15 +246,35 @@ k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, in
    const int ntile = (f.m + RT - 1) / RT;
    const int t0 = (j0 + wd) / RT;
    const double* pb = pbuf + (size_t)wbeg[fi] * SB * NR;
-   for (int k = warp; k < NR; k += RT / 32) {
-      double v = (g >= 0) ? x[g + (size_t)k * ldx] : 0.0;
-      for (int t = t0; t < ntile; ++t) v -= pb[(size_t)t * SB * NR + lane * NR + k];
-      for (int j = wd - 1; j >= 0; --j) {
-         double zj = __shfl_sync(0xffffffffu, v, j);
-         if (POSDEF) { zj /= lkk[j][j]; if (lane == j) v = zj; }
-         if (lane < j) v -= lkk[j][lane] * zj;
+   constexpr int NW = RT / 32;
+   constexpr int NRW = (NR + NW - 1) / NW;
+   double v[NRW];
+   #pragma unroll
+   for (int q = 0; q < NRW; ++q) {
+      int k = warp * NRW + q;
+      v[q] = (g >= 0 && k < NR) ? x[XI(g, k)] : 0.0;
+   }
+   for (int t = t0; t < ntile; ++t) {
+      #pragma unroll
+      for (int q = 0; q < NRW; ++q) {
+         int k = warp * NRW + q;
+         if (k < NR) v[q] -= pb[(size_t)t * SB * NR + lane * NR + k];
       }
-      if (g >= 0) x[g + (size_t)k * ldx] = v;
+   }
+   for (int j = wd - 1; j >= 0; --j) {
+      const double l = (lane < j) ? lkk[j][lane] : 0.0;
+      const double dj = POSDEF ? lkk[j][j] : 1.0;
+      #pragma unroll
+      for (int q = 0; q < NRW; ++q) {
+         double zj = __shfl_sync(0xffffffffu, v[q], j);
+         if (POSDEF) { zj /= dj; if (lane == j) v[q] = zj; }
+         v[q] -= l * zj;
+      }
+   }
+   #pragma unroll
+   for (int q = 0; q < NRW; ++q) {
+      int k = warp * NRW + q;
+      if (g >= 0 && k < NR) x[XI(g, k)] = v[q];
    }
 }
 
@@ -267,6 +301,20 @@ void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* wo
 }
 
 } // namespace
+
+/* x (column-major, ld = ldx, nr columns) <-> xt (n rows of nr contiguous values) */
+__global__ void __launch_bounds__(256)
+k_transpose_rhs(double* __restrict__ x, int ldx, double* __restrict__ xt, int n, int nr, int to_xt) {
+   int g = blockIdx.x * blockDim.x + threadIdx.x;
+   if (g >= n) return;
+   if (to_xt) for (int k = 0; k < nr; ++k) xt[(size_t)g * nr + k] = x[g + (size_t)k * ldx];
+   else       for (int k = 0; k < nr; ++k) x[g + (size_t)k * ldx] = xt[(size_t)g * nr + k];
+}
+
+void launch_transpose_rhs(double* x, int ldx, double* xt, int n, int nr, bool to_xt, cudaStream_t s) {
+   if (n == 0) return;
+   k_transpose_rhs<<<(n + 255) / 256, 256, 0, s>>>(x, ldx, xt, n, nr, to_xt ? 1 : 0); COUNT_LAUNCH();
+}
 
 int solve_block() { return SB; }
 

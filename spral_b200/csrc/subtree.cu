@@ -107,7 +107,7 @@ struct Symbolic {
    int64_t aval_len = 0;              // entries of aval this part reads: max source index of its nlist slice
    /* scratch pool shared by the factorisations / solves of this subtree */
    std::mutex mtx;
-   Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf;
+   Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf, b_xt;
 
    ~Symbolic() {
       cudaSetDevice(device);
@@ -115,7 +115,7 @@ struct Symbolic {
       cudaFree(d_node_of_front);
       b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
       b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
-      b_y.release(); b_pbuf.release(); b_retry.release();
+      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release();
    }
 };
 
@@ -380,7 +380,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       const std::vector<int>& fronts, bool big, const FactorParams& prm, Buf& wb, double& t_sync) {
    cudaStream_t s = N.stream;
    const bool posdef = N.posdef;
-   const int T = update_tile_size(big), Ti = inner_tile_size();
+   const int T = update_tile_size(big), Ti = inner_tile_size(big);
    std::vector<HostState> H(fronts.size());
    for (size_t i = 0; i < fronts.size(); ++i) {
       HostState& h = H[i];
@@ -625,10 +625,12 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    const int MAXRANK = 8;
    double t_sync = 0;
 
+   const bool trace_levels = getenv("SPRAL_B200_TRACE") != nullptr;
    for (int lev = 0; lev < S.nlevels; ++lev) {
       const int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
       const int nfl = f1 - f0;
       if (nfl == 0) continue;
+      auto tl0 = std::chrono::steady_clock::now();
 
       /* ---- geometry ---- */
       size_t lbytes = 0, ldd = 0, bkd = 0;
@@ -758,6 +760,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       S.b_work.ensure(wbytes + (1 << 16), s);
       Bump bump; bump.reset(S.b_work);
 
+      auto tl1 = std::chrono::steady_clock::now();
       /* ---- init + assemble (fully-summed part) ---- */
       int2* d_scat = upload(bump, scat, s);
       PROF(PC_INIT, launch_scatter_a(N.d_fronts, d_scat, (int)scat.size(), S.d_nlist, S.d_nptr, S.d_node_of_front,
@@ -777,6 +780,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       }
       MatTile* d_ctiles = upload(bump, ctiles, s);
 
+      auto tl2 = std::chrono::steady_clock::now();
       /* ---- factorise the fully-summed columns (panel by panel, one sync per panel) ---- */
       {
          int err = factor_fronts(N, N.d_fronts, F, lfronts, big, prm, S.b_retry, t_sync);
@@ -814,6 +818,12 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          if (d_post[r]) PROF(PC_ASSEMBLE, launch_assemble(N.d_fronts, d_srcs, d_post[r], (int)post[r].size(), true, r == MAXRANK, s));
       CUDA_TRY(cudaGetLastError());
 
+      if (trace_levels) {
+         auto tl3 = std::chrono::steady_clock::now();
+         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+         fprintf(stderr, "[level %d] fronts %d maxm %d: host prep %.2f ms, init+assemble launches %.2f ms, factor %.2f ms\n",
+                 lev, nfl, maxm, ms(tl0, tl1), ms(tl1, tl2), ms(tl2, tl3));
+      }
       /* ---- statistics (cpu/factor.hxx:117-124, NumericSubtree.hxx:248-280) ---- */
       for (int fi = f0; fi < f1; ++fi) {
          const Front& f = F[fi];
@@ -910,20 +920,28 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          dx = (double*)S.b_x.p;
          CUDA_TRY(cudaMemcpyAsync(dx, x, xbytes, cudaMemcpyHostToDevice, s));
       }
-      if (job == JOB_FWD) S.b_y.ensure(xbytes, s);
+      const int maxnr = std::min(nrhs, solve_max_chunk());
+      const size_t chunk_bytes = (size_t)S.n * maxnr * sizeof(double);
+      if (job == JOB_FWD) S.b_y.ensure(chunk_bytes, s);
+      if (nrhs > 1) S.b_xt.ensure(chunk_bytes, s);
       if (job == JOB_DIAG_BWD || job == JOB_BWD)
          S.b_pbuf.ensure(std::max<size_t>(N.max_level_work, 1) * solve_block() * solve_max_chunk() * sizeof(double), s);
       double* ywork = (double*)S.b_y.p;
       double* pbuf = (double*)S.b_pbuf.p;
       for (int r0 = 0; r0 < nrhs;) {
          int nr = solve_rhs_chunk(nrhs - r0);
-         double* xs = dx + (size_t)r0 * ldx;
+         double* xcol = dx + (size_t)r0 * ldx;
+         /* chunks of several right-hand sides are swept in RHS-contiguous layout */
+         double* xs = xcol;
+         if (nr > 1) {
+            xs = (double*)S.b_xt.p;
+            launch_transpose_rhs(xcol, ldx, xs, S.n, nr, true, s);
+         }
          if (job == JOB_FWD) {
             for (int lev = 0; lev < S.nlevels; ++lev)
                launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev],
-                     N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx,
-                     ywork + (size_t)r0 * ldx, s);
-            launch_fwd_flush(N.d_sfronts, 0, S.nloc, nr, xs, ldx, ywork + (size_t)r0 * ldx, s);
+                     N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx, ywork, s);
+            launch_fwd_flush(N.d_sfronts, 0, S.nloc, nr, xs, ldx, ywork, s);
          } else if (job == JOB_DIAG) {
             if (!posdef) launch_diag_solve(N.d_sfronts, 0, S.nloc, nr, xs, ldx, s);
          } else {
@@ -935,6 +953,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                      xs, ldx, pbuf, s);
             }
          }
+         if (nr > 1) launch_transpose_rhs(xcol, ldx, xs, S.n, nr, false, s);
          r0 += nr;
       }
       CUDA_TRY(cudaGetLastError());
