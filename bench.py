@@ -31,6 +31,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 os.environ.setdefault("OMP_CANCELLATION", "TRUE")
 os.environ.setdefault("OMP_PROC_BIND", "TRUE")
+os.environ.setdefault("NCCL_DEBUG", "WARN")       # keeps NCCL's version banner off stdout (one JSON line only)
 
 import numpy as np  # noqa: E402
 
@@ -346,7 +347,8 @@ def main():
             out["cpu_baseline"] = {"error": repr(e)}
     sdist.free(fk)
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

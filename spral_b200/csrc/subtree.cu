@@ -108,6 +108,7 @@ struct Symbolic {
    /* scratch pool shared by the factorisations / solves of this subtree */
    std::mutex mtx;
    Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf, b_xt;
+   Buf b_export;                      // packed contribution block handed to another process (IPC)
 
    ~Symbolic() {
       cudaSetDevice(device);
@@ -115,7 +116,7 @@ struct Symbolic {
       cudaFree(d_node_of_front);
       b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
       b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
-      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release();
+      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export.release();
    }
 };
 
@@ -1263,10 +1264,13 @@ int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned c
    size_t rows = (size_t)nd + cn;
    size_t b_val = (size_t)cn * cn * sizeof(double), b_del = rows * nd * sizeof(double);
    size_t total = b_val + b_del + (size_t)nd * sizeof(int);
-   char* blk = nullptr;
-   cudaError_t e = cudaMalloc((void**)&blk, std::max<size_t>(total, 256));
-   if (e != cudaSuccess) return (int)e;
-   N.ext_allocs.push_back(blk);
+   /* the block lives in the symbolic subtree's pool: same address (and IPC handle)
+    * for every factorisation, so the consumer maps it once */
+   Symbolic& Sm = *N.S;
+   cudaError_t e = cudaSuccess;
+   try { Sm.b_export.ensure(std::max<size_t>(total, 256), N.stream); }
+   catch (const CudaError& ce) { return (int)ce.code; }
+   char* blk = (char*)Sm.b_export.p;
    if (cn) e = cudaMemcpy2D(blk, (size_t)cn * sizeof(double), f.C, (size_t)f.ldc * sizeof(double),
                             (size_t)cn * sizeof(double), cn, cudaMemcpyDeviceToDevice);
    if (e == cudaSuccess && nd)
@@ -1286,15 +1290,23 @@ int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned c
 /* Consumer side: maps the producer's block and copies `bytes` into dst (a
  * device pointer of the calling process' current device) over NVLink. */
 int spral_ssids_b200_ipc_pull(const unsigned char* handle, int64_t bytes, void* dst) {
-   ABI_GUARD();
-   cudaIpcMemHandle_t h;
-   std::memcpy(&h, handle, sizeof(h));
+   /* opened handles are cached for the life of the process: mapping a peer
+    * allocation costs milliseconds, the copy itself ~1 ms per GB over NVLink */
+   static std::mutex mtx;
+   static std::vector<std::pair<std::vector<unsigned char>, void*>> cache;
    void* src = nullptr;
-   cudaError_t e = cudaIpcOpenMemHandle(&src, h, cudaIpcMemLazyEnablePeerAccess);
-   if (e != cudaSuccess) return (int)e;
-   e = cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault);
-   cudaError_t e2 = cudaIpcCloseMemHandle(src);
-   return (int)(e != cudaSuccess ? e : e2);
+   {
+      std::lock_guard<std::mutex> lock(mtx);
+      for (auto& c : cache) if (std::memcmp(c.first.data(), handle, 64) == 0) { src = c.second; break; }
+      if (!src) {
+         cudaIpcMemHandle_t h;
+         std::memcpy(&h, handle, sizeof(h));
+         cudaError_t e = cudaIpcOpenMemHandle(&src, h, cudaIpcMemLazyEnablePeerAccess);
+         if (e != cudaSuccess) return (int)e;
+         cache.push_back({std::vector<unsigned char>(handle, handle + 64), src});
+      }
+   }
+   return (int)cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault);
 }
 
 int spral_ssids_b200_copy_to_host(void* dst, const void* src, int64_t bytes) {

@@ -39,6 +39,7 @@ class DistContext:
     def __init__(self, world=1, rank=0, local_rank=0, engine="gpu", store=None, tag="ssids"):
         self.world, self.rank, self.local_rank, self.engine = world, rank, local_rank, engine
         self._store, self.tag, self.epoch = store, tag, 0
+        self._stage = {}          # producer part -> (device block, capacity): re-used across factorisations
 
     @property
     def store(self):
@@ -196,9 +197,15 @@ def fetch_contrib(ctx, ak, p, posdef):
     c.rlist = rl.ctypes.data
     if meta["kind"] == "ipc":
         lib = _lib.load()
-        blk = lib.spral_ssids_b200_device_alloc(meta["bytes"])
-        if not blk:
-            raise MemoryError("device_alloc failed")
+        blk, cap = ctx._stage.get(p, (None, 0))
+        if cap < meta["bytes"]:
+            if blk:
+                lib.spral_ssids_b200_device_free(blk)
+            cap = int(meta["bytes"] * 1.1) + 256
+            blk = lib.spral_ssids_b200_device_alloc(cap)
+            if not blk:
+                raise MemoryError("device_alloc failed")
+            ctx._stage[p] = (blk, cap)
         handle = (C.c_ubyte * 64).from_buffer_copy(meta["handle"])
         rc = lib.spral_ssids_b200_ipc_pull(handle, meta["bytes"], blk)
         if rc != 0:
@@ -210,7 +217,7 @@ def fetch_contrib(ctx, ak, p, posdef):
         c.lddelay = rows
         c.delay_perm = blk + b_val + rows * nd * 8 if nd else None
         c.device = ctx.local_rank
-        return _Fetched(c, [rl], blk)
+        return _Fetched(c, [rl], None)          # the staging block stays with the context
     keep = [rl, meta["val"], meta["dval"], meta["dperm"]]
     c.val = meta["val"].ctypes.data if meta["val"] is not None else None
     c.ldval = meta["ldval"]
