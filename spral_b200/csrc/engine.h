@@ -114,9 +114,11 @@ int assemble_cols_per_cta();
 int scatter_chunk();
 
 /* ---- DMMA update kernels (gemm_dmma.cu) ---- */
-enum UpdateMode { UPD_INNER = 0, UPD_OUTER = 1, UPD_CONTRIB = 2 };
+enum UpdateMode { UPD_INNER = 0, UPD_OUTER = 1, UPD_CONTRIB = 2, UPD_EXPLICIT = 3 };
 void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
-      bool big_tiles, cudaStream_t s);
+      bool big_tiles, cudaStream_t s, int max_ctas = 0,      // max_ctas: cap on the persistent grid (0 = all SMs)
+      const int4* xregs = nullptr);                         // UPD_EXPLICIT (large tiles only): {front, k0, k1, c_lo} per region
+int device_sm_count();
 int update_tile_size(bool big_tiles);
 int inner_tile_size(bool big_tiles);
 void configure_update_kernels();   // per device: opt in to > 48 KB dynamic shared memory

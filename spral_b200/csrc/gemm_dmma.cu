@@ -190,10 +190,26 @@ struct TileJob {
    int nchunk;
 };
 
+/* UPD_EXPLICIT: the region does not come from the front's (moving) pivoting
+ * state but from a table written by the host: {front, k0, k1, c_lo}.  Used by
+ * the look-ahead bulk update, which runs while the next panel advances the state. */
+__device__ __forceinline__ Region explicit_region(const Front* fronts, const int4 xr) {
+   const Front* f = &fronts[xr.x];
+   Region g;
+   g.A = f->L; g.B = f->LD; g.C = f->L;
+   g.lda = g.ldb = g.ldc = (size_t)f->ldl; g.rows_alloc = f->ldl; g.m = f->m;
+   g.k0 = xr.y; g.k1 = xr.z; g.c_lo = xr.w; g.c_hi = f->n;
+   g.tj_base = 0; g.accumulate = true;
+   g.valid = (g.k1 > g.k0) && (g.c_lo < g.c_hi);
+   return g;
+}
+
 template <int T, int BKT = BK>
-__device__ __forceinline__ bool load_job(const Front* fronts, const MatTile* work, int item, int mode, TileJob& j) {
+__device__ __forceinline__ bool load_job(const Front* fronts, const MatTile* work, int item, int mode, TileJob& j,
+      const int4* xregs = nullptr) {
    MatTile w = work[item];
-   j.g = make_region(&fronts[w.front], mode, T);
+   if (mode == UPD_EXPLICIT) j.g = explicit_region(fronts, xregs[w.front]);
+   else j.g = make_region(&fronts[w.front], mode, T);
    if (!j.g.valid) return false;
    j.r0 = w.ti * T; j.c0 = w.tj * T;          // absolute tile coordinates of the front
    if (j.c0 + T <= j.g.c_lo) return false;
@@ -326,7 +342,7 @@ k_update(Front* fronts, const MatTile* work, int nwork, int mode) {
  * it keeps loading across tile boundaries while the consumers run the epilogue. */
 template <int T, int NWR, int NWC, int NS, int BKT>
 __global__ void __launch_bounds__((NWR * NWC + 1) * 32, 1)
-k_update_ws(Front* fronts, const MatTile* work, int nwork, int mode) {
+k_update_ws(Front* fronts, const MatTile* work, int nwork, int mode, const int4* xregs) {
    constexpr int LDS = T + 4;
    constexpr int WTR = T / NWR, WTC = T / NWC;
    constexpr int NR = WTR / 8, NC = WTC / 8;
@@ -350,7 +366,7 @@ k_update_ws(Front* fronts, const MatTile* work, int nwork, int mode) {
       int g = 0;
       for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
          TileJob pj;
-         if (!load_job<T, BKT>(fronts, work, item, mode, pj)) continue;
+         if (!load_job<T, BKT>(fronts, work, item, mode, pj, xregs)) continue;
          const Region& rg = pj.g;
          const int klen = rg.k1 - rg.k0;
          const int rowsA = min(T, rg.rows_alloc - pj.r0);   // even
@@ -387,7 +403,7 @@ k_update_ws(Front* fronts, const MatTile* work, int nwork, int mode) {
    int g = 0;
    for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
       TileJob cj;
-      if (!load_job<T, BKT>(fronts, work, item, mode, cj)) continue;
+      if (!load_job<T, BKT>(fronts, work, item, mode, cj, xregs)) continue;
       const Region& rg = cj.g;
       const int r0 = cj.r0, c0 = cj.c0;
       const bool warp_active = (r0 + rbase + WTR > c0 + cbase) && (r0 + rbase < rg.m)
@@ -459,16 +475,19 @@ void configure_update_kernels() {
    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
+int device_sm_count() { return g_num_sms > 0 ? g_num_sms : 148; }
+
 void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
-      bool big_tiles, cudaStream_t s) {
+      bool big_tiles, cudaStream_t s, int max_ctas, const int4* xregs) {
    if (nwork == 0) return;
-   const int sms = g_num_sms > 0 ? g_num_sms : 148;
+   int sms = g_num_sms > 0 ? g_num_sms : 148;
+   if (max_ctas > 0) sms = std::min(sms, max_ctas);
    if (mode == UPD_INNER && inner_tile_size(big_tiles) == 64) {
       int grid = std::min(nwork, sms * 5);
       k_update<64, 2, 2, 2><<<grid, 128, update_smem_bytes<64, 2>(), s>>>(fronts, work, nwork, (int)mode);
    } else if (big_tiles) {
       int grid = std::min(nwork, sms);
-      k_update_ws<128, 2, 4, WS_NS, WS_BK><<<grid, 288, update_smem_bytes<128, WS_NS, WS_BK>(), s>>>(fronts, work, nwork, (int)mode);
+      k_update_ws<128, 2, 4, WS_NS, WS_BK><<<grid, 288, update_smem_bytes<128, WS_NS, WS_BK>(), s>>>(fronts, work, nwork, (int)mode, xregs);
    } else {
       int grid = std::min(nwork, sms * 3);
       k_update<64, 2, 2, NSTAGE><<<grid, 128, update_smem_bytes<64, NSTAGE>(), s>>>(fronts, work, nwork, (int)mode);

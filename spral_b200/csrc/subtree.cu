@@ -34,6 +34,8 @@ namespace b200 {
 
 struct CudaError { cudaError_t code; };
 static bool g_profile = false;
+static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
+static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS)
 /* Clears (and, with SPRAL_B200_DEBUG set, reports) a pending non-sticky CUDA
  * error so that it cannot leak into the host application's own CUDA calls. */
 static void clear_cuda_error(const char* where) {
@@ -109,6 +111,7 @@ struct Symbolic {
    std::mutex mtx;
    Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf, b_xt;
    Buf b_export;                      // packed contribution block handed to another process (IPC)
+   Buf b_bulk[2];                     // tile lists of the look-ahead bulk updates (alternating panels)
 
    ~Symbolic() {
       cudaSetDevice(device);
@@ -116,7 +119,7 @@ struct Symbolic {
       cudaFree(d_node_of_front);
       b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
       b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
-      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export.release();
+      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export.release(); b_bulk[0].release(); b_bulk[1].release();
    }
 };
 
@@ -258,6 +261,8 @@ struct Numeric {
    Symbolic* S = nullptr;
    bool posdef = false;
    cudaStream_t stream = nullptr;
+   cudaStream_t stream2 = nullptr;     // bulk trailing updates overlapped with the next panel (look-ahead)
+   cudaEvent_t ev_bulk = nullptr;
    std::vector<void*> chunks;          // factor storage (L, D, perm), stream-ordered allocations
    char* chunk_base = nullptr; size_t chunk_off = 0, chunk_cap = 0;
    Front* d_fronts = nullptr;          // level order
@@ -285,6 +290,8 @@ struct Numeric {
       if (!S) return;
       cudaSetDevice(device);
       if (stream) cudaStreamSynchronize(stream);
+      if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+      if (ev_bulk) cudaEventDestroy(ev_bulk);
       if (ev_begin) cudaEventDestroy(ev_begin);
       if (ev_end) cudaEventDestroy(ev_end);
       for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -335,18 +342,21 @@ struct Prof {
       next_flops = 0; next_tiles = 0;
    }
    void collect() {       // call after a stream synchronisation
+      std::vector<Rec> keep;
       for (auto& r : recs) {
+         if (cudaEventQuery(r.b) != cudaSuccess) { cudaGetLastError(); keep.push_back(r); continue; }
          float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.cls] += t;
          if (r.flops > 0 && getenv("SPRAL_B200_TRACE"))
             fprintf(stderr, "[launch] class %d tiles %d flops %.3e ms %.3f -> %.2f TF/s\n", r.cls, r.ntiles, r.flops, t,
                     r.flops / t / 1e9);
          cudaEventDestroy(r.a); cudaEventDestroy(r.b);
       }
-      recs.clear();
+      recs.swap(keep);
    }
 };
 static thread_local Prof* g_prof = nullptr;
 #define PROF(cls, stmt) do { cudaEvent_t pe_ = g_prof ? g_prof->begin(s) : nullptr; stmt; if (pe_) g_prof->end(cls, pe_, s); } while (0)
+#define PROF_ON(cls, strm, stmt) do { cudaEvent_t pe_ = g_prof ? g_prof->begin(strm) : nullptr; stmt; if (pe_) g_prof->end(cls, pe_, strm); } while (0)
 
 template <class T>
 static T* upload(Bump& bump, const std::vector<T>& v, cudaStream_t s) {
@@ -393,11 +403,16 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
    }
    std::vector<int> snap_host;
    int err = 0;
+   bool bulk_pending = false;       // a bulk update is (possibly) still running on stream2
+   int bulk_parity = 0;
    for (;;) {
       /* active fronts, most candidates first (so that per-step launches use a prefix) */
       std::vector<int> act;
       for (size_t i = 0; i < H.size(); ++i) if (!H[i].finished) act.push_back((int)i);
-      if (act.empty()) break;
+      if (act.empty()) {
+         if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(s, N.ev_bulk, 0));     // join
+         break;
+      }
       std::stable_sort(act.begin(), act.end(), [&](int a, int b) {
          return H[a].pend0 - H[a].p0 > H[b].pend0 - H[b].p0; });
       const int na_all = (int)act.size();
@@ -456,9 +471,21 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       t_sync += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
       if (g_prof) g_prof->collect();
 
-      /* what happened in the panel; exact outer-update and swap work */
-      std::vector<MatTile> outer;
+      /* what happened in the panel; exact outer-update and swap work.  Look-ahead:
+       * when no front failed a pivot in this panel, only the tile columns that hold
+       * the NEXT panel are updated on the main stream; the rest of the trailing
+       * update (the bulk of the flops) runs on the second stream, on a capped
+       * number of SMs, concurrently with the next panel's latency-bound steps.
+       * The two touch disjoint rows/columns. */
+      std::vector<MatTile> outer, bulk;
+      std::vector<int4> bulk_regs;          // {front, k0, k1, c_lo} of every front in the bulk list
       std::vector<RowTile> swap_rows;
+      bool any_fail = false;
+      for (int k = 0; k < na_all; ++k) {
+         const int* sn = &snap_host[(size_t)k * 8];
+         if (sn[6] >= 0 && H[act[k]].pend0 - sn[2] > 0) any_fail = true;
+      }
+      const bool lookahead = big && !any_fail && g_lookahead;
       for (int k = 0; k < na_all; ++k) {
          HostState& h = H[act[k]];
          const int* sn = &snap_host[(size_t)k * 8];   // p0, done, pend, pend0, end, finished, flag
@@ -472,19 +499,50 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
                g_prof->next_flops += 2.0 * K * ((nn - c0) * mm - (nn * (nn - 1) - c0 * (c0 - 1)) / 2.0);
             }
             int mt = (h.m + T - 1) / T, nt = (h.n + T - 1) / T;
+            /* last tile column that holds a column of the next panel */
+            int tj_urgent = (std::min(h.pend0 + PW, h.n) - 1) / T;
+            bool has_bulk = lookahead && tj_urgent + 1 < nt;
+            if (has_bulk) bulk_regs.push_back(make_int4(h.fi, h.p0, h.done, (tj_urgent + 1) * T));
             for (int tj = h.pend0 / T; tj < nt; ++tj)
-               for (int ti = tj; ti < mt; ++ti) outer.push_back({h.fi, ti, tj});
+               for (int ti = tj; ti < mt; ++ti) {
+                  if (has_bulk && tj > tj_urgent) bulk.push_back({(int)bulk_regs.size() - 1, ti, tj});
+                  else outer.push_back({h.fi, ti, tj});
+               }
          }
          if (!posdef && h.pend0 - h.pend > 0 && h.end - h.pend0 > 0) {
             int ntr = (h.m + RT - 1) / RT;
             for (int t = 0; t < ntr; ++t) swap_rows.push_back({h.fi, t});
          }
       }
-      if (err) return err;
+      if (err) { if (bulk_pending) cudaStreamSynchronize(N.stream2); return err; }
+      if (lookahead && (int)bulk.size() < device_sm_count()) {      // too little to be worth a second stream
+         for (const MatTile& t : bulk) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
+         bulk.clear();
+      }
+      if (bulk_pending && (!outer.empty() || !swap_rows.empty())) {
+         /* the columns touched now were part of the previous bulk update */
+         CUDA_TRY(cudaStreamWaitEvent(s, N.ev_bulk, 0));
+         bulk_pending = false;
+      }
       if (!outer.empty()) {
          MatTile* d_outer = upload(bump, outer, s);
          if (g_prof) g_prof->next_tiles = (int)outer.size();
          PROF(PC_OUTER, launch_update(d_fronts, d_outer, (int)outer.size(), UPD_OUTER, big, s));
+      }
+      if (!bulk.empty()) {
+         cudaStream_t s2 = N.stream2;
+         Buf& bb = N.S->b_bulk[bulk_parity];
+         bulk_parity ^= 1;
+         size_t regs_bytes = align_up(bulk_regs.size() * sizeof(int4), 256);
+         size_t need_b = regs_bytes + bulk.size() * sizeof(MatTile) + 256;
+         if (need_b > bb.cap) bb.ensure(need_b * 2 + 4096, s2);       // drains stream2 before re-allocating
+         CUDA_TRY(cudaMemcpyAsync(bb.p, bulk_regs.data(), bulk_regs.size() * sizeof(int4), cudaMemcpyHostToDevice, s2));
+         MatTile* d_bulk = (MatTile*)((char*)bb.p + regs_bytes);
+         CUDA_TRY(cudaMemcpyAsync(d_bulk, bulk.data(), bulk.size() * sizeof(MatTile), cudaMemcpyHostToDevice, s2));
+         PROF_ON(PC_OUTER, s2, launch_update(d_fronts, d_bulk, (int)bulk.size(), UPD_EXPLICIT, big, s2,
+                                              g_bulk_ctas, (const int4*)bb.p));
+         CUDA_TRY(cudaEventRecord(N.ev_bulk, s2));
+         bulk_pending = true;
       }
       if (!swap_rows.empty()) {
          RowTile* d_sw = upload(bump, swap_rows, s);
@@ -514,9 +572,14 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    std::lock_guard<std::mutex> lock(S.mtx);
    CUDA_TRY(cudaSetDevice(S.device));
    CUDA_TRY(cudaStreamCreateWithFlags(&N.stream, cudaStreamNonBlocking));
+   CUDA_TRY(cudaStreamCreateWithFlags(&N.stream2, cudaStreamNonBlocking));
+   CUDA_TRY(cudaEventCreateWithFlags(&N.ev_bulk, cudaEventDisableTiming));
    cudaStream_t s = N.stream;
    configure_update_kernels();
    configure_solve_kernels();
+   if (const char* e = getenv("SPRAL_B200_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
+   g_bulk_ctas = device_sm_count() - 28;
+   if (const char* e = getenv("SPRAL_B200_BULK_CTAS")) g_bulk_ctas = atoi(e);
    auto t_begin = std::chrono::steady_clock::now();
    CUDA_TRY(cudaEventCreate(&N.ev_begin));
    CUDA_TRY(cudaEventCreate(&N.ev_end));
