@@ -185,9 +185,14 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    if os.environ.get("SPRAL_B200_ONE_DEVICE"):      # debugging aid: ranks share GPUs (gloo instead of NCCL)
+        local_rank = rank % int(os.environ["SPRAL_B200_ONE_DEVICE"])
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        if os.environ.get("SPRAL_B200_ONE_DEVICE"):
+            dist.init_process_group(backend="gloo")
+        else:
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     import spral_b200 as sb
     from spral_b200 import _lib, dist as sdist

@@ -192,13 +192,14 @@ void spral_ssids_b200_contrib_fill(struct spral_ssids_b200_contrib* c,
  * (src/ssids/gpu/factor.f90:155-221).  The producer packs
  * [val n*n | delay_val (ndelay+n)*ndelay | delay_perm ndelay ints] into one
  * device block it keeps owning and returns its 64-byte CUDA IPC handle; the
- * consumer pulls the block over NVLink into its own memory.  Return 0 or the
- * raw cudaError_t. */
+ * consumer pulls the block over NVLink into its own memory (`device` = the
+ * consumer's CUDA device; the calls may come from any host thread).  Return 0
+ * or the raw cudaError_t. */
 int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned char* handle,
       int* n, int* ndelay, int64_t* bytes, void** device_block);
-int spral_ssids_b200_ipc_pull(const unsigned char* handle, int64_t bytes, void* dst);
+int spral_ssids_b200_ipc_pull(int device, const unsigned char* handle, int64_t bytes, void* dst);
 int spral_ssids_b200_copy_to_host(void* dst, const void* src, int64_t bytes);
-void* spral_ssids_b200_device_alloc(int64_t bytes);
+void* spral_ssids_b200_device_alloc(int device, int64_t bytes);
 void spral_ssids_b200_device_free(void* p);
 
 /* Introspection used by the parity tests ("bit-exact extend-add index maps

@@ -84,9 +84,9 @@ SYMBOLS = {
     "spral_ssids_gpu_subtree_free_contrib_dbl": (None, [_b, _vp]),
     "spral_ssids_gpu_subtree_export_contrib_ipc":
         (_i, [_vp, _vp, _ip, _ip, _lp, C.POINTER(_vp)]),
-    "spral_ssids_b200_ipc_pull": (_i, [_vp, C.c_int64, _vp]),
+    "spral_ssids_b200_ipc_pull": (_i, [_i, _vp, C.c_int64, _vp]),
     "spral_ssids_b200_copy_to_host": (_i, [_vp, _vp, C.c_int64]),
-    "spral_ssids_b200_device_alloc": (_vp, [C.c_int64]),
+    "spral_ssids_b200_device_alloc": (_vp, [_i, C.c_int64]),
     "spral_ssids_b200_device_free": (None, [_vp]),
     "spral_ssids_b200_contrib_fill": (None, [C.POINTER(Contrib), _b, _vp, _b]),
     "spral_ssids_gpu_symbolic_get_maps": (None, [_vp, _vp, _ip, _vp, _vp]),

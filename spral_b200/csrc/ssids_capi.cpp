@@ -1,0 +1,357 @@
+/* The factor/solve subset of SPRAL's C interface on top of the B200 engine.
+ *
+ * Semantics follow interfaces/C/ssids.f90 (:135-229 analyse, :505-590 factor,
+ * :727-772 solve, :600-720 enquire/alter/free) and src/ssids/ssids.f90
+ * (analyse :148-389, factor :767-1109, solve :1140-1250): array_base handling,
+ * data checking (clean_cscl_oop of matrix_util.f90, restated minimally), flag
+ * codes (src/ssids/datatypes.f90:25-59), inform fill-in (anal.F90:1100-1116),
+ * x permutation and scaling (fkeep.F90:252-266,300-315).
+ *
+ * One process drives all parts of the subtree partition one after the other on
+ * device 0 (ngpu = 1 gives a single part); the one-process-per-GPU scheduler
+ * lives in spral_b200/dist.py.
+ */
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "spral_ssids_b200.h"
+#include "spral_ssids_compat.h"
+
+namespace {
+
+enum { OK = 0, E_CALL_SEQUENCE = -1, E_A_N_OOR = -2, E_A_PTR = -3, E_A_ALL_OOR = -4, E_ORDER = -8,
+       E_X_SIZE = -10, E_JOB_OOR = -11, E_NOT_LLT = -13, E_NOT_LDLT = -14, E_ALLOCATION = -50,
+       E_UNIMPLEMENTED = -98,
+       W_IDX_OOR = 1, W_DUP_IDX = 2, W_DUP_AND_OOR = 3, W_MISSING_DIAGONAL = 4, W_MISS_DIAG_OORDUP = 5,
+       W_ANAL_SINGULAR = 6, W_FACT_SINGULAR = 7 };
+
+struct Akeep {
+   int n = 0;
+   bool check = false;
+   std::vector<int64_t> ptr;            // cleaned lower-triangular CSC, 1-based
+   std::vector<int> row;
+   std::vector<int64_t> map_ptr, map;   // cleaned entry k sums user entries map[map_ptr[k]..map_ptr[k+1])
+   spral_ssids_b200_analysis* an = nullptr;
+   spral_ssids_b200_analysis_view v;
+   std::vector<void*> symbolic;         // one per part
+   spral_ssids_inform inform;           // analyse-time values
+   ~Akeep() {
+      for (void* s : symbolic) if (s) spral_ssids_gpu_destroy_symbolic_subtree(s);
+      if (an) spral_ssids_b200_analysis_free(an);
+   }
+};
+
+struct Fkeep {
+   bool posdef = false;
+   std::vector<void*> numeric;
+   std::vector<double> scaling;         // in pivot order (fkeep%scaling(i) = scale(invp(i)))
+   ~Fkeep() { for (void* p : numeric) if (p) spral_ssids_gpu_destroy_num_subtree_dbl(posdef, p); }
+};
+
+spral_ssids_b200_options engine_options(const spral_ssids_options* o) {
+   spral_ssids_b200_options e;
+   std::memset(&e, 0, sizeof(e));
+   e.print_level = o->print_level; e.action = o->action; e.small = o->small; e.u = o->u;
+   e.multiplier = 1.1; e.small_subtree_threshold = o->small_subtree_threshold;
+   e.cpu_block_size = o->cpu_block_size;
+   e.pivot_method = std::min(3, std::max(1, o->pivot_method));
+   e.failed_pivot_method = 1;
+   return e;
+}
+
+/* Data checking of ssids_analyse(check=true): out-of-range entries are dropped,
+ * upper-triangular entries moved to the lower triangle, duplicates summed
+ * (clean_cscl_oop, src/matrix_util.f90; counts reported as the reference does). */
+int clean_matrix(int n, int base, const int64_t* ptr, const int* row, Akeep& A, spral_ssids_inform* inf) {
+   int64_t ne = ptr[n] - base;
+   std::vector<std::vector<std::pair<int, int64_t>>> cols(n);   // per cleaned column: (row, source index)
+   int64_t oor = 0;
+   for (int j = 0; j < n; ++j) {
+      if (ptr[j + 1] < ptr[j]) return E_A_PTR;
+      for (int64_t k = ptr[j] - base; k < ptr[j + 1] - base; ++k) {
+         int i = row[k] - base;
+         if (i < 0 || i >= n) { oor++; continue; }
+         if (i >= j) cols[j].push_back({i, k}); else cols[i].push_back({j, k});
+      }
+   }
+   if (ne > 0 && oor == ne) return E_A_ALL_OOR;
+   int64_t dup = 0;
+   int missing = 0;
+   A.ptr.assign(n + 1, 1);
+   A.row.clear(); A.map_ptr.assign(1, 0); A.map.clear();
+   for (int j = 0; j < n; ++j) {
+      auto& c = cols[j];
+      std::stable_sort(c.begin(), c.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+      bool diag = false;
+      for (size_t q = 0; q < c.size(); ++q) {
+         if (q > 0 && c[q].first == c[q - 1].first) { dup++; A.map.push_back(c[q].second); A.map_ptr.back() = (int64_t)A.map.size(); continue; }
+         A.row.push_back(c[q].first + 1);
+         A.map.push_back(c[q].second);
+         A.map_ptr.push_back((int64_t)A.map.size());
+         if (c[q].first == j) diag = true;
+      }
+      if (!diag) missing++;
+      A.ptr[j + 1] = (int64_t)A.row.size() + 1;
+   }
+   inf->matrix_dup = (int)dup; inf->matrix_outrange = (int)oor; inf->matrix_missing_diag = missing;
+   int flag = OK;
+   if (oor && dup) flag = W_DUP_AND_OOR; else if (oor) flag = W_IDX_OOR; else if (dup) flag = W_DUP_IDX;
+   if (missing) flag = (flag == OK) ? W_MISSING_DIAGONAL : W_MISS_DIAG_OORDUP;
+   return flag;
+}
+
+void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int* row,
+      void** akeep, const spral_ssids_options* opt, spral_ssids_inform* inf) {
+   std::memset(inf, 0, sizeof(*inf));
+   if (*akeep) { delete static_cast<Akeep*>(*akeep); *akeep = nullptr; }
+   if (n < 0) { inf->flag = E_A_N_OOR; return; }
+   const int base = opt->array_base ? 1 : 0;
+   Akeep* A = new (std::nothrow) Akeep;
+   if (!A) { inf->flag = E_ALLOCATION; return; }
+   *akeep = A;
+   A->n = n; A->check = check;
+   int wflag = OK;
+   if (check) {
+      wflag = clean_matrix(n, base, ptr, row, *A, inf);
+      if (wflag < 0) { inf->flag = wflag; return; }
+   } else {
+      A->ptr.resize(n + 1);
+      for (int j = 0; j <= n; ++j) A->ptr[j] = ptr[j] - base + 1;
+      int64_t ne = A->ptr[n] - 1;
+      A->row.resize(ne);
+      for (int64_t k = 0; k < ne; ++k) A->row[k] = row[k] - base + 1;
+   }
+   if (n == 0) { inf->flag = wflag; A->inform = *inf; return; }
+   /* ordering (ssids.f90:287-353) */
+   std::vector<int> ord(n);
+   if (opt->ordering == 0) {
+      if (!order) { inf->flag = E_ORDER; return; }
+      std::vector<char> seen(n + 1, 0);
+      for (int i = 0; i < n; ++i) {
+         int p = order[i] - base + 1;
+         if (p < 1 || p > n || seen[p]) { inf->flag = E_ORDER; return; }
+         seen[p] = 1; ord[i] = p;
+      }
+   } else if (opt->ordering == 1) {
+      int rc = spral_ssids_b200_metis_order(n, A->ptr.data(), A->row.data(), ord.data());
+      if (rc != 0) { inf->flag = rc; return; }
+   } else { inf->flag = E_UNIMPLEMENTED; return; }
+   int aflag = 0;
+   A->an = spral_ssids_b200_analyse(n, A->ptr.data(), A->row.data(), ord.data(), opt->nemin, -1,
+                                    0, opt->max_load_inbalance, opt->gpu_perf_coeff, &aflag);
+   spral_ssids_b200_analysis_get(A->an, &A->v);
+   if (order) for (int i = 0; i < n; ++i) order[i] = ord[i] - 1 + base;
+   spral_ssids_b200_options eo = engine_options(opt);
+   for (int p = 0; p < A->v.nparts; ++p) {
+      int lo = A->v.contrib_ptr[p] - 1, hi = A->v.contrib_ptr[p + 1] - 1;
+      void* s = spral_ssids_gpu_create_symbolic_subtree(0, n, A->v.part[p], A->v.part[p + 1], A->v.sptr,
+            A->v.sparent, A->v.rptr, A->v.rlist, A->v.nptr, A->v.nlist, hi - lo, A->v.contrib_dest + lo, &eo);
+      if (!s) { inf->flag = -51; return; }
+      A->symbolic.push_back(s);
+   }
+   /* inform (anal.F90:1100-1116) */
+   inf->matrix_rank = A->v.sptr[A->v.nnodes] - 1;
+   inf->num_sup = A->v.nnodes;
+   inf->maxdepth = A->v.maxdepth; inf->maxfront = A->v.maxfront; inf->maxsupernode = A->v.maxsupernode;
+   inf->num_factor = A->v.num_factor; inf->num_flops = A->v.num_flops;
+   inf->flag = (aflag == W_ANAL_SINGULAR) ? W_ANAL_SINGULAR : wflag;
+   A->inform = *inf;
+}
+
+/* x2(i) = x(invp(i)) [* scaling(i)]; the sweeps; back (fkeep.F90:252-315) */
+void solve_common(int job, int nrhs, double* x, int ldx, Akeep* A, Fkeep* F, spral_ssids_inform* inf) {
+   const int n = A->n;
+   if (n == 0 || nrhs == 0) return;
+   std::vector<double> x2((size_t)n * nrhs);
+   const int* invp = A->v.invp;
+   const bool sc = !F->scaling.empty();
+   for (int r = 0; r < nrhs; ++r)
+      for (int i = 0; i < n; ++i) {
+         double v = x[(size_t)r * ldx + invp[i] - 1];
+         if (sc && (job == 0 || job == 1)) v *= F->scaling[i];
+         x2[(size_t)r * n + i] = v;
+      }
+   int rc = 0;
+   const int np = (int)F->numeric.size();
+   if (job == 0 || job == 1)
+      for (int p = 0; p < np && rc == 0; ++p) rc = spral_ssids_gpu_subtree_solve_fwd_dbl(F->posdef, F->numeric[p], nrhs, x2.data(), n);
+   if (job == 2)
+      for (int p = 0; p < np && rc == 0; ++p) rc = spral_ssids_gpu_subtree_solve_diag_dbl(F->posdef, F->numeric[p], nrhs, x2.data(), n);
+   if (job == 3)
+      for (int p = np - 1; p >= 0 && rc == 0; --p) rc = spral_ssids_gpu_subtree_solve_bwd_dbl(F->posdef, F->numeric[p], nrhs, x2.data(), n);
+   if (job == 0 || job == 4)
+      for (int p = np - 1; p >= 0 && rc == 0; --p) rc = spral_ssids_gpu_subtree_solve_diag_bwd_dbl(F->posdef, F->numeric[p], nrhs, x2.data(), n);
+   if (rc < 0) { inf->flag = rc; return; }
+   for (int r = 0; r < nrhs; ++r)
+      for (int i = 0; i < n; ++i) {
+         double v = x2[(size_t)r * n + i];
+         if (sc && (job == 0 || job == 3 || job == 4)) v *= F->scaling[i];
+         x[(size_t)r * ldx + invp[i] - 1] = v;
+      }
+}
+
+} // namespace
+
+extern "C" {
+
+/* defaults of ssids_options (src/ssids/datatypes.f90:188-284) */
+void spral_ssids_default_options(struct spral_ssids_options* o) {
+   std::memset(o, 0, sizeof(*o));
+   o->array_base = 0; o->print_level = 0; o->unit_diagnostics = 6; o->unit_error = 6; o->unit_warning = 6;
+   o->ordering = 1; o->nemin = 32; o->ignore_numa = true; o->use_gpu = true;
+   o->min_gpu_work = 5000000000LL; o->max_load_inbalance = 1.2f; o->gpu_perf_coeff = 1.0f;
+   o->scaling = 0; o->small_subtree_threshold = 4000000; o->cpu_block_size = 256;
+   o->action = true; o->pivot_method = 2; o->small = 1e-20; o->u = 0.01;
+}
+
+void spral_ssids_analyse(bool check, int n, int* order, const int64_t* ptr, const int* row,
+      const double*, void** akeep, const struct spral_ssids_options* options,
+      struct spral_ssids_inform* inform) {
+   analyse_common(check, n, order, ptr, row, akeep, options, inform);
+}
+
+void spral_ssids_analyse_ptr32(bool check, int n, int* order, const int* ptr, const int* row,
+      const double*, void** akeep, const struct spral_ssids_options* options,
+      struct spral_ssids_inform* inform) {
+   std::vector<int64_t> p64(ptr, ptr + (n >= 0 ? n + 1 : 0));
+   analyse_common(check, n, order, p64.data(), row, akeep, options, inform);
+}
+
+void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* val, double* scale,
+      void* akeep, void** fkeep, const struct spral_ssids_options* options,
+      struct spral_ssids_inform* inform) {
+   Akeep* A = static_cast<Akeep*>(akeep);
+   if (!A) { inform->flag = E_CALL_SEQUENCE; return; }
+   *inform = A->inform;
+   if (A->inform.flag < 0) { inform->flag = E_CALL_SEQUENCE; return; }
+   if (options->scaling != 0) { inform->flag = E_UNIMPLEMENTED; return; }
+   if (*fkeep) { delete static_cast<Fkeep*>(*fkeep); *fkeep = nullptr; }
+   Fkeep* F = new (std::nothrow) Fkeep;
+   if (!F) { inform->flag = E_ALLOCATION; return; }
+   *fkeep = F;
+   F->posdef = posdef;
+   const int n = A->n;
+   if (n == 0) return;
+   /* apply_conversion_map (ssids.f90:862-867) */
+   std::vector<double> cleaned;
+   const double* aval = val;
+   if (A->check) {
+      cleaned.assign(A->row.size(), 0.0);
+      for (size_t k = 0; k < cleaned.size(); ++k)
+         for (int64_t q = A->map_ptr[k]; q < A->map_ptr[k + 1]; ++q) cleaned[k] += val[A->map[q]];
+      aval = cleaned.data();
+   }
+   if (scale) {                        /* user scaling: fkeep%scaling(i) = scale(invp(i)) (ssids.f90:921-926) */
+      F->scaling.resize(n);
+      for (int i = 0; i < n; ++i) F->scaling[i] = scale[A->v.invp[i] - 1];
+   }
+   spral_ssids_b200_options eo = engine_options(options);
+   const int np = A->v.nparts;
+   std::vector<spral_ssids_b200_contrib> slots(np + 1);
+   std::memset((void*)slots.data(), 0, slots.size() * sizeof(slots[0]));
+   inform->num_delay = 0; inform->num_neg = 0; inform->num_two = 0;
+   inform->num_factor = 0; inform->num_flops = 0; inform->maxfront = 0; inform->maxsupernode = 0;
+   for (int p = 0; p < np; ++p) {
+      int lo = A->v.contrib_ptr[p] - 1, hi = A->v.contrib_ptr[p + 1] - 1;
+      std::vector<void*> cc(std::max(1, hi - lo));
+      for (int i = lo; i < hi; ++i) cc[i - lo] = &slots[i];
+      spral_ssids_b200_stats st;
+      void* ns = spral_ssids_gpu_create_num_subtree_dbl(posdef, A->symbolic[p], aval,
+            F->scaling.empty() ? nullptr : F->scaling.data(), cc.data(), &eo, &st);
+      F->numeric.push_back(ns);
+      for (int i = lo; i < hi; ++i)      /* the consumer releases what it was handed (contrib_free.f90) */
+         if (slots[i].owner_ptr) spral_ssids_gpu_subtree_free_contrib_dbl(posdef, slots[i].owner_ptr);
+      /* cpu_copy_stats_out (src/ssids/cpu/cpu_iface.f90:74-94) */
+      if (st.flag < 0) { inform->flag = st.flag; inform->cuda_error = st.cuda_error; return; }
+      inform->flag = std::max(inform->flag, st.flag);
+      inform->num_delay += st.num_delay; inform->num_neg += st.num_neg; inform->num_two += st.num_two;
+      inform->num_factor += st.num_factor; inform->num_flops += st.num_flops;
+      inform->maxfront = std::max(inform->maxfront, st.maxfront);
+      inform->maxsupernode = std::max(inform->maxsupernode, st.maxsupernode);
+      inform->matrix_rank -= st.num_zero;
+      int idx = A->v.contrib_idx[p] - 1;
+      if (idx < np) spral_ssids_b200_contrib_fill(&slots[idx], posdef, ns, true);
+   }
+   if (inform->matrix_rank < n && inform->flag >= 0 && inform->flag != W_FACT_SINGULAR
+       && A->inform.flag != W_ANAL_SINGULAR) inform->flag = W_FACT_SINGULAR;
+}
+
+void spral_ssids_solve(int job, int nrhs, double* x, int ldx, void* akeep, void* fkeep,
+      const struct spral_ssids_options*, struct spral_ssids_inform* inform) {
+   Akeep* A = static_cast<Akeep*>(akeep);
+   Fkeep* F = static_cast<Fkeep*>(fkeep);
+   inform->flag = OK;
+   if (!A || !F) { inform->flag = E_CALL_SEQUENCE; return; }
+   if (job < 0 || job > 4) { inform->flag = E_JOB_OOR; return; }
+   if (F->posdef && (job == 2 || job == 4)) { inform->flag = E_JOB_OOR; return; }   /* ssids.f90:1187-1191 */
+   if (ldx < A->n || nrhs < 1) { inform->flag = E_X_SIZE; return; }
+   solve_common(job, nrhs, x, ldx, A, F, inform);
+}
+
+void spral_ssids_solve1(int job, double* x1, void* akeep, void* fkeep,
+      const struct spral_ssids_options* options, struct spral_ssids_inform* inform) {
+   Akeep* A = static_cast<Akeep*>(akeep);
+   spral_ssids_solve(job, 1, x1, A ? std::max(1, A->n) : 1, akeep, fkeep, options, inform);
+}
+
+int spral_ssids_free_akeep(void** akeep) {
+   if (akeep && *akeep) { delete static_cast<Akeep*>(*akeep); *akeep = nullptr; }
+   return 0;
+}
+int spral_ssids_free_fkeep(void** fkeep) {
+   if (fkeep && *fkeep) { delete static_cast<Fkeep*>(*fkeep); *fkeep = nullptr; }
+   return 0;
+}
+int spral_ssids_free(void** akeep, void** fkeep) {      /* fkeep first: it refers to akeep (ssids.f90:1429) */
+   spral_ssids_free_fkeep(fkeep);
+   return spral_ssids_free_akeep(akeep);
+}
+
+void spral_ssids_enquire_posdef(const void* akeep, const void* fkeep, const struct spral_ssids_options*,
+      struct spral_ssids_inform* inform, double* d) {
+   const Akeep* A = static_cast<const Akeep*>(akeep);
+   const Fkeep* F = static_cast<const Fkeep*>(fkeep);
+   inform->flag = OK;
+   if (!A || !F) { inform->flag = E_CALL_SEQUENCE; return; }
+   if (!F->posdef) { inform->flag = E_NOT_LLT; return; }
+   for (size_t p = 0; p < F->numeric.size(); ++p) {
+      spral_ssids_gpu_subtree_enquire_dbl(true, F->numeric[p], nullptr, d);
+      d += A->v.sptr[A->v.part[p + 1] - 1] - A->v.sptr[A->v.part[p] - 1];
+   }
+}
+
+void spral_ssids_enquire_indef(const void* akeep, const void* fkeep, const struct spral_ssids_options*,
+      struct spral_ssids_inform* inform, int* piv_order, double* d) {
+   const Akeep* A = static_cast<const Akeep*>(akeep);
+   const Fkeep* F = static_cast<const Fkeep*>(fkeep);
+   inform->flag = OK;
+   if (!A || !F) { inform->flag = E_CALL_SEQUENCE; return; }
+   if (F->posdef) { inform->flag = E_NOT_LDLT; return; }
+   const int n = A->n;
+   /* the subtree reports in pivot order; the user gets piv_order per ORIGINAL variable
+    * and d in elimination order (ssids.f90:1288-1316; single part) */
+   std::vector<int> po(n, 0);
+   std::vector<double> dd(2 * (size_t)n, 0.0);
+   if (F->numeric.size() != 1) { inform->flag = E_UNIMPLEMENTED; return; }
+   spral_ssids_gpu_subtree_enquire_dbl(false, F->numeric[0], po.data(), dd.data());
+   if (piv_order)
+      for (int i = 0; i < n; ++i) {
+         int v = po[i];                                  // 0-based position, negative for 2x2
+         piv_order[A->v.invp[i] - 1] = (v < 0) ? -(-v + 1) : v + 1;     // reported 1-based
+      }
+   if (d) std::copy(dd.begin(), dd.end(), d);
+}
+
+void spral_ssids_alter(const double* d, const void* akeep, void* fkeep, const struct spral_ssids_options*,
+      struct spral_ssids_inform* inform) {
+   Fkeep* F = static_cast<Fkeep*>(fkeep);
+   inform->flag = OK;
+   if (!akeep || !F) { inform->flag = E_CALL_SEQUENCE; return; }
+   if (F->posdef) { inform->flag = E_NOT_LDLT; return; }
+   if (F->numeric.size() != 1) { inform->flag = E_UNIMPLEMENTED; return; }
+   spral_ssids_gpu_subtree_alter_dbl(false, F->numeric[0], d);
+}
+
+} /* extern "C" */

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <new>
 #include <stdexcept>
 #include <vector>
@@ -51,6 +52,80 @@ std::atomic<long> g_launches{0};      // incremented by every launch wrapper
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+/* Per-device cache of device allocations.  cudaMalloc / cudaFree are slow
+ * (milliseconds per GB, much more once peer access between the GPUs of the box
+ * is enabled, as NCCL and CUDA IPC do), so blocks released by one factorisation
+ * are kept and handed to the next.  Every block is a whole cudaMalloc
+ * allocation (IPC handles stay valid). */
+class DevicePool {
+   struct Blk { void* p; size_t bytes; };
+   std::mutex mtx_;
+   std::vector<Blk> free_[16];
+   std::vector<std::pair<void*, size_t>> live_[16];      // size of every block handed out
+   size_t cached_[16] = {0};
+   static constexpr size_t kMaxCached = (size_t)96 << 30;
+public:
+   void* alloc(size_t bytes) {
+      int dev = 0;
+      CUDA_TRY(cudaGetDevice(&dev));
+      bytes = align_up(std::max<size_t>(bytes, 256), 256);
+      {
+         std::lock_guard<std::mutex> lock(mtx_);
+         auto& fl = free_[dev & 15];
+         int best = -1;
+         for (int i = 0; i < (int)fl.size(); ++i)
+            if (fl[i].bytes >= bytes && fl[i].bytes <= bytes + bytes / 4 + (1 << 20) &&
+                (best < 0 || fl[i].bytes < fl[best].bytes)) best = i;
+         if (best >= 0) {
+            Blk b = fl[best];
+            fl.erase(fl.begin() + best);
+            cached_[dev & 15] -= b.bytes;
+            live_[dev & 15].push_back({b.p, b.bytes});
+            return b.p;
+         }
+      }
+      void* p = nullptr;
+      cudaError_t e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) {            // out of memory: drop the cache and retry once
+         cudaGetLastError();
+         trim(dev, 0);
+         CUDA_TRY(cudaMalloc(&p, bytes));
+      }
+      std::lock_guard<std::mutex> lock(mtx_);
+      live_[dev & 15].push_back({p, bytes});
+      return p;
+   }
+   void release(void* p) {
+      if (!p) return;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      size_t bytes = 0;
+      {
+         std::lock_guard<std::mutex> lock(mtx_);
+         auto& lv = live_[dev & 15];
+         for (size_t i = 0; i < lv.size(); ++i)
+            if (lv[i].first == p) { bytes = lv[i].second; lv[i] = lv.back(); lv.pop_back(); break; }
+         if (bytes) { free_[dev & 15].push_back({p, bytes}); cached_[dev & 15] += bytes; }
+      }
+      if (!bytes) { cudaFree(p); return; }          // not ours (or another device): plain free
+      if (cached_[dev & 15] > kMaxCached) trim(dev, kMaxCached / 2);
+   }
+   void trim(int dev, size_t keep) {
+      std::vector<Blk> drop;
+      {
+         std::lock_guard<std::mutex> lock(mtx_);
+         auto& fl = free_[dev & 15];
+         while (!fl.empty() && cached_[dev & 15] > keep) {
+            drop.push_back(fl.front());
+            cached_[dev & 15] -= fl.front().bytes;
+            fl.erase(fl.begin());
+         }
+      }
+      for (auto& b : drop) cudaFree(b.p);
+   }
+};
+static DevicePool g_pool;
+
 /* Grow-only device buffer. */
 struct Buf {
    void* p = nullptr;
@@ -59,12 +134,12 @@ struct Buf {
     * is drained first because kernels in flight may still use the old one. */
    void ensure(size_t bytes, cudaStream_t s) {
       if (bytes <= cap) return;
-      if (p) { CUDA_TRY(cudaStreamSynchronize(s)); CUDA_TRY(cudaFree(p)); p = nullptr; cap = 0; }
+      if (p) { CUDA_TRY(cudaStreamSynchronize(s)); g_pool.release(p); p = nullptr; cap = 0; }
       size_t want = align_up(bytes + bytes / 8, 256);
-      CUDA_TRY(cudaMalloc(&p, want));
+      p = g_pool.alloc(want);
       cap = want;
    }
-   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+   void release() { if (p) g_pool.release(p); p = nullptr; cap = 0; }
 };
 
 /* Bump allocator over a Buf. */
@@ -295,9 +370,10 @@ struct Numeric {
       if (ev_begin) cudaEventDestroy(ev_begin);
       if (ev_end) cudaEventDestroy(ev_end);
       for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-      for (void* p : chunks) cudaFree(p);
-      for (void* p : ext_allocs) cudaFree(p);
-      cudaFree(d_fronts); cudaFree(d_sfronts); cudaFree(d_swork); cudaFree(d_wbeg); cudaFree(d_export);
+      for (void* p : chunks) g_pool.release(p);
+      for (void* p : ext_allocs) g_pool.release(p);
+      g_pool.release(d_fronts); g_pool.release(d_sfronts); g_pool.release(d_swork); g_pool.release(d_wbeg);
+      g_pool.release(d_export);
       if (stream) cudaStreamDestroy(stream);
    }
 
@@ -306,8 +382,7 @@ struct Numeric {
       bytes = align_up(bytes, 256);
       if (chunk_off + bytes > chunk_cap) {
          size_t want = std::max(bytes, (size_t)256 << 20);
-         void* p;
-         CUDA_TRY(cudaMalloc(&p, want));
+         void* p = g_pool.alloc(want);
          chunks.push_back(p);
          chunk_base = (char*)p; chunk_off = 0; chunk_cap = want;
       }
@@ -317,8 +392,7 @@ struct Numeric {
    }
    void reserve(size_t bytes) {
       if (chunk_cap - chunk_off >= bytes) return;
-      void* p;
-      CUDA_TRY(cudaMalloc(&p, align_up(bytes, 256)));
+      void* p = g_pool.alloc(align_up(bytes, 256));
       chunks.push_back(p);
       chunk_base = (char*)p; chunk_off = 0; chunk_cap = align_up(bytes, 256);
    }
@@ -608,7 +682,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    /* fixed-size scratch */
    S.b_cbuf[0].ensure(std::max<size_t>(S.cbuf_bytes[0], 256), s);
    S.b_cbuf[1].ensure(std::max<size_t>(S.cbuf_bytes[1], 256), s);
-   CUDA_TRY(cudaMalloc((void**)&N.d_fronts, nloc * sizeof(Front)));
+   N.d_fronts = (Front*)g_pool.alloc(nloc * sizeof(Front));
    N.h_fronts.assign(nloc, Front());
    std::vector<Front>& F = N.h_fronts;
 
@@ -643,7 +717,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          for (int i = 0; i < cn; ++i) { map[i] = pos[crl[i]]; if (map[i] <= S.n0[node]) npl++; }
          e.src.npassl = npl;
       }
-      int* d_map; CUDA_TRY(cudaMalloc((void**)&d_map, std::max(cn, 1) * sizeof(int)));
+      int* d_map = (int*)g_pool.alloc(std::max(cn, 1) * sizeof(int));
       N.ext_allocs.push_back(d_map);
       if (cn) CUDA_TRY(cudaMemcpyAsync(d_map, map.data(), cn * sizeof(int), cudaMemcpyHostToDevice, s));
       CUDA_TRY(cudaStreamSynchronize(s));   // map is a local vector
@@ -659,7 +733,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       if (c->val && cn) {
          if (local) { e.src.C = c->val; e.src.ldc = c->ldval; }
          else {
-            double* d; CUDA_TRY(cudaMalloc((void**)&d, (size_t)cn * cn * sizeof(double)));
+            double* d = (double*)g_pool.alloc((size_t)cn * cn * sizeof(double));
             N.ext_allocs.push_back(d);
             CUDA_TRY(cudaMemcpy2DAsync(d, (size_t)cn * sizeof(double), c->val, (size_t)c->ldval * sizeof(double),
                                        (size_t)cn * sizeof(double), cn, cudaMemcpyDefault, s));
@@ -670,8 +744,8 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          if (local) { e.src.dval = c->delay_val; e.src.lddelay = c->lddelay; e.src.dperm = c->delay_perm; }
          else {
             size_t rows = (size_t)nd + cn;
-            double* d; CUDA_TRY(cudaMalloc((void**)&d, rows * nd * sizeof(double)));
-            int* dp; CUDA_TRY(cudaMalloc((void**)&dp, nd * sizeof(int)));
+            double* d = (double*)g_pool.alloc(rows * nd * sizeof(double));
+            int* dp = (int*)g_pool.alloc(nd * sizeof(int));
             N.ext_allocs.push_back(d); N.ext_allocs.push_back(dp);
             CUDA_TRY(cudaMemcpy2DAsync(d, rows * sizeof(double), c->delay_val, (size_t)c->lddelay * sizeof(double),
                                        rows * sizeof(double), nd, cudaMemcpyDefault, s));
@@ -748,7 +822,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
             f.ldc = (int)align_up((size_t)cm, 2);
             if (cm > 0) {
                if (S.exported[node]) {
-                  CUDA_TRY(cudaMalloc((void**)&N.d_export, (size_t)f.ldc * cm * sizeof(double)));
+                  N.d_export = (double*)g_pool.alloc((size_t)f.ldc * cm * sizeof(double));
                   f.C = N.d_export; N.export_front = fi;
                } else {
                   f.C = (double*)((char*)S.b_cbuf[lev & 1].p + co);
@@ -933,9 +1007,9 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          N.max_level_work = std::max(N.max_level_work, sw.size() - (size_t)N.swork_ptr[lev]);
       }
       N.swork_ptr[S.nlevels] = (int)sw.size();
-      CUDA_TRY(cudaMalloc((void**)&N.d_sfronts, nloc * sizeof(SolveFront)));
-      CUDA_TRY(cudaMalloc((void**)&N.d_swork, std::max<size_t>(sw.size(), 1) * sizeof(RowTile)));
-      CUDA_TRY(cudaMalloc((void**)&N.d_wbeg, nloc * sizeof(int)));
+      N.d_sfronts = (SolveFront*)g_pool.alloc(nloc * sizeof(SolveFront));
+      N.d_swork = (RowTile*)g_pool.alloc(std::max<size_t>(sw.size(), 1) * sizeof(RowTile));
+      N.d_wbeg = (int*)g_pool.alloc(nloc * sizeof(int));
       CUDA_TRY(cudaMemcpyAsync(N.d_sfronts, sf.data(), nloc * sizeof(SolveFront), cudaMemcpyHostToDevice, s));
       if (!sw.empty()) CUDA_TRY(cudaMemcpyAsync(N.d_swork, sw.data(), sw.size() * sizeof(RowTile), cudaMemcpyHostToDevice, s));
       CUDA_TRY(cudaMemcpyAsync(N.d_wbeg, wbeg.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1240,7 +1314,7 @@ void spral_ssids_gpu_subtree_free_contrib_dbl(bool, void* p) {
    ABI_GUARD();
    Numeric& N = *static_cast<Numeric*>(p);
    cudaSetDevice(N.S->device);
-   if (N.d_export) { cudaFree(N.d_export); N.d_export = nullptr; }
+   if (N.d_export) { g_pool.release(N.d_export); N.d_export = nullptr; }
    std::vector<double>().swap(N.h_cval);
    std::vector<double>().swap(N.h_dval);
 }
@@ -1352,12 +1426,14 @@ int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned c
 
 /* Consumer side: maps the producer's block and copies `bytes` into dst (a
  * device pointer of the calling process' current device) over NVLink. */
-int spral_ssids_b200_ipc_pull(const unsigned char* handle, int64_t bytes, void* dst) {
+int spral_ssids_b200_ipc_pull(int device, const unsigned char* handle, int64_t bytes, void* dst) {
    /* opened handles are cached for the life of the process: mapping a peer
     * allocation costs milliseconds, the copy itself ~1 ms per GB over NVLink */
    static std::mutex mtx;
    static std::vector<std::pair<std::vector<unsigned char>, void*>> cache;
    void* src = nullptr;
+   cudaError_t es = cudaSetDevice(device);      // the caller may be a fresh host thread (current device 0)
+   if (es != cudaSuccess) return (int)es;
    {
       std::lock_guard<std::mutex> lock(mtx);
       for (auto& c : cache) if (std::memcmp(c.first.data(), handle, 64) == 0) { src = c.second; break; }
@@ -1377,9 +1453,10 @@ int spral_ssids_b200_copy_to_host(void* dst, const void* src, int64_t bytes) {
    return (int)cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost);
 }
 
-void* spral_ssids_b200_device_alloc(int64_t bytes) {
+void* spral_ssids_b200_device_alloc(int device, int64_t bytes) {
    ABI_GUARD();
    void* p = nullptr;
+   if (cudaSetDevice(device) != cudaSuccess) return nullptr;
    if (cudaMalloc(&p, (size_t)std::max<int64_t>(bytes, 256)) != cudaSuccess) return nullptr;
    return p;
 }

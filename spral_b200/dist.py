@@ -202,12 +202,12 @@ def fetch_contrib(ctx, ak, p, posdef):
             if blk:
                 lib.spral_ssids_b200_device_free(blk)
             cap = int(meta["bytes"] * 1.1) + 256
-            blk = lib.spral_ssids_b200_device_alloc(cap)
+            blk = lib.spral_ssids_b200_device_alloc(ctx.local_rank, cap)
             if not blk:
                 raise MemoryError("device_alloc failed")
             ctx._stage[p] = (blk, cap)
         handle = (C.c_ubyte * 64).from_buffer_copy(meta["handle"])
-        rc = lib.spral_ssids_b200_ipc_pull(handle, meta["bytes"], blk)
+        rc = lib.spral_ssids_b200_ipc_pull(ctx.local_rank, handle, meta["bytes"], blk)
         if rc != 0:
             raise RuntimeError(f"ipc_pull failed: cudaError {rc}")
         b_val = n * n * 8
@@ -273,9 +273,19 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
     inform = _new_inform(a)
     trace = os.environ.get("SPRAL_B200_TRACE")
     t_start = time.perf_counter()
-    for p in range(nparts):
-        if ak.rank_of[p] != ctx.rank:
-            continue
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    lock = threading.Lock()
+    futures = {}
+    failed = threading.Event()
+
+    def run_part(p):
+        """One part: wait for the local children, pull the remote ones, factorise, hand on."""
+        for c_part in ak.children[p]:
+            if ak.rank_of[c_part] == ctx.rank:
+                futures[c_part].result()
+        if failed.is_set():
+            return
         t_p0 = time.perf_counter()
         cc, fetched = [], []
         for c_part in ak.children[p]:
@@ -300,9 +310,11 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
                 free_contrib(c)
         for f in fetched:
             f.release()
-        _accumulate(inform, st)
+        with lock:
+            _accumulate(inform, st)
         if st.flag < 0:
-            break
+            failed.set()
+            return
         t_p2 = time.perf_counter()
         q = ak.consumer[p]
         if q >= 0:
@@ -331,6 +343,18 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
             print(f"[trace r{ctx.rank} e{ctx.epoch}] part {p}: start +{1e3*(t_p0-t_start):.1f} ms, fetch {1e3*(t_p1-t_p0):.1f}, "
                   f"factor {1e3*(t_p2-t_p1):.1f} (dev {float(ns.timings()[1]) if ctx.engine == 'gpu' else 0:.1f}), "
                   f"publish {1e3*(t_p3-t_p2):.1f} ms, flops {st.num_flops:.3g}", file=sys.stderr, flush=True)
+
+    mine = [p for p in range(nparts) if ak.rank_of[p] == ctx.rank]
+    nthreads = max(1, int(os.environ.get("SPRAL_B200_PART_THREADS", "2")))
+    if ctx.engine != "gpu" or len(mine) <= 1:
+        nthreads = 1
+    # independent parts of this rank run concurrently (each on its own stream); tasks are
+    # submitted in postorder, so a parent never starts before its children have started
+    with ThreadPoolExecutor(max_workers=nthreads) as ex:
+        for p in mine:
+            futures[p] = ex.submit(run_part, p)
+        for p in mine:
+            futures[p].result()
     return DistFkeep(ak, posdef, numeric, finish_inform(a, inform), ext_rows, sc, ctx.epoch)
 
 

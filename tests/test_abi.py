@@ -15,8 +15,11 @@ from spral_b200 import _lib
 HEADER = os.path.join(ROOT, "include", "spral_ssids_b200.h")
 
 
-def declared_functions():
-    src = open(HEADER).read()
+COMPAT = os.path.join(ROOT, "include", "spral_ssids_compat.h")
+
+
+def declared_functions(header=HEADER):
+    src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(spral_ssids_\w+)\s*\(", src)))
 
@@ -62,3 +65,32 @@ def test_options_layout_matches_reference_cpu_factor_options():
                                           "small_subtree_threshold", "cpu_block_size",
                                           "pivot_method", "failed_pivot_method"]
     assert C.sizeof(o) == 56
+
+
+def test_compat_header_symbols_exported_and_layout_matches_reference_sizes():
+    """include/spral_ssids_compat.h (the spral_ssids.h subset): every function is
+    exported; the two interoperable structs have the sizes of the reference's
+    (include/spral_ssids.h:15-57: options 176 bytes, inform 152 bytes)."""
+    lib = C.CDLL(_lib.LIB_PATH)
+    names = [f for f in declared_functions(COMPAT) if f.startswith("spral_ssids_")]
+    assert len(names) == 12
+    assert not [f for f in names if not hasattr(lib, f)]
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "s.c")
+        open(src, "w").write('#include <stdio.h>\n#include "spral_ssids_compat.h"\nint main(void){printf("%zu %zu\\n",'
+                             'sizeof(struct spral_ssids_options), sizeof(struct spral_ssids_inform));return 0;}\n')
+        exe = os.path.join(td, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        a, b = map(int, subprocess.check_output([exe]).split())
+    ref = os.path.join("/root/reference/include/spral_ssids.h")
+    if os.path.exists(ref):
+        with tempfile.TemporaryDirectory() as td:
+            src = os.path.join(td, "r.c")
+            open(src, "w").write('#include <stdio.h>\n#include "spral_ssids.h"\nint main(void){printf("%zu %zu\\n",'
+                                 'sizeof(struct spral_ssids_options), sizeof(struct spral_ssids_inform));return 0;}\n')
+            exe = os.path.join(td, "r")
+            subprocess.check_call(["gcc", "-I", "/root/reference/include", src, "-o", exe])
+            ra, rb = map(int, subprocess.check_output([exe]).split())
+        assert (a, b) == (ra, rb)
+    assert (a, b) == (176, 152)

@@ -369,3 +369,16 @@ def test_full_size_properties_cfg2():
     assert oracle_ref.backward_error(A, Xs, B) <= 1e-14
     comb = sb.solve(fk, B[:, 0] + 2.0 * B[:, 1])
     np.testing.assert_allclose(comb, Xs[:, 0] + 2.0 * Xs[:, 1], rtol=1e-9, atol=1e-11)
+
+
+def test_c_api_client(tmp_path):
+    """A C program written against the reference's C interface (spral_ssids.h names,
+    structs and call sequence; tests/c/ssids_capi_check.c) linked with the engine."""
+    import subprocess
+    exe = tmp_path / "capi"
+    libdir = os.path.join(ROOT, "spral_b200")
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "ssids_capi_check.c"), "-o", str(exe),
+                           "-L", libdir, "-lspral_ssids_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "CAPI OK" in out.stdout, out.stdout + out.stderr
