@@ -83,6 +83,8 @@ CASES = [
     ("st27_12_s13", lambda: M.stencil_3d_27pt(12, shift=13.0), False, 3),
     ("st27_20_s13", lambda: M.stencil_3d_27pt(20, shift=13.0), False, 5),
     ("st27_16_s26", lambda: M.stencil_3d_27pt(16, shift=26.5), False, 1),
+    ("st27_32_s13", lambda: M.stencil_3d_27pt(32, shift=13.0), False, 2),
+    ("st27_24_s20", lambda: M.stencil_3d_27pt(24, shift=20.0), False, 1),
     ("kkt_2000", lambda: M.kkt_saddle(2000), False, 4),
     ("kkt_6000", lambda: M.kkt_saddle(6000), False, 1),
     ("lap3d_7x9x30", lambda: M.laplacian_3d_7pt(7, 9, 30), True, 1),    # ragged
@@ -382,3 +384,36 @@ def test_c_api_client(tmp_path):
                            "-L", libdir, "-lspral_ssids_b200", "-lm", f"-Wl,-rpath,{libdir}"])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "CAPI OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_full_size_properties_cfg3():
+    """BASELINE config 3 at full size (3-D 27-point 80^3, shifted, u = 0.01): the
+    oracle would need minutes, so size-independent properties are checked instead:
+    Sylvester's law (the inertia does not depend on the pivot threshold), rank,
+    num_flops >= the analyse prediction (delays only add work), residual below the
+    reference tolerance and <= 1e-14 after one refinement step, linearity."""
+    n, ptr, row, val = M.stencil_3d_27pt(80, shift=13.0)
+    ak = sb.analyse(n, ptr, row)
+    a = ak.analysis
+    fk = sb.factor(ak, False, val)
+    g = fk.inform
+    assert g["flag"] == 0 and g["matrix_rank"] == n
+    assert g["num_flops"] >= a.num_flops and g["num_factor"] >= a.num_factor
+    assert g["num_delay"] <= 64
+    A = M.to_scipy(n, ptr, row, val)
+    rng = np.random.default_rng(1)
+    X = np.asfortranarray(rng.uniform(-1, 1, (n, 2)))
+    B = np.asfortranarray(A @ X)
+    Xs = sb.solve(fk, B)
+    assert oracle_ref.backward_error(A, Xs, B) < REF_TOL
+    Xs2 = Xs + sb.solve(fk, np.asfortranarray(B - A @ Xs))
+    assert oracle_ref.backward_error(A, Xs2, B) <= 1e-14
+    comb = sb.solve(fk, B[:, 0] - 3.0 * B[:, 1])
+    np.testing.assert_allclose(comb, Xs[:, 0] - 3.0 * Xs[:, 1], rtol=1e-6, atol=1e-8)
+    neg = g["num_neg"]
+    for ns in fk.numeric:
+        ns.close()
+    opt = _lib.Options.default()
+    opt.u = 0.1
+    fk2 = sb.factor(ak, False, val, options=opt)
+    assert fk2.inform["num_neg"] == neg and fk2.inform["matrix_rank"] == n
