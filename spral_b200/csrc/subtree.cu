@@ -35,6 +35,7 @@ namespace b200 {
 
 struct CudaError { cudaError_t code; };
 static bool g_profile = false;
+static bool g_solve_graphs = true;   // SPRAL_B200_SOLVE_GRAPHS=0: launch the solve kernels one by one
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS)
 /* Clears (and, with SPRAL_B200_DEBUG set, reports) a pending non-sticky CUDA
@@ -337,7 +338,8 @@ struct Numeric {
    bool posdef = false;
    cudaStream_t stream = nullptr;
    cudaStream_t stream2 = nullptr;     // bulk trailing updates overlapped with the next panel (look-ahead)
-   cudaEvent_t ev_bulk = nullptr;
+   cudaEvent_t ev_bulk = nullptr;       // recorded after the part of a bulk update the NEXT urgent update depends on
+   cudaEvent_t ev_bulk_all = nullptr;   // recorded after the whole bulk update
    std::vector<void*> chunks;          // factor storage (L, D, perm), stream-ordered allocations
    char* chunk_base = nullptr; size_t chunk_off = 0, chunk_cap = 0;
    Front* d_fronts = nullptr;          // level order
@@ -354,6 +356,9 @@ struct Numeric {
    std::vector<void*> ext_allocs;
    double timings[8] = {0};
    double class_ms[16] = {0};          // profiling mode: device ms per kernel class (ProfClass order)
+   /* CUDA graphs of the solve sweeps, one per (job, right-hand sides per pass) */
+   struct SolveGraph { int job, nr; cudaGraphExec_t exec; double* xs; double* ywork; double* pbuf; };
+   std::vector<SolveGraph> graphs;
    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
    /* profiling of the Schur-complement launches (enabled by spral_ssids_b200_set_profile) */
    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -366,7 +371,9 @@ struct Numeric {
       cudaSetDevice(device);
       if (stream) cudaStreamSynchronize(stream);
       if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+      for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
       if (ev_bulk) cudaEventDestroy(ev_bulk);
+      if (ev_bulk_all) cudaEventDestroy(ev_bulk_all);
       if (ev_begin) cudaEventDestroy(ev_begin);
       if (ev_end) cudaEventDestroy(ev_end);
       for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -484,7 +491,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       std::vector<int> act;
       for (size_t i = 0; i < H.size(); ++i) if (!H[i].finished) act.push_back((int)i);
       if (act.empty()) {
-         if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(s, N.ev_bulk, 0));     // join
+         if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(s, N.ev_bulk_all, 0));     // join
          break;
       }
       std::stable_sort(act.begin(), act.end(), [&](int a, int b) {
@@ -551,8 +558,8 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
        * update (the bulk of the flops) runs on the second stream, on a capped
        * number of SMs, concurrently with the next panel's latency-bound steps.
        * The two touch disjoint rows/columns. */
-      std::vector<MatTile> outer, bulk;
-      std::vector<int4> bulk_regs;          // {front, k0, k1, c_lo} of every front in the bulk list
+      std::vector<MatTile> outer, bulk, bulk_b;   // bulk: columns of the panel after next; bulk_b: the rest
+      std::vector<int4> bulk_regs;          // {front, k0, k1, c_lo} of every front in the bulk lists
       std::vector<RowTile> swap_rows;
       bool any_fail = false;
       for (int k = 0; k < na_all; ++k) {
@@ -575,11 +582,13 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
             int mt = (h.m + T - 1) / T, nt = (h.n + T - 1) / T;
             /* last tile column that holds a column of the next panel */
             int tj_urgent = (std::min(h.pend0 + PW, h.n) - 1) / T;
+            int tj_next = (std::min(h.pend0 + 2 * PW, h.n) - 1) / T;     // last tile column of the panel after next
             bool has_bulk = lookahead && tj_urgent + 1 < nt;
             if (has_bulk) bulk_regs.push_back(make_int4(h.fi, h.p0, h.done, (tj_urgent + 1) * T));
             for (int tj = h.pend0 / T; tj < nt; ++tj)
                for (int ti = tj; ti < mt; ++ti) {
-                  if (has_bulk && tj > tj_urgent) bulk.push_back({(int)bulk_regs.size() - 1, ti, tj});
+                  if (has_bulk && tj > tj_next) bulk_b.push_back({(int)bulk_regs.size() - 1, ti, tj});
+                  else if (has_bulk && tj > tj_urgent) bulk.push_back({(int)bulk_regs.size() - 1, ti, tj});
                   else outer.push_back({h.fi, ti, tj});
                }
          }
@@ -589,33 +598,47 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          }
       }
       if (err) { if (bulk_pending) cudaStreamSynchronize(N.stream2); return err; }
-      if (lookahead && (int)bulk.size() < device_sm_count()) {      // too little to be worth a second stream
+      if (lookahead && (int)(bulk.size() + bulk_b.size()) < device_sm_count()) {   // not worth a second stream
          for (const MatTile& t : bulk) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
-         bulk.clear();
+         for (const MatTile& t : bulk_b) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
+         bulk.clear(); bulk_b.clear();
       }
+      const bool have_bulk = !bulk.empty() || !bulk_b.empty();
       if (bulk_pending && (!outer.empty() || !swap_rows.empty())) {
-         /* the columns touched now were part of the previous bulk update */
-         CUDA_TRY(cudaStreamWaitEvent(s, N.ev_bulk, 0));
-         bulk_pending = false;
+         /* With look-ahead the urgent update only touches the next panel's columns,
+          * which the previous bulk update finished first (ev_bulk); a full update or
+          * a swap touches everything, so it waits for the whole backlog. */
+         CUDA_TRY(cudaStreamWaitEvent(s, (lookahead && have_bulk) ? N.ev_bulk : N.ev_bulk_all, 0));
+         if (!(lookahead && have_bulk)) bulk_pending = false;
       }
       if (!outer.empty()) {
          MatTile* d_outer = upload(bump, outer, s);
          if (g_prof) g_prof->next_tiles = (int)outer.size();
          PROF(PC_OUTER, launch_update(d_fronts, d_outer, (int)outer.size(), UPD_OUTER, big, s));
       }
-      if (!bulk.empty()) {
+      if (have_bulk) {
          cudaStream_t s2 = N.stream2;
          Buf& bb = N.S->b_bulk[bulk_parity];
          bulk_parity ^= 1;
          size_t regs_bytes = align_up(bulk_regs.size() * sizeof(int4), 256);
-         size_t need_b = regs_bytes + bulk.size() * sizeof(MatTile) + 256;
+         size_t a_bytes = align_up(bulk.size() * sizeof(MatTile), 256);
+         size_t need_b = regs_bytes + a_bytes + bulk_b.size() * sizeof(MatTile) + 256;
          if (need_b > bb.cap) bb.ensure(need_b * 2 + 4096, s2);       // drains stream2 before re-allocating
          CUDA_TRY(cudaMemcpyAsync(bb.p, bulk_regs.data(), bulk_regs.size() * sizeof(int4), cudaMemcpyHostToDevice, s2));
-         MatTile* d_bulk = (MatTile*)((char*)bb.p + regs_bytes);
-         CUDA_TRY(cudaMemcpyAsync(d_bulk, bulk.data(), bulk.size() * sizeof(MatTile), cudaMemcpyHostToDevice, s2));
-         PROF_ON(PC_OUTER, s2, launch_update(d_fronts, d_bulk, (int)bulk.size(), UPD_EXPLICIT, big, s2,
-                                              g_bulk_ctas, (const int4*)bb.p));
-         CUDA_TRY(cudaEventRecord(N.ev_bulk, s2));
+         MatTile* d_a = (MatTile*)((char*)bb.p + regs_bytes);
+         MatTile* d_b = (MatTile*)((char*)bb.p + regs_bytes + a_bytes);
+         if (!bulk.empty()) {
+            CUDA_TRY(cudaMemcpyAsync(d_a, bulk.data(), bulk.size() * sizeof(MatTile), cudaMemcpyHostToDevice, s2));
+            PROF_ON(PC_OUTER, s2, launch_update(d_fronts, d_a, (int)bulk.size(), UPD_EXPLICIT, big, s2,
+                                                 g_bulk_ctas, (const int4*)bb.p));
+         }
+         CUDA_TRY(cudaEventRecord(N.ev_bulk, s2));       // the panel after next has all its updates from this panel
+         if (!bulk_b.empty()) {
+            CUDA_TRY(cudaMemcpyAsync(d_b, bulk_b.data(), bulk_b.size() * sizeof(MatTile), cudaMemcpyHostToDevice, s2));
+            PROF_ON(PC_OUTER, s2, launch_update(d_fronts, d_b, (int)bulk_b.size(), UPD_EXPLICIT, big, s2,
+                                                 g_bulk_ctas, (const int4*)bb.p));
+         }
+         CUDA_TRY(cudaEventRecord(N.ev_bulk_all, s2));
          bulk_pending = true;
       }
       if (!swap_rows.empty()) {
@@ -648,10 +671,12 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    CUDA_TRY(cudaStreamCreateWithFlags(&N.stream, cudaStreamNonBlocking));
    CUDA_TRY(cudaStreamCreateWithFlags(&N.stream2, cudaStreamNonBlocking));
    CUDA_TRY(cudaEventCreateWithFlags(&N.ev_bulk, cudaEventDisableTiming));
+   CUDA_TRY(cudaEventCreateWithFlags(&N.ev_bulk_all, cudaEventDisableTiming));
    cudaStream_t s = N.stream;
    configure_update_kernels();
    configure_solve_kernels();
    if (const char* e = getenv("SPRAL_B200_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
+   if (const char* e = getenv("SPRAL_B200_SOLVE_GRAPHS")) g_solve_graphs = atoi(e) != 0;
    g_bulk_ctas = device_sm_count() - 28;
    if (const char* e = getenv("SPRAL_B200_BULK_CTAS")) g_bulk_ctas = atoi(e);
    auto t_begin = std::chrono::steady_clock::now();
@@ -1061,37 +1086,59 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
       const int maxnr = std::min(nrhs, solve_max_chunk());
       const size_t chunk_bytes = (size_t)S.n * maxnr * sizeof(double);
       if (job == JOB_FWD) S.b_y.ensure(chunk_bytes, s);
-      if (nrhs > 1) S.b_xt.ensure(chunk_bytes, s);
       if (job == JOB_DIAG_BWD || job == JOB_BWD)
          S.b_pbuf.ensure(std::max<size_t>(N.max_level_work, 1) * solve_block() * solve_max_chunk() * sizeof(double), s);
       double* ywork = (double*)S.b_y.p;
       double* pbuf = (double*)S.b_pbuf.p;
+      S.b_xt.ensure(chunk_bytes, s);
       for (int r0 = 0; r0 < nrhs;) {
          int nr = solve_rhs_chunk(nrhs - r0);
          double* xcol = dx + (size_t)r0 * ldx;
-         /* chunks of several right-hand sides are swept in RHS-contiguous layout */
-         double* xs = xcol;
-         if (nr > 1) {
-            xs = (double*)S.b_xt.p;
-            launch_transpose_rhs(xcol, ldx, xs, S.n, nr, true, s);
-         }
-         if (job == JOB_FWD) {
-            for (int lev = 0; lev < S.nlevels; ++lev)
-               launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev],
-                     N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx, ywork, s);
-            launch_fwd_flush(N.d_sfronts, 0, S.nloc, nr, xs, ldx, ywork, s);
-         } else if (job == JOB_DIAG) {
-            if (!posdef) launch_diag_solve(N.d_sfronts, 0, S.nloc, nr, xs, ldx, s);
-         } else {
-            for (int lev = S.nlevels - 1; lev >= 0; --lev) {
-               int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
-               if (job == JOB_DIAG_BWD && !posdef) launch_diag_solve(N.d_sfronts, f0, f1 - f0, nr, xs, ldx, s);
-               launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
-                     N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
-                     xs, ldx, pbuf, s);
+         /* every chunk is swept in the pool's RHS-contiguous buffer: its address is
+          * stable, so the (long, launch-latency-bound) kernel sequence of a sweep is
+          * captured once into a CUDA graph per (job, chunk width) and replayed */
+         double* xs = (double*)S.b_xt.p;
+         launch_transpose_rhs(xcol, ldx, xs, S.n, nr, true, s);
+         auto sweep = [&]() {
+            if (job == JOB_FWD) {
+               for (int lev = 0; lev < S.nlevels; ++lev)
+                  launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev],
+                        N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx, ywork, s);
+               launch_fwd_flush(N.d_sfronts, 0, S.nloc, nr, xs, ldx, ywork, s);
+            } else if (job == JOB_DIAG) {
+               if (!posdef) launch_diag_solve(N.d_sfronts, 0, S.nloc, nr, xs, ldx, s);
+            } else {
+               for (int lev = S.nlevels - 1; lev >= 0; --lev) {
+                  int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
+                  if (job == JOB_DIAG_BWD && !posdef) launch_diag_solve(N.d_sfronts, f0, f1 - f0, nr, xs, ldx, s);
+                  launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
+                        N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
+                        xs, ldx, pbuf, s);
+               }
             }
+         };
+         Numeric::SolveGraph* sg = nullptr;
+         if (g_solve_graphs) {
+            for (auto& c : N.graphs)
+               if (c.job == (int)job && c.nr == nr) { sg = &c; break; }
+            if (sg && (sg->xs != xs || sg->ywork != ywork || sg->pbuf != pbuf)) {   // a pool buffer moved
+               cudaGraphExecDestroy(sg->exec); sg->exec = nullptr;
+            }
+            if (!sg) { N.graphs.push_back(Numeric::SolveGraph{(int)job, nr, nullptr, nullptr, nullptr, nullptr}); sg = &N.graphs.back(); }
+            if (!sg->exec) {
+               cudaGraph_t graph = nullptr;
+               CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+               sweep();
+               CUDA_TRY(cudaStreamEndCapture(s, &graph));
+               CUDA_TRY(cudaGraphInstantiate(&sg->exec, graph, 0));
+               cudaGraphDestroy(graph);
+               sg->xs = xs; sg->ywork = ywork; sg->pbuf = pbuf;
+            }
+            CUDA_TRY(cudaGraphLaunch(sg->exec, s));
+         } else {
+            sweep();
          }
-         if (nr > 1) launch_transpose_rhs(xcol, ldx, xs, S.n, nr, false, s);
+         launch_transpose_rhs(xcol, ldx, xs, S.n, nr, false, s);
          r0 += nr;
       }
       CUDA_TRY(cudaGetLastError());
