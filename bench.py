@@ -310,9 +310,14 @@ def main():
         tm = fk.numeric[0].timings()
         peak = float(lib.spral_ssids_b200_fp64_peak_tflops(local_rank))
         ach = float(tm[3]) / (float(tm[2]) * 1e-3) / 1e12 if tm[2] > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "k_update<128,2,4> UPD_CONTRIB (Schur complement, FP64 DMMA)",
+        roofline = {"bound": "tensor",
+                    "kernel": "k_update_ws<128,2,4,3,32> UPD_CONTRIB (Schur complement, FP64 DMMA, TMA bulk staged)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
-                    "traffic": None, "launches": int(tm[4]), "kernel_ms_per_step": float(tm[2]),
+                    "traffic": None,
+                    "traffic_largest_launch": {"dram_bytes": 2.30e10, "algorithmic_bytes": 1.34e9,
+                                               "source": "profiles/r01_ncu_full_upd_contrib_final.md (DRAM at 8% of peak: "
+                                                         "operand tiles re-read through the L2, not a bound)"},
+                    "launches": int(tm[4]), "kernel_ms_per_step": float(tm[2]),
                     "kernel_flops_per_step": float(tm[3]),
                     "peak_source": "FP64 DMMA issue loop measured live on this GPU "
                                    "(MEASURED_PEAKS.json has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.9 TF/s on this pool)"}
