@@ -134,13 +134,14 @@ int solve_rhs_chunk(int nrhs);
 int solve_max_chunk();
 void configure_solve_kernels();
 void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps,
-      bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s);
+      bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s,
+      unsigned int* bar = nullptr);      // bar: zeroable device counter -> one cooperative launch per level
 void launch_fwd_flush(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
       const double* ywork, cudaStream_t s);
 void launch_diag_solve(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
       cudaStream_t s);
 void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
       const int* wbeg, int nsteps, bool posdef, int nr, double* x, int ldx, double* pbuf,
-      cudaStream_t s);
+      cudaStream_t s, unsigned int* bar = nullptr);
 
 } // namespace b200

@@ -44,11 +44,28 @@ __device__ __forceinline__ int row_index(const SolveFront& f, int i) {
 }
 
 /* ---- forward ---------------------------------------------------------- */
-template <int NR, bool POSDEF>
-__global__ void __launch_bounds__(RT)
-k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
-      double* __restrict__ x, int ldx, double* __restrict__ ywork) {
-   RowTile w = work[blockIdx.x];
+/* Loads of data that other CTAs write during the same launch (cooperative
+ * kernels only) must bypass the non-coherent L1. */
+template <bool COH>
+__device__ __forceinline__ double ld_shared_data(const double* p) { return COH ? __ldcg(p) : *p; }
+
+/* Grid-wide barrier of a cooperative launch (all CTAs co-resident): `target` is
+ * the value the arrival counter reaches when every CTA has arrived. */
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(bar, 1u);
+      while (*(volatile unsigned int*)bar < target) { }
+      __threadfence();
+   }
+   __syncthreads();
+}
+
+template <int NR, bool POSDEF, bool COH>
+__device__ __forceinline__ void fwd_step_body(const SolveFront* fronts, const RowTile* work, int item, int step,
+      double* __restrict__ x, double* __restrict__ ywork) {
+   RowTile w = work[item];
    const SolveFront f = fronts[w.front];
    const int j0 = step * SB;
    if (j0 >= f.nelim) return;
@@ -69,7 +86,7 @@ k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
       int g = (threadIdx.x < wd) ? f.perm[j0 + threadIdx.x] - 1 : -1;
       gidx[threadIdx.x] = g;
       #pragma unroll
-      for (int k = 0; k < NR; ++k) xs[threadIdx.x][k] = (g >= 0) ? x[XI(g, k)] : 0.0;
+      for (int k = 0; k < NR; ++k) xs[threadIdx.x][k] = (g >= 0) ? ld_shared_data<COH>(&x[XI(g, k)]) : 0.0;   // L2: other CTAs update x within the launch
    }
    __syncthreads();
    {  /* forward substitution: lanes are rows; every warp takes NR/4 right-hand sides and
@@ -116,6 +133,26 @@ k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
        * shared with sibling fronts */
       #pragma unroll
       for (int k = 0; k < NR; ++k) atomicAdd(&x[XI(g, k)], -acc[k]);
+   }
+}
+
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(RT)
+k_fwd_step(const SolveFront* fronts, const RowTile* work, int step,
+      double* __restrict__ x, int ldx, double* __restrict__ ywork) {
+   fwd_step_body<NR, POSDEF, false>(fronts, work, blockIdx.x, step, x, ywork);
+}
+
+/* All block steps of a level in ONE cooperative launch: a grid barrier replaces
+ * the kernel boundary between dependent steps (the sweeps are bound by that
+ * latency, not by bandwidth, on the large fronts at the top of the tree). */
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(RT)
+k_fwd_level_coop(const SolveFront* fronts, const RowTile* work, int nsteps,
+      double* __restrict__ x, double* __restrict__ ywork, unsigned int* bar) {
+   for (int step = 0; step < nsteps; ++step) {
+      fwd_step_body<NR, POSDEF, true>(fronts, work, blockIdx.x, step, x, ywork);
+      if (step + 1 < nsteps) grid_barrier(bar, (unsigned int)(step + 1) * gridDim.x);
    }
 }
 
@@ -166,11 +203,10 @@ __device__ __forceinline__ int bwd_block(const SolveFront& f, int step) {
 }
 
 /* partial(t, j, k) = sum over rows r of tile t below the block of L(r, j0+j) * x(r, k) */
-template <int NR>
-__global__ void __launch_bounds__(RT)
-k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
-      const double* __restrict__ x, int ldx, double* __restrict__ pbuf) {
-   RowTile w = work[blockIdx.x];
+template <int NR, bool COH>
+__device__ __forceinline__ void bwd_reduce_body(const SolveFront* fronts, const RowTile* work, int item, int step,
+      const double* __restrict__ x, double* __restrict__ pbuf) {
+   RowTile w = work[item];
    const SolveFront f = fronts[w.front];
    const int b = bwd_block(f, step);
    if (b < 0) return;
@@ -191,7 +227,7 @@ k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
    {
       int g = active ? row_index(f, r) : 0;
       #pragma unroll
-      for (int k = 0; k < NR; ++k) xr[threadIdx.x][k] = active ? x[XI(g, k)] : 0.0;
+      for (int k = 0; k < NR; ++k) xr[threadIdx.x][k] = active ? ld_shared_data<COH>(&x[XI(g, k)]) : 0.0;
       const double* Lr = f.L + r + (size_t)j0 * ldl;
       for (int j = 0; j < SB; ++j) tile[warp][lane][j] = (active && j < wd) ? Lr[j * ldl] : 0.0;
    }
@@ -211,7 +247,7 @@ k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
    }
    __syncthreads();
    if (threadIdx.x < SB) {
-      double* out = pbuf + (size_t)blockIdx.x * SB * NR;
+      double* out = pbuf + (size_t)item * SB * NR;
       #pragma unroll
       for (int k = 0; k < NR; ++k) {
          double s = 0.0;
@@ -223,11 +259,16 @@ k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
 
 /* one CTA per front: y = x_blk - sum_t partial(t) (fixed order), solve L_kk^T z = y;
  * lanes are the block's columns, the right-hand sides are dealt to the warps */
-template <int NR, bool POSDEF>
+template <int NR>
 __global__ void __launch_bounds__(RT)
-k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, int step,
-      double* __restrict__ x, int ldx, const double* __restrict__ pbuf) {
-   const int fi = first + blockIdx.x;
+k_bwd_reduce(const SolveFront* fronts, const RowTile* work, int step,
+      const double* __restrict__ x, int ldx, double* __restrict__ pbuf) {
+   bwd_reduce_body<NR, false>(fronts, work, blockIdx.x, step, x, pbuf);
+}
+
+template <int NR, bool POSDEF, bool COH>
+__device__ __forceinline__ void bwd_diag_body(const SolveFront* fronts, int fi, const int* __restrict__ wbeg, int step,
+      double* __restrict__ x, const double* __restrict__ pbuf) {
    const SolveFront f = fronts[fi];
    const int b = bwd_block(f, step);
    if (b < 0) return;
@@ -252,13 +293,13 @@ k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, in
    #pragma unroll
    for (int q = 0; q < NRW; ++q) {
       int k = warp * NRW + q;
-      v[q] = (g >= 0 && k < NR) ? x[XI(g, k)] : 0.0;
+      v[q] = (g >= 0 && k < NR) ? ld_shared_data<COH>(&x[XI(g, k)]) : 0.0;
    }
    for (int t = t0; t < ntile; ++t) {
       #pragma unroll
       for (int q = 0; q < NRW; ++q) {
          int k = warp * NRW + q;
-         if (k < NR) v[q] -= pb[(size_t)t * SB * NR + lane * NR + k];
+         if (k < NR) v[q] -= ld_shared_data<COH>(&pb[(size_t)t * SB * NR + lane * NR + k]);
       }
    }
    for (int j = wd - 1; j >= 0; --j) {
@@ -278,26 +319,97 @@ k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, in
    }
 }
 
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(RT)
+k_bwd_diag(const SolveFront* fronts, int first, const int* __restrict__ wbeg, int step,
+      double* __restrict__ x, int ldx, const double* __restrict__ pbuf) {
+   bwd_diag_body<NR, POSDEF, false>(fronts, first + blockIdx.x, wbeg, step, x, pbuf);
+}
+
+/* Backward counterpart: per step the partial sums of every tile, a grid barrier,
+ * the diagonal-block solve by the CTA that owns tile 0 of each front, a barrier. */
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(RT)
+k_bwd_level_coop(const SolveFront* fronts, const RowTile* work, const int* __restrict__ wbeg, int nsteps,
+      double* __restrict__ x, double* __restrict__ pbuf, unsigned int* bar) {
+   const RowTile w = work[blockIdx.x];
+   unsigned int target = 0;
+   for (int step = 0; step < nsteps; ++step) {
+      bwd_reduce_body<NR, true>(fronts, work, blockIdx.x, step, x, pbuf);
+      target += gridDim.x; grid_barrier(bar, target);
+      if (w.tile == 0) bwd_diag_body<NR, POSDEF, true>(fronts, w.front, wbeg, step, x, pbuf);
+      if (step + 1 < nsteps) { target += gridDim.x; grid_barrier(bar, target); }
+   }
+}
+
 template <int NR>
 constexpr size_t reduce_smem() { return ((size_t)(RT / 32) * 32 * (SB + 1) + (size_t)RT * NR) * sizeof(double); }
 
+/* CTAs of a kernel that can be resident at once on the current device */
+template <class K>
+int coop_capacity(K kernel, size_t smem) {
+   int nb = 0, dev = 0, sms = 0;
+   cudaGetDevice(&dev);
+   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, RT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+   return nb * sms;
+}
+
+template <int NR, bool POSDEF>
+void fwd_level_t(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps,
+      double* x, int ldx, double* ywork, unsigned int* bar, cudaStream_t s) {
+   static int cap = -1;
+   if (cap < 0) cap = coop_capacity(k_fwd_level_coop<NR, POSDEF>, 0);
+   if (bar && nsteps > 1 && nwork <= cap) {
+      cudaMemsetAsync(bar, 0, sizeof(unsigned int), s);
+      void* args[] = {(void*)&fronts, (void*)&work, (void*)&nsteps, (void*)&x, (void*)&ywork, (void*)&bar};
+      if (cudaLaunchCooperativeKernel((const void*)k_fwd_level_coop<NR, POSDEF>, dim3(nwork), dim3(RT), args, 0, s) == cudaSuccess) {
+         COUNT_LAUNCH();
+         return;
+      }
+      cudaGetLastError();      // fall back to one launch per step
+   }
+   for (int st = 0; st < nsteps; ++st) {
+      k_fwd_step<NR, POSDEF><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork); COUNT_LAUNCH();
+   }
+}
+
 template <int NR>
 void fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps, bool posdef,
-      double* x, int ldx, double* ywork, cudaStream_t s) {
+      double* x, int ldx, double* ywork, unsigned int* bar, cudaStream_t s) {
+   if (posdef) fwd_level_t<NR, true>(fronts, work, nwork, nsteps, x, ldx, ywork, bar, s);
+   else fwd_level_t<NR, false>(fronts, work, nwork, nsteps, x, ldx, ywork, bar, s);
+}
+
+template <int NR, bool POSDEF>
+void bwd_level_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      const int* wbeg, int nsteps, double* x, int ldx, double* pbuf, unsigned int* bar, cudaStream_t s) {
+   static int cap = -1;
+   if (cap < 0) {
+      cudaFuncSetAttribute(k_bwd_level_coop<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduce_smem<NR>());
+      cap = coop_capacity(k_bwd_level_coop<NR, POSDEF>, reduce_smem<NR>());
+   }
+   if (bar && nsteps > 1 && nwork <= cap) {
+      cudaMemsetAsync(bar, 0, sizeof(unsigned int), s);
+      void* args[] = {(void*)&fronts, (void*)&work, (void*)&wbeg, (void*)&nsteps, (void*)&x, (void*)&pbuf, (void*)&bar};
+      if (cudaLaunchCooperativeKernel((const void*)k_bwd_level_coop<NR, POSDEF>, dim3(nwork), dim3(RT), args,
+                                      reduce_smem<NR>(), s) == cudaSuccess) {
+         COUNT_LAUNCH();
+         return;
+      }
+      cudaGetLastError();
+   }
    for (int st = 0; st < nsteps; ++st) {
-      if (posdef) k_fwd_step<NR, true><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork);
-      else k_fwd_step<NR, false><<<nwork, RT, 0, s>>>(fronts, work, st, x, ldx, ywork); COUNT_LAUNCH();
+      k_bwd_reduce<NR><<<nwork, RT, reduce_smem<NR>(), s>>>(fronts, work, st, x, ldx, pbuf); COUNT_LAUNCH();
+      k_bwd_diag<NR, POSDEF><<<count, RT, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf); COUNT_LAUNCH();
    }
 }
 
 template <int NR>
 void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      const int* wbeg, int nsteps, bool posdef, double* x, int ldx, double* pbuf, cudaStream_t s) {
-   for (int st = 0; st < nsteps; ++st) {
-      k_bwd_reduce<NR><<<nwork, RT, reduce_smem<NR>(), s>>>(fronts, work, st, x, ldx, pbuf); COUNT_LAUNCH();
-      if (posdef) k_bwd_diag<NR, true><<<count, RT, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf);
-      else k_bwd_diag<NR, false><<<count, RT, 0, s>>>(fronts, first, wbeg, st, x, ldx, pbuf); COUNT_LAUNCH();
-   }
+      const int* wbeg, int nsteps, bool posdef, double* x, int ldx, double* pbuf, unsigned int* bar, cudaStream_t s) {
+   if (posdef) bwd_level_t<NR, true>(fronts, first, count, work, nwork, wbeg, nsteps, x, ldx, pbuf, bar, s);
+   else bwd_level_t<NR, false>(fronts, first, count, work, nwork, wbeg, nsteps, x, ldx, pbuf, bar, s);
 }
 
 } // namespace
@@ -328,15 +440,15 @@ int solve_rhs_chunk(int nrhs) { return nrhs >= 32 ? 32 : nrhs >= 16 ? 16 : nrhs 
 int solve_max_chunk() { return 32; }
 
 void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps,
-      bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s) {
+      bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s, unsigned int* bar) {
    if (nwork == 0 || nsteps == 0) return;
    switch (nr) {
-   case 32: fwd_level<32>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
-   case 16: fwd_level<16>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
-   case 8: fwd_level<8>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
-   case 4: fwd_level<4>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
-   case 2: fwd_level<2>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
-   default: fwd_level<1>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, s); break;
+   case 32: fwd_level<32>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, bar, s); break;
+   case 16: fwd_level<16>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, bar, s); break;
+   case 8: fwd_level<8>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, bar, s); break;
+   case 4: fwd_level<4>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, bar, s); break;
+   case 2: fwd_level<2>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, bar, s); break;
+   default: fwd_level<1>(fronts, work, nwork, nsteps, posdef, x, ldx, ywork, bar, s); break;
    }
 }
 
@@ -354,15 +466,15 @@ void launch_diag_solve(const SolveFront* fronts, int first, int count, int nrhs,
 
 void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
       const int* wbeg, int nsteps, bool posdef, int nr, double* x, int ldx, double* pbuf,
-      cudaStream_t s) {
+      cudaStream_t s, unsigned int* bar) {
    if (nwork == 0 || nsteps == 0) return;
    switch (nr) {
-   case 32: bwd_level<32>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
-   case 16: bwd_level<16>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
-   case 8: bwd_level<8>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
-   case 4: bwd_level<4>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
-   case 2: bwd_level<2>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
-   default: bwd_level<1>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, s); break;
+   case 32: bwd_level<32>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, bar, s); break;
+   case 16: bwd_level<16>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, bar, s); break;
+   case 8: bwd_level<8>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, bar, s); break;
+   case 4: bwd_level<4>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, bar, s); break;
+   case 2: bwd_level<2>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, bar, s); break;
+   default: bwd_level<1>(fronts, first, count, work, nwork, wbeg, nsteps, posdef, x, ldx, pbuf, bar, s); break;
    }
 }
 

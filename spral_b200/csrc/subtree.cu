@@ -35,7 +35,8 @@ namespace b200 {
 
 struct CudaError { cudaError_t code; };
 static bool g_profile = false;
-static bool g_solve_graphs = true;   // SPRAL_B200_SOLVE_GRAPHS=0: launch the solve kernels one by one
+static bool g_solve_graphs = false;  // SPRAL_B200_SOLVE_GRAPHS=1: replay the sweeps as CUDA graphs (no measured gain)
+static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative launch per level (experimental: no measured gain yet)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS)
 /* Clears (and, with SPRAL_B200_DEBUG set, reports) a pending non-sticky CUDA
@@ -186,6 +187,7 @@ struct Symbolic {
    /* scratch pool shared by the factorisations / solves of this subtree */
    std::mutex mtx;
    Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf, b_xt;
+   Buf b_bar;                         // arrival counter of the cooperative solve kernels
    Buf b_export;                      // packed contribution block handed to another process (IPC)
    Buf b_bulk[2];                     // tile lists of the look-ahead bulk updates (alternating panels)
 
@@ -195,7 +197,7 @@ struct Symbolic {
       cudaFree(d_node_of_front);
       b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
       b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
-      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export.release(); b_bulk[0].release(); b_bulk[1].release();
+      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export.release(); b_bar.release(); b_bulk[0].release(); b_bulk[1].release();
    }
 };
 
@@ -677,6 +679,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    configure_solve_kernels();
    if (const char* e = getenv("SPRAL_B200_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_GRAPHS")) g_solve_graphs = atoi(e) != 0;
+   if (const char* e = getenv("SPRAL_B200_SOLVE_COOP")) g_solve_coop = atoi(e) != 0;
    g_bulk_ctas = device_sm_count() - 28;
    if (const char* e = getenv("SPRAL_B200_BULK_CTAS")) g_bulk_ctas = atoi(e);
    auto t_begin = std::chrono::steady_clock::now();
@@ -1090,6 +1093,8 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          S.b_pbuf.ensure(std::max<size_t>(N.max_level_work, 1) * solve_block() * solve_max_chunk() * sizeof(double), s);
       double* ywork = (double*)S.b_y.p;
       double* pbuf = (double*)S.b_pbuf.p;
+      S.b_bar.ensure(256, s);
+      unsigned int* bar = g_solve_coop ? (unsigned int*)S.b_bar.p : nullptr;
       S.b_xt.ensure(chunk_bytes, s);
       for (int r0 = 0; r0 < nrhs;) {
          int nr = solve_rhs_chunk(nrhs - r0);
@@ -1103,7 +1108,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
             if (job == JOB_FWD) {
                for (int lev = 0; lev < S.nlevels; ++lev)
                   launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev],
-                        N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx, ywork, s);
+                        N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx, ywork, s, bar);
                launch_fwd_flush(N.d_sfronts, 0, S.nloc, nr, xs, ldx, ywork, s);
             } else if (job == JOB_DIAG) {
                if (!posdef) launch_diag_solve(N.d_sfronts, 0, S.nloc, nr, xs, ldx, s);
@@ -1113,7 +1118,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                   if (job == JOB_DIAG_BWD && !posdef) launch_diag_solve(N.d_sfronts, f0, f1 - f0, nr, xs, ldx, s);
                   launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                         N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
-                        xs, ldx, pbuf, s);
+                        xs, ldx, pbuf, s, bar);
                }
             }
          };
