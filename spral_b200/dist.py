@@ -111,10 +111,44 @@ class DistAkeep:
         self.rank_of, self.consumer, self.children = rank_of, consumer, children
 
 
-def analyse(ctx, n, ptr, row, order=None, nemin=32, options=None, **kw):
+def modelled_critical_path(a, world):
+    """Length of the longest chain of the part schedule when every part costs its
+    flops (normalised to the whole tree) plus a fixed per-part overhead."""
+    consumer, children = part_graph(a)
+    rank_of = assign_ranks(a, world)
+    fl = part_flops(a)
+    tot = max(float(fl.sum()), 1.0)
+    fin = [0.0] * a.nparts
+    busy = [0.0] * world
+    for p in range(a.nparts):
+        start = max([fin[c] for c in children[p]] + [busy[rank_of[p]]])
+        fin[p] = start + fl[p] / tot + 0.005
+        busy[rank_of[p]] = fin[p]
+    return max(fin) if fin else 0.0
+
+
+def analyse(ctx, n, ptr, row, order=None, nemin=32, options=None, tune_partition=True, **kw):
     """ssids_analyse on every rank (deterministic, replicated), symbolic subtrees
-    only for the parts this rank owns."""
+    only for the parts this rank owns.  With several GPUs the subtree partition is
+    computed for a few values of options%max_load_inbalance (the reference's own
+    knob, src/ssids/datatypes.f90:223-228) and the one with the shortest modelled
+    critical path is kept: a finer partition is not always better, every part
+    boundary costs the level-set batching across its subtrees."""
     a = Analysis(n, ptr, row, order=order, nemin=nemin, ngpu=ctx.world, **kw)
+    if ctx.world > 1 and tune_partition and "max_load_inbalance" not in kw:
+        best, best_cp = a, modelled_critical_path(a, ctx.world)
+        for mli in (2.0, 3.0):
+            kw2 = dict(kw, max_load_inbalance=mli)
+            cand = Analysis(n, ptr, row, order=a.order.copy(), nemin=nemin, ngpu=ctx.world, **kw2)
+            cp = modelled_critical_path(cand, ctx.world)
+            if cand.nparts > 1 and cp < best_cp - 1e-9:
+                best.close() if best is not a else None
+                best, best_cp = cand, cp
+            else:
+                cand.close()
+        if best is not a:
+            a.close()
+        a = best
     rank_of = assign_ranks(a, ctx.world)
     consumer, children = part_graph(a)
     subtrees = []
