@@ -30,13 +30,16 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 os.environ.setdefault("OMP_CANCELLATION", "TRUE")
-os.environ.setdefault("OMP_PROC_BIND", "TRUE")
 os.environ.setdefault("NCCL_DEBUG", "WARN")       # keeps NCCL's version banner off stdout (one JSON line only)
+# OMP_PROC_BIND belongs to the CPU reference arm only (run_reference): with it set, libgomp pins
+# the initial thread of EVERY process that loads it (torch does) to the first CPU of the mask, and
+# every thread created later inherits that mask -- all ranks of a torchrun job then share core 0.
+_FULL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
 
 import numpy as np  # noqa: E402
 
 SHIFT = 13.0
-CPU_SAMPLE_GRID = 56      # the CPU arms factor the same stencil on a smaller grid
+CPU_SAMPLE_GRID = 72      # the CPU arms factor the same stencil on a smaller grid
 
 
 def make_matrix(grid):
@@ -109,25 +112,41 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
-def cpu_reference_factor(grid, nthreads=0):
-    """The reference's own CPU engine (oracle/_ref, unmodified sources) on the same
-    stencil at `grid`^3; returns (GFLOP/s, seconds, cores, flops)."""
-    import oracle_ref
-    from spral_b200.ssids import Analysis
-    oracle_ref.ensure_env()
-    n, ptr, row, val = make_matrix(grid)
-    a = Analysis(n, ptr, row)
-    cores = nthreads or os.cpu_count()
-    parts, inform, _ = oracle_ref.ref_factor(a, False, val, nthreads=cores)
-    for p in parts:
-        p.close()
-    t = inform["factor_time"]
-    return inform["num_flops"] / t / 1e9, t, cores, inform["num_flops"], a
+def host_cores():
+    """CPUs this process may run on (cgroup cpusets / taskset respected)."""
+    return len(_FULL_AFFINITY) if _FULL_AFFINITY else (os.cpu_count() or 1)
+
+
+def restore_affinity():
+    """Undo a thread pin inherited from the environment (OMP_PROC_BIND / GOMP_CPU_AFFINITY set by
+    the caller): the engine's host threads, NCCL's and the CUDA driver's inherit the mask of the
+    thread that creates them."""
+    if _FULL_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+        except OSError:
+            pass
+
+
+def cpu_reference_factor(grid):
+    """cpu_baseline leg: the reference's own CPU engine (oracle/_ref, unmodified sources) on the
+    same stencil at `grid`^3, in a process of its own (`bench.py --impl reference`) so that its
+    OpenMP binding does not touch this process.  Returns the reference arm's JSON line."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS", "MASTER_ADDR", "MASTER_PORT")}
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-grid", str(grid)], env=env, capture_output=True, text=True,
+                         timeout=900)
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("reference arm printed no JSON line: " + out.stderr[-300:])
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
+    os.environ.setdefault("OMP_PROC_BIND", "TRUE")     # before libgomp loads (SURVEY 8d: OpenMP tasks bound to cores)
     import oracle_ref
     from spral_b200.ssids import Analysis
     if not oracle_ref.available():
@@ -137,7 +156,7 @@ def run_reference(args, rank):
     grid = args.cpu_grid
     n, ptr, row, val = make_matrix(grid)
     a = Analysis(n, ptr, row)
-    cores = os.cpu_count()
+    cores = host_cores()
     times, flops = [], 0
     for it in range(args.warmup + args.steps):
         parts, inform, _ = oracle_ref.ref_factor(a, False, val, nthreads=cores)
@@ -183,6 +202,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    restore_affinity()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     if os.environ.get("SPRAL_B200_ONE_DEVICE"):      # debugging aid: ranks share GPUs (gloo instead of NCCL)
@@ -225,13 +245,17 @@ def main():
     def factor_once(values_ptr):
         """One ssids_factor over all parts; returns (fkeep, wall seconds, device ms of this rank)."""
         barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t = time.perf_counter()
-        fk = sdist.factor(ctx, ak, False, values_ptr)
+        ev0.record()
+        fk = sdist.factor(ctx, ak, False, values_ptr)   # returns when this rank's streams have drained
+        ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t
+        span_ms = ev0.elapsed_time(ev1)                  # device clock, first launch .. last part done
         dev_ms = sum(float(ns.timings()[1]) for ns in fk.numeric if ns is not None)
         barrier()
-        return fk, wall, dev_ms
+        return fk, wall, (dev_ms if world == 1 else span_ms)
 
     # ---- warm-up ----
     fk = None
@@ -248,8 +272,10 @@ def main():
         if fk is not None:
             sdist.free(fk)
         fk, wall, dev_ms = factor_once(dval.data_ptr())
-        # whole-job time = slowest rank; at N=1 the device-event time of the call
-        t_step = max_over_ranks(dev_ms / 1e3 if world == 1 else wall)
+        # whole-job time = slowest rank, on the device clock: at N=1 the CUDA events the engine
+        # records on its factorisation stream, at N>1 events bracketing this rank's parts
+        # (several streams and the waits for other ranks' contribution blocks in between)
+        t_step = max_over_ranks(dev_ms / 1e3)
         walls.append(t_step)
         launches += int(sum(float(ns.timings()[6]) for ns in fk.numeric if ns is not None))
     clocks = sampler.stop()
@@ -331,7 +357,7 @@ def main():
                                f"n={n}, LDL^T u=0.01, METIS order, nemin=32 (BASELINE configs[4])",
                    "parallelism": f"subtree-partition x{world}" if world > 1 else "1 GPU",
                    "nparts": int(a.nparts), "l2": "inputs larger than L2 (factor storage %.1f GB)" % (inform["num_factor"] * 8 / 1e9),
-                   "timer": "CUDA events on the factorisation stream (N=1); wall clock, max over ranks (N>1)"},
+                   "timer": "CUDA events: on the factorisation stream (N=1); bracketing each rank's parts, max over ranks (N>1)"},
         "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": int(nz * 8),
                 "d2h_bytes_per_step": int(front_bytes)},
         "gpu_launches": launches,
@@ -349,10 +375,10 @@ def main():
         try:
             import oracle_ref
             if oracle_ref.available():
-                v, t, cores, fl, a2 = cpu_reference_factor(args.cpu_grid)
-                out["cpu_baseline"] = {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
-                                       "sample": f"3-D 27-point {args.cpu_grid}^3 shifted indefinite, whole factor "
-                                                 f"({fl:.3g} flops in {t:.2f} s), same ordering/options"}
+                ref = cpu_reference_factor(args.cpu_grid)
+                if "cpu_baseline" not in ref:
+                    raise RuntimeError(ref.get("unavailable", "no cpu_baseline in the reference arm's line"))
+                out["cpu_baseline"] = dict(ref["cpu_baseline"], seconds=ref["ms_per_step"] / 1e3)
         except Exception as e:
             out["cpu_baseline"] = {"error": repr(e)}
     sdist.free(fk)

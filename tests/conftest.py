@@ -7,7 +7,6 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
         sys.path.insert(0, p)
 # the reference CPU engine needs these before libgomp starts (src/ssids/ssids.f90:1448-1452)
 os.environ.setdefault("OMP_CANCELLATION", "TRUE")
-os.environ.setdefault("OMP_PROC_BIND", "TRUE")
 
 
 def pytest_configure(config):

@@ -27,8 +27,6 @@ def ensure_env():
     """The reference needs OMP_CANCELLATION before libgomp initialises
     (src/ssids/ssids.f90:1448-1452)."""
     os.environ.setdefault("OMP_CANCELLATION", "TRUE")
-    os.environ.setdefault("OMP_PROC_BIND", "TRUE")
-
 
 def load():
     global _ref
