@@ -116,7 +116,7 @@ int scatter_chunk();
 /* ---- DMMA update kernels (gemm_dmma.cu) ---- */
 enum UpdateMode { UPD_INNER = 0, UPD_OUTER = 1, UPD_CONTRIB = 2, UPD_EXPLICIT = 3 };
 void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
-      bool big_tiles, cudaStream_t s, int max_ctas = 0,      // max_ctas: cap on the persistent grid (0 = all SMs)
+      bool big_tiles, cudaStream_t s, int max_ctas = 0,      // max_ctas: cap on the persistent grid (0 = all SMs, < 0 = one CTA per tile)
       const int4* xregs = nullptr);                         // UPD_EXPLICIT (large tiles only): {front, k0, k1, c_lo} per region
 int device_sm_count();
 int update_tile_size(bool big_tiles);

@@ -30,8 +30,10 @@
  * candidate range.  Failed columns are retried in later passes; what is left
  * is delayed to the parent.
  */
+#include <cstdlib>
 #include "engine.h"
 #include "device_utils.cuh"
+#include "diag_block.h"
 
 namespace b200 {
 #ifndef COUNT_LAUNCH
@@ -449,9 +451,100 @@ k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams
    }
 }
 
+
+/* Version 2 (opt-in, SPRAL_B200_DIAG_V2=1): the same factorisation with NW warps,
+ * every thread owning BS/NW entries of a column (diag_block.h).  The body is also
+ * compiled for the host and checked bit for bit against a sequential model of
+ * k_diag above (tests/c/diag_block_emu.cpp). */
+struct DiagDevCtx {
+   __device__ __forceinline__ int tid() const { return threadIdx.x; }
+   __device__ __forceinline__ void sync() { __syncthreads(); }
+   __device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+   __device__ __forceinline__ int shfl_xor(int v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+};
+
+template <bool POSDEF, int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_diag_v2(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
+   Front* f = &fronts[flist[blockIdx.x]];
+   __shared__ DiagShared<NW> sh;
+   __shared__ int s_go;
+   constexpr int RPT = BS / NW;
+   const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
+
+   if (threadIdx.x == 0) {
+      advance_state(f, new_panel != 0);
+      if (!f->finished && f->done < f->pend) {
+         f->bs = min(BS, f->pend - f->done);
+         f->first_fail = f->bs;
+         f->step_valid = 1;
+         s_go = 1;
+      } else {
+         f->bs = 0;
+         s_go = 0;
+      }
+   }
+   __syncthreads();
+   if (!s_go) return;
+   const int bs = f->bs, done = f->done, ldl = f->ldl;
+   double* Ld = f->L + (size_t)done * ldl + done;   // the diagonal block
+   BlockWS* ws = f->ws;
+
+   DiagDevCtx cx;
+   int cur = 0, zfrom = BS;
+   const int rc = diag_block_factor<NW, POSDEF>(cx, sh, Ld, (size_t)ldl, bs, prm.small, prm.action, CUDART_INF,
+                                                POSDEF ? nullptr : ws->a0, cur, zfrom);
+   if (rc != DB_OK) {
+      if (threadIdx.x == 0) { f->flag = rc; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
+      return;
+   }
+   if (POSDEF) {
+      #pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+         const int r = q * RPT + i;
+         const double l = (r < bs && c < bs && r >= c) ? sh.A[cur][r][c] : 0.0;
+         if (r < bs && c < bs && r >= c) Ld[r + (size_t)c * ldl] = l;
+         ws->l11[r + c * BS] = l;
+      }
+      if (q == 0) ws->dinv[c] = (c < bs) ? sh.dinv[c] : 0.0;
+   } else {
+      /* publish L11 (unit lower), L11*D, D^-1 and the local permutation */
+      #pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+         const int r = q * RPT + i;
+         double l = 0.0, y = 0.0;
+         if (r < bs && c < bs) {
+            if (r > c) { l = sh.A[cur][r][c]; y = sh.LDm[cur][r][c]; }
+            else if (r == c) l = 1.0;
+         }
+         ws->l11[r + c * BS] = l;
+         ws->ld11[r + c * BS] = y;
+      }
+      if (q == 0) {
+         ws->dinv[2 * c] = (c < bs) ? sh.dinv[2 * c] : 0.0;
+         ws->dinv[2 * c + 1] = (c < bs) ? sh.dinv[2 * c + 1] : 0.0;
+         ws->lperm[c] = sh.lperm[c];
+         if (c == 0) ws->zfrom = zfrom;
+      }
+   }
+}
+
+static int diag_version() {
+   static int v = -1;
+   if (v < 0) { const char* e = getenv("SPRAL_B200_DIAG_V2"); v = (e && atoi(e) != 0) ? 2 : 1; }
+   return v;
+}
+
 void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool new_panel,
       const FactorParams& prm, cudaStream_t s) {
    if (count == 0) return;
+   if (diag_version() == 2) {
+      constexpr int NW = 4;
+      if (posdef) k_diag_v2<true, NW><<<count, NW * 32, 0, s>>>(fronts, flist, new_panel, prm);
+      else k_diag_v2<false, NW><<<count, NW * 32, 0, s>>>(fronts, flist, new_panel, prm);
+      COUNT_LAUNCH();
+      return;
+   }
    if (posdef) k_diag<true><<<count, BS * BS, 0, s>>>(fronts, flist, new_panel, prm);
    else k_diag<false><<<count, BS * BS, 0, s>>>(fronts, flist, new_panel, prm); COUNT_LAUNCH();
 }

@@ -38,7 +38,10 @@ static bool g_profile = false;
 static bool g_solve_graphs = false;  // SPRAL_B200_SOLVE_GRAPHS=1: replay the sweeps as CUDA graphs (no measured gain)
 static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative launch per level (experimental: no measured gain yet)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
-static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS)
+static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS); < 0: one CTA per tile
+static bool g_bulk_prio = false;     // SPRAL_B200_BULK_PRIO=1 (experimental, unmeasured): instead of a static SM split,
+                                     // the panel stream gets the highest stream priority and the bulk update runs one
+                                     // tile per CTA on the lowest, so the panel kernels take SMs as bulk tiles retire
 /* Clears (and, with SPRAL_B200_DEBUG set, reports) a pending non-sticky CUDA
  * error so that it cannot leak into the host application's own CUDA calls. */
 static void clear_cuda_error(const char* where) {
@@ -670,8 +673,16 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    const bool posdef = N.posdef;
    std::lock_guard<std::mutex> lock(S.mtx);
    CUDA_TRY(cudaSetDevice(S.device));
-   CUDA_TRY(cudaStreamCreateWithFlags(&N.stream, cudaStreamNonBlocking));
-   CUDA_TRY(cudaStreamCreateWithFlags(&N.stream2, cudaStreamNonBlocking));
+   if (const char* e = getenv("SPRAL_B200_BULK_PRIO")) g_bulk_prio = atoi(e) != 0;
+   if (g_bulk_prio) {
+      int least = 0, greatest = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      CUDA_TRY(cudaStreamCreateWithPriority(&N.stream, cudaStreamNonBlocking, greatest));
+      CUDA_TRY(cudaStreamCreateWithPriority(&N.stream2, cudaStreamNonBlocking, least));
+   } else {
+      CUDA_TRY(cudaStreamCreateWithFlags(&N.stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamCreateWithFlags(&N.stream2, cudaStreamNonBlocking));
+   }
    CUDA_TRY(cudaEventCreateWithFlags(&N.ev_bulk, cudaEventDisableTiming));
    CUDA_TRY(cudaEventCreateWithFlags(&N.ev_bulk_all, cudaEventDisableTiming));
    cudaStream_t s = N.stream;
@@ -680,7 +691,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    if (const char* e = getenv("SPRAL_B200_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_GRAPHS")) g_solve_graphs = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_COOP")) g_solve_coop = atoi(e) != 0;
-   g_bulk_ctas = device_sm_count() - 28;
+   g_bulk_ctas = g_bulk_prio ? -1 : device_sm_count() - 28;
    if (const char* e = getenv("SPRAL_B200_BULK_CTAS")) g_bulk_ctas = atoi(e);
    auto t_begin = std::chrono::steady_clock::now();
    CUDA_TRY(cudaEventCreate(&N.ev_begin));

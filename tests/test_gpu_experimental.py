@@ -1,0 +1,47 @@
+"""Opt-in kernel variants against the default engine (GPU; runs only with
+SPRAL_B200_EXPERIMENTAL_TESTS=1 because the variants have not been on a B200 yet).
+
+Each variant is selected by an environment variable that the library reads once per
+process, so both sides run tools/dump_factor.py in a process of their own.  A variant
+that only changes HOW the same arithmetic is scheduled must reproduce pivot order,
+D^-1, inform and the solution bit for bit:
+  SPRAL_B200_DIAG_V2=1     4-warp diagonal-block kernel (diag_block.h; the body is
+                           checked on the CPU by tests/test_kernel_emulation.py)
+  SPRAL_B200_BULK_PRIO=1   look-ahead bulk update one tile per CTA on a low-priority
+                           stream instead of a capped persistent grid
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SPRAL_B200_EXPERIMENTAL_TESTS") != "1",
+                                 reason="set SPRAL_B200_EXPERIMENTAL_TESTS=1 to run the opt-in kernel variants")]
+
+
+def _dump(tmp_path, tag, **env):
+    out = str(tmp_path / f"{tag}.npz")
+    e = dict(os.environ)
+    for k in ("SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO", "SPRAL_B200_PANEL_V2"):
+        e.pop(k, None)
+    e.update(env)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_factor.py"), out], env=e, timeout=900)
+    return np.load(out)
+
+
+@pytest.fixture(scope="module")
+def baseline(tmp_path_factory):
+    return _dump(tmp_path_factory.mktemp("base"), "base")
+
+
+@pytest.mark.parametrize("var", ["SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO"])
+def test_variant_reproduces_default_engine_bit_for_bit(tmp_path, baseline, var):
+    got = _dump(tmp_path, var, **{var: "1"})
+    assert sorted(got.files) == sorted(baseline.files)
+    for k in baseline.files:
+        assert np.array_equal(baseline[k], got[k], equal_nan=True), (var, k)

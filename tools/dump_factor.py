@@ -1,0 +1,43 @@
+"""Factorises a few fixed matrices on cuda:0 and dumps what identifies the result
+bit for bit (pivot order, D^-1, inform, one solution) to an .npz.  Used by
+tests/test_gpu_experimental.py to compare an opt-in kernel variant (selected
+through the SPRAL_B200_* environment of THIS process) with the default engine."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import spral_b200 as sb                      # noqa: E402
+from spral_b200 import matrices as M         # noqa: E402
+
+CASES = {
+    "stencil27_20_indef": (lambda: M.stencil_3d_27pt(20, shift=13.0), False),
+    "stencil27_36_indef": (lambda: M.stencil_3d_27pt(36, shift=13.0), False),
+    "lap3d_24_posdef": (lambda: M.laplacian_3d_7pt(24), True),
+    "kkt_3000": (lambda: M.kkt_saddle(3000, 0.3, seed=3), False),
+}
+
+
+def main(out):
+    res = {}
+    for name, (gen, posdef) in CASES.items():
+        n, ptr, row, val = gen()
+        ak = sb.analyse(n, ptr, row)
+        fk = sb.factor(ak, posdef, val)
+        piv, d = fk.numeric[0].enquire()
+        A = M.to_scipy(n, ptr, row, val)
+        x = sb.solve(fk, A @ np.ones(n))
+        g = fk.inform
+        res[name + "/d"] = d
+        if piv is not None:
+            res[name + "/piv"] = piv
+        res[name + "/x"] = x
+        res[name + "/inform"] = np.array([g[k] for k in ("flag", "num_delay", "num_neg", "num_two", "matrix_rank",
+                                                          "num_factor", "num_flops")], dtype=np.int64)
+    np.savez(out, **res)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
