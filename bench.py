@@ -339,10 +339,14 @@ def main():
         roofline = {"bound": "tensor",
                     "kernel": "k_update_ws<128,2,4,3,32> UPD_CONTRIB (Schur complement, FP64 DMMA, TMA bulk staged)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
-                    "traffic": None,
-                    "traffic_largest_launch": {"dram_bytes": 2.30e10, "algorithmic_bytes": 1.34e9,
-                                               "source": "profiles/r01_ncu_full_upd_contrib_final.md (DRAM at 8% of peak: "
-                                                         "operand tiles re-read through the L2, not a bound)"},
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the largest of the 14, root-side
+                    # front: 20.46 + 2.56 GB) from the committed ncu --set full capture; not re-measured here
+                    "traffic": 2.30e10,
+                    "traffic_launch": {"which": "largest UPD_CONTRIB launch (contribution block 10600^2, K = 5243)",
+                                       "algorithmic_bytes": 1.34e9, "algorithmic_flops": 5.9e11,
+                                       "source": "profiles/r01_ncu_full_upd_contrib_final.md (DRAM at 8% of peak: the row "
+                                                 "panels of L are re-read through the L2 once per tile column; bound is the "
+                                                 "FP64 tensor pipe, 92% active)"},
                     "launches": int(tm[4]), "kernel_ms_per_step": float(tm[2]),
                     "kernel_flops_per_step": float(tm[3]),
                     "peak_source": "FP64 DMMA issue loop measured live on this GPU "

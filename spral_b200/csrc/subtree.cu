@@ -39,6 +39,8 @@ static bool g_solve_graphs = false;  // SPRAL_B200_SOLVE_GRAPHS=1: replay the sw
 static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative launch per level (experimental: no measured gain yet)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS); < 0: one CTA per tile
+static int g_ctile_block = 0;        // SPRAL_B200_CTILE_BLOCK=12 (experimental, unmeasured): Schur-complement tiles in
+                                     // SB x SB blocked order for L2 reuse of the operand panels (0 = column by column)
 static bool g_bulk_prio = false;     // SPRAL_B200_BULK_PRIO=1 (experimental, unmeasured): instead of a static SM split,
                                      // the panel stream gets the highest stream priority and the bulk update runs one
                                      // tile per CTA on the lowest, so the panel kernels take SMs as bulk tiles retire
@@ -674,6 +676,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    std::lock_guard<std::mutex> lock(S.mtx);
    CUDA_TRY(cudaSetDevice(S.device));
    if (const char* e = getenv("SPRAL_B200_BULK_PRIO")) g_bulk_prio = atoi(e) != 0;
+   if (const char* e = getenv("SPRAL_B200_CTILE_BLOCK")) g_ctile_block = atoi(e);
    if (g_bulk_prio) {
       int least = 0, greatest = 0;
       CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -925,8 +928,20 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
             const Front& f = F[fi];
             if (f.m == f.n) continue;
             int mt = (f.m + T - 1) / T;
-            for (int tj = f.n / T; tj < mt; ++tj)
-               for (int ti = tj; ti < mt; ++ti) ctiles.push_back({fi, ti, tj});
+            const int tj0 = f.n / T;
+            const int SB = g_ctile_block;
+            if (big && SB > 1 && (mt - tj0) >= 2 * SB) {
+               /* blocked order: consecutive groups of ~SB*SB tiles form SB x SB squares, so the CTAs of
+                * one wave of the persistent kernel share SB row panels and SB column panels of L / LD in
+                * the L2 instead of one column panel and 148 different row panels */
+               for (int bj = tj0; bj < mt; bj += SB)
+                  for (int bi = bj; bi < mt; bi += SB)
+                     for (int tj = bj; tj < std::min(bj + SB, mt); ++tj)
+                        for (int ti = std::max(bi, tj); ti < std::min(bi + SB, mt); ++ti) ctiles.push_back({fi, ti, tj});
+            } else {
+               for (int tj = tj0; tj < mt; ++tj)
+                  for (int ti = tj; ti < mt; ++ti) ctiles.push_back({fi, ti, tj});
+            }
          }
       }
       size_t wbytes = 4096 + (scat.size() + dly.size()) * sizeof(int2) + srcs.size() * sizeof(AsmSrc)

@@ -9,6 +9,7 @@ D^-1, inform and the solution bit for bit:
                            checked on the CPU by tests/test_kernel_emulation.py)
   SPRAL_B200_BULK_PRIO=1   look-ahead bulk update one tile per CTA on a low-priority
                            stream instead of a capped persistent grid
+  SPRAL_B200_CTILE_BLOCK=4 Schur-complement tiles in blocked order (L2 reuse)
 """
 import os
 import subprocess
@@ -27,7 +28,7 @@ pytestmark = [pytest.mark.gpu,
 def _dump(tmp_path, tag, **env):
     out = str(tmp_path / f"{tag}.npz")
     e = dict(os.environ)
-    for k in ("SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO", "SPRAL_B200_PANEL_V2"):
+    for k in ("SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO", "SPRAL_B200_CTILE_BLOCK"):
         e.pop(k, None)
     e.update(env)
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_factor.py"), out], env=e, timeout=900)
@@ -39,9 +40,10 @@ def baseline(tmp_path_factory):
     return _dump(tmp_path_factory.mktemp("base"), "base")
 
 
-@pytest.mark.parametrize("var", ["SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO"])
-def test_variant_reproduces_default_engine_bit_for_bit(tmp_path, baseline, var):
-    got = _dump(tmp_path, var, **{var: "1"})
+@pytest.mark.parametrize("var,value", [("SPRAL_B200_DIAG_V2", "1"), ("SPRAL_B200_BULK_PRIO", "1"),
+                                       ("SPRAL_B200_CTILE_BLOCK", "4")])
+def test_variant_reproduces_default_engine_bit_for_bit(tmp_path, baseline, var, value):
+    got = _dump(tmp_path, var, **{var: value})
     assert sorted(got.files) == sorted(baseline.files)
     for k in baseline.files:
         assert np.array_equal(baseline[k], got[k], equal_nan=True), (var, k)
