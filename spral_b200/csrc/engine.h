@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <vector>
 #include "spral_ssids_b200.h"
+#include "solve_types.h"
 
 namespace b200 {
 
@@ -26,7 +27,6 @@ extern std::atomic<long> g_launches;   // kernels launched (the gpu_launches fig
 
 constexpr int BS = 32;    // block column width (inner step)
 constexpr int PW = 256;   // outer panel width (a multiple of BS)
-constexpr int RT = 128;   // row tile of the panel kernels
 
 /* Per-front workspace written by the diagonal-block kernel each inner step. */
 struct BlockWS {
@@ -90,8 +90,7 @@ struct FactorParams {
    int action;
 };
 
-/* One tile of work for the panel kernels: front index and row-tile index. */
-struct RowTile { int front; int tile; };
+/* RowTile (front index, row-tile index): solve_types.h */
 /* One tile of work for the DMMA update kernels: absolute tile row / column of the front. */
 struct MatTile { int front; int ti; int tj; };
 
@@ -124,10 +123,7 @@ int inner_tile_size(bool big_tiles);
 void configure_update_kernels();   // per device: opt in to > 48 KB dynamic shared memory
 
 /* ---- solve (solve_kernels.cu) ---- */
-struct SolveFront {    // immutable view of a factorised front for the solves
-   const double* L; const double* D; const int* perm; const int* rows;
-   int ldl, m, n, n0, m0, nelim;
-};
+/* SolveFront: solve_types.h */
 int solve_block();
 void launch_transpose_rhs(double* x, int ldx, double* xt, int n, int nr, bool to_xt, cudaStream_t s);
 int solve_rhs_chunk(int nrhs);
@@ -143,5 +139,12 @@ void launch_diag_solve(const SolveFront* fronts, int first, int count, int nrhs,
 void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
       const int* wbeg, int nsteps, bool posdef, int nr, double* x, int ldx, double* pbuf,
       cudaStream_t s, unsigned int* bar = nullptr);
+
+/* wide sweeps for levels of large fronts (solve_wide.h; opt-in) */
+int solve_wide_block();
+void launch_fwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s);
+void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s);
 
 } // namespace b200

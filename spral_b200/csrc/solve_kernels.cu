@@ -23,6 +23,7 @@
  *   order and solves the transposed diagonal block.
  */
 #include "engine.h"
+#include "solve_wide.h"
 #include <math_constants.h>
 
 namespace b200 {
@@ -412,6 +413,87 @@ void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* wo
    else bwd_level_t<NR, false>(fronts, first, count, work, nwork, wbeg, nsteps, x, ldx, pbuf, bar, s);
 }
 
+
+/* ---- wide sweeps (solve_wide.h) ---------------------------------------- */
+struct SolveDevCtx {
+   __device__ __forceinline__ int tid() const { return threadIdx.x; }
+   __device__ __forceinline__ void sync() { __syncthreads(); }
+   __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+   __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
+};
+
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(SW_TT)
+k_fwd_wide_T(const SolveFront* fronts, int first, int blk, const double* __restrict__ x, double* __restrict__ ywork) {
+   extern __shared__ double smem_dyn[];
+   const SolveFront f = fronts[first + blockIdx.x];
+   SolveDevCtx cx;
+   fwd_wide_T<NR, POSDEF>(cx, f, blk, x, ywork, smem_dyn);
+}
+
+template <int NR>
+__global__ void __launch_bounds__(RT)
+k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork) {
+   extern __shared__ double smem_dyn[];
+   const RowTile w = work[blockIdx.x];
+   const SolveFront f = fronts[w.front];
+   SolveDevCtx cx;
+   fwd_wide_G<NR>(cx, f, w.tile, blk, x, ywork, smem_dyn);
+}
+
+template <int NR>
+__global__ void __launch_bounds__(RT)
+k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int step, const double* __restrict__ x, double* __restrict__ pbuf) {
+   extern __shared__ double smem_dyn[];
+   const RowTile w = work[blockIdx.x];
+   const SolveFront f = fronts[w.front];
+   SolveDevCtx cx;
+   bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)blockIdx.x * SWB * NR, smem_dyn);
+}
+
+template <int NR, bool POSDEF>
+__global__ void __launch_bounds__(SW_TT)
+k_bwd_wide_T(const SolveFront* fronts, int first, const int* __restrict__ wbeg, int step,
+      double* __restrict__ x, const double* __restrict__ pbuf) {
+   extern __shared__ double smem_dyn[];
+   const int fi = first + blockIdx.x;
+   const SolveFront f = fronts[fi];
+   SolveDevCtx cx;
+   bwd_wide_T<NR, POSDEF>(cx, f, step, x, pbuf + (size_t)wbeg[fi] * SWB * NR, smem_dyn);
+}
+
+template <int NR, bool POSDEF>
+void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork, int nblk,
+      double* x, double* ywork, cudaStream_t s) {
+   static bool configured = false;
+   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double), smG = sw_fG_smem_doubles<NR>() * sizeof(double);
+   if (!configured) {
+      cudaFuncSetAttribute(k_fwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+      cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+      configured = true;
+   }
+   for (int b = 0; b < nblk; ++b) {
+      k_fwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, b, x, ywork); COUNT_LAUNCH();
+      k_fwd_wide_G<NR><<<nwork, RT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
+   }
+}
+
+template <int NR, bool POSDEF>
+void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      const int* wbeg, int nblk, double* x, double* pbuf, cudaStream_t s) {
+   static bool configured = false;
+   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double), smG = sw_bG_smem_doubles<NR>() * sizeof(double);
+   if (!configured) {
+      cudaFuncSetAttribute(k_bwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+      cudaFuncSetAttribute(k_bwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+      configured = true;
+   }
+   for (int st = 0; st < nblk; ++st) {
+      k_bwd_wide_G<NR><<<nwork, RT, smG, s>>>(fronts, work, st, x, pbuf); COUNT_LAUNCH();
+      k_bwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, wbeg, st, x, pbuf); COUNT_LAUNCH();
+   }
+}
+
 } // namespace
 
 /* x (column-major, ld = ldx, nr columns) <-> xt (n rows of nr contiguous values) */
@@ -429,6 +511,29 @@ void launch_transpose_rhs(double* x, int ldx, double* xt, int n, int nr, bool to
 }
 
 int solve_block() { return SB; }
+
+/* Wide sweeps of one level (solve_wide.h): nblk = number of 256-column blocks of its largest front. */
+int solve_wide_block() { return SWB; }
+
+#define SW_DISPATCH(NRV, CALL_T, CALL_F) case NRV: if (posdef) { CALL_T; } else { CALL_F; } break
+void launch_fwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s) {
+   if (nwork == 0 || nblk == 0 || count == 0) return;
+#define SW_F(NRV) SW_DISPATCH(NRV, (fwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, nblk, x, ywork, s)), \
+                                   (fwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, nblk, x, ywork, s)))
+   switch (nr) { SW_F(32); SW_F(16); SW_F(8); SW_F(4); SW_F(2); default: SW_F(1); }
+#undef SW_F
+}
+
+void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
+      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s) {
+   if (nwork == 0 || nblk == 0 || count == 0) return;
+#define SW_B(NRV) SW_DISPATCH(NRV, (bwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s)), \
+                                   (bwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s)))
+   switch (nr) { SW_B(32); SW_B(16); SW_B(8); SW_B(4); SW_B(2); default: SW_B(1); }
+#undef SW_B
+}
+#undef SW_DISPATCH
 
 void configure_solve_kernels() {
    cudaFuncSetAttribute(k_bwd_reduce<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduce_smem<32>());

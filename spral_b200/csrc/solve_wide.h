@@ -1,0 +1,309 @@
+/* "Wide" triangular sweeps for the large fronts at the top of the tree (opt-in,
+ * SPRAL_B200_SOLVE_WIDE=1): the column blocks that need a device-wide
+ * synchronisation are SWB = 256 columns wide instead of 32.
+ *
+ * The level kernels of solve_kernels.cu advance all fronts of a level 32 columns
+ * per launch (or per grid barrier); a front with 16 000 eliminated columns needs
+ * 511 such steps per sweep, each bound by the latency of its dependent loads.
+ * Here a block of 256 columns costs two launches:
+ *   forward   T: ONE CTA per front solves the 256 x 256 triangle in 8 sub-steps of
+ *                32 columns that are separated by CTA barriers only; every thread
+ *                owns a row and keeps the next 32-column slab of its row in
+ *                registers (prefetched one sub-step ahead), the rows of the
+ *                sub-block publish the 32 x 32 diagonal block to shared memory;
+ *             G: all (front, row-tile) CTAs subtract L(rows below, block) * y.
+ *   backward  G: partial L(rows below, block)^T x per row tile; T: ONE CTA per
+ *                front sums the partials in a fixed order and solves the
+ *                transposed triangle, sub-blocks last to first, every thread
+ *                owning a column.
+ * Same mathematics and data as the 32-column kernels (NumericSubtree.hxx:286-418
+ * of the reference CPU engine: gather, trsv/trsm + gemv/gemm, scatter); sums are
+ * taken over up to 256 terms before they are applied, so results differ from the
+ * narrow path by rounding only.
+ *
+ * The bodies are written against a context (tid, sync, shfl, atomic_add) and
+ * compiled twice: by nvcc for the kernels in solve_kernels.cu and by g++ for
+ * tests/c/solve_wide_emu.cpp, which runs them on host threads against a plain
+ * gather / substitute / scatter implementation.
+ */
+#pragma once
+#include <cstddef>
+#include "solve_types.h"
+
+#ifdef __CUDACC__
+#define SW_FN __device__ __forceinline__
+#else
+#define SW_FN inline
+#endif
+
+namespace b200 {
+
+constexpr int SWB = 256;     // wide block: columns per T/G pair
+constexpr int SSB = 32;      // sub-block inside T
+constexpr int SW_TT = 256;   // threads of a T kernel CTA (one per row / column of the block)
+constexpr int SW_LK = SSB + 1;
+
+#define SW_XI(g, k) ((size_t)(g) * NR + (k))
+
+SW_FN int sw_min(int a, int b) { return a < b ? a : b; }
+SW_FN int sw_row_index(const SolveFront& f, int i) {
+   return (i < f.n ? f.perm[i] : f.rows[f.n0 + i - f.n]) - 1;
+}
+
+/* shared memory of the T kernels: xs/vs [SWB * NR], lkk [SSB * SW_LK] doubles */
+template <int NR> constexpr size_t sw_T_smem_doubles() { return (size_t)SWB * NR + (size_t)SSB * SW_LK; }
+/* forward G: ys [SWB * NR] doubles */
+template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)SWB * NR; }
+/* backward G: tile [RT * SW_LK] + xr [RT * NR] doubles */
+template <int NR> constexpr size_t sw_bG_smem_doubles() { return (size_t)RT * SW_LK + (size_t)RT * NR; }
+
+/* ---- forward, T: y(block) = L(block, block)^-1 x(block); y -> ywork ---------------- */
+template <int NR, bool POSDEF, class Ctx>
+SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, double* ywork, double* smem) {
+   const int kb = blk * SWB;
+   if (kb >= f.nelim) return;
+   double* xs = smem;
+   double* lkk = smem + (size_t)SWB * NR;
+   const int w = sw_min(SWB, f.nelim - kb);
+   const int t = cx.tid(), lane = t & 31, warp = t >> 5;
+   const size_t ldl = (size_t)f.ldl;
+   const bool arow = t < w;
+   const int g = arow ? f.perm[kb + t] - 1 : -1;
+   #pragma unroll
+   for (int k = 0; k < NR; ++k) xs[(size_t)t * NR + k] = arow ? x[SW_XI(g, k)] : 0.0;
+   const double* Lrow = f.L + (size_t)(kb + t) + (size_t)kb * ldl;     // row kb+t of the block, from column kb
+   double cur[SSB], nxt[SSB];
+   {
+      const int wd0 = sw_min(SSB, w);
+      #pragma unroll
+      for (int j = 0; j < SSB; ++j) cur[j] = (arow && j < wd0) ? Lrow[(size_t)j * ldl] : 0.0;
+   }
+   constexpr int NWARP = SW_TT / 32;
+   constexpr int NRW = (NR + NWARP - 1) / NWARP;
+   for (int jb = 0; jb < w; jb += SSB) {
+      const int wd = sw_min(SSB, w - jb);
+      if (t >= jb && t < jb + SSB) {              // the rows of the sub-block publish its diagonal block
+         const int i = t - jb;
+         #pragma unroll
+         for (int j = 0; j < SSB; ++j) lkk[i * SW_LK + j] = (i < wd && j < wd && i >= j) ? cur[j] : 0.0;
+      }
+      const int jn = jb + SSB;                    // next slab of the rows below this sub-block
+      if (jn < w) {
+         const int wdn = sw_min(SSB, w - jn);
+         #pragma unroll
+         for (int j = 0; j < SSB; ++j) nxt[j] = (arow && t >= jn && j < wdn) ? Lrow[(size_t)(jn + j) * ldl] : 0.0;
+      } else {
+         #pragma unroll
+         for (int j = 0; j < SSB; ++j) nxt[j] = 0.0;
+      }
+      cx.sync();
+      {  /* forward substitution: lanes are the rows of the sub-block, the right-hand sides are dealt to the warps */
+         double v[NRW];
+         #pragma unroll
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? xs[(size_t)(jb + lane) * NR + k] : 0.0; }
+         for (int j = 0; j < wd; ++j) {
+            const double l = (lane > j && lane < wd) ? lkk[lane * SW_LK + j] : 0.0;
+            const double dj = POSDEF ? lkk[j * SW_LK + j] : 1.0;
+            #pragma unroll
+            for (int q = 0; q < NRW; ++q) {
+               double yj = cx.shfl(v[q], j);
+               if (POSDEF) { yj /= dj; if (lane == j) v[q] = yj; }
+               v[q] -= l * yj;
+            }
+         }
+         #pragma unroll
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) xs[(size_t)(jb + lane) * NR + k] = v[q]; }
+      }
+      cx.sync();
+      if (arow && t >= jn) {                      // rows of the block below the sub-block
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) {
+            double s = xs[(size_t)t * NR + k];
+            #pragma unroll
+            for (int j = 0; j < SSB; ++j) s -= cur[j] * xs[(size_t)(jb + j) * NR + k];
+            xs[(size_t)t * NR + k] = s;
+         }
+      }
+      #pragma unroll
+      for (int j = 0; j < SSB; ++j) cur[j] = nxt[j];
+   }
+   cx.sync();
+   if (arow) {
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) ywork[SW_XI(g, k)] = xs[(size_t)t * NR + k];
+   }
+}
+
+/* ---- forward, G: x(rows below the block) -= L(rows, block) * y --------------------- */
+template <int NR, class Ctx>
+SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, double* x, const double* ywork, double* smem) {
+   const int kb = blk * SWB;
+   if (kb >= f.nelim) return;
+   const int w = sw_min(SWB, f.nelim - kb);
+   const int r0 = tile * RT;
+   if (r0 + RT <= kb + w || r0 >= f.m) return;
+   double* ys = smem;
+   for (int e = cx.tid(); e < w; e += RT) {
+      const int g = f.perm[kb + e] - 1;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) ys[(size_t)e * NR + k] = ywork[SW_XI(g, k)];
+   }
+   cx.sync();
+   const int r = r0 + cx.tid();
+   if (r >= kb + w && r < f.m) {
+      double acc[NR];
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+      const double* Lr = f.L + r + (size_t)kb * (size_t)f.ldl;
+      for (int j = 0; j < w; ++j) {
+         const double l = Lr[(size_t)j * (size_t)f.ldl];
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) acc[k] += l * ys[(size_t)j * NR + k];
+      }
+      const int g = sw_row_index(f, r);
+      /* rows < nelim are touched by this thread only, rows >= nelim are shared with sibling fronts */
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) cx.atomic_add(&x[SW_XI(g, k)], -acc[k]);
+   }
+}
+
+/* block handled by front f at backward step s (last block first) */
+SW_FN int sw_bwd_block(const SolveFront& f, int step) {
+   const int nblk = (f.nelim + SWB - 1) / SWB;
+   return nblk - 1 - step;
+}
+
+/* ---- backward, G: out(j, k) = sum over the tile's rows r below the block of L(r, kb+j) x(r, k) ---- */
+template <int NR, class Ctx>
+SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const double* x, double* out, double* smem) {
+   const int b = sw_bwd_block(f, step);
+   if (b < 0) return;
+   const int kb = b * SWB;
+   const int w = sw_min(SWB, f.nelim - kb);
+   const int r0 = tileidx * RT;
+   if (r0 + RT <= kb + w || r0 >= f.m) return;      // no row of this tile below the block
+   double* tile = smem;                             // [RT][SW_LK]; re-used for the cross-warp reduction
+   double* xr = smem + (size_t)RT * SW_LK;          // [RT][NR]
+   const int t = cx.tid(), lane = t & 31, warp = t >> 5;
+   const int r = r0 + t;
+   const bool active = (r >= kb + w) && (r < f.m);
+   const size_t ldl = (size_t)f.ldl;
+   {
+      const int g = active ? sw_row_index(f, r) : 0;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) xr[(size_t)t * NR + k] = active ? x[SW_XI(g, k)] : 0.0;
+   }
+   for (int jb = 0; jb < w; jb += SSB) {
+      const int wd = sw_min(SSB, w - jb);
+      const double* Lr = f.L + r + (size_t)(kb + jb) * ldl;
+      for (int j = 0; j < SSB; ++j) tile[(size_t)t * SW_LK + j] = (active && j < wd) ? Lr[(size_t)j * ldl] : 0.0;
+      cx.sync();
+      double acc[NR];
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+      for (int i = 0; i < 32; ++i) {
+         const double l = tile[(size_t)(warp * 32 + i) * SW_LK + lane];
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) acc[k] += l * xr[(size_t)(warp * 32 + i) * NR + k];
+      }
+      cx.sync();
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) tile[(size_t)t * SW_LK + k] = acc[k];       // NR <= 32 < SW_LK
+      cx.sync();
+      if (t < SSB) {
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) {
+            double s = 0.0;
+            for (int q = 0; q < RT / 32; ++q) s += tile[(size_t)(q * 32 + t) * SW_LK + k];
+            out[(size_t)(jb + t) * NR + k] = s;
+         }
+      }
+      cx.sync();
+   }
+}
+
+/* ---- backward, T: x(block) = L(block, block)^-T (x(block) - sum of the partials) ---- */
+template <int NR, bool POSDEF, class Ctx>
+SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const double* pb, double* smem) {
+   const int b = sw_bwd_block(f, step);
+   if (b < 0) return;
+   double* vs = smem;
+   double* lkk = smem + (size_t)SWB * NR;
+   const int kb = b * SWB;
+   const int w = sw_min(SWB, f.nelim - kb);
+   const int t = cx.tid(), lane = t & 31, warp = t >> 5;
+   const bool acol = t < w;
+   const int g = acol ? f.perm[kb + t] - 1 : -1;
+   const int ntile = (f.m + RT - 1) / RT;
+   const int t0 = (kb + w) / RT;                    // first tile that holds a row below the block
+   #pragma unroll
+   for (int k = 0; k < NR; ++k) {
+      double v = 0.0;
+      if (acol) {
+         v = x[SW_XI(g, k)];
+         for (int tt = t0; tt < ntile; ++tt) v -= pb[(size_t)tt * SWB * NR + (size_t)t * NR + k];
+      }
+      vs[(size_t)t * NR + k] = v;
+   }
+   const size_t ldl = (size_t)f.ldl;
+   const double* Lcol = f.L + (size_t)kb + (size_t)(kb + t) * ldl;     // column kb+t of the block, from row kb
+   const int jbl = ((w - 1) / SSB) * SSB;           // last sub-block: the first one to be solved
+   double cur[SSB], nxt[SSB];
+   #pragma unroll
+   for (int i = 0; i < SSB; ++i) cur[i] = (acol && t < jbl + SSB && jbl + i < w) ? Lcol[jbl + i] : 0.0;
+   constexpr int NWARP = SW_TT / 32;
+   constexpr int NRW = (NR + NWARP - 1) / NWARP;
+   for (int jb = jbl; jb >= 0; jb -= SSB) {
+      const int wd = sw_min(SSB, w - jb);
+      if (t >= jb && t < jb + SSB) {              // the columns of the sub-block publish its diagonal block
+         const int j = t - jb;
+         #pragma unroll
+         for (int i = 0; i < SSB; ++i) lkk[i * SW_LK + j] = (i < wd && j < wd && i >= j) ? cur[i] : 0.0;
+      }
+      const int jp = jb - SSB;                    // rows of the previous sub-block, for the columns up to its end
+      if (jp >= 0) {
+         #pragma unroll
+         for (int i = 0; i < SSB; ++i) nxt[i] = (acol && t < jp + SSB) ? Lcol[jp + i] : 0.0;
+      } else {
+         #pragma unroll
+         for (int i = 0; i < SSB; ++i) nxt[i] = 0.0;
+      }
+      cx.sync();
+      {  /* transposed substitution: lanes are the columns of the sub-block */
+         double v[NRW];
+         #pragma unroll
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? vs[(size_t)(jb + lane) * NR + k] : 0.0; }
+         for (int j = wd - 1; j >= 0; --j) {
+            const double l = (lane < j) ? lkk[j * SW_LK + lane] : 0.0;
+            const double dj = POSDEF ? lkk[j * SW_LK + j] : 1.0;
+            #pragma unroll
+            for (int q = 0; q < NRW; ++q) {
+               double zj = cx.shfl(v[q], j);
+               if (POSDEF) { zj /= dj; if (lane == j) v[q] = zj; }
+               v[q] -= l * zj;
+            }
+         }
+         #pragma unroll
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) vs[(size_t)(jb + lane) * NR + k] = v[q]; }
+      }
+      cx.sync();
+      if (acol && t < jb) {                       // columns of the block left of the sub-block
+         #pragma unroll
+         for (int k = 0; k < NR; ++k) {
+            double s = vs[(size_t)t * NR + k];
+            #pragma unroll
+            for (int i = 0; i < SSB; ++i) s -= cur[i] * vs[(size_t)(jb + i) * NR + k];
+            vs[(size_t)t * NR + k] = s;
+         }
+      }
+      #pragma unroll
+      for (int i = 0; i < SSB; ++i) cur[i] = nxt[i];
+   }
+   cx.sync();
+   if (acol) {
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) x[SW_XI(g, k)] = vs[(size_t)t * NR + k];
+   }
+}
+
+} // namespace b200

@@ -37,6 +37,9 @@ struct CudaError { cudaError_t code; };
 static bool g_profile = false;
 static bool g_solve_graphs = false;  // SPRAL_B200_SOLVE_GRAPHS=1: replay the sweeps as CUDA graphs (no measured gain)
 static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative launch per level (experimental: no measured gain yet)
+static int g_solve_wide = 0;         // SPRAL_B200_SOLVE_WIDE=1 (experimental, unmeasured): 256-column sweeps (solve_wide.h) on
+                                     // levels whose largest front has at least SPRAL_B200_SOLVE_WIDE_MIN (8) 32-column steps
+static int g_solve_wide_min = 8;
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS); < 0: one CTA per tile
 static int g_ctile_block = 0;        // SPRAL_B200_CTILE_BLOCK=12 (experimental, unmeasured): Schur-complement tiles in
@@ -694,6 +697,8 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    if (const char* e = getenv("SPRAL_B200_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_GRAPHS")) g_solve_graphs = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_COOP")) g_solve_coop = atoi(e) != 0;
+   if (const char* e = getenv("SPRAL_B200_SOLVE_WIDE")) g_solve_wide = atoi(e);
+   if (const char* e = getenv("SPRAL_B200_SOLVE_WIDE_MIN")) g_solve_wide_min = std::max(1, atoi(e));
    g_bulk_ctas = g_bulk_prio ? -1 : device_sm_count() - 28;
    if (const char* e = getenv("SPRAL_B200_BULK_CTAS")) g_bulk_ctas = atoi(e);
    auto t_begin = std::chrono::steady_clock::now();
@@ -1115,8 +1120,19 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
       const int maxnr = std::min(nrhs, solve_max_chunk());
       const size_t chunk_bytes = (size_t)S.n * maxnr * sizeof(double);
       if (job == JOB_FWD) S.b_y.ensure(chunk_bytes, s);
-      if (job == JOB_DIAG_BWD || job == JOB_BWD)
-         S.b_pbuf.ensure(std::max<size_t>(N.max_level_work, 1) * solve_block() * solve_max_chunk() * sizeof(double), s);
+      /* levels swept 256 columns at a time (solve_wide.h) */
+      auto wide_level = [&](int lev, int nr) {
+         if (!g_solve_wide || N.lvl_steps[lev] < g_solve_wide_min) return false;
+         size_t nwork = (size_t)(N.swork_ptr[lev + 1] - N.swork_ptr[lev]);
+         return nwork * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
+      };
+      if (job == JOB_DIAG_BWD || job == JOB_BWD) {
+         size_t need = std::max<size_t>(N.max_level_work, 1) * solve_block() * solve_max_chunk() * sizeof(double);
+         for (int lev = 0; lev < S.nlevels; ++lev)
+            if (wide_level(lev, maxnr))
+               need = std::max(need, (size_t)(N.swork_ptr[lev + 1] - N.swork_ptr[lev]) * solve_wide_block() * maxnr * sizeof(double));
+         S.b_pbuf.ensure(need, s);
+      }
       double* ywork = (double*)S.b_y.p;
       double* pbuf = (double*)S.b_pbuf.p;
       S.b_bar.ensure(256, s);
@@ -1132,9 +1148,16 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          launch_transpose_rhs(xcol, ldx, xs, S.n, nr, true, s);
          auto sweep = [&]() {
             if (job == JOB_FWD) {
-               for (int lev = 0; lev < S.nlevels; ++lev)
-                  launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev],
-                        N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.lvl_steps[lev], posdef, nr, xs, ldx, ywork, s, bar);
+               for (int lev = 0; lev < S.nlevels; ++lev) {
+                  const int nwork = N.swork_ptr[lev + 1] - N.swork_ptr[lev];
+                  if (wide_level(lev, nr)) {
+                     int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
+                     launch_fwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev], nwork,
+                           (N.lvl_steps[lev] + 7) / 8, posdef, nr, xs, ywork, s);
+                  } else
+                     launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev], nwork, N.lvl_steps[lev], posdef, nr,
+                           xs, ldx, ywork, s, bar);
+               }
                launch_fwd_flush(N.d_sfronts, 0, S.nloc, nr, xs, ldx, ywork, s);
             } else if (job == JOB_DIAG) {
                if (!posdef) launch_diag_solve(N.d_sfronts, 0, S.nloc, nr, xs, ldx, s);
@@ -1142,6 +1165,11 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                for (int lev = S.nlevels - 1; lev >= 0; --lev) {
                   int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
                   if (job == JOB_DIAG_BWD && !posdef) launch_diag_solve(N.d_sfronts, f0, f1 - f0, nr, xs, ldx, s);
+                  if (wide_level(lev, nr))
+                     launch_bwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
+                           N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, (N.lvl_steps[lev] + 7) / 8, posdef, nr,
+                           xs, pbuf, s);
+                  else
                   launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                         N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
                         xs, ldx, pbuf, s, bar);

@@ -10,6 +10,10 @@ D^-1, inform and the solution bit for bit:
   SPRAL_B200_BULK_PRIO=1   look-ahead bulk update one tile per CTA on a low-priority
                            stream instead of a capped persistent grid
   SPRAL_B200_CTILE_BLOCK=4 Schur-complement tiles in blocked order (L2 reuse)
+and one that changes the order of the sums of the solves (same factors; solutions
+agree to rounding):
+  SPRAL_B200_SOLVE_WIDE=1  256-column sweeps on the levels of large fronts (solve_wide.h;
+                           bodies checked on the CPU by tests/test_kernel_emulation.py)
 """
 import os
 import subprocess
@@ -28,7 +32,8 @@ pytestmark = [pytest.mark.gpu,
 def _dump(tmp_path, tag, **env):
     out = str(tmp_path / f"{tag}.npz")
     e = dict(os.environ)
-    for k in ("SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO", "SPRAL_B200_CTILE_BLOCK"):
+    for k in ("SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO", "SPRAL_B200_CTILE_BLOCK", "SPRAL_B200_SOLVE_WIDE",
+              "SPRAL_B200_SOLVE_WIDE_MIN"):
         e.pop(k, None)
     e.update(env)
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_factor.py"), out], env=e, timeout=900)
@@ -47,3 +52,14 @@ def test_variant_reproduces_default_engine_bit_for_bit(tmp_path, baseline, var, 
     assert sorted(got.files) == sorted(baseline.files)
     for k in baseline.files:
         assert np.array_equal(baseline[k], got[k], equal_nan=True), (var, k)
+
+
+@pytest.mark.parametrize("wide_min", ["2", "8"])
+def test_wide_solve_agrees_with_narrow_sweeps(tmp_path, baseline, wide_min):
+    got = _dump(tmp_path, "wide" + wide_min, SPRAL_B200_SOLVE_WIDE="1", SPRAL_B200_SOLVE_WIDE_MIN=wide_min)
+    for k in baseline.files:
+        if k.endswith("/x") or k.endswith("/x5"):
+            scale = np.abs(baseline[k]).max()
+            assert np.abs(baseline[k] - got[k]).max() <= 1e-9 * scale, k
+        else:                                            # the factorisation is untouched
+            assert np.array_equal(baseline[k], got[k], equal_nan=True), k

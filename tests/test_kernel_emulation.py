@@ -30,3 +30,16 @@ def test_diag_block_v2_body_matches_k_diag_model_bit_for_bit():
     if have_ref:
         n_ref = int(r.stdout.split("worst reconstruction error")[1].split(",")[1].split()[0])
         assert n_ref > 0, r.stdout
+
+
+def test_wide_solve_bodies_match_plain_sweeps():
+    """spral_b200/csrc/solve_wide.h (256-column forward / backward sweeps, T and G kernels)
+    on host threads against gather / substitute / scatter over one front."""
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "solve_wide_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "solve_wide_emu.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "solve_wide_emu: 0 failures" in r.stdout

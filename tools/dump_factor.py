@@ -29,6 +29,9 @@ def main(out):
         piv, d = fk.numeric[0].enquire()
         A = M.to_scipy(n, ptr, row, val)
         x = sb.solve(fk, A @ np.ones(n))
+        rng = np.random.default_rng(11)
+        X5 = sb.solve(fk, np.asfortranarray(A @ rng.uniform(-1, 1, (n, 5))))      # chunks of 4 + 1 right-hand sides
+        res[name + "/x5"] = X5
         g = fk.inform
         res[name + "/d"] = d
         if piv is not None:
