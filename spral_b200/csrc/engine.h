@@ -23,6 +23,7 @@
 
 namespace b200 {
 
+struct SegWS;
 extern std::atomic<long> g_launches;   // kernels launched (the gpu_launches figure of bench.py)
 
 constexpr int BS = 32;    // block column width (inner step)
@@ -69,6 +70,12 @@ struct Front {
    int nelim;
    int num_neg, num_two, num_zero;
    int flag;         // 0, -5 singular (action=false), -6 not positive definite
+   /* speculative segments of the panel (panel_v2.h; null / 0 unless SPRAL_B200_PANEL_V2) */
+   SegWS* sws;       // chain workspace of this front
+   int seg_valid;    // a segment of CW columns starting at `done` is in flight
+   int seg_ok;       // ... its diagonal block was factorised by the chain kernel
+   int seg_fail;     // ... a row below failed the a-posteriori test: the tiles roll back
+   int spec_off;     // the rest of this panel is done step by step
 };
 
 /* A child contribution to be extend-added into a parent front (either a child
@@ -109,11 +116,19 @@ void launch_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s
 void launch_swap(Front* fronts, const RowTile* work, int nwork, bool outer, cudaStream_t s);
 void launch_finalize(Front* fronts, const int* flist, int count, bool posdef, cudaStream_t s);
 void launch_snapshot(Front* fronts, const int* flist, int count, int* snap, cudaStream_t s);
+/* speculative panel segments (panel_v2.h) */
+int panel_segment_width();
+size_t panel_segment_ws_bytes();
+void configure_panel_kernels();
+void launch_panel_chain(Front* fronts, const int* flist, int count, bool new_panel, const FactorParams& prm, cudaStream_t s);
+void launch_panel_tiles(Front* fronts, const RowTile* work, int nwork, const FactorParams& prm, cudaStream_t s);
+void launch_seg_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s);
 int assemble_cols_per_cta();
 int scatter_chunk();
 
 /* ---- DMMA update kernels (gemm_dmma.cu) ---- */
-enum UpdateMode { UPD_INNER = 0, UPD_OUTER = 1, UPD_CONTRIB = 2, UPD_EXPLICIT = 3 };
+enum UpdateMode { UPD_INNER = 0, UPD_OUTER = 1, UPD_CONTRIB = 2, UPD_EXPLICIT = 3,
+                  UPD_SEG = 4 };   // UPD_SEG: the panel's columns right of an accepted speculative segment, K = the segment
 void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mode,
       bool big_tiles, cudaStream_t s, int max_ctas = 0,      // max_ctas: cap on the persistent grid (0 = all SMs, < 0 = one CTA per tile)
       const int4* xregs = nullptr);                         // UPD_EXPLICIT (large tiles only): {front, k0, k1, c_lo} per region

@@ -34,6 +34,7 @@
 #include "engine.h"
 #include "device_utils.cuh"
 #include "diag_block.h"
+#include "panel_v2.h"
 
 namespace b200 {
 #ifndef COUNT_LAUNCH
@@ -194,8 +195,18 @@ void launch_delays(Front* fronts, const AsmSrc* srcs, const int2* work, int nwor
 
 /* Accounts the last inner step and opens / closes panels and passes.
  * Executed by ONE thread per front (first thing in k_diag and k_finalize). */
+/* Accounts a speculative segment (panel_v2.h): accepted -> CW more columns are done;
+ * given up or rolled back -> the rest of the panel is done step by step. */
+__device__ void account_segment(Front* f) {
+   if (!f->seg_valid) return;
+   if (f->seg_ok && !f->seg_fail) f->done += CW;
+   else f->spec_off = 1;
+   f->seg_valid = 0;
+}
+
 __device__ void advance_state(Front* f, bool new_panel) {
    if (f->finished) return;
+   account_segment(f);
    if (f->step_valid) {
       int ne = calc_ne(f);
       f->done += ne;
@@ -218,6 +229,7 @@ __device__ void advance_state(Front* f, bool new_panel) {
          f->pend0 = min(f->done + PW, f->end);
          f->pend = f->pend0;
          f->panel_open = 1;
+         f->spec_off = 0;
       }
    }
    if (f->finished) f->nelim = f->done;
@@ -550,6 +562,124 @@ void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool n
 }
 
 /* ------------------------------------------------------------------------ */
+/* Speculative panel segments (panel_v2.h)                                   */
+/* ------------------------------------------------------------------------ */
+
+/* One CTA per front: opens the panel / accounts the previous segment, then factorises
+ * the CW x CW diagonal block at `done` in shared memory.  Nothing of the front is
+ * modified; the factors go to f->sws. */
+__global__ void __launch_bounds__(CNT)
+k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
+   extern __shared__ __align__(16) unsigned char pv_smem[];
+   ChainShared& sh = *reinterpret_cast<ChainShared*>(pv_smem);
+   Front* f = &fronts[flist[blockIdx.x]];
+   __shared__ int s_go;
+   if (threadIdx.x == 0) {
+      advance_state(f, new_panel != 0);
+      int go = !f->finished && f->panel_open && !f->spec_off && f->sws != nullptr && !f->step_valid
+               && (f->pend - f->done >= CW);
+      if (go) { f->seg_valid = 1; f->seg_ok = 0; f->seg_fail = 0; }
+      s_go = go;
+   }
+   __syncthreads();
+   if (!s_go) return;
+   const int p = f->done;
+   const size_t ldl = (size_t)f->ldl;
+   DiagDevCtx cx;
+   const int ok = chain_segment(cx, sh, f->L + p + (size_t)p * ldl, ldl, prm.u, prm.small, CUDART_INF, f->sws);
+   if (threadIdx.x == 0) { f->sws->ok = ok; f->seg_ok = ok; }
+}
+
+/* One CTA per (front, 128-row tile): the rows below the segment. */
+__global__ void __launch_bounds__(RT)
+k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
+   extern __shared__ __align__(16) unsigned char pv_smem[];
+   TileShared& sh = *reinterpret_cast<TileShared*>(pv_smem);
+   const RowTile w = work[blockIdx.x];
+   Front* f = &fronts[w.front];
+   if (!f->seg_valid || !f->seg_ok) return;
+   const int p = f->done, m = f->m;
+   const int r0 = w.tile * RT;
+   if (r0 + RT <= p + CW || r0 >= m) return;
+   const size_t ldl = (size_t)f->ldl;
+   DiagDevCtx cx;
+   panel_tile(cx, sh, f->L + (size_t)p * ldl, f->LD + (size_t)p * ldl, f->BK, ldl, m, r0, p, prm.u, CUDART_INF,
+              f->sws, &f->seg_fail);
+}
+
+/* Accept (diagonal block, D, perm, row permutation of the earlier columns) or roll back. */
+__global__ void __launch_bounds__(RT)
+k_seg_commit(Front* fronts, const RowTile* work) {
+   const RowTile w = work[blockIdx.x];
+   Front* f = &fronts[w.front];
+   if (!f->seg_valid || !f->seg_ok) return;
+   const int p = f->done, m = f->m;
+   const size_t ldl = (size_t)f->ldl;
+   const int r0 = w.tile * RT;
+   double* L = f->L;
+   const SegWS* ws = f->sws;
+   if (f->seg_fail) {
+      const int r = r0 + threadIdx.x;
+      if (r >= p + CW && r < m) {
+         const double* BKr = f->BK + r;
+         double* Lr = L + r + (size_t)p * ldl;
+         for (int c = 0; c < CW; ++c) Lr[(size_t)c * ldl] = BKr[(size_t)c * ldl];
+      }
+      return;
+   }
+   __shared__ int s_lperm[CW];
+   __shared__ int s_perm[CW];
+   for (int i = threadIdx.x; i < CW; i += RT) s_lperm[i] = ws->lperm[i];
+   __syncthreads();
+   /* (1) rows of the segment in the already-factored columns c < p */
+   if (r0 < p) {
+      const int c = r0 + threadIdx.x;
+      if (c < p) {
+         double* col = L + (size_t)c * ldl + p;
+         for (int jb = 0; jb < CW; jb += BS) {
+            double v[BS];
+            #pragma unroll
+            for (int i = 0; i < BS; ++i) v[i] = col[jb + s_lperm[jb + i]];
+            #pragma unroll
+            for (int i = 0; i < BS; ++i) col[jb + i] = v[i];
+         }
+      }
+   }
+   /* (2) the diagonal block, D and perm: one CTA per front */
+   if (w.tile == p / RT) {
+      for (int e = threadIdx.x; e < CW * CW; e += RT) {
+         const int i = e % CW, c = e / CW;
+         if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
+      }
+      for (int e = threadIdx.x; e < 2 * CW; e += RT) f->D[2 * p + e] = ws->dinv[e];
+      for (int i = threadIdx.x; i < CW; i += RT) s_perm[i] = f->perm[p + (i / BS) * BS + s_lperm[i]];
+      __syncthreads();
+      for (int i = threadIdx.x; i < CW; i += RT) f->perm[p + i] = s_perm[i];
+   }
+}
+
+int panel_segment_width() { return CW; }
+size_t panel_segment_ws_bytes() { return sizeof(SegWS); }
+
+void configure_panel_kernels() {
+   cudaFuncSetAttribute(k_panel_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
+   cudaFuncSetAttribute(k_panel_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+}
+
+void launch_panel_chain(Front* fronts, const int* flist, int count, bool new_panel, const FactorParams& prm, cudaStream_t s) {
+   if (count == 0) return;
+   k_panel_chain<<<count, CNT, sizeof(ChainShared), s>>>(fronts, flist, new_panel ? 1 : 0, prm); COUNT_LAUNCH();
+}
+void launch_panel_tiles(Front* fronts, const RowTile* work, int nwork, const FactorParams& prm, cudaStream_t s) {
+   if (nwork == 0) return;
+   k_panel_tiles<<<nwork, RT, sizeof(TileShared), s>>>(fronts, work, prm); COUNT_LAUNCH();
+}
+void launch_seg_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s) {
+   if (nwork == 0) return;
+   k_seg_commit<<<nwork, RT, 0, s>>>(fronts, work); COUNT_LAUNCH();
+}
+
+/* ------------------------------------------------------------------------ */
 /* Apply the block pivots to the rows below                                  */
 /* ------------------------------------------------------------------------ */
 
@@ -840,6 +970,7 @@ __global__ void k_snapshot(Front* fronts, const int* __restrict__ flist, int cou
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= count) return;
    Front* f = &fronts[flist[i]];
+   if (!f->finished) account_segment(f);
    if (!f->finished && f->step_valid) {
       int ne = calc_ne(f);
       f->done += ne;

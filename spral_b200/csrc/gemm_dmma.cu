@@ -113,6 +113,12 @@ __device__ __forceinline__ Region make_region(const Front* f, int mode, int T) {
       if (g.k1 <= g.k0) return g;
       g.c_lo = f->pend0; g.c_hi = f->n;
       g.C = f->L; g.ldc = g.lda; g.accumulate = true;
+   } else if (mode == UPD_SEG) {
+      if (!f->seg_valid || !f->seg_ok || f->seg_fail) return g;
+      const int cw = 128;                       // panel_v2.h: CW
+      g.k0 = f->done; g.k1 = f->done + cw;
+      g.c_lo = f->done + cw; g.c_hi = f->pend0;
+      g.C = f->L; g.ldc = g.lda; g.accumulate = true;
    } else {
       if (f->m == f->n || !f->C) return g;
       g.k0 = 0; g.k1 = f->nelim;

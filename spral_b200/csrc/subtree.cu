@@ -42,6 +42,9 @@ static int g_solve_wide = 0;         // SPRAL_B200_SOLVE_WIDE=1 (experimental, u
 static int g_solve_wide_min = 8;
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS); < 0: one CTA per tile
+static bool g_panel_v2 = false;      // SPRAL_B200_PANEL_V2=1 (experimental, unmeasured): speculative 128-column panel segments
+                                     // (panel_v2.h) on levels of at most g_panel_v2_fronts large fronts
+static int g_panel_v2_fronts = 32;
 static int g_ctile_block = 0;        // SPRAL_B200_CTILE_BLOCK=12 (experimental, unmeasured): Schur-complement tiles in
                                      // SB x SB blocked order for L2 reuse of the operand panels (0 = column by column)
 static bool g_bulk_prio = false;     // SPRAL_B200_BULK_PRIO=1 (experimental, unmeasured): instead of a static SM split,
@@ -198,6 +201,7 @@ struct Symbolic {
    Buf b_bar;                         // arrival counter of the cooperative solve kernels
    Buf b_export;                      // packed contribution block handed to another process (IPC)
    Buf b_bulk[2];                     // tile lists of the look-ahead bulk updates (alternating panels)
+   Buf b_segws;                       // chain workspaces of the speculative panel segments (panel_v2.h)
 
    ~Symbolic() {
       cudaSetDevice(device);
@@ -206,6 +210,7 @@ struct Symbolic {
       b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
       b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
       b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export.release(); b_bar.release(); b_bulk[0].release(); b_bulk[1].release();
+      b_segws.release();
    }
 };
 
@@ -545,22 +550,49 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          while (lo < hi) { int mid = (lo + hi) / 2; if (cand[mid] > thr) lo = mid + 1; else hi = mid; }
          return lo;
       };
-      for (int st = 0; st < nsteps; ++st) {
-         int na = count_gt(st * BS);
+      auto take_snapshot = [&]() {
+         launch_snapshot(d_fronts, d_flist, na_all, d_snap, s);
+         snap_host.resize((size_t)na_all * 8);
+         CUDA_TRY(cudaMemcpyAsync(snap_host.data(), d_snap, snap_host.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+         auto ts0 = std::chrono::steady_clock::now();
+         CUDA_TRY(cudaStreamSynchronize(s));
+         t_sync += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
+         if (g_prof) g_prof->collect();
+      };
+      /* Speculative path (panel_v2.h): the panel in PW / CW segments of three launches each (chain, tiles,
+       * commit) plus one DMMA update of the panel's remaining columns between segments.  A segment that meets
+       * a failed or zero pivot changes nothing; the step-by-step loop below then finishes the panel. */
+      bool steps_new_panel = true;
+      int steps_todo = nsteps;
+      const bool v2 = F[fronts[0]].sws != nullptr;
+      if (v2) {
+         const int nseg = PW / panel_segment_width();
+         for (int seg = 0; seg < nseg; ++seg) {
+            PROF(PC_DIAG, launch_panel_chain(d_fronts, d_flist, na_all, seg == 0, prm, s));
+            PROF(PC_APPLY, launch_panel_tiles(d_fronts, d_rows, rows_prefix[na_all], prm, s));
+            PROF(PC_COMMIT, launch_seg_commit(d_fronts, d_rows, rows_prefix[na_all], s));
+            if (seg + 1 < nseg) PROF(PC_INNER, launch_update(d_fronts, d_inner, inner_prefix[na_all], UPD_SEG, false, s));
+         }
+         take_snapshot();
+         int maxrem = 0;
+         for (int k = 0; k < na_all; ++k) {
+            const int* sn = &snap_host[(size_t)k * 8];          // p0, done, pend, pend0, end, finished, flag
+            if (sn[6] < 0 || sn[5]) continue;
+            maxrem = std::max(maxrem, sn[2] - sn[1]);
+         }
+         steps_new_panel = false;                                // the chain kernel opened the panel
+         steps_todo = (maxrem + BS - 1) / BS;
+      }
+      for (int st = 0; st < steps_todo; ++st) {
+         int na = v2 ? na_all : count_gt(st * BS);
          if (na == 0) break;
-         PROF(PC_DIAG, launch_diag(d_fronts, d_flist, na, posdef, st == 0, prm, s));
+         PROF(PC_DIAG, launch_diag(d_fronts, d_flist, na, posdef, st == 0 && steps_new_panel, prm, s));
          PROF(PC_APPLY, launch_apply(d_fronts, d_rows, rows_prefix[na], posdef, prm, s));
          if (!posdef) PROF(PC_COMMIT, launch_commit(d_fronts, d_rows, rows_prefix[na], s));
          PROF(PC_INNER, launch_update(d_fronts, d_inner, inner_prefix[na], UPD_INNER, big, s));
          if (!posdef) PROF(PC_SWAP, launch_swap(d_fronts, d_rows, rows_prefix[na], false, s));
       }
-      launch_snapshot(d_fronts, d_flist, na_all, d_snap, s);
-      snap_host.resize((size_t)na_all * 8);
-      CUDA_TRY(cudaMemcpyAsync(snap_host.data(), d_snap, snap_host.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
-      auto ts0 = std::chrono::steady_clock::now();
-      CUDA_TRY(cudaStreamSynchronize(s));
-      t_sync += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
-      if (g_prof) g_prof->collect();
+      if (!v2 || steps_todo > 0) take_snapshot();
 
       /* what happened in the panel; exact outer-update and swap work.  Look-ahead:
        * when no front failed a pivot in this panel, only the tile columns that hold
@@ -680,6 +712,9 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    CUDA_TRY(cudaSetDevice(S.device));
    if (const char* e = getenv("SPRAL_B200_BULK_PRIO")) g_bulk_prio = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_CTILE_BLOCK")) g_ctile_block = atoi(e);
+   if (const char* e = getenv("SPRAL_B200_PANEL_V2")) g_panel_v2 = atoi(e) != 0;
+   if (const char* e = getenv("SPRAL_B200_PANEL_V2_FRONTS")) g_panel_v2_fronts = std::max(1, atoi(e));
+   if (g_panel_v2) configure_panel_kernels();
    if (g_bulk_prio) {
       int least = 0, greatest = 0;
       CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -843,6 +878,14 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          bkd += (size_t)f.ldl * BS + 32;
       }
       const bool big = maxm >= 192;
+      /* speculative panel segments: a few large fronts per level only (the chain workspace is 260 KB per front) */
+      const bool v2 = g_panel_v2 && big && !posdef && nfl <= g_panel_v2_fronts;
+      const int bkw = v2 ? panel_segment_width() : BS;        // columns of the backup scratch
+      if (v2) {
+         bkd = 0;
+         for (int fi = f0; fi < f1; ++fi) bkd += (size_t)F[fi].ldl * bkw + 32;
+         S.b_segws.ensure((size_t)nfl * panel_segment_ws_bytes(), s);
+      }
       char* lblock = (char*)N.falloc(lbytes);
       if (!posdef) {
          S.b_ld.ensure(std::max(ldd, S.ld_estimate) * sizeof(double), s);
@@ -861,9 +904,10 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
             f.perm = (int*)(lblock + off); off += align_up((size_t)f.n * sizeof(int), 256);
             if (!posdef) {
                f.LD = (double*)S.b_ld.p + ldo; ldo += align_up((size_t)f.ldl * f.n, 32);
-               f.BK = (double*)S.b_bk.p + bko; bko += align_up((size_t)f.ldl * BS, 32);
+               f.BK = (double*)S.b_bk.p + bko; bko += align_up((size_t)f.ldl * bkw, 32);
             } else { f.LD = f.L; f.BK = nullptr; }
             f.ws = (BlockWS*)S.b_ws.p + (fi - f0);
+            f.sws = v2 ? (SegWS*)((char*)S.b_segws.p + (size_t)(fi - f0) * panel_segment_ws_bytes()) : nullptr;
             f.rows = S.d_rlist + S.rptr[node];
             int cm = f.m0 - f.n0;
             f.ldc = (int)align_up((size_t)cm, 2);

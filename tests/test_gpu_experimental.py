@@ -10,6 +10,9 @@ D^-1, inform and the solution bit for bit:
   SPRAL_B200_BULK_PRIO=1   look-ahead bulk update one tile per CTA on a low-priority
                            stream instead of a capped persistent grid
   SPRAL_B200_CTILE_BLOCK=4 Schur-complement tiles in blocked order (L2 reuse)
+one that factorises the panels speculatively in 128-column segments (panel_v2.h; other
+but equally valid pivots where entries tie, sums in another order):
+  SPRAL_B200_PANEL_V2=1    inertia, rank and flops identical; delays close; solutions to rounding
 and one that changes the order of the sums of the solves (same factors; solutions
 agree to rounding):
   SPRAL_B200_SOLVE_WIDE=1  256-column sweeps on the levels of large fronts (solve_wide.h;
@@ -33,7 +36,7 @@ def _dump(tmp_path, tag, **env):
     out = str(tmp_path / f"{tag}.npz")
     e = dict(os.environ)
     for k in ("SPRAL_B200_DIAG_V2", "SPRAL_B200_BULK_PRIO", "SPRAL_B200_CTILE_BLOCK", "SPRAL_B200_SOLVE_WIDE",
-              "SPRAL_B200_SOLVE_WIDE_MIN"):
+              "SPRAL_B200_SOLVE_WIDE_MIN", "SPRAL_B200_PANEL_V2"):
         e.pop(k, None)
     e.update(env)
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_factor.py"), out], env=e, timeout=900)
@@ -63,3 +66,17 @@ def test_wide_solve_agrees_with_narrow_sweeps(tmp_path, baseline, wide_min):
             assert np.abs(baseline[k] - got[k]).max() <= 1e-9 * scale, k
         else:                                            # the factorisation is untouched
             assert np.array_equal(baseline[k], got[k], equal_nan=True), k
+
+
+def test_speculative_panel_segments_agree_with_step_by_step_path(tmp_path, baseline):
+    got = _dump(tmp_path, "panel_v2", SPRAL_B200_PANEL_V2="1")
+    for k in baseline.files:
+        if k.endswith("/inform"):
+            b, g = baseline[k], got[k]      # flag, num_delay, num_neg, num_two, matrix_rank, num_factor, num_flops
+            assert g[0] == b[0] and g[2] == b[2] and g[4] == b[4], (k, b, g)
+            assert abs(int(g[1]) - int(b[1])) <= 8 + 0.25 * int(b[1]), (k, b, g)
+            if b[1] == 0 and g[1] == 0:
+                assert g[5] == b[5] and g[6] == b[6], (k, b, g)
+        elif k.endswith("/x") or k.endswith("/x5"):
+            scale = np.abs(baseline[k]).max()
+            assert np.abs(baseline[k] - got[k]).max() <= 1e-7 * scale, k

@@ -43,3 +43,16 @@ def test_wide_solve_bodies_match_plain_sweeps():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "solve_wide_emu: 0 failures" in r.stdout
+
+
+def test_speculative_panel_bodies_factorise_a_segment():
+    """spral_b200/csrc/panel_v2.h (chain_segment, panel_tile) on host threads: P A P^T = L D L^T on
+    the 128 x 128 diagonal block, A21 P^T = (W D) L11^T below it, |l| <= 1/u, backups, give-up paths."""
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "panel_v2_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "panel_v2_emu.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "panel_v2_emu: 0 failures" in r.stdout
