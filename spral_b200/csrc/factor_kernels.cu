@@ -616,46 +616,9 @@ k_seg_commit(Front* fronts, const RowTile* work) {
    const int p = f->done, m = f->m;
    const size_t ldl = (size_t)f->ldl;
    const int r0 = w.tile * RT;
-   double* L = f->L;
-   const SegWS* ws = f->sws;
-   if (f->seg_fail) {
-      const int r = r0 + threadIdx.x;
-      if (r >= p + CW && r < m) {
-         const double* BKr = f->BK + r;
-         double* Lr = L + r + (size_t)p * ldl;
-         for (int c = 0; c < CW; ++c) Lr[(size_t)c * ldl] = BKr[(size_t)c * ldl];
-      }
-      return;
-   }
-   __shared__ int s_lperm[CW];
-   __shared__ int s_perm[CW];
-   for (int i = threadIdx.x; i < CW; i += RT) s_lperm[i] = ws->lperm[i];
-   __syncthreads();
-   /* (1) rows of the segment in the already-factored columns c < p */
-   if (r0 < p) {
-      const int c = r0 + threadIdx.x;
-      if (c < p) {
-         double* col = L + (size_t)c * ldl + p;
-         for (int jb = 0; jb < CW; jb += BS) {
-            double v[BS];
-            #pragma unroll
-            for (int i = 0; i < BS; ++i) v[i] = col[jb + s_lperm[jb + i]];
-            #pragma unroll
-            for (int i = 0; i < BS; ++i) col[jb + i] = v[i];
-         }
-      }
-   }
-   /* (2) the diagonal block, D and perm: one CTA per front */
-   if (w.tile == p / RT) {
-      for (int e = threadIdx.x; e < CW * CW; e += RT) {
-         const int i = e % CW, c = e / CW;
-         if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
-      }
-      for (int e = threadIdx.x; e < 2 * CW; e += RT) f->D[2 * p + e] = ws->dinv[e];
-      for (int i = threadIdx.x; i < CW; i += RT) s_perm[i] = f->perm[p + (i / BS) * BS + s_lperm[i]];
-      __syncthreads();
-      for (int i = threadIdx.x; i < CW; i += RT) f->perm[p + i] = s_perm[i];
-   }
+   __shared__ CommitShared sh;
+   DiagDevCtx cx;
+   seg_commit(cx, sh, f->L, f->D, f->perm, f->BK, ldl, m, p, r0, w.tile == p / RT, f->seg_fail, f->sws);
 }
 
 int panel_segment_width() { return CW; }

@@ -248,4 +248,51 @@ PV_FN void panel_tile(Ctx& cx, TileShared& sh, double* Lp, double* LDp, double* 
    }
 }
 
+struct CommitShared { int lperm[CW]; int perm[CW]; };
+
+/* Commit of a segment by the CTA of row tile r0 (RT threads): on failure the rows below
+ * the segment are restored from the backup; on success (1) the rows of the segment in the
+ * already-factored columns c < p are permuted block by block, (2) the CTA whose tile holds
+ * row p (diag_cta) writes the diagonal block, D^-1 and the pivot order. */
+template <class Ctx>
+PV_FN void seg_commit(Ctx& cx, CommitShared& sh, double* L, double* D, int* perm, const double* BK, size_t ldl,
+      int m, int p, int r0, bool diag_cta, int seg_fail, const SegWS* ws) {
+   constexpr int BS = DB_BS;
+   const int t = cx.tid();
+   if (seg_fail) {
+      const int r = r0 + t;
+      if (r >= p + CW && r < m) {
+         const double* BKr = BK + r;
+         double* Lr = L + r + (size_t)p * ldl;
+         for (int c = 0; c < CW; ++c) Lr[(size_t)c * ldl] = BKr[(size_t)c * ldl];
+      }
+      return;
+   }
+   for (int i = t; i < CW; i += RT) sh.lperm[i] = ws->lperm[i];
+   cx.sync();
+   if (r0 < p) {
+      const int c = r0 + t;
+      if (c < p) {
+         double* col = L + (size_t)c * ldl + p;
+         for (int jb = 0; jb < CW; jb += BS) {
+            double v[BS];
+            #pragma unroll
+            for (int i = 0; i < BS; ++i) v[i] = col[jb + sh.lperm[jb + i]];
+            #pragma unroll
+            for (int i = 0; i < BS; ++i) col[jb + i] = v[i];
+         }
+      }
+   }
+   if (diag_cta) {
+      for (int e = t; e < CW * CW; e += RT) {
+         const int i = e % CW, c = e / CW;
+         if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
+      }
+      for (int e = t; e < 2 * CW; e += RT) D[2 * p + e] = ws->dinv[e];
+      for (int i = t; i < CW; i += RT) sh.perm[i] = perm[p + (i / BS) * BS + sh.lperm[i]];
+      cx.sync();
+      for (int i = t; i < CW; i += RT) perm[p + i] = sh.perm[i];
+   }
+}
+
 } // namespace b200

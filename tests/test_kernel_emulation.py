@@ -56,3 +56,17 @@ def test_speculative_panel_bodies_factorise_a_segment():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "panel_v2_emu: 0 failures" in r.stdout
+
+
+def test_speculative_panel_whole_front_flow():
+    """chain / tiles / commit in the order factor_fronts issues them over a 384-column dense front
+    (three segments, two panels), the DMMA updates replaced by plain loops over the same regions:
+    P A P^T = L D L^T with P from the front's perm array; roll-back leaves the front unchanged."""
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "panel_v2_front_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "panel_v2_front_emu.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "panel_v2_front_emu: 0 failures" in r.stdout
