@@ -1,0 +1,112 @@
+"""A/B of the opt-in kernel variants on one GPU: for every variant a fresh process
+(the library reads its SPRAL_B200_* switches once) factorises the stencil problem a few
+times and reports the best device time, the class times of a profiled run, inertia /
+delays and the solve times.  One table at the end.
+
+  python tools/ab_variants.py [grid=100] [reps=3] [variant ...]
+  variants: base diag_v2 panel_v2 panel_v2+diag... any '+'-joined combination of
+            diag_v2 panel_v2 bulk_prio ctile12 solve_wide
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENV = {
+    "base": {},
+    "diag_v2": {"SPRAL_B200_DIAG_V2": "1"},
+    "panel_v2": {"SPRAL_B200_PANEL_V2": "1"},
+    "bulk_prio": {"SPRAL_B200_BULK_PRIO": "1"},
+    "ctile12": {"SPRAL_B200_CTILE_BLOCK": "12"},
+    "solve_wide": {"SPRAL_B200_SOLVE_WIDE": "1"},
+}
+DEFAULT = ["base", "diag_v2", "bulk_prio", "ctile12", "panel_v2", "panel_v2+bulk_prio", "panel_v2+bulk_prio+ctile12",
+           "solve_wide"]
+
+
+def child(grid, reps):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import torch
+    import spral_b200 as sb
+    from spral_b200 import matrices as M, _lib
+    import oracle_ref
+    n, ptr, row, val = M.stencil_3d_27pt(grid, shift=13.0)
+    ak = sb.analyse(n, ptr, row)
+    dval = torch.from_numpy(val).cuda()
+    best, fk = 1e30, None
+    for _ in range(reps + 1):
+        if fk is not None:
+            for ns in fk.numeric:
+                ns.close()
+        fk = sb.factor(ak, False, dval.data_ptr())
+        best = min(best, float(fk.numeric[0].timings()[1]))
+    g = fk.inform
+    A = M.to_scipy(n, ptr, row, val)
+    b = A @ np.ones(n)
+    X = torch.from_numpy(np.ascontiguousarray(b)).cuda()
+    ns = fk.numeric[0]
+    # the solve entry points take pivot-order vectors; a backward-error check goes through sb.solve
+    x = sb.solve(fk, b)
+    be = float(oracle_ref.backward_error(A, x, b))
+    ts = {}
+    for nrhs in (1, 32):
+        xx = torch.ones(n * nrhs, dtype=torch.float64, device="cuda")
+        for rep in range(2):
+            torch.cuda.synchronize(); t = time.perf_counter()
+            ns.solve_fwd(xx.data_ptr(), nrhs, n)
+            ns.solve_diag_bwd(xx.data_ptr(), nrhs, n)
+            torch.cuda.synchronize(); ts[nrhs] = 1e3 * (time.perf_counter() - t)
+    lib = _lib.load()
+    lib.spral_ssids_b200_set_profile(1)
+    for q in fk.numeric:
+        q.close()
+    fk = sb.factor(ak, False, dval.data_ptr())
+    lib.spral_ssids_b200_set_profile(0)
+    tm = fk.numeric[0].timings()
+    names = ["diag", "apply", "commit", "inner", "swap", "outer", "contrib", "assemble", "init"]
+    out = {"ms": best, "tflops": g["num_flops"] / best / 1e9, "launches": int(tm[6]),
+           "num_neg": int(g["num_neg"]), "num_delay": int(g["num_delay"]), "num_two": int(g["num_two"]),
+           "rank": int(g["matrix_rank"]), "bwd": be, "solve1_ms": ts[1], "solve32_ms": ts[32],
+           "class_ms": {k: round(float(v), 2) for k, v in zip(names, tm[8:17])},
+           "contrib_tflops": float(tm[3]) / (float(tm[2]) * 1e-3) / 1e12 if tm[2] > 0 else 0.0}
+    print("AB_RESULT " + json.dumps(out), flush=True)
+
+
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--child":
+        return child(int(sys.argv[2]), int(sys.argv[3]))
+    grid = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    variants = sys.argv[3:] or DEFAULT
+    rows = []
+    for v in variants:
+        env = dict(os.environ)
+        for part in v.split("+"):
+            env.update(ENV[part])
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(grid), str(reps)], env=env,
+                               capture_output=True, text=True, timeout=1500)
+            line = [l for l in r.stdout.splitlines() if l.startswith("AB_RESULT ")]
+            res = json.loads(line[-1][10:]) if line else {"error": (r.stderr or r.stdout)[-400:]}
+        except subprocess.TimeoutExpired:
+            res = {"error": "timeout"}
+        rows.append((v, res))
+        print(v, json.dumps(res), flush=True)
+    print("\n| variant | factor ms | TFLOP/s | launches | num_neg | delays | bwd err | solve 1 / 32 RHS ms | chain ms (diag+apply+commit+inner+swap) | outer | contrib TF/s |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for v, r in rows:
+        if "error" in r:
+            print(f"| {v} | ERROR: {r['error'][:120]!r} |")
+            continue
+        c = r["class_ms"]
+        chain = c["diag"] + c["apply"] + c["commit"] + c["inner"] + c["swap"]
+        print(f"| {v} | {r['ms']:.1f} | {r['tflops']:.2f} | {r['launches']} | {r['num_neg']} | {r['num_delay']} | {r['bwd']:.1e} | "
+              f"{r['solve1_ms']:.1f} / {r['solve32_ms']:.1f} | {chain:.1f} | {c['outer']:.1f} | {r['contrib_tflops']:.1f} |")
+
+
+if __name__ == "__main__":
+    main()
