@@ -268,6 +268,25 @@ struct spral_ssids_b200_analysis_view {
 void spral_ssids_b200_analysis_get(const struct spral_ssids_b200_analysis*,
       struct spral_ssids_b200_analysis_view* view);
 
+/* ------------------------------------------------------------------------ */
+/* Layer 2b: scaling pre-processing on the host (options%scaling of          */
+/* ssids_factor, src/ssids/ssids.f90:861-1028); scaling.cpp                  */
+/* ------------------------------------------------------------------------ */
+
+/* hungarian_scale_sym (src/scaling.f90:134-170, hungarian_wrapper :597-801): MC64-type
+ * matching-based scaling of the symmetric matrix given by its lower triangle (1-based
+ * CSC).  scaling[n]; match[n] (may be NULL): 1-based column matched to row i, negative
+ * for the variables outside the matching of a structurally singular matrix.  Returns
+ * inform%flag: 0, 1 (WARNING_SINGULAR, only with scale_if_singular != 0), -2
+ * (ERROR_SINGULAR: scaling = 1).  *matched = size of the matching. */
+int spral_ssids_b200_hungarian_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,
+      double* scaling, int* match, int scale_if_singular, int* matched);
+
+/* equilib_scale_sym (src/scaling.f90:381-416, inf_norm_equilib_sym :480-521);
+ * equilib_options defaults: max_iterations = 10, tol = 1e-8.  Returns 0. */
+int spral_ssids_b200_equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,
+      double* scaling, int max_iterations, double tol, int* iterations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,8 @@ SYMBOLS = {
         (_vp, [_i, _vp, _vp, _vp, _i, _i, C.c_int64, C.c_float, C.c_float, _ip]),
     "spral_ssids_b200_analysis_free": (None, [_vp]),
     "spral_ssids_b200_analysis_get": (None, [_vp, C.POINTER(AnalysisView)]),
+    "spral_ssids_b200_hungarian_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
+    "spral_ssids_b200_equilib_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _i, _d, _ip]),
 }
 
 _lib = None

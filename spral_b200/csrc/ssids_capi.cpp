@@ -21,7 +21,7 @@
 
 namespace {
 
-enum { OK = 0, E_CALL_SEQUENCE = -1, E_A_N_OOR = -2, E_A_PTR = -3, E_A_ALL_OOR = -4, E_ORDER = -8,
+enum { OK = 0, E_CALL_SEQUENCE = -1, E_A_N_OOR = -2, E_A_PTR = -3, E_A_ALL_OOR = -4, E_SINGULAR = -5, E_ORDER = -8,
        E_X_SIZE = -10, E_JOB_OOR = -11, E_NOT_LLT = -13, E_NOT_LDLT = -14, E_ALLOCATION = -50,
        E_UNIMPLEMENTED = -98,
        W_IDX_OOR = 1, W_DUP_IDX = 2, W_DUP_AND_OOR = 3, W_MISSING_DIAGONAL = 4, W_MISS_DIAG_OORDUP = 5,
@@ -226,7 +226,9 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
    if (!A) { inform->flag = E_CALL_SEQUENCE; return; }
    *inform = A->inform;
    if (A->inform.flag < 0) { inform->flag = E_CALL_SEQUENCE; return; }
-   if (options->scaling != 0) { inform->flag = E_UNIMPLEMENTED; return; }
+   /* options%scaling (ssids.f90:899-1028): <= 0 user vector, 1 Hungarian (MC64), 4.. equilibration;
+    * 2 (auction) and 3 (from a matching-based ordering at analyse time) are not provided */
+   if (options->scaling == 2 || options->scaling == 3) { inform->flag = E_UNIMPLEMENTED; return; }
    if (*fkeep) { delete static_cast<Fkeep*>(*fkeep); *fkeep = nullptr; }
    Fkeep* F = new (std::nothrow) Fkeep;
    if (!F) { inform->flag = E_ALLOCATION; return; }
@@ -243,9 +245,24 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
          for (int64_t q = A->map_ptr[k]; q < A->map_ptr[k + 1]; ++q) cleaned[k] += val[A->map[q]];
       aval = cleaned.data();
    }
-   if (scale) {                        /* user scaling: fkeep%scaling(i) = scale(invp(i)) (ssids.f90:921-926) */
+   if (options->scaling <= 0) {
+      if (scale) {                     /* user scaling: fkeep%scaling(i) = scale(invp(i)) (ssids.f90:921-926) */
+         F->scaling.resize(n);
+         for (int i = 0; i < n; ++i) F->scaling[i] = scale[A->v.invp[i] - 1];
+      }
+   } else {
+      std::vector<double> sc(n);
+      if (options->scaling == 1) {     /* hungarian_scale_sym, scale_if_singular = options%action (:927-959) */
+         int matched = 0;
+         int hf = spral_ssids_b200_hungarian_scale_sym(n, A->ptr.data(), A->row.data(), aval, sc.data(), nullptr,
+                                                       options->action ? 1 : 0, &matched);
+         if (hf == -2) { inform->flag = E_SINGULAR; return; }
+      } else {                         /* equilib_scale_sym with default equilib_options (:998-1028) */
+         spral_ssids_b200_equilib_scale_sym(n, A->ptr.data(), A->row.data(), aval, sc.data(), 10, 1e-8, nullptr);
+      }
       F->scaling.resize(n);
-      for (int i = 0; i < n; ++i) F->scaling[i] = scale[A->v.invp[i] - 1];
+      for (int i = 0; i < n; ++i) F->scaling[i] = sc[A->v.invp[i] - 1];
+      if (scale) for (int i = 0; i < n; ++i) scale[i] = sc[i];
    }
    spral_ssids_b200_options eo = engine_options(options);
    const int np = A->v.nparts;

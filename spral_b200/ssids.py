@@ -236,6 +236,23 @@ def free_contrib(c):
         c._free_hook(c)
 
 
+def compute_scaling(analysis, val, method, options=None):
+    """options%scaling of ssids_factor (src/ssids/ssids.f90:899-1028): "hungarian" (= 1, MC64-type
+    matching, scale_if_singular = options%action) or "equilib" (= 4, infinity-norm equilibration).
+    Returns the scaling vector in the user's variable order."""
+    from . import scaling as S
+    a = analysis
+    if method in ("hungarian", "mc64", 1):
+        action = True if options is None else bool(options.action)
+        s, _, flag, _ = S.hungarian_scale_sym(a.n, a.ptr, a.row, val, scale_if_singular=action)
+        if flag == S.ERROR_SINGULAR:
+            raise ValueError("matrix is structurally singular and options.action is false (SSIDS_ERROR_SINGULAR)")
+        return s
+    if method in ("equilib", "mc77", 4):
+        return S.equilib_scale_sym(a.n, a.ptr, a.row, val)[0]
+    raise ValueError(f"unknown scaling {method!r}")
+
+
 class Fkeep:
     def __init__(self, akeep, posdef, numeric, inform, scaling):
         self.akeep, self.posdef, self.numeric, self.inform, self.scaling = akeep, posdef, numeric, inform, scaling
@@ -246,6 +263,8 @@ def factor(akeep, posdef, val, options=None, scaling=None, device_contrib=True):
     every part in order, handing contribution blocks child part -> parent part."""
     a = akeep.analysis
     sc = None
+    if isinstance(scaling, str):
+        scaling = compute_scaling(a, val, scaling, options)
     if scaling is not None:   # fkeep%scaling(i) = scale(invp(i))  (ssids.f90:921-926)
         sc = np.ascontiguousarray(np.asarray(scaling, dtype=np.float64)[a.invp - 1])
     nparts = a.nparts

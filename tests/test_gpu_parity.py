@@ -485,3 +485,17 @@ def test_random_problems_like_reference_test_random():
             p.close()
         for ns in fk.numeric:
             ns.close()
+
+
+@pytest.mark.parametrize("method", ["hungarian", "equilib"])
+def test_computed_scalings_cfg4_like(method):
+    """BASELINE config 4 in small: KKT saddle-point matrix with ~30 % zero-diagonal rows, scaled by
+    the host pre-processing of options%scaling = 1 / 4 (spral_b200/scaling.py; src/ssids/ssids.f90:
+    927-1028); both engines get the same scaling vector."""
+    from spral_b200 import ssids as host
+    n, ptr, row, val = M.kkt_saddle(4000, 0.3)
+    a = Analysis(n, ptr, row)
+    s = host.compute_scaling(a, val, method)
+    a.close()
+    assert s.shape == (n,) and np.all(s > 0) and np.all(np.isfinite(s))
+    _check(lambda: (n, ptr, row, val), False, 2, scaling=s)
