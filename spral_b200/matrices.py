@@ -81,6 +81,124 @@ class SpralRandom:
         return int(self.state * n // self.M) + 1
 
 
+    def integer_in_range(self, lo, hi):
+        """random_integer_in_range (src/random_matrix.f90:302-309)."""
+        return lo + self.integer(hi - lo + 1) - 1
+
+    def sym_wt_integer(self, n):
+        """random_sym_wt_integer (src/random_matrix.f90:281-297): column index weighted by the
+        number of entries of the column in the lower triangle."""
+        r1, r2 = self.integer(n), self.integer(n)
+        while r2 < r1:
+            r1, r2 = self.integer(n), self.integer(n)
+        return r1
+
+    def perm(self, n):
+        """random_perm (src/random_matrix.f90:314-335), 1-based values."""
+        p = list(range(1, n + 1))
+        for i in range(1, n):
+            j = self.integer_in_range(i, n)
+            p[i - 1], p[j - 1] = p[j - 1], p[i - 1]
+        return p
+
+
+MATRIX_REAL_RECT, MATRIX_REAL_UNSYM, MATRIX_REAL_SYM_PSDEF, MATRIX_REAL_SYM_INDEF = 1, 2, 3, 4
+
+
+def random_matrix_generate(state, matrix_type, m, n, nnz, nonsingular=False, sort=False):
+    """Restatement of random_matrix_generate (src/random_matrix.f90:84-279) on a SpralRandom
+    state: random m x n CSC pattern with nnz entries (lower triangle for the symmetric types),
+    optionally structurally non-singular and with sorted columns, values uniform in [-1, 1].
+    Returns (ptr, row, val) with 1-based ptr / row as the reference does.  Pure Python: meant
+    for the small problems of the reference's own tests (tests/ssids/ssids.f90: n <= 1000)."""
+    sym = matrix_type in (MATRIX_REAL_SYM_PSDEF, MATRIX_REAL_SYM_INDEF)
+    if sym and m != n:
+        raise ValueError("symmetric matrix must be square")
+    if m < 1 or n < 1 or nnz < 1 or (sym and n * (n + 1) // 2 < nnz) or (not sym and m * n < nnz):
+        raise ValueError("arguments out of range")
+    if nonsingular and nnz < min(m, n):
+        raise ValueError("not enough entries for a non-singular matrix")
+    cnt = [0] * (n + 1)                                   # 1-based
+    rperm = cperm = None
+    if sym:
+        if nonsingular:
+            rperm = list(range(1, m + 1))
+            cperm = list(range(1, n + 1))
+            for j in range(1, n + 1):
+                cnt[j] += 1
+        for _ in range(nnz - (min(m, n) if nonsingular else 0)):
+            j = state.sym_wt_integer(n)
+            while cnt[j] >= m - j + 1:
+                j = state.sym_wt_integer(n)
+            cnt[j] += 1
+    else:
+        if nonsingular:
+            rperm, cperm = state.perm(m), state.perm(n)
+            for j in range(1, n + 1):
+                if cperm[j - 1] <= min(m, n):
+                    cnt[j] = 1
+        for _ in range(nnz - (min(m, n) if nonsingular else 0)):
+            j = state.integer(n)
+            while cnt[j] >= m:
+                j = state.integer(n)
+            cnt[j] += 1
+    ptr = [1] * (n + 2)
+    row = [0] * (nnz + 1)
+    rused = [False] * (m + 1)
+    for i in range(1, n + 1):
+        ptr[i + 1] = ptr[i] + cnt[i]
+        jj = ptr[i]
+        if nonsingular and cperm[i - 1] <= min(m, n):
+            k = rperm[cperm[i - 1] - 1]
+            row[jj] = k
+            rused[k] = True
+            jj += 1
+        minidx = i if sym else 1
+        for q in range(jj, ptr[i + 1]):
+            k = state.integer_in_range(minidx, m)
+            while rused[k]:
+                k = state.integer_in_range(minidx, m)
+            row[q] = k
+            rused[k] = True
+        for q in range(ptr[i], ptr[i + 1]):
+            rused[row[q]] = False
+    if sort:                                              # dbl_tr_sort: increasing row order per column
+        for i in range(1, n + 1):
+            row[ptr[i]:ptr[i + 1]] = sorted(row[ptr[i]:ptr[i + 1]])
+    val = [state.real() for _ in range(ptr[n + 1] - 1)]
+    return (np.asarray(ptr[1:n + 2], dtype=np.int64), np.asarray(row[1:], dtype=np.int32),
+            np.asarray(val, dtype=np.float64))
+
+
+def gen_random_posdef(state, n, nza):
+    """gen_random_posdef (tests/ssids/ssids.f90:2872-2897): sorted non-singular random pattern made
+    diagonally dominant (the first entry of a sorted column is its diagonal)."""
+    ptr, row, val = random_matrix_generate(state, MATRIX_REAL_SYM_PSDEF, n, n, nza, nonsingular=True, sort=True)
+    for k in range(1, n + 1):
+        tempv = 0.0
+        for j in range(ptr[k - 1] + 1, ptr[k]):           # 1-based positions ptr(k)+1 .. ptr(k+1)-1
+            tempv += abs(val[j - 1])
+            i = ptr[row[j - 1] - 1]
+            val[i - 1] += abs(val[j - 1])
+        i = ptr[k - 1]
+        val[i - 1] = 1.0 + val[i - 1] + tempv
+    return n, ptr, row, val
+
+
+def gen_random_indef(state, n, nza):
+    """gen_random_indef (tests/ssids/ssids.f90:2829-2868) without the zero-row option: some
+    explicit zeros on the diagonal and a large last off-diagonal entry in every column."""
+    ptr, row, val = random_matrix_generate(state, MATRIX_REAL_SYM_INDEF, n, n, nza, nonsingular=True, sort=True)
+    if n > 3:
+        step = max(1, state.integer(n // 2))
+        for k in range(1, n + 1, step):
+            if ptr[k] > ptr[k - 1] + 1:
+                val[ptr[k - 1] - 1] = 0.0
+        for k in range(1, n + 1):
+            val[ptr[k] - 2] *= 1000.0
+    return n, ptr, row, val
+
+
 def kkt_saddle(n, frac_constraints=0.3, nnz_per_row=6, seed=486502):
     """cfg4: synthetic KKT saddle-point matrix [H B^T; B 0] of order n with
     m = frac*n zero-diagonal constraint rows.  H is a sparse diagonally dominant

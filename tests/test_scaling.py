@@ -92,3 +92,52 @@ def test_equilibration_converges_to_unit_inf_norms():
     assert it <= 50 and np.abs(rmax - 1).max() < 1e-3
     s10, it10 = S.equilib_scale_sym(n, ptr, row, val)          # the reference's defaults: 10 sweeps
     assert it10 <= 10 and np.all(s10 > 0)
+
+
+def test_spral_random_lcg_known_answers():
+    """The reference's generator is the ANSI C / glibc TYPE_0 LCG x <- (1103515245 x + 12345) mod 2^31
+    (src/random.f90:19-22); its sequence from seed 1 is the published one."""
+    r = M.SpralRandom(1)
+    seq = []
+    for _ in range(5):
+        r.integer(10)
+        seq.append(r.state)
+    assert seq == [1103527590, 377401575, 662824084, 1147902781, 2035015474]
+    r = M.SpralRandom()                       # default seed 486502
+    x1 = (1103515245 * 486502 + 12345) % 2 ** 31
+    assert r.real() == 1.0 - 2.0 * x1 / 2.0 ** 31
+    assert 1 <= M.SpralRandom(7).integer(13) <= 13
+
+
+@pytest.mark.parametrize("mtype,m,n,nnz", [(M.MATRIX_REAL_SYM_INDEF, 50, 50, 220), (M.MATRIX_REAL_SYM_PSDEF, 9, 9, 45),
+                                           (M.MATRIX_REAL_UNSYM, 30, 30, 100), (M.MATRIX_REAL_RECT, 12, 40, 90)])
+def test_random_matrix_generate_invariants(mtype, m, n, nnz):
+    """What tests/random_matrix.f90 checks of the reference's generator: entry count, row range,
+    no duplicates, sorted columns, the diagonal of a symmetric non-singular pattern."""
+    st = M.SpralRandom()
+    ptr, row, val = M.random_matrix_generate(st, mtype, m, n, nnz, nonsingular=True, sort=True)
+    sym = mtype in (M.MATRIX_REAL_SYM_INDEF, M.MATRIX_REAL_SYM_PSDEF)
+    assert ptr[0] == 1 and ptr[n] - 1 == nnz == len(row) == len(val)
+    assert np.all(np.abs(val) <= 1.0)
+    for j in range(n):
+        col = row[ptr[j] - 1:ptr[j + 1] - 1]
+        assert list(col) == sorted(set(col)) and (len(col) == 0 or (col[0] >= (j + 1 if sym else 1) and col[-1] <= m))
+        if sym:
+            assert col[0] == j + 1                        # forced diagonal comes first after sorting
+    if not sym:                                           # structurally non-singular: a full matching exists
+        A = sp.csc_matrix((np.ones(nnz), row - 1, ptr - 1), shape=(m, n))
+        from scipy.sparse.csgraph import maximum_bipartite_matching
+        assert (maximum_bipartite_matching(A.tocsr(), perm_type="column") >= 0).sum() == min(m, n)
+    # same state -> same matrix
+    ptr2, row2, val2 = M.random_matrix_generate(M.SpralRandom(), mtype, m, n, nnz, nonsingular=True, sort=True)
+    assert np.array_equal(ptr, ptr2) and np.array_equal(row, row2) and np.array_equal(val, val2)
+
+
+def test_reference_test_generators():
+    st = M.SpralRandom()
+    n, ptr, row, val = M.gen_random_posdef(st, 40, 160)
+    A = M.to_scipy(n, ptr, row, val).toarray()
+    assert np.all(np.linalg.eigvalsh(A) > 0)              # diagonally dominant
+    n, ptr, row, val = M.gen_random_indef(st, 40, 160)
+    A = M.to_scipy(n, ptr, row, val).toarray()
+    assert (np.diag(A) == 0).any() and np.abs(A).max() > 10.0
