@@ -80,6 +80,7 @@ PV_FN int chain_segment(Ctx& cx, ChainShared& sh, const double* Lseg, size_t ldl
    constexpr int BS = DB_BS;
    const int t = cx.tid();
    double* S = sh.S;
+   #pragma unroll 8
    for (int c = 0; c < CW; ++c) S[(size_t)c * CLD + t] = (t >= c) ? Lseg[t + (size_t)c * ldl] : 0.0;
    if (t == 0) sh.fail = 0;
    cx.sync();
@@ -184,7 +185,8 @@ PV_FN void panel_tile(Ctx& cx, TileShared& sh, double* Lp, double* LDp, double* 
    const int t = cx.tid();
    const int r = r0 + t;
    const bool active = (r >= p + CW) && (r < m);
-   for (int c = 0; c < CW; ++c) {
+   #pragma unroll 16
+   for (int c = 0; c < CW; ++c) {       /* independent loads: many in flight per thread */
       const double v = active ? Lp[r + (size_t)c * ldl] : 0.0;
       sh.T[(size_t)c * CLD + t] = v;
       if (active) BK[r + (size_t)c * ldl] = v;
@@ -243,6 +245,7 @@ PV_FN void panel_tile(Ctx& cx, TileShared& sh, double* Lp, double* LDp, double* 
       cx.sync();
    }
    if (active) {
+      #pragma unroll 16
       for (int c = 0; c < CW; ++c) Lp[r + (size_t)c * ldl] = sh.T[(size_t)c * CLD + t];
       if (bad) *fail = 1;
    }
@@ -264,6 +267,7 @@ PV_FN void seg_commit(Ctx& cx, CommitShared& sh, double* L, double* D, int* perm
       if (r >= p + CW && r < m) {
          const double* BKr = BK + r;
          double* Lr = L + r + (size_t)p * ldl;
+         #pragma unroll 16
          for (int c = 0; c < CW; ++c) Lr[(size_t)c * ldl] = BKr[(size_t)c * ldl];
       }
       return;
