@@ -120,9 +120,10 @@ void launch_snapshot(Front* fronts, const int* flist, int count, int* snap, cuda
 int panel_segment_width();
 size_t panel_segment_ws_bytes();
 void configure_panel_kernels();
-void launch_panel_chain(Front* fronts, const int* flist, int count, bool new_panel, const FactorParams& prm, cudaStream_t s);
-void launch_panel_tiles(Front* fronts, const RowTile* work, int nwork, const FactorParams& prm, cudaStream_t s);
-void launch_seg_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s);
+void launch_panel_chain(Front* fronts, const int* flist, int count, bool posdef, bool new_panel, const FactorParams& prm,
+      cudaStream_t s);
+void launch_panel_tiles(Front* fronts, const RowTile* work, int nwork, bool posdef, const FactorParams& prm, cudaStream_t s);
+void launch_seg_commit(Front* fronts, const RowTile* work, int nwork, bool posdef, cudaStream_t s);
 int assemble_cols_per_cta();
 int scatter_chunk();
 

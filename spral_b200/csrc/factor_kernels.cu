@@ -568,6 +568,7 @@ void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool n
 /* One CTA per front: opens the panel / accounts the previous segment, then factorises
  * the CW x CW diagonal block at `done` in shared memory.  Nothing of the front is
  * modified; the factors go to f->sws. */
+template <bool POSDEF>
 __global__ void __launch_bounds__(CNT)
 k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
    extern __shared__ __align__(16) unsigned char pv_smem[];
@@ -586,11 +587,12 @@ k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, Facto
    const int p = f->done;
    const size_t ldl = (size_t)f->ldl;
    DiagDevCtx cx;
-   const int ok = chain_segment(cx, sh, f->L + p + (size_t)p * ldl, ldl, prm.u, prm.small, CUDART_INF, f->sws);
+   const int ok = chain_segment<POSDEF>(cx, sh, f->L + p + (size_t)p * ldl, ldl, prm.u, prm.small, CUDART_INF, f->sws);
    if (threadIdx.x == 0) { f->sws->ok = ok; f->seg_ok = ok; }
 }
 
 /* One CTA per (front, 128-row tile): the rows below the segment. */
+template <bool POSDEF>
 __global__ void __launch_bounds__(RT)
 k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
    extern __shared__ __align__(16) unsigned char pv_smem[];
@@ -603,11 +605,12 @@ k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
    if (r0 + RT <= p + CW || r0 >= m) return;
    const size_t ldl = (size_t)f->ldl;
    DiagDevCtx cx;
-   panel_tile(cx, sh, f->L + (size_t)p * ldl, f->LD + (size_t)p * ldl, f->BK, ldl, m, r0, p, prm.u, CUDART_INF,
-              f->sws, &f->seg_fail);
+   panel_tile<POSDEF>(cx, sh, f->L + (size_t)p * ldl, f->LD + (size_t)p * ldl, f->BK, ldl, m, r0, p, prm.u, CUDART_INF,
+                      f->sws, &f->seg_fail);
 }
 
 /* Accept (diagonal block, D, perm, row permutation of the earlier columns) or roll back. */
+template <bool POSDEF>
 __global__ void __launch_bounds__(RT)
 k_seg_commit(Front* fronts, const RowTile* work) {
    const RowTile w = work[blockIdx.x];
@@ -618,28 +621,37 @@ k_seg_commit(Front* fronts, const RowTile* work) {
    const int r0 = w.tile * RT;
    __shared__ CommitShared sh;
    DiagDevCtx cx;
-   seg_commit(cx, sh, f->L, f->D, f->perm, f->BK, ldl, m, p, r0, w.tile == p / RT, f->seg_fail, f->sws);
+   seg_commit<POSDEF>(cx, sh, f->L, f->D, f->perm, f->BK, ldl, m, p, r0, w.tile == p / RT, f->seg_fail, f->sws);
 }
 
 int panel_segment_width() { return CW; }
 size_t panel_segment_ws_bytes() { return sizeof(SegWS); }
 
 void configure_panel_kernels() {
-   cudaFuncSetAttribute(k_panel_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
-   cudaFuncSetAttribute(k_panel_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+   cudaFuncSetAttribute(k_panel_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
+   cudaFuncSetAttribute(k_panel_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
+   cudaFuncSetAttribute(k_panel_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+   cudaFuncSetAttribute(k_panel_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
 }
 
-void launch_panel_chain(Front* fronts, const int* flist, int count, bool new_panel, const FactorParams& prm, cudaStream_t s) {
+void launch_panel_chain(Front* fronts, const int* flist, int count, bool posdef, bool new_panel, const FactorParams& prm,
+      cudaStream_t s) {
    if (count == 0) return;
-   k_panel_chain<<<count, CNT, sizeof(ChainShared), s>>>(fronts, flist, new_panel ? 1 : 0, prm); COUNT_LAUNCH();
+   if (posdef) k_panel_chain<true><<<count, CNT, sizeof(ChainShared), s>>>(fronts, flist, new_panel ? 1 : 0, prm);
+   else k_panel_chain<false><<<count, CNT, sizeof(ChainShared), s>>>(fronts, flist, new_panel ? 1 : 0, prm);
+   COUNT_LAUNCH();
 }
-void launch_panel_tiles(Front* fronts, const RowTile* work, int nwork, const FactorParams& prm, cudaStream_t s) {
+void launch_panel_tiles(Front* fronts, const RowTile* work, int nwork, bool posdef, const FactorParams& prm, cudaStream_t s) {
    if (nwork == 0) return;
-   k_panel_tiles<<<nwork, RT, sizeof(TileShared), s>>>(fronts, work, prm); COUNT_LAUNCH();
+   if (posdef) k_panel_tiles<true><<<nwork, RT, sizeof(TileShared), s>>>(fronts, work, prm);
+   else k_panel_tiles<false><<<nwork, RT, sizeof(TileShared), s>>>(fronts, work, prm);
+   COUNT_LAUNCH();
 }
-void launch_seg_commit(Front* fronts, const RowTile* work, int nwork, cudaStream_t s) {
+void launch_seg_commit(Front* fronts, const RowTile* work, int nwork, bool posdef, cudaStream_t s) {
    if (nwork == 0) return;
-   k_seg_commit<<<nwork, RT, 0, s>>>(fronts, work); COUNT_LAUNCH();
+   if (posdef) k_seg_commit<true><<<nwork, RT, 0, s>>>(fronts, work);
+   else k_seg_commit<false><<<nwork, RT, 0, s>>>(fronts, work);
+   COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */

@@ -74,7 +74,7 @@ PV_FN void pv_dinv_coeffs(const double* d, int j, double inf, double& v0, double
 
 /* Chain: factorises the CW x CW diagonal block whose lower triangle is at Lseg (ld = ldl).
  * CNT threads.  Returns 1 (every thread) when `out` holds the factors, 0 when it gave up. */
-template <class Ctx>
+template <bool POSDEF, class Ctx>
 PV_FN int chain_segment(Ctx& cx, ChainShared& sh, const double* Lseg, size_t ldl, double u, double small,
       double inf, SegWS* out) {
    constexpr int BS = DB_BS;
@@ -87,14 +87,15 @@ PV_FN int chain_segment(Ctx& cx, ChainShared& sh, const double* Lseg, size_t ldl
    const double lim = 1.0 / u;
    for (int jb = 0; jb < CW; jb += BS) {
       int cur = 0, zfrom = BS;
-      const int rc = diag_block_factor<4, false>(cx, sh.dg, S + (size_t)jb * CLD + jb, (size_t)CLD, BS, small, 1, inf,
-                                                 (double*)nullptr, cur, zfrom);
-      if (rc != DB_OK || zfrom < BS) return 0;
+      const int rc = diag_block_factor<4, POSDEF>(cx, sh.dg, S + (size_t)jb * CLD + jb, (size_t)CLD, BS, small, 1, inf,
+                                                  (double*)nullptr, cur, zfrom);
+      if (rc != DB_OK || zfrom < BS) return 0;     // not positive definite / zero pivots: the step-by-step path reports it
       if (t < BS) {
-         double v0, v1, v2;
-         pv_dinv_coeffs(sh.dg.dinv, t, inf, v0, v1, v2);
+         double v0, v1 = 0.0, v2 = 0.0;
+         if (POSDEF) v0 = sh.dg.dinv[t];            // 1 / l_tt (cholesky_factor, cholesky.cxx:33-187)
+         else pv_dinv_coeffs(sh.dg.dinv, t, inf, v0, v1, v2);
          sh.c0[t] = v0; sh.c1[t] = v1; sh.c2[t] = v2;
-         sh.lperm[t] = sh.dg.lperm[t];
+         sh.lperm[t] = POSDEF ? t : sh.dg.lperm[t];
       }
       cx.sync();
       double wv[BS];
@@ -106,26 +107,37 @@ PV_FN int chain_segment(Ctx& cx, ChainShared& sh, const double* Lseg, size_t ldl
          double y[BS];
          #pragma unroll
          for (int j = 0; j < BS; ++j) y[j] = S[(size_t)(jb + sh.lperm[j]) * CLD + t];
-         #pragma unroll
-         for (int j = 0; j < BS; ++j) {
-            double s = y[j];
-            #pragma unroll
-            for (int k = 0; k < j; ++k) s -= y[k] * sh.dg.A[cur][j][k];
-            y[j] = s;
-         }
          int bad = 0;
-         #pragma unroll
-         for (int j = 0; j < BS; ++j) {
-            double w = sh.c0[j] * y[j];
-            if (j + 1 < BS) w += sh.c1[j] * y[(j + 1) % BS];
-            if (j > 0) w += sh.c2[j] * y[(j + BS - 1) % BS];
-            wv[j] = w;
-            if (!(fabs(w) <= lim)) bad = 1;
+         if (POSDEF) {                                    /* l_tj = (a_tj - sum_k l_tk l_jk) / l_jj */
+            #pragma unroll
+            for (int j = 0; j < BS; ++j) {
+               double s = y[j];
+               #pragma unroll
+               for (int k = 0; k < j; ++k) s -= y[k] * sh.dg.A[cur][j][k];
+               y[j] = s * sh.c0[j];
+               wv[j] = y[j];
+            }
+         } else {
+            #pragma unroll
+            for (int j = 0; j < BS; ++j) {
+               double s = y[j];
+               #pragma unroll
+               for (int k = 0; k < j; ++k) s -= y[k] * sh.dg.A[cur][j][k];
+               y[j] = s;
+            }
+            #pragma unroll
+            for (int j = 0; j < BS; ++j) {
+               double w = sh.c0[j] * y[j];
+               if (j + 1 < BS) w += sh.c1[j] * y[(j + 1) % BS];
+               if (j > 0) w += sh.c2[j] * y[(j + BS - 1) % BS];
+               wv[j] = w;
+               if (!(fabs(w) <= lim)) bad = 1;
+            }
          }
          #pragma unroll
          for (int j = 0; j < BS; ++j) {
             S[(size_t)(jb + j) * CLD + t] = wv[j];       // L(t, jb + j)
-            S[(size_t)t * CLD + jb + j] = y[j];          // (L D)(t, jb + j), mirrored
+            S[(size_t)t * CLD + jb + j] = y[j];          // (L D)(t, jb + j), mirrored (== L for Cholesky)
          }
          if (bad) sh.fail = 1;
       } else if (t >= jb) {
@@ -134,10 +146,10 @@ PV_FN int chain_segment(Ctx& cx, ChainShared& sh, const double* Lseg, size_t ldl
          for (int c = 0; c < BS; ++c) {
             if (c < i) {
                S[(size_t)(jb + c) * CLD + t] = sh.dg.A[cur][i][c];
-               S[(size_t)t * CLD + jb + c] = sh.dg.LDm[cur][i][c];
-            } else if (c == i) S[(size_t)(jb + c) * CLD + t] = 1.0;
+               S[(size_t)t * CLD + jb + c] = POSDEF ? sh.dg.A[cur][i][c] : sh.dg.LDm[cur][i][c];
+            } else if (c == i) S[(size_t)(jb + c) * CLD + t] = POSDEF ? sh.dg.A[cur][i][i] : 1.0;
          }
-      } else {
+      } else if (!POSDEF) {
          /* an earlier column of the segment: the block's permutation is a row permutation of L */
          double v[BS];
          #pragma unroll
@@ -156,12 +168,13 @@ PV_FN int chain_segment(Ctx& cx, ChainShared& sh, const double* Lseg, size_t ldl
             S[(size_t)c * CLD + t] = s;
          }
       }
-      if (t < 2 * BS) out->dinv[2 * jb + t] = sh.dg.dinv[t];
+      if (POSDEF) { if (t < BS) out->dinv[jb + t] = sh.dg.dinv[t]; }      // 1 / l_jj, one per column
+      else if (t < 2 * BS) out->dinv[2 * jb + t] = sh.dg.dinv[t];
       if (t < BS) out->lperm[jb + t] = sh.lperm[t];
       cx.sync();
    }
    for (int c = 0; c < CW; ++c) {
-      out->l11[t + (size_t)c * CW] = (t > c) ? S[(size_t)c * CLD + t] : (t == c ? 1.0 : 0.0);
+      out->l11[t + (size_t)c * CW] = (t > c) ? S[(size_t)c * CLD + t] : (t == c ? (POSDEF ? S[(size_t)c * CLD + c] : 1.0) : 0.0);
       out->ld11[t + (size_t)c * CW] = (t > c) ? S[(size_t)t * CLD + c] : 0.0;
    }
    return 1;
@@ -178,7 +191,7 @@ struct TileShared {
 /* Tiles: rows [r0, r0 + RT) of the front below the segment (r >= p + CW), RT threads.
  * Lp / LDp: column p of L / of the L*D scratch; BK: backup, same layout, CW columns.
  * Sets *fail when an entry violates |l_ij| <= 1/u (the segment is then rolled back). */
-template <class Ctx>
+template <bool POSDEF, class Ctx>
 PV_FN void panel_tile(Ctx& cx, TileShared& sh, double* Lp, double* LDp, double* BK, size_t ldl, int m, int r0,
       int p, double u, double inf, const SegWS* ws, int* fail) {
    constexpr int BS = DB_BS;
@@ -189,7 +202,7 @@ PV_FN void panel_tile(Ctx& cx, TileShared& sh, double* Lp, double* LDp, double* 
    for (int c = 0; c < CW; ++c) {       /* independent loads: many in flight per thread */
       const double v = active ? Lp[r + (size_t)c * ldl] : 0.0;
       sh.T[(size_t)c * CLD + t] = v;
-      if (active) BK[r + (size_t)c * ldl] = v;
+      if (!POSDEF && active) BK[r + (size_t)c * ldl] = v;       // Cholesky never rolls back
    }
    const double lim = 1.0 / u;
    int bad = 0;
@@ -204,8 +217,9 @@ PV_FN void panel_tile(Ctx& cx, TileShared& sh, double* Lp, double* LDp, double* 
          sh.ys[cc * PV_YLD + k] = ws->ld11[(jb + BS + cc) + (size_t)(jb + k) * CW];
       }
       if (t < BS) {
-         double v0, v1, v2;
-         pv_dinv_coeffs(ws->dinv + 2 * jb, t, inf, v0, v1, v2);
+         double v0, v1 = 0.0, v2 = 0.0;
+         if (POSDEF) v0 = ws->dinv[jb + t];
+         else pv_dinv_coeffs(ws->dinv + 2 * jb, t, inf, v0, v1, v2);
          sh.c0[t] = v0; sh.c1[t] = v1; sh.c2[t] = v2;
          sh.lperm[t] = ws->lperm[jb + t];
       }
@@ -214,25 +228,36 @@ PV_FN void panel_tile(Ctx& cx, TileShared& sh, double* Lp, double* LDp, double* 
          double y[BS], wv[BS];
          #pragma unroll
          for (int j = 0; j < BS; ++j) y[j] = sh.T[(size_t)(jb + sh.lperm[j]) * CLD + t];
-         #pragma unroll
-         for (int j = 0; j < BS; ++j) {
-            double s = y[j];
+         if (POSDEF) {
             #pragma unroll
-            for (int k = 0; k < j; ++k) s -= y[k] * sh.l11[j * PV_YLD + k];
-            y[j] = s;
-         }
-         #pragma unroll
-         for (int j = 0; j < BS; ++j) {
-            double w = sh.c0[j] * y[j];
-            if (j + 1 < BS) w += sh.c1[j] * y[(j + 1) % BS];
-            if (j > 0) w += sh.c2[j] * y[(j + BS - 1) % BS];
-            wv[j] = w;
-            if (!(fabs(w) <= lim)) bad = 1;
+            for (int j = 0; j < BS; ++j) {
+               double s = y[j];
+               #pragma unroll
+               for (int k = 0; k < j; ++k) s -= y[k] * sh.l11[j * PV_YLD + k];
+               y[j] = s * sh.c0[j];
+               wv[j] = y[j];
+            }
+         } else {
+            #pragma unroll
+            for (int j = 0; j < BS; ++j) {
+               double s = y[j];
+               #pragma unroll
+               for (int k = 0; k < j; ++k) s -= y[k] * sh.l11[j * PV_YLD + k];
+               y[j] = s;
+            }
+            #pragma unroll
+            for (int j = 0; j < BS; ++j) {
+               double w = sh.c0[j] * y[j];
+               if (j + 1 < BS) w += sh.c1[j] * y[(j + 1) % BS];
+               if (j > 0) w += sh.c2[j] * y[(j + BS - 1) % BS];
+               wv[j] = w;
+               if (!(fabs(w) <= lim)) bad = 1;
+            }
          }
          #pragma unroll
          for (int j = 0; j < BS; ++j) {
             sh.T[(size_t)(jb + j) * CLD + t] = wv[j];
-            LDp[r + (size_t)(jb + j) * ldl] = y[j];
+            if (!POSDEF) LDp[r + (size_t)(jb + j) * ldl] = y[j];      // Cholesky: L*D is L itself (f->LD == f->L)
          }
          for (int cc = 0; cc < ncc; ++cc) {               // A(r, c) -= sum_k L(r, jb+k) (L D)(c, jb+k)
             const double* Yc = sh.ys + cc * PV_YLD;
@@ -257,11 +282,19 @@ struct CommitShared { int lperm[CW]; int perm[CW]; };
  * the segment are restored from the backup; on success (1) the rows of the segment in the
  * already-factored columns c < p are permuted block by block, (2) the CTA whose tile holds
  * row p (diag_cta) writes the diagonal block, D^-1 and the pivot order. */
-template <class Ctx>
+template <bool POSDEF, class Ctx>
 PV_FN void seg_commit(Ctx& cx, CommitShared& sh, double* L, double* D, int* perm, const double* BK, size_t ldl,
       int m, int p, int r0, bool diag_cta, int seg_fail, const SegWS* ws) {
    constexpr int BS = DB_BS;
    const int t = cx.tid();
+   if (POSDEF) {                      /* no permutation, no D: only the diagonal block is left to write */
+      if (diag_cta)
+         for (int e = t; e < CW * CW; e += RT) {
+            const int i = e % CW, c = e / CW;
+            if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
+         }
+      return;
+   }
    if (seg_fail) {
       const int r = r0 + t;
       if (r >= p + CW && r < m) {

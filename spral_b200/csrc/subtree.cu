@@ -568,9 +568,9 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       if (v2) {
          const int nseg = PW / panel_segment_width();
          for (int seg = 0; seg < nseg; ++seg) {
-            PROF(PC_DIAG, launch_panel_chain(d_fronts, d_flist, na_all, seg == 0, prm, s));
-            PROF(PC_APPLY, launch_panel_tiles(d_fronts, d_rows, rows_prefix[na_all], prm, s));
-            PROF(PC_COMMIT, launch_seg_commit(d_fronts, d_rows, rows_prefix[na_all], s));
+            PROF(PC_DIAG, launch_panel_chain(d_fronts, d_flist, na_all, posdef, seg == 0, prm, s));
+            PROF(PC_APPLY, launch_panel_tiles(d_fronts, d_rows, rows_prefix[na_all], posdef, prm, s));
+            PROF(PC_COMMIT, launch_seg_commit(d_fronts, d_rows, rows_prefix[na_all], posdef, s));
             if (seg + 1 < nseg) PROF(PC_INNER, launch_update(d_fronts, d_inner, inner_prefix[na_all], UPD_SEG, false, s));
          }
          take_snapshot();
@@ -879,11 +879,11 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       }
       const bool big = maxm >= 192;
       /* speculative panel segments: a few large fronts per level only (the chain workspace is 260 KB per front) */
-      const bool v2 = g_panel_v2 && big && !posdef && nfl <= g_panel_v2_fronts;
+      const bool v2 = g_panel_v2 && big && nfl <= g_panel_v2_fronts;
       const int bkw = v2 ? panel_segment_width() : BS;        // columns of the backup scratch
       if (v2) {
          bkd = 0;
-         for (int fi = f0; fi < f1; ++fi) bkd += (size_t)F[fi].ldl * bkw + 32;
+         for (int fi = f0; fi < f1; ++fi) bkd += (size_t)F[fi].ldl * bkw + 32;      // (unused when posdef)
          S.b_segws.ensure((size_t)nfl * panel_segment_ws_bytes(), s);
       }
       char* lblock = (char*)N.falloc(lbytes);

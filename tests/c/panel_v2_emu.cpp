@@ -43,7 +43,7 @@ static Result run(int m, std::mt19937_64& rng, int kind) {
    std::fill((char*)csh.get(), (char*)csh.get() + sizeof(ChainShared), (char)0xAB);
    int ok = -1;
    emu::run_cta(CNT, [&](emu::Ctx& cx) {
-      int r = chain_segment(cx, *csh, L.data() + p + (size_t)p * ldl, (size_t)ldl, 0.01, 1e-20, INF, ws.get());
+      int r = chain_segment<false>(cx, *csh, L.data() + p + (size_t)p * ldl, (size_t)ldl, 0.01, 1e-20, INF, ws.get());
       if (cx.tid() == 0) ok = r;
    });
    Result res{ok, 0, 0, 0, 0, 0, 0, true};
@@ -81,7 +81,7 @@ static Result run(int m, std::mt19937_64& rng, int kind) {
       if (r0 + RT <= p + CW) continue;
       std::fill((char*)tsh.get(), (char*)tsh.get() + sizeof(TileShared), (char)0xAB);
       emu::run_cta(RT, [&](emu::Ctx& cx) {
-         panel_tile(cx, *tsh, L.data() + (size_t)p * ldl, LD.data() + (size_t)p * ldl, BK.data(), (size_t)ldl, m, r0, p,
+         panel_tile<false>(cx, *tsh, L.data() + (size_t)p * ldl, LD.data() + (size_t)p * ldl, BK.data(), (size_t)ldl, m, r0, p,
                     0.01, INF, ws.get(), &res.tile_fail);
       });
    }

@@ -29,12 +29,13 @@ struct FrontEmu {
 };
 
 /* one speculative segment at p = done: returns 1 accepted, 0 chain gave up, -1 rolled back */
+template <bool POSDEF>
 static int segment(FrontEmu& f) {
    const int p = f.done, m = f.m, ldl = f.ldl;
    auto csh = std::make_unique<ChainShared>();
    int ok = 0;
    emu::run_cta(CNT, [&](emu::Ctx& cx) {
-      int r = chain_segment(cx, *csh, f.L.data() + p + (size_t)p * ldl, (size_t)ldl, 0.01, 1e-20, INF, f.ws.get());
+      int r = chain_segment<POSDEF>(cx, *csh, f.L.data() + p + (size_t)p * ldl, (size_t)ldl, 0.01, 1e-20, INF, f.ws.get());
       if (cx.tid() == 0) ok = r;
    });
    if (!ok) return 0;
@@ -43,14 +44,14 @@ static int segment(FrontEmu& f) {
    for (int r0 = 0; r0 < m; r0 += RT) {
       if (r0 + RT <= p + CW) continue;
       emu::run_cta(RT, [&](emu::Ctx& cx) {
-         panel_tile(cx, *tsh, f.L.data() + (size_t)p * ldl, f.LD.data() + (size_t)p * ldl, f.BK.data(), (size_t)ldl, m, r0,
+         panel_tile<POSDEF>(cx, *tsh, f.L.data() + (size_t)p * ldl, (POSDEF ? f.L.data() : f.LD.data()) + (size_t)p * ldl, POSDEF ? nullptr : f.BK.data(), (size_t)ldl, m, r0,
                     p, 0.01, INF, f.ws.get(), &seg_fail);
       });
    }
    CommitShared cs;
    for (int r0 = 0; r0 < m; r0 += RT)
       emu::run_cta(RT, [&](emu::Ctx& cx) {
-         seg_commit(cx, cs, f.L.data(), f.D.data(), f.perm.data(), f.BK.data(), (size_t)ldl, m, p, r0, r0 / RT == p / RT,
+         seg_commit<POSDEF>(cx, cs, f.L.data(), f.D.data(), f.perm.data(), f.BK.data(), (size_t)ldl, m, p, r0, r0 / RT == p / RT,
                     seg_fail, f.ws.get());
       });
    if (seg_fail) return -1;
@@ -59,11 +60,12 @@ static int segment(FrontEmu& f) {
 }
 
 /* C(r, c) -= sum_{k in [k0, k1)} L(r, k) LD(c, k) for c in [c_lo, c_hi), r >= c */
-static void update(FrontEmu& f, int k0, int k1, int c_lo, int c_hi) {
+static void update(FrontEmu& f, int k0, int k1, int c_lo, int c_hi, bool posdef = false) {
+   const std::vector<double>& B = posdef ? f.L : f.LD;        // f->LD == f->L for Cholesky
    for (int c = c_lo; c < c_hi; ++c)
       for (int r = c; r < f.m; ++r) {
          double s = 0;
-         for (int k = k0; k < k1; ++k) s += f.L[r + (size_t)k * f.ldl] * f.LD[c + (size_t)k * f.ldl];
+         for (int k = k0; k < k1; ++k) s += f.L[r + (size_t)k * f.ldl] * B[c + (size_t)k * f.ldl];
          f.L[r + (size_t)c * f.ldl] -= s;
       }
 }
@@ -120,11 +122,11 @@ int main() {
    int failures = 0;
    for (int m : {384, 500}) {
       FrontEmu f = make_front(m, 384, rng);
-      int a = segment(f);                       // p = 0
+      int a = segment<false>(f);                       // p = 0
       update(f, 0, 128, 128, 256);              // UPD_SEG
-      int b = segment(f);                       // p = 128
+      int b = segment<false>(f);                       // p = 128
       update(f, 0, 256, 256, f.n);              // UPD_OUTER
-      int c = segment(f);                       // p = 256
+      int c = segment<false>(f);                       // p = 256
       double err = check(f, 384);
       bool ok = a == 1 && b == 1 && c == 1 && f.done == 384 && err < 1e-10;
       printf("m=%d n=384: segments %d %d %d, |P A P' - L D L'| = %.2e %s\n", m, a, b, c, err, ok ? "ok" : "FAIL");
@@ -134,16 +136,48 @@ int main() {
       FrontEmu f = make_front(500, 384, rng);
       for (int c = 128; c < 256; ++c)
          for (int r = 256; r < f.m; ++r) { f.A[r + (size_t)c * f.ldl] *= 1e9; f.L[r + (size_t)c * f.ldl] *= 1e9; }
-      int a = segment(f);
+      int a = segment<false>(f);
       update(f, 0, 128, 128, 256);
       std::vector<double> Lb = f.L, Db = f.D;
       std::vector<int> pb = f.perm;
-      int b = segment(f);
+      int b = segment<false>(f);
       bool same = (f.L.size() == Lb.size());
       for (size_t e = 0; e < Lb.size() && same; ++e) same = (f.L[e] == Lb[e]) || (std::isnan(f.L[e]) && std::isnan(Lb[e]));
       same = same && f.D == Db && f.perm == pb && f.done == 128;
       printf("roll-back: segments %d %d, front unchanged = %d %s\n", a, b, (int)same, (a == 1 && b == -1 && same) ? "ok" : "FAIL");
       failures += !(a == 1 && b == -1 && same);
+   }
+   for (int m : {384, 470}) {
+      /* positive definite: Cholesky segments, no permutation, no D, no backup */
+      FrontEmu f = make_front(m, 384, rng);
+      for (int c = 0; c < f.n; ++c) {                     // make it strictly diagonally dominant
+         f.A[c + (size_t)c * f.ldl] = 40.0 + c % 7;
+         f.L[c + (size_t)c * f.ldl] = f.A[c + (size_t)c * f.ldl];
+      }
+      int a = segment<true>(f);
+      update(f, 0, 128, 128, 256, true);
+      int b = segment<true>(f);
+      update(f, 0, 256, 256, f.n, true);
+      int c = segment<true>(f);
+      double err = 0;
+      for (int cc = 0; cc < f.n; ++cc)
+         for (int i = cc; i < m; ++i) {
+            double sum = 0;
+            for (int k = 0; k <= cc; ++k) sum += f.L[i + (size_t)k * f.ldl] * f.L[cc + (size_t)k * f.ldl];
+            err = std::max(err, std::fabs(sum - f.A[i + (size_t)cc * f.ldl]));
+         }
+      bool ok = a == 1 && b == 1 && c == 1 && f.done == 384 && err < 1e-10;
+      printf("posdef m=%d n=384: segments %d %d %d, |A - L L'| = %.2e %s\n", m, a, b, c, err, ok ? "ok" : "FAIL");
+      failures += !ok;
+   }
+   {  /* not positive definite: the chain gives up and changes nothing */
+      FrontEmu f = make_front(300, 256, rng);
+      std::vector<double> Lb = f.L;
+      int a = segment<true>(f);                           // make_front's diagonal alternates in sign
+      bool same = true;
+      for (size_t e = 0; e < Lb.size() && same; ++e) same = (f.L[e] == Lb[e]) || (std::isnan(f.L[e]) && std::isnan(Lb[e]));
+      printf("not positive definite: segment %d, front unchanged = %d %s\n", a, (int)same, (a == 0 && same) ? "ok" : "FAIL");
+      failures += !(a == 0 && same);
    }
    printf("panel_v2_front_emu: %d failures\n", failures);
    return failures ? 1 : 0;
