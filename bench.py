@@ -128,6 +128,53 @@ def restore_affinity():
             pass
 
 
+def hbm_peak_gbs():
+    """Measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst)"
+    except Exception:
+        return 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def assembly_algorithmic_bytes(a):
+    """Extend-add traffic of one factorisation without delays: every child contribution
+    entry is read once and its parent entry read and written, (m-n)(m-n+1)/2 entries x 24 B per
+    child front, plus the 4 (m-n) index bytes; reading A (8 + 16 B per entry) and zeroing +
+    writing the fronts' fully-summed columns once (16 B per entry of L)."""
+    m = (a.rptr[1:] - a.rptr[:-1]).astype(np.float64)
+    nc = (a.sptr[1:] - a.sptr[:-1]).astype(np.float64)
+    cm = m - nc
+    has_parent = np.asarray(a.sparent) <= a.nnodes
+    ext = float(((cm * (cm + 1) / 2 * 24 + 4 * cm) * has_parent).sum())
+    nz = int(a.ptr[a.n]) - 1
+    return {"extend_add": ext, "scatter_a": 24.0 * nz, "zero_and_write_L": 16.0 * float((m * nc).sum())}
+
+
+def hbm_bound_parts(a, inform, solve_ms, tm):
+    """Achieved HBM GB/s of the memory-bound parts, algorithmic bytes / measured time: the 1-RHS solve
+    (reads L once forward, once backward: 2 x 8 x num_factor bytes) from the device-resident
+    solve timing, and assembly / front initialisation from the CUDA-event class times of the profiled
+    factorisation (timings()[8..16] = diag, apply, commit, inner, swap, outer, contrib, assemble, init)."""
+    peak, src = hbm_peak_gbs()
+    out = {"peak": peak, "unit": "GB/s", "peak_source": src}
+    t1 = solve_ms.get("1_device")
+    if t1:
+        b = 2 * 8.0 * inform["num_factor"]
+        out["solve_1rhs"] = {"bytes": b, "ms": t1, "achieved": b / (t1 * 1e-3) / 1e9, "frac": b / (t1 * 1e-3) / 1e9 / peak,
+                             "note": "latency-bound per 32-column block step, not bandwidth-bound (DESIGN.md 6)"}
+    ab = assembly_algorithmic_bytes(a)
+    t_asm, t_init = float(tm[8 + 7]), float(tm[8 + 8])
+    if t_asm > 0:
+        out["extend_add"] = {"bytes": ab["extend_add"], "ms": t_asm, "achieved": ab["extend_add"] / (t_asm * 1e-3) / 1e9,
+                             "frac": ab["extend_add"] / (t_asm * 1e-3) / 1e9 / peak, "kernel": "k_assemble"}
+    if t_init > 0:
+        bi = ab["scatter_a"] + ab["zero_and_write_L"]
+        out["init_fronts"] = {"bytes": bi, "ms": t_init, "achieved": bi / (t_init * 1e-3) / 1e9,
+                              "frac": bi / (t_init * 1e-3) / 1e9 / peak, "kernel": "cudaMemsetAsync + k_scatter_a"}
+    return out
+
+
 def cpu_reference_factor(grid):
     """cpu_baseline leg: the reference's own CPU engine (oracle/_ref, unmodified sources) on the
     same stencil at `grid`^3, in a process of its own (`bench.py --impl reference`) so that its
@@ -352,6 +399,14 @@ def main():
                     "peak_source": "FP64 DMMA issue loop measured live on this GPU "
                                    "(MEASURED_PEAKS.json has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.9 TF/s on this pool)"}
 
+    # ---- the HBM-bound parts (north_star: achieved GB/s of assembly and solves against the copy bandwidth) ----
+    hbm_rooflines = None
+    if world == 1 and roofline is not None:
+        try:
+            hbm_rooflines = hbm_bound_parts(a, inform, solve_ms, tm)
+        except Exception as e:                                  # extra figures only
+            hbm_rooflines = {"error": repr(e)}
+
     out = {
         "metric": "ssids_factor FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_mean,
@@ -373,6 +428,8 @@ def main():
     }
     if roofline:
         out["roofline"] = roofline
+    if hbm_rooflines:
+        out["roofline_hbm_parts"] = hbm_rooflines
 
     # ---- CPU baseline: the reference engine on a bounded sample (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
