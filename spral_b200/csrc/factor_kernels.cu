@@ -200,7 +200,7 @@ void launch_delays(Front* fronts, const AsmSrc* srcs, const int2* work, int nwor
 __device__ void account_segment(Front* f) {
    if (!f->seg_valid) return;
    if (f->seg_ok && !f->seg_fail) f->done += CW;
-   else f->spec_off = 1;
+   else { f->spec_off = 1; f->spec_fails++; }
    f->seg_valid = 0;
 }
 
@@ -578,7 +578,7 @@ k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, Facto
    if (threadIdx.x == 0) {
       advance_state(f, new_panel != 0);
       int go = !f->finished && f->panel_open && !f->spec_off && f->sws != nullptr && !f->step_valid
-               && (f->pend - f->done >= CW);
+               && f->spec_fails < SPEC_MAX_FAILS && (f->pend - f->done >= CW);
       if (go) { f->seg_valid = 1; f->seg_ok = 0; f->seg_fail = 0; }
       s_go = go;
    }

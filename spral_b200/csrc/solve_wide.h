@@ -51,26 +51,30 @@ SW_FN int sw_row_index(const SolveFront& f, int i) {
 }
 
 /* shared memory of the T kernels: xs/vs [SWB * NR], lkk [SSB * SW_LK] doubles */
-template <int NR> constexpr size_t sw_T_smem_doubles() { return (size_t)SWB * NR + (size_t)SSB * SW_LK; }
+/* row stride of the right-hand-side blocks in shared memory: odd, so that threads that own consecutive
+ * rows hit different banks also with 32 right-hand sides */
+template <int NR> constexpr int sw_xld() { return NR | 1; }
+template <int NR> constexpr size_t sw_T_smem_doubles() { return (size_t)SWB * sw_xld<NR>() + (size_t)SSB * SW_LK; }
 /* forward G: ys [SWB * NR] doubles */
 template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)SWB * NR; }
 /* backward G: tile [RT * SW_LK] + xr [RT * NR] doubles */
-template <int NR> constexpr size_t sw_bG_smem_doubles() { return (size_t)RT * SW_LK + (size_t)RT * NR; }
+template <int NR> constexpr size_t sw_bG_smem_doubles() { return (size_t)RT * SW_LK + (size_t)RT * sw_xld<NR>(); }
 
 /* ---- forward, T: y(block) = L(block, block)^-1 x(block); y -> ywork ---------------- */
 template <int NR, bool POSDEF, class Ctx>
 SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, double* ywork, double* smem) {
    const int kb = blk * SWB;
    if (kb >= f.nelim) return;
+   constexpr int XLD = sw_xld<NR>();
    double* xs = smem;
-   double* lkk = smem + (size_t)SWB * NR;
+   double* lkk = smem + (size_t)SWB * XLD;
    const int w = sw_min(SWB, f.nelim - kb);
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
    const size_t ldl = (size_t)f.ldl;
    const bool arow = t < w;
    const int g = arow ? f.perm[kb + t] - 1 : -1;
    #pragma unroll
-   for (int k = 0; k < NR; ++k) xs[(size_t)t * NR + k] = arow ? x[SW_XI(g, k)] : 0.0;
+   for (int k = 0; k < NR; ++k) xs[(size_t)t * XLD + k] = arow ? x[SW_XI(g, k)] : 0.0;
    const double* Lrow = f.L + (size_t)(kb + t) + (size_t)kb * ldl;     // row kb+t of the block, from column kb
    double cur[SSB], nxt[SSB];
    {
@@ -100,7 +104,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
       {  /* forward substitution: lanes are the rows of the sub-block, the right-hand sides are dealt to the warps */
          double v[NRW];
          #pragma unroll
-         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? xs[(size_t)(jb + lane) * NR + k] : 0.0; }
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? xs[(size_t)(jb + lane) * XLD + k] : 0.0; }
          for (int j = 0; j < wd; ++j) {
             const double l = (lane > j && lane < wd) ? lkk[lane * SW_LK + j] : 0.0;
             const double dj = POSDEF ? lkk[j * SW_LK + j] : 1.0;
@@ -112,16 +116,16 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
             }
          }
          #pragma unroll
-         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) xs[(size_t)(jb + lane) * NR + k] = v[q]; }
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) xs[(size_t)(jb + lane) * XLD + k] = v[q]; }
       }
       cx.sync();
       if (arow && t >= jn) {                      // rows of the block below the sub-block
          #pragma unroll
          for (int k = 0; k < NR; ++k) {
-            double s = xs[(size_t)t * NR + k];
+            double s = xs[(size_t)t * XLD + k];
             #pragma unroll
-            for (int j = 0; j < SSB; ++j) s -= cur[j] * xs[(size_t)(jb + j) * NR + k];
-            xs[(size_t)t * NR + k] = s;
+            for (int j = 0; j < SSB; ++j) s -= cur[j] * xs[(size_t)(jb + j) * XLD + k];
+            xs[(size_t)t * XLD + k] = s;
          }
       }
       #pragma unroll
@@ -130,7 +134,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
    cx.sync();
    if (arow) {
       #pragma unroll
-      for (int k = 0; k < NR; ++k) ywork[SW_XI(g, k)] = xs[(size_t)t * NR + k];
+      for (int k = 0; k < NR; ++k) ywork[SW_XI(g, k)] = xs[(size_t)t * XLD + k];
    }
 }
 
@@ -183,7 +187,8 @@ SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const
    const int r0 = tileidx * RT;
    if (r0 + RT <= kb + w || r0 >= f.m) return;      // no row of this tile below the block
    double* tile = smem;                             // [RT][SW_LK]; re-used for the cross-warp reduction
-   double* xr = smem + (size_t)RT * SW_LK;          // [RT][NR]
+   constexpr int XLD = sw_xld<NR>();
+   double* xr = smem + (size_t)RT * SW_LK;          // [RT][XLD]
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
    const int r = r0 + t;
    const bool active = (r >= kb + w) && (r < f.m);
@@ -191,7 +196,7 @@ SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const
    {
       const int g = active ? sw_row_index(f, r) : 0;
       #pragma unroll
-      for (int k = 0; k < NR; ++k) xr[(size_t)t * NR + k] = active ? x[SW_XI(g, k)] : 0.0;
+      for (int k = 0; k < NR; ++k) xr[(size_t)t * XLD + k] = active ? x[SW_XI(g, k)] : 0.0;
    }
    for (int jb = 0; jb < w; jb += SSB) {
       const int wd = sw_min(SSB, w - jb);
@@ -204,7 +209,7 @@ SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const
       for (int i = 0; i < 32; ++i) {
          const double l = tile[(size_t)(warp * 32 + i) * SW_LK + lane];
          #pragma unroll
-         for (int k = 0; k < NR; ++k) acc[k] += l * xr[(size_t)(warp * 32 + i) * NR + k];
+         for (int k = 0; k < NR; ++k) acc[k] += l * xr[(size_t)(warp * 32 + i) * XLD + k];
       }
       cx.sync();
       #pragma unroll
@@ -227,8 +232,9 @@ template <int NR, bool POSDEF, class Ctx>
 SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const double* pb, double* smem) {
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
+   constexpr int XLD = sw_xld<NR>();
    double* vs = smem;
-   double* lkk = smem + (size_t)SWB * NR;
+   double* lkk = smem + (size_t)SWB * XLD;
    const int kb = b * SWB;
    const int w = sw_min(SWB, f.nelim - kb);
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
@@ -243,7 +249,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const d
          v = x[SW_XI(g, k)];
          for (int tt = t0; tt < ntile; ++tt) v -= pb[(size_t)tt * SWB * NR + (size_t)t * NR + k];
       }
-      vs[(size_t)t * NR + k] = v;
+      vs[(size_t)t * XLD + k] = v;
    }
    const size_t ldl = (size_t)f.ldl;
    const double* Lcol = f.L + (size_t)kb + (size_t)(kb + t) * ldl;     // column kb+t of the block, from row kb
@@ -272,7 +278,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const d
       {  /* transposed substitution: lanes are the columns of the sub-block */
          double v[NRW];
          #pragma unroll
-         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? vs[(size_t)(jb + lane) * NR + k] : 0.0; }
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? vs[(size_t)(jb + lane) * XLD + k] : 0.0; }
          for (int j = wd - 1; j >= 0; --j) {
             const double l = (lane < j) ? lkk[j * SW_LK + lane] : 0.0;
             const double dj = POSDEF ? lkk[j * SW_LK + j] : 1.0;
@@ -284,16 +290,16 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const d
             }
          }
          #pragma unroll
-         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) vs[(size_t)(jb + lane) * NR + k] = v[q]; }
+         for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) vs[(size_t)(jb + lane) * XLD + k] = v[q]; }
       }
       cx.sync();
       if (acol && t < jb) {                       // columns of the block left of the sub-block
          #pragma unroll
          for (int k = 0; k < NR; ++k) {
-            double s = vs[(size_t)t * NR + k];
+            double s = vs[(size_t)t * XLD + k];
             #pragma unroll
-            for (int i = 0; i < SSB; ++i) s -= cur[i] * vs[(size_t)(jb + i) * NR + k];
-            vs[(size_t)t * NR + k] = s;
+            for (int i = 0; i < SSB; ++i) s -= cur[i] * vs[(size_t)(jb + i) * XLD + k];
+            vs[(size_t)t * XLD + k] = s;
          }
       }
       #pragma unroll
@@ -302,7 +308,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const d
    cx.sync();
    if (acol) {
       #pragma unroll
-      for (int k = 0; k < NR; ++k) x[SW_XI(g, k)] = vs[(size_t)t * NR + k];
+      for (int k = 0; k < NR; ++k) x[SW_XI(g, k)] = vs[(size_t)t * XLD + k];
    }
 }
 
