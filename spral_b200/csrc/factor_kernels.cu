@@ -954,7 +954,7 @@ __global__ void k_snapshot(Front* fronts, const int* __restrict__ flist, int cou
    }
    int* o = snap + (size_t)i * 8;
    o[0] = f->p0; o[1] = f->done; o[2] = f->pend; o[3] = f->pend0; o[4] = f->end;
-   o[5] = f->finished; o[6] = f->flag; o[7] = 0;
+   o[5] = f->finished; o[6] = f->flag; o[7] = f->spec_fails;
 }
 
 void launch_snapshot(Front* fronts, const int* flist, int count, int* snap, cudaStream_t s) {

@@ -476,6 +476,7 @@ struct HostState {
    int fi = 0, m = 0, n = 0;
    int done = 0, end = 0, pass_start = 0, p0 = 0, pend0 = 0, pend = 0;
    bool finished = false;
+   bool spec_dead = false;      // panel_v2: the front gave up SPEC_MAX_FAILS segments, no more speculative launches
 };
 
 /* Factorises the n fully-summed columns of every front in `fronts` (indices
@@ -564,7 +565,12 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
        * a failed or zero pivot changes nothing; the step-by-step loop below then finishes the panel. */
       bool steps_new_panel = true;
       int steps_todo = nsteps;
-      const bool v2 = F[fronts[0]].sws != nullptr;
+      bool v2 = F[fronts[0]].sws != nullptr;
+      if (v2) {                              // nothing to gain once every active front has stopped speculating
+         bool any_alive = false;
+         for (int k = 0; k < na_all; ++k) any_alive = any_alive || !H[act[k]].spec_dead;
+         v2 = any_alive;
+      }
       if (v2) {
          const int nseg = PW / panel_segment_width();
          for (int seg = 0; seg < nseg; ++seg) {
@@ -616,6 +622,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          if (sn[0] != h.p0 || sn[3] != h.pend0 || sn[4] != h.end)
             throw std::runtime_error("host mirror of the pivoting state diverged from the device");
          h.done = sn[1]; h.pend = sn[2];
+         h.spec_dead = sn[7] >= SPEC_MAX_FAILS;
          if (h.done > h.p0 && h.pend0 < h.n) {
             if (g_prof) {
                double K = h.done - h.p0, nn = h.n, c0 = h.pend0, mm = h.m;
