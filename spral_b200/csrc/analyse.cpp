@@ -744,6 +744,14 @@ struct spral_ssids_b200_analysis* spral_ssids_b200_analyse(
    *flag = 0;
    A->n = n;
    if (nemin < 1) nemin = 32; /* nemin_default, datatypes.f90 */
+   if (n <= 0) {
+      /* trivial matrix: ssids_analyse returns with akeep%nnodes = 0 (src/ssids/ssids.f90:212-218)
+       * and factor / solve return immediately (:848-852, :1193) */
+      A->n = 0;
+      A->sptr.assign(1, 1); A->rptr.assign(1, 1); A->nptr.assign(1, 1); A->part.assign(1, 1);
+      A->contrib_ptr.assign(3, 1);
+      return A;
+   }
    i64 nz = ptr[n] - 1;
    vec<i64> ptr2;
    vec<int> row2;

@@ -31,7 +31,7 @@ class Analysis:
         self.row = np.ascontiguousarray(row, dtype=np.int32)
         if order is None:
             order = np.zeros(n, dtype=np.int32)
-            rc = lib.spral_ssids_b200_metis_order(n, _ptr(self.ptr), _ptr(self.row), _ptr(order))
+            rc = lib.spral_ssids_b200_metis_order(n, _ptr(self.ptr), _ptr(self.row), _ptr(order)) if n > 0 else 0
             if rc != 0:
                 raise RuntimeError(f"metis_order failed: {rc}")
         self.order = np.ascontiguousarray(order, dtype=np.int32).copy()
@@ -53,12 +53,13 @@ class Analysis:
         self.nptr = as_np(v.nptr, (nn + 1,))
         nz = int(self.ptr[n]) - 1
         self.nlist = as_np(v.nlist, (2 * nz,)) if nz else np.zeros(0, np.int64)
-        self.invp = as_np(v.invp, (n,))
-        self.part = as_np(v.part, (v.nparts + 1,))
-        self.exec_loc = as_np(v.exec_loc, (v.nparts,))
-        self.contrib_ptr = as_np(v.contrib_ptr, (v.nparts + 3,))
-        self.contrib_idx = as_np(v.contrib_idx, (v.nparts,))
-        self.contrib_dest = as_np(v.contrib_dest, (v.nparts,))
+        npt = v.nparts
+        self.invp = as_np(v.invp, (n,)) if n else np.zeros(0, np.int32)
+        self.part = as_np(v.part, (npt + 1,))
+        self.exec_loc = as_np(v.exec_loc, (npt,)) if npt else np.zeros(0, np.int32)
+        self.contrib_ptr = as_np(v.contrib_ptr, (npt + 3,))
+        self.contrib_idx = as_np(v.contrib_idx, (npt,)) if npt else np.zeros(0, np.int32)
+        self.contrib_dest = as_np(v.contrib_dest, (npt,)) if npt else np.zeros(0, np.int32)
         self.num_factor, self.num_flops = v.num_factor, v.num_flops
         self.maxfront, self.maxsupernode, self.maxdepth = v.maxfront, v.maxsupernode, v.maxdepth
 
@@ -308,6 +309,8 @@ def solve(fkeep, x, job=0):
     x: (n,) or (n, nrhs) Fortran-ordered; returns the solution (same shape)."""
     a = fkeep.akeep.analysis
     x = np.asarray(x, dtype=np.float64)
+    if a.n == 0:                      # trivial matrix: nothing to do (src/ssids/ssids.f90:1193)
+        return x.copy()
     one = x.ndim == 1
     X = np.asfortranarray(x.reshape(a.n, -1))
     nrhs = X.shape[1]

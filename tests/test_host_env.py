@@ -57,3 +57,15 @@ def test_cpu_baseline_leg_runs_in_its_own_process():
     cb = ref["cpu_baseline"]
     assert ref["impl"] == "reference" and cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] > 0
     assert ref["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_trivial_matrix_n0():
+    """ssids_analyse / factor / solve on the empty matrix return immediately with rank 0
+    (src/ssids/ssids.f90:212-218, 848-852, 1193); no GPU is touched."""
+    import numpy as np
+    import spral_b200 as sb
+    ak = sb.analyse(0, np.array([1], dtype=np.int64), np.zeros(0, dtype=np.int32))
+    assert ak.analysis.nnodes == 0 and ak.analysis.nparts == 0 and ak.subtrees == []
+    fk = sb.factor(ak, False, np.zeros(0))
+    assert fk.inform["flag"] == 0 and fk.inform["matrix_rank"] == 0 and fk.numeric == []
+    assert sb.solve(fk, np.zeros(0)).shape == (0,)
