@@ -766,6 +766,15 @@ struct spral_ssids_b200_analysis* spral_ssids_b200_analyse(
    find_etree(n, ptr2, row2, perm, invp, parent);
    find_postorder(n, realn, ptr2, perm, invp, parent);
    if (n != realn) *flag = 6; /* SSIDS_WARNING_ANAL_SINGULAR */
+   if (realn == 0) {
+      /* no entries at all: every variable is structurally unused, there is nothing to factorise
+       * (the numeric phases see nnodes = 0 like for n = 0; matrix_rank = 0) */
+      A->sptr.assign(1, 1); A->rptr.assign(1, 1); A->nptr.assign(1, 1); A->part.assign(1, 1);
+      A->contrib_ptr.assign(3, 1);
+      A->invp.resize(n);
+      for (int i = 0; i < n; ++i) A->invp[i] = i + 1;
+      return A;
+   }
    find_col_counts(n, ptr2, row2, perm, invp, parent, cc);
    int nnodes = 0;
    find_supernodes(n, realn, parent, cc, tperm, nnodes, sptr, sparent, scc, nemin);
