@@ -232,6 +232,32 @@ def kkt_saddle(n, frac_constraints=0.3, nnz_per_row=6, seed=486502):
     return _lower_csc_keep_zeros(K)
 
 
+def kkt_grid(g, frac_constraints=0.3, seed=486502):
+    """cfg4 at benchmark size: a KKT saddle-point matrix [H B^T; B 0] with LOCAL coupling, so that it
+    can be factorised at n ~ 500 000 (g = 70).  H is the 3-D 7-point Laplacian on a g^3 grid (SPD),
+    each of the m = frac/(1-frac) g^3 constraints couples one grid node (drawn without repetition) with
+    its +x, +y, +z neighbours (a perturbed discrete divergence; B has full row rank), the (2,2) block is
+    an explicit zero diagonal.  Inertia is exactly (g^3 positive, m negative).  The random-pattern
+    matrices of kkt_saddle / random_matrix_generate are expanders: their factors grow like n^2
+    (measured: n = 100 000 -> 3.2e13 flops, 39 000-row front) and cannot be formed at n = 500 000."""
+    nh = g ** 3
+    m = int(round(frac_constraints / (1.0 - frac_constraints) * nh))
+    n_, ptr, row, val = laplacian_3d_7pt(g)
+    H = to_scipy(n_, ptr, row, val).tocsr()
+    rng = np.random.default_rng(SpralRandom(seed).integer(2 ** 30))
+    cells = np.sort(rng.choice(nh, size=m, replace=False))
+    idx = np.arange(nh).reshape(g, g, g)
+    nb = [np.roll(idx, -1, axis=ax).ravel() for ax in range(3)]
+    rows = np.repeat(np.arange(m), 4)
+    cols = np.stack([cells, nb[0][cells], nb[1][cells], nb[2][cells]], axis=1).ravel()
+    vals = np.stack([np.full(m, 1.0)] + [rng.uniform(-0.6, -0.2, m) for _ in range(3)], axis=1).ravel()
+    Bm = sp.coo_matrix((vals, (rows, cols)), shape=(m, nh)).tocsr()
+    n = nh + m
+    K = sp.bmat([[H, Bm.T], [Bm, None]], format="csc")
+    K = K + sp.csc_matrix((np.zeros(m), (np.arange(nh, n), np.arange(nh, n))), shape=(n, n))
+    return _lower_csc_keep_zeros(K)
+
+
 def _lower_csc_keep_zeros(A):
     A = sp.csc_matrix(A)
     A.sort_indices()

@@ -534,3 +534,47 @@ def test_reference_generator_problems():
             p.close()
         for ns in fk.numeric:
             ns.close()
+
+
+def _kkt_properties(g, scaling_method, refine_steps=2):
+    """KKT matrix [H B^T; B 0] with H SPD and B of full row rank: inertia is exactly (dim H positive,
+    rows of B negative) whatever the pivot order -- a size-independent check that needs no oracle."""
+    from spral_b200 import ssids as host
+    n, ptr, row, val = M.kkt_grid(g)
+    m = n - g ** 3
+    ak = sb.analyse(n, ptr, row)
+    s = host.compute_scaling(ak.analysis, val, scaling_method) if scaling_method else None
+    fk = sb.factor(ak, False, val, scaling=s)
+    gi = fk.inform
+    assert gi["flag"] == 0, gi
+    assert gi["matrix_rank"] == n and gi["num_neg"] == m, (gi, m)
+    A = M.to_scipy(n, ptr, row, val)
+    B = np.asfortranarray(A @ np.ones((n, 1)))
+    X = sb.solve(fk, B)
+    be = oracle_ref.backward_error(A, X, B)
+    assert be < REF_TOL, be
+    for _ in range(refine_steps):
+        X = X + sb.solve(fk, np.asfortranarray(B - A @ X))
+    assert oracle_ref.backward_error(A, X, B) <= 1e-14
+    return gi
+
+
+@pytest.mark.parametrize("method", [None, "hungarian"])
+def test_structured_kkt_inertia_small(method):
+    gi = _kkt_properties(14, method)
+    n, ptr, row, val = M.kkt_grid(14)
+    a = Analysis(n, ptr, row)
+    from spral_b200 import ssids as host
+    s = host.compute_scaling(a, val, method) if method else None
+    parts, r, sc = oracle_ref.ref_factor(a, False, val, scaling=s)
+    for p in parts:
+        p.close()
+    assert gi["num_neg"] == r["num_neg"] and gi["matrix_rank"] == r["matrix_rank"]
+
+
+@pytest.mark.timeout(900)
+def test_full_size_properties_cfg4():
+    """BASELINE config 4 at benchmark size (n = 490 000, 30 % zero-diagonal constraint rows, matching-based
+    scaling): the structured KKT matrix of matrices.kkt_grid(70); inertia, rank, residual, refinement."""
+    gi = _kkt_properties(70, "hungarian")
+    assert gi["maxfront"] > 1000
