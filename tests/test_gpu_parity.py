@@ -498,7 +498,18 @@ def test_computed_scalings_cfg4_like(method):
     s = host.compute_scaling(a, val, method)
     a.close()
     assert s.shape == (n,) and np.all(s > 0) and np.all(np.isfinite(s))
-    _check(lambda: (n, ptr, row, val), False, 2, scaling=s)
+    ak = sb.analyse(n, ptr, row)
+    fk = sb.factor(ak, False, val, scaling=s)
+    parts, r, sc = oracle_ref.ref_factor(ak.analysis, False, val, scaling=s)
+    g = fk.inform
+    assert g["flag"] >= 0 and g["num_neg"] == r["num_neg"] and g["matrix_rank"] == r["matrix_rank"]
+    A = M.to_scipy(n, ptr, row, val)
+    B = np.asfortranarray(A @ np.ones((n, 2)))
+    Xg, Xr = sb.solve(fk, B), oracle_ref.ref_solve(ak.analysis, parts, False, B, sc)
+    for p in parts:
+        p.close()
+    bg, br = oracle_ref.backward_error(A, Xg, B), oracle_ref.backward_error(A, Xr, B)
+    assert bg < REF_TOL and bg <= 100 * br + 1e-13, (bg, br)
 
 
 def test_reference_generator_problems():
