@@ -282,6 +282,13 @@ void spral_ssids_b200_analysis_get(const struct spral_ssids_b200_analysis*,
 int spral_ssids_b200_hungarian_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,
       double* scaling, int* match, int scale_if_singular, int* matched);
 
+/* match_order_metis (src/match_order.f90:51-208; options%ordering = 2): matching-based ordering.  order[n]:
+ * 1-based pivot position of every variable, the two variables of a matched 2-cycle consecutive;
+ * scaling[n]: the matching-based scaling (options%scaling = 3 uses it at factor time).  Returns 0, 1
+ * (structurally singular) or a negative flag. */
+int spral_ssids_b200_match_order_metis(int n, const int64_t* ptr, const int* row, const double* val,
+      int* order, double* scaling);
+
 /* equilib_scale_sym (src/scaling.f90:381-416, inf_norm_equilib_sym :480-521);
  * equilib_options defaults: max_iterations = 10, tol = 1e-8.  Returns 0. */
 int spral_ssids_b200_equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,

@@ -100,6 +100,7 @@ SYMBOLS = {
     "spral_ssids_b200_analysis_get": (None, [_vp, C.POINTER(AnalysisView)]),
     "spral_ssids_b200_hungarian_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "spral_ssids_b200_equilib_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _i, _d, _ip]),
+    "spral_ssids_b200_match_order_metis": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -236,6 +236,128 @@ int spral_ssids_b200_hungarian_scale_sym(int n, const int64_t* ptr, const int* r
    return flag;
 }
 
+/* match_order_metis (src/match_order.f90:51-208): matching-based ordering for options%ordering = 2.
+ * The MC64-type matching and scaling (mo_scale / mo_match there; hungarian_scale_sym here, with
+ * scale_if_singular), then mo_split (:220-396): the matching is split into 1- and 2-cycles, the matrix
+ * is condensed so that a matched pair is one vertex, METIS orders the condensed graph, and the order is
+ * expanded so that the two variables of a pair are consecutive -- the 2x2 pivot the matching suggests is
+ * available to the factorisation without delays.  order[i] = position of variable i+1 in the pivot
+ * sequence (1-based).  Returns 0, 1 (structurally singular: warning) or a negative flag. */
+int spral_ssids_b200_match_order_metis(int n, const int64_t* ptr, const int* row, const double* val,
+      int* order, double* scaling) {
+   if (n < 0) return -1;
+   if (n == 0) return 0;
+   std::vector<int> cperm(n);
+   int matched = 0;
+   int flag = spral_ssids_b200_hungarian_scale_sym(n, ptr, row, val, scaling, cperm.data(), 1, &matched);
+   if (flag < 0) return flag;
+   for (int i = 0; i < n; ++i) if (cperm[i] < 0) cperm[i] = -1;
+   /* full pattern (both triangles), explicit zeros dropped, 1-based like the reference */
+   std::vector<int64_t> ptr2(n + 2, 0);
+   for (int j = 0; j < n; ++j)
+      for (int64_t e = ptr[j] - 1; e < ptr[j + 1] - 1; ++e) {
+         if (val[e] == 0.0) continue;
+         const int i = row[e] - 1;
+         ptr2[j + 2]++;
+         if (i != j) ptr2[i + 2]++;
+      }
+   ptr2[1] = 1;
+   for (int j = 1; j <= n; ++j) ptr2[j + 1] += ptr2[j];          // ptr2[j] = start of column j (1-based)
+   std::vector<int> row2((size_t)(ptr2[n + 1] - 1) + 1);
+   {
+      std::vector<int64_t> pos(ptr2.begin(), ptr2.end());
+      for (int j = 0; j < n; ++j)
+         for (int64_t e = ptr[j] - 1; e < ptr[j + 1] - 1; ++e) {
+            if (val[e] == 0.0) continue;
+            const int i = row[e] - 1;
+            row2[pos[j + 1]++] = i + 1;
+            if (i != j) row2[pos[i + 1]++] = j + 1;
+         }
+   }
+   /* ---- mo_split ---- (1-based arrays as in the reference) */
+   std::vector<int> iwork(n + 1, 0), cp(n + 1);
+   for (int i = 1; i <= n; ++i) cp[i] = cperm[i - 1];
+   for (int i = 1; i <= n; ++i) {
+      if (iwork[i] != 0) continue;
+      int j = i;
+      for (;;) {
+         if (cp[j] == -1) { iwork[j] = -2; break; }               // unmatched
+         else if (cp[j] == i) { iwork[j] = -1; break; }           // singleton (or the end of an odd cycle)
+         const int jj = cp[j];
+         iwork[j] = jj; iwork[jj] = j;                            // pair j with cperm(j)
+         j = cp[jj];
+         if (j == i) break;
+      }
+   }
+   for (int i = 1; i <= n; ++i) cp[i] = iwork[i];
+   std::vector<int> old_to_new(n + 1, 0), new_to_old(n + 1, 0);
+   int k = 1;
+   for (int i = 1; i <= n; ++i) {
+      const int j = cp[i];
+      if (j < i && j > 0) continue;
+      old_to_new[i] = k; new_to_old[k] = i;
+      if (j > 0) old_to_new[j] = k;
+      ++k;
+   }
+   const int ncomp_matched = k - 1;
+   std::vector<int64_t> ptr3(n + 2, 0);
+   std::vector<int> row3(row2.size() + 1);
+   std::fill(iwork.begin(), iwork.end(), 0);
+   ptr3[1] = 1;
+   int ncomp = 1;
+   int64_t jj = 1;
+   for (int i = 1; i <= n; ++i) {
+      const int j = cp[i];
+      if (j < i && j > 0) continue;
+      for (int pass = 0; pass < 2; ++pass) {
+         const int col = pass == 0 ? i : j;
+         if (pass == 1 && j <= 0) break;
+         for (int64_t kl = ptr2[col]; kl < ptr2[col + 1]; ++kl) {
+            const int krow = old_to_new[row2[kl]];
+            if (iwork[krow] == i) continue;
+            if (krow > ncomp_matched) continue;
+            row3[jj++] = krow;
+            iwork[krow] = i;
+         }
+      }
+      ptr3[ncomp + 1] = jj;
+      ++ncomp;
+   }
+   --ncomp;
+   /* lower triangle of the condensed pattern for metis_order */
+   {
+      int64_t out = 1, j1 = 1;
+      for (int i = 1; i <= ncomp; ++i) {
+         const int64_t j2 = ptr3[i + 1];
+         for (int64_t q = j1; q < j2; ++q) {
+            const int krow = row3[q];
+            if (krow < i) continue;
+            row3[out++] = krow;
+         }
+         ptr3[i + 1] = out;
+         j1 = j2;
+      }
+   }
+   std::vector<int> corder(ncomp);
+   {
+      std::vector<int64_t> p3((size_t)ncomp + 1);
+      for (int i = 0; i <= ncomp; ++i) p3[i] = ptr3[i + 1];
+      std::vector<int> r3((size_t)std::max<int64_t>(p3[ncomp] - 1, 1), 0);
+      for (int64_t q = 1; q < p3[ncomp]; ++q) r3[q - 1] = row3[q];
+      const int rc = spral_ssids_b200_metis_order(ncomp, p3.data(), r3.data(), corder.data());
+      if (rc != 0) return rc;
+   }
+   std::vector<int> inv(ncomp + 1);
+   for (int i = 1; i <= ncomp; ++i) inv[corder[i - 1]] = i;        // iwork(order(i)) = i
+   k = 1;
+   for (int i = 1; i <= ncomp; ++i) {
+      int j = new_to_old[inv[i]];
+      order[j - 1] = k++;
+      if (cp[j] > 0) { j = cp[j]; order[j - 1] = k++; }
+   }
+   return flag;
+}
+
 /* equilib_scale_sym -> inf_norm_equilib_sym (src/scaling.f90:480-521); defaults of
  * equilib_options: max_iterations = 10, tol = 1e-8 (:48-51). */
 int spral_ssids_b200_equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,

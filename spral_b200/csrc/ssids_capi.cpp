@@ -21,9 +21,9 @@
 
 namespace {
 
-enum { OK = 0, E_CALL_SEQUENCE = -1, E_A_N_OOR = -2, E_A_PTR = -3, E_A_ALL_OOR = -4, E_SINGULAR = -5, E_ORDER = -8,
+enum { OK = 0, E_CALL_SEQUENCE = -1, E_A_N_OOR = -2, E_A_PTR = -3, E_A_ALL_OOR = -4, E_SINGULAR = -5, E_ORDER = -8, E_VAL = -9,
        E_X_SIZE = -10, E_JOB_OOR = -11, E_NOT_LLT = -13, E_NOT_LDLT = -14, E_ALLOCATION = -50,
-       E_UNIMPLEMENTED = -98,
+       E_NO_SAVED_SCALING = -15, E_UNIMPLEMENTED = -98,
        W_IDX_OOR = 1, W_DUP_IDX = 2, W_DUP_AND_OOR = 3, W_MISSING_DIAGONAL = 4, W_MISS_DIAG_OORDUP = 5,
        W_ANAL_SINGULAR = 6, W_FACT_SINGULAR = 7 };
 
@@ -33,6 +33,7 @@ struct Akeep {
    std::vector<int64_t> ptr;            // cleaned lower-triangular CSC, 1-based
    std::vector<int> row;
    std::vector<int64_t> map_ptr, map;   // cleaned entry k sums user entries map[map_ptr[k]..map_ptr[k+1])
+   std::vector<double> mo_scaling;      // scaling found by the matching-based ordering (options%ordering = 2)
    spral_ssids_b200_analysis* an = nullptr;
    spral_ssids_b200_analysis_view v;
    std::vector<void*> symbolic;         // one per part
@@ -102,7 +103,7 @@ int clean_matrix(int n, int base, const int64_t* ptr, const int* row, Akeep& A, 
    return flag;
 }
 
-void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int* row,
+void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int* row, const double* val,
       void** akeep, const spral_ssids_options* opt, spral_ssids_inform* inf) {
    std::memset(inf, 0, sizeof(*inf));
    if (*akeep) { delete static_cast<Akeep*>(*akeep); *akeep = nullptr; }
@@ -137,7 +138,23 @@ void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int
    } else if (opt->ordering == 1) {
       int rc = spral_ssids_b200_metis_order(n, A->ptr.data(), A->row.data(), ord.data());
       if (rc != 0) { inf->flag = rc; return; }
-   } else { inf->flag = E_UNIMPLEMENTED; return; }
+   } else if (opt->ordering == 2) {
+      /* matching-based ordering (ssids.f90:312-353): needs the values; the scaling is kept for
+       * options%scaling = 3 at factor time */
+      if (!val) { inf->flag = E_VAL; return; }
+      std::vector<double> cleaned;
+      const double* aval = val;
+      if (check) {
+         cleaned.assign(A->row.size(), 0.0);
+         for (size_t k = 0; k < cleaned.size(); ++k)
+            for (int64_t q = A->map_ptr[k]; q < A->map_ptr[k + 1]; ++q) cleaned[k] += val[A->map[q]];
+         aval = cleaned.data();
+      }
+      A->mo_scaling.resize(n);
+      int rc = spral_ssids_b200_match_order_metis(n, A->ptr.data(), A->row.data(), aval, ord.data(), A->mo_scaling.data());
+      if (rc < 0) { inf->flag = (rc == -1 || rc == -50) ? E_ALLOCATION : rc; return; }
+      if (rc == 1) wflag = W_ANAL_SINGULAR;
+   } else { inf->flag = E_ORDER; return; }
    int aflag = 0;
    A->an = spral_ssids_b200_analyse(n, A->ptr.data(), A->row.data(), ord.data(), opt->nemin, -1,
                                     0, opt->max_load_inbalance, opt->gpu_perf_coeff, &aflag);
@@ -207,16 +224,16 @@ void spral_ssids_default_options(struct spral_ssids_options* o) {
 }
 
 void spral_ssids_analyse(bool check, int n, int* order, const int64_t* ptr, const int* row,
-      const double*, void** akeep, const struct spral_ssids_options* options,
+      const double* val, void** akeep, const struct spral_ssids_options* options,
       struct spral_ssids_inform* inform) {
-   analyse_common(check, n, order, ptr, row, akeep, options, inform);
+   analyse_common(check, n, order, ptr, row, val, akeep, options, inform);
 }
 
 void spral_ssids_analyse_ptr32(bool check, int n, int* order, const int* ptr, const int* row,
-      const double*, void** akeep, const struct spral_ssids_options* options,
+      const double* val, void** akeep, const struct spral_ssids_options* options,
       struct spral_ssids_inform* inform) {
    std::vector<int64_t> p64(ptr, ptr + (n >= 0 ? n + 1 : 0));
-   analyse_common(check, n, order, p64.data(), row, akeep, options, inform);
+   analyse_common(check, n, order, p64.data(), row, val, akeep, options, inform);
 }
 
 void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* val, double* scale,
@@ -227,8 +244,9 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
    *inform = A->inform;
    if (A->inform.flag < 0) { inform->flag = E_CALL_SEQUENCE; return; }
    /* options%scaling (ssids.f90:899-1028): <= 0 user vector, 1 Hungarian (MC64), 4.. equilibration;
-    * 2 (auction) and 3 (from a matching-based ordering at analyse time) are not provided */
-   if (options->scaling == 2 || options->scaling == 3) { inform->flag = E_UNIMPLEMENTED; return; }
+    * 3 the scaling of the matching-based ordering (options%ordering = 2); 2 (auction) is not provided */
+   if (options->scaling == 2) { inform->flag = E_UNIMPLEMENTED; return; }
+   if (options->scaling == 3 && A->mo_scaling.empty()) { inform->flag = E_NO_SAVED_SCALING; return; }
    if (*fkeep) { delete static_cast<Fkeep*>(*fkeep); *fkeep = nullptr; }
    Fkeep* F = new (std::nothrow) Fkeep;
    if (!F) { inform->flag = E_ALLOCATION; return; }
@@ -252,7 +270,9 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
       }
    } else {
       std::vector<double> sc(n);
-      if (options->scaling == 1) {     /* hungarian_scale_sym, scale_if_singular = options%action (:927-959) */
+      if (options->scaling == 3) {     /* the scaling saved by the matching-based ordering (:989-997) */
+         sc = A->mo_scaling;
+      } else if (options->scaling == 1) {     /* hungarian_scale_sym, scale_if_singular = options%action (:927-959) */
          int matched = 0;
          int hf = spral_ssids_b200_hungarian_scale_sym(n, A->ptr.data(), A->row.data(), aval, sc.data(), nullptr,
                                                        options->action ? 1 : 0, &matched);

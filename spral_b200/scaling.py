@@ -44,3 +44,16 @@ def equilib_scale_sym(n, ptr, row, val, max_iterations=10, tol=1e-8):
     _lib.load().spral_ssids_b200_equilib_scale_sym(n, ptr.ctypes.data, row.ctypes.data, val.ctypes.data,
                                                    scaling.ctypes.data, max_iterations, tol, C.byref(it))
     return scaling, it.value
+
+
+def match_order_metis(n, ptr, row, val):
+    """(order, scaling, flag): src/match_order.f90:51-208, options%ordering = 2.  order[i] is the 1-based
+    pivot position of variable i+1 (pass it to analyse(order=...)); matched pairs are consecutive."""
+    ptr, row, val = _args(n, ptr, row, val)
+    order = np.zeros(n, dtype=np.int32)
+    scaling = np.empty(n)
+    flag = _lib.load().spral_ssids_b200_match_order_metis(n, ptr.ctypes.data, row.ctypes.data, val.ctypes.data,
+                                                          order.ctypes.data, scaling.ctypes.data)
+    if flag < 0:
+        raise RuntimeError(f"match_order_metis failed with flag {flag}")
+    return order, scaling, flag

@@ -210,13 +210,22 @@ class NumericSubtree:
 # --------------------------------------------------------------------------
 
 class Akeep:
-    def __init__(self, analysis, subtrees):
+    def __init__(self, analysis, subtrees, scaling=None):
         self.analysis, self.subtrees = analysis, subtrees
+        self.scaling = scaling        # akeep%scaling: saved by the matching-based ordering (options%ordering = 2)
 
 
-def analyse(n, ptr, row, order=None, nemin=32, ngpu=1, devices=None, options=None, **kw):
+def analyse(n, ptr, row, order=None, nemin=32, ngpu=1, devices=None, options=None, val=None, ordering=None, **kw):
     """ssids_analyse (src/ssids/ssids.f90:148-389): ordering, symbolic
-    factorisation, subtree partition, one SymbolicSubtree per part."""
+    factorisation, subtree partition, one SymbolicSubtree per part.
+    ordering: None / 1 = METIS (or the user's `order`), 2 / "matching" = matching-based ordering
+    (match_order_metis, needs `val`; its scaling is kept for factor(scaling="matching"))."""
+    saved = None
+    if ordering in (2, "matching"):
+        if val is None:
+            raise ValueError("the matching-based ordering needs the matrix values (SSIDS_ERROR_VAL)")
+        from . import scaling as S
+        order, saved, _ = S.match_order_metis(n, ptr, row, val)
     a = Analysis(n, ptr, row, order=order, nemin=nemin, ngpu=ngpu, **kw)
     devices = devices or list(range(ngpu))
     subtrees = []
@@ -224,7 +233,7 @@ def analyse(n, ptr, row, order=None, nemin=32, ngpu=1, devices=None, options=Non
         loc = int(a.exec_loc[p])
         dev = devices[0] if loc <= 1 else devices[(loc - 2) % len(devices)]
         subtrees.append(SymbolicSubtree(a, p, device=dev, options=options))
-    return Akeep(a, subtrees)
+    return Akeep(a, subtrees, saved)
 
 
 def free_contrib(c):
@@ -264,7 +273,11 @@ def factor(akeep, posdef, val, options=None, scaling=None, device_contrib=True):
     every part in order, handing contribution blocks child part -> parent part."""
     a = akeep.analysis
     sc = None
-    if isinstance(scaling, str):
+    if isinstance(scaling, str) and scaling in ("matching", "saved"):      # options%scaling = 3
+        if akeep.scaling is None:
+            raise ValueError("no scaling saved by analyse (SSIDS_ERROR_NO_SAVED_SCALING)")
+        scaling = akeep.scaling
+    elif isinstance(scaling, str):
         scaling = compute_scaling(a, val, scaling, options)
     if scaling is not None:   # fkeep%scaling(i) = scale(invp(i))  (ssids.f90:921-926)
         sc = np.ascontiguousarray(np.asarray(scaling, dtype=np.float64)[a.invp - 1])

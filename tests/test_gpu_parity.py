@@ -547,14 +547,17 @@ def test_reference_generator_problems():
             ns.close()
 
 
-def _kkt_properties(g, scaling_method, refine_steps=2):
+def _kkt_properties(g, scaling_method, refine_steps=2, ordering=None):
     """KKT matrix [H B^T; B 0] with H SPD and B of full row rank: inertia is exactly (dim H positive,
     rows of B negative) whatever the pivot order -- a size-independent check that needs no oracle."""
     from spral_b200 import ssids as host
     n, ptr, row, val = M.kkt_grid(g)
     m = n - g ** 3
-    ak = sb.analyse(n, ptr, row)
-    s = host.compute_scaling(ak.analysis, val, scaling_method) if scaling_method else None
+    ak = sb.analyse(n, ptr, row, val=val, ordering=ordering)
+    if scaling_method == "matching":
+        s = "matching"                                  # options%scaling = 3: saved by the matching-based ordering
+    else:
+        s = host.compute_scaling(ak.analysis, val, scaling_method) if scaling_method else None
     fk = sb.factor(ak, False, val, scaling=s)
     gi = fk.inform
     assert gi["flag"] == 0, gi
@@ -581,6 +584,13 @@ def test_structured_kkt_inertia_small(method):
     for p in parts:
         p.close()
     assert gi["num_neg"] == r["num_neg"] and gi["matrix_rank"] == r["matrix_rank"]
+
+
+def test_matching_based_ordering_kkt():
+    """options%ordering = 2 + options%scaling = 3 (match_order_metis): the reference CPU engine delays no
+    pivot on this matrix with that ordering (tests/test_scaling.py); inertia, rank, residual here."""
+    gi = _kkt_properties(14, "matching", ordering="matching")
+    print("matching-based ordering: gpu delays", gi["num_delay"], "two-by-two pivots", gi["num_two"])
 
 
 @pytest.mark.timeout(900)
