@@ -55,7 +55,13 @@ void spral_ssids_analyse(bool check, int n, int* order, const int64_t* ptr, cons
 void spral_ssids_analyse_ptr32(bool check, int n, int* order, const int* ptr, const int* row,
       const double* val, void** akeep, const struct spral_ssids_options* options,
       struct spral_ssids_inform* inform);
+void spral_ssids_analyse_coord(int n, int* order, int64_t ne, const int* row, const int* col,
+      const double* val, void** akeep, const struct spral_ssids_options* options,
+      struct spral_ssids_inform* inform);
 void spral_ssids_factor(bool posdef, const int64_t* ptr, const int* row, const double* val,
+      double* scale, void* akeep, void** fkeep, const struct spral_ssids_options* options,
+      struct spral_ssids_inform* inform);
+void spral_ssids_factor_ptr32(bool posdef, const int* ptr, const int* row, const double* val,
       double* scale, void* akeep, void** fkeep, const struct spral_ssids_options* options,
       struct spral_ssids_inform* inform);
 void spral_ssids_solve1(int job, double* x1, void* akeep, void* fkeep,

@@ -13,6 +13,7 @@
  */
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -34,6 +35,7 @@ struct Akeep {
    std::vector<int> row;
    std::vector<int64_t> map_ptr, map;   // cleaned entry k sums user entries map[map_ptr[k]..map_ptr[k+1])
    std::vector<double> mo_scaling;      // scaling found by the matching-based ordering (options%ordering = 2)
+   bool analyse_only = false;           // built with SPRAL_B200_ANALYSE_ONLY: cannot be factorised
    spral_ssids_b200_analysis* an = nullptr;
    spral_ssids_b200_analysis_view v;
    std::vector<void*> symbolic;         // one per part
@@ -65,6 +67,9 @@ spral_ssids_b200_options engine_options(const spral_ssids_options* o) {
 /* Data checking of ssids_analyse(check=true): out-of-range entries are dropped,
  * upper-triangular entries moved to the lower triangle, duplicates summed
  * (clean_cscl_oop, src/matrix_util.f90; counts reported as the reference does). */
+int clean_columns(int n, int64_t ne, int64_t oor, std::vector<std::vector<std::pair<int, int64_t>>>& cols, Akeep& A,
+      spral_ssids_inform* inf);
+
 int clean_matrix(int n, int base, const int64_t* ptr, const int* row, Akeep& A, spral_ssids_inform* inf) {
    int64_t ne = ptr[n] - base;
    std::vector<std::vector<std::pair<int, int64_t>>> cols(n);   // per cleaned column: (row, source index)
@@ -77,6 +82,24 @@ int clean_matrix(int n, int base, const int64_t* ptr, const int* row, Akeep& A, 
          if (i >= j) cols[j].push_back({i, k}); else cols[i].push_back({j, k});
       }
    }
+   return clean_columns(n, ne, oor, cols, A, inf);
+}
+
+/* Coordinate input of ssids_analyse_coord (src/ssids/ssids.f90:392-700; clean_coord, matrix_util.f90):
+ * entries with an index out of range are dropped, upper-triangular ones mirrored, duplicates summed. */
+int clean_coord(int n, int base, int64_t ne, const int* row, const int* col, Akeep& A, spral_ssids_inform* inf) {
+   std::vector<std::vector<std::pair<int, int64_t>>> cols(n);
+   int64_t oor = 0;
+   for (int64_t k = 0; k < ne; ++k) {
+      int i = row[k] - base, j = col[k] - base;
+      if (i < 0 || i >= n || j < 0 || j >= n) { oor++; continue; }
+      if (i >= j) cols[j].push_back({i, k}); else cols[i].push_back({j, k});
+   }
+   return clean_columns(n, ne, oor, cols, A, inf);
+}
+
+int clean_columns(int n, int64_t ne, int64_t oor, std::vector<std::vector<std::pair<int, int64_t>>>& cols, Akeep& A,
+      spral_ssids_inform* inf) {
    if (ne > 0 && oor == ne) return E_A_ALL_OOR;
    int64_t dup = 0;
    int missing = 0;
@@ -104,7 +127,8 @@ int clean_matrix(int n, int base, const int64_t* ptr, const int* row, Akeep& A, 
 }
 
 void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int* row, const double* val,
-      void** akeep, const spral_ssids_options* opt, spral_ssids_inform* inf) {
+      void** akeep, const spral_ssids_options* opt, spral_ssids_inform* inf,
+      int64_t coord_ne = -1, const int* coord_col = nullptr) {
    std::memset(inf, 0, sizeof(*inf));
    if (*akeep) { delete static_cast<Akeep*>(*akeep); *akeep = nullptr; }
    if (n < 0) { inf->flag = E_A_N_OOR; return; }
@@ -114,7 +138,11 @@ void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int
    *akeep = A;
    A->n = n; A->check = check;
    int wflag = OK;
-   if (check) {
+   if (coord_ne >= 0) {                 /* coordinate input: always cleaned; `row` / coord_col are the triplets */
+      A->check = true; check = true;
+      wflag = clean_coord(n, base, coord_ne, row, coord_col, *A, inf);
+      if (wflag < 0) { inf->flag = wflag; return; }
+   } else if (check) {
       wflag = clean_matrix(n, base, ptr, row, *A, inf);
       if (wflag < 0) { inf->flag = wflag; return; }
    } else {
@@ -161,7 +189,12 @@ void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int
    spral_ssids_b200_analysis_get(A->an, &A->v);
    if (order) for (int i = 0; i < n; ++i) order[i] = ord[i] - 1 + base;
    spral_ssids_b200_options eo = engine_options(opt);
-   for (int p = 0; p < A->v.nparts; ++p) {
+   /* SPRAL_B200_ANALYSE_ONLY (test hook): no symbolic subtrees, i.e. no device is touched; such an akeep
+    * can be inspected and freed but not factorised (the CPU test-suite checks data cleaning, orderings
+    * and the analyse-time inform this way) */
+   const bool analyse_only = getenv("SPRAL_B200_ANALYSE_ONLY") != nullptr;
+   A->analyse_only = analyse_only;
+   for (int p = 0; p < A->v.nparts && !analyse_only; ++p) {
       int lo = A->v.contrib_ptr[p] - 1, hi = A->v.contrib_ptr[p + 1] - 1;
       void* s = spral_ssids_gpu_create_symbolic_subtree(0, n, A->v.part[p], A->v.part[p + 1], A->v.sptr,
             A->v.sparent, A->v.rptr, A->v.rlist, A->v.nptr, A->v.nlist, hi - lo, A->v.contrib_dest + lo, &eo);
@@ -236,13 +269,19 @@ void spral_ssids_analyse_ptr32(bool check, int n, int* order, const int* ptr, co
    analyse_common(check, n, order, p64.data(), row, val, akeep, options, inform);
 }
 
+void spral_ssids_analyse_coord(int n, int* order, int64_t ne, const int* row, const int* col, const double* val,
+      void** akeep, const struct spral_ssids_options* options, struct spral_ssids_inform* inform) {
+   if (ne < 0) { std::memset(inform, 0, sizeof(*inform)); inform->flag = E_A_ALL_OOR; return; }
+   analyse_common(true, n, order, nullptr, row, val, akeep, options, inform, ne, col);
+}
+
 void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* val, double* scale,
       void* akeep, void** fkeep, const struct spral_ssids_options* options,
       struct spral_ssids_inform* inform) {
    Akeep* A = static_cast<Akeep*>(akeep);
    if (!A) { inform->flag = E_CALL_SEQUENCE; return; }
    *inform = A->inform;
-   if (A->inform.flag < 0) { inform->flag = E_CALL_SEQUENCE; return; }
+   if (A->inform.flag < 0 || A->analyse_only) { inform->flag = E_CALL_SEQUENCE; return; }
    /* options%scaling (ssids.f90:899-1028): <= 0 user vector, 1 Hungarian (MC64), 4.. equilibration;
     * 3 the scaling of the matching-based ordering (options%ordering = 2); 2 (auction) is not provided */
    if (options->scaling == 2) { inform->flag = E_UNIMPLEMENTED; return; }
@@ -389,6 +428,13 @@ void spral_ssids_alter(const double* d, const void* akeep, void* fkeep, const st
    if (F->posdef) { inform->flag = E_NOT_LDLT; return; }
    if (F->numeric.size() != 1) { inform->flag = E_UNIMPLEMENTED; return; }
    spral_ssids_gpu_subtree_alter_dbl(false, F->numeric[0], d);
+}
+
+/* 32-bit column pointers: the factor phase takes the pattern from akeep, ptr / row are not read
+ * (interfaces/C/ssids.f90: they may be NULL when check = true). */
+void spral_ssids_factor_ptr32(bool posdef, const int*, const int* row, const double* val, double* scale,
+      void* akeep, void** fkeep, const struct spral_ssids_options* options, struct spral_ssids_inform* inform) {
+   spral_ssids_factor(posdef, nullptr, row, val, scale, akeep, fkeep, options, inform);
 }
 
 } /* extern "C" */

@@ -604,3 +604,16 @@ def test_full_size_properties_cfg4():
     assert gi["num_flops"] >= gold["predicted_flops"]
     print(f"cfg4: delays gpu {gi['num_delay']} / reference {gold['num_delay']}, flops gpu {gi['num_flops']:.4g} / "
           f"reference {gold['num_flops']:.4g}")
+
+
+def test_c_api_coordinate_input_orderings_scalings(tmp_path):
+    """tests/c/ssids_capi_coord_check.c: ssids_analyse_coord, options.ordering = 2, options.scaling = 1 / 3 / 4,
+    factor_ptr32 through the reference's C interface."""
+    import subprocess
+    exe = tmp_path / "capi_coord"
+    libdir = os.path.join(ROOT, "spral_b200")
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "ssids_capi_coord_check.c"), "-o", str(exe),
+                           "-L", libdir, "-lspral_ssids_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "CAPI COORD OK" in out.stdout, out.stdout + out.stderr
