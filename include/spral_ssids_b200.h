@@ -282,6 +282,13 @@ void spral_ssids_b200_analysis_get(const struct spral_ssids_b200_analysis*,
 int spral_ssids_b200_hungarian_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,
       double* scaling, int* match, int scale_if_singular, int* matched);
 
+/* auction_scale_sym (src/scaling.f90:269-309; options%scaling = 2): scaling from an approximate matching
+ * found by the auction algorithm.  opts: NULL or {int max_iterations; int max_unchanged[3]; float
+ * min_proportion[3]; float eps_initial;} as auction_options (:33-38).  match[n] (may be NULL): 1-based
+ * column matched to row i, 0 if none.  Returns 0. */
+int spral_ssids_b200_auction_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,
+      double* scaling, int* match, const void* opts, int* matched, int* iterations);
+
 /* match_order_metis (src/match_order.f90:51-208; options%ordering = 2): matching-based ordering.  order[n]:
  * 1-based pivot position of every variable, the two variables of a matched 2-cycle consecutive;
  * scaling[n]: the matching-based scaling (options%scaling = 3 uses it at factor time).  Returns 0, 1

@@ -101,6 +101,7 @@ SYMBOLS = {
     "spral_ssids_b200_hungarian_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "spral_ssids_b200_equilib_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _i, _d, _ip]),
     "spral_ssids_b200_match_order_metis": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "spral_ssids_b200_auction_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _ip, _ip]),
 }
 
 _lib = None

@@ -236,6 +236,97 @@ int spral_ssids_b200_hungarian_scale_sym(int n, const int64_t* ptr, const int* r
    return flag;
 }
 
+/* auction_scale_sym (src/scaling.f90:269-309) -> auction_match (:1481-1586) -> auction_match_core
+ * (:1328-1466), restated line by line: an approximate maximum-product matching by single-column auction
+ * rounds with epsilon scaling; the row / column prices become the scaling after match_postproc
+ * (:1588-1696, square case: the two dual vectors are shifted to the same mean).  opts: max_iterations,
+ * max_unchanged[3], min_proportion[3], eps_initial as auction_options (:33-38; NULL = defaults 30000,
+ * {10,100,100}, {0.90,0,0}, 0.01).  match[i] (may be NULL) = 1-based column matched to row i, 0 if none.
+ * Returns 0. */
+struct spral_ssids_b200_auction_options_ { int max_iterations; int max_unchanged[3]; float min_proportion[3]; float eps_initial; };
+int spral_ssids_b200_auction_scale_sym(int n, const int64_t* ptr, const int* row, const double* val,
+      double* scaling, int* match, const void* opts_in, int* matched_out, int* iterations_out) {
+   spral_ssids_b200_auction_options_ o{30000, {10, 100, 100}, {0.90f, 0.0f, 0.0f}, 0.01f};
+   if (opts_in) o = *static_cast<const spral_ssids_b200_auction_options_*>(opts_in);
+   /* expand, drop explicit zeros, log|a|; cost = maxentry - (cmax - log|a|) */
+   Csc C = expand_log_abs(n, ptr, row, val);
+   std::vector<double> cmax(n, 0.0), rsc(n, 0.0), csc(n, 0.0);
+   double maxentry = -RINF;
+   for (int j = 0; j < n; ++j) {
+      if (C.ptr[j + 1] <= C.ptr[j]) { cmax[j] = 0.0; continue; }
+      double mx = -RINF;
+      for (int64_t e = C.ptr[j]; e < C.ptr[j + 1]; ++e) mx = std::max(mx, C.val[e]);
+      cmax[j] = mx;
+      for (int64_t e = C.ptr[j]; e < C.ptr[j + 1]; ++e) { C.val[e] = mx - C.val[e]; maxentry = std::max(maxentry, C.val[e]); }
+   }
+   if (maxentry == -RINF) maxentry = 0.0;
+   maxentry = 2 * maxentry + 1;               // prefers high-cardinality matchings (+1 avoids zero columns)
+   for (double& x : C.val) x = maxentry - x;
+   for (int j = 0; j < n; ++j) csc[j] = -cmax[j];
+   /* ---- auction_match_core ---- */
+   std::vector<int> cmatch(n, 0), owner(n, -1), next(n);
+   std::vector<double>& dualu = rsc;
+   std::vector<double>& dualv = csc;
+   int unmatched = n, prev = -1, nunchanged = 0, tail = n, itr = 1;
+   for (int i = 0; i < n; ++i) next[i] = i;
+   double eps = o.eps_initial;
+   for (; itr <= o.max_iterations; ++itr) {
+      if (unmatched == 0) break;
+      if (unmatched != prev) nunchanged = 0;
+      prev = unmatched;
+      ++nunchanged;
+      const float prop = (float)(n - unmatched) / (float)n;
+      if (nunchanged >= o.max_unchanged[0] && prop >= o.min_proportion[0]) break;
+      if (nunchanged >= o.max_unchanged[1] && prop >= o.min_proportion[1]) break;
+      if (nunchanged >= o.max_unchanged[2] && prop >= o.min_proportion[2]) break;
+      eps = std::min(1.0, eps + 1.0 / (n + 1));
+      int insert = 0;
+      for (int cp = 0; cp < tail; ++cp) {
+         const int col = next[cp];
+         if (cmatch[col] != 0) continue;                          // matched (> 0) or ineligible (-1)
+         if (C.ptr[col] == C.ptr[col + 1]) continue;              // empty column
+         int64_t e = C.ptr[col];
+         int bestr = C.row[e];
+         double bestu = C.val[e] - dualu[bestr], bestv = -RINF;
+         for (e = C.ptr[col] + 1; e < C.ptr[col + 1]; ++e) {
+            const double u = C.val[e] - dualu[C.row[e]];
+            if (u > bestu) { bestv = bestu; bestr = C.row[e]; bestu = u; }
+            else if (u > bestv) bestv = u;
+         }
+         if (bestv == -RINF) bestv = 0.0;                         // no second best
+         if (bestu > 0) {
+            dualu[bestr] += bestu - bestv + eps;
+            dualv[col] = bestv - eps;
+            cmatch[col] = bestr + 1;
+            --unmatched;
+            const int k = owner[bestr];
+            owner[bestr] = col;
+            if (k >= 0) { cmatch[k] = 0; ++unmatched; next[insert++] = k; }
+         } else {
+            cmatch[col] = -1;                                     // no net benefit: never considered again
+            --unmatched;
+         }
+      }
+      tail = insert;
+   }
+   if (iterations_out) *iterations_out = itr - 1;
+   int matched = 0;
+   for (int j = 0; j < n; ++j) { if (cmatch[j] == -1) cmatch[j] = 0; if (cmatch[j] != 0) ++matched; }
+   if (matched_out) *matched_out = matched;
+   /* undo the pre-processing; match_postproc for a square matrix */
+   for (int i = 0; i < n; ++i) { rsc[i] = -rsc[i] + maxentry; csc[i] = -csc[i] - cmax[i]; }
+   if (match) {
+      for (int i = 0; i < n; ++i) match[i] = 0;
+      for (int j = 0; j < n; ++j) if (cmatch[j] != 0) match[cmatch[j] - 1] = j + 1;
+   }
+   double ravg = 0, cavg = 0;
+   for (int i = 0; i < n; ++i) { ravg += rsc[i]; cavg += csc[i]; }
+   if (n > 0) { ravg /= n; cavg /= n; }
+   const double adjust = (ravg - cavg) / 2;
+   for (int i = 0; i < n; ++i) scaling[i] = std::exp(((rsc[i] - adjust) + (csc[i] + adjust)) / 2);
+   return 0;
+}
+
 /* match_order_metis (src/match_order.f90:51-208): matching-based ordering for options%ordering = 2.
  * The MC64-type matching and scaling (mo_scale / mo_match there; hungarian_scale_sym here, with
  * scale_if_singular), then mo_split (:220-396): the matching is split into 1- and 2-cycles, the matrix

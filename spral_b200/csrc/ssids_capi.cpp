@@ -283,8 +283,7 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
    *inform = A->inform;
    if (A->inform.flag < 0 || A->analyse_only) { inform->flag = E_CALL_SEQUENCE; return; }
    /* options%scaling (ssids.f90:899-1028): <= 0 user vector, 1 Hungarian (MC64), 4.. equilibration;
-    * 3 the scaling of the matching-based ordering (options%ordering = 2); 2 (auction) is not provided */
-   if (options->scaling == 2) { inform->flag = E_UNIMPLEMENTED; return; }
+    * 2 auction, 3 the scaling of the matching-based ordering (options%ordering = 2) */
    if (options->scaling == 3 && A->mo_scaling.empty()) { inform->flag = E_NO_SAVED_SCALING; return; }
    if (*fkeep) { delete static_cast<Fkeep*>(*fkeep); *fkeep = nullptr; }
    Fkeep* F = new (std::nothrow) Fkeep;
@@ -311,6 +310,9 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
       std::vector<double> sc(n);
       if (options->scaling == 3) {     /* the scaling saved by the matching-based ordering (:989-997) */
          sc = A->mo_scaling;
+      } else if (options->scaling == 2) {   /* auction_scale_sym with default auction_options (:961-987) */
+         spral_ssids_b200_auction_scale_sym(n, A->ptr.data(), A->row.data(), aval, sc.data(), nullptr, nullptr,
+                                            nullptr, nullptr);
       } else if (options->scaling == 1) {     /* hungarian_scale_sym, scale_if_singular = options%action (:927-959) */
          int matched = 0;
          int hf = spral_ssids_b200_hungarian_scale_sym(n, A->ptr.data(), A->row.data(), aval, sc.data(), nullptr,

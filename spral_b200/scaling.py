@@ -57,3 +57,16 @@ def match_order_metis(n, ptr, row, val):
     if flag < 0:
         raise RuntimeError(f"match_order_metis failed with flag {flag}")
     return order, scaling, flag
+
+
+def auction_scale_sym(n, ptr, row, val):
+    """(scaling, match, matched, iterations): src/scaling.f90:269-309 with the default auction_options;
+    options%scaling = 2.  An approximate matching: a few rows may stay unmatched (match[i] = 0)."""
+    ptr, row, val = _args(n, ptr, row, val)
+    scaling = np.empty(n)
+    match = np.zeros(n, dtype=np.int32)
+    matched, it = C.c_int(0), C.c_int(0)
+    _lib.load().spral_ssids_b200_auction_scale_sym(n, ptr.ctypes.data, row.ctypes.data, val.ctypes.data,
+                                                   scaling.ctypes.data, match.ctypes.data, None,
+                                                   C.byref(matched), C.byref(it))
+    return scaling, match, matched.value, it.value

@@ -258,6 +258,8 @@ def compute_scaling(analysis, val, method, options=None):
         if flag == S.ERROR_SINGULAR:
             raise ValueError("matrix is structurally singular and options.action is false (SSIDS_ERROR_SINGULAR)")
         return s
+    if method in ("auction", 2):
+        return S.auction_scale_sym(a.n, a.ptr, a.row, val)[0]
     if method in ("equilib", "mc77", 4):
         return S.equilib_scale_sym(a.n, a.ptr, a.row, val)[0]
     raise ValueError(f"unknown scaling {method!r}")

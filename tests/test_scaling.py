@@ -183,3 +183,23 @@ def test_matching_based_ordering_on_singular_and_definite_matrices():
     n, ptr, row, val = _lower_csc(A)
     order, s, flag = S.match_order_metis(n, ptr, row, val)
     assert flag == 1 and sorted(order.tolist()) == list(range(1, n + 1)) and np.all(np.isfinite(s))
+
+
+@pytest.mark.parametrize("n,density,seed", [(40, 0.15, 0), (300, 0.02, 1), (2000, 0.003, 2)])
+def test_auction_scaling(n, density, seed):
+    """auction_scale_sym (src/scaling.f90:269-309): an approximate matching (the reference's tests accept
+    >= 90 % matched, tests/scaling.f90) whose prices scale the entries to O(1)."""
+    rng = np.random.default_rng(seed)
+    A = _random_sym(n, density, rng)
+    nn, ptr, row, val = _lower_csc(A)
+    s, match, matched, it = S.auction_scale_sym(nn, ptr, row, val)
+    assert matched >= 0.9 * n and it >= 1
+    m = match[match > 0]
+    assert len(set(m.tolist())) == len(m) == matched             # a (partial) matching
+    assert np.all(s > 0) and np.all(np.isfinite(s))
+    B = abs(sp.diags(s) @ A @ sp.diags(s)).tocsc()
+    # epsilon-optimal duals: scaled entries are bounded by exp(eps) with eps <= 1
+    assert B.max() <= np.e * (1 + 1e-12)
+    s_h, _, _, _ = S.hungarian_scale_sym(nn, ptr, row, val)
+    Bh = abs(sp.diags(s_h) @ A @ sp.diags(s_h))
+    assert B.max() < 1e3 * Bh.max()
