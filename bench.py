@@ -47,6 +47,31 @@ def make_matrix(grid):
     return M.stencil_3d_27pt(grid, shift=SHIFT)
 
 
+def make_workload(args):
+    """(description, posdef, scaling method or None, (n, ptr, row, val)).  The default -- what the driver
+    measures -- is BASELINE configs[4] (cfg5); the others are the remaining BASELINE configs, for the
+    developer's own runs (`--workload cfg2|cfg3|cfg4`)."""
+    from spral_b200 import matrices as M
+    w = args.workload
+    if w == "cfg5":
+        g = args.grid
+        return (f"ssids_factor 3-D 27-point {g}^3 shifted (sigma={SHIFT}) indefinite, n={g ** 3}, LDL^T u=0.01, "
+                f"METIS order, nemin=32 (BASELINE configs[4])", False, None, make_matrix(g))
+    if w == "cfg3":
+        g = args.grid if args.grid != 100 else 80
+        return (f"ssids_factor 3-D 27-point {g}^3 shifted (sigma={SHIFT}) indefinite, LDL^T u=0.01 (BASELINE configs[2])",
+                False, None, make_matrix(g))
+    if w == "cfg2":
+        g = args.grid if args.grid != 100 else 60
+        return (f"ssids_factor 3-D 7-point Laplacian {g}^3, positive definite LL^T (BASELINE configs[1])", True, None,
+                M.laplacian_3d_7pt(g))
+    if w == "cfg4":
+        g = args.grid if args.grid != 100 else 70
+        return (f"ssids_factor structured KKT saddle point kkt_grid({g}), n={int(round(g ** 3 / 0.7))}, 30% zero-diagonal "
+                f"rows, matching-based scaling (BASELINE configs[3])", False, "hungarian", M.kkt_grid(g))
+    raise SystemExit(f"unknown workload {w}")
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons while the timed region runs (NVML in
     process -- spawning nvidia-smi every 200 ms measurably perturbs the run)."""
@@ -234,6 +259,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=100, help="stencil grid size (BASELINE: 100)")
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg4", "cfg3", "cfg2"],
+                    help="BASELINE config to run (default cfg5 = configs[4], the headline workload)")
     ap.add_argument("--cpu-grid", type=int, default=CPU_SAMPLE_GRID)
     ap.add_argument("--nrhs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -266,13 +293,17 @@ def main():
     lib = _lib.load()
 
     # ---- set-up (untimed): matrix, ordering, symbolic analysis, subtree partition ----
-    n, ptr, row, val = make_matrix(args.grid)
+    wl_desc, posdef, scaling_method, (n, ptr, row, val) = make_workload(args)
     t0 = time.perf_counter()
     ctx = sdist.DistContext(world, rank, local_rank)
     ak = sdist.analyse(ctx, n, ptr, row)
     t_analyse = time.perf_counter() - t0
     a = ak.analysis
     nz = len(val)
+    scaling_vec = None
+    if scaling_method:                  # host pre-processing of options%scaling, untimed like the analyse phase
+        from spral_b200 import ssids as host
+        scaling_vec = host.compute_scaling(a, val, scaling_method)
     hval = torch.from_numpy(val).pin_memory()
     dval = hval.cuda(non_blocking=False)
 
@@ -295,7 +326,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t = time.perf_counter()
         ev0.record()
-        fk = sdist.factor(ctx, ak, False, values_ptr)   # returns when this rank's streams have drained
+        fk = sdist.factor(ctx, ak, posdef, values_ptr, scaling=scaling_vec)   # returns when this rank's streams have drained
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t
@@ -412,8 +443,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_mean,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"ssids_factor 3-D 27-point {args.grid}^3 shifted (sigma={SHIFT}) indefinite, "
-                               f"n={n}, LDL^T u=0.01, METIS order, nemin=32 (BASELINE configs[4])",
+        "config": {"workload": wl_desc,
                    "parallelism": f"subtree-partition x{world}" if world > 1 else "1 GPU",
                    "nparts": int(a.nparts), "l2": "inputs larger than L2 (factor storage %.1f GB)" % (inform["num_factor"] * 8 / 1e9),
                    "timer": "CUDA events: on the factorisation stream (N=1); bracketing each rank's parts, max over ranks (N>1)"},
@@ -432,7 +462,7 @@ def main():
         out["roofline_hbm_parts"] = hbm_rooflines
 
     # ---- CPU baseline: the reference engine on a bounded sample (rank 0, N=1 only) ----
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cfg5":
         try:
             import oracle_ref
             if oracle_ref.available():
