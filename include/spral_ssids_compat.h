@@ -48,10 +48,22 @@ struct spral_ssids_inform {
    char unused[76];
 };
 
+/* layout of the reference struct (include/spral_ssids.h:59-63) */
+struct spral_numa_region {
+   int nproc;
+   int ngpu;
+   int* gpus;
+};
+
 void spral_ssids_default_options(struct spral_ssids_options* options);
 void spral_ssids_analyse(bool check, int n, int* order, const int64_t* ptr, const int* row,
       const double* val, void** akeep, const struct spral_ssids_options* options,
       struct spral_ssids_inform* inform);
+/* the topology is accepted and ignored: this interface drives ONE device (the current one); the
+ * subtree partition over several GPUs is the one-process-per-GPU driver's (spral_b200/dist.py) */
+void spral_ssids_analyse_topology(bool check, int n, int* order, const int64_t* ptr, const int* row,
+      const double* val, void** akeep, const struct spral_ssids_options* options,
+      struct spral_ssids_inform* inform, int nregions, const struct spral_numa_region* regions);
 void spral_ssids_analyse_ptr32(bool check, int n, int* order, const int* ptr, const int* row,
       const double* val, void** akeep, const struct spral_ssids_options* options,
       struct spral_ssids_inform* inform);

@@ -73,7 +73,7 @@ def test_compat_header_symbols_exported_and_layout_matches_reference_sizes():
     (include/spral_ssids.h:15-57: options 176 bytes, inform 152 bytes)."""
     lib = C.CDLL(_lib.LIB_PATH)
     names = [f for f in declared_functions(COMPAT) if f.startswith("spral_ssids_")]
-    assert len(names) == 14        # all of spral_ssids.h except analyse_topology
+    assert len(names) == 15        # every function of spral_ssids.h:70-127
     assert not [f for f in names if not hasattr(lib, f)]
     import subprocess, tempfile
     with tempfile.TemporaryDirectory() as td:
