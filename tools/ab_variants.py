@@ -5,7 +5,7 @@ delays and the solve times.  One table at the end.
 
   python tools/ab_variants.py [grid=100] [reps=3] [variant ...]
   variants: base diag_v2 panel_v2 panel_v2+diag... any '+'-joined combination of
-            diag_v2 panel_v2 bulk_prio ctile12 solve_wide
+            diag_v2 panel_v2 bulk_prio bulk84 ctile8 ctile12 solve_wide
 """
 import json
 import os
@@ -20,10 +20,12 @@ ENV = {
     "panel_v2": {"SPRAL_B200_PANEL_V2": "1"},
     "bulk_prio": {"SPRAL_B200_BULK_PRIO": "1"},
     "ctile12": {"SPRAL_B200_CTILE_BLOCK": "12"},
+    "ctile8": {"SPRAL_B200_CTILE_BLOCK": "8"},       # 16 operand panels of 5.4 MB (K = 5243) stay inside the 126 MB L2
+    "bulk84": {"SPRAL_B200_BULK_CTAS": "84"},        # more SMs left for the panel kernels (PANEL_V2 tiles: 1 CTA / SM)
     "solve_wide": {"SPRAL_B200_SOLVE_WIDE": "1"},
 }
-DEFAULT = ["base", "diag_v2", "bulk_prio", "ctile12", "panel_v2", "panel_v2+bulk_prio", "panel_v2+bulk_prio+ctile12",
-           "solve_wide"]
+DEFAULT = ["base", "diag_v2", "bulk_prio", "ctile8", "ctile12", "panel_v2", "panel_v2+bulk84", "panel_v2+bulk_prio",
+           "panel_v2+bulk_prio+ctile8", "solve_wide"]
 
 
 def child(grid, reps):
