@@ -45,3 +45,53 @@ def test_matrices_without_entries():
     assert a.nnodes == 0 and a.invp.tolist() == [1, 2, 3]
     a = Analysis(0, np.array([1], dtype=np.int64), e)
     assert a.nnodes == 0 and a.flag == 0
+
+
+def _symbolic_cholesky(P):
+    """Brute-force structure of the Cholesky factor of a symmetric 0/1 pattern (dense, right-looking)."""
+    n = P.shape[0]
+    S = P.copy().astype(bool)
+    S[np.arange(n), np.arange(n)] = True
+    for k in range(n):
+        below = np.nonzero(S[k + 1:, k])[0] + k + 1
+        for j in below:
+            S[below[below >= j], j] = True
+    return np.tril(S)
+
+
+def test_row_lists_equal_the_true_fill_pattern():
+    """Independent check of the restated basic_analyse (core_analyse.f90:38-156: etree, column counts,
+    supernodes, row lists): with nemin = 1 only no-fill merges happen, so the row list of a supernode is
+    EXACTLY the structure of L in its first column and num_factor is nnz(L); with nemin = 8 the row
+    lists contain that structure.  The truth comes from a dense brute-force symbolic factorisation of
+    the permuted pattern."""
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        n = int(rng.integers(2, 45))
+        R = sp.random(n, n, density=rng.uniform(0.02, 0.25), random_state=rng)
+        A = sp.tril(R + R.T + sp.eye(n)).tocsc()
+        A.sort_indices()
+        ptr, row = A.indptr.astype(np.int64) + 1, A.indices.astype(np.int32) + 1
+        order = (rng.permutation(n) + 1).astype(np.int32)            # any ordering, not only METIS
+        for nemin in (1, 8):
+            a = Analysis(n, ptr, row, order=order, nemin=nemin)
+            pos = np.empty(n, dtype=np.int64)                        # pivot position (0-based) of each variable
+            pos[a.invp - 1] = np.arange(n)
+            F = (A + A.T).toarray() != 0
+            Pm = np.zeros((n, n), dtype=bool)
+            Pm[np.ix_(pos, pos)] = F
+            L = _symbolic_cholesky(Pm)
+            nn = a.nnodes
+            for i in range(nn):
+                c0, c1 = int(a.sptr[i]) - 1, int(a.sptr[i + 1]) - 1  # 0-based pivot positions [c0, c1)
+                rows = a.rlist[a.rptr[i] - 1:a.rptr[i + 1] - 1] - 1
+                for j in range(c0, c1):
+                    truth = set(np.nonzero(L[:, j])[0].tolist())
+                    mine = set(r for r in rows.tolist() if r >= j)
+                    if nemin == 1:
+                        assert truth == mine, (trial, n, i, j)
+                    else:
+                        assert truth <= mine, (trial, n, i, j)
+            if nemin == 1:
+                assert a.num_factor == int(L.sum())
+            a.close()
