@@ -95,3 +95,32 @@ def test_row_lists_equal_the_true_fill_pattern():
             if nemin == 1:
                 assert a.num_factor == int(L.sum())
             a.close()
+
+
+def test_a_to_l_map_places_every_entry_where_it_belongs():
+    """build_map (src/ssids/anal.F90:1137-1239): entry k of A, at (r, c) in the user's numbering, must land
+    in the node that owns pivot column min(pos r, pos c), at local column = that pivot column and at the
+    row of the node's row list that holds max(pos r, pos c)."""
+    rng = np.random.default_rng(11)
+    for trial in range(30):
+        n = int(rng.integers(2, 70))
+        R = sp.random(n, n, density=rng.uniform(0.02, 0.2), random_state=rng)
+        A = sp.tril(R + R.T + sp.eye(n)).tocsc()
+        A.sort_indices()
+        ptr, row = A.indptr.astype(np.int64) + 1, A.indices.astype(np.int32) + 1
+        for nemin in (1, 16):
+            a = Analysis(n, ptr, row, nemin=nemin)
+            pos = np.empty(n + 1, dtype=np.int64)
+            pos[a.invp] = np.arange(1, n + 1)                        # 1-based pivot position of variable v
+            col_of_entry = np.repeat(np.arange(1, n + 1), np.diff(ptr))
+            nl = a.nlist.reshape(-1, 2)
+            for i in range(a.nnodes):
+                m = int(a.rptr[i + 1] - a.rptr[i])
+                rows = a.rlist[a.rptr[i] - 1:a.rptr[i + 1] - 1]
+                for src, dest in nl[a.nptr[i] - 1:a.nptr[i + 1] - 1]:
+                    lc, lr = (dest - 1) // m, (dest - 1) % m          # local column / row, 0-based
+                    r, c = int(row[src - 1]), int(col_of_entry[src - 1])
+                    pr, pc = int(pos[r]), int(pos[c])
+                    assert int(a.sptr[i]) + lc == min(pr, pc), (trial, i, src)
+                    assert int(rows[lr]) == max(pr, pc), (trial, i, src)
+            a.close()
