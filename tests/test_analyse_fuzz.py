@@ -124,3 +124,44 @@ def test_a_to_l_map_places_every_entry_where_it_belongs():
                     assert int(a.sptr[i]) + lc == min(pr, pc), (trial, i, src)
                     assert int(rows[lr]) == max(pr, pc), (trial, i, src)
             a.close()
+
+
+def test_index_map_oracle_satisfies_the_definitions():
+    """oracle/index_maps.py (what the device-built maps are compared with bit for bit on the GPU) against
+    the definitions: rlist_direct(ii) is the position of the child's row in the parent's row list
+    (gpu/subtree.f90:204-234); level(node) = num_levels - depth(node), roots last, deepest nodes in level 1,
+    nodes of a level in increasing order (gpu/factor.f90:824-879)."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import index_maps
+    from spral_b200 import matrices as M
+    for gen in (lambda: M.stencil_3d_27pt(7, shift=13.0), lambda: M.laplacian_2d_5pt(23), lambda: M.kkt_saddle(600)):
+        n, ptr, row, val = gen()
+        a = Analysis(n, ptr, row, nemin=4)
+        nn, spar, rp, rl, ncol = index_maps.part_view(a.sptr, a.sparent, a.rptr, a.rlist, 1, a.nnodes + 1)
+        rd = index_maps.build_rlist_direct(n, nn, spar, rp, rl, ncol)
+        for node in range(1, nn + 1):
+            par = int(spar[node - 1])
+            for ii in range(int(rp[node - 1]) + int(ncol[node - 1]), int(rp[node])):
+                if par > nn:
+                    assert rd[ii - 1] == -1
+                else:
+                    assert rl[int(rp[par - 1]) + int(rd[ii - 1]) - 2] == rl[ii - 1]
+        nlev, lptr, llist = index_maps.assign_nodes_to_levels(nn, spar)
+        depth = np.zeros(nn + 2, dtype=np.int64)
+        for node in range(nn, 0, -1):                                 # parents have larger indices
+            par = min(int(spar[node - 1]), nn + 1)
+            depth[node] = 0 if par == nn + 1 else depth[par] + 1
+        assert nlev == depth[1:nn + 1].max() + 1
+        assert sorted(llist.tolist()) == list(range(1, nn + 1)) and lptr[0] == 1 and lptr[nlev] == nn + 1
+        for lev in range(1, nlev + 1):
+            nodes = llist[lptr[lev - 1] - 1:lptr[lev] - 1]
+            assert np.all(np.diff(nodes) > 0)
+            assert np.all(depth[nodes] == nlev - lev)
+        cptr, clist = index_maps.build_child_pointers(nn, spar)
+        for node in range(1, nn + 1):
+            kids = clist[cptr[node - 1] - 1:cptr[node] - 1]
+            assert np.all(np.diff(kids) > 0) and all(int(spar[k - 1]) == node for k in kids)
+        a.close()
