@@ -125,6 +125,15 @@ int main() {
              c.m, c.n, c.n0, c.nelim, (int)c.posdef, e1, e4, ok ? "ok" : "FAIL");
       failures += !ok;
    }
+   {  /* several right-hand sides per warp (NRW = 2 and 4) */
+      const Case c{520, 300, 257, 257, false};
+      double e16 = run_case<16, false>(c, rng), e32 = run_case<32, false>(c, rng);
+      const Case cp{333, 300, 280, 270, true};
+      double p32 = run_case<32, true>(cp, rng);
+      bool ok = e16 < 1e-11 && e32 < 1e-11 && p32 < 1e-11;
+      printf("16 / 32 right-hand sides: %.2e %.2e, posdef 32: %.2e %s\n", e16, e32, p32, ok ? "ok" : "FAIL");
+      failures += !ok;
+   }
    printf("solve_wide_emu: %d failures\n", failures);
    return failures ? 1 : 0;
 }
