@@ -147,6 +147,30 @@ int main() {
       printf("roll-back: segments %d %d, front unchanged = %d %s\n", a, b, (int)same, (a == 1 && b == -1 && same) ? "ok" : "FAIL");
       failures += !(a == 1 && b == -1 && same);
    }
+   {  /* a segment that does not start on a tile boundary: 37 columns eliminated by plain 1x1 pivots first
+         (what the step-by-step path leaves behind after a panel with delays), then segments at p = 37, 165 */
+      const int lead = 37, m = 430, n = lead + 256;
+      FrontEmu f = make_front(m, n, rng);
+      for (int j = 0; j < lead; ++j) {
+         const double d = f.L[j + (size_t)j * f.ldl];
+         f.D[2 * j] = 1.0 / d; f.D[2 * j + 1] = 0.0;
+         for (int i = j + 1; i < m; ++i) {
+            f.LD[i + (size_t)j * f.ldl] = f.L[i + (size_t)j * f.ldl];
+            f.L[i + (size_t)j * f.ldl] /= d;
+         }
+         f.L[j + (size_t)j * f.ldl] = 1.0;
+         update(f, j, j + 1, j + 1, n);
+      }
+      f.done = lead;
+      int a = segment<false>(f);                // p = 37
+      update(f, lead, lead + 128, lead + 128, n);
+      int b = segment<false>(f);                // p = 165
+      double err = check(f, n);
+      bool ok = a == 1 && b == 1 && f.done == n && err < 1e-10;
+      printf("unaligned segments (p = 37, 165), m=%d: segments %d %d, |P A P' - L D L'| = %.2e %s\n", m, a, b, err,
+             ok ? "ok" : "FAIL");
+      failures += !ok;
+   }
    for (int m : {384, 470}) {
       /* positive definite: Cholesky segments, no permutation, no D, no backup */
       FrontEmu f = make_front(m, 384, rng);
