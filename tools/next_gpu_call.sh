@@ -1,0 +1,19 @@
+#!/bin/bash
+# First GPU call of the next session (one GPU, ~20 min):
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/next_gpu_call.sh'
+# 1. the GPU tests added without a GPU at hand (scalings, orderings, generators, cfg4, C client for coordinates)
+# 2. the opt-in variants against the default engine (bit for bit / to rounding)
+# 3. the A/B table of the variants on the benchmark problem
+# Everything goes to gpurun_out/ (merged back by gpurun).
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+echo "== new default GPU tests" | tee gpurun_out/next_call.log
+timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "computed_scalings or reference_generator or structured_kkt or matching_based or cfg4 or coordinate" \
+   >> gpurun_out/next_call.log 2>&1
+tail -5 gpurun_out/next_call.log
+echo "== opt-in variants vs default engine" | tee -a gpurun_out/next_call.log
+SPRAL_B200_EXPERIMENTAL_TESTS=1 timeout 1500 python -m pytest tests/test_gpu_experimental.py -q -m gpu >> gpurun_out/next_call.log 2>&1
+tail -8 gpurun_out/next_call.log
+echo "== A/B table (27-pt 100^3)" | tee -a gpurun_out/next_call.log
+timeout 2400 python tools/ab_variants.py 100 2 > gpurun_out/ab_variants.log 2>&1
+tail -16 gpurun_out/ab_variants.log
