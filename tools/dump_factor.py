@@ -12,7 +12,21 @@ sys.path.insert(0, ROOT)
 import spral_b200 as sb                      # noqa: E402
 from spral_b200 import matrices as M         # noqa: E402
 
+def _dense_sym(n, posdef, seed):
+    """One dense front: the whole matrix is the root supernode (exercises the panel kernels alone)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-1, 1, (n, n))
+    A = (A + A.T) / 2
+    if posdef:
+        A = A @ A.T / n + np.eye(n)
+    return M._lower_csc_keep_zeros(sp.csc_matrix(A))
+
+
 CASES = {
+    "dense_600_indef": (lambda: _dense_sym(600, False, 1), False),
+    "dense_391_indef": (lambda: _dense_sym(391, False, 2), False),
+    "dense_500_posdef": (lambda: _dense_sym(500, True, 3), True),
     "stencil27_20_indef": (lambda: M.stencil_3d_27pt(20, shift=13.0), False),
     "stencil27_36_indef": (lambda: M.stencil_3d_27pt(36, shift=13.0), False),
     "lap3d_24_posdef": (lambda: M.laplacian_3d_7pt(24), True),
