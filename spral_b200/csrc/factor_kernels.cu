@@ -33,6 +33,7 @@
 #include <cstdlib>
 #include "engine.h"
 #include "device_utils.cuh"
+#include "pivot_state.h"
 #include "diag_block.h"
 #include "panel_v2.h"
 
@@ -193,47 +194,8 @@ void launch_delays(Front* fronts, const AsmSrc* srcs, const int2* work, int nwor
 /* State machine                                                             */
 /* ------------------------------------------------------------------------ */
 
-/* Accounts the last inner step and opens / closes panels and passes.
- * Executed by ONE thread per front (first thing in k_diag and k_finalize). */
-/* Accounts a speculative segment (panel_v2.h): accepted -> CW more columns are done;
- * given up or rolled back -> the rest of the panel is done step by step. */
-__device__ void account_segment(Front* f) {
-   if (!f->seg_valid) return;
-   if (f->seg_ok && !f->seg_fail) f->done += CW;
-   else { f->spec_off = 1; f->spec_fails++; }
-   f->seg_valid = 0;
-}
-
-__device__ void advance_state(Front* f, bool new_panel) {
-   if (f->finished) return;
-   account_segment(f);
-   if (f->step_valid) {
-      int ne = calc_ne(f);
-      f->done += ne;
-      f->pend -= f->bs - ne;
-      f->step_valid = 0;
-   }
-   if (new_panel && f->panel_open) {
-      f->end -= f->pend0 - f->pend;   // failed columns were swapped to the end
-      f->panel_open = 0;
-   }
-   if (!f->panel_open) {
-      if (f->done == f->end) {
-         if (f->first_pass_done < 0) f->first_pass_done = f->done;
-         if (f->end == f->n) f->finished = 1;
-         else if (f->done > f->pass_start) { f->pass_start = f->done; f->end = f->n; }
-         else f->finished = 1;
-      }
-      if (!f->finished) {
-         f->p0 = f->done;
-         f->pend0 = min(f->done + PW, f->end);
-         f->pend = f->pend0;
-         f->panel_open = 1;
-         f->spec_off = 0;
-      }
-   }
-   if (f->finished) f->nelim = f->done;
-}
+/* advance_state(), account_segment(), snapshot_state(): pivot_state.h (shared with the host model
+ * tests/c/pivot_state_emu.cpp) */
 
 /* ------------------------------------------------------------------------ */
 /* Diagonal block                                                            */
@@ -577,8 +539,7 @@ k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, Facto
    __shared__ int s_go;
    if (threadIdx.x == 0) {
       advance_state(f, new_panel != 0);
-      int go = !f->finished && f->panel_open && !f->spec_off && f->sws != nullptr && !f->step_valid
-               && f->spec_fails < SPEC_MAX_FAILS && (f->pend - f->done >= CW);
+      int go = segment_may_start(f) ? 1 : 0;
       if (go) { f->seg_valid = 1; f->seg_ok = 0; f->seg_fail = 0; }
       s_go = go;
    }
@@ -944,17 +905,7 @@ void launch_swap(Front* fronts, const RowTile* work, int nwork, bool outer, cuda
 __global__ void k_snapshot(Front* fronts, const int* __restrict__ flist, int count, int* __restrict__ snap) {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= count) return;
-   Front* f = &fronts[flist[i]];
-   if (!f->finished) account_segment(f);
-   if (!f->finished && f->step_valid) {
-      int ne = calc_ne(f);
-      f->done += ne;
-      f->pend -= f->bs - ne;
-      f->step_valid = 0;
-   }
-   int* o = snap + (size_t)i * 8;
-   o[0] = f->p0; o[1] = f->done; o[2] = f->pend; o[3] = f->pend0; o[4] = f->end;
-   o[5] = f->finished; o[6] = f->flag; o[7] = f->spec_fails;
+   snapshot_state(&fronts[flist[i]], snap + (size_t)i * 8);
 }
 
 void launch_snapshot(Front* fronts, const int* flist, int count, int* snap, cudaStream_t s) {

@@ -70,3 +70,22 @@ def test_speculative_panel_whole_front_flow():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "panel_v2_front_emu: 0 failures" in r.stdout
+
+
+def test_pivoting_protocol_model_check():
+    """tests/c/pivot_state_emu.cpp: the device state machine (spral_b200/csrc/pivot_state.h, the code the
+    kernels run) against the host mirror of factor_fronts, over thousands of random levels with failed
+    block columns, unsplittable 2x2 pivots, passes, delays and accepted / given-up / rolled-back
+    speculative segments: no divergence, every panel complete, termination, consistent statistics."""
+    import pytest
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "pivot_state_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "pivot_state_emu.cpp")])
+    r = subprocess.run([exe, "6000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " 0 failures" in r.stdout
