@@ -35,10 +35,14 @@ def _worker(rank, world, port, case, q):
         ref.ensure_env()
         from spral_b200 import matrices as M, dist as sdist
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        gen, posdef, nrhs = CASES[case]
+        gen, posdef, nrhs = CASES[case][:3]
         n, ptr, row, val = gen()
+        order = scal = None
+        if len(CASES[case]) > 3 and CASES[case][3] == "matching":   # options%ordering = 2 + options%scaling = 3
+            from spral_b200 import scaling as S
+            order, scal, _ = S.match_order_metis(n, ptr, row, val)
         ctx = sdist.DistContext(world, rank, 0, engine="oracle")
-        ak = sdist.analyse(ctx, n, ptr, row)
+        ak = sdist.analyse(ctx, n, ptr, row, order=order)
         a = ak.analysis
         A = M.to_scipy(n, ptr, row, val)
         rng = np.random.default_rng(11)
@@ -46,7 +50,7 @@ def _worker(rank, world, port, case, q):
         B = np.asfortranarray(A @ X)
         out = {}
         for rep in range(2):                       # twice: epochs / store keys must not collide
-            fk = sdist.factor(ctx, ak, posdef, val)
+            fk = sdist.factor(ctx, ak, posdef, val, scaling=scal)
             inform = sdist.reduce_inform(ctx, fk.inform)
             Xs = sdist.solve(ctx, fk, B)
             out = dict(bwd=float(ref.backward_error(A, Xs, B)), inform=inform, nparts=int(a.nparts),
@@ -57,8 +61,8 @@ def _worker(rank, world, port, case, q):
             sdist.free(fk) if False else None
         # single-process reference on the same analysis
         if rank == 0:
-            parts, r, sc = ref.ref_factor(a, posdef, val)
-            Xr = ref.ref_solve(a, parts, posdef, B)
+            parts, r, sc = ref.ref_factor(a, posdef, val, scaling=scal)
+            Xr = ref.ref_solve(a, parts, posdef, B, sc)
             out["ref_bwd"] = float(ref.backward_error(A, Xr, B))
             out["ref_inform"] = {k: int(r[k]) for k in ("num_neg", "num_two", "num_delay", "num_factor", "matrix_rank")}
             out["maxdiff"] = float(np.abs(Xr - Xs).max() / max(1.0, np.abs(Xr).max()))
@@ -76,13 +80,15 @@ def _cases():
         "st27_indef": (lambda: M.stencil_3d_27pt(12, shift=13.0), False, 3),
         "lap3d_posdef": (lambda: M.laplacian_3d_7pt(12), True, 2),
         "kkt_delays": (lambda: M.kkt_saddle(3000), False, 1),
+        "kkt_grid_matching": (lambda: M.kkt_grid(12), False, 2, "matching"),   # cfg4 in small, across ranks
     }
 
 
 CASES = _cases()
 
 
-@pytest.mark.parametrize("case,world", [("st27_indef", 2), ("lap3d_posdef", 2), ("kkt_delays", 2), ("st27_indef", 3)])
+@pytest.mark.parametrize("case,world", [("st27_indef", 2), ("lap3d_posdef", 2), ("kkt_delays", 2), ("st27_indef", 3),
+                                        ("kkt_grid_matching", 2)])
 def test_two_rank_factor_solve(case, world):
     import torch.multiprocessing as mp
     ctxmp = mp.get_context("spawn")
