@@ -19,8 +19,10 @@ one PROCESS per GPU (torchrun) and
     rows of its ancestors (forward) and the ancestors' solution on those rows
     (backward); the final solution is one all-reduce.
 
-The same driver runs on CPU for the world_size-2 gloo tests with the reference
-CPU engine standing in for the GPU engine and the store carrying the payload.
+The numeric engine is reached through a small adapter (`GpuEngine` below: symbolic
+subtree, factor, solve, contribution hand-over).  The product knows no other engine; the
+world_size-2 gloo tests on CPU inject their own adapter (tests/oracle_engine.py), so the
+host logic of this file is exercised without a GPU and without any engine-specific code here.
 """
 import ctypes as C
 import os
@@ -35,8 +37,39 @@ from ._lib import Contrib, Options
 from .ssids import Analysis, SymbolicSubtree, free_contrib
 
 
+class GpuEngine:
+    """The B200 engine behind the C ABI (the only engine of the product).  An adapter offers:
+    device_ipc (contribution blocks stay on the device and cross ranks by CUDA IPC; otherwise the
+    payload is staged through the rendezvous store), device(local_rank) for the right-hand sides,
+    symbolic / factor / solve / get_contrib / device_ms."""
+    device_ipc = True
+
+    def device(self, local_rank):
+        import torch
+        return torch.device("cuda", local_rank)
+
+    def symbolic(self, analysis, part, local_rank, options):
+        return SymbolicSubtree(analysis, part, device=local_rank, options=options)
+
+    def factor(self, symb, analysis, part, posdef, val, child_contrib, options, scaling):
+        return symb.factor(posdef, val, child_contrib, options, scaling)
+
+    def solve(self, ns, which, X, nrhs, n):
+        getattr(ns, f"solve_{which}")(X.data_ptr(), nrhs, n)
+
+    def get_contrib(self, ns):
+        return ns.get_contrib(device_resident=True)
+
+    def device_ms(self, ns):
+        return float(ns.timings()[1])
+
+
 class DistContext:
-    def __init__(self, world=1, rank=0, local_rank=0, engine="gpu", store=None, tag="ssids"):
+    def __init__(self, world=1, rank=0, local_rank=0, engine=None, store=None, tag="ssids"):
+        if engine is None or engine == "gpu":
+            engine = GpuEngine()
+        elif isinstance(engine, str):
+            raise ValueError(f"unknown engine {engine!r}: the product has the GPU engine only; tests inject an adapter object")
         self.world, self.rank, self.local_rank, self.engine = world, rank, local_rank, engine
         self._store, self.tag, self.epoch = store, tag, 0
         self._stage = {}          # producer part -> (device block, capacity): re-used across factorisations
@@ -155,10 +188,8 @@ def analyse(ctx, n, ptr, row, order=None, nemin=32, options=None, tune_partition
     for p in range(a.nparts):
         if rank_of[p] != ctx.rank:
             subtrees.append(None)
-        elif ctx.engine == "gpu":
-            subtrees.append(SymbolicSubtree(a, p, device=ctx.local_rank, options=options))
         else:
-            subtrees.append(("oracle", p))
+            subtrees.append(ctx.engine.symbolic(a, p, ctx.local_rank, options))
     return DistAkeep(a, subtrees, rank_of, consumer, children)
 
 
@@ -180,7 +211,7 @@ def _contrib_rlist(a, p):
 
 def publish_contrib(ctx, ak, p, ns):
     """Producer side of a cross-rank edge."""
-    if ctx.engine == "gpu":
+    if ctx.engine.device_ipc:
         lib = _lib.load()
         handle = (C.c_ubyte * 64)()
         n, nd, nbytes, blk = C.c_int(), C.c_int(), C.c_int64(), C.c_void_p()
@@ -331,13 +362,8 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
                 cc.append(f.contrib)
         # children[] is ordered by part; the slots contrib_ptr[p].. follow the same order
         t_p1 = time.perf_counter()
-        if ctx.engine == "gpu":
-            ns = ak.subtrees[p].factor(posdef, val, cc, options, sc)
-            st = ns.stats
-        else:
-            import oracle_ref
-            ns = oracle_ref.RefSubtree(a, p, posdef, val, cc, options, sc)
-            st = ns.stats
+        ns = ctx.engine.factor(ak.subtrees[p], a, p, posdef, val, cc, options, sc)
+        st = ns.stats
         numeric[p] = ns
         for c in cc:
             if c.owner == 1:
@@ -352,10 +378,7 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
         t_p2 = time.perf_counter()
         q = ak.consumer[p]
         if q >= 0:
-            if ctx.engine == "gpu":
-                c = ns.get_contrib(device_resident=True)
-            else:
-                c = ns.get_contrib()
+            c = ctx.engine.get_contrib(ns)
             rows = [_contrib_rlist(a, p)]
             if c.ndelay:
                 if c.device >= 0:
@@ -375,12 +398,12 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
         if trace:
             t_p3 = time.perf_counter()
             print(f"[trace r{ctx.rank} e{ctx.epoch}] part {p}: start +{1e3*(t_p0-t_start):.1f} ms, fetch {1e3*(t_p1-t_p0):.1f}, "
-                  f"factor {1e3*(t_p2-t_p1):.1f} (dev {float(ns.timings()[1]) if ctx.engine == 'gpu' else 0:.1f}), "
+                  f"factor {1e3*(t_p2-t_p1):.1f} (dev {ctx.engine.device_ms(ns):.1f}), "
                   f"publish {1e3*(t_p3-t_p2):.1f} ms, flops {st.num_flops:.3g}", file=sys.stderr, flush=True)
 
     mine = [p for p in range(nparts) if ak.rank_of[p] == ctx.rank]
     nthreads = max(1, int(os.environ.get("SPRAL_B200_PART_THREADS", "2")))
-    if ctx.engine != "gpu" or len(mine) <= 1:
+    if not ctx.engine.device_ipc or len(mine) <= 1:
         nthreads = 1
     # independent parts of this rank run concurrently (each on its own stream); tasks are
     # submitted in postorder, so a parent never starts before its children have started
@@ -400,7 +423,7 @@ def reduce_inform(ctx, inform):
     else:
         import torch
         import torch.distributed as dist
-        dev = "cuda" if ctx.engine == "gpu" else "cpu"
+        dev = ctx.engine.device(ctx.local_rank)
         keys_sum = ("num_delay", "num_factor", "num_flops", "num_neg", "num_two", "num_zero",
                     "not_first_pass", "not_second_pass")
         t = torch.tensor([inform[k] for k in keys_sum], dtype=torch.int64, device=dev)
@@ -438,12 +461,7 @@ def free(fk):
 
 def _engine_solve(ctx, ns, which, X, nrhs, n):
     """X: torch tensor (nrhs, n) contiguous == column-major n x nrhs."""
-    if ctx.engine == "gpu":
-        getattr(ns, f"solve_{which}")(X.data_ptr(), nrhs, n)
-    else:
-        f = getattr(__import__("oracle_ref").load(), f"spral_ssids_cpu_subtree_solve_{which}_dbl")
-        rc = f(ns.posdef, ns.h, nrhs, C.c_void_p(X.data_ptr()), n)
-        assert rc == 0
+    ctx.engine.solve(ns, which, X, nrhs, n)
 
 
 def _send(ctx, kind, p, t):
@@ -465,7 +483,7 @@ def solve(ctx, fk, x, job=0):
     import torch
     a = fk.akeep.analysis
     n = a.n
-    dev = torch.device("cuda", ctx.local_rank) if ctx.engine == "gpu" else torch.device("cpu")
+    dev = ctx.engine.device(ctx.local_rank)
     x = np.asarray(x, dtype=np.float64)
     one = x.ndim == 1
     Xh = x.reshape(n, -1)

@@ -2,7 +2,7 @@
 against the reference CPU engine (oracle/_ref).  Not part of the test-suite."""
 import os, sys, time, traceback
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_ref
 oracle_ref.ensure_env()

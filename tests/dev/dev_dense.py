@@ -1,7 +1,7 @@
 """Developer check: dense single-front matrices that force pivot failures."""
 import os, sys, traceback
 import numpy as np, scipy.sparse as sp
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_ref
 oracle_ref.ensure_env()

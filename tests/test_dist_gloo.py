@@ -1,8 +1,8 @@
 """World-size-2 (and 3) gloo tests on CPU of the one-process-per-GPU driver
 (spral_b200/dist.py): part ownership, cross-rank contribution hand-over, the
 solve exchanges and the final all-reduce.  The reference CPU engine stands in
-for the GPU engine (engine="oracle"), so what is tested here is the host logic
-the GPU path shares."""
+for the GPU engine through an injected adapter (tests/oracle_engine.py), so what is
+tested here is the host logic the GPU path shares."""
 import os
 import socket
 import sys
@@ -41,7 +41,8 @@ def _worker(rank, world, port, case, q):
         if len(CASES[case]) > 3 and CASES[case][3] == "matching":   # options%ordering = 2 + options%scaling = 3
             from spral_b200 import scaling as S
             order, scal, _ = S.match_order_metis(n, ptr, row, val)
-        ctx = sdist.DistContext(world, rank, 0, engine="oracle")
+        from oracle_engine import OracleEngine
+        ctx = sdist.DistContext(world, rank, 0, engine=OracleEngine())
         ak = sdist.analyse(ctx, n, ptr, row, order=order)
         a = ak.analysis
         A = M.to_scipy(n, ptr, row, val)

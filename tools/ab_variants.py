@@ -30,12 +30,10 @@ DEFAULT = ["base", "diag_v2", "bulk_prio", "ctile8", "ctile12", "panel_v2", "pan
 
 def child(grid, reps):
     sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import torch
     import spral_b200 as sb
     from spral_b200 import matrices as M, _lib
-    import oracle_ref
     n, ptr, row, val = M.stencil_3d_27pt(grid, shift=13.0)
     ak = sb.analyse(n, ptr, row)
     dval = torch.from_numpy(val).cuda()
@@ -53,7 +51,8 @@ def child(grid, reps):
     ns = fk.numeric[0]
     # the solve entry points take pivot-order vectors; a backward-error check goes through sb.solve
     x = sb.solve(fk, b)
-    be = float(oracle_ref.backward_error(A, x, b))
+    r = A @ x - b                                     # scaled residual of driver/spral_ssids.F90:419-480
+    be = float(np.abs(r).max() / (abs(A).sum(axis=1).max() * np.abs(x).max() + np.abs(b).max()))
     ts = {}
     for nrhs in (1, 32):
         xx = torch.ones(n * nrhs, dtype=torch.float64, device="cuda")
