@@ -249,11 +249,29 @@ class _Fetched:
             self.block = None
 
 
+class PartFailed(Exception):
+    """A part this one depends on ended with an error flag on another rank."""
+
+    def __init__(self, flag):
+        super().__init__(f"a child part failed with flag {flag}")
+        self.flag = flag
+
+
+def publish_failure(ctx, ak, p, flag):
+    """Tells the (remote) consumer of part p that no contribution will come: without it that rank
+    would wait in fetch_contrib until the store times out."""
+    q = ak.consumer[p]
+    if q >= 0 and ak.rank_of[q] != ctx.rank:
+        ctx.store.set(_key(ctx, "contrib", p), pickle.dumps(dict(kind="failed", flag=int(flag))))
+
+
 def fetch_contrib(ctx, ak, p, posdef):
     """Consumer side: waits for part p's block and brings it to this rank."""
     key = _key(ctx, "contrib", p)
     ctx.store.wait([key])
     meta = pickle.loads(ctx.store.get(key))
+    if meta["kind"] == "failed":
+        raise PartFailed(meta["flag"])
     a = ak.analysis
     rl = _contrib_rlist(a, p)
     n, nd = meta["n"], meta["ndelay"]
@@ -350,16 +368,26 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
             if ak.rank_of[c_part] == ctx.rank:
                 futures[c_part].result()
         if failed.is_set():
+            publish_failure(ctx, ak, p, inform["flag"] if inform["flag"] < 0 else -99)
             return
         t_p0 = time.perf_counter()
         cc, fetched = [], []
-        for c_part in ak.children[p]:
-            if ak.rank_of[c_part] == ctx.rank:
-                cc.append(local.pop(c_part))
-            else:
-                f = fetch_contrib(ctx, ak, c_part, posdef)
-                fetched.append(f)
-                cc.append(f.contrib)
+        try:
+            for c_part in ak.children[p]:
+                if ak.rank_of[c_part] == ctx.rank:
+                    cc.append(local.pop(c_part))
+                else:
+                    f = fetch_contrib(ctx, ak, c_part, posdef)
+                    fetched.append(f)
+                    cc.append(f.contrib)
+        except PartFailed as e:                       # the error of another rank's part ends this one too
+            with lock:
+                inform["flag"] = min(inform["flag"], e.flag) if inform["flag"] < 0 else e.flag
+            failed.set()
+            for f in fetched:
+                f.release()
+            publish_failure(ctx, ak, p, e.flag)
+            return
         # children[] is ordered by part; the slots contrib_ptr[p].. follow the same order
         t_p1 = time.perf_counter()
         ns = ctx.engine.factor(ak.subtrees[p], a, p, posdef, val, cc, options, sc)
@@ -374,6 +402,7 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
             _accumulate(inform, st)
         if st.flag < 0:
             failed.set()
+            publish_failure(ctx, ak, p, st.flag)
             return
         t_p2 = time.perf_counter()
         q = ak.consumer[p]

@@ -128,3 +128,48 @@ def test_assign_ranks_every_part_owned_and_roots_on_heaviest_child():
             if int(a.exec_loc[p]) == -1 and children[p]:
                 assert rank_of[p] in {rank_of[c] for c in children[p]}
         a.close()
+
+
+def _worker_failure(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        for p in (ROOT, os.path.join(ROOT, "tests")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import torch.distributed as dist
+        import oracle_ref as ref
+        ref.ensure_env()
+        from datetime import timedelta
+        from spral_b200 import matrices as M, dist as sdist
+        from oracle_engine import OracleEngine
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=60))
+        n, ptr, row, val = M.stencil_3d_27pt(12, shift=13.0)          # indefinite ...
+        ctx = sdist.DistContext(world, rank, 0, engine=OracleEngine())
+        ak = sdist.analyse(ctx, n, ptr, row)
+        fk = sdist.factor(ctx, ak, True, val)                          # ... factorised as positive definite
+        inform = sdist.reduce_inform(ctx, fk.inform)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, dict(flag=int(inform["flag"]), local_flag=int(fk.inform["flag"]), nparts=int(ak.analysis.nparts))))
+    except Exception:          # pragma: no cover
+        import traceback
+        q.put((rank, dict(error=traceback.format_exc())))
+
+
+def test_an_error_in_one_part_reaches_every_rank_without_hanging():
+    """A part that ends with an error flag publishes that instead of its contribution block: the ranks
+    that wait for it stop too (inform%flag = -6 everywhere), nobody sits in the rendezvous store."""
+    import torch.multiprocessing as mp
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctxmp.Process(target=_worker_failure, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r, out in res.items():
+        assert "error" not in out, out.get("error")
+        assert out["flag"] == -6 and out["nparts"] > 1, out
