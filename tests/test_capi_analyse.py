@@ -80,3 +80,49 @@ def test_orderings(capi):
     assert inf.flag == -8
     akeep, opt, inf = _coord(capi, 7, None)
     assert inf.flag == -8                                           # options%ordering out of range
+
+
+def _csc(lib, ptr, row, n, check=True, base=1, order=None, ordering=1):
+    opt, inf = Options(), Inform()
+    lib.spral_ssids_default_options(C.byref(opt))
+    opt.array_base, opt.ordering = base, ordering
+    ptr = np.asarray(ptr, dtype=np.int64)
+    row = np.asarray(row, dtype=np.int32)
+    akeep = C.c_void_p(None)
+    lib.spral_ssids_analyse(check, n, order.ctypes.data if order is not None else None, ptr.ctypes.data,
+                            row.ctypes.data, None, C.byref(akeep), C.byref(opt), C.byref(inf))
+    lib.spral_ssids_free_akeep(C.byref(akeep))
+    return inf
+
+
+def test_csc_data_checking_warnings_and_errors(capi):
+    """The warnings / errors of ssids_analyse(check = true) (src/ssids/datatypes.f90:25-59; the reference's
+    tests/ssids/ssids.f90 test_warnings / test_errors): duplicates (2), out-of-range (1), both (3), missing
+    diagonal (4), missing diagonal with duplicates or out-of-range (5), all out of range (-4), bad ptr (-3),
+    n < 0 (-2)."""
+    # 3 x 3 tridiagonal, lower triangle, 1-based: the clean case
+    inf = _csc(capi, [1, 3, 5, 6], [1, 2, 2, 3, 3], 3)
+    assert inf.flag == 0 and inf.matrix_dup == 0 and inf.matrix_outrange == 0 and inf.matrix_missing_diag == 0
+    assert inf.matrix_rank == 3 and inf.num_factor == 6      # nemin = 32 merges the three columns: dense 3 x 3
+    inf = _csc(capi, [1, 4, 6, 7], [1, 2, 2, 2, 3, 3], 3)                  # (2,1) twice
+    assert inf.flag == 2 and inf.matrix_dup == 1
+    inf = _csc(capi, [1, 4, 6, 7], [1, 2, 9, 2, 3, 3], 3)                  # row 9 out of range
+    assert inf.flag == 1 and inf.matrix_outrange == 1
+    inf = _csc(capi, [1, 5, 7, 8], [1, 2, 2, 9, 2, 3, 3], 3)
+    assert inf.flag == 3 and inf.matrix_dup == 1 and inf.matrix_outrange == 1
+    inf = _csc(capi, [1, 3, 4, 5], [1, 2, 3, 3], 3)                        # (2,2) absent
+    assert inf.flag == 4 and inf.matrix_missing_diag == 1
+    inf = _csc(capi, [1, 4, 5, 6], [1, 2, 2, 3, 3], 3)                     # (2,2) absent and a duplicate
+    assert inf.flag == 5
+    inf = _csc(capi, [1, 3, 5, 6], [7, 8, 9, 7, 8], 3)
+    assert inf.flag == -4
+    inf = _csc(capi, [1, 3, 2, 6], [1, 2, 2, 3, 3], 3)
+    assert inf.flag == -3
+    inf = _csc(capi, [1], [], -1)
+    assert inf.flag == -2
+    # entries given in the UPPER triangle, 0-based: mirrored, same prediction as the clean case
+    inf = _csc(capi, [0, 1, 3, 5], [0, 0, 1, 1, 2], 3, base=0)
+    assert inf.flag == 0 and inf.num_factor == 6
+    # structurally singular (an empty row and column): warning 6 unless data warnings take over
+    inf = _csc(capi, [1, 2, 2, 3], [1, 3], 3, check=False)
+    assert inf.flag == 6 and inf.matrix_rank == 2
