@@ -203,3 +203,35 @@ def test_auction_scaling(n, density, seed):
     s_h, _, _, _ = S.hungarian_scale_sym(nn, ptr, row, val)
     Bh = abs(sp.diags(s_h) @ A @ sp.diags(s_h))
     assert B.max() < 1e3 * Bh.max()
+
+
+def test_fuzz_orderings_and_scalings_on_random_matrices():
+    """Random symmetric patterns with values over 12 orders of magnitude, missing diagonals, structurally
+    singular ones included: every routine returns finite positive scalings, match_order_metis a permutation,
+    and on non-singular matrices the matching scaling keeps |S A S| <= 1."""
+    rng = np.random.default_rng(5)
+    done = singular = 0
+    for trial in range(150):
+        n = int(rng.integers(1, 80))
+        R = sp.random(n, n, density=rng.uniform(0.01, 0.3), random_state=rng,
+                      data_rvs=lambda k: rng.uniform(-1, 1, k) * 10.0 ** rng.integers(-6, 7, k))
+        A = (R + R.T).tolil()
+        for i in range(n):
+            if rng.uniform() < 0.6:
+                A[i, i] = rng.uniform(-2, 2)
+        A = A.tocsc()
+        A.eliminate_zeros()
+        if A.nnz == 0:
+            continue
+        nn, ptr, row, val = _lower_csc(A)
+        order, s, flag = S.match_order_metis(nn, ptr, row, val)
+        assert sorted(order.tolist()) == list(range(1, n + 1))
+        assert np.all(np.isfinite(s)) and np.all(s > 0)
+        if flag == 0:
+            assert abs(sp.diags(s) @ A @ sp.diags(s)).max() <= 1 + 1e-9
+        else:
+            singular += 1
+        for sc in (S.auction_scale_sym(nn, ptr, row, val)[0], S.equilib_scale_sym(nn, ptr, row, val)[0]):
+            assert np.all(np.isfinite(sc)) and np.all(sc > 0)
+        done += 1
+    assert done > 100 and singular > 5
