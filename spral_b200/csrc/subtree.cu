@@ -40,6 +40,7 @@ static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative
 static int g_solve_wide = 0;         // SPRAL_B200_SOLVE_WIDE=1 (experimental, unmeasured): 256-column sweeps (solve_wide.h) on
                                      // levels whose largest front has at least SPRAL_B200_SOLVE_WIDE_MIN (8) 32-column steps
 static int g_solve_wide_min = 8;
+static bool g_trace_panels = false;  // SPRAL_B200_TRACE_PANELS=1: per-panel trace lines on stderr (host time between panels)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS); < 0: one CTA per tile
 static bool g_panel_v2 = false;      // SPRAL_B200_PANEL_V2=1 (experimental, unmeasured): speculative 128-column panel segments
@@ -653,6 +654,19 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          bulk.clear(); bulk_b.clear();
       }
       const bool have_bulk = !bulk.empty() || !bulk_b.empty();
+      if (g_trace_panels) {              /* SPRAL_B200_TRACE_PANELS=1: one line per panel of a level of large fronts */
+         static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+         auto now = std::chrono::steady_clock::now();
+         const HostState& h0 = H[act[0]];
+         int failed_cols = 0;
+         for (int k = 0; k < na_all; ++k) failed_cols += H[act[k]].pend0 - H[act[k]].pend;
+         if (big) fprintf(stderr, "[panel] fronts %d first(m %d n %d p0 %d done %d pend0 %d) failed_cols %d v2 %d steps %d "
+                 "lookahead %d tiles urgent %zu bulk %zu+%zu swap %zu  %.1f us since the previous panel\n",
+                 na_all, h0.m, h0.n, h0.p0, h0.done, h0.pend0, failed_cols, (int)v2, steps_todo, (int)lookahead,
+                 outer.size(), bulk.size(), bulk_b.size(), swap_rows.size(),
+                 std::chrono::duration<double, std::micro>(now - last).count());
+         last = now;
+      }
       if (bulk_pending && (!outer.empty() || !swap_rows.empty())) {
          /* With look-ahead the urgent update only touches the next panel's columns,
           * which the previous bulk update finished first (ev_bulk); a full update or
@@ -719,6 +733,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    CUDA_TRY(cudaSetDevice(S.device));
    if (const char* e = getenv("SPRAL_B200_BULK_PRIO")) g_bulk_prio = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_CTILE_BLOCK")) g_ctile_block = atoi(e);
+   g_trace_panels = getenv("SPRAL_B200_TRACE_PANELS") != nullptr;
    if (const char* e = getenv("SPRAL_B200_PANEL_V2")) g_panel_v2 = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_PANEL_V2_FRONTS")) g_panel_v2_fronts = std::max(1, atoi(e));
    if (g_panel_v2) configure_panel_kernels();
