@@ -17,3 +17,6 @@ tail -8 gpurun_out/next_call.log
 echo "== A/B table (27-pt 100^3)" | tee -a gpurun_out/next_call.log
 timeout 2400 python tools/ab_variants.py 100 2 > gpurun_out/ab_variants.log 2>&1
 tail -16 gpurun_out/ab_variants.log
+echo "== per-panel trace of the default engine (where do the top fronts lose their time?)"
+SPRAL_B200_TRACE=1 SPRAL_B200_TRACE_PANELS=1 timeout 600 python tools/profile_factor.py 100 > gpurun_out/panels_trace.out 2> gpurun_out/panels_trace.log
+grep -c "\[panel\]" gpurun_out/panels_trace.log; grep "\[level" gpurun_out/panels_trace.log | tail -4
