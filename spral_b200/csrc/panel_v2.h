@@ -44,7 +44,7 @@ namespace b200 {
 constexpr int CW = 128;            // segment width (columns per chain / tiles / commit round)
 constexpr int CLD = CW + 1;        // shared-memory column stride (bank = row + column)
 constexpr int CNT = CW;            // threads of the chain kernel: one per row of the diagonal block
-constexpr int PV_YLD = DB_BS + 1;
+constexpr int PV_YLD = DB_BS + 2;   // even: rows stay 16-byte aligned, the broadcast reads of a row vectorise (LDS.128)
 
 /* Per-front workspace of a segment (device global memory). */
 struct SegWS {
