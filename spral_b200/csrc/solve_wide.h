@@ -51,9 +51,10 @@ SW_FN int sw_row_index(const SolveFront& f, int i) {
 }
 
 /* shared memory of the T kernels: xs/vs [SWB * NR], lkk [SSB * SW_LK] doubles */
-/* row stride of the right-hand-side blocks in shared memory: odd, so that threads that own consecutive
- * rows hit different banks also with 32 right-hand sides */
-template <int NR> constexpr int sw_xld() { return NR | 1; }
+/* row stride of the right-hand-side blocks in shared memory: not a multiple of 32 doubles (threads that own
+ * consecutive rows would all hit one bank with 32 right-hand sides) and even, so that a row stays 16-byte
+ * aligned and the broadcast reads of another row's values vectorise */
+template <int NR> constexpr int sw_xld() { return NR == 1 ? 1 : NR + 2; }
 template <int NR> constexpr size_t sw_T_smem_doubles() { return (size_t)SWB * sw_xld<NR>() + (size_t)SSB * SW_LK; }
 /* forward G: ys [SWB * NR] doubles */
 template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)SWB * NR; }
