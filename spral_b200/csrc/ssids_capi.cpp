@@ -71,6 +71,7 @@ int clean_columns(int n, int64_t ne, int64_t oor, std::vector<std::vector<std::p
       spral_ssids_inform* inf);
 
 int clean_matrix(int n, int base, const int64_t* ptr, const int* row, Akeep& A, spral_ssids_inform* inf) {
+   if (ptr[0] < base) return E_A_PTR;          /* ptr(1) < 1 (matrix_util.f90, clean_cscl_oop) */
    int64_t ne = ptr[n] - base;
    std::vector<std::vector<std::pair<int, int64_t>>> cols(n);   // per cleaned column: (row, source index)
    int64_t oor = 0;

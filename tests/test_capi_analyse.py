@@ -126,3 +126,61 @@ def test_csc_data_checking_warnings_and_errors(capi):
     # structurally singular (an empty row and column): warning 6 unless data warnings take over
     inf = _csc(capi, [1, 2, 2, 3], [1, 3], 3, check=False)
     assert inf.flag == 6 and inf.matrix_rank == 2
+
+
+# simple_mat_lower of the reference's tests (tests/ssids/ssids.f90:1475-1510)
+SM_PTR = [1, 4, 5, 7, 8]
+SM_ROW = [1, 2, 4, 2, 3, 4, 4]
+SM_COL = [1, 1, 1, 2, 3, 3, 4]
+
+
+def _analyse_raw(lib, n, ptr, row, ordering, order=None, val=None, check=True, nemin=8):
+    opt, inf = Options(), Inform()
+    lib.spral_ssids_default_options(C.byref(opt))
+    opt.array_base, opt.ordering, opt.nemin = 1, ordering, nemin
+    ptr = np.asarray(ptr, dtype=np.int64)
+    row = np.asarray(row, dtype=np.int32)
+    akeep = C.c_void_p(None)
+    lib.spral_ssids_analyse(check, n, order.ctypes.data if order is not None else None, ptr.ctypes.data,
+                            row.ctypes.data, val.ctypes.data if val is not None else None, C.byref(akeep),
+                            C.byref(opt), C.byref(inf))
+    lib.spral_ssids_free_akeep(C.byref(akeep))
+    return inf.flag
+
+
+def test_the_reference_test_errors_of_analyse(capi):
+    """test_errors of tests/ssids/ssids.f90:140-345, the calls that end inside ssids_analyse /
+    ssids_analyse_coord, with the flags the reference expects."""
+    ident = np.arange(1, 5, dtype=np.int32)
+    assert _analyse_raw(capi, -1, SM_PTR, SM_ROW, 0, ident) == -2                       # n < 0
+    assert _analyse_raw(capi, 4, [0, 4, 5, 7, 8], SM_ROW, 0, ident) == -3               # ptr with zero component
+    assert _analyse_raw(capi, 4, [1, 5, 4, 7, 8], SM_ROW, 0, ident) == -3               # non-monotonic ptr
+    assert _analyse_raw(capi, 4, SM_PTR, [0, 0, 0, 0, 0, 0, 0], 0, ident) == -4         # all of A%row out of range
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, 0, ident, nemin=-1) == 0               # nemin oor -> default, success
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, 0, None) == -8                         # order absent
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, 0, np.array([5, 2, 3, 4], np.int32)) == -8    # out of range above
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, 0, np.array([0, 2, 3, 4], np.int32)) == -8    # out of range below
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, 0, np.array([1, 1, 1, 1], np.int32)) == -8    # not a permutation
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, -1, ident) == -8                       # options%ordering out of range
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, 3, ident) == -8
+    assert _analyse_raw(capi, 4, SM_PTR, SM_ROW, 2, ident) == -9                        # val absent
+    # coordinate form
+    row, col = np.array(SM_ROW, np.int32), np.array(SM_COL, np.int32)
+
+    def coord(n, ne, ordering, order=None):
+        opt, inf = Options(), Inform()
+        capi.spral_ssids_default_options(C.byref(opt))
+        opt.array_base, opt.ordering = 1, ordering
+        akeep = C.c_void_p(None)
+        capi.spral_ssids_analyse_coord(n, order.ctypes.data if order is not None else None, C.c_int64(ne), row.ctypes.data,
+                                       col.ctypes.data, None, C.byref(akeep), C.byref(opt), C.byref(inf))
+        capi.spral_ssids_free_akeep(C.byref(akeep))
+        return inf.flag
+    assert coord(4, 7, 0, np.array([5, 2, 3, 4], np.int32)) == -8
+    assert coord(4, 7, 0, np.array([0, 2, 3, 4], np.int32)) == -8
+    assert coord(4, 7, 25, ident.copy()) == -8
+    assert coord(4, 7, 2, ident.copy()) == -9
+    assert coord(4, 7, 0, None) == -8
+    assert coord(-1, 7, 0, ident.copy()) == -2                                          # n < 0
+    assert coord(4, -1, 0, ident.copy()) == -4                                          # ne < 0
+    assert coord(4, 7, 1) == 0
