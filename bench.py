@@ -369,7 +369,7 @@ def main():
         fk, wall, _ = factor_once(hval.data_ptr())
         e2e_t.append(max_over_ranks(wall))
     e2e_value = flops / float(np.mean(e2e_t)) / 1e9
-    front_bytes = 200 * a.nnodes           # sizeof(Front) per front, read back once per level
+    front_bytes = 192 * a.nnodes           # sizeof(Front) (engine.h) per front, read back once per level
 
     # ---- solves (fkeep%inner_solve): 1 and nrhs right-hand sides ----
     # "device": b and x resident in HBM (CUDA-side permutation, sweeps, un-permutation);

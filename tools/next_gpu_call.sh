@@ -8,7 +8,7 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 echo "== new default GPU tests" | tee gpurun_out/next_call.log
-timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "computed_scalings or reference_generator or structured_kkt or matching_based or cfg4 or coordinate" \
+timeout 1200 python -m pytest tests/test_gpu_widened.py -q -m gpu \
    >> gpurun_out/next_call.log 2>&1
 tail -5 gpurun_out/next_call.log
 echo "== opt-in variants vs default engine" | tee -a gpurun_out/next_call.log
