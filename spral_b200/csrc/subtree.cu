@@ -578,7 +578,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
             PROF(PC_DIAG, launch_panel_chain(d_fronts, d_flist, na_all, posdef, seg == 0, prm, s));
             PROF(PC_APPLY, launch_panel_tiles(d_fronts, d_rows, rows_prefix[na_all], posdef, prm, s));
             PROF(PC_COMMIT, launch_seg_commit(d_fronts, d_rows, rows_prefix[na_all], posdef, s));
-            if (seg + 1 < nseg) PROF(PC_INNER, launch_update(d_fronts, d_inner, inner_prefix[na_all], UPD_SEG, false, s));
+            if (seg + 1 < nseg) PROF(PC_INNER, launch_update(d_fronts, d_inner, inner_prefix[na_all], UPD_SEG, Ti == 128, s));   // the tile size the list was built with
          }
          take_snapshot();
          int maxrem = 0;

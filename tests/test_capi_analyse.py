@@ -28,6 +28,11 @@ class Inform(C.Structure):
                                        "maxsupernode")] + [("unused", C.c_char * 76)]
 
 
+def _p(a):
+    """numpy array -> void* (a bare Python int would be passed as a 32-bit C int: no argtypes on this handle)."""
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
 @pytest.fixture()
 def capi(monkeypatch):
     monkeypatch.setenv("SPRAL_B200_ANALYSE_ONLY", "1")
@@ -46,8 +51,8 @@ def _coord(lib, ordering, val, order=None):
     lib.spral_ssids_default_options(C.byref(opt))
     opt.array_base, opt.ordering = 1, ordering
     akeep = C.c_void_p(None)
-    lib.spral_ssids_analyse_coord(5, order.ctypes.data if order is not None else None, C.c_int64(len(ROW)),
-                                  ROW.ctypes.data, COL.ctypes.data, val.ctypes.data if val is not None else None,
+    lib.spral_ssids_analyse_coord(5, _p(order), C.c_int64(len(ROW)),
+                                  _p(ROW), _p(COL), _p(val),
                                   C.byref(akeep), C.byref(opt), C.byref(inf))
     return akeep, opt, inf
 
@@ -58,7 +63,7 @@ def test_coordinate_input_is_cleaned_like_the_reference(capi):
     assert inf.num_factor == 15 and inf.num_flops == 55 and inf.matrix_rank == 5      # examples/C/ssids.c
     fkeep = C.c_void_p(None)
     inf2 = Inform()
-    capi.spral_ssids_factor(False, None, None, VAL.ctypes.data, None, akeep, C.byref(fkeep), C.byref(opt), C.byref(inf2))
+    capi.spral_ssids_factor(False, None, None, _p(VAL), None, akeep, C.byref(fkeep), C.byref(opt), C.byref(inf2))
     assert inf2.flag == -1                                          # analyse-only akeep: call sequence error
     assert capi.spral_ssids_free_akeep(C.byref(akeep)) == 0
 
@@ -89,8 +94,8 @@ def _csc(lib, ptr, row, n, check=True, base=1, order=None, ordering=1):
     ptr = np.asarray(ptr, dtype=np.int64)
     row = np.asarray(row, dtype=np.int32)
     akeep = C.c_void_p(None)
-    lib.spral_ssids_analyse(check, n, order.ctypes.data if order is not None else None, ptr.ctypes.data,
-                            row.ctypes.data, None, C.byref(akeep), C.byref(opt), C.byref(inf))
+    lib.spral_ssids_analyse(check, n, _p(order), _p(ptr),
+                            _p(row), None, C.byref(akeep), C.byref(opt), C.byref(inf))
     lib.spral_ssids_free_akeep(C.byref(akeep))
     return inf
 
@@ -141,8 +146,8 @@ def _analyse_raw(lib, n, ptr, row, ordering, order=None, val=None, check=True, n
     ptr = np.asarray(ptr, dtype=np.int64)
     row = np.asarray(row, dtype=np.int32)
     akeep = C.c_void_p(None)
-    lib.spral_ssids_analyse(check, n, order.ctypes.data if order is not None else None, ptr.ctypes.data,
-                            row.ctypes.data, val.ctypes.data if val is not None else None, C.byref(akeep),
+    lib.spral_ssids_analyse(check, n, _p(order), _p(ptr),
+                            _p(row), _p(val), C.byref(akeep),
                             C.byref(opt), C.byref(inf))
     lib.spral_ssids_free_akeep(C.byref(akeep))
     return inf.flag
@@ -172,8 +177,8 @@ def test_the_reference_test_errors_of_analyse(capi):
         capi.spral_ssids_default_options(C.byref(opt))
         opt.array_base, opt.ordering = 1, ordering
         akeep = C.c_void_p(None)
-        capi.spral_ssids_analyse_coord(n, order.ctypes.data if order is not None else None, C.c_int64(ne), row.ctypes.data,
-                                       col.ctypes.data, None, C.byref(akeep), C.byref(opt), C.byref(inf))
+        capi.spral_ssids_analyse_coord(n, _p(order), C.c_int64(ne), _p(row),
+                                       _p(col), None, C.byref(akeep), C.byref(opt), C.byref(inf))
         capi.spral_ssids_free_akeep(C.byref(akeep))
         return inf.flag
     assert coord(4, 7, 0, np.array([5, 2, 3, 4], np.int32)) == -8
