@@ -89,3 +89,23 @@ def test_pivoting_protocol_model_check():
     r = subprocess.run([exe, "6000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " 0 failures" in r.stdout
+
+
+def test_two_stream_lookahead_schedule_model_check():
+    """tests/c/lookahead_race_emu.cpp: factor_fronts' two-stream schedule (panel kernels on the main stream, look-ahead
+    bulk updates on the second, ordered only by the per-panel host sync and the ev_bulk / ev_bulk_all waits) restated
+    launch for launch on the shared state machine, every launch with the footprint of the real kernel: no unordered
+    pair of launches conflicts, every column has every update when its block is factorised -- with and without the
+    speculative segments, with failed block columns, passes and delays; four injected faults must be detected."""
+    import pytest
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "lookahead_race_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "lookahead_race_emu.cpp")])
+    r = subprocess.run([exe, "4000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " 0 failures" in r.stdout and "detected in 0 " not in r.stdout and "/ 0 (" not in r.stdout, r.stdout
