@@ -109,3 +109,22 @@ def test_two_stream_lookahead_schedule_model_check():
     r = subprocess.run([exe, "4000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " 0 failures" in r.stdout and "detected in 0 " not in r.stdout and "/ 0 (" not in r.stdout, r.stdout
+
+
+def test_distributed_top_front_protocol_model_check():
+    """tests/c/dist_front_emu.cpp: the protocol PLANNED for splitting a top front between an owner and a helper GPU
+    (not built yet): flags, panel buffers with back-pressure, blocks coming back just in time, draining
+    on the first failed pivot.  No deadlock, no unordered conflicting pair over the three streams, every column fully
+    updated; four injected protocol faults must be detected."""
+    import pytest
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "dist_front_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "dist_front_emu.cpp")])
+    r = subprocess.run([exe, "1500"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " 0 failures" in r.stdout and "detected in 0 " not in r.stdout and "/ 0 (" not in r.stdout, r.stdout
