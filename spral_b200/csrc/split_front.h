@@ -1,0 +1,276 @@
+/* Distributed top front, first version ("bulk offload"): the owner of a large front keeps
+ * the open panel and the next one, a helper GPU of the same box holds a mirror of the columns further right
+ * and applies every trailing update to them.
+ *
+ * STATUS: compiled only with -DSPRAL_B200_SPLIT (the default build does not contain a line of it) and NOT
+ * YET RUN ON GPUS.  The protocol it implements is the one tests/c/dist_front_emu.cpp model-checks (no
+ * deadlock, no unordered conflicting accesses, complete updates), in its host-driven form: no kernel ever
+ * spins.  The two processes talk through a POSIX shared-memory segment; a flag is raised from a
+ * cudaLaunchHostFunc callback behind the copy / update it announces and polled by the other host with a
+ * time-out.
+ *
+ *   owner                                              helper (spral_ssids_b200_split_helper_serve)
+ *   begin_front : geometry -> shm, phase 1             allocates the mirror (L and L*D, full shape of the
+ *                 waits phase 2, maps the mirror,       front), publishes its IPC handles, phase 2
+ *                 copies the far columns (>= 2 blocks)
+ *   per panel k without a failed pivot:
+ *     need_block(k+1): waits updated[k+1], copies       waits ready[k]; UPD_EXPLICIT of block k+2 with panel k
+ *                 block k+1 back, then the urgent       (the kernel of the look-ahead bulk update, against a
+ *                 update of block k+1 (as today)        Front descriptor that points at the mirror), raises
+ *     push_panel(k): L, L*D of panel k, rows of the     updated[k+2]; then the blocks > k+2
+ *                 far blocks, into the mirror; ready[k]
+ *   first failed pivot -> drain(k): ready[k] = DRAIN,   drains its stream, raises drained
+ *                 waits drained, copies every far column back and carries on alone
+ *   end_front   : phase 3                               releases the mirror, waits for the next front
+ *
+ * Included by subtree.cu inside namespace b200 (needs CUDA_TRY, g_pool, Front, launch_update). */
+#pragma once
+#ifdef SPRAL_B200_SPLIT
+/* (system headers: subtree.cu includes <fcntl.h> <sys/mman.h> <sys/stat.h> <unistd.h> <thread> <string> at file scope) */
+
+constexpr int SPLIT_MAXP = 512;          // panels of PW columns per front (n <= 131 072)
+constexpr int SPLIT_DRAIN = 2;
+constexpr int SPLIT_MAGIC = 0x5b200;
+
+struct SplitShm {
+   std::atomic<int> magic;
+   std::atomic<int> phase;               // 0 idle (helper), 1 front published (owner), 2 helper ready, 3 front done (owner;
+                                         // the helper answers 3 -> 0 when it has released the mirror), 4 exit (owner)
+   std::atomic<int> error;               // raised by either side: the other gives up
+   int m, n, ldl, ld_is_l;               // geometry of the front; ld_is_l: positive definite (L*D == L)
+   unsigned char h_L[64], h_LD[64];      // IPC handles of the helper's mirror
+   std::atomic<int> ready[SPLIT_MAXP + 4];   // panel k is in the mirror (1) / the split ends here (SPLIT_DRAIN)
+   int k0[SPLIT_MAXP + 4], k1[SPLIT_MAXP + 4];   // its columns
+   std::atomic<int> updated[SPLIT_MAXP + 4]; // block J of the mirror has every update the helper owes it
+   std::atomic<int> drained;
+};
+
+static inline int split_block(int j) { return j * PW; }
+
+struct SplitFlagSet { std::atomic<int>* p; int v; };
+static void CUDART_CB split_set_flag(void* arg) {
+   auto* f = static_cast<SplitFlagSet*>(arg);
+   f->p->store(f->v, std::memory_order_release);
+   delete f;
+}
+static inline void split_raise_behind(cudaStream_t s, std::atomic<int>* p, int v) {
+   CUDA_TRY(cudaLaunchHostFunc(s, split_set_flag, new SplitFlagSet{p, v}));
+}
+/* Polls until pred() or the time-out; false on time-out or when the other side raised `error`. */
+template <class Pred>
+static bool split_wait(SplitShm* sh, double timeout_s, Pred pred) {
+   auto t0 = std::chrono::steady_clock::now();
+   for (long it = 0;; ++it) {
+      if (pred()) return true;
+      if (sh && sh->error.load(std::memory_order_acquire)) return false;
+      if ((it & 1023) == 1023) {
+         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) return false;
+         std::this_thread::yield();
+      }
+   }
+}
+static SplitShm* split_map(const char* name, bool create) {
+   int fd = shm_open(name, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+   if (fd < 0) return nullptr;
+   if (create && ftruncate(fd, sizeof(SplitShm)) != 0) { close(fd); return nullptr; }
+   struct stat st;
+   if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(SplitShm)) { close(fd); return nullptr; }
+   void* p = mmap(nullptr, sizeof(SplitShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+   close(fd);
+   return p == MAP_FAILED ? nullptr : static_cast<SplitShm*>(p);
+}
+
+/* ---- owner side ---------------------------------------------------------------------------------------- */
+struct SplitOwner {
+   SplitShm* sh = nullptr;
+   std::string name;
+   double timeout_s = 20.0;
+   bool active = false;                  // a front is split right now
+   bool dead = false;                    // no helper answered: do not try again
+   const Front* f = nullptr;             // host copy of its descriptor (owner's pointers)
+   double* mL = nullptr; double* mLD = nullptr;    // the helper's mirror, mapped here
+   std::vector<std::pair<std::vector<unsigned char>, void*>> opened;
+
+   static SplitOwner* create(const char* shm_name) {
+      shm_unlink(shm_name);
+      SplitShm* sh = split_map(shm_name, true);
+      if (!sh) return nullptr;
+      std::memset((void*)sh, 0, sizeof(SplitShm));
+      sh->magic.store(SPLIT_MAGIC, std::memory_order_release);
+      auto* o = new SplitOwner;
+      o->sh = sh; o->name = shm_name;
+      if (const char* e = getenv("SPRAL_B200_SPLIT_TIMEOUT")) o->timeout_s = atof(e);
+      return o;
+   }
+   ~SplitOwner() {
+      if (sh) { sh->phase.store(4, std::memory_order_release); munmap((void*)sh, sizeof(SplitShm)); shm_unlink(name.c_str()); }
+      for (auto& o : opened) cudaIpcCloseMemHandle(o.second);
+   }
+   void* open_handle(const unsigned char* h) {
+      for (auto& o : opened) if (std::memcmp(o.first.data(), h, 64) == 0) return o.second;
+      cudaIpcMemHandle_t hh; std::memcpy(&hh, h, sizeof(hh));
+      void* p = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&p, hh, cudaIpcMemLazyEnablePeerAccess));
+      opened.push_back({std::vector<unsigned char>(h, h + 64), p});
+      return p;
+   }
+   /* Worth splitting: at least four blocks.  Returns false (and leaves the front alone) when no helper answers. */
+   bool begin_front(const Front& fr, bool posdef, cudaStream_t s) {
+      if (active || dead || fr.n < 4 * PW || (fr.n + PW - 1) / PW > SPLIT_MAXP) return false;
+      /* the helper has released the previous front (3 -> 0) */
+      if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 0; })) { dead = true; return false; }
+      for (int k = 0; k < SPLIT_MAXP + 4; ++k) { sh->ready[k].store(0); sh->updated[k].store(0); }
+      sh->drained.store(0);
+      sh->m = fr.m; sh->n = fr.n; sh->ldl = fr.ldl; sh->ld_is_l = posdef ? 1 : 0;
+      sh->phase.store(1, std::memory_order_release);
+      if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 2; })) {
+         sh->phase.store(3, std::memory_order_release);       // nobody there: the front stays whole
+         dead = true;
+         return false;
+      }
+      mL = static_cast<double*>(open_handle(sh->h_L));
+      mLD = posdef ? mL : static_cast<double*>(open_handle(sh->h_LD));
+      f = &fr;
+      /* the far columns (blocks >= 2), rows from the first of them down */
+      const int c0 = split_block(2);
+      const size_t off = (size_t)c0 + (size_t)c0 * fr.ldl;
+      CUDA_TRY(cudaMemcpy2DAsync(mL + off, (size_t)fr.ldl * sizeof(double), fr.L + off, (size_t)fr.ldl * sizeof(double),
+                                 (size_t)(fr.m - c0) * sizeof(double), fr.n - c0, cudaMemcpyDefault, s));
+      active = true;
+      return true;
+   }
+   bool has_far(int k) const { return split_block(k + 2) < f->n; }
+   /* Panel k = columns [k0, k1): rows of the far blocks into the mirror, then ready[k] (copy stream). */
+   void push_panel(int k, int k0, int k1, cudaStream_t s2) {
+      const int r0 = split_block(k + 2);
+      const size_t off = (size_t)r0 + (size_t)k0 * f->ldl;
+      const size_t pitch = (size_t)f->ldl * sizeof(double), width = (size_t)(f->m - r0) * sizeof(double);
+      CUDA_TRY(cudaMemcpy2DAsync(mL + off, pitch, f->L + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
+      if (mLD != mL) CUDA_TRY(cudaMemcpy2DAsync(mLD + off, pitch, f->LD + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
+      sh->k0[k] = k0; sh->k1[k] = k1;
+      split_raise_behind(s2, &sh->ready[k], 1);
+   }
+   /* Block J comes back (main stream), in order before the urgent update that touches it. */
+   void need_block(int J, cudaStream_t s) {
+      if (J < 2 || split_block(J) >= f->n) return;
+      if (!split_wait(sh, timeout_s, [&] { return sh->updated[J].load(std::memory_order_acquire) != 0; })) {
+         sh->error.store(1, std::memory_order_release);
+         throw std::runtime_error("split front: the helper did not return a block in time");
+      }
+      const int c0 = split_block(J), c1 = std::min(split_block(J + 1), f->n);
+      const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
+      CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), mL + off, (size_t)f->ldl * sizeof(double),
+                                 (size_t)(f->m - c0) * sizeof(double), c1 - c0, cudaMemcpyDefault, s));
+   }
+   /* The split ends at panel k (failed pivot, or nothing is left on the helper): every column the helper
+    * still holds -- blocks >= first_block -- comes back; the helper has applied panels 0 .. k-1 to them. */
+   void drain(int k, int first_block, cudaStream_t s, cudaStream_t s2) {
+      CUDA_TRY(cudaStreamSynchronize(s2));                     // every pushed panel has been announced
+      sh->ready[k].store(SPLIT_DRAIN, std::memory_order_release);
+      if (!split_wait(sh, timeout_s, [&] { return sh->drained.load(std::memory_order_acquire) != 0; })) {
+         sh->error.store(1, std::memory_order_release);
+         throw std::runtime_error("split front: the helper did not drain in time");
+      }
+      const int c0 = split_block(std::max(2, first_block));
+      if (c0 < f->n) {
+         const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
+         CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), mL + off, (size_t)f->ldl * sizeof(double),
+                                    (size_t)(f->m - c0) * sizeof(double), f->n - c0, cudaMemcpyDefault, s));
+      }
+      end_front(s);
+   }
+   void end_front(cudaStream_t s) {
+      CUDA_TRY(cudaStreamSynchronize(s));                      // the copies out of the mirror are done
+      sh->phase.store(3, std::memory_order_release);
+      active = false; f = nullptr;
+   }
+};
+
+/* ---- helper side --------------------------------------------------------------------------------------- */
+static int split_helper_serve(const char* shm_name, int device, double timeout_s) {
+   CUDA_TRY(cudaSetDevice(device));
+   SplitShm* sh = nullptr;
+   if (!split_wait(nullptr, timeout_s, [&] { sh = split_map(shm_name, false); return sh != nullptr; })) return 1;   // no owner showed up
+   if (!split_wait(sh, timeout_s, [&] { return sh->magic.load(std::memory_order_acquire) == SPLIT_MAGIC; })) return 1;
+   cudaStream_t s = nullptr;
+   CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+   configure_update_kernels();
+   int fronts_served = 0;
+   for (;;) {
+      int ph = 0;
+      if (!split_wait(sh, timeout_s, [&] { ph = sh->phase.load(std::memory_order_acquire); return ph == 1 || ph == 4; })) break;
+      if (ph == 4) break;
+      const int m = sh->m, n = sh->n, ldl = sh->ldl;
+      const bool ld_is_l = sh->ld_is_l != 0;
+      const size_t bytes = (size_t)ldl * n * sizeof(double);
+      double* mL = (double*)g_pool.alloc(bytes);
+      double* mLD = ld_is_l ? mL : (double*)g_pool.alloc(bytes);
+      cudaIpcMemHandle_t h;
+      CUDA_TRY(cudaIpcGetMemHandle(&h, mL)); std::memcpy(sh->h_L, &h, 64);
+      if (!ld_is_l) { CUDA_TRY(cudaIpcGetMemHandle(&h, mLD)); std::memcpy(sh->h_LD, &h, 64); }
+      /* descriptor of the mirror for the update kernel (explicit regions: only L, LD, ldl, m, n are read) */
+      Front hf;
+      std::memset(&hf, 0, sizeof(hf));
+      hf.L = mL; hf.LD = mLD; hf.ldl = ldl; hf.m = m; hf.n = n;
+      Front* d_front = (Front*)g_pool.alloc(sizeof(Front));
+      CUDA_TRY(cudaMemcpyAsync(d_front, &hf, sizeof(Front), cudaMemcpyHostToDevice, s));
+      /* tile lists and regions of every panel, built up front (no failed pivot: panel k == block k) */
+      const int T = update_tile_size(true), mt = (m + T - 1) / T, nblk = (n + PW - 1) / PW;
+      std::vector<MatTile> tiles;
+      std::vector<int4> regs(nblk);
+      std::vector<size_t> first(nblk + 1, 0), split_at(nblk, 0);
+      for (int k = 0; k < nblk; ++k) {
+         first[k] = tiles.size();
+         for (int J = k + 2; split_block(J) < n; ++J) {
+            if (J == k + 3) split_at[k] = tiles.size() - first[k];
+            const int tj0 = split_block(J) / T, tj1 = (std::min(split_block(J + 1), n) - 1) / T;
+            for (int tj = tj0; tj <= tj1; ++tj)
+               for (int ti = tj; ti < mt; ++ti) tiles.push_back({k, ti, tj});
+         }
+         if (split_block(k + 3) >= n) split_at[k] = tiles.size() - first[k];      // block k+2 is the only (or no) far block
+      }
+      first[nblk] = tiles.size();
+      MatTile* d_tiles = (MatTile*)g_pool.alloc(std::max<size_t>(tiles.size(), 1) * sizeof(MatTile));
+      int4* d_regs = (int4*)g_pool.alloc((size_t)nblk * sizeof(int4));
+      if (!tiles.empty()) CUDA_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(MatTile), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      sh->phase.store(2, std::memory_order_release);
+
+      bool ok = true;
+      for (int k = 0; k < nblk && ok; ++k) {
+         int r = 0;
+         ok = split_wait(sh, timeout_s, [&] {
+            r = sh->ready[k].load(std::memory_order_acquire);
+            return r != 0 || sh->phase.load(std::memory_order_acquire) >= 3; });
+         if (!ok || r == 0) break;                                 // time-out, or the owner closed the front
+         if (r == SPLIT_DRAIN) {
+            CUDA_TRY(cudaStreamSynchronize(s));
+            sh->drained.store(1, std::memory_order_release);
+            break;
+         }
+         /* the panel columns the owner announced; the region table entry is uploaded now (pageable, 16 bytes) */
+         regs[k] = make_int4(0, sh->k0[k], sh->k1[k], split_block(k + 2));
+         CUDA_TRY(cudaMemcpyAsync(d_regs + k, &regs[k], sizeof(int4), cudaMemcpyHostToDevice, s));
+         const size_t nt_all = first[k + 1] - first[k], nt_a = split_at[k];
+         if (nt_a) launch_update(d_front, d_tiles + first[k], (int)nt_a, UPD_EXPLICIT, true, s, 0, d_regs);
+         split_raise_behind(s, &sh->updated[k + 2], 1);            // block k+2 may go back
+         if (nt_all > nt_a) launch_update(d_front, d_tiles + first[k] + nt_a, (int)(nt_all - nt_a), UPD_EXPLICIT, true, s, 0, d_regs);
+      }
+      if (!ok) sh->error.store(2, std::memory_order_release);
+      /* the owner reads the mirror until it closes the front */
+      split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) >= 3; });
+      CUDA_TRY(cudaStreamSynchronize(s));
+      g_pool.release(d_regs); g_pool.release(d_tiles); g_pool.release(d_front);
+      if (!ld_is_l) g_pool.release(mLD);
+      g_pool.release(mL);
+      ++fronts_served;
+      if (!ok) break;
+      { int expect = 3; sh->phase.compare_exchange_strong(expect, 0, std::memory_order_acq_rel); }   // (4 stays 4)
+      /* phase 3 -> wait for the next front (phase 1 again) or the end (phase 4) */
+      if (!split_wait(sh, timeout_s, [&] { int p = sh->phase.load(std::memory_order_acquire); return p == 1 || p == 4; })) break;
+   }
+   cudaStreamDestroy(s);
+   munmap((void*)sh, sizeof(SplitShm));
+   return fronts_served > 0 ? 0 : 2;
+}
+#endif /* SPRAL_B200_SPLIT */

@@ -29,6 +29,14 @@
 #include <stdexcept>
 #include <vector>
 #include <nvtx3/nvToolsExt.h>
+#ifdef SPRAL_B200_SPLIT              /* distributed top front (split_front.h): opt-in build, not run on GPUs yet */
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <string>
+#include <thread>
+#endif
 #include "engine.h"
 
 namespace b200 {
@@ -169,6 +177,8 @@ struct Bump {
    }
 };
 
+#include "split_front.h"      /* empty unless built with -DSPRAL_B200_SPLIT */
+
 /* ------------------------------------------------------------------------ */
 /* Symbolic subtree                                                          */
 /* ------------------------------------------------------------------------ */
@@ -203,6 +213,9 @@ struct Symbolic {
    Buf b_export;                      // packed contribution block handed to another process (IPC)
    Buf b_bulk[2];                     // tile lists of the look-ahead bulk updates (alternating panels)
    Buf b_segws;                       // chain workspaces of the speculative panel segments (panel_v2.h)
+#ifdef SPRAL_B200_SPLIT
+   std::string split_shm;             // shared-memory name of the split protocol (set for the root part only)
+#endif
 
    ~Symbolic() {
       cudaSetDevice(device);
@@ -382,9 +395,15 @@ struct Numeric {
    int n_launch = 0;
 
    int device = 0;                     // copy of S->device: the symbolic object may die first
+#ifdef SPRAL_B200_SPLIT
+   SplitOwner* split = nullptr;
+#endif
    ~Numeric() {
       if (!S) return;
       cudaSetDevice(device);
+#ifdef SPRAL_B200_SPLIT
+      delete split;
+#endif
       if (stream) cudaStreamSynchronize(stream);
       if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
       for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -616,6 +635,17 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          if (sn[6] >= 0 && H[act[k]].pend0 - sn[2] > 0) any_fail = true;
       }
       const bool lookahead = big && !any_fail && g_lookahead;
+#ifdef SPRAL_B200_SPLIT
+      /* distributed top front (split_front.h; protocol: tests/c/dist_front_emu.cpp): while the split is active the far
+       * columns live on the helper; the first panel with a failed pivot brings them back and ends it */
+      bool split_now = false;
+      int split_k = 0;
+      if (N.split && N.split->active) {
+         split_k = H[act[0]].p0 / PW;
+         if (any_fail || !lookahead || na_all != 1 || H[act[0]].p0 % PW != 0) N.split->drain(split_k, split_k + 1, s, N.stream2);
+         else split_now = true;
+      }
+#endif
       for (int k = 0; k < na_all; ++k) {
          HostState& h = H[act[k]];
          const int* sn = &snap_host[(size_t)k * 8];   // p0, done, pend, pend0, end, finished, flag
@@ -648,6 +678,10 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          }
       }
       if (err) { if (bulk_pending) cudaStreamSynchronize(N.stream2); return err; }
+#ifdef SPRAL_B200_SPLIT
+      if (split_now) {}                       // the far columns are on the helper whatever their number
+      else
+#endif
       if (lookahead && (int)(bulk.size() + bulk_b.size()) < device_sm_count()) {   // not worth a second stream
          for (const MatTile& t : bulk) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
          for (const MatTile& t : bulk_b) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
@@ -674,11 +708,21 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          CUDA_TRY(cudaStreamWaitEvent(s, (lookahead && have_bulk) ? N.ev_bulk : N.ev_bulk_all, 0));
          if (!(lookahead && have_bulk)) bulk_pending = false;
       }
+#ifdef SPRAL_B200_SPLIT
+      if (split_now) N.split->need_block(split_k + 1, s);
+#endif
       if (!outer.empty()) {
          MatTile* d_outer = upload(bump, outer, s);
          if (g_prof) g_prof->next_tiles = (int)outer.size();
          PROF(PC_OUTER, launch_update(d_fronts, d_outer, (int)outer.size(), UPD_OUTER, big, s));
       }
+#ifdef SPRAL_B200_SPLIT
+      if (split_now) {
+         const HostState& h0 = H[act[0]];
+         if (N.split->has_far(split_k)) N.split->push_panel(split_k, h0.p0, h0.done, N.stream2);
+         else N.split->end_front(s);          // nothing is left on the helper
+      } else
+#endif
       if (have_bulk) {
          cudaStream_t s2 = N.stream2;
          Buf& bb = N.S->b_bulk[bulk_parity];
@@ -765,6 +809,11 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
 
    FactorParams prm{opt->u, opt->small, opt->action ? 1 : 0};
    if (nloc == 0) return;
+#ifdef SPRAL_B200_SPLIT
+   /* the segment exists for the whole part, so that the helper -- which arrives when its own parts are done, before
+    * this part can end -- always finds it and always sees its end (phase 4 in ~SplitOwner) */
+   if (!S.split_shm.empty()) N.split = SplitOwner::create(S.split_shm.c_str());
+#endif
    Prof prof;
    struct ProfScope { ProfScope(Prof* p) { g_prof = g_profile ? p : nullptr; } ~ProfScope() { g_prof = nullptr; } } prof_scope(&prof);
 
@@ -1046,7 +1095,14 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       auto tl2 = std::chrono::steady_clock::now();
       /* ---- factorise the fully-summed columns (panel by panel, one sync per panel) ---- */
       {
+#ifdef SPRAL_B200_SPLIT
+         /* a single large front at the top of the root part: its far columns go to the helper GPU (split_front.h) */
+         if (N.split && nfl == 1 && big && g_lookahead) N.split->begin_front(F[f0], posdef, s);
+#endif
          int err = factor_fronts(N, N.d_fronts, F, lfronts, big, prm, S.b_retry, t_sync);
+#ifdef SPRAL_B200_SPLIT
+         if (!err && N.split && N.split->active) throw std::runtime_error("split front: still active when the front is finished");
+#endif
          if (err) { st.flag = err; *stats = st; return; }
          int* d_lf = upload(bump, lfronts, s);
          launch_finalize(N.d_fronts, d_lf, nfl, posdef, s);
@@ -1140,6 +1196,9 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       CUDA_TRY(cudaMemcpyAsync(N.d_wbeg, wbeg.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, s));
       CUDA_TRY(cudaStreamSynchronize(s));
    }
+#ifdef SPRAL_B200_SPLIT
+   delete N.split; N.split = nullptr;          // phase 4: the helper leaves its service loop
+#endif
    CUDA_TRY(cudaEventRecord(N.ev_end, s));
    CUDA_TRY(cudaEventSynchronize(N.ev_end));
    float ems = 0;
@@ -1520,6 +1579,28 @@ void spral_ssids_gpu_symbolic_get_maps(const void* p, int* rlist_direct, int* nu
 
 void spral_ssids_b200_set_profile(int on) {
    ABI_GUARD(); g_profile = (on != 0); }
+
+#ifdef SPRAL_B200_SPLIT
+/* Distributed top front (split_front.h; opt-in build).  enable: the owner rank names the shared-memory segment
+ * for the part that holds the top of the tree, before it factorises it.  serve: called by the helper rank once
+ * its own parts are done; returns when the owner's part is finished (0), when no owner showed up (1) or no
+ * front was split (2), or the raw cudaError_t. */
+void spral_ssids_b200_split_enable(void* symbolic_subtree, const char* shm_name) {
+   ABI_GUARD();
+   static_cast<Symbolic*>(symbolic_subtree)->split_shm = shm_name ? shm_name : "";
+}
+int spral_ssids_b200_split_helper_serve(const char* shm_name, int device, double timeout_s) {
+   ABI_GUARD();
+   try { return split_helper_serve(shm_name, device, timeout_s); }
+   catch (const CudaError& e) {
+      fprintf(stderr, "spral_ssids_b200: CUDA error %d (%s) in the split helper\n", (int)e.code, cudaGetErrorString(e.code));
+      return (int)e.code;
+   } catch (const std::exception& e) {
+      fprintf(stderr, "spral_ssids_b200: %s in the split helper\n", e.what());
+      return -1;
+   }
+}
+#endif
 
 void spral_ssids_gpu_subtree_get_timings(const void* p, double* ms, int n) {
    ABI_GUARD();

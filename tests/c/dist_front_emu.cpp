@@ -6,15 +6,18 @@
  * One top front, an owner rank R0 and a helper rank R1.  R0 runs factor_fronts (restated launch for launch,
  * on the shared state machine of spral_b200/csrc/pivot_state.h, as tests/c/lookahead_race_emu.cpp does) but
  * does not run the look-ahead bulk update itself while the split is active:
- *   set-up   R0 main:  copy the far columns (blocks J >= 2 of 256 columns) to R1's mirror, set `init`
- *   panel k  R0 main:  [wait returned[k+1]]  urgent update of block k+1 with panel k        (as today)
- *            R0 copy:  [wait consumed[k-2]]  copy L, L*D of panel k, rows >= 256 (k+2), into R1's panel
- *                      buffer k % 2, set ready[k]
- *            R1      :  wait ready[k]; update block k+2 with panel k; copy block k+2 into R0's front, set
- *                      returned[k+2]; update the blocks > k+2 with panel k; set consumed[k]
- *   failure  the first panel with a failed pivot ends the split by DRAINING: R0 sets ready[k](last); R1, in
- *            stream order behind everything it was given, copies every block it still holds back and sets
- *            `drained`; R0 waits for it and carries on alone (full outer update, swaps, local look-ahead).
+ *   set-up   R0 main:  copy the far columns (blocks J >= 2 of 256 columns) into R1's mirror (full shape of the
+ *                      front, for L and for L*D), set `init`
+ *   panel k  R0 main:  wait updated[k+1], copy block k+1 back out of the mirror, urgent update of block k+1
+ *                      with panel k                                                           (as today)
+ *            R0 copy:  copy L, L*D of panel k, rows >= 256 (k+2), into the same columns of the mirror, set ready[k]
+ *            R1      :  wait ready[k]; update block k+2 with panel k (the UPD_EXPLICIT kernel against the mirror),
+ *                      set updated[k+2]; update the blocks > k+2 with panel k
+ *   failure  the first panel with a failed pivot ends the split by DRAINING: R0 sets ready[k] = DRAIN; R1, in
+ *            stream order behind everything it was given, sets `drained`; R0 waits for it, copies every far
+ *            column back and carries on alone (full outer update, swaps, local look-ahead).
+ * This is the host-driven first version that spral_b200/csrc/split_front.h implements (flags raised from host
+ * callbacks behind the stream work they announce, polled by the other host).
  * Streams are in-order; the only cross-stream orderings are R0's host synchronisation of its main stream
  * at each panel snapshot (which orders what R0's host issues afterwards, on either of its streams) and
  * the flags.  Checked, over random fronts / failure patterns / speculative segments:
@@ -23,7 +26,8 @@
  *      entries of R0's front, R1's mirror or R1's panel buffers unless both only read them;
  *   3. every column has received the update of every eliminated column when its block is factorised,
  *      and R1 applied exactly the panels R0 accounts for when a block comes back.
- * Injected faults (a wait dropped, a buffer re-used too early, the drain forgotten) must be detected.
+ * Injected faults (a wait dropped, a block announced before it is updated, the drain not awaited, a panel copy
+ * that reaches into rows the owner is permuting) must be detected.
  *
  * Build: g++ -O2 -std=c++17 -I/usr/local/cuda/include -Iinclude tests/c/dist_front_emu.cpp */
 #include <algorithm>
@@ -41,7 +45,7 @@ using namespace b200;
 static const double INF = std::numeric_limits<double>::infinity();
 static const int T = 128, Ti = 64;   // update_tile_size(big), inner_tile_size(big)  (gemm_dmma.cu)
 
-enum Arr { A_L = 0, A_LD = 1, A_BK = 2, A_HM = 3, A_PBL0 = 4, A_PBL1 = 5, A_PBD0 = 6, A_PBD1 = 7 };   // HM: R1's mirror; PB*: its panel buffers
+enum Arr { A_L = 0, A_LD = 1, A_BK = 2, A_HM = 3, A_HMD = 4 };   // HM / HMD: R1's mirror of L / of L*D (full shape of the front)
 enum Stream { S_MAIN = 0, S_COPY = 1, S_HELP = 2, NSTREAM = 3 };
 
 struct Rect { int arr, front, r0, r1, c0, c1; bool w; };       // half-open; L / LD in front coordinates
@@ -66,7 +70,7 @@ struct Sim {
    double p_fail = 0, p_chain_giveup = 0, p_tile_fail = 0;
    bool v2 = false, lookahead_on = true;
    int sm_count = 148;
-   int split_inject = 0;             // faults of the split protocol: 1 no wait for the returned block, 2 no back-pressure, 3 drain not awaited,
+   int split_inject = 0;             // faults of the split protocol: 1 no wait for the updated block, 2 block announced before its update, 3 drain not awaited,
                                      // 4 the panel copy also reads the rows of the next panel (which R0 is permuting)
    int inject = 0;                   // fault injection (the checker must notice): 1 drop the ev_bulk wait, 2 drop the
                                      // ev_bulk_all wait, 3 the bulk starts one tile column early, 4 the second bulk part is lost
@@ -101,7 +105,7 @@ struct Sim {
    bool offload_active = false;
    int drain_at = -1;                             // panel whose failure ended the split
    int flag_init = -1, flag_drained = -1;
-   std::vector<int> flag_ready, flag_returned, flag_consumed;     // by panel / block / panel (-1: never created)
+   std::vector<int> flag_ready, flag_updated;     // by panel / by block (-1: never created)
    std::vector<int> accounted;                    // by block: panels R0 counted when the block came back
    long n_helper = 0, n_drains = 0, n_offloaded = 0;
    int& slot(std::vector<int>& v, int i) { if ((int)v.size() <= i) v.resize(i + 1, -1); if (v[i] < 0) v[i] = new_flag(); return v[i]; }
@@ -110,8 +114,7 @@ struct Sim {
       accounted[J] = npanels;
       for (int c = B(J); c < std::min(B(J + 1), n); ++c) upd[0][c] += npanels * PW;
    }
-   /* R1's schedule: a function of the geometry and of the flags R0 raised (it is enqueued up front on the device;
-    * everything behind the drain is turned into no-ops by the `stopped` word) */
+   /* R1's schedule (split_front.h: split_helper_serve): a function of the geometry and of the flags R0 raised */
    void helper_schedule(const Front& f) {
       if (flag_init < 0) return;
       push_wait(S_HELP, flag_init);
@@ -119,36 +122,35 @@ struct Sim {
       for (int k = 0; k < (int)flag_ready.size(); ++k) {
          if (flag_ready[k] < 0) break;
          push_wait(S_HELP, flag_ready[k]);
-         const int pb_l = (k % 2) ? A_PBL1 : A_PBL0, pb_d = (k % 2) ? A_PBD1 : A_PBD0;
-         auto give_back = [&](int J) {
-            Launch y{"return block", {}};
-            y.rects.push_back({A_HM, 0, B(J), f.m, B(J), std::min(B(J + 1), f.n), false});
-            y.rects.push_back({A_L, 0, B(J), f.m, B(J), std::min(B(J + 1), f.n), true});
-            ops[S_HELP].push_back({0, std::move(y), -1}); ++n_helper;
-            if ((int)accounted.size() <= J || accounted[J] != cnt[J]) {
-               char buf[160];
-               snprintf(buf, sizeof buf, "block %d comes back with %d panels applied, R0 accounts for %d", J, cnt[J],
-                        (int)accounted.size() > J ? accounted[J] : -1);
-               throw std::runtime_error(buf);
-            }
-         };
-         if (k == drain_at) {
-            for (int J = std::max(2, k + 2); B(J) < f.n; ++J) give_back(J);
+         if (k == drain_at) {                               /* in stream order behind everything it was given */
+            for (int J = std::max(2, k + 1); B(J) < f.n; ++J) check_count(J, cnt[J]);
             push_set(S_HELP, flag_drained);
             return;
          }
          for (int J = k + 2; B(J) < f.n; ++J) {
+            if (J == k + 2 && split_inject == 2) push_set(S_HELP, slot(flag_updated, J));      // fault: announced too early
             Launch y{"helper update", {}};
-            y.rects.push_back({pb_l, 0, B(J), f.ldl, 0, PW, false});
-            y.rects.push_back({pb_d, 0, B(J), std::min(f.ldl, B(J + 1)), 0, PW, false});
+            y.rects.push_back({A_HM, 0, B(J), f.ldl, panel_k0[k], panel_k1[k], false});
+            y.rects.push_back({A_HMD, 0, B(J), std::min(f.ldl, B(J + 1)), panel_k0[k], panel_k1[k], false});
             y.rects.push_back({A_HM, 0, B(J), f.m, B(J), std::min(B(J + 1), f.n), true});
             ops[S_HELP].push_back({0, std::move(y), -1}); ++n_helper;
             ++cnt[J];
-            if (J == k + 2) { give_back(J); push_set(S_HELP, slot(flag_returned, J)); }
+            if (J == k + 2) {
+               if (split_inject != 2) push_set(S_HELP, slot(flag_updated, J));
+               if ((int)accounted.size() > J && accounted[J] >= 0 && !(drain_at >= 0 && J > drain_at)) check_count(J, cnt[J]);
+            }
          }
-         push_set(S_HELP, slot(flag_consumed, k));
       }
    }
+   void check_count(int J, int applied) {
+      if ((int)accounted.size() <= J || accounted[J] != applied) {
+         char buf[160];
+         snprintf(buf, sizeof buf, "block %d comes back with %d panels applied, R0 accounts for %d", J, applied,
+                  (int)accounted.size() > J ? accounted[J] : -1);
+         throw std::runtime_error(buf);
+      }
+   }
+   std::vector<int> panel_k0, panel_k1;           // columns of the panels R0 pushed
 
    /* Vector clocks + pairwise check.  Returns the number of unordered pairs compared. */
    void order_and_check() {
@@ -468,13 +470,19 @@ struct Sim {
          if (offload_active) {
             const HostState& h = H[act[0]];
             if (h.p0 % PW != 0) throw std::runtime_error("split active although the panels are no longer block aligned");
-            if (any_fail) {                                         /* drain: R1 hands everything back, R0 carries on alone */
+            if (any_fail) {                                         /* drain: everything comes back, R0 carries on alone */
                host_order_copy();
                push_set(S_COPY, slot(flag_ready, kpanel));
                drain_at = kpanel; ++n_drains;
                if (split_inject != 3) push_wait(S_MAIN, flag_drained);
-               for (int J = std::max(2, kpanel + 1); B(J) < h.n; ++J)
-                  if ((int)accounted.size() <= J || accounted[J] < 0) account_block(J, std::min(J - 1, kpanel), h.n);
+               const int J0 = std::max(2, kpanel + 1);
+               if (B(J0) < h.n) {
+                  Launch x{"pull the far columns", {}};
+                  x.rects.push_back({A_HM, 0, B(J0), F[0].m, B(J0), h.n, false});
+                  x.rects.push_back({A_L, 0, B(J0), F[0].m, B(J0), h.n, true});
+                  issue_main(std::move(x));
+               }
+               for (int J = J0; B(J) < h.n; ++J) account_block(J, std::min(J - 1, kpanel), h.n);
                offload_active = false;
             }
          }
@@ -528,8 +536,12 @@ struct Sim {
             const HostState& h = H[act[0]];
             const int J = kpanel + 1;                               // the block the urgent update is about to touch
             if (J >= 2 && B(J) < h.n) {
-               if (split_inject != 1) push_wait(S_MAIN, slot(flag_returned, J));
-               else slot(flag_returned, J);
+               if (split_inject != 1) push_wait(S_MAIN, slot(flag_updated, J));
+               else slot(flag_updated, J);
+               Launch x{"pull block", {}};
+               x.rects.push_back({A_HM, 0, B(J), F[0].m, B(J), std::min(B(J + 1), h.n), false});
+               x.rects.push_back({A_L, 0, B(J), F[0].m, B(J), std::min(B(J + 1), h.n), true});
+               issue_main(std::move(x));
                account_block(J, J - 1, h.n);
             }
          }
@@ -551,13 +563,14 @@ struct Sim {
             if (h.done != h.pend0) throw std::runtime_error("split: a panel without failure is not complete");
             if (B(kpanel + 2) < h.n) {                              /* panel k to R1: rows of the far blocks only */
                host_order_copy();
-               if (kpanel >= 2 && split_inject != 2) push_wait(S_COPY, slot(flag_consumed, kpanel - 2));
                Launch y{"copy panel", {}};
                const int rtop = B(kpanel + (split_inject == 4 ? 1 : 2));      // fault 4: the rows of the NEXT panel are copied too
                y.rects.push_back({A_L, 0, rtop, f.ldl, h.p0, h.done, false});
                y.rects.push_back({A_LD, 0, rtop, f.ldl, h.p0, h.done, false});
-               y.rects.push_back({(kpanel % 2) ? A_PBL1 : A_PBL0, 0, B(kpanel + 2), f.ldl, 0, PW, true});
-               y.rects.push_back({(kpanel % 2) ? A_PBD1 : A_PBD0, 0, B(kpanel + 2), f.ldl, 0, PW, true});
+               y.rects.push_back({A_HM, 0, rtop, f.ldl, h.p0, h.done, true});
+               y.rects.push_back({A_HMD, 0, rtop, f.ldl, h.p0, h.done, true});
+               if ((int)panel_k0.size() <= kpanel) { panel_k0.resize(kpanel + 1, 0); panel_k1.resize(kpanel + 1, 0); }
+               panel_k0[kpanel] = h.p0; panel_k1[kpanel] = h.done;
                ops[S_COPY].push_back({0, std::move(y), -1}); ++n_offloaded;
                push_set(S_COPY, slot(flag_ready, kpanel));
                /* the far columns get this panel from R1: nothing to add here, account_block() does it when they return */
@@ -654,8 +667,8 @@ int main(int argc, char** argv) {
    bool blind = false;
    for (int inj = 1; inj <= 4; ++inj) { detected[inj] = run(std::min(ntrial, 300), inj, st2); blind = blind || detected[inj] == 0; }
    printf("dist_front_emu: %d fronts, %ld owner launches, %ld panels sent, %ld helper operations, %ld drains, %ld flag waits, "
-          "%ld unordered footprint pairs compared, %d failures; fault injection detected in %d (wait for the returned block "
-          "dropped) / %d (panel buffer re-used without back-pressure) / %d (drain not awaited) / %d (panel copy reaches into the rows R0 is permuting) fronts\n", ntrial, st[0], st[1],
+          "%ld unordered footprint pairs compared, %d failures; fault injection detected in %d (wait for the updated block "
+          "dropped) / %d (block announced before its update) / %d (drain not awaited) / %d (panel copy reaches into the rows R0 is permuting) fronts\n", ntrial, st[0], st[1],
           st[4], st[5], st[3], st[2], failures, detected[1], detected[2], detected[3], detected[4]);
    return (failures || blind) ? 1 : 0;
 }

@@ -128,3 +128,24 @@ def test_distributed_top_front_protocol_model_check():
     r = subprocess.run([exe, "1500"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " 0 failures" in r.stdout and "detected in 0 " not in r.stdout and "/ 0 (" not in r.stdout, r.stdout
+
+
+def test_split_front_variant_compiles_and_default_build_is_untouched():
+    """spral_b200/csrc/split_front.h (distributed top front, `make SPLIT=1`; not run on GPUs yet): the variant compiles
+    for sm_100a, and without the switch the preprocessed subtree.cu does not contain a token of it."""
+    import shutil
+    import pytest
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    csrc = os.path.join(ROOT, "spral_b200", "csrc")
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp",
+                           "-I" + os.path.join(ROOT, "include"), "--expt-relaxed-constexpr", "-DSPRAL_B200_SPLIT", "-c",
+                           os.path.join(csrc, "subtree.cu"), "-o", os.path.join(out, "subtree_split.o")])
+    pre = subprocess.run(["g++", "-x", "c++", "-E", "-P", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                          "-I/usr/local/cuda/include", os.path.join(csrc, "subtree.cu")], capture_output=True, text=True)
+    assert pre.returncode == 0, pre.stderr[-2000:]
+    for token in ("SplitOwner", "SplitShm", "split_now", "split_helper_serve", "shm_open"):
+        assert token not in pre.stdout, token
