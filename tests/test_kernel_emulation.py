@@ -149,3 +149,24 @@ def test_split_front_variant_compiles_and_default_build_is_untouched():
     assert pre.returncode == 0, pre.stderr[-2000:]
     for token in ("SplitOwner", "SplitShm", "split_now", "split_helper_serve", "shm_open"):
         assert token not in pre.stdout, token
+
+
+def test_split_front_host_code_on_a_cuda_mock():
+    """tests/c/split_front_emu.cpp: the real spral_b200/csrc/split_front.h (SplitOwner, split_helper_serve, the
+    shared-memory protocol) with the owner and the helper as two threads over a mock of the CUDA runtime calls it makes
+    (in-order worker-thread streams, host-callback flags, pointer-carrying IPC handles, UPD_EXPLICIT as a triple loop with
+    the kernel's region / tile semantics): ten fronts -- square, with contribution rows, Cholesky flavour, odd sizes,
+    "failed pivot" (drain) at the first / middle / last panel, too small to split -- reproduce the unsplit run bit for bit."""
+    out = os.path.join(ROOT, "build", "tests")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "split_front_emu")
+    cuda_inc = "/usr/local/cuda/include"
+    import pytest
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-DSPRAL_B200_SPLIT", "-I" + cuda_inc,
+                           "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "split_front_emu.cpp"), "-lrt"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "split_front_emu: 10 cases, 0 failures" in r.stdout
