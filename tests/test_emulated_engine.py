@@ -1,0 +1,51 @@
+"""The engine's REAL sources on a CPU: tests/emu compiles subtree.cu, factor_kernels.cu and solve_kernels.cu with g++ on
+top of a small SIMT emulator (every CUDA thread of a CTA on a fiber, __syncthreads / shuffles as rendezvous points,
+__shared__ as static storage, the CUDA runtime answered synchronously; only gemm_dmma.cu -- inline PTX -- is replaced
+by loops over the same regions and tiles).  The library is loaded BY TESTS ONLY (tests/conftest.py,
+SPRAL_B200_EMU_LIB); the package knows the CUDA library and nothing else.
+
+This runs the logic of the GPU test files in a GPU-less container: host scheduling, assembly, pivoting kernels, delays,
+solves -- and every opt-in variant -- against the oracle.  It is not a parity claim (parity is measured on the B200,
+`-m gpu`); it is how changes are checked before GPU minutes are spent on them.  The whole of test_gpu_parity.py
+(38 tests without the full-size / device-pointer / C-client ones), test_gpu_widened.py and test_gpu_experimental.py pass
+this way (6 + 6 tests, ~30 min); the CPU suite runs a slice of a couple of minutes."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+EMU_LIB = os.path.join(ROOT, "build", "emu", "libspral_ssids_b200_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu_env():
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("CUDA headers not found")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "emu", "build_emu.py")], stdout=subprocess.DEVNULL)
+    env = dict(os.environ)
+    env.update(SPRAL_B200_EMU_LIB=EMU_LIB, SPRAL_B200_DIAG_V2="1", OMP_CANCELLATION="TRUE")   # 128-fiber diagonal blocks: 8x faster to emulate
+    return env
+
+
+def _pytest(env, args, timeout):
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + args, cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_slice_of_the_gpu_parity_suite_on_the_emulator(emu_env):
+    out = _pytest(emu_env, ["tests/test_gpu_parity.py", "-k",
+                            "(dense_fronts and (31 or 33 or 100)) or (doctored and 64) or singular_matrix or not_positive_definite "
+                            "or solve_jobs or enquire or multi_part or index_maps"], 900)
+    assert " passed" in out and "failed" not in out, out[-500:]
+
+
+def test_opt_in_variants_against_the_default_engine_on_the_emulator(emu_env):
+    env = dict(emu_env, SPRAL_B200_EXPERIMENTAL_TESTS="1", SPRAL_B200_DUMP_CASES="dense_391_indef,dense_500_posdef")
+    env.pop("SPRAL_B200_DIAG_V2")            # this file compares DIAG_V2 with the default kernel itself
+    out = _pytest(env, ["tests/test_gpu_experimental.py"], 1500)
+    assert "6 passed" in out, out[-500:]

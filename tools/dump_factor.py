@@ -9,6 +9,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if os.environ.get("SPRAL_B200_EMU_LIB"):      # developer / test hook: the CPU-emulated build of tests/emu (see tests/conftest.py)
+    from spral_b200 import _lib as _emu_lib
+    _emu_lib.LIB_PATH = os.environ["SPRAL_B200_EMU_LIB"]
 import spral_b200 as sb                      # noqa: E402
 from spral_b200 import matrices as M         # noqa: E402
 
@@ -36,7 +39,10 @@ CASES = {
 
 def main(out):
     res = {}
+    only = os.environ.get("SPRAL_B200_DUMP_CASES")          # comma-separated subset (the emulated build is slow)
     for name, (gen, posdef) in CASES.items():
+        if only and name not in only.split(","):
+            continue
         n, ptr, row, val = gen()
         ak = sb.analyse(n, ptr, row)
         fk = sb.factor(ak, posdef, val)
