@@ -87,6 +87,8 @@ struct SplitOwner {
    double timeout_s = 20.0;
    bool active = false;                  // a front is split right now
    bool dead = false;                    // no helper answered: do not try again
+   bool trace = getenv("SPRAL_B200_TRACE") != nullptr;
+   int n_pushed = 0, n_pulled = 0;
    const Front* f = nullptr;             // host copy of its descriptor (owner's pointers)
    double* mL = nullptr; double* mLD = nullptr;    // the helper's mirror, mapped here
    std::vector<std::pair<std::vector<unsigned char>, void*>> opened;
@@ -136,7 +138,8 @@ struct SplitOwner {
       const size_t off = (size_t)c0 + (size_t)c0 * fr.ldl;
       CUDA_TRY(cudaMemcpy2DAsync(mL + off, (size_t)fr.ldl * sizeof(double), fr.L + off, (size_t)fr.ldl * sizeof(double),
                                  (size_t)(fr.m - c0) * sizeof(double), fr.n - c0, cudaMemcpyDefault, s));
-      active = true;
+      active = true; n_pushed = n_pulled = 0;
+      if (trace) fprintf(stderr, "[split] front m %d n %d: far columns %d.. on the helper\n", fr.m, fr.n, c0);
       return true;
    }
    bool has_far(int k) const { return split_block(k + 2) < f->n; }
@@ -149,6 +152,7 @@ struct SplitOwner {
       if (mLD != mL) CUDA_TRY(cudaMemcpy2DAsync(mLD + off, pitch, f->LD + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
       sh->k0[k] = k0; sh->k1[k] = k1;
       split_raise_behind(s2, &sh->ready[k], 1);
+      ++n_pushed;
    }
    /* Block J comes back (main stream), in order before the urgent update that touches it. */
    void need_block(int J, cudaStream_t s) {
@@ -161,11 +165,13 @@ struct SplitOwner {
       const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
       CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), mL + off, (size_t)f->ldl * sizeof(double),
                                  (size_t)(f->m - c0) * sizeof(double), c1 - c0, cudaMemcpyDefault, s));
+      ++n_pulled;
    }
    /* The split ends at panel k (failed pivot, or nothing is left on the helper): every column the helper
     * still holds -- blocks >= first_block -- comes back; the helper has applied panels 0 .. k-1 to them. */
    void drain(int k, int first_block, cudaStream_t s, cudaStream_t s2) {
       CUDA_TRY(cudaStreamSynchronize(s2));                     // every pushed panel has been announced
+      if (trace) fprintf(stderr, "[split] drain at panel %d (%d panels pushed, %d blocks pulled)\n", k, n_pushed, n_pulled);
       sh->ready[k].store(SPLIT_DRAIN, std::memory_order_release);
       if (!split_wait(sh, timeout_s, [&] { return sh->drained.load(std::memory_order_acquire) != 0; })) {
          sh->error.store(1, std::memory_order_release);
@@ -181,6 +187,7 @@ struct SplitOwner {
    }
    void end_front(cudaStream_t s) {
       CUDA_TRY(cudaStreamSynchronize(s));                      // the copies out of the mirror are done
+      if (trace) fprintf(stderr, "[split] front closed (%d panels pushed, %d blocks pulled)\n", n_pushed, n_pulled);
       sh->phase.store(3, std::memory_order_release);
       active = false; f = nullptr;
    }

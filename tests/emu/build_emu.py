@@ -69,10 +69,13 @@ def transform(src):
     return "".join(out)
 
 
-def build(verbose=False):
+def build(verbose=False, defines=(), tag=""):
+    """defines: extra -D switches (e.g. SPRAL_B200_SPLIT); tag: suffix of the build directory / library name."""
+    global OUT
+    OUT = os.path.join(ROOT, "build", "emu" + tag)
     os.makedirs(OUT, exist_ok=True)
     flags = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-w", "-I" + EMU, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
-             "-I" + CUDA_INC, "-U_FORTIFY_SOURCE"]
+             "-I" + CUDA_INC, "-U_FORTIFY_SOURCE"] + ["-D" + d for d in defines]
     objs = []
     for name in ("subtree.cu", "factor_kernels.cu", "solve_kernels.cu"):
         gen = os.path.join(OUT, name.replace(".cu", ".emu.cpp"))
@@ -88,10 +91,13 @@ def build(verbose=False):
         obj = os.path.join(OUT, os.path.basename(path).replace(".cpp", ".o"))
         subprocess.check_call(["g++"] + flags + ["-c", path, "-o", obj])
         objs.append(obj)
-    lib = os.path.join(OUT, "libspral_ssids_b200_emu.so")
+    lib = os.path.join(OUT, f"libspral_ssids_b200_emu{tag}.so")
     subprocess.check_call(["g++", "-shared", "-fopenmp", "-o", lib] + objs + [METIS, "-lm", "-ldl", "-lrt"])
     return lib
 
 
 if __name__ == "__main__":
-    print(build(verbose=True))
+    if len(sys.argv) > 1 and sys.argv[1] == "split":
+        print(build(verbose=True, defines=("SPRAL_B200_SPLIT",), tag="_split"))
+    else:
+        print(build(verbose=True))

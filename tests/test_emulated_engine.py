@@ -49,3 +49,21 @@ def test_opt_in_variants_against_the_default_engine_on_the_emulator(emu_env):
     env.pop("SPRAL_B200_DIAG_V2")            # this file compares DIAG_V2 with the default kernel itself
     out = _pytest(env, ["tests/test_gpu_experimental.py"], 1500)
     assert "6 passed" in out, out[-500:]
+
+
+@pytest.fixture(scope="module")
+def emu_split_lib(emu_env):
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "emu", "build_emu.py"), "split"], stdout=subprocess.DEVNULL)
+    return os.path.join(ROOT, "build", "emu_split", "libspral_ssids_b200_emu_split.so")
+
+
+@pytest.mark.parametrize("n,kind,expect", [(1300, "posdef", "4 panels pushed, 4 blocks pulled"), (1300, "indef", "drain at panel")])
+def test_distributed_top_front_end_to_end_on_the_emulator(emu_env, emu_split_lib, n, kind, expect):
+    """csrc/split_front.h and its hooks in factor_fronts (`make SPLIT=1`, not run on GPUs yet) with the owner and the helper
+    as two threads of one process on the emulator: a front that is split to its end (Cholesky) and one whose split is
+    drained by a failed pivot give the factors and solutions of the unsplit run bit for bit."""
+    env = dict(emu_env, SPRAL_B200_EMU_LIB=emu_split_lib, SPRAL_B200_TRACE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "split_check.py"), str(n), kind], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "BITWISE IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert expect in r.stderr, r.stderr[-2000:]
