@@ -92,7 +92,8 @@ def build(verbose=False, defines=(), tag=""):
         subprocess.check_call(["g++"] + flags + ["-c", path, "-o", obj])
         objs.append(obj)
     lib = os.path.join(OUT, f"libspral_ssids_b200_emu{tag}.so")
-    subprocess.check_call(["g++", "-shared", "-fopenmp", "-o", lib] + objs + [METIS, "-lm", "-ldl", "-lrt"])
+    # -Bsymbolic: the mock runtime of THIS library answers its CUDA calls even when torch has loaded the real libcudart
+    subprocess.check_call(["g++", "-shared", "-fopenmp", "-Wl,-Bsymbolic", "-o", lib] + objs + [METIS, "-lm", "-ldl", "-lrt"])
     return lib
 
 

@@ -2,6 +2,11 @@
  * CUDA runtime calls the engine's host code makes ("device" memory is host memory, a stream executes at once). */
 #include <ucontext.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <atomic>
+#include <string>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -112,6 +117,8 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::functio
 namespace {
 std::mutex reg_mtx;
 std::map<const char*, size_t> allocs;          // base -> bytes
+std::map<const char*, std::string> shm_names;  // base -> shared-memory name (SPRAL_B200_EMU_SHM)
+struct ShmCleanup { ~ShmCleanup() { for (auto& kv : shm_names) shm_unlink(kv.second.c_str()); } } shm_cleanup;   // the pool keeps blocks until exit
 bool is_dev(const void* p) {
    std::lock_guard<std::mutex> l(reg_mtx);
    auto it = allocs.upper_bound((const char*)p);
@@ -129,17 +136,44 @@ cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
+/* "Device" memory: malloc, or -- SPRAL_B200_EMU_SHM=1 -- POSIX shared memory, so that an IPC handle (which then carries
+ * the segment's name) can be opened by ANOTHER process: the one-process-per-GPU paths run as real processes on the CPU. */
+static bool shm_mode() { static int v = -1; if (v < 0) v = getenv("SPRAL_B200_EMU_SHM") ? 1 : 0; return v == 1; }
 cudaError_t cudaMalloc(void** p, size_t bytes) {
-   void* q = std::malloc(bytes ? bytes : 1);
-   if (!q) return cudaErrorMemoryAllocation;
-   std::memset(q, 0xEE, bytes);                       // device memory is not zero
-   { std::lock_guard<std::mutex> l(reg_mtx); allocs[(const char*)q] = bytes ? bytes : 1; }
+   if (!bytes) bytes = 1;
+   void* q = nullptr;
+   std::string name;
+   if (shm_mode()) {
+      static std::atomic<long> counter{0};
+      name = "/spral_emu_" + std::to_string((long)getpid()) + "_" + std::to_string(counter.fetch_add(1));
+      int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+      if (fd < 0) return cudaErrorMemoryAllocation;
+      if (ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name.c_str()); return cudaErrorMemoryAllocation; }
+      q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      close(fd);
+      if (q == MAP_FAILED) { shm_unlink(name.c_str()); return cudaErrorMemoryAllocation; }
+      if (bytes <= ((size_t)64 << 20)) std::memset(q, 0xEE, bytes);
+   } else {
+      q = std::malloc(bytes);
+      if (!q) return cudaErrorMemoryAllocation;
+      std::memset(q, 0xEE, bytes);                       // device memory is not zero
+   }
+   { std::lock_guard<std::mutex> l(reg_mtx); allocs[(const char*)q] = bytes; if (!name.empty()) shm_names[(const char*)q] = name; }
    *p = q; return cudaSuccess;
 }
 cudaError_t cudaFree(void* p) {
    if (!p) return cudaSuccess;
-   { std::lock_guard<std::mutex> l(reg_mtx); allocs.erase((const char*)p); }
-   std::free(p); return cudaSuccess;
+   size_t bytes = 0; std::string name;
+   {
+      std::lock_guard<std::mutex> l(reg_mtx);
+      auto it = allocs.find((const char*)p);
+      if (it != allocs.end()) { bytes = it->second; allocs.erase(it); }
+      auto jt = shm_names.find((const char*)p);
+      if (jt != shm_names.end()) { name = jt->second; shm_names.erase(jt); }
+   }
+   if (!name.empty()) { munmap(p, bytes); shm_unlink(name.c_str()); }
+   else std::free(p);
+   return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) std::memmove(d, s, n); return cudaSuccess; }
@@ -174,9 +208,41 @@ cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return c
 cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 0; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaLaunchHostFunc(cudaStream_t, cudaHostFn_t fn, void* arg) { fn(arg); return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h, &p, sizeof(p)); return cudaSuccess; }
-cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+   std::memset(h, 0, sizeof(*h));
+   if (shm_mode()) {
+      std::lock_guard<std::mutex> l(reg_mtx);
+      auto it = shm_names.find((const char*)p);
+      if (it == shm_names.end() || it->second.size() > 55) return cudaErrorInvalidValue;      // must be the base of an allocation
+      std::memcpy((char*)h, "SHM:", 4);
+      std::memcpy((char*)h + 4, it->second.c_str(), it->second.size() + 1);
+      return cudaSuccess;
+   }
+   std::memcpy(h, &p, sizeof(p)); return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+   if (std::memcmp((const char*)&h, "SHM:", 4) == 0) {
+      const char* name = (const char*)&h + 4;
+      int fd = shm_open(name, O_RDWR, 0600);
+      if (fd < 0) return cudaErrorInvalidValue;
+      struct stat st;
+      if (fstat(fd, &st) != 0) { close(fd); return cudaErrorInvalidValue; }
+      void* q = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      close(fd);
+      if (q == MAP_FAILED) return cudaErrorInvalidValue;
+      { std::lock_guard<std::mutex> l(reg_mtx); allocs[(const char*)q] = (size_t)st.st_size; }     // counts as device memory here too
+      *p = q; return cudaSuccess;
+   }
+   std::memcpy(p, &h, sizeof(*p)); return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+   if (shm_mode()) {
+      size_t bytes = 0;
+      { std::lock_guard<std::mutex> l(reg_mtx); auto it = allocs.find((const char*)p); if (it != allocs.end()) { bytes = it->second; allocs.erase(it); } }
+      if (bytes) munmap(p, bytes);
+   }
+   return cudaSuccess;
+}
 /* opt-in paths that the emulator does not serve */
 cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
 cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t*) { return cudaErrorNotSupported; }

@@ -67,3 +67,15 @@ def test_distributed_top_front_end_to_end_on_the_emulator(emu_env, emu_split_lib
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "BITWISE IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert expect in r.stderr, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(os.environ.get("SPRAL_B200_SLOW_TESTS") != "1", reason="3 minutes: set SPRAL_B200_SLOW_TESTS=1")
+@pytest.mark.parametrize("grid,kind", [(28, "stencil"), (34, "lap")])
+def test_two_process_gpu_path_with_split_on_the_emulator(emu_env, emu_split_lib, grid, kind):
+    """spral_b200/dist.py on its real GPU code path (GpuEngine, contribution blocks by "CUDA IPC", the distributed top
+    front between an owner and a helper rank) as two processes over gloo, "device" memory in POSIX shared memory
+    (tests/emu/dist_split_check.py): inertia and statistics equal the single-process run, solutions agree; the indefinite
+    problem drains the split at a failed pivot, the Cholesky problem runs it to its end (4 panels out, 4 blocks back)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dist_split_check.py"), str(grid), kind],
+                       env=dict(os.environ), capture_output=True, text=True, timeout=1700)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
