@@ -38,6 +38,7 @@ struct SplitShm {
                                          // the helper answers 3 -> 0 when it has released the mirror), 4 exit (owner)
    std::atomic<int> error;               // raised by either side: the other gives up
    int m, n, ldl, ld_is_l;               // geometry of the front; ld_is_l: positive definite (L*D == L)
+   int base;                             // first column of block 0 (a multiple of the update tile): 0, or where the split was re-started
    unsigned char h_L[64], h_LD[64];      // IPC handles of the helper's mirror
    std::atomic<int> ready[SPLIT_MAXP + 4];   // panel k is in the mirror (1) / the split ends here (SPLIT_DRAIN)
    int k0[SPLIT_MAXP + 4], k1[SPLIT_MAXP + 4];   // its columns
@@ -45,7 +46,8 @@ struct SplitShm {
    std::atomic<int> drained;
 };
 
-static inline int split_block(int j) { return j * PW; }
+static inline int split_block(int base, int j) { return base + j * PW; }
+static inline int split_round_up(int c, int t) { return (c + t - 1) / t * t; }
 
 struct SplitFlagSet { std::atomic<int>* p; int v; };
 static void CUDART_CB split_set_flag(void* arg) {
@@ -87,9 +89,15 @@ struct SplitOwner {
    double timeout_s = 20.0;
    bool active = false;                  // a front is split right now
    bool dead = false;                    // no helper answered: do not try again
+   bool level_ok = false;                // the level being factorised is one large front (set by factor_subtree)
+   bool restart = true;                  // SPRAL_B200_SPLIT_RESTART=0: a drained split stays off for the rest of the front
    bool trace = getenv("SPRAL_B200_TRACE") != nullptr;
    int n_pushed = 0, n_pulled = 0;
    const Front* f = nullptr;             // host copy of its descriptor (owner's pointers)
+   int base = 0;                         // block j = columns [base + j PW, base + (j + 1) PW): tile aligned, so that what the
+                                         // owner's urgent update touches (whole tile columns) ends where the helper's columns begin
+   int p_first = 0;                      // first column of panel 0 of this split (== base unless re-started off a tile boundary)
+   int blk(int j) const { return split_block(base, j); }
    double* mL = nullptr; double* mLD = nullptr;    // the helper's mirror, mapped here
    std::vector<std::pair<std::vector<unsigned char>, void*>> opened;
 
@@ -102,6 +110,7 @@ struct SplitOwner {
       auto* o = new SplitOwner;
       o->sh = sh; o->name = shm_name;
       if (const char* e = getenv("SPRAL_B200_SPLIT_TIMEOUT")) o->timeout_s = atof(e);
+      if (const char* e = getenv("SPRAL_B200_SPLIT_RESTART")) o->restart = atoi(e) != 0;
       return o;
    }
    ~SplitOwner() {
@@ -116,14 +125,18 @@ struct SplitOwner {
       opened.push_back({std::vector<unsigned char>(h, h + 64), p});
       return p;
    }
-   /* Worth splitting: at least four blocks.  Returns false (and leaves the front alone) when no helper answers. */
-   bool begin_front(const Front& fr, bool posdef, cudaStream_t s) {
-      if (active || dead || fr.n < 4 * PW || (fr.n + PW - 1) / PW > SPLIT_MAXP) return false;
+   /* Worth splitting: at least four blocks right of `first_col`, the first column of the next panel (0 at the start of a
+    * front; where a drained split is re-started otherwise).  The far columns are copied on stream `s`, in order behind
+    * whatever updated them last.  Returns false (and leaves the front alone) when no helper answers. */
+   bool begin_front(const Front& fr, bool posdef, cudaStream_t s, int first_col = 0) {
+      const int T = update_tile_size(true);
+      const int b = split_round_up(first_col, T);
+      if (active || dead || fr.n - b < 4 * PW || (fr.n - b + PW - 1) / PW > SPLIT_MAXP) return false;
       /* the helper has released the previous front (3 -> 0) */
       if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 0; })) { dead = true; return false; }
       for (int k = 0; k < SPLIT_MAXP + 4; ++k) { sh->ready[k].store(0); sh->updated[k].store(0); }
       sh->drained.store(0);
-      sh->m = fr.m; sh->n = fr.n; sh->ldl = fr.ldl; sh->ld_is_l = posdef ? 1 : 0;
+      sh->m = fr.m; sh->n = fr.n; sh->ldl = fr.ldl; sh->ld_is_l = posdef ? 1 : 0; sh->base = b;
       sh->phase.store(1, std::memory_order_release);
       if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 2; })) {
          sh->phase.store(3, std::memory_order_release);       // nobody there: the front stays whole
@@ -132,20 +145,22 @@ struct SplitOwner {
       }
       mL = static_cast<double*>(open_handle(sh->h_L));
       mLD = posdef ? mL : static_cast<double*>(open_handle(sh->h_LD));
-      f = &fr;
+      f = &fr; base = b; p_first = first_col;
       /* the far columns (blocks >= 2), rows from the first of them down */
-      const int c0 = split_block(2);
+      const int c0 = blk(2);
       const size_t off = (size_t)c0 + (size_t)c0 * fr.ldl;
       CUDA_TRY(cudaMemcpy2DAsync(mL + off, (size_t)fr.ldl * sizeof(double), fr.L + off, (size_t)fr.ldl * sizeof(double),
                                  (size_t)(fr.m - c0) * sizeof(double), fr.n - c0, cudaMemcpyDefault, s));
       active = true; n_pushed = n_pulled = 0;
-      if (trace) fprintf(stderr, "[split] front m %d n %d: far columns %d.. on the helper\n", fr.m, fr.n, c0);
+      if (trace) fprintf(stderr, "[split] front m %d n %d: far columns %d.. on the helper (panels from column %d)\n", fr.m, fr.n, c0, first_col);
       return true;
    }
-   bool has_far(int k) const { return split_block(k + 2) < f->n; }
+   /* panel index of the panel that starts at column p0, or -1 when the panels are no longer the split's blocks */
+   int panel_of(int p0) const { return (p0 >= p_first && (p0 - p_first) % PW == 0) ? (p0 - p_first) / PW : -1; }
+   bool has_far(int k) const { return blk(k + 2) < f->n; }
    /* Panel k = columns [k0, k1): rows of the far blocks into the mirror, then ready[k] (copy stream). */
    void push_panel(int k, int k0, int k1, cudaStream_t s2) {
-      const int r0 = split_block(k + 2);
+      const int r0 = blk(k + 2);
       const size_t off = (size_t)r0 + (size_t)k0 * f->ldl;
       const size_t pitch = (size_t)f->ldl * sizeof(double), width = (size_t)(f->m - r0) * sizeof(double);
       CUDA_TRY(cudaMemcpy2DAsync(mL + off, pitch, f->L + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
@@ -156,12 +171,12 @@ struct SplitOwner {
    }
    /* Block J comes back (main stream), in order before the urgent update that touches it. */
    void need_block(int J, cudaStream_t s) {
-      if (J < 2 || split_block(J) >= f->n) return;
+      if (J < 2 || blk(J) >= f->n) return;
       if (!split_wait(sh, timeout_s, [&] { return sh->updated[J].load(std::memory_order_acquire) != 0; })) {
          sh->error.store(1, std::memory_order_release);
          throw std::runtime_error("split front: the helper did not return a block in time");
       }
-      const int c0 = split_block(J), c1 = std::min(split_block(J + 1), f->n);
+      const int c0 = blk(J), c1 = std::min(blk(J + 1), f->n);
       const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
       CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), mL + off, (size_t)f->ldl * sizeof(double),
                                  (size_t)(f->m - c0) * sizeof(double), c1 - c0, cudaMemcpyDefault, s));
@@ -177,7 +192,7 @@ struct SplitOwner {
          sh->error.store(1, std::memory_order_release);
          throw std::runtime_error("split front: the helper did not drain in time");
       }
-      const int c0 = split_block(std::max(2, first_block));
+      const int c0 = blk(std::max(2, first_block));
       if (c0 < f->n) {
          const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
          CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), mL + off, (size_t)f->ldl * sizeof(double),
@@ -207,7 +222,7 @@ static int split_helper_serve(const char* shm_name, int device, double timeout_s
       int ph = 0;
       if (!split_wait(sh, timeout_s, [&] { ph = sh->phase.load(std::memory_order_acquire); return ph == 1 || ph == 4; })) break;
       if (ph == 4) break;
-      const int m = sh->m, n = sh->n, ldl = sh->ldl;
+      const int m = sh->m, n = sh->n, ldl = sh->ldl, base = sh->base;
       const bool ld_is_l = sh->ld_is_l != 0;
       const size_t bytes = (size_t)ldl * n * sizeof(double);
       double* mL = (double*)g_pool.alloc(bytes);
@@ -222,19 +237,19 @@ static int split_helper_serve(const char* shm_name, int device, double timeout_s
       Front* d_front = (Front*)g_pool.alloc(sizeof(Front));
       CUDA_TRY(cudaMemcpyAsync(d_front, &hf, sizeof(Front), cudaMemcpyHostToDevice, s));
       /* tile lists and regions of every panel, built up front (no failed pivot: panel k == block k) */
-      const int T = update_tile_size(true), mt = (m + T - 1) / T, nblk = (n + PW - 1) / PW;
+      const int T = update_tile_size(true), mt = (m + T - 1) / T, nblk = (n - base + PW - 1) / PW;
       std::vector<MatTile> tiles;
       std::vector<int4> regs(nblk);
       std::vector<size_t> first(nblk + 1, 0), split_at(nblk, 0);
       for (int k = 0; k < nblk; ++k) {
          first[k] = tiles.size();
-         for (int J = k + 2; split_block(J) < n; ++J) {
+         for (int J = k + 2; split_block(base, J) < n; ++J) {
             if (J == k + 3) split_at[k] = tiles.size() - first[k];
-            const int tj0 = split_block(J) / T, tj1 = (std::min(split_block(J + 1), n) - 1) / T;
+            const int tj0 = split_block(base, J) / T, tj1 = (std::min(split_block(base, J + 1), n) - 1) / T;
             for (int tj = tj0; tj <= tj1; ++tj)
                for (int ti = tj; ti < mt; ++ti) tiles.push_back({k, ti, tj});
          }
-         if (split_block(k + 3) >= n) split_at[k] = tiles.size() - first[k];      // block k+2 is the only (or no) far block
+         if (split_block(base, k + 3) >= n) split_at[k] = tiles.size() - first[k];      // block k+2 is the only (or no) far block
       }
       first[nblk] = tiles.size();
       MatTile* d_tiles = (MatTile*)g_pool.alloc(std::max<size_t>(tiles.size(), 1) * sizeof(MatTile));
@@ -256,7 +271,7 @@ static int split_helper_serve(const char* shm_name, int device, double timeout_s
             break;
          }
          /* the panel columns the owner announced; the region table entry is uploaded now (pageable, 16 bytes) */
-         regs[k] = make_int4(0, sh->k0[k], sh->k1[k], split_block(k + 2));
+         regs[k] = make_int4(0, sh->k0[k], sh->k1[k], split_block(base, k + 2));
          CUDA_TRY(cudaMemcpyAsync(d_regs + k, &regs[k], sizeof(int4), cudaMemcpyHostToDevice, s));
          const size_t nt_all = first[k + 1] - first[k], nt_a = split_at[k];
          if (nt_a) launch_update(d_front, d_tiles + first[k], (int)nt_a, UPD_EXPLICIT, true, s, 0, d_regs);

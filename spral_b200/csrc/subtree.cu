@@ -638,12 +638,23 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
 #ifdef SPRAL_B200_SPLIT
       /* distributed top front (split_front.h; protocol: tests/c/dist_front_emu.cpp): while the split is active the far
        * columns live on the helper; the first panel with a failed pivot brings them back and ends it */
-      bool split_now = false;
+      bool split_now = false, split_restart = false;
       int split_k = 0;
       if (N.split && N.split->active) {
-         split_k = H[act[0]].p0 / PW;
-         if (any_fail || !lookahead || na_all != 1 || H[act[0]].p0 % PW != 0) N.split->drain(split_k, split_k + 1, s, N.stream2);
-         else split_now = true;
+         const HostState& h0 = H[act[0]];
+         split_k = N.split->panel_of(h0.p0);
+         /* the split lives on full panels that are its blocks; a failed pivot (columns swapped across the front), a short
+          * panel (candidates parked at the end) or a new pass ends it */
+         if (any_fail || !lookahead || na_all != 1 || split_k < 0 || h0.pend0 != h0.p0 + PW) {
+            const int kd = std::max(0, (h0.p0 - N.split->p_first + PW - 1) / PW);      // panels the helper was given: 0 .. kd-1
+            N.split->drain(kd, kd + 1, s, N.stream2);
+         } else split_now = true;
+      } else if (N.split && N.split->level_ok && N.split->restart && !N.split->dead && !any_fail && lookahead && na_all == 1) {
+         /* a drained split starts again behind a clean full panel of the first pass order (sporadic failures must not
+          * cost the rest of a 64-panel front): this panel is still updated here, the far columns go out behind its bulk */
+         const HostState& h0 = H[act[0]];
+         const int* sn0 = &snap_host[0];
+         split_restart = sn0[6] >= 0 && h0.pend0 == h0.p0 + PW && sn0[1] == h0.pend0;
       }
 #endif
       for (int k = 0; k < na_all; ++k) {
@@ -748,6 +759,13 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          CUDA_TRY(cudaEventRecord(N.ev_bulk_all, s2));
          bulk_pending = true;
       }
+#ifdef SPRAL_B200_SPLIT
+      if (split_restart) {
+         /* the far columns got this panel's update on either stream: the main stream joins the bulk, then copies them */
+         if (bulk_pending) { CUDA_TRY(cudaStreamWaitEvent(s, N.ev_bulk_all, 0)); bulk_pending = false; }
+         N.split->begin_front(F[H[act[0]].fi], posdef, s, H[act[0]].pend0);
+      }
+#endif
       if (!swap_rows.empty()) {
          RowTile* d_sw = upload(bump, swap_rows, s);
          PROF(PC_SWAP, launch_swap(d_fronts, d_sw, (int)swap_rows.size(), true, s));
@@ -1097,11 +1115,13 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
       {
 #ifdef SPRAL_B200_SPLIT
          /* a single large front at the top of the root part: its far columns go to the helper GPU (split_front.h) */
-         if (N.split && nfl == 1 && big && g_lookahead) N.split->begin_front(F[f0], posdef, s);
+         if (N.split) N.split->level_ok = (nfl == 1 && big && g_lookahead);
+         if (N.split && N.split->level_ok) N.split->begin_front(F[f0], posdef, s);
 #endif
          int err = factor_fronts(N, N.d_fronts, F, lfronts, big, prm, S.b_retry, t_sync);
 #ifdef SPRAL_B200_SPLIT
          if (!err && N.split && N.split->active) throw std::runtime_error("split front: still active when the front is finished");
+         if (N.split) N.split->level_ok = false;
 #endif
          if (err) { st.flag = err; *stats = st; return; }
          int* d_lf = upload(bump, lfronts, s);

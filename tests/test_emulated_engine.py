@@ -57,7 +57,8 @@ def emu_split_lib(emu_env):
     return os.path.join(ROOT, "build", "emu_split", "libspral_ssids_b200_emu_split.so")
 
 
-@pytest.mark.parametrize("n,kind,expect", [(1300, "posdef", "4 panels pushed, 4 blocks pulled"), (1300, "indef", "drain at panel")])
+@pytest.mark.parametrize("n,kind,expect", [(1300, "posdef", "4 panels pushed, 4 blocks pulled"), (1300, "indef", "drain at panel"),
+                                           (2600, "indef", "panels from column 1278")])      # drained twice, re-started twice
 def test_distributed_top_front_end_to_end_on_the_emulator(emu_env, emu_split_lib, n, kind, expect):
     """csrc/split_front.h and its hooks in factor_fronts (`make SPLIT=1`, not run on GPUs yet) with the owner and the helper
     as two threads of one process on the emulator: a front that is split to its end (Cholesky) and one whose split is
