@@ -80,3 +80,15 @@ def test_two_process_gpu_path_with_split_on_the_emulator(emu_env, emu_split_lib,
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dist_split_check.py"), str(grid), kind],
                        env=dict(os.environ), capture_output=True, text=True, timeout=1700)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("client,ok", [("ssids_capi_check.c", "CAPI OK"), ("ssids_capi_coord_check.c", "CAPI COORD OK")])
+def test_c_clients_of_the_spral_ssids_h_interface_on_the_emulator(emu_env, tmp_path, client, ok):
+    """The C clients of include/spral_ssids_compat.h (the reference's C interface: analyse / analyse_coord, factor,
+    factor_ptr32, solve1, enquire, orderings, scalings) linked against the emulated library."""
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(EMU_LIB)
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", client), "-o", str(exe),
+                           "-L", libdir, "-lspral_ssids_b200_emu", "-lm", f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([str(exe)], env=emu_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and ok in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
