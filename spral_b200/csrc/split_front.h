@@ -38,6 +38,7 @@ struct SplitShm {
                                          // the helper answers 3 -> 0 when it has released the mirror), 4 exit (owner)
    std::atomic<int> error;               // raised by either side: the other gives up
    int m, n, ldl, ld_is_l;               // geometry of the front; ld_is_l: positive definite (L*D == L)
+   int nhelpers, helper_index;           // the far blocks are dealt round robin: block J >= 2 lives on helper (J - 2) % nhelpers
    int base;                             // first column of block 0 (a multiple of the update tile): 0, or where the split was re-started
    unsigned char h_L[64], h_LD[64];      // IPC handles of the helper's mirror
    std::atomic<int> ready[SPLIT_MAXP + 4];   // panel k is in the mirror (1) / the split ends here (SPLIT_DRAIN)
@@ -83,38 +84,48 @@ static SplitShm* split_map(const char* name, bool create) {
 }
 
 /* ---- owner side ---------------------------------------------------------------------------------------- */
+/* One shared-memory segment and one mirror per helper; the far blocks are dealt round robin: block J >= 2 lives on
+ * helper (J - 2) % H.  Every helper that still holds a block gets every panel. */
 struct SplitOwner {
-   SplitShm* sh = nullptr;
-   std::string name;
+   struct Link { SplitShm* sh = nullptr; std::string name; double* mL = nullptr; double* mLD = nullptr;
+                 int next_k = 0; };      // next_k: panels this helper was given (it waits for ready[next_k] next)
+   std::vector<Link> links;
    double timeout_s = 20.0;
    bool active = false;                  // a front is split right now
-   bool dead = false;                    // no helper answered: do not try again
+   bool dead = false;                    // a helper did not answer: do not try again
    bool level_ok = false;                // the level being factorised is one large front (set by factor_subtree)
    bool restart = true;                  // SPRAL_B200_SPLIT_RESTART=0: a drained split stays off for the rest of the front
    bool trace = getenv("SPRAL_B200_TRACE") != nullptr;
    int n_pushed = 0, n_pulled = 0;
    const Front* f = nullptr;             // host copy of its descriptor (owner's pointers)
    int base = 0;                         // block j = columns [base + j PW, base + (j + 1) PW): tile aligned, so that what the
-                                         // owner's urgent update touches (whole tile columns) ends where the helper's columns begin
+                                         // owner's urgent update touches (whole tile columns) ends where the helpers' columns begin
    int p_first = 0;                      // first column of panel 0 of this split (== base unless re-started off a tile boundary)
    int blk(int j) const { return split_block(base, j); }
-   double* mL = nullptr; double* mLD = nullptr;    // the helper's mirror, mapped here
+   int H() const { return (int)links.size(); }
+   Link& link_of(int J) { return links[(J - 2) % H()]; }
    std::vector<std::pair<std::vector<unsigned char>, void*>> opened;
 
-   static SplitOwner* create(const char* shm_name) {
-      shm_unlink(shm_name);
-      SplitShm* sh = split_map(shm_name, true);
-      if (!sh) return nullptr;
-      std::memset((void*)sh, 0, sizeof(SplitShm));
-      sh->magic.store(SPLIT_MAGIC, std::memory_order_release);
+   static std::string segment_name(const char* shm_name, int h) { return std::string(shm_name) + "_" + std::to_string(h); }
+   static SplitOwner* create(const char* shm_name, int nhelpers) {
       auto* o = new SplitOwner;
-      o->sh = sh; o->name = shm_name;
+      for (int h = 0; h < std::max(1, nhelpers); ++h) {
+         Link l;
+         l.name = segment_name(shm_name, h);
+         shm_unlink(l.name.c_str());
+         l.sh = split_map(l.name.c_str(), true);
+         if (!l.sh) { delete o; return nullptr; }
+         std::memset((void*)l.sh, 0, sizeof(SplitShm));
+         l.sh->magic.store(SPLIT_MAGIC, std::memory_order_release);
+         o->links.push_back(l);
+      }
       if (const char* e = getenv("SPRAL_B200_SPLIT_TIMEOUT")) o->timeout_s = atof(e);
       if (const char* e = getenv("SPRAL_B200_SPLIT_RESTART")) o->restart = atoi(e) != 0;
       return o;
    }
    ~SplitOwner() {
-      if (sh) { sh->phase.store(4, std::memory_order_release); munmap((void*)sh, sizeof(SplitShm)); shm_unlink(name.c_str()); }
+      for (Link& l : links)
+         if (l.sh) { l.sh->phase.store(4, std::memory_order_release); munmap((void*)l.sh, sizeof(SplitShm)); shm_unlink(l.name.c_str()); }
       for (auto& o : opened) cudaIpcCloseMemHandle(o.second);
    }
    void* open_handle(const unsigned char* h) {
@@ -125,91 +136,111 @@ struct SplitOwner {
       opened.push_back({std::vector<unsigned char>(h, h + 64), p});
       return p;
    }
+   void give_up() { for (Link& l : links) l.sh->phase.store(3, std::memory_order_release); dead = true; }
    /* Worth splitting: at least four blocks right of `first_col`, the first column of the next panel (0 at the start of a
     * front; where a drained split is re-started otherwise).  The far columns are copied on stream `s`, in order behind
-    * whatever updated them last.  Returns false (and leaves the front alone) when no helper answers. */
+    * whatever updated them last.  Returns false (and leaves the front alone) when a helper does not answer. */
    bool begin_front(const Front& fr, bool posdef, cudaStream_t s, int first_col = 0) {
       const int T = update_tile_size(true);
       const int b = split_round_up(first_col, T);
       if (active || dead || fr.n - b < 4 * PW || (fr.n - b + PW - 1) / PW > SPLIT_MAXP) return false;
-      /* the helper has released the previous front (3 -> 0) */
-      if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 0; })) { dead = true; return false; }
-      for (int k = 0; k < SPLIT_MAXP + 4; ++k) { sh->ready[k].store(0); sh->updated[k].store(0); }
-      sh->drained.store(0);
-      sh->m = fr.m; sh->n = fr.n; sh->ldl = fr.ldl; sh->ld_is_l = posdef ? 1 : 0; sh->base = b;
-      sh->phase.store(1, std::memory_order_release);
-      if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 2; })) {
-         sh->phase.store(3, std::memory_order_release);       // nobody there: the front stays whole
-         dead = true;
-         return false;
+      for (int h = 0; h < H(); ++h) {
+         SplitShm* sh = links[h].sh;
+         /* the helper has released the previous front (3 -> 0) */
+         if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 0; })) { dead = true; return false; }
+         for (int k = 0; k < SPLIT_MAXP + 4; ++k) { sh->ready[k].store(0); sh->updated[k].store(0); }
+         sh->drained.store(0);
+         sh->m = fr.m; sh->n = fr.n; sh->ldl = fr.ldl; sh->ld_is_l = posdef ? 1 : 0; sh->base = b;
+         sh->nhelpers = H(); sh->helper_index = h; links[h].next_k = 0;
+         sh->phase.store(1, std::memory_order_release);
       }
-      mL = static_cast<double*>(open_handle(sh->h_L));
-      mLD = posdef ? mL : static_cast<double*>(open_handle(sh->h_LD));
+      for (int h = 0; h < H(); ++h) {
+         SplitShm* sh = links[h].sh;
+         if (!split_wait(sh, timeout_s, [&] { return sh->phase.load(std::memory_order_acquire) == 2; })) { give_up(); return false; }
+         links[h].mL = static_cast<double*>(open_handle(sh->h_L));
+         links[h].mLD = posdef ? links[h].mL : static_cast<double*>(open_handle(sh->h_LD));
+      }
       f = &fr; base = b; p_first = first_col;
-      /* the far columns (blocks >= 2), rows from the first of them down */
-      const int c0 = blk(2);
-      const size_t off = (size_t)c0 + (size_t)c0 * fr.ldl;
-      CUDA_TRY(cudaMemcpy2DAsync(mL + off, (size_t)fr.ldl * sizeof(double), fr.L + off, (size_t)fr.ldl * sizeof(double),
-                                 (size_t)(fr.m - c0) * sizeof(double), fr.n - c0, cudaMemcpyDefault, s));
+      /* the far blocks, each to the helper that owns it, rows from its first column down */
+      for (int J = 2; blk(J) < fr.n; ++J) {
+         const int c0 = blk(J), c1 = std::min(blk(J + 1), fr.n);
+         const size_t off = (size_t)c0 + (size_t)c0 * fr.ldl;
+         CUDA_TRY(cudaMemcpy2DAsync(link_of(J).mL + off, (size_t)fr.ldl * sizeof(double), fr.L + off, (size_t)fr.ldl * sizeof(double),
+                                    (size_t)(fr.m - c0) * sizeof(double), c1 - c0, cudaMemcpyDefault, s));
+      }
       active = true; n_pushed = n_pulled = 0;
-      if (trace) fprintf(stderr, "[split] front m %d n %d: far columns %d.. on the helper (panels from column %d)\n", fr.m, fr.n, c0, first_col);
+      if (trace) fprintf(stderr, "[split] front m %d n %d: far columns %d.. on %d helper(s) (panels from column %d)\n", fr.m, fr.n,
+                         blk(2), H(), first_col);
       return true;
    }
    /* panel index of the panel that starts at column p0, or -1 when the panels are no longer the split's blocks */
    int panel_of(int p0) const { return (p0 >= p_first && (p0 - p_first) % PW == 0) ? (p0 - p_first) / PW : -1; }
    bool has_far(int k) const { return blk(k + 2) < f->n; }
-   /* Panel k = columns [k0, k1): rows of the far blocks into the mirror, then ready[k] (copy stream). */
+   /* helper h still holds a block >= J0 */
+   bool holds_from(int h, int J0) const {
+      for (int J = std::max(2, J0); blk(J) < f->n; ++J) if ((J - 2) % (int)links.size() == h) return true;
+      return false;
+   }
+   /* Panel k = columns [k0, k1): rows of the far blocks into the mirror of every helper that still holds one, then
+    * ready[k] (copy stream). */
    void push_panel(int k, int k0, int k1, cudaStream_t s2) {
       const int r0 = blk(k + 2);
       const size_t off = (size_t)r0 + (size_t)k0 * f->ldl;
       const size_t pitch = (size_t)f->ldl * sizeof(double), width = (size_t)(f->m - r0) * sizeof(double);
-      CUDA_TRY(cudaMemcpy2DAsync(mL + off, pitch, f->L + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
-      if (mLD != mL) CUDA_TRY(cudaMemcpy2DAsync(mLD + off, pitch, f->LD + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
-      sh->k0[k] = k0; sh->k1[k] = k1;
-      split_raise_behind(s2, &sh->ready[k], 1);
+      for (int h = 0; h < H(); ++h) {
+         if (!holds_from(h, k + 2)) continue;
+         Link& l = links[h];
+         CUDA_TRY(cudaMemcpy2DAsync(l.mL + off, pitch, f->L + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
+         if (l.mLD != l.mL) CUDA_TRY(cudaMemcpy2DAsync(l.mLD + off, pitch, f->LD + off, pitch, width, k1 - k0, cudaMemcpyDefault, s2));
+         l.sh->k0[k] = k0; l.sh->k1[k] = k1;
+         split_raise_behind(s2, &l.sh->ready[k], 1);
+         l.next_k = k + 1;
+      }
       ++n_pushed;
+   }
+   void pull_block(int J, cudaStream_t s) {
+      const int c0 = blk(J), c1 = std::min(blk(J + 1), f->n);
+      const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
+      CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), link_of(J).mL + off, (size_t)f->ldl * sizeof(double),
+                                 (size_t)(f->m - c0) * sizeof(double), c1 - c0, cudaMemcpyDefault, s));
+      ++n_pulled;
    }
    /* Block J comes back (main stream), in order before the urgent update that touches it. */
    void need_block(int J, cudaStream_t s) {
       if (J < 2 || blk(J) >= f->n) return;
+      SplitShm* sh = link_of(J).sh;
       if (!split_wait(sh, timeout_s, [&] { return sh->updated[J].load(std::memory_order_acquire) != 0; })) {
          sh->error.store(1, std::memory_order_release);
-         throw std::runtime_error("split front: the helper did not return a block in time");
+         throw std::runtime_error("split front: a helper did not return a block in time");
       }
-      const int c0 = blk(J), c1 = std::min(blk(J + 1), f->n);
-      const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
-      CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), mL + off, (size_t)f->ldl * sizeof(double),
-                                 (size_t)(f->m - c0) * sizeof(double), c1 - c0, cudaMemcpyDefault, s));
-      ++n_pulled;
+      pull_block(J, s);
    }
-   /* The split ends at panel k (failed pivot, or nothing is left on the helper): every column the helper
-    * still holds -- blocks >= first_block -- comes back; the helper has applied panels 0 .. k-1 to them. */
+   /* The split ends at panel k (failed pivot, short panel): every block the helpers still hold -- J >= first_block --
+    * comes back; they have applied panels 0 .. k-1 to them. */
    void drain(int k, int first_block, cudaStream_t s, cudaStream_t s2) {
       CUDA_TRY(cudaStreamSynchronize(s2));                     // every pushed panel has been announced
       if (trace) fprintf(stderr, "[split] drain at panel %d (%d panels pushed, %d blocks pulled)\n", k, n_pushed, n_pulled);
-      sh->ready[k].store(SPLIT_DRAIN, std::memory_order_release);
-      if (!split_wait(sh, timeout_s, [&] { return sh->drained.load(std::memory_order_acquire) != 0; })) {
-         sh->error.store(1, std::memory_order_release);
-         throw std::runtime_error("split front: the helper did not drain in time");
-      }
-      const int c0 = blk(std::max(2, first_block));
-      if (c0 < f->n) {
-         const size_t off = (size_t)c0 + (size_t)c0 * f->ldl;
-         CUDA_TRY(cudaMemcpy2DAsync(f->L + off, (size_t)f->ldl * sizeof(double), mL + off, (size_t)f->ldl * sizeof(double),
-                                    (size_t)(f->m - c0) * sizeof(double), f->n - c0, cudaMemcpyDefault, s));
-      }
+      for (Link& l : links) l.sh->ready[l.next_k].store(SPLIT_DRAIN, std::memory_order_release);   // where that helper waits
+      for (Link& l : links)
+         if (!split_wait(l.sh, timeout_s, [&] { return l.sh->drained.load(std::memory_order_acquire) != 0; })) {
+            l.sh->error.store(1, std::memory_order_release);
+            throw std::runtime_error("split front: a helper did not drain in time");
+         }
+      for (int J = std::max(2, first_block); blk(J) < f->n; ++J) pull_block(J, s);
       end_front(s);
    }
    void end_front(cudaStream_t s) {
-      CUDA_TRY(cudaStreamSynchronize(s));                      // the copies out of the mirror are done
+      CUDA_TRY(cudaStreamSynchronize(s));                      // the copies out of the mirrors are done
       if (trace) fprintf(stderr, "[split] front closed (%d panels pushed, %d blocks pulled)\n", n_pushed, n_pulled);
-      sh->phase.store(3, std::memory_order_release);
+      for (Link& l : links) l.sh->phase.store(3, std::memory_order_release);
       active = false; f = nullptr;
    }
 };
 
 /* ---- helper side --------------------------------------------------------------------------------------- */
-static int split_helper_serve(const char* shm_name, int device, double timeout_s) {
+static int split_helper_serve(const char* shm_name_base, int device, double timeout_s, int helper_index) {
+   const std::string seg = SplitOwner::segment_name(shm_name_base, helper_index);
+   const char* shm_name = seg.c_str();
    CUDA_TRY(cudaSetDevice(device));
    SplitShm* sh = nullptr;
    if (!split_wait(nullptr, timeout_s, [&] { sh = split_map(shm_name, false); return sh != nullptr; })) return 1;   // no owner showed up
@@ -224,6 +255,7 @@ static int split_helper_serve(const char* shm_name, int device, double timeout_s
       if (ph == 4) break;
       const int m = sh->m, n = sh->n, ldl = sh->ldl, base = sh->base;
       const bool ld_is_l = sh->ld_is_l != 0;
+      const int Hn = std::max(1, sh->nhelpers), hidx = sh->helper_index;
       const size_t bytes = (size_t)ldl * n * sizeof(double);
       double* mL = (double*)g_pool.alloc(bytes);
       double* mLD = ld_is_l ? mL : (double*)g_pool.alloc(bytes);
@@ -245,6 +277,7 @@ static int split_helper_serve(const char* shm_name, int device, double timeout_s
          first[k] = tiles.size();
          for (int J = k + 2; split_block(base, J) < n; ++J) {
             if (J == k + 3) split_at[k] = tiles.size() - first[k];
+            if ((J - 2) % Hn != hidx) continue;                     // another helper's block
             const int tj0 = split_block(base, J) / T, tj1 = (std::min(split_block(base, J + 1), n) - 1) / T;
             for (int tj = tj0; tj <= tj1; ++tj)
                for (int ti = tj; ti < mt; ++ti) tiles.push_back({k, ti, tj});
@@ -275,7 +308,7 @@ static int split_helper_serve(const char* shm_name, int device, double timeout_s
          CUDA_TRY(cudaMemcpyAsync(d_regs + k, &regs[k], sizeof(int4), cudaMemcpyHostToDevice, s));
          const size_t nt_all = first[k + 1] - first[k], nt_a = split_at[k];
          if (nt_a) launch_update(d_front, d_tiles + first[k], (int)nt_a, UPD_EXPLICIT, true, s, 0, d_regs);
-         split_raise_behind(s, &sh->updated[k + 2], 1);            // block k+2 may go back
+         if (k % Hn == hidx) split_raise_behind(s, &sh->updated[k + 2], 1);   // block k+2 (this helper's) may go back
          if (nt_all > nt_a) launch_update(d_front, d_tiles + first[k] + nt_a, (int)(nt_all - nt_a), UPD_EXPLICIT, true, s, 0, d_regs);
       }
       if (!ok) sh->error.store(2, std::memory_order_release);

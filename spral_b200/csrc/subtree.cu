@@ -215,6 +215,7 @@ struct Symbolic {
    Buf b_segws;                       // chain workspaces of the speculative panel segments (panel_v2.h)
 #ifdef SPRAL_B200_SPLIT
    std::string split_shm;             // shared-memory name of the split protocol (set for the root part only)
+   int split_helpers = 1;             // helper ranks that serve it
 #endif
 
    ~Symbolic() {
@@ -830,7 +831,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
 #ifdef SPRAL_B200_SPLIT
    /* the segment exists for the whole part, so that the helper -- which arrives when its own parts are done, before
     * this part can end -- always finds it and always sees its end (phase 4 in ~SplitOwner) */
-   if (!S.split_shm.empty()) N.split = SplitOwner::create(S.split_shm.c_str());
+   if (!S.split_shm.empty()) N.split = SplitOwner::create(S.split_shm.c_str(), S.split_helpers);
 #endif
    Prof prof;
    struct ProfScope { ProfScope(Prof* p) { g_prof = g_profile ? p : nullptr; } ~ProfScope() { g_prof = nullptr; } } prof_scope(&prof);
@@ -1605,13 +1606,14 @@ void spral_ssids_b200_set_profile(int on) {
  * for the part that holds the top of the tree, before it factorises it.  serve: called by the helper rank once
  * its own parts are done; returns when the owner's part is finished (0), when no owner showed up (1) or no
  * front was split (2), or the raw cudaError_t. */
-void spral_ssids_b200_split_enable(void* symbolic_subtree, const char* shm_name) {
+void spral_ssids_b200_split_enable(void* symbolic_subtree, const char* shm_name, int nhelpers) {
    ABI_GUARD();
    static_cast<Symbolic*>(symbolic_subtree)->split_shm = shm_name ? shm_name : "";
+   static_cast<Symbolic*>(symbolic_subtree)->split_helpers = std::max(1, nhelpers);
 }
-int spral_ssids_b200_split_helper_serve(const char* shm_name, int device, double timeout_s) {
+int spral_ssids_b200_split_helper_serve(const char* shm_name, int device, double timeout_s, int helper_index) {
    ABI_GUARD();
-   try { return split_helper_serve(shm_name, device, timeout_s); }
+   try { return split_helper_serve(shm_name, device, timeout_s, helper_index); }
    catch (const CudaError& e) {
       fprintf(stderr, "spral_ssids_b200: CUDA error %d (%s) in the split helper\n", (int)e.code, cudaGetErrorString(e.code));
       return (int)e.code;

@@ -431,9 +431,9 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
                   f"publish {1e3*(t_p3-t_p2):.1f} ms, flops {st.num_flops:.3g}", file=sys.stderr, flush=True)
 
     mine = [p for p in range(nparts) if ak.rank_of[p] == ctx.rank]
-    split = _split_roles(ctx, ak)                # distributed top front: (shm name, owner rank, helper rank) or None
+    split = _split_roles(ctx, ak)                # distributed top front: (shm name, owner rank, helper ranks) or None
     if split and ctx.rank == split[1]:
-        _lib.load().spral_ssids_b200_split_enable(ak.subtrees[nparts - 1]._h, split[0].encode())
+        _lib.load().spral_ssids_b200_split_enable(ak.subtrees[nparts - 1]._h, split[0].encode(), len(split[2]))
     nthreads = max(1, int(os.environ.get("SPRAL_B200_PART_THREADS", "2")))
     if not ctx.engine.device_ipc or len(mine) <= 1:
         nthreads = 1
@@ -444,10 +444,11 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
             futures[p] = ex.submit(run_part, p)
         for p in mine:
             futures[p].result()
-    if split and ctx.rank == split[2]:
+    if split and ctx.rank in split[2]:
         # this rank's parts are done: serve the owner of the top fronts until its part is finished
         rc = _lib.load().spral_ssids_b200_split_helper_serve(split[0].encode(), ctx.local_rank,
-                                                             float(os.environ.get("SPRAL_B200_SPLIT_TIMEOUT", "20")))
+                                                             float(os.environ.get("SPRAL_B200_SPLIT_TIMEOUT", "20")),
+                                                             split[2].index(ctx.rank))
         if trace:
             print(f"[trace r{ctx.rank} e{ctx.epoch}] split helper returned {rc}", file=sys.stderr, flush=True)
     return DistFkeep(ak, posdef, numeric, finish_inform(a, inform), ext_rows, sc, ctx.epoch)
@@ -456,20 +457,22 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
 def _split_roles(ctx, ak):
     """SPRAL_B200_SPLIT=1 with a library built with -DSPRAL_B200_SPLIT (csrc/split_front.h; opt-in, not run on GPUs
     yet): the rank that owns the last part (the top of the tree) offloads the far columns of its large fronts to the
-    next rank.  Returns (shared-memory name, owner, helper) or None."""
+    other ranks (SPRAL_B200_SPLIT_HELPERS caps their number; the far blocks are dealt round robin).  Returns (shared-memory
+    name, owner, [helper ranks]) or None."""
     if os.environ.get("SPRAL_B200_SPLIT") != "1" or ctx.world < 2 or not ctx.engine.device_ipc:
         return None
     lib = _lib.load()
     if not hasattr(lib, "spral_ssids_b200_split_helper_serve"):
         return None
-    lib.spral_ssids_b200_split_enable.argtypes = [C.c_void_p, C.c_char_p]
+    lib.spral_ssids_b200_split_enable.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.spral_ssids_b200_split_enable.restype = None
-    lib.spral_ssids_b200_split_helper_serve.argtypes = [C.c_char_p, C.c_int, C.c_double]
+    lib.spral_ssids_b200_split_helper_serve.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int]
     lib.spral_ssids_b200_split_helper_serve.restype = C.c_int
     owner = ak.rank_of[ak.analysis.nparts - 1]
-    helper = (owner + 1) % ctx.world
+    nh = max(1, min(ctx.world - 1, int(os.environ.get("SPRAL_B200_SPLIT_HELPERS", str(ctx.world - 1)))))
+    helpers = [(owner + 1 + i) % ctx.world for i in range(nh)]
     name = f"/spral_b200_split_{os.environ.get('MASTER_PORT', '0')}_{ctx.epoch}"
-    return name, owner, helper
+    return name, owner, helpers
 
 
 def reduce_inform(ctx, inform):

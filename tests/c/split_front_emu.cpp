@@ -161,12 +161,12 @@ static int run_case(int m, int n, int fail_at, bool posdef_like, unsigned seed, 
    std::vector<double> L(A), LD((size_t)ldl * n, 0.0);
    int helper_rc = -99;
    std::thread helper([&] {
-      try { helper_rc = split_helper_serve(shm.c_str(), 0, 10.0); }
+      try { helper_rc = split_helper_serve(shm.c_str(), 0, 10.0, 0); }
       catch (const std::exception& e) { printf("helper: %s\n", e.what()); helper_rc = -1; }
    });
    cudaStream_t s = nullptr, s2 = nullptr;
    cudaStreamCreateWithFlags(&s, 0); cudaStreamCreateWithFlags(&s2, 0);
-   SplitOwner* sp = SplitOwner::create(shm.c_str());
+   SplitOwner* sp = SplitOwner::create(shm.c_str(), 1);
    if (!sp) throw std::runtime_error("cannot create the shared-memory segment");
    sp->timeout_s = 10.0;
    Front f;

@@ -3,7 +3,7 @@ GpuEngine, contribution blocks handed over by "CUDA IPC", the distributed top fr
 helper rank talking through POSIX shared memory) -- as two real processes over gloo, on the SIMT emulator of tests/emu
 with shared-memory-backed "device" memory (SPRAL_B200_EMU_SHM=1), so that an IPC handle can be opened by the other
 process.  The only thing injected is where the right-hand sides live (torch has no CUDA device here).
-usage: dist_split_check.py [grid=28] [stencil|lap]   prints one JSON line; exit code 0 when everything agrees."""
+usage: dist_split_check.py [grid=28] [stencil|lap] [ranks=2]   prints one JSON line; exit code 0 when everything agrees."""
 import json
 import multiprocessing as mp
 import os
@@ -72,24 +72,25 @@ def _worker(rank, world, port, grid, kind, logdir, q):
 def main():
     grid = int(sys.argv[1]) if len(sys.argv) > 1 else 28
     kind = sys.argv[2] if len(sys.argv) > 2 else "stencil"       # stencil: 27-point indefinite; lap: 7-point Laplacian, Cholesky
+    world = int(sys.argv[3]) if len(sys.argv) > 3 else 2             # ranks: one owner of the top fronts, world - 1 helpers
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     with tempfile.TemporaryDirectory() as logdir:
-        procs = [ctxm.Process(target=_worker, args=(r, 2, port, grid, kind, logdir, q)) for r in range(2)]
+        procs = [ctxm.Process(target=_worker, args=(r, world, port, grid, kind, logdir, q)) for r in range(world)]
         for p in procs:
             p.start()
         res = dict(q.get(timeout=1700) for _ in procs)
         for p in procs:
             p.join(timeout=60)
-        logs = "".join(open(os.path.join(logdir, f"rank{r}.log")).read() for r in range(2))
+        logs = "".join(open(os.path.join(logdir, f"rank{r}.log")).read() for r in range(world))
     split_lines = [l for l in logs.splitlines() if l.startswith("[split]") or "split helper returned" in l]
     ok = all("error" not in res[r] for r in res)
     if ok:
         r0 = res[0]
-        ok = (r0["inform"] == r0["single"] and r0["bwd"] < 5e-11 and r0["maxdiff"] < 1e-9 and res[1]["inform"] == r0["inform"]
+        ok = (r0["inform"] == r0["single"] and r0["bwd"] < 5e-11 and r0["maxdiff"] < 1e-9 and all(res[r]["inform"] == r0["inform"] for r in res)
               and any("panels pushed" in l and "front closed" in l and not l.startswith("[split] front closed (0 ") for l in split_lines)
-              and any("split helper returned 0" in l for l in split_lines))
+              and sum("split helper returned 0" in l for l in split_lines) >= 2 * (world - 1))
     print(json.dumps(dict(ok=ok, res=res, split=split_lines[-8:], log=None if ok else logs[-3000:])))
     for f in os.listdir("/dev/shm"):
         if f.startswith("spral_emu_") and any(f.startswith(f"spral_emu_{p.pid}_") for p in procs):

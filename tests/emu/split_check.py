@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE (CPU only): the distributed top front END TO END on the SIMT emulator -- the library built with
 -DSPRAL_B200_SPLIT (tests/emu/build_emu.py split), the owner's factorisation in this thread, the helper's service loop
 (spral_ssids_b200_split_helper_serve) in another, one dense front.  The factors and the solution must equal the ones of
-the same library without a helper, bit for bit.  usage: split_check.py n indef|posdef|saddle"""
+the same library without a helper, bit for bit.  usage: split_check.py n indef|posdef|saddle [helpers=1]"""
 import sys, os, time, threading, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 os.environ.setdefault("OMP_CANCELLATION", "TRUE")
@@ -13,11 +13,12 @@ import spral_b200 as sb
 from spral_b200 import matrices as M
 import oracle_ref
 lib = _lib.load()
-lib.spral_ssids_b200_split_enable.argtypes = [C.c_void_p, C.c_char_p]
-lib.spral_ssids_b200_split_helper_serve.argtypes = [C.c_char_p, C.c_int, C.c_double]
+lib.spral_ssids_b200_split_enable.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+lib.spral_ssids_b200_split_helper_serve.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int]
 lib.spral_ssids_b200_split_helper_serve.restype = C.c_int
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1300
 kind = sys.argv[2] if len(sys.argv) > 2 else "indef"
+NH = int(sys.argv[3]) if len(sys.argv) > 3 else 1          # helper threads
 rng = np.random.default_rng(n)
 A = rng.uniform(-1, 1, (n, n)); A = (A + A.T) / 2
 posdef = kind == "posdef"
@@ -33,13 +34,16 @@ for split in (False, True):
     name = f"/spral_b200_emu_split_{os.getpid()}".encode()
     rc = [None]
     if split:
-        lib.spral_ssids_b200_split_enable(ak.subtrees[-1]._h, name)
-        th = threading.Thread(target=lambda: rc.__setitem__(0, lib.spral_ssids_b200_split_helper_serve(name, 0, 30.0)))
-        th.start()
+        lib.spral_ssids_b200_split_enable(ak.subtrees[-1]._h, name, NH)
+        rcs = [None] * NH
+        ths = [threading.Thread(target=lambda h=h: rcs.__setitem__(h, lib.spral_ssids_b200_split_helper_serve(name, 0, 30.0, h))) for h in range(NH)]
+        for th in ths: th.start()
     t = time.time()
     fk = sb.factor(ak, posdef, val)
     dt = time.time() - t
-    if split: th.join()
+    if split:
+        for th in ths: th.join()
+        rc[0] = max(rcs)
     X = sb.solve(fk, B)
     piv, d = fk.numeric[0].enquire()
     res[split] = (fk.inform, X, d)

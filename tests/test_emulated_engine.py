@@ -57,27 +57,27 @@ def emu_split_lib(emu_env):
     return os.path.join(ROOT, "build", "emu_split", "libspral_ssids_b200_emu_split.so")
 
 
-@pytest.mark.parametrize("n,kind,expect", [(1300, "posdef", "4 panels pushed, 4 blocks pulled"), (1300, "indef", "drain at panel"),
-                                           (2600, "indef", "panels from column 1278")])      # drained twice, re-started twice
-def test_distributed_top_front_end_to_end_on_the_emulator(emu_env, emu_split_lib, n, kind, expect):
+@pytest.mark.parametrize("n,kind,helpers,expect", [(1300, "posdef", 1, "4 panels pushed, 4 blocks pulled"), (1300, "indef", 1, "drain at panel"),
+                                                   (2600, "indef", 3, "panels from column 1278")])      # three helpers; drained twice, re-started twice
+def test_distributed_top_front_end_to_end_on_the_emulator(emu_env, emu_split_lib, n, kind, helpers, expect):
     """csrc/split_front.h and its hooks in factor_fronts (`make SPLIT=1`, not run on GPUs yet) with the owner and the helper
     as two threads of one process on the emulator: a front that is split to its end (Cholesky) and one whose split is
     drained by a failed pivot give the factors and solutions of the unsplit run bit for bit."""
     env = dict(emu_env, SPRAL_B200_EMU_LIB=emu_split_lib, SPRAL_B200_TRACE="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "split_check.py"), str(n), kind], env=env,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "split_check.py"), str(n), kind, str(helpers)], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "BITWISE IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert expect in r.stderr, r.stderr[-2000:]
 
 
 @pytest.mark.skipif(os.environ.get("SPRAL_B200_SLOW_TESTS") != "1", reason="3 minutes: set SPRAL_B200_SLOW_TESTS=1")
-@pytest.mark.parametrize("grid,kind", [(28, "stencil"), (34, "lap")])
-def test_two_process_gpu_path_with_split_on_the_emulator(emu_env, emu_split_lib, grid, kind):
+@pytest.mark.parametrize("grid,kind,ranks", [(28, "stencil", 2), (34, "lap", 3)])
+def test_two_process_gpu_path_with_split_on_the_emulator(emu_env, emu_split_lib, grid, kind, ranks):
     """spral_b200/dist.py on its real GPU code path (GpuEngine, contribution blocks by "CUDA IPC", the distributed top
     front between an owner and a helper rank) as two processes over gloo, "device" memory in POSIX shared memory
     (tests/emu/dist_split_check.py): inertia and statistics equal the single-process run, solutions agree; the indefinite
     problem drains the split at a failed pivot, the Cholesky problem runs it to its end (4 panels out, 4 blocks back)."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dist_split_check.py"), str(grid), kind],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dist_split_check.py"), str(grid), kind, str(ranks)],
                        env=dict(os.environ), capture_output=True, text=True, timeout=1700)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
