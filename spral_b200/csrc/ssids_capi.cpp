@@ -26,7 +26,7 @@ enum { OK = 0, E_CALL_SEQUENCE = -1, E_A_N_OOR = -2, E_A_PTR = -3, E_A_ALL_OOR =
        E_X_SIZE = -10, E_JOB_OOR = -11, E_NOT_LLT = -13, E_NOT_LDLT = -14, E_ALLOCATION = -50,
        E_NO_SAVED_SCALING = -15, E_UNIMPLEMENTED = -98,
        W_IDX_OOR = 1, W_DUP_IDX = 2, W_DUP_AND_OOR = 3, W_MISSING_DIAGONAL = 4, W_MISS_DIAG_OORDUP = 5,
-       W_ANAL_SINGULAR = 6, W_FACT_SINGULAR = 7 };
+       W_ANAL_SINGULAR = 6, W_FACT_SINGULAR = 7, W_MATCH_ORD_NO_SCALE = 8 };
 
 struct Akeep {
    int n = 0;
@@ -37,9 +37,9 @@ struct Akeep {
    std::vector<double> mo_scaling;      // scaling found by the matching-based ordering (options%ordering = 2)
    bool analyse_only = false;           // built with SPRAL_B200_ANALYSE_ONLY: cannot be factorised
    spral_ssids_b200_analysis* an = nullptr;
-   spral_ssids_b200_analysis_view v;
+   spral_ssids_b200_analysis_view v{};
    std::vector<void*> symbolic;         // one per part
-   spral_ssids_inform inform;           // analyse-time values
+   spral_ssids_inform inform{};         // analyse-time values (the flag of a failed analyse included)
    ~Akeep() {
       for (void* s : symbolic) if (s) spral_ssids_gpu_destroy_symbolic_subtree(s);
       if (an) spral_ssids_b200_analysis_free(an);
@@ -138,14 +138,17 @@ void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int
    if (!A) { inf->flag = E_ALLOCATION; return; }
    *akeep = A;
    A->n = n; A->check = check;
+   /* every error exit leaves the flag in the akeep as well: a later ssids_factor then answers
+    * SSIDS_ERROR_CALL_SEQUENCE (ssids.f90:806-811) instead of walking a half-built analysis */
+   auto fail = [&](int flag) { inf->flag = flag; A->inform = *inf; };
    int wflag = OK;
    if (coord_ne >= 0) {                 /* coordinate input: always cleaned; `row` / coord_col are the triplets */
       A->check = true; check = true;
       wflag = clean_coord(n, base, coord_ne, row, coord_col, *A, inf);
-      if (wflag < 0) { inf->flag = wflag; return; }
+      if (wflag < 0) { fail(wflag); return; }
    } else if (check) {
       wflag = clean_matrix(n, base, ptr, row, *A, inf);
-      if (wflag < 0) { inf->flag = wflag; return; }
+      if (wflag < 0) { fail(wflag); return; }
    } else {
       A->ptr.resize(n + 1);
       for (int j = 0; j <= n; ++j) A->ptr[j] = ptr[j] - base + 1;
@@ -157,20 +160,20 @@ void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int
    /* ordering (ssids.f90:287-353) */
    std::vector<int> ord(n);
    if (opt->ordering == 0) {
-      if (!order) { inf->flag = E_ORDER; return; }
+      if (!order) { fail(E_ORDER); return; }
       std::vector<char> seen(n + 1, 0);
       for (int i = 0; i < n; ++i) {
          int p = order[i] - base + 1;
-         if (p < 1 || p > n || seen[p]) { inf->flag = E_ORDER; return; }
+         if (p < 1 || p > n || seen[p]) { fail(E_ORDER); return; }
          seen[p] = 1; ord[i] = p;
       }
    } else if (opt->ordering == 1) {
       int rc = spral_ssids_b200_metis_order(n, A->ptr.data(), A->row.data(), ord.data());
-      if (rc != 0) { inf->flag = rc; return; }
+      if (rc != 0) { fail(rc); return; }
    } else if (opt->ordering == 2) {
       /* matching-based ordering (ssids.f90:312-353): needs the values; the scaling is kept for
        * options%scaling = 3 at factor time */
-      if (!val) { inf->flag = E_VAL; return; }
+      if (!val) { fail(E_VAL); return; }
       std::vector<double> cleaned;
       const double* aval = val;
       if (check) {
@@ -181,12 +184,13 @@ void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int
       }
       A->mo_scaling.resize(n);
       int rc = spral_ssids_b200_match_order_metis(n, A->ptr.data(), A->row.data(), aval, ord.data(), A->mo_scaling.data());
-      if (rc < 0) { inf->flag = (rc == -1 || rc == -50) ? E_ALLOCATION : rc; return; }
+      if (rc < 0) { fail((rc == -1 || rc == -50) ? E_ALLOCATION : rc); return; }
       if (rc == 1) wflag = W_ANAL_SINGULAR;
-   } else { inf->flag = E_ORDER; return; }
+   } else { fail(E_ORDER); return; }
    int aflag = 0;
    A->an = spral_ssids_b200_analyse(n, A->ptr.data(), A->row.data(), ord.data(), opt->nemin, -1,
                                     0, opt->max_load_inbalance, opt->gpu_perf_coeff, &aflag);
+   if (!A->an) { fail(aflag < 0 ? aflag : E_ALLOCATION); return; }
    spral_ssids_b200_analysis_get(A->an, &A->v);
    if (order) for (int i = 0; i < n; ++i) order[i] = ord[i] - 1 + base;
    spral_ssids_b200_options eo = engine_options(opt);
@@ -199,7 +203,7 @@ void analyse_common(bool check, int n, int* order, const int64_t* ptr, const int
       int lo = A->v.contrib_ptr[p] - 1, hi = A->v.contrib_ptr[p + 1] - 1;
       void* s = spral_ssids_gpu_create_symbolic_subtree(0, n, A->v.part[p], A->v.part[p + 1], A->v.sptr,
             A->v.sparent, A->v.rptr, A->v.rlist, A->v.nptr, A->v.nlist, hi - lo, A->v.contrib_dest + lo, &eo);
-      if (!s) { inf->flag = -51; return; }
+      if (!s) { fail(-51); return; }
       A->symbolic.push_back(s);
    }
    /* inform (anal.F90:1100-1116) */
@@ -289,6 +293,7 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
    if (!A) { inform->flag = E_CALL_SEQUENCE; return; }
    *inform = A->inform;
    if (A->inform.flag < 0 || A->analyse_only) { inform->flag = E_CALL_SEQUENCE; return; }
+   if (A->n > 0 && (!A->an || (int)A->symbolic.size() != A->v.nparts)) { inform->flag = E_CALL_SEQUENCE; return; }
    /* options%scaling (ssids.f90:899-1028): <= 0 user vector, 1 Hungarian (MC64), 4.. equilibration;
     * 2 auction, 3 the scaling of the matching-based ordering (options%ordering = 2) */
    if (options->scaling == 3 && A->mo_scaling.empty()) { inform->flag = E_NO_SAVED_SCALING; return; }
@@ -359,8 +364,11 @@ void spral_ssids_factor(bool posdef, const int64_t*, const int*, const double* v
       int idx = A->v.contrib_idx[p] - 1;
       if (idx < np) spral_ssids_b200_contrib_fill(&slots[idx], posdef, ns, true);
    }
-   if (inform->matrix_rank < n && inform->flag >= 0 && inform->flag != W_FACT_SINGULAR
-       && A->inform.flag != W_ANAL_SINGULAR) inform->flag = W_FACT_SINGULAR;
+   /* rank deficient: always WARNING_FACT_SINGULAR, whatever the analyse phase warned (ssids.f90:1050-1058;
+    * action = false never gets here: the engine returned -5) */
+   if (inform->matrix_rank < n && inform->flag >= 0) inform->flag = W_FACT_SINGULAR;
+   /* matching-based ordering without its scaling (ssids.f90:1060-1063) */
+   else if (inform->flag >= 0 && !A->mo_scaling.empty() && options->scaling != 3) inform->flag = W_MATCH_ORD_NO_SCALE;
 }
 
 void spral_ssids_solve(int job, int nrhs, double* x, int ldx, void* akeep, void* fkeep,
