@@ -16,6 +16,9 @@ e2e    = num_flops / wall time of the same call through the C ABI with the HOST
 roofline = the Schur-complement DMMA kernel (k_update, UPD_CONTRIB launches):
          algorithmic flops (m-n)(m-n+1)*nelim per front / CUDA-event time of those
          launches, against the FP64 tensor-pipe peak measured live on this GPU
+The reference arm (--impl reference) and the cpu_baseline leg factorise THE SAME workload
+(same matrix, ordering and options) with the reference's own CPU engine on all host cores,
+and time its solves (1 and nrhs right-hand sides) beside it.
 """
 import argparse
 import json
@@ -39,7 +42,7 @@ _FULL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") els
 import numpy as np  # noqa: E402
 
 SHIFT = 13.0
-CPU_SAMPLE_GRID = 72      # the CPU arms factor the same stencil on a smaller grid
+REF_MAX_STEPS = 2         # the reference arm times at most this many full factorisations (one takes 10-50 s of CPU)
 
 
 def make_matrix(grid):
@@ -162,18 +165,31 @@ def hbm_peak_gbs():
         return 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this round (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the
+    .ncu-rep).  None when no capture of the current kernel is committed -- never a constant from an older one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            d = json.load(fh)
+        return float(d["dram_bytes_per_launch"]), d.get("note", "")
+    except Exception:
+        return None, "no ncu --set full capture of this kernel committed for this round"
+
+
 def assembly_algorithmic_bytes(a):
     """Extend-add traffic of one factorisation without delays: every child contribution
     entry is read once and its parent entry read and written, (m-n)(m-n+1)/2 entries x 24 B per
-    child front, plus the 4 (m-n) index bytes; reading A (8 + 16 B per entry) and zeroing +
-    writing the fronts' fully-summed columns once (16 B per entry of L)."""
+    child front, plus the 4 (m-n) index bytes.  Front initialisation (the timed class holds the memset of
+    the level's factor storage and k_scatter_a only): 8 B written per entry of L (memset) + 24 B read per
+    entry of A (value, int64 source and destination index)."""
     m = (a.rptr[1:] - a.rptr[:-1]).astype(np.float64)
     nc = (a.sptr[1:] - a.sptr[:-1]).astype(np.float64)
     cm = m - nc
     has_parent = np.asarray(a.sparent) <= a.nnodes
     ext = float(((cm * (cm + 1) / 2 * 24 + 4 * cm) * has_parent).sum())
     nz = int(a.ptr[a.n]) - 1
-    return {"extend_add": ext, "scatter_a": 24.0 * nz, "zero_and_write_L": 16.0 * float((m * nc).sum())}
+    return {"extend_add": ext, "scatter_a": 24.0 * nz, "zero_L": 8.0 * float((m * nc).sum())}
 
 
 def hbm_bound_parts(a, inform, solve_ms, tm):
@@ -187,28 +203,36 @@ def hbm_bound_parts(a, inform, solve_ms, tm):
     if t1:
         b = 2 * 8.0 * inform["num_factor"]
         out["solve_1rhs"] = {"bytes": b, "ms": t1, "achieved": b / (t1 * 1e-3) / 1e9, "frac": b / (t1 * 1e-3) / 1e9 / peak,
-                             "note": "latency-bound per 32-column block step, not bandwidth-bound (DESIGN.md 6)"}
+                             "note": "fwd + diag_bwd sweeps read L once each (2 x 8 x num_factor bytes)"}
     ab = assembly_algorithmic_bytes(a)
     t_asm, t_init = float(tm[8 + 7]), float(tm[8 + 8])
     if t_asm > 0:
         out["extend_add"] = {"bytes": ab["extend_add"], "ms": t_asm, "achieved": ab["extend_add"] / (t_asm * 1e-3) / 1e9,
                              "frac": ab["extend_add"] / (t_asm * 1e-3) / 1e9 / peak, "kernel": "k_assemble"}
     if t_init > 0:
-        bi = ab["scatter_a"] + ab["zero_and_write_L"]
+        bi = ab["scatter_a"] + ab["zero_L"]
         out["init_fronts"] = {"bytes": bi, "ms": t_init, "achieved": bi / (t_init * 1e-3) / 1e9,
                               "frac": bi / (t_init * 1e-3) / 1e9 / peak, "kernel": "cudaMemsetAsync + k_scatter_a"}
     return out
 
 
-def cpu_reference_factor(grid):
-    """cpu_baseline leg: the reference's own CPU engine (oracle/_ref, unmodified sources) on the
-    same stencil at `grid`^3, in a process of its own (`bench.py --impl reference`) so that its
-    OpenMP binding does not touch this process.  Returns the reference arm's JSON line."""
+def cpu_reference_arm(args, order):
+    """cpu_baseline leg: the reference's own CPU engine (oracle/_ref, unmodified sources) on the SAME workload,
+    in a process of its own (`bench.py --impl reference`) so that its OpenMP binding does not touch this
+    process; the ordering computed by this process is handed over (METIS once).  Returns the arm's JSON line."""
+    import tempfile
     env = {k: v for k, v in os.environ.items()
            if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS", "MASTER_ADDR", "MASTER_PORT")}
-    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--cpu-grid", str(grid)], env=env, capture_output=True, text=True,
-                         timeout=900)
+    with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as fh:
+        np.save(fh, np.asarray(order, dtype=np.int32))
+        opath = fh.name
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                              "--warmup", "0", "--workload", args.workload, "--grid", str(args.grid),
+                              "--nrhs", str(args.nrhs), "--order-file", opath], env=env, capture_output=True,
+                             text=True, timeout=1500)
+    finally:
+        os.unlink(opath)
     for line in reversed(out.stdout.strip().splitlines()):
         if line.startswith("{"):
             return json.loads(line)
@@ -216,6 +240,9 @@ def cpu_reference_factor(grid):
 
 
 def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (src/ssids/cpu, compiled unmodified into oracle/_ref)
+    on the box's host cores: ssids_factor of the same workload, then solve_fwd + solve_diag_bwd for 1 and
+    nrhs right-hand sides (driver pattern: driver/spral_ssids.F90:419-480)."""
     if rank != 0:
         return
     os.environ.setdefault("OMP_PROC_BIND", "TRUE")     # before libgomp loads (SURVEY 8d: OpenMP tasks bound to cores)
@@ -225,30 +252,64 @@ def run_reference(args, rank):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libspral_cpu_ref.so was not built"}))
         return
     oracle_ref.ensure_env()
-    grid = args.cpu_grid
-    n, ptr, row, val = make_matrix(grid)
-    a = Analysis(n, ptr, row)
+    wl_desc, posdef, scaling_method, (n, ptr, row, val) = make_workload(args)
+    order = np.load(args.order_file) if args.order_file else None
+    a = Analysis(n, ptr, row, order=order)
+    scaling_vec = None
+    if scaling_method:
+        from spral_b200 import ssids as host
+        scaling_vec = host.compute_scaling(a, val, scaling_method)
     cores = host_cores()
-    times, flops = [], 0
-    for it in range(args.warmup + args.steps):
-        parts, inform, _ = oracle_ref.ref_factor(a, False, val, nthreads=cores)
-        for p in parts:
-            p.close()
-        flops = inform["num_flops"]
-        if it >= args.warmup:
+    nwarm, nsteps = min(args.warmup, 1), max(1, min(args.steps, REF_MAX_STEPS))
+    times, inform, parts, sc = [], None, None, None
+    for it in range(nwarm + nsteps):
+        if parts is not None:
+            for p in parts:
+                p.close()
+        parts, inform, sc = oracle_ref.ref_factor(a, posdef, val, scaling=scaling_vec, nthreads=cores)
+        if it >= nwarm:
             times.append(inform["factor_time"])
     t = float(np.mean(times))
+    flops = inform["num_flops"]
     v = flops / t / 1e9
-    sample = f"3-D 27-point {grid}^3 shifted indefinite (n={n}), whole factor, same ordering/options"
+    # solves: the sweeps only (x already permuted).  The reference's solve is a serial loop over the nodes whose only
+    # parallelism is the BLAS library's; OpenBLAS threads on these small per-node calls make it 100x SLOWER (measured),
+    # so the sweeps run the way the factorisation leaves the library: one BLAS thread.
+    blas_threads = int(os.environ.get("SPRAL_B200_REF_SOLVE_BLAS_THREADS", "1"))
+    oracle_ref.load().oracle_blas_set_threads(blas_threads)
+    solve_s = {}
+    rng = np.random.default_rng(0)
+    for nr in sorted({1, args.nrhs}):
+        x2 = np.asfortranarray(rng.uniform(-1, 1, (n, nr)))
+        best = None
+        for rep in range(2 if nr == 1 else 1):
+            t0 = time.perf_counter()
+            for st in parts:
+                st.solve("fwd", x2, nr)
+            for st in reversed(parts):
+                st.solve("diag_bwd", x2, nr)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        solve_s[str(nr)] = best
+    for p in parts:
+        p.close()
+    sample = (f"the whole workload: {nsteps} full factorisation(s) after {nwarm} warm-up (capped at {REF_MAX_STEPS}: one "
+              f"takes {t:.0f} s of CPU), same matrix / ordering / options as the GPU arm; solves: fwd + diag_bwd sweeps")
+    cpu = {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample, "seconds": t,
+           "solve_seconds": solve_s, "solve_cores": blas_threads,
+           "solve_note": "the reference's solve is a serial loop over nodes; BLAS threads = solve_cores",
+           "inform": {k: int(inform[k]) for k in ("flag", "num_neg", "num_two", "num_delay", "matrix_rank", "num_factor", "num_flops")}}
     print(json.dumps({
         "impl": "reference", "metric": "ssids_factor FP64 GFLOP/s", "value": v, "unit": "GFLOP/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
+        "n_gpus": args.gpus, "steps": nsteps, "warmup": nwarm, "steps_requested": args.steps,
+        "warmup_requested": args.warmup, "ms_per_step": 1e3 * t,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"ssids_factor 3-D 27-point {args.grid}^3 indefinite (bounded CPU sample: {grid}^3)",
-                   "sample": sample, "engine": "reference CPU engine src/ssids/cpu (OpenMP tasks + OpenBLAS)"},
-        "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample},
+        "config": {"workload": wl_desc, "engine": "reference CPU engine src/ssids/cpu (OpenMP tasks + OpenBLAS)",
+                   "nparts": int(a.nparts)},
+        "cpu_baseline": cpu,
         "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "solve_ms": {k: 1e3 * x for k, x in solve_s.items()},
     }))
 
 
@@ -261,7 +322,7 @@ def main():
     ap.add_argument("--grid", type=int, default=100, help="stencil grid size (BASELINE: 100)")
     ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg4", "cfg3", "cfg2"],
                     help="BASELINE config to run (default cfg5 = configs[4], the headline workload)")
-    ap.add_argument("--cpu-grid", type=int, default=CPU_SAMPLE_GRID)
+    ap.add_argument("--order-file", default=None, help="(reference arm) .npy elimination order computed by the caller")
     ap.add_argument("--nrhs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -414,21 +475,21 @@ def main():
         tm = fk.numeric[0].timings()
         peak = float(lib.spral_ssids_b200_fp64_peak_tflops(local_rank))
         ach = float(tm[3]) / (float(tm[2]) * 1e-3) / 1e12 if tm[2] > 0 else 0.0
+        traffic, traffic_note = ncu_traffic()
         roofline = {"bound": "tensor",
                     "kernel": "k_update_ws<128,2,4,3,32> UPD_CONTRIB (Schur complement, FP64 DMMA, TMA bulk staged)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the largest of the 14, root-side
-                    # front: 20.46 + 2.56 GB) from the committed ncu --set full capture; not re-measured here
-                    "traffic": 2.30e10,
-                    "traffic_launch": {"which": "largest UPD_CONTRIB launch (contribution block 10600^2, K = 5243)",
-                                       "algorithmic_bytes": 1.34e9, "algorithmic_flops": 5.9e11,
-                                       "source": "profiles/r01_ncu_full_upd_contrib_final.md (DRAM at 8% of peak: the row "
-                                                 "panels of L are re-read through the L2 once per tile column; bound is the "
-                                                 "FP64 tensor pipe, 92% active)"},
+                    "traffic": traffic, "traffic_note": traffic_note,
                     "launches": int(tm[4]), "kernel_ms_per_step": float(tm[2]),
                     "kernel_flops_per_step": float(tm[3]),
                     "peak_source": "FP64 DMMA issue loop measured live on this GPU "
                                    "(MEASURED_PEAKS.json has no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.9 TF/s on this pool)"}
+        # the 64-RHS solve against the same tensor roofline (4 x num_factor x nrhs flops)
+        tn = solve_ms.get(f"{args.nrhs}_device")
+        if tn and args.nrhs > 1:
+            fl = 4.0 * inform["num_factor"] * args.nrhs
+            roofline["solve_nrhs"] = {"nrhs": args.nrhs, "flops": fl, "ms": tn, "achieved": fl / (tn * 1e-3) / 1e12,
+                                      "frac": fl / (tn * 1e-3) / 1e12 / peak if peak > 0 else None, "unit": "TFLOP/s"}
 
     # ---- the HBM-bound parts (north_star: achieved GB/s of assembly and solves against the copy bandwidth) ----
     hbm_rooflines = None
@@ -462,14 +523,14 @@ def main():
         out["roofline_hbm_parts"] = hbm_rooflines
 
     # ---- CPU baseline: the reference engine on a bounded sample (rank 0, N=1 only) ----
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cfg5":
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             import oracle_ref
             if oracle_ref.available():
-                ref = cpu_reference_factor(args.cpu_grid)
+                ref = cpu_reference_arm(args, a.order)
                 if "cpu_baseline" not in ref:
                     raise RuntimeError(ref.get("unavailable", "no cpu_baseline in the reference arm's line"))
-                out["cpu_baseline"] = dict(ref["cpu_baseline"], seconds=ref["ms_per_step"] / 1e3)
+                out["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:
             out["cpu_baseline"] = {"error": repr(e)}
     sdist.free(fk)

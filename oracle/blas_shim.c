@@ -56,3 +56,5 @@ void spral_c_dgemv(char* trans, int* m, int* n, const double* alpha,
 
 /* Task parallelism comes from SSIDS' OpenMP tasks; keep BLAS serial. */
 void oracle_blas_single_thread(void) { scipy_openblas_set_num_threads(1); }
+/* the solves of the reference are a serial loop over the nodes: their parallelism is the BLAS library's */
+void oracle_blas_set_threads(int n) { scipy_openblas_set_num_threads(n < 1 ? 1 : n); }

@@ -76,10 +76,11 @@ struct Front {
    int seg_ok;       // ... its diagonal block was factorised by the chain kernel
    int seg_fail;     // ... a row below failed the a-posteriori test: the tiles roll back
    int spec_off;     // the rest of this panel is done step by step
-   int spec_fails;   // segments of this front that were given up: after SPEC_MAX_FAILS the front stops speculating
+   int spec_fails;   // penalty account of given-up segments: at SPEC_MAX_FAILS the front stops speculating
    int pad2_;
 };
-constexpr int SPEC_MAX_FAILS = 2;
+constexpr int SPEC_PENALTY = 3;      // pivot_state.h: account_segment
+constexpr int SPEC_MAX_FAILS = 9;
 
 /* A child contribution to be extend-added into a parent front (either a child
  * front of the same part or a contribution block received from another part). */

@@ -30,11 +30,13 @@
  * candidate range.  Failed columns are retried in later passes; what is left
  * is delayed to the parent.
  */
+#include <algorithm>
 #include <cstdlib>
 #include "engine.h"
 #include "device_utils.cuh"
 #include "pivot_state.h"
 #include "diag_block.h"
+#include "diag_warp.cuh"
 #include "panel_v2.h"
 
 namespace b200 {
@@ -503,15 +505,100 @@ k_diag_v2(Front* fronts, const int* __restrict__ flist, int new_panel, FactorPar
    }
 }
 
+/* Version 3 (default): ONE warp per front (diag_warp.cuh) -- no block-wide barrier inside the chain of
+ * pivots, the decision taken redundantly by every lane.  SPRAL_B200_DIAG=1 selects the thread-per-entry
+ * kernel above, =2 the four-warp variant. */
+template <bool POSDEF>
+__global__ void __launch_bounds__(32)
+k_diag_w(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
+   Front* f = &fronts[flist[blockIdx.x]];
+   __shared__ double S[BS * DW_LD];
+   __shared__ double dinv[2 * BS];
+   __shared__ int lperm[BS];
+   const int lane = threadIdx.x;
+   int go = 0;
+   if (lane == 0) {
+      advance_state(f, new_panel != 0);
+      if (!f->finished && f->done < f->pend) {
+         f->bs = min(BS, f->pend - f->done);
+         f->first_fail = f->bs;
+         f->step_valid = 1;
+         go = 1;
+      } else f->bs = 0;
+   }
+   go = __shfl_sync(0xffffffffu, go, 0);
+   if (!go) return;
+   __syncwarp();
+   const int bs = f->bs, done = f->done, ldl = f->ldl;
+   double* Ld = f->L + (size_t)done * ldl + done;   // the diagonal block
+   BlockWS* ws = f->ws;
+   /* lane = row: coalesced column segments */
+   #pragma unroll 8
+   for (int c = 0; c < BS; ++c)
+      S[lane * DW_LD + c] = (lane < bs && c < bs && lane >= c) ? Ld[lane + (size_t)c * ldl] : 0.0;
+   __syncwarp();
+   if (POSDEF) {
+      const int rc = diag_warp_chol(S, dinv, bs);
+      if (rc != DW_OK) {
+         if (lane == 0) { f->flag = rc; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
+         return;
+      }
+      #pragma unroll 8
+      for (int c = 0; c < BS; ++c) {
+         const bool in = lane < bs && c < bs && lane >= c;
+         const double l = in ? S[lane * DW_LD + c] : 0.0;
+         if (in) Ld[lane + (size_t)c * ldl] = l;
+         ws->l11[lane + c * BS] = l;
+      }
+      ws->dinv[lane] = (lane < bs) ? dinv[lane] : 0.0;
+      return;
+   }
+   /* keep the unfactorised block (full symmetric) for k_commit */
+   #pragma unroll 8
+   for (int c = 0; c < BS; ++c) ws->a0[lane + c * BS] = (lane >= c) ? S[lane * DW_LD + c] : S[c * DW_LD + lane];
+   __syncwarp();
+   int zfrom = BS;
+   const int rc = diag_warp_ldlt(S, dinv, lperm, bs, prm.small, prm.action, CUDART_INF, zfrom);
+   if (rc != DW_OK) {
+      if (lane == 0) { f->flag = rc; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
+      return;
+   }
+   /* publish L11 (unit lower), L11*D, D^-1 and the local permutation */
+   #pragma unroll 8
+   for (int c = 0; c < BS; ++c) {
+      double l = 0.0, y = 0.0;
+      if (lane < bs && c < bs) {
+         if (lane > c) { l = S[lane * DW_LD + c]; y = S[c * DW_LD + lane]; }
+         else if (lane == c) l = 1.0;
+      }
+      ws->l11[lane + c * BS] = l;
+      ws->ld11[lane + c * BS] = y;
+   }
+   ws->dinv[2 * lane] = (lane < bs) ? dinv[2 * lane] : 0.0;
+   ws->dinv[2 * lane + 1] = (lane < bs) ? dinv[2 * lane + 1] : 0.0;
+   ws->lperm[lane] = lperm[lane];
+   if (lane == 0) ws->zfrom = zfrom;
+}
+
 static int diag_version() {
    static int v = -1;
-   if (v < 0) { const char* e = getenv("SPRAL_B200_DIAG_V2"); v = (e && atoi(e) != 0) ? 2 : 1; }
+   if (v < 0) {
+      v = 3;
+      if (const char* e = getenv("SPRAL_B200_DIAG")) v = std::max(1, std::min(3, atoi(e)));
+      if (const char* e = getenv("SPRAL_B200_DIAG_V2")) if (atoi(e) != 0) v = 2;
+   }
    return v;
 }
 
 void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool new_panel,
       const FactorParams& prm, cudaStream_t s) {
    if (count == 0) return;
+   if (diag_version() == 3) {
+      if (posdef) k_diag_w<true><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
+      else k_diag_w<false><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
+      COUNT_LAUNCH();
+      return;
+   }
    if (diag_version() == 2) {
       constexpr int NW = 4;
       if (posdef) k_diag_v2<true, NW><<<count, NW * 32, 0, s>>>(fronts, flist, new_panel, prm);
@@ -527,14 +614,47 @@ void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool n
 /* Speculative panel segments (panel_v2.h)                                   */
 /* ------------------------------------------------------------------------ */
 
-/* One CTA per front: opens the panel / accounts the previous segment, then factorises
- * the CW x CW diagonal block at `done` in shared memory.  Nothing of the front is
- * modified; the factors go to f->sws. */
+/* FP64 tensor-core MMA, m8n8k4: D(8x8) += A(8x4) B(4x8).  Lane l holds A[l/4][l%4], B[l%4][l/4] and
+ * D[l/4][2(l%4) .. 2(l%4)+1].  (g++ build of the test emulator: the same contraction through a warp gather.) */
+#ifdef __CUDACC__
+__device__ __forceinline__ void pv_dmma(double& d0, double& d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#else
+inline void pv_dmma(double& d0, double& d1, double a, double b) {
+   double av[32], bv[32];
+   emu::warp_gather(&a, av, sizeof(double));
+   emu::warp_gather(&b, bv, sizeof(double));
+   const int lane = threadIdx.x & 31, i = lane >> 2, j0 = 2 * (lane & 3);
+   for (int k = 0; k < 4; ++k) { d0 += av[i * 4 + k] * bv[j0 * 4 + k]; d1 += av[i * 4 + k] * bv[(j0 + 1) * 4 + k]; }
+}
+#endif
+
+constexpr int CH_NT = 256;           // threads of the chain kernel
+constexpr int CLD = CW + 4;          // column stride of the segment in shared memory: = 4 mod 16 doubles, so the 8 x 4
+                                     // DMMA fragment loads are bank-conflict free along rows AND along the mirrored L*D
+constexpr int TNT = 256;             // threads of the tiles kernel
+constexpr int PBLD = PV_BS + 4;      // stride of the small k-major operand tiles (same rule)
+
+struct ChainSm {
+   double S[CW * CLD];               // S[c * CLD + r]: lower triangle A / L; (L D)(r, c) mirrored to S[r * CLD + c]
+   double B[PV_BS * DW_LD];          // the 32 x 32 block being factorised (diag_warp.cuh storage)
+   double X[PV_BS * DW_LD];          // inverse of its lower factor, X(r, c) = X[r * DW_LD + c]
+   double dinv[2 * PV_BS];
+   double c0[PV_BS], c1[PV_BS], c2[PV_BS];
+   int lperm[PV_BS];
+   int status;                       // 1: the block cannot be taken (failed / zero pivot, not positive definite)
+   int fail;                         // a row of the diagonal block failed the a-posteriori test
+};
+
+/* One CTA per front: opens the panel / accounts the previous segment, then factorises the CW x CW diagonal
+ * block at `done` in shared memory.  Nothing of the front is modified; the factors go to f->sws. */
 template <bool POSDEF>
-__global__ void __launch_bounds__(CNT)
+__global__ void __launch_bounds__(CH_NT)
 k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
    extern __shared__ __align__(16) unsigned char pv_smem[];
-   ChainShared& sh = *reinterpret_cast<ChainShared*>(pv_smem);
+   ChainSm& sh = *reinterpret_cast<ChainSm*>(pv_smem);
    Front* f = &fronts[flist[blockIdx.x]];
    __shared__ int s_go;
    if (threadIdx.x == 0) {
@@ -547,17 +667,207 @@ k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, Facto
    if (!s_go) return;
    const int p = f->done;
    const size_t ldl = (size_t)f->ldl;
-   DiagDevCtx cx;
-   const int ok = chain_segment<POSDEF>(cx, sh, f->L + p + (size_t)p * ldl, ldl, prm.u, prm.small, CUDART_INF, f->sws);
-   if (threadIdx.x == 0) { f->sws->ok = ok; f->seg_ok = ok; }
+   SegWS* out = f->sws;
+   const double* Lseg = f->L + p + (size_t)p * ldl;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   double* S = sh.S;
+
+   for (int c = warp; c < CW; c += CH_NT / 32) {
+      #pragma unroll
+      for (int i = 0; i < CW / 32; ++i) {
+         const int r = lane + 32 * i;
+         S[c * CLD + r] = (r >= c) ? Lseg[r + (size_t)c * ldl] : 0.0;
+      }
+   }
+   if (tid == 0) { sh.fail = 0; sh.status = 0; }
+   __syncthreads();
+   const double lim = 1.0 / prm.u;
+   int ok = 1;
+   for (int jb = 0; jb < CW; jb += PV_BS) {
+      for (int e = tid; e < PV_BS * PV_BS; e += CH_NT) {
+         const int r = e & 31, c = e >> 5;
+         sh.B[r * DW_LD + c] = (r >= c) ? S[(jb + c) * CLD + jb + r] : 0.0;
+      }
+      __syncthreads();
+      if (warp == 0) {
+         int zfrom = PV_BS, rc;
+         if (POSDEF) rc = diag_warp_chol(sh.B, sh.dinv, PV_BS);
+         else rc = diag_warp_ldlt(sh.B, sh.dinv, sh.lperm, PV_BS, prm.small, 1, CUDART_INF, zfrom);
+         /* not positive definite / zero pivots: the step-by-step path reports it */
+         if (rc != DW_OK || zfrom < PV_BS) { if (lane == 0) sh.status = 1; }
+         else {
+            double v0, v1 = 0.0, v2 = 0.0;
+            if (POSDEF) { v0 = sh.dinv[lane]; sh.lperm[lane] = lane; }
+            else pv_dinv_coeffs(sh.dinv, lane, CUDART_INF, v0, v1, v2);
+            sh.c0[lane] = v0; sh.c1[lane] = v1; sh.c2[lane] = v2;
+         }
+      }
+      __syncthreads();
+      if (sh.status) { ok = 0; break; }
+
+      if (warp == 1) {
+         /* X = L_jj^-1 (lower): lane c owns column c; x_r = -(sum_{c <= k < r} L(r, k) x_k) / l_rr */
+         const int c = lane;
+         for (int r = 0; r < PV_BS; ++r) {
+            double x;
+            if (r < c) x = 0.0;
+            else if (r == c) x = POSDEF ? sh.c0[c] : 1.0;
+            else {
+               double s0 = 0.0, s1 = 0.0;
+               int k = c;
+               for (; k + 1 < r; k += 2) {
+                  s0 += sh.B[r * DW_LD + k] * sh.X[k * DW_LD + c];
+                  s1 += sh.B[r * DW_LD + k + 1] * sh.X[(k + 1) * DW_LD + c];
+               }
+               if (k < r) s0 += sh.B[r * DW_LD + k] * sh.X[k * DW_LD + c];
+               x = -(s0 + s1);
+               if (POSDEF) x *= sh.c0[r];
+            }
+            sh.X[r * DW_LD + c] = x;
+         }
+      } else if (warp >= 2 && warp <= 4) {
+         /* rows of the diagonal block below the 32 x 32 block: Y = A21(:, lperm) L11^-T, W = Y D^-1,
+          * a-posteriori test |w| <= 1/u (ldlt_app.cxx:303-321) */
+         const int t = jb + PV_BS + (tid - 64);
+         if (t < CW) {
+            double y[PV_BS], wv[PV_BS];
+            #pragma unroll
+            for (int j = 0; j < PV_BS; ++j) y[j] = S[(jb + sh.lperm[j]) * CLD + t];
+            int bad = 0;
+            if (POSDEF) {                                    /* l_tj = (a_tj - sum_k l_tk l_jk) / l_jj */
+               #pragma unroll
+               for (int j = 0; j < PV_BS; ++j) {
+                  double s = y[j];
+                  #pragma unroll
+                  for (int k = 0; k < j; ++k) s -= y[k] * sh.B[j * DW_LD + k];
+                  y[j] = s * sh.c0[j];
+                  wv[j] = y[j];
+               }
+            } else {
+               #pragma unroll
+               for (int j = 0; j < PV_BS; ++j) {
+                  double s = y[j];
+                  #pragma unroll
+                  for (int k = 0; k < j; ++k) s -= y[k] * sh.B[j * DW_LD + k];
+                  y[j] = s;
+               }
+               #pragma unroll
+               for (int j = 0; j < PV_BS; ++j) {
+                  double w = sh.c0[j] * y[j];
+                  if (j + 1 < PV_BS) w += sh.c1[j] * y[(j + 1) % PV_BS];
+                  if (j > 0) w += sh.c2[j] * y[(j + PV_BS - 1) % PV_BS];
+                  wv[j] = w;
+                  if (!(fabs(w) <= lim)) bad = 1;
+               }
+            }
+            #pragma unroll
+            for (int j = 0; j < PV_BS; ++j) {
+               S[(jb + j) * CLD + t] = wv[j];          // L(t, jb + j)
+               S[t * CLD + jb + j] = y[j];             // (L D)(t, jb + j), mirrored (== L for Cholesky)
+            }
+            if (bad) sh.fail = 1;
+         }
+      } else if (warp == 5) {
+         const int i = lane;                            // a row of the 32 x 32 block itself
+         #pragma unroll 8
+         for (int c = 0; c < PV_BS; ++c) {
+            if (c < i) {
+               S[(jb + c) * CLD + jb + i] = sh.B[i * DW_LD + c];
+               S[(jb + i) * CLD + jb + c] = POSDEF ? sh.B[i * DW_LD + c] : sh.B[c * DW_LD + i];
+            } else if (c == i) S[(jb + c) * CLD + jb + i] = POSDEF ? sh.B[i * DW_LD + i] : 1.0;
+         }
+      } else if (!POSDEF) {
+         /* earlier columns of the segment (warps 0, 6, 7): the block's permutation is a row permutation of L */
+         const int t0 = (warp == 0) ? lane : (warp - 5) * 32 + lane;
+         if (t0 < jb) {
+            double v[PV_BS];
+            #pragma unroll
+            for (int i = 0; i < PV_BS; ++i) v[i] = S[t0 * CLD + jb + sh.lperm[i]];
+            #pragma unroll
+            for (int i = 0; i < PV_BS; ++i) S[t0 * CLD + jb + i] = v[i];
+         }
+      }
+      if (warp == 0) {
+         if (POSDEF) out->dinv[jb + lane] = sh.dinv[lane];      // 1 / l_jj, one per column
+         else { out->dinv[2 * jb + lane] = sh.dinv[lane]; out->dinv[2 * jb + 32 + lane] = sh.dinv[32 + lane]; }
+         out->lperm[jb + lane] = sh.lperm[lane];
+      }
+      __syncthreads();
+      if (sh.fail) { ok = 0; break; }
+      /* the inverse block for the tiles kernel (column-major, ld = 32) */
+      for (int e = tid; e < PV_BS * PV_BS; e += CH_NT) {
+         const int r = e & 31, c = e >> 5;
+         out->invl[jb / PV_BS][e] = sh.X[r * DW_LD + c];
+      }
+      /* trailing update of the rest of the diagonal block on the tensor cores, 32 x 32 tiles, one per warp:
+       * A(t, c) -= sum_k L(t, jb + k) (L D)(c, jb + k), t >= c >= jb + 32 */
+      const int nb = (CW - jb - PV_BS) / PV_BS;
+      for (int tile = warp; tile < nb * (nb + 1) / 2; tile += CH_NT / 32) {
+         int bi = 0, rem = tile;
+         while (rem > bi) { rem -= bi + 1; ++bi; }       // tile -> (bi >= bj)
+         const int bj = rem;
+         const int rb = jb + PV_BS + bi * PV_BS, cb = jb + PV_BS + bj * PV_BS;
+         double acc[4][4][2];
+         #pragma unroll
+         for (int j = 0; j < 4; ++j)
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+         #pragma unroll
+         for (int kk = 0; kk < PV_BS; kk += 4) {
+            double af[4], bf[4];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = S[(jb + kk + (lane & 3)) * CLD + rb + i * 8 + (lane >> 2)];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = S[(cb + j * 8 + (lane >> 2)) * CLD + jb + kk + (lane & 3)];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j)
+               #pragma unroll
+               for (int i = 0; i < 4; ++i) pv_dmma(acc[j][i][0], acc[j][i][1], bf[j], af[i]);
+         }
+         #pragma unroll
+         for (int j = 0; j < 4; ++j) {
+            const int c = cb + j * 8 + (lane >> 2);
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+               const int r = rb + i * 8 + 2 * (lane & 3);
+               if (r >= c) S[c * CLD + r] -= acc[j][i][0];
+               if (r + 1 >= c) S[c * CLD + r + 1] -= acc[j][i][1];
+            }
+         }
+      }
+      __syncthreads();
+   }
+   if (ok) {
+      for (int c = warp; c < CW; c += CH_NT / 32) {
+         #pragma unroll
+         for (int i = 0; i < CW / 32; ++i) {
+            const int t = lane + 32 * i;
+            out->l11[t + (size_t)c * CW] = (t > c) ? S[c * CLD + t] : (t == c ? (POSDEF ? S[c * CLD + c] : 1.0) : 0.0);
+            out->ld11[t + (size_t)c * CW] = (t > c) ? S[t * CLD + c] : 0.0;
+         }
+      }
+   }
+   if (tid == 0) { out->ok = ok; f->seg_ok = ok; }
 }
 
-/* One CTA per (front, 128-row tile): the rows below the segment. */
+struct TileSm {
+   double T[CW * CLD];               // the tile, column-major: T[c * CLD + r], r < RT
+   double Ys[PV_BS * CLD];           // Y = A21 P L11^-T of the current block column, same layout
+   double Bs[(CW - PV_BS) * PBLD];   // Bs[k * PBLD + n] = (L11 D)(jb + n, k), k < jb
+   double Xs[PV_BS * PBLD];          // Xs[k * PBLD + c] = X(c, k), X the inverse of the diagonal block of L11
+   double c0[PV_BS], c1[PV_BS], c2[PV_BS];
+   int lperm[PV_BS];
+};
+
+/* One CTA per (front, 128-row tile): the rows below the segment.  Per 32-column block: (U) left-looking DMMA
+ * update with the earlier blocks, T_j -= W_{<j} (L11 D)(j, <j)^T; (S) Y = T_j(:, lperm) X^T, the triangular
+ * solve as a multiplication by the inverse diagonal block; (D) W = Y D^-1, threshold test |w| <= 1/u
+ * (ldlt_app.cxx:303-321), W -> L, Y -> L*D.  The originals go to the backup when the tile is loaded. */
 template <bool POSDEF>
-__global__ void __launch_bounds__(RT)
+__global__ void __launch_bounds__(TNT)
 k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
    extern __shared__ __align__(16) unsigned char pv_smem[];
-   TileShared& sh = *reinterpret_cast<TileShared*>(pv_smem);
+   TileSm& sh = *reinterpret_cast<TileSm*>(pv_smem);
    const RowTile w = work[blockIdx.x];
    Front* f = &fronts[w.front];
    if (!f->seg_valid || !f->seg_ok) return;
@@ -565,12 +875,140 @@ k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
    const int r0 = w.tile * RT;
    if (r0 + RT <= p + CW || r0 >= m) return;
    const size_t ldl = (size_t)f->ldl;
-   DiagDevCtx cx;
-   panel_tile<POSDEF>(cx, sh, f->L + (size_t)p * ldl, f->LD + (size_t)p * ldl, f->BK, ldl, m, r0, p, prm.u, CUDART_INF,
-                      f->sws, &f->seg_fail);
+   double* Lp = f->L + (size_t)p * ldl;
+   double* LDp = f->LD + (size_t)p * ldl;
+   double* BK = f->BK;
+   const SegWS* ws = f->sws;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   double* T = sh.T;
+
+   {  /* load: two rows per thread, 64 threads per column (1 KB contiguous) */
+      const int rr = (tid & 63) * 2, cq = tid >> 6;
+      const int r = r0 + rr;
+      const bool a0 = (r >= p + CW) && (r < m), a1 = (r + 1 >= p + CW) && (r + 1 < m);
+      #pragma unroll 8
+      for (int c = cq; c < CW; c += TNT / 64) {
+         double2 v = make_double2(0.0, 0.0);
+         const double* src = Lp + r + (size_t)c * ldl;
+         if (a0 && a1) v = *reinterpret_cast<const double2*>(src);
+         else { if (a0) v.x = src[0]; if (a1) v.y = src[1]; }
+         *reinterpret_cast<double2*>(&T[c * CLD + rr]) = v;
+         if (!POSDEF) {                                      // Cholesky never rolls back
+            double* dst = BK + r + (size_t)c * ldl;
+            if (a0 && a1) *reinterpret_cast<double2*>(dst) = v;
+            else { if (a0) dst[0] = v.x; if (a1) dst[1] = v.y; }
+         }
+      }
+   }
+   const double lim = 1.0 / prm.u;
+   int bad = 0;
+   const int rbase = warp * 16;                              // the warp's rows in phases U and S
+   for (int jb = 0; jb < CW; jb += PV_BS) {
+      for (int e = tid; e < jb * PV_BS; e += TNT) {
+         const int n = e & 31, k = e >> 5;
+         sh.Bs[k * PBLD + n] = ws->ld11[(jb + n) + (size_t)k * CW];
+      }
+      for (int e = tid; e < PV_BS * PV_BS; e += TNT) {
+         const int c = e & 31, k = e >> 5;
+         sh.Xs[k * PBLD + c] = ws->invl[jb / PV_BS][e];
+      }
+      if (tid < PV_BS) {
+         double v0, v1 = 0.0, v2 = 0.0;
+         if (POSDEF) v0 = 1.0;
+         else pv_dinv_coeffs(ws->dinv + 2 * jb, tid, CUDART_INF, v0, v1, v2);
+         sh.c0[tid] = v0; sh.c1[tid] = v1; sh.c2[tid] = v2;
+         sh.lperm[tid] = ws->lperm[jb + tid];
+      }
+      __syncthreads();
+      /* (U) the warp's 16 rows x the block's 32 columns */
+      if (jb > 0) {
+         double acc[4][2][2];
+         #pragma unroll
+         for (int j = 0; j < 4; ++j)
+            #pragma unroll
+            for (int i = 0; i < 2; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+         for (int kk = 0; kk < jb; kk += 4) {
+            double af[2], bf[4];
+            #pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = T[(kk + (lane & 3)) * CLD + rbase + i * 8 + (lane >> 2)];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = sh.Bs[(kk + (lane & 3)) * PBLD + j * 8 + (lane >> 2)];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j)
+               #pragma unroll
+               for (int i = 0; i < 2; ++i) pv_dmma(acc[j][i][0], acc[j][i][1], bf[j], af[i]);
+         }
+         #pragma unroll
+         for (int j = 0; j < 4; ++j)
+            #pragma unroll
+            for (int i = 0; i < 2; ++i) {
+               double2* q = reinterpret_cast<double2*>(&T[(jb + j * 8 + (lane >> 2)) * CLD + rbase + i * 8 + 2 * (lane & 3)]);
+               double2 v = *q;
+               v.x -= acc[j][i][0]; v.y -= acc[j][i][1];
+               *q = v;
+            }
+         __syncwarp();                                       // (S) reads what the other lanes of this warp wrote
+      }
+      /* (S) */
+      {
+         double acc[4][2][2];
+         #pragma unroll
+         for (int j = 0; j < 4; ++j)
+            #pragma unroll
+            for (int i = 0; i < 2; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+         #pragma unroll
+         for (int kk = 0; kk < PV_BS; kk += 4) {
+            double af[2], bf[4];
+            const int col = jb + sh.lperm[kk + (lane & 3)];
+            #pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = T[col * CLD + rbase + i * 8 + (lane >> 2)];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = sh.Xs[(kk + (lane & 3)) * PBLD + j * 8 + (lane >> 2)];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j)
+               #pragma unroll
+               for (int i = 0; i < 2; ++i) pv_dmma(acc[j][i][0], acc[j][i][1], bf[j], af[i]);
+         }
+         #pragma unroll
+         for (int j = 0; j < 4; ++j)
+            #pragma unroll
+            for (int i = 0; i < 2; ++i)
+               *reinterpret_cast<double2*>(&sh.Ys[(j * 8 + (lane >> 2)) * CLD + rbase + i * 8 + 2 * (lane & 3)]) =
+                  make_double2(acc[j][i][0], acc[j][i][1]);
+      }
+      __syncthreads();
+      /* (D) one row and 16 columns per thread */
+      {
+         const int r = tid & (RT - 1), h = tid / RT;
+         const int grow = r0 + r;
+         const bool active = (grow >= p + CW) && (grow < m);
+         #pragma unroll 4
+         for (int j = h * 16; j < h * 16 + 16; ++j) {
+            const double y = sh.Ys[j * CLD + r];
+            double wv = y;
+            if (!POSDEF) {
+               wv = sh.c0[j] * y;
+               if (j + 1 < PV_BS) wv += sh.c1[j] * sh.Ys[(j + 1) * CLD + r];
+               if (j > 0) wv += sh.c2[j] * sh.Ys[(j - 1) * CLD + r];
+               if (active && !(fabs(wv) <= lim)) bad = 1;
+            }
+            T[(jb + j) * CLD + r] = wv;
+            if (active) {
+               Lp[grow + (size_t)(jb + j) * ldl] = wv;
+               if (!POSDEF) LDp[grow + (size_t)(jb + j) * ldl] = y;      // Cholesky: L*D is L itself (f->LD == f->L)
+            }
+         }
+      }
+      __syncthreads();
+   }
+   if (bad) f->seg_fail = 1;
 }
 
-/* Accept (diagonal block, D, perm, row permutation of the earlier columns) or roll back. */
+/* Accept (diagonal block, D, perm, row permutation of the earlier columns) or roll back.  One CTA per
+ * (front, 128-row tile): on failure the rows below the segment are restored from the backup; on success
+ * the CTAs left of the segment permute the segment's rows in their 128 already-factored columns (one
+ * thread per row of the segment: coalesced), and the CTA whose tile holds row p writes the diagonal block,
+ * D^-1 and the pivot order. */
 template <bool POSDEF>
 __global__ void __launch_bounds__(RT)
 k_seg_commit(Front* fronts, const RowTile* work) {
@@ -580,32 +1018,82 @@ k_seg_commit(Front* fronts, const RowTile* work) {
    const int p = f->done, m = f->m;
    const size_t ldl = (size_t)f->ldl;
    const int r0 = w.tile * RT;
-   __shared__ CommitShared sh;
-   DiagDevCtx cx;
-   seg_commit<POSDEF>(cx, sh, f->L, f->D, f->perm, f->BK, ldl, m, p, r0, w.tile == p / RT, f->seg_fail, f->sws);
+   const int t = threadIdx.x;
+   const SegWS* ws = f->sws;
+   double* L = f->L;
+   const bool diag_cta = (w.tile == p / RT);
+   if (POSDEF) {                      /* no permutation, no D: only the diagonal block is left to write */
+      if (diag_cta)
+         for (int e = t; e < CW * CW; e += RT) {
+            const int i = e % CW, c = e / CW;
+            if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
+         }
+      return;
+   }
+   if (f->seg_fail) {
+      const int r = r0 + t;
+      if (r >= p + CW && r < m) {
+         const double* BKr = f->BK + r;
+         double* Lr = L + r + (size_t)p * ldl;
+         #pragma unroll 16
+         for (int c = 0; c < CW; ++c) Lr[(size_t)c * ldl] = BKr[(size_t)c * ldl];
+      }
+      return;
+   }
+   __shared__ int s_lperm[CW];
+   __shared__ int s_perm[CW];
+   __shared__ int s_moved;
+   if (t == 0) s_moved = 0;
+   __syncthreads();
+   const int src = (t & ~(PV_BS - 1)) + ws->lperm[t];
+   s_lperm[t] = src;
+   if (src != t) s_moved = 1;
+   __syncthreads();
+   if (r0 < p && s_moved) {
+      const int cend = min(r0 + RT, p);
+      constexpr int NB = 8;
+      for (int c0 = r0; c0 < cend; c0 += NB) {
+         double v[NB];
+         #pragma unroll
+         for (int q = 0; q < NB; ++q) v[q] = (c0 + q < cend) ? L[(size_t)(c0 + q) * ldl + p + src] : 0.0;
+         __syncthreads();
+         #pragma unroll
+         for (int q = 0; q < NB; ++q) if (c0 + q < cend) L[(size_t)(c0 + q) * ldl + p + t] = v[q];
+      }
+   }
+   if (diag_cta) {
+      for (int e = t; e < CW * CW; e += RT) {
+         const int i = e % CW, c = e / CW;
+         if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
+      }
+      for (int e = t; e < 2 * CW; e += RT) f->D[2 * p + e] = ws->dinv[e];
+      s_perm[t] = f->perm[p + src];
+      __syncthreads();
+      f->perm[p + t] = s_perm[t];
+   }
 }
 
 int panel_segment_width() { return CW; }
 size_t panel_segment_ws_bytes() { return sizeof(SegWS); }
 
 void configure_panel_kernels() {
-   cudaFuncSetAttribute(k_panel_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
-   cudaFuncSetAttribute(k_panel_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
-   cudaFuncSetAttribute(k_panel_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
-   cudaFuncSetAttribute(k_panel_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+   cudaFuncSetAttribute(k_panel_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSm));
+   cudaFuncSetAttribute(k_panel_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSm));
+   cudaFuncSetAttribute(k_panel_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSm));
+   cudaFuncSetAttribute(k_panel_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSm));
 }
 
 void launch_panel_chain(Front* fronts, const int* flist, int count, bool posdef, bool new_panel, const FactorParams& prm,
       cudaStream_t s) {
    if (count == 0) return;
-   if (posdef) k_panel_chain<true><<<count, CNT, sizeof(ChainShared), s>>>(fronts, flist, new_panel ? 1 : 0, prm);
-   else k_panel_chain<false><<<count, CNT, sizeof(ChainShared), s>>>(fronts, flist, new_panel ? 1 : 0, prm);
+   if (posdef) k_panel_chain<true><<<count, CH_NT, sizeof(ChainSm), s>>>(fronts, flist, new_panel ? 1 : 0, prm);
+   else k_panel_chain<false><<<count, CH_NT, sizeof(ChainSm), s>>>(fronts, flist, new_panel ? 1 : 0, prm);
    COUNT_LAUNCH();
 }
 void launch_panel_tiles(Front* fronts, const RowTile* work, int nwork, bool posdef, const FactorParams& prm, cudaStream_t s) {
    if (nwork == 0) return;
-   if (posdef) k_panel_tiles<true><<<nwork, RT, sizeof(TileShared), s>>>(fronts, work, prm);
-   else k_panel_tiles<false><<<nwork, RT, sizeof(TileShared), s>>>(fronts, work, prm);
+   if (posdef) k_panel_tiles<true><<<nwork, TNT, sizeof(TileSm), s>>>(fronts, work, prm);
+   else k_panel_tiles<false><<<nwork, TNT, sizeof(TileSm), s>>>(fronts, work, prm);
    COUNT_LAUNCH();
 }
 void launch_seg_commit(Front* fronts, const RowTile* work, int nwork, bool posdef, cudaStream_t s) {

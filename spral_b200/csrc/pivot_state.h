@@ -28,11 +28,15 @@ PS_FN int calc_ne(const Front* f) {
 }
 
 /* Accounts a speculative segment (panel_v2.h): accepted -> CW more columns are done;
- * given up or rolled back -> the rest of the panel is done step by step. */
+ * given up or rolled back -> the rest of the panel is done step by step.  spec_fails is a
+ * penalty account: +SPEC_PENALTY per segment that was given up, -1 per accepted one; a front whose
+ * account reaches SPEC_MAX_FAILS (more than one segment in SPEC_PENALTY + 1 fails, sustained) stops
+ * speculating for good, sporadic failures (the benchmark's top fronts: 5 in 128 segments) cost one
+ * panel each. */
 PS_FN void account_segment(Front* f) {
    if (!f->seg_valid) return;
-   if (f->seg_ok && !f->seg_fail) f->done += CW;
-   else { f->spec_off = 1; f->spec_fails++; }
+   if (f->seg_ok && !f->seg_fail) { f->done += CW; if (f->spec_fails > 0) f->spec_fails--; }
+   else { f->spec_off = 1; f->spec_fails += SPEC_PENALTY; }
    f->seg_valid = 0;
 }
 

@@ -423,17 +423,33 @@ void spral_ssids_enquire_indef(const void* akeep, const void* fkeep, const struc
    if (!A || !F) { inform->flag = E_CALL_SEQUENCE; return; }
    if (F->posdef) { inform->flag = E_NOT_LDLT; return; }
    const int n = A->n;
-   /* the subtree reports in pivot order; the user gets piv_order per ORIGINAL variable
-    * and d in elimination order (ssids.f90:1288-1316; single part) */
-   std::vector<int> po(n, 0);
-   std::vector<double> dd(2 * (size_t)n, 0.0);
-   if (F->numeric.size() != 1) { inform->flag = E_UNIMPLEMENTED; return; }
-   spral_ssids_gpu_subtree_enquire_dbl(false, F->numeric[0], po.data(), dd.data());
-   if (piv_order)
+   /* The subtrees report in pivot order -- position in the part's pivot sequence, 0-based, negative for a variable of
+    * a 2x2 pivot (NumericSubtree::enquire, src/ssids/cpu/NumericSubtree.hxx:424-470) -- and d in elimination order.
+    * The user gets piv_order per ORIGINAL variable, 1-based (ssids.f90:1288-1350).  Two things the reference's CPU
+    * path gets wrong are done properly here: (i) position 0 cannot carry a sign, so the first variable of a LEADING
+    * 2x2 pivot would come back positive -- the 2x2 marker is taken from d instead (off-diagonal entry non-zero);
+    * (ii) with several parts every part's positions start at 0 and the reference reads part 1 only
+    * (fkeep.F90:386-405, "FIXME") -- here the positions and d are concatenated part by part. */
+   std::vector<int> po(n, 0), tmp(n);
+   std::vector<double> dd(2 * (size_t)n, 0.0), dpart(2 * (size_t)n);
+   const int UNSET = -2147483647 - 1;
+   int off = 0;                                              // pivots reported by the parts before this one
+   for (size_t p = 0; p < F->numeric.size(); ++p) {
+      std::fill(tmp.begin(), tmp.end(), UNSET);
+      std::fill(dpart.begin(), dpart.end(), 0.0);
+      spral_ssids_gpu_subtree_enquire_dbl(false, F->numeric[p], tmp.data(), dpart.data());
+      int cnt = 0;
       for (int i = 0; i < n; ++i) {
-         int v = po[i];                                  // 0-based position, negative for 2x2
-         piv_order[A->v.invp[i] - 1] = (v < 0) ? -(-v + 1) : v + 1;     // reported 1-based
+         if (tmp[i] == UNSET) continue;
+         const int pos = tmp[i] < 0 ? -tmp[i] : tmp[i];       // 0-based position inside the part
+         const bool two = tmp[i] < 0 || dpart[2 * (size_t)pos + 1] != 0.0;      // first variable of a 2x2: d(2, pos) != 0
+         po[i] = two ? -(off + pos + 1) : (off + pos + 1);
+         ++cnt;
       }
+      for (int k = 0; k < cnt && off + k < n; ++k) { dd[2 * (size_t)(off + k)] = dpart[2 * (size_t)k]; dd[2 * (size_t)(off + k) + 1] = dpart[2 * (size_t)k + 1]; }
+      off += cnt;
+   }
+   if (piv_order) for (int i = 0; i < n; ++i) piv_order[A->v.invp[i] - 1] = po[i];
    if (d) std::copy(dd.begin(), dd.end(), d);
 }
 
@@ -443,8 +459,21 @@ void spral_ssids_alter(const double* d, const void* akeep, void* fkeep, const st
    inform->flag = OK;
    if (!akeep || !F) { inform->flag = E_CALL_SEQUENCE; return; }
    if (F->posdef) { inform->flag = E_NOT_LDLT; return; }
-   if (F->numeric.size() != 1) { inform->flag = E_UNIMPLEMENTED; return; }
-   spral_ssids_gpu_subtree_alter_dbl(false, F->numeric[0], d);
+   /* part by part, each taking the d entries of the pivots it eliminated (alter_cpu, fkeep.F90:420-437; the
+    * offsets follow the parts' eliminated counts, as enquire_indef reports them) */
+   const Akeep* A = static_cast<const Akeep*>(akeep);
+   const int n = A->n;
+   std::vector<int> tmp(n);
+   const int UNSET = -2147483647 - 1;
+   size_t off = 0;
+   for (size_t p = 0; p < F->numeric.size(); ++p) {
+      std::fill(tmp.begin(), tmp.end(), UNSET);
+      spral_ssids_gpu_subtree_enquire_dbl(false, F->numeric[p], tmp.data(), nullptr);
+      size_t cnt = 0;
+      for (int i = 0; i < n; ++i) if (tmp[i] != UNSET) ++cnt;
+      spral_ssids_gpu_subtree_alter_dbl(false, F->numeric[p], d + 2 * off);
+      off += cnt;
+   }
 }
 
 /* 32-bit column pointers: the factor phase takes the pattern from akeep, ptr / row are not read

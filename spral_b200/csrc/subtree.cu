@@ -210,7 +210,8 @@ struct Symbolic {
    std::mutex mtx;
    Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf, b_xt;
    Buf b_bar;                         // arrival counter of the cooperative solve kernels
-   Buf b_export;                      // packed contribution block handed to another process (IPC)
+   Buf b_export[2];                   // packed contribution block handed to another process (IPC), double-buffered
+   int export_slot = 0;
    Buf b_bulk[2];                     // tile lists of the look-ahead bulk updates (alternating panels)
    Buf b_segws;                       // chain workspaces of the speculative panel segments (panel_v2.h)
 #ifdef SPRAL_B200_SPLIT
@@ -224,7 +225,7 @@ struct Symbolic {
       cudaFree(d_node_of_front);
       b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
       b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
-      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export.release(); b_bar.release(); b_bulk[0].release(); b_bulk[1].release();
+      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export[0].release(); b_export[1].release(); b_bar.release(); b_bulk[0].release(); b_bulk[1].release();
       b_segws.release();
    }
 };
@@ -572,13 +573,16 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          while (lo < hi) { int mid = (lo + hi) / 2; if (cand[mid] > thr) lo = mid + 1; else hi = mid; }
          return lo;
       };
+      double t_wait_panel = 0.0;
+      const auto t_panel0 = std::chrono::steady_clock::now();
       auto take_snapshot = [&]() {
          launch_snapshot(d_fronts, d_flist, na_all, d_snap, s);
          snap_host.resize((size_t)na_all * 8);
          CUDA_TRY(cudaMemcpyAsync(snap_host.data(), d_snap, snap_host.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
          auto ts0 = std::chrono::steady_clock::now();
          CUDA_TRY(cudaStreamSynchronize(s));
-         t_sync += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
+         const double dtw = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
+         t_sync += dtw; t_wait_panel += dtw;
          if (g_prof) g_prof->collect();
       };
       /* Speculative path (panel_v2.h): the panel in PW / CW segments of three launches each (chain, tiles,
@@ -707,10 +711,12 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          int failed_cols = 0;
          for (int k = 0; k < na_all; ++k) failed_cols += H[act[k]].pend0 - H[act[k]].pend;
          if (big) fprintf(stderr, "[panel] fronts %d first(m %d n %d p0 %d done %d pend0 %d) failed_cols %d v2 %d steps %d "
-                 "lookahead %d tiles urgent %zu bulk %zu+%zu swap %zu  %.1f us since the previous panel\n",
+                 "lookahead %d tiles urgent %zu bulk %zu+%zu swap %zu  %.1f us since the previous panel "
+                 "(this panel: %.1f us from its first launch to the snapshot, of which %.1f us waiting in the sync)\n",
                  na_all, h0.m, h0.n, h0.p0, h0.done, h0.pend0, failed_cols, (int)v2, steps_todo, (int)lookahead,
                  outer.size(), bulk.size(), bulk_b.size(), swap_rows.size(),
-                 std::chrono::duration<double, std::micro>(now - last).count());
+                 std::chrono::duration<double, std::micro>(now - last).count(),
+                 std::chrono::duration<double, std::micro>(now - t_panel0).count(), 1e3 * t_wait_panel);
          last = now;
       }
       if (bulk_pending && (!outer.empty() || !swap_rows.empty())) {
@@ -1676,20 +1682,27 @@ int spral_ssids_gpu_subtree_export_contrib_ipc(void* numeric_subtree, unsigned c
    size_t rows = (size_t)nd + cn;
    size_t b_val = (size_t)cn * cn * sizeof(double), b_del = rows * nd * sizeof(double);
    size_t total = b_val + b_del + (size_t)nd * sizeof(int);
-   /* the block lives in the symbolic subtree's pool: same address (and IPC handle)
-    * for every factorisation, so the consumer maps it once */
+   /* the block lives in the symbolic subtree's pool -- two buffers used alternately, so that a slow consumer can
+    * still pull the block of the previous factorisation while this one is packed (the host protocol of dist.py
+    * waits for the consumer's acknowledgement before a buffer comes round again); the addresses (and IPC handles)
+    * repeat, so the consumer maps each buffer once */
    Symbolic& Sm = *N.S;
+   Buf& eb = Sm.b_export[Sm.export_slot];
+   Sm.export_slot ^= 1;
    cudaError_t e = cudaSuccess;
-   try { Sm.b_export.ensure(std::max<size_t>(total, 256), N.stream); }
+   try { eb.ensure(std::max<size_t>(total, 256), N.stream); }
    catch (const CudaError& ce) { return (int)ce.code; }
-   char* blk = (char*)Sm.b_export.p;
-   if (cn) e = cudaMemcpy2D(blk, (size_t)cn * sizeof(double), f.C, (size_t)f.ldc * sizeof(double),
-                            (size_t)cn * sizeof(double), cn, cudaMemcpyDeviceToDevice);
+   char* blk = (char*)eb.p;
+   /* packed on the factorisation stream (ordered behind the kernels that produced the block) and complete before
+    * the handle leaves this function: the consumer's copy runs in another process, ordered against nothing here */
+   if (cn) e = cudaMemcpy2DAsync(blk, (size_t)cn * sizeof(double), f.C, (size_t)f.ldc * sizeof(double),
+                                 (size_t)cn * sizeof(double), cn, cudaMemcpyDeviceToDevice, N.stream);
    if (e == cudaSuccess && nd)
-      e = cudaMemcpy2D(blk + b_val, rows * sizeof(double), f.L + (size_t)f.nelim * (f.ldl + 1),
-                       (size_t)f.ldl * sizeof(double), rows * sizeof(double), nd, cudaMemcpyDeviceToDevice);
+      e = cudaMemcpy2DAsync(blk + b_val, rows * sizeof(double), f.L + (size_t)f.nelim * (f.ldl + 1),
+                            (size_t)f.ldl * sizeof(double), rows * sizeof(double), nd, cudaMemcpyDeviceToDevice, N.stream);
    if (e == cudaSuccess && nd)
-      e = cudaMemcpy(blk + b_val + b_del, f.perm + f.nelim, (size_t)nd * sizeof(int), cudaMemcpyDeviceToDevice);
+      e = cudaMemcpyAsync(blk + b_val + b_del, f.perm + f.nelim, (size_t)nd * sizeof(int), cudaMemcpyDeviceToDevice, N.stream);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(N.stream);
    if (e != cudaSuccess) return (int)e;
    cudaIpcMemHandle_t h;
    e = cudaIpcGetMemHandle(&h, blk);

@@ -51,10 +51,21 @@ class GpuEngine:
     def symbolic(self, analysis, part, local_rank, options):
         return SymbolicSubtree(analysis, part, device=local_rank, options=options)
 
+    @staticmethod
+    def _join_torch_stream():
+        """The engine runs on private non-blocking streams: whatever torch has queued on ITS current stream
+        (index_select / scaling of the right-hand side, a device-resident value array being filled) must have
+        finished before the engine reads it.  The return path is ordered by the engine's own synchronisation."""
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
+
     def factor(self, symb, analysis, part, posdef, val, child_contrib, options, scaling):
+        self._join_torch_stream()
         return symb.factor(posdef, val, child_contrib, options, scaling)
 
     def solve(self, ns, which, X, nrhs, n):
+        self._join_torch_stream()
         getattr(ns, f"solve_{which}")(X.data_ptr(), nrhs, n)
 
     def get_contrib(self, ns):
@@ -73,6 +84,7 @@ class DistContext:
         self.world, self.rank, self.local_rank, self.engine = world, rank, local_rank, engine
         self._store, self.tag, self.epoch = store, tag, 0
         self._stage = {}          # producer part -> (device block, capacity): re-used across factorisations
+        self._exported = {}       # producer part -> epochs whose export buffers may still be read by the consumer
 
     @property
     def store(self):
@@ -201,6 +213,14 @@ def _key(ctx, kind, p):
     return f"{ctx.tag}/{ctx.epoch}/{kind}/{p}"
 
 
+def _delete(ctx, key):
+    """Spent rendezvous keys are removed (a long-running solve loop must not grow the store)."""
+    try:
+        ctx.store.delete_key(key)
+    except Exception:           # a store without delete_key (FileStore on some builds): keys are small, keep them
+        pass
+
+
 def _contrib_rlist(a, p):
     """Global row indices of part p's root contribution (host, from the replicated analysis)."""
     root = int(a.part[p + 1]) - 1
@@ -213,6 +233,14 @@ def publish_contrib(ctx, ak, p, ns):
     """Producer side of a cross-rank edge."""
     if ctx.engine.device_ipc:
         lib = _lib.load()
+        # the engine packs into one of TWO export buffers per part, alternating: the buffer of two exports ago is
+        # re-used now, so its consumer must have pulled it (it acknowledges with a "pulled" key, deleted here)
+        hist = ctx._exported.setdefault(p, [])
+        while len(hist) >= 2:
+            old = _Epoch(ctx, hist.pop(0))
+            ctx.store.wait([_key(old, "pulled", p)])
+            _delete(ctx, _key(old, "pulled", p))
+        hist.append(ctx.epoch)
         handle = (C.c_ubyte * 64)()
         n, nd, nbytes, blk = C.c_int(), C.c_int(), C.c_int64(), C.c_void_p()
         rc = lib.spral_ssids_gpu_subtree_export_contrib_ipc(ns._h, handle, C.byref(n), C.byref(nd),
@@ -293,6 +321,8 @@ def fetch_contrib(ctx, ak, p, posdef):
         rc = lib.spral_ssids_b200_ipc_pull(ctx.local_rank, handle, meta["bytes"], blk)
         if rc != 0:
             raise RuntimeError(f"ipc_pull failed: cudaError {rc}")
+        _delete(ctx, key)                                   # single consumer: the key is spent
+        ctx.store.set(_key(ctx, "pulled", p), b"1")         # the producer may re-use that export buffer
         b_val = n * n * 8
         rows = nd + n
         c.val, c.ldval = (blk if n else None), n
@@ -301,6 +331,7 @@ def fetch_contrib(ctx, ak, p, posdef):
         c.delay_perm = blk + b_val + rows * nd * 8 if nd else None
         c.device = ctx.local_rank
         return _Fetched(c, [rl], None)          # the staging block stays with the context
+    _delete(ctx, key)
     keep = [rl, meta["val"], meta["dval"], meta["dperm"]]
     c.val = meta["val"].ctypes.data if meta["val"] is not None else None
     c.ldval = meta["ldval"]
@@ -532,7 +563,9 @@ def _recv(ctx, kind, p, dev):
     import torch
     key = _key(ctx, kind, p)
     ctx.store.wait([key])
-    return torch.from_numpy(pickle.loads(ctx.store.get(key))).to(dev)
+    t = torch.from_numpy(pickle.loads(ctx.store.get(key))).to(dev)
+    _delete(ctx, key)                                       # one consumer per cross-rank edge
+    return t
 
 
 def solve(ctx, fk, x, job=0):

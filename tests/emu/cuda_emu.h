@@ -39,6 +39,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::functio
 void sync_block();
 void* dyn_smem();
 void shfl_exchange(const void* in, void* out, size_t bytes, int src_lane);
+void warp_gather(const void* in, void* out32, size_t bytes);
 long switches();
 }
 extern emu::Idx threadIdx, blockIdx, blockDim, gridDim;
@@ -49,6 +50,26 @@ template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { T r; emu::shfl_exchange(&v, &r, sizeof(T), src); return r; }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int off) {
    T r; emu::shfl_exchange(&v, &r, sizeof(T), (int)(threadIdx.x & 31) ^ off); return r; }
+/* warp collectives used by diag_warp.cuh / the panel kernels: every lane of the warp takes part */
+inline void __syncwarp(unsigned = 0xffffffffu) { int z = 0, o[32]; emu::warp_gather(&z, o, sizeof(int)); }
+inline unsigned __ballot_sync(unsigned, int pred) {
+   int v = pred ? 1 : 0, o[32];
+   emu::warp_gather(&v, o, sizeof(int));
+   unsigned r = 0;
+   for (int l = 0; l < 32; ++l) if (o[l]) r |= 1u << l;
+   return r;
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+   unsigned o[32];
+   emu::warp_gather(&v, o, sizeof(unsigned));
+   unsigned r = v;
+   for (int l = 0; l < 32; ++l) if (o[l] > r) r = o[l];
+   return r;
+}
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __double2hiint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b >> 32); }
+inline int __double2loint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b & 0xffffffffLL); }
+inline double __hiloint2double(int hi, int lo) { long long b = ((long long)(unsigned)hi << 32) | (unsigned)lo; double d; std::memcpy(&d, &b, 8); return d; }
 inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }

@@ -56,6 +56,18 @@ void shfl_exchange(const void* in, void* out, size_t bytes, int src_lane) {
    sync_warp();
 }
 
+/* all-gather inside the warp: out[l] = the value lane l passed in (lanes that do not exist: zero bytes) */
+void warp_gather(const void* in, void* out32, size_t bytes) {
+   const int lane = cur & 31, warp = cur >> 5;
+   std::memcpy(slots[warp].v[lane], in, bytes);
+   sync_warp();
+   for (int l = 0; l < 32; ++l) {
+      if (warp * 32 + l < nthreads) std::memcpy((char*)out32 + l * bytes, slots[warp].v[l], bytes);
+      else std::memset((char*)out32 + l * bytes, 0, bytes);
+   }
+   sync_warp();
+}
+
 void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()>& body) {
    std::lock_guard<std::mutex> lock(big_lock);
    if (block == 0 || grid == 0) return;

@@ -354,6 +354,66 @@ def test_device_resident_inputs():
     assert oracle_ref.backward_error(A, x, b) < 1e-14
 
 
+def _golden_full(name):
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "oracle_stats_full.json")) as fh:
+        return json.load(fh)[name]
+
+
+def _full_size_oracle_parity(name, gen, posdef):
+    """CUDA path against the oracle's committed statistics of the SAME matrix, ordering and options
+    (tests/golden/make_golden_full.py ran oracle/_ref at full size): flag, rank and inertia identical,
+    delays within the stated tolerance, num_factor / num_flops identical when neither side delays,
+    backward error of the golden right-hand sides <= 10x the oracle's and <= 1e-14 after one refinement step
+    (the bars of north_star; residual definition: tests/ssids/ssids.f90:1685-1691, driver/spral_ssids.F90:419-480)."""
+    gold = _golden_full(name)
+    n, ptr, row, val = gen()
+    assert n == gold["n"]
+    ak = sb.analyse(n, ptr, row)
+    a = ak.analysis
+    assert a.nnodes == gold["nnodes"] and a.num_flops == gold["predicted_num_flops"]      # same ordering, same tree
+    fk = sb.factor(ak, posdef, val)
+    g = fk.inform
+    assert g["flag"] == gold["flag"] == 0
+    assert g["matrix_rank"] == gold["matrix_rank"] == n
+    assert g["maxfront"] >= gold["maxfront"] - 64 and g["maxfront"] <= gold["maxfront"] + 64
+    if not posdef:
+        assert g["num_neg"] == gold["num_neg"]
+        assert abs(g["num_delay"] - gold["num_delay"]) <= 8 + 0.25 * gold["num_delay"], (g["num_delay"], gold["num_delay"])
+    if g["num_delay"] == 0 and gold["num_delay"] == 0:
+        assert g["num_factor"] == gold["num_factor"] and g["num_flops"] == gold["num_flops"]
+    else:
+        assert g["num_flops"] >= gold["predicted_num_flops"]
+        assert abs(g["num_flops"] - gold["num_flops"]) <= 1e-4 * gold["num_flops"]
+    A = M.to_scipy(n, ptr, row, val)
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.uniform(-1, 1, (n, 2)))
+    X[:, 0] = 1.0
+    B = np.asfortranarray(A @ X)
+    Xs = sb.solve(fk, B)
+    bwd = oracle_ref.backward_error(A, Xs, B)
+    assert bwd < REF_TOL and bwd <= 10 * gold["bwd"] + 2e-15, (bwd, gold["bwd"])
+    Xs2 = Xs + sb.solve(fk, np.asfortranarray(B - A @ Xs))
+    assert oracle_ref.backward_error(A, Xs2, B) <= 1e-14
+    return ak, fk, g
+
+
+def test_full_size_parity_cfg2():
+    """BASELINE config 2 (3-D 7-point 60^3, LL^T) against the oracle golden."""
+    _full_size_oracle_parity("cfg2", lambda: M.laplacian_3d_7pt(60), True)
+
+
+def test_full_size_parity_cfg3():
+    """BASELINE config 3 (3-D 27-point 80^3 shifted, LDL^T u = 0.01) against the oracle golden."""
+    _full_size_oracle_parity("cfg3", lambda: M.stencil_3d_27pt(80, shift=13.0), False)
+
+
+def test_full_size_parity_cfg5():
+    """BASELINE config 5, the headline workload (3-D 27-point 100^3 shifted, n = 10^6) against the oracle golden
+    (oracle: num_neg 39211, rank 10^6, 18 delays, backward error 2.5e-12)."""
+    _full_size_oracle_parity("cfg5", lambda: M.stencil_3d_27pt(100, shift=13.0), False)
+
+
 def test_full_size_properties_cfg2():
     """BASELINE config 2 at full size (3-D 7-point 60^3, posdef): size-independent
     properties -- residual, num_flops == analyse prediction, linearity of the solve."""

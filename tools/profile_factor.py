@@ -20,7 +20,8 @@ for ns in fk.numeric: ns.close()
 torch.cuda.synchronize()
 rt = torch.cuda.cudart()
 from spral_b200 import _lib
-_lib.load().spral_ssids_b200_set_profile(1)      # NVTX range "upd_contrib" + event timing
+if not os.environ.get("SPRAL_B200_NOPROFILE"):
+    _lib.load().spral_ssids_b200_set_profile(1)      # NVTX range "upd_contrib" + event timing
 rt.cudaProfilerStart()
 t = time.time()
 fk = sb.factor(ak, posdef, dval.data_ptr())
