@@ -35,7 +35,6 @@
 #include "engine.h"
 #include "device_utils.cuh"
 #include "pivot_state.h"
-#include "diag_block.h"
 #include "diag_warp.cuh"
 #include "panel_v2.h"
 
@@ -203,311 +202,10 @@ void launch_delays(Front* fronts, const AsmSrc* srcs, const int2* work, int nwor
 /* Diagonal block                                                            */
 /* ------------------------------------------------------------------------ */
 
-/* One 32x32-thread CTA per front: thread (r, c) owns entry (r, c) of the block,
- * a warp owns a column.  The block lives in shared memory as a full symmetric
- * matrix, double buffered: every pivot reads the old buffer (through the
- * permutation that brings the chosen pivot to the front) and writes the new
- * one, so a pivot costs two block-wide barriers.  Entry (r,c) and its mirror
- * (c,r) are computed with the same expression, which keeps the block exactly
- * symmetric. */
-template <bool POSDEF>
-__global__ void __launch_bounds__(BS * BS)
-k_diag(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
-   Front* f = &fronts[flist[blockIdx.x]];
-   const int r = threadIdx.x & 31, c = threadIdx.x >> 5;     // warp == column c
-   __shared__ double A[2][BS][BS + 1];
-   __shared__ double LDm[2][BS][BS + 1];
-   __shared__ double dinv[2 * BS];
-   __shared__ double cmax[BS];
-   __shared__ int crow[BS];
-   __shared__ int lperm[BS];
-   __shared__ int s_go;
-   __shared__ int s_piv_i[4];
-   __shared__ double s_piv_d[4];
-
-   if (threadIdx.x == 0) {
-      advance_state(f, new_panel != 0);
-      if (!f->finished && f->done < f->pend) {
-         f->bs = min(BS, f->pend - f->done);
-         f->first_fail = f->bs;
-         f->step_valid = 1;
-         s_go = 1;
-      } else {
-         f->bs = 0;
-         s_go = 0;
-      }
-   }
-   __syncthreads();
-   if (!s_go) return;
-   const int bs = f->bs, done = f->done, ldl = f->ldl;
-   double* Ld = f->L + (size_t)done * ldl + done;   // the diagonal block
-   BlockWS* ws = f->ws;
-
-   /* load the lower triangle, mirror it */
-   {
-      double v = 0.0;
-      if (r < bs && c < bs && r >= c) v = Ld[r + (size_t)c * ldl];
-      A[0][r][c] = v;
-      LDm[0][r][c] = 0.0; LDm[1][r][c] = 0.0;
-      if (c == 0) { lperm[r] = r; dinv[2 * r] = 0.0; dinv[2 * r + 1] = 0.0; }
-   }
-   __syncthreads();
-   if (r < c) A[0][r][c] = A[0][c][r];
-   __syncthreads();
-   int cur = 0;
-
-   if (POSDEF) {
-      /* Cholesky of the block (cholesky_factor, src/ssids/cpu/kernels/cholesky.cxx:33-187) */
-      for (int p = 0; p < bs; ++p) {
-         double d = A[cur][p][p];
-         if (!(d > 0.0)) {
-            if (threadIdx.x == 0) { f->flag = SPRAL_SSIDS_ERROR_NOT_POS_DEF; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
-            return;
-         }
-         double lpp = sqrt(d);
-         const int R = max(r, c), C = min(r, c);
-         double v = A[cur][R][C];
-         if (C == p) v = (R == p) ? lpp : v / lpp;
-         else if (C > p) v -= (A[cur][R][p] / lpp) * (A[cur][C][p] / lpp);
-         A[cur ^ 1][r][c] = v;
-         if (threadIdx.x == 0) dinv[p] = 1.0 / lpp;
-         __syncthreads();
-         cur ^= 1;
-      }
-      double l = (r < bs && c < bs && r >= c) ? A[cur][r][c] : 0.0;
-      if (r < bs && c < bs && r >= c) Ld[r + (size_t)c * ldl] = l;
-      ws->l11[r + c * BS] = l;
-      if (c == 0) ws->dinv[r] = (r < bs) ? dinv[r] : 0.0;
-      return;
-   }
-
-   /* keep the unfactorised block for k_commit */
-   ws->a0[r + c * BS] = A[0][r][c];
-
-   int zfrom = BS;
-   int p = 0;
-   /* column-wise maxima of the remaining lower triangle (ties: smallest row); the
-    * search for pivot p+1 is folded into the update of pivot p */
-   auto column_max = [&](double val, int pp) {
-      double v = (r >= c && c >= pp && r < bs) ? fabs(val) : -1.0;
-      int rr = r;
-      #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-         double ov = __shfl_xor_sync(0xffffffffu, v, off);
-         int orr = __shfl_xor_sync(0xffffffffu, rr, off);
-         if (ov > v || (ov == v && orr < rr)) { v = ov; rr = orr; }
-      }
-      if (r == 0) { cmax[c] = v; crow[c] = rr; }
-   };
-   column_max(A[cur][r][c], 0);
-   while (p < bs) {
-      __syncthreads();
-      /* one warp takes the decision and does the divisions; everybody else waits */
-      if (c == 0) {
-         double best = cmax[r];
-         int bidx = r * BS + crow[r];          // lane r looks at column r
-         #pragma unroll
-         for (int off = 16; off > 0; off >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, off);
-            int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-         }
-         if (r == 0) {
-            int m_ = bidx / BS, t_ = bidx % BS;      // column m <= row t
-            int ps = 1;
-            double e11 = 0, e21 = 0, e22 = 0;
-            if (!(best >= prm.small)) ps = 0;
-            else if (t_ == m_) e11 = 1.0 / A[cur][t_][t_];
-            else {
-               double a11 = A[cur][m_][m_], a22 = A[cur][t_][t_], a21 = A[cur][t_][m_];
-               double detscale = 1.0 / fabs(a21);
-               double detpiv = (a11 * detscale) * a22 - fabs(a21);
-               if (fabs(detpiv) >= fabs(a21) / 2) {
-                  ps = 2;
-                  e11 = (a22 * detscale) / detpiv;
-                  e22 = (a11 * detscale) / detpiv;
-                  e21 = (-a21 * detscale) / detpiv;
-               } else {
-                  if (fabs(a11) > fabs(a22)) t_ = m_;    // a11 as 1x1, else a22 (row/col t)
-                  e11 = 1.0 / A[cur][t_][t_];
-               }
-            }
-            s_piv_i[0] = ps; s_piv_i[1] = t_; s_piv_i[2] = m_;
-            s_piv_d[0] = e11; s_piv_d[1] = e21; s_piv_d[2] = e22;
-         }
-      }
-      __syncthreads();
-      const int pivsiz = s_piv_i[0], t = s_piv_i[1], m = s_piv_i[2];
-      const double d11 = s_piv_d[0], d21 = s_piv_d[1], d22 = s_piv_d[2];
-
-      if (pivsiz == 0) {
-         /* everything left is (numerically) zero: block_ldlt.hxx:303-317 */
-         if (!prm.action) {
-            if (threadIdx.x == 0) { f->flag = SPRAL_SSIDS_ERROR_SINGULAR; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
-            return;
-         }
-         zfrom = p;
-         const int R = max(r, c), C = min(r, c);
-         if (C >= p) { A[cur][r][c] = (R == C) ? 1.0 : 0.0; LDm[cur][r][c] = 0.0; }
-         __syncthreads();
-         break;
-      }
-
-      const int R = max(r, c), C = min(r, c);
-      const double (*Ao)[BS + 1] = A[cur];
-      const double (*Lo)[BS + 1] = LDm[cur];
-      double vnew, ldnew;
-      if (pivsiz == 1) {
-         /* new position x holds old position pi(x): swap p <-> t */
-         auto pi = [&](int x) { return x == p ? t : (x == t ? p : x); };
-         const int oR = pi(R), oC = pi(C);
-         if (C < p) { vnew = Ao[oR][C]; ldnew = Lo[oR][C]; }
-         else if (C == p) {
-            double wr = Ao[oR][t];
-            vnew = (R == p) ? 1.0 : wr * d11;
-            ldnew = (R == p) ? 0.0 : wr;
-         } else {
-            vnew = Ao[oR][oC] - (Ao[oR][t] * d11) * Ao[oC][t];
-            ldnew = 0.0;
-         }
-         if (threadIdx.x == 0) {
-            dinv[2 * p] = d11; dinv[2 * p + 1] = 0.0;
-            int q = lperm[p]; lperm[p] = lperm[t]; lperm[t] = q;
-         }
-      } else {
-         /* swap p <-> m, then p+1 <-> t */
-         auto pi1 = [&](int y) { return y == p ? m : (y == m ? p : y); };
-         auto pi = [&](int x) { return x == p + 1 ? pi1(t) : (x == t ? pi1(p + 1) : pi1(x)); };
-         const int oR = pi(R), oC = pi(C);
-         if (C < p) { vnew = Ao[oR][C]; ldnew = Lo[oR][C]; }
-         else if (C <= p + 1) {
-            if (R <= p + 1) {              // the 2x2 diagonal block of L is the identity
-               vnew = (R == C) ? 1.0 : 0.0; ldnew = 0.0;
-            } else {
-               double w1 = Ao[oR][m], w2 = Ao[oR][t];
-               if (C == p) { vnew = d11 * w1 + d21 * w2; ldnew = w1; }
-               else        { vnew = d21 * w1 + d22 * w2; ldnew = w2; }
-            }
-         } else {
-            double w1 = Ao[oR][m], w2 = Ao[oR][t];
-            double l1 = d11 * w1 + d21 * w2, l2 = d21 * w1 + d22 * w2;
-            vnew = Ao[oR][oC] - (Ao[oC][m] * l1 + Ao[oC][t] * l2);
-            ldnew = 0.0;
-         }
-         if (threadIdx.x == 0) {
-            dinv[2 * p] = d11; dinv[2 * p + 1] = d21;
-            dinv[2 * p + 2] = CUDART_INF; dinv[2 * p + 3] = d22;
-            int q = lperm[p]; lperm[p] = lperm[m]; lperm[m] = q;
-            q = lperm[p + 1]; lperm[p + 1] = lperm[t]; lperm[t] = q;
-         }
-      }
-      A[cur ^ 1][r][c] = vnew;
-      /* LD is only meaningful strictly below the diagonal of eliminated columns */
-      LDm[cur ^ 1][r][c] = (r > c) ? ldnew : 0.0;
-      cur ^= 1;
-      p += pivsiz;
-      if (p < bs) column_max(vnew, p);      // cmax was consumed before the previous barrier
-   }
-
-   /* publish L11 (unit lower), L11*D, D^-1 and the local permutation */
-   {
-      double l = 0.0, y = 0.0;
-      if (r < bs && c < bs) {
-         if (r > c) { l = A[cur][r][c]; y = LDm[cur][r][c]; }
-         else if (r == c) l = 1.0;
-      }
-      ws->l11[r + c * BS] = l;
-      ws->ld11[r + c * BS] = y;
-      if (c == 0) {
-         ws->dinv[2 * r] = (r < bs) ? dinv[2 * r] : 0.0;
-         ws->dinv[2 * r + 1] = (r < bs) ? dinv[2 * r + 1] : 0.0;
-         ws->lperm[r] = lperm[r];
-         if (r == 0) ws->zfrom = zfrom;
-      }
-   }
-}
-
-
-/* Version 2 (opt-in, SPRAL_B200_DIAG_V2=1): the same factorisation with NW warps,
- * every thread owning BS/NW entries of a column (diag_block.h).  The body is also
- * compiled for the host and checked bit for bit against a sequential model of
- * k_diag above (tests/c/diag_block_emu.cpp). */
-struct DiagDevCtx {
-   __device__ __forceinline__ int tid() const { return threadIdx.x; }
-   __device__ __forceinline__ void sync() { __syncthreads(); }
-   __device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
-   __device__ __forceinline__ int shfl_xor(int v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
-};
-
-template <bool POSDEF, int NW>
-__global__ void __launch_bounds__(NW * 32)
-k_diag_v2(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
-   Front* f = &fronts[flist[blockIdx.x]];
-   __shared__ DiagShared<NW> sh;
-   __shared__ int s_go;
-   constexpr int RPT = BS / NW;
-   const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
-
-   if (threadIdx.x == 0) {
-      advance_state(f, new_panel != 0);
-      if (!f->finished && f->done < f->pend) {
-         f->bs = min(BS, f->pend - f->done);
-         f->first_fail = f->bs;
-         f->step_valid = 1;
-         s_go = 1;
-      } else {
-         f->bs = 0;
-         s_go = 0;
-      }
-   }
-   __syncthreads();
-   if (!s_go) return;
-   const int bs = f->bs, done = f->done, ldl = f->ldl;
-   double* Ld = f->L + (size_t)done * ldl + done;   // the diagonal block
-   BlockWS* ws = f->ws;
-
-   DiagDevCtx cx;
-   int cur = 0, zfrom = BS;
-   const int rc = diag_block_factor<NW, POSDEF>(cx, sh, Ld, (size_t)ldl, bs, prm.small, prm.action, CUDART_INF,
-                                                POSDEF ? nullptr : ws->a0, cur, zfrom);
-   if (rc != DB_OK) {
-      if (threadIdx.x == 0) { f->flag = rc; f->finished = 1; f->step_valid = 0; f->nelim = f->done; }
-      return;
-   }
-   if (POSDEF) {
-      #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-         const int r = q * RPT + i;
-         const double l = (r < bs && c < bs && r >= c) ? sh.A[cur][r][c] : 0.0;
-         if (r < bs && c < bs && r >= c) Ld[r + (size_t)c * ldl] = l;
-         ws->l11[r + c * BS] = l;
-      }
-      if (q == 0) ws->dinv[c] = (c < bs) ? sh.dinv[c] : 0.0;
-   } else {
-      /* publish L11 (unit lower), L11*D, D^-1 and the local permutation */
-      #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-         const int r = q * RPT + i;
-         double l = 0.0, y = 0.0;
-         if (r < bs && c < bs) {
-            if (r > c) { l = sh.A[cur][r][c]; y = sh.LDm[cur][r][c]; }
-            else if (r == c) l = 1.0;
-         }
-         ws->l11[r + c * BS] = l;
-         ws->ld11[r + c * BS] = y;
-      }
-      if (q == 0) {
-         ws->dinv[2 * c] = (c < bs) ? sh.dinv[2 * c] : 0.0;
-         ws->dinv[2 * c + 1] = (c < bs) ? sh.dinv[2 * c + 1] : 0.0;
-         ws->lperm[c] = sh.lperm[c];
-         if (c == 0) ws->zfrom = zfrom;
-      }
-   }
-}
-
-/* Version 3 (default): ONE warp per front (diag_warp.cuh) -- no block-wide barrier inside the chain of
- * pivots, the decision taken redundantly by every lane.  SPRAL_B200_DIAG=1 selects the thread-per-entry
- * kernel above, =2 the four-warp variant. */
+/* ONE warp per front (diag_warp.cuh): no block-wide barrier inside the chain of pivots, the decision taken
+ * redundantly by every lane, every load of a rank-1 / rank-2 update issued before its stores.  (Round 1 used a
+ * 1024-thread CTA, thread per entry, two block barriers per pivot: 51 us per block; a 4-warp variant measured the
+ * same.  This kernel: 25 us per block on a B200, tools/micro/bench_diag.cu.) */
 template <bool POSDEF>
 __global__ void __launch_bounds__(32)
 k_diag_w(Front* fronts, const int* __restrict__ flist, int new_panel, FactorParams prm) {
@@ -580,34 +278,12 @@ k_diag_w(Front* fronts, const int* __restrict__ flist, int new_panel, FactorPara
    if (lane == 0) ws->zfrom = zfrom;
 }
 
-static int diag_version() {
-   static int v = -1;
-   if (v < 0) {
-      v = 3;
-      if (const char* e = getenv("SPRAL_B200_DIAG")) v = std::max(1, std::min(3, atoi(e)));
-      if (const char* e = getenv("SPRAL_B200_DIAG_V2")) if (atoi(e) != 0) v = 2;
-   }
-   return v;
-}
-
 void launch_diag(Front* fronts, const int* flist, int count, bool posdef, bool new_panel,
       const FactorParams& prm, cudaStream_t s) {
    if (count == 0) return;
-   if (diag_version() == 3) {
-      if (posdef) k_diag_w<true><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
-      else k_diag_w<false><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
-      COUNT_LAUNCH();
-      return;
-   }
-   if (diag_version() == 2) {
-      constexpr int NW = 4;
-      if (posdef) k_diag_v2<true, NW><<<count, NW * 32, 0, s>>>(fronts, flist, new_panel, prm);
-      else k_diag_v2<false, NW><<<count, NW * 32, 0, s>>>(fronts, flist, new_panel, prm);
-      COUNT_LAUNCH();
-      return;
-   }
-   if (posdef) k_diag<true><<<count, BS * BS, 0, s>>>(fronts, flist, new_panel, prm);
-   else k_diag<false><<<count, BS * BS, 0, s>>>(fronts, flist, new_panel, prm); COUNT_LAUNCH();
+   if (posdef) k_diag_w<true><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
+   else k_diag_w<false><<<count, 32, 0, s>>>(fronts, flist, new_panel, prm);
+   COUNT_LAUNCH();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -706,25 +382,24 @@ k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, Facto
       if (sh.status) { ok = 0; break; }
 
       if (warp == 1) {
-         /* X = L_jj^-1 (lower): lane c owns column c; x_r = -(sum_{c <= k < r} L(r, k) x_k) / l_rr */
+         /* X = L_jj^-1 (lower): lane c owns column c, kept in registers (no store / load round trip through shared
+          * memory between rows): x_r = -(sum_{c <= k < r} L(r, k) x_k) / l_rr */
          const int c = lane;
+         double x[PV_BS];
+         #pragma unroll
          for (int r = 0; r < PV_BS; ++r) {
-            double x;
-            if (r < c) x = 0.0;
-            else if (r == c) x = POSDEF ? sh.c0[c] : 1.0;
-            else {
-               double s0 = 0.0, s1 = 0.0;
-               int k = c;
-               for (; k + 1 < r; k += 2) {
-                  s0 += sh.B[r * DW_LD + k] * sh.X[k * DW_LD + c];
-                  s1 += sh.B[r * DW_LD + k + 1] * sh.X[(k + 1) * DW_LD + c];
-               }
-               if (k < r) s0 += sh.B[r * DW_LD + k] * sh.X[k * DW_LD + c];
-               x = -(s0 + s1);
-               if (POSDEF) x *= sh.c0[r];
+            double s0 = 0.0, s1 = 0.0;
+            #pragma unroll
+            for (int k = 0; k < r; ++k) {
+               const double t = sh.B[r * DW_LD + k] * x[k];      // x[k] == 0 for k < c
+               if (k & 1) s1 += t; else s0 += t;
             }
-            sh.X[r * DW_LD + c] = x;
+            double v = -(s0 + s1);
+            if (POSDEF) v *= sh.c0[r];
+            x[r] = (r < c) ? 0.0 : (r == c ? (POSDEF ? sh.c0[c] : 1.0) : v);
          }
+         #pragma unroll
+         for (int r = 0; r < PV_BS; ++r) sh.X[r * DW_LD + c] = x[r];
       } else if (warp >= 2 && warp <= 4) {
          /* rows of the diagonal block below the 32 x 32 block: Y = A21(:, lperm) L11^-T, W = Y D^-1,
           * a-posteriori test |w| <= 1/u (ldlt_app.cxx:303-321) */
@@ -769,12 +444,15 @@ k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, Facto
          }
       } else if (warp == 5) {
          const int i = lane;                            // a row of the 32 x 32 block itself
-         #pragma unroll 8
+         double lv[PV_BS], dv[PV_BS];
+         #pragma unroll
+         for (int c = 0; c < PV_BS; ++c) { lv[c] = sh.B[i * DW_LD + c]; dv[c] = POSDEF ? lv[c] : sh.B[c * DW_LD + i]; }
+         #pragma unroll
          for (int c = 0; c < PV_BS; ++c) {
             if (c < i) {
-               S[(jb + c) * CLD + jb + i] = sh.B[i * DW_LD + c];
-               S[(jb + i) * CLD + jb + c] = POSDEF ? sh.B[i * DW_LD + c] : sh.B[c * DW_LD + i];
-            } else if (c == i) S[(jb + c) * CLD + jb + i] = POSDEF ? sh.B[i * DW_LD + i] : 1.0;
+               S[(jb + c) * CLD + jb + i] = lv[c];
+               S[(jb + i) * CLD + jb + c] = dv[c];
+            } else if (c == i) S[(jb + c) * CLD + jb + i] = POSDEF ? lv[c] : 1.0;
          }
       } else if (!POSDEF) {
          /* earlier columns of the segment (warps 0, 6, 7): the block's permutation is a row permutation of L */
@@ -886,17 +564,26 @@ k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
       const int rr = (tid & 63) * 2, cq = tid >> 6;
       const int r = r0 + rr;
       const bool a0 = (r >= p + CW) && (r < m), a1 = (r + 1 >= p + CW) && (r + 1 < m);
-      #pragma unroll 8
-      for (int c = cq; c < CW; c += TNT / 64) {
-         double2 v = make_double2(0.0, 0.0);
-         const double* src = Lp + r + (size_t)c * ldl;
-         if (a0 && a1) v = *reinterpret_cast<const double2*>(src);
-         else { if (a0) v.x = src[0]; if (a1) v.y = src[1]; }
-         *reinterpret_cast<double2*>(&T[c * CLD + rr]) = v;
-         if (!POSDEF) {                                      // Cholesky never rolls back
-            double* dst = BK + r + (size_t)c * ldl;
-            if (a0 && a1) *reinterpret_cast<double2*>(dst) = v;
-            else { if (a0) dst[0] = v.x; if (a1) dst[1] = v.y; }
+      constexpr int NBL = 8;                                  // columns in flight per thread: all loads, then all stores
+      for (int c0 = cq; c0 < CW; c0 += NBL * (TNT / 64)) {
+         double2 v[NBL];
+         #pragma unroll
+         for (int q = 0; q < NBL; ++q) {
+            const int c = c0 + q * (TNT / 64);
+            v[q] = make_double2(0.0, 0.0);
+            const double* src = Lp + r + (size_t)c * ldl;
+            if (a0 && a1) v[q] = *reinterpret_cast<const double2*>(src);
+            else { if (a0) v[q].x = src[0]; if (a1) v[q].y = src[1]; }
+         }
+         #pragma unroll
+         for (int q = 0; q < NBL; ++q) {
+            const int c = c0 + q * (TNT / 64);
+            *reinterpret_cast<double2*>(&T[c * CLD + rr]) = v[q];
+            if (!POSDEF) {                                      // Cholesky never rolls back
+               double* dst = BK + r + (size_t)c * ldl;
+               if (a0 && a1) *reinterpret_cast<double2*>(dst) = v[q];
+               else { if (a0) dst[0] = v[q].x; if (a1) dst[1] = v[q].y; }
+            }
          }
       }
    }
@@ -982,14 +669,19 @@ k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
          const int r = tid & (RT - 1), h = tid / RT;
          const int grow = r0 + r;
          const bool active = (grow >= p + CW) && (grow < m);
-         #pragma unroll 4
-         for (int j = h * 16; j < h * 16 + 16; ++j) {
-            const double y = sh.Ys[j * CLD + r];
+         double yv[18];                                       // columns h*16 - 1 .. h*16 + 16: loads first, then the stores
+         #pragma unroll
+         for (int q = 0; q < 18; ++q) {
+            const int j = h * 16 - 1 + q;
+            yv[q] = (j >= 0 && j < PV_BS) ? sh.Ys[j * CLD + r] : 0.0;
+         }
+         #pragma unroll
+         for (int q = 1; q < 17; ++q) {
+            const int j = h * 16 - 1 + q;
+            const double y = yv[q];
             double wv = y;
             if (!POSDEF) {
-               wv = sh.c0[j] * y;
-               if (j + 1 < PV_BS) wv += sh.c1[j] * sh.Ys[(j + 1) * CLD + r];
-               if (j > 0) wv += sh.c2[j] * sh.Ys[(j - 1) * CLD + r];
+               wv = sh.c0[j] * y + sh.c1[j] * yv[q + 1] + sh.c2[j] * yv[q - 1];
                if (active && !(fabs(wv) <= lim)) bad = 1;
             }
             T[(jb + j) * CLD + r] = wv;

@@ -45,20 +45,21 @@ struct CudaError { cudaError_t code; };
 static bool g_profile = false;
 static bool g_solve_graphs = false;  // SPRAL_B200_SOLVE_GRAPHS=1: replay the sweeps as CUDA graphs (no measured gain)
 static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative launch per level (experimental: no measured gain yet)
-static int g_solve_wide = 0;         // SPRAL_B200_SOLVE_WIDE=1 (experimental, unmeasured): 256-column sweeps (solve_wide.h) on
+static int g_solve_wide = 1;         // 256-column sweeps (solve_wide.h; SPRAL_B200_SOLVE_WIDE=0: 32-column steps everywhere) on
                                      // levels whose largest front has at least SPRAL_B200_SOLVE_WIDE_MIN (8) 32-column steps
 static int g_solve_wide_min = 8;
 static bool g_trace_panels = false;  // SPRAL_B200_TRACE_PANELS=1: per-panel trace lines on stderr (host time between panels)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS); < 0: one CTA per tile
-static bool g_panel_v2 = false;      // SPRAL_B200_PANEL_V2=1 (experimental, unmeasured): speculative 128-column panel segments
-                                     // (panel_v2.h) on levels of at most g_panel_v2_fronts large fronts
+static bool g_panel_v2 = true;       // speculative 128-column panel segments (panel_v2.h) on levels of at most g_panel_v2_fronts
+                                     // large fronts (SPRAL_B200_PANEL_V2=0: every panel step by step).  Measured on cfg5:
+                                     // 376 -> 357 ms together with g_bulk_prio (profiles/r02_ab_variants.md)
 static int g_panel_v2_fronts = 32;
 static int g_ctile_block = 0;        // SPRAL_B200_CTILE_BLOCK=12 (experimental, unmeasured): Schur-complement tiles in
                                      // SB x SB blocked order for L2 reuse of the operand panels (0 = column by column)
-static bool g_bulk_prio = false;     // SPRAL_B200_BULK_PRIO=1 (experimental, unmeasured): instead of a static SM split,
-                                     // the panel stream gets the highest stream priority and the bulk update runs one
-                                     // tile per CTA on the lowest, so the panel kernels take SMs as bulk tiles retire
+static bool g_bulk_prio = true;      // no static SM split: the panel stream has the highest stream priority and the bulk
+                                     // update runs one tile per CTA on the lowest, so the panel kernels take SMs as bulk
+                                     // tiles retire (SPRAL_B200_BULK_PRIO=0: persistent bulk kernel on SMs - 28)
 /* Clears (and, with SPRAL_B200_DEBUG set, reports) a pending non-sticky CUDA
  * error so that it cannot leak into the host application's own CUDA calls. */
 static void clear_cuda_error(const char* where) {

@@ -66,6 +66,8 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
    for (int l = 0; l < 32; ++l) if (o[l] > r) r = o[l];
    return r;
 }
+inline long long __double_as_longlong(double d) { long long b; std::memcpy(&b, &d, 8); return b; }
+inline double __longlong_as_double(long long b) { double d; std::memcpy(&d, &b, 8); return d; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __double2hiint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b >> 32); }
 inline int __double2loint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b & 0xffffffffLL); }

@@ -1,35 +1,14 @@
 """CPU checks of device-code bodies that are written once and compiled twice.
 
-spral_b200/csrc/diag_block.h is the body of k_diag_v2 (the NW-warp diagonal-block
-LDL^T / Cholesky); tests/c/diag_block_emu.cpp runs it on host threads (one per CUDA
-thread, barriers and shuffles emulated), compares it bit for bit with a sequential
-model of the thread-per-entry kernel k_diag, checks P A P^T = L D L^T, and -- when the
-reference tree is mounted -- that the pivot sequence and D agree with the reference's
-own block_ldlt<double,32> (src/ssids/cpu/kernels/block_ldlt.hxx:289-413)."""
+spral_b200/csrc/diag_warp.cuh (the one-warp 32 x 32 LDL^T / Cholesky of k_diag_w and of the chain
+kernel) runs on the fiber emulator of tests/emu; solve_wide.h on host threads (tests/c/emu.h); the
+pivoting state machine, the two-stream look-ahead and the distributed-front protocol are model-checked."""
 import os
 import subprocess
 
 from conftest import ROOT
 
 REF = "/root/reference"
-
-
-def test_diag_block_v2_body_matches_k_diag_model_bit_for_bit():
-    out = os.path.join(ROOT, "build", "tests")
-    os.makedirs(out, exist_ok=True)
-    exe = os.path.join(out, "diag_block_emu")
-    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread"]
-    have_ref = os.path.isdir(os.path.join(REF, "src", "ssids", "cpu", "kernels"))
-    if have_ref:
-        cmd += ["-DHAVE_REF", "-mavx2", "-mfma", "-I" + os.path.join(REF, "src")]
-    cmd += ["-o", exe, os.path.join(ROOT, "tests", "c", "diag_block_emu.cpp")]
-    subprocess.check_call(cmd)
-    r = subprocess.run([exe, "96"], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert " 0 failures" in r.stdout, r.stdout
-    if have_ref:
-        n_ref = int(r.stdout.split("worst reconstruction error")[1].split(",")[1].split()[0])
-        assert n_ref > 0, r.stdout
 
 
 def test_wide_solve_bodies_match_plain_sweeps():
