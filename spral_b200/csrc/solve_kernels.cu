@@ -23,6 +23,7 @@
  *   order and solves the transposed diagonal block.
  */
 #include "engine.h"
+#include "device_utils.cuh"
 #include "solve_wide.h"
 #include <math_constants.h>
 
@@ -157,13 +158,14 @@ k_fwd_level_coop(const SolveFront* fronts, const RowTile* work, int nsteps,
    }
 }
 
-/* x(eliminated variables) <- ywork */
-__global__ void __launch_bounds__(128)
-k_fwd_flush(const SolveFront* fronts, int first, int nrhs, double* __restrict__ x, int ldx,
+/* x(eliminated variables) <- ywork.  Grid = fronts x column chunks (block b: front b % count, chunk b / count): the large fronts are not left to one CTA. */
+__global__ void __launch_bounds__(256)
+k_fwd_flush(const SolveFront* fronts, int first, int count, int nrhs, double* __restrict__ x, int ldx,
       const double* __restrict__ ywork) {
    const int NR = nrhs;
-   const SolveFront f = fronts[first + blockIdx.x];
-   for (int j = threadIdx.x; j < f.nelim; j += blockDim.x) {
+   const SolveFront f = fronts[first + blockIdx.x % count];
+   const int chunk = blockIdx.x / count, nchunk = gridDim.x / count;
+   for (int j = chunk * 256 + threadIdx.x; j < f.nelim; j += nchunk * 256) {
       int g = f.perm[j] - 1;
       for (int k = 0; k < nrhs; ++k) x[XI(g, k)] = ywork[XI(g, k)];
    }
@@ -172,13 +174,14 @@ k_fwd_flush(const SolveFront* fronts, int first, int nrhs, double* __restrict__ 
 /* ---- diagonal --------------------------------------------------------- */
 /* x <- D^-1 x on the eliminated variables; D^-1 is stored (2 per column,
  * second column of a 2x2 marked by +Inf), src/ssids/cpu/kernels/ldlt_app.cxx
- * ldlt_app_solve_diag :2553-2573. */
-__global__ void __launch_bounds__(128)
-k_diag_solve(const SolveFront* fronts, int first, int nrhs, double* __restrict__ x, int ldx) {
+ * ldlt_app_solve_diag :2553-2573.  Grid = fronts x column chunks. */
+__global__ void __launch_bounds__(256)
+k_diag_solve(const SolveFront* fronts, int first, int count, int nrhs, double* __restrict__ x, int ldx) {
    const int NR = nrhs;
-   const SolveFront f = fronts[first + blockIdx.x];
+   const SolveFront f = fronts[first + blockIdx.x % count];
    const double* d = f.D;
-   for (int j = threadIdx.x; j < f.nelim; j += blockDim.x) {
+   const int chunk = blockIdx.x / count, nchunk = gridDim.x / count;
+   for (int j = chunk * 256 + threadIdx.x; j < f.nelim; j += nchunk * 256) {
       double d11 = d[2 * j];
       if (isinf(d11)) continue;                 // handled by the first column of the pair
       int g1 = f.perm[j] - 1;
@@ -419,6 +422,7 @@ struct SolveDevCtx {
    __device__ __forceinline__ int tid() const { return threadIdx.x; }
    __device__ __forceinline__ void sync() { __syncthreads(); }
    __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+   __device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
    __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
 };
 
@@ -432,7 +436,7 @@ k_fwd_wide_T(const SolveFront* fronts, int first, int blk, const double* __restr
 }
 
 template <int NR>
-__global__ void __launch_bounds__(RT)
+__global__ void __launch_bounds__(SW_GT)
 k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork) {
    extern __shared__ double smem_dyn[];
    const RowTile w = work[blockIdx.x];
@@ -442,55 +446,237 @@ k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __r
 }
 
 template <int NR>
-__global__ void __launch_bounds__(RT)
-k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int step, const double* __restrict__ x, double* __restrict__ pbuf) {
+__global__ void __launch_bounds__(SW_GT)
+k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int first, int step, const double* __restrict__ x, double* __restrict__ pbuf) {
    extern __shared__ double smem_dyn[];
    const RowTile w = work[blockIdx.x];
    const SolveFront f = fronts[w.front];
    SolveDevCtx cx;
-   bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)blockIdx.x * SWB * NR, smem_dyn);
+   bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)(w.front - first) * SWB * NR, smem_dyn);
 }
 
 template <int NR, bool POSDEF>
 __global__ void __launch_bounds__(SW_TT)
-k_bwd_wide_T(const SolveFront* fronts, int first, const int* __restrict__ wbeg, int step,
-      double* __restrict__ x, const double* __restrict__ pbuf) {
+k_bwd_wide_T(const SolveFront* fronts, int first, int step, double* __restrict__ x, double* __restrict__ pbuf) {
    extern __shared__ double smem_dyn[];
    const int fi = first + blockIdx.x;
    const SolveFront f = fronts[fi];
    SolveDevCtx cx;
-   bwd_wide_T<NR, POSDEF>(cx, f, step, x, pbuf + (size_t)wbeg[fi] * SWB * NR, smem_dyn);
+   bwd_wide_T<NR, POSDEF>(cx, f, step, x, pbuf + (size_t)blockIdx.x * SWB * NR, smem_dyn);
 }
+
+/* ---- G kernels on the FP64 tensor cores (16 or 32 right-hand sides) ---------------------------------------- */
+/* A 128-row tile times the block's <= 256 columns: L is streamed through shared memory in chunks of 32 columns
+ * (two buffers; the next chunk travels global -> registers while the current one is multiplied), the right-hand
+ * sides of the block (forward) or of the tile's rows (backward) sit in shared memory for the whole tile.  Strides
+ * = 4 mod 16 doubles keep the 8 x 4 fragment loads bank-conflict free.  mma.sync.m8n8k4 with M = right-hand side. */
+constexpr int SG_LLD = RT + 4;
+template <int NR> constexpr int sg_xld() { return NR + 4; }
+template <int NR> constexpr size_t sg_f_smem_bytes() { return ((size_t)2 * 32 * SG_LLD + (size_t)SWB * sg_xld<NR>()) * sizeof(double); }
+template <int NR> constexpr size_t sg_b_smem_bytes() { return ((size_t)2 * 32 * SG_LLD + (size_t)RT * sg_xld<NR>()) * sizeof(double); }
+
+struct SgChunk { double2 v[8]; };
+/* chunk c of the tile: columns kb + 32 c .. + 31, rows r0 .. r0 + 127; rows outside [rlo, m) and columns >= kb + w read 0 */
+__device__ __forceinline__ void sg_load(SgChunk& ck, const SolveFront& f, int kb, int w, int r0, int rlo, int c, int tid) {
+   const int rr = (tid & 63) * 2, cq = tid >> 6;
+   const int r = r0 + rr;
+   const bool a0 = r >= rlo && r < f.m, a1 = r + 1 >= rlo && r + 1 < f.m;
+   const size_t ldl = (size_t)f.ldl;
+   #pragma unroll
+   for (int q = 0; q < 8; ++q) {
+      const int col = 32 * c + cq + 4 * q;
+      double2 v = make_double2(0.0, 0.0);
+      if (col < w && (a0 || a1)) {
+         const double* src = f.L + r + (size_t)(kb + col) * ldl;
+         if (a0 && a1) v = *reinterpret_cast<const double2*>(src);
+         else { if (a0) v.x = src[0]; if (a1) v.y = src[1]; }
+      }
+      ck.v[q] = v;
+   }
+}
+__device__ __forceinline__ void sg_store(const SgChunk& ck, double* Ls, int tid) {
+   const int rr = (tid & 63) * 2, cq = tid >> 6;
+   #pragma unroll
+   for (int q = 0; q < 8; ++q) *reinterpret_cast<double2*>(&Ls[(cq + 4 * q) * SG_LLD + rr]) = ck.v[q];
+}
+
+template <int NR>
+__global__ void __launch_bounds__(SW_GT)
+k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork) {
+   extern __shared__ __align__(16) double smem_dyn[];
+   const RowTile wk = work[blockIdx.x];
+   const SolveFront f = fronts[wk.front];
+   const int kb = blk * SWB;
+   if (kb >= f.nelim) return;
+   const int w = min(SWB, f.nelim - kb);
+   const int r0 = wk.tile * RT;
+   if (r0 + RT <= kb + w || r0 >= f.m) return;
+   constexpr int YLD = sg_xld<NR>();
+   double* Ls = smem_dyn;
+   double* ys = smem_dyn + 2 * 32 * SG_LLD;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int nchunk = (w + 31) / 32;
+   for (int e = tid; e < nchunk * 32; e += SW_GT) {
+      const int g = (e < w) ? f.perm[kb + e] - 1 : -1;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) ys[e * YLD + k] = (g >= 0) ? ywork[XI(g, k)] : 0.0;
+   }
+   SgChunk ck;
+   sg_load(ck, f, kb, w, r0, kb + w, 0, tid);
+   sg_store(ck, Ls, tid);
+   __syncthreads();
+   const int rbase = warp * 16;
+   double acc[NR / 8][2][2];
+   #pragma unroll
+   for (int j = 0; j < NR / 8; ++j)
+      #pragma unroll
+      for (int i = 0; i < 2; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
+   for (int c = 0; c < nchunk; ++c) {
+      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, kb + w, c + 1, tid);
+      const double* Lc = Ls + (c & 1) * 32 * SG_LLD;
+      #pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+         double bfr[2], afr[NR / 8];
+         #pragma unroll
+         for (int i = 0; i < 2; ++i) bfr[i] = Lc[(kk + (lane & 3)) * SG_LLD + rbase + i * 8 + (lane >> 2)];
+         #pragma unroll
+         for (int j = 0; j < NR / 8; ++j) afr[j] = ys[(32 * c + kk + (lane & 3)) * YLD + j * 8 + (lane >> 2)];
+         #pragma unroll
+         for (int j = 0; j < NR / 8; ++j)
+            #pragma unroll
+            for (int i = 0; i < 2; ++i) pv_dmma(acc[j][i][0], acc[j][i][1], afr[j], bfr[i]);
+      }
+      if (c + 1 < nchunk) sg_store(ck, Ls + ((c + 1) & 1) * 32 * SG_LLD, tid);
+      __syncthreads();
+   }
+   /* acc[j][i][e] = sum for right-hand side 8 j + lane / 4 and row rbase + 8 i + 2 (lane % 4) + e */
+   #pragma unroll
+   for (int i = 0; i < 2; ++i)
+      #pragma unroll
+      for (int e = 0; e < 2; ++e) {
+         const int r = r0 + rbase + i * 8 + 2 * (lane & 3) + e;
+         if (r >= kb + w && r < f.m) {
+            const int g = row_index(f, r);
+            #pragma unroll
+            for (int j = 0; j < NR / 8; ++j) atomicAdd(&x[XI(g, j * 8 + (lane >> 2))], -acc[j][i][e]);
+         }
+      }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(SW_GT)
+k_bwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int first, int step, const double* __restrict__ x,
+      double* __restrict__ pbuf) {
+   extern __shared__ __align__(16) double smem_dyn[];
+   const RowTile wk = work[blockIdx.x];
+   const SolveFront f = fronts[wk.front];
+   const int b = sw_bwd_block(f, step);
+   if (b < 0) return;
+   const int kb = b * SWB;
+   const int w = min(SWB, f.nelim - kb);
+   const int r0 = wk.tile * RT;
+   if (r0 + RT <= kb + w || r0 >= f.m) return;
+   constexpr int XLD = sg_xld<NR>();
+   double* Ls = smem_dyn;
+   double* xs = smem_dyn + 2 * 32 * SG_LLD;
+   double* accb = pbuf + (size_t)(wk.front - first) * SWB * NR;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int nchunk = (w + 31) / 32;
+   for (int e = tid; e < RT; e += SW_GT) {
+      const int r = r0 + e;
+      const bool act = r >= kb + w && r < f.m;
+      const int g = act ? row_index(f, r) : 0;
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) xs[e * XLD + k] = act ? x[XI(g, k)] : 0.0;
+   }
+   SgChunk ck;
+   sg_load(ck, f, kb, w, r0, kb + w, 0, tid);
+   sg_store(ck, Ls, tid);
+   __syncthreads();
+   constexpr int NB = NR / 16;               // 8 x 8 output blocks per warp and chunk: (NR / 8 right-hand-side groups) x 4 column groups / 8 warps
+   for (int c = 0; c < nchunk; ++c) {
+      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, kb + w, c + 1, tid);
+      const double* Lc = Ls + (c & 1) * 32 * SG_LLD;
+      double acc[NB][2];
+      int jg[NB], cg[NB];
+      #pragma unroll
+      for (int u = 0; u < NB; ++u) { acc[u][0] = 0.0; acc[u][1] = 0.0; const int bid = warp + 8 * u; jg[u] = bid % (NR / 8); cg[u] = bid / (NR / 8); }
+      #pragma unroll 8
+      for (int kk = 0; kk < RT; kk += 4) {
+         #pragma unroll
+         for (int u = 0; u < NB; ++u) {
+            const double afr = xs[(kk + (lane & 3)) * XLD + 8 * jg[u] + (lane >> 2)];
+            const double bfr = Lc[(8 * cg[u] + (lane >> 2)) * SG_LLD + kk + (lane & 3)];
+            pv_dmma(acc[u][0], acc[u][1], afr, bfr);
+         }
+      }
+      /* acc[u][e]: right-hand side 8 jg + lane / 4, column 32 c + 8 cg + 2 (lane % 4) + e of the block */
+      #pragma unroll
+      for (int u = 0; u < NB; ++u)
+         #pragma unroll
+         for (int e = 0; e < 2; ++e) {
+            const int col = 32 * c + 8 * cg[u] + 2 * (lane & 3) + e;
+            if (col < w) atomicAdd(&accb[(size_t)col * NR + 8 * jg[u] + (lane >> 2)], acc[u][e]);
+         }
+      if (c + 1 < nchunk) sg_store(ck, Ls + ((c + 1) & 1) * 32 * SG_LLD, tid);
+      __syncthreads();
+   }
+}
+
+template <int NR> struct UseMma { static constexpr bool value = (NR >= 16); };
 
 template <int NR, bool POSDEF>
 void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork, int nblk,
       double* x, double* ywork, cudaStream_t s) {
    static bool configured = false;
-   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double), smG = sw_fG_smem_doubles<NR>() * sizeof(double);
-   if (!configured) {
-      cudaFuncSetAttribute(k_fwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
-      cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
-      configured = true;
-   }
-   for (int b = 0; b < nblk; ++b) {
-      k_fwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, b, x, ywork); COUNT_LAUNCH();
-      k_fwd_wide_G<NR><<<nwork, RT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
+   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double);
+   if constexpr (UseMma<NR>::value) {
+      const size_t smG = sg_f_smem_bytes<NR>();
+      if (!configured) {
+         cudaFuncSetAttribute(k_fwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+         cudaFuncSetAttribute(k_fwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+         configured = true;
+      }
+      for (int b = 0; b < nblk; ++b) {
+         k_fwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, b, x, ywork); COUNT_LAUNCH();
+         k_fwd_wide_G_mma<NR><<<nwork, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
+      }
+   } else {
+      const size_t smG = sw_fG_smem_doubles<NR>() * sizeof(double);
+      if (!configured) {
+         cudaFuncSetAttribute(k_fwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+         cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+         configured = true;
+      }
+      for (int b = 0; b < nblk; ++b) {
+         k_fwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, b, x, ywork); COUNT_LAUNCH();
+         k_fwd_wide_G<NR><<<nwork, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
+      }
    }
 }
 
+/* pbuf: one SWB x NR accumulator per front of the level, all zero when the sweep of the level starts (the T kernel
+ * clears what it consumed) */
 template <int NR, bool POSDEF>
 void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
       const int* wbeg, int nblk, double* x, double* pbuf, cudaStream_t s) {
    static bool configured = false;
-   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double), smG = sw_bG_smem_doubles<NR>() * sizeof(double);
+   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double);
    if (!configured) {
       cudaFuncSetAttribute(k_bwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
-      cudaFuncSetAttribute(k_bwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+      if constexpr (UseMma<NR>::value)
+         cudaFuncSetAttribute(k_bwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_b_smem_bytes<NR>());
       configured = true;
    }
+   cudaMemsetAsync(pbuf, 0, (size_t)count * SWB * NR * sizeof(double), s);
    for (int st = 0; st < nblk; ++st) {
-      k_bwd_wide_G<NR><<<nwork, RT, smG, s>>>(fronts, work, st, x, pbuf); COUNT_LAUNCH();
-      k_bwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, wbeg, st, x, pbuf); COUNT_LAUNCH();
+      if constexpr (UseMma<NR>::value) {
+         k_bwd_wide_G_mma<NR><<<nwork, SW_GT, sg_b_smem_bytes<NR>(), s>>>(fronts, work, first, st, x, pbuf);
+      } else {
+         k_bwd_wide_G<NR><<<nwork, SW_GT, 0, s>>>(fronts, work, first, st, x, pbuf);
+      }
+      COUNT_LAUNCH();
+      k_bwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, st, x, pbuf); COUNT_LAUNCH();
    }
 }
 
@@ -560,13 +746,14 @@ void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, 
 void launch_fwd_flush(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
       const double* ywork, cudaStream_t s) {
    if (count == 0) return;
-   k_fwd_flush<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx, ywork); COUNT_LAUNCH();
+   k_fwd_flush<<<count * 8, 256, 0, s>>>(fronts, first, count, nrhs, x, ldx, ywork); COUNT_LAUNCH();
 }
 
 void launch_diag_solve(const SolveFront* fronts, int first, int count, int nrhs, double* x, int ldx,
       cudaStream_t s) {
    if (count == 0) return;
-   k_diag_solve<<<count, 128, 0, s>>>(fronts, first, nrhs, x, ldx); COUNT_LAUNCH();
+   const int nchunk = count <= 64 ? 16 : 2;
+   k_diag_solve<<<count * nchunk, 256, 0, s>>>(fronts, first, count, nrhs, x, ldx); COUNT_LAUNCH();
 }
 
 void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,

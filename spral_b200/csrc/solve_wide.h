@@ -1,6 +1,5 @@
-/* "Wide" triangular sweeps for the large fronts at the top of the tree (opt-in,
- * SPRAL_B200_SOLVE_WIDE=1): the column blocks that need a device-wide
- * synchronisation are SWB = 256 columns wide instead of 32.
+/* "Wide" triangular sweeps (default; SPRAL_B200_SOLVE_WIDE=0 selects the 32-column kernels): the
+ * column blocks that need a device-wide synchronisation are SWB = 256 columns wide instead of 32.
  *
  * The level kernels of solve_kernels.cu advance all fronts of a level 32 columns
  * per launch (or per grid barrier); a front with 16 000 eliminated columns needs
@@ -12,10 +11,12 @@
  *                registers (prefetched one sub-step ahead), the rows of the
  *                sub-block publish the 32 x 32 diagonal block to shared memory;
  *             G: all (front, row-tile) CTAs subtract L(rows below, block) * y.
- *   backward  G: partial L(rows below, block)^T x per row tile; T: ONE CTA per
- *                front sums the partials in a fixed order and solves the
- *                transposed triangle, sub-blocks last to first, every thread
- *                owning a column.
+ *   backward  G: L(rows below, block)^T x per row tile, added (atomics) into one
+ *                256 x nrhs accumulator per front; T: ONE CTA per front takes the
+ *                accumulator (and clears it), solves the transposed triangle,
+ *                sub-blocks last to first, every thread owning a column.
+ * The G kernels are the bandwidth part (they read all of L below the diagonal blocks once per
+ * sweep): 256 threads per 128-row tile, >= 16 independent loads in flight per thread.
  * Same mathematics and data as the 32-column kernels (NumericSubtree.hxx:286-418
  * of the reference CPU engine: gather, trsv/trsm + gemv/gemm, scatter); sums are
  * taken over up to 256 terms before they are applied, so results differ from the
@@ -56,10 +57,11 @@ SW_FN int sw_row_index(const SolveFront& f, int i) {
  * aligned and the broadcast reads of another row's values vectorise */
 template <int NR> constexpr int sw_xld() { return NR == 1 ? 1 : NR + 2; }
 template <int NR> constexpr size_t sw_T_smem_doubles() { return (size_t)SWB * sw_xld<NR>() + (size_t)SSB * SW_LK; }
-/* forward G: ys [SWB * NR] doubles */
-template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)SWB * NR; }
-/* backward G: tile [RT * SW_LK] + xr [RT * NR] doubles */
-template <int NR> constexpr size_t sw_bG_smem_doubles() { return (size_t)RT * SW_LK + (size_t)RT * sw_xld<NR>(); }
+constexpr int SW_GT = 256;   // threads of a G kernel CTA
+/* forward G: ys [SWB * NR] + the partial sums of the second column half [RT * NR] doubles */
+template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)SWB * NR + (size_t)RT * NR; }
+/* backward G: nothing (registers and shuffles only) */
+template <int NR> constexpr size_t sw_bG_smem_doubles() { return 1; }
 
 /* ---- forward, T: y(block) = L(block, block)^-1 x(block); y -> ywork ---------------- */
 template <int NR, bool POSDEF, class Ctx>
@@ -140,6 +142,8 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
 }
 
 /* ---- forward, G: x(rows below the block) -= L(rows, block) * y --------------------- */
+/* SW_GT = 256 threads: thread (row r0 + (t & 127), half h = t >> 7) sums the columns [128 h, 128 h + 128) of its row,
+ * 16 or 32 independent loads at a time; the halves meet in shared memory. */
 template <int NR, class Ctx>
 SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, double* x, const double* ywork, double* smem) {
    const int kb = blk * SWB;
@@ -148,27 +152,47 @@ SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, double* x
    const int r0 = tile * RT;
    if (r0 + RT <= kb + w || r0 >= f.m) return;
    double* ys = smem;
-   for (int e = cx.tid(); e < w; e += RT) {
+   double* part = smem + (size_t)SWB * NR;
+   const int t = cx.tid();
+   for (int e = t; e < w; e += SW_GT) {
       const int g = f.perm[kb + e] - 1;
       #pragma unroll
       for (int k = 0; k < NR; ++k) ys[(size_t)e * NR + k] = ywork[SW_XI(g, k)];
    }
    cx.sync();
-   const int r = r0 + cx.tid();
-   if (r >= kb + w && r < f.m) {
-      double acc[NR];
-      #pragma unroll
-      for (int k = 0; k < NR; ++k) acc[k] = 0.0;
-      const double* Lr = f.L + r + (size_t)kb * (size_t)f.ldl;
-      for (int j = 0; j < w; ++j) {
-         const double l = Lr[(size_t)j * (size_t)f.ldl];
+   const int rl = t & (RT - 1), h = t / RT;
+   const int r = r0 + rl;
+   const bool active = r >= kb + w && r < f.m;
+   double acc[NR];
+   #pragma unroll
+   for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+   if (active) {
+      const size_t ldl = (size_t)f.ldl;
+      const double* Lr = f.L + r + (size_t)kb * ldl;
+      const int jend = sw_min(w, h * (SWB / 2) + SWB / 2);
+      constexpr int NL = (NR <= 2) ? 32 : 16;      // independent loads in flight per thread
+      for (int j0 = h * (SWB / 2); j0 < jend; j0 += NL) {
+         double l[NL];
          #pragma unroll
-         for (int k = 0; k < NR; ++k) acc[k] += l * ys[(size_t)j * NR + k];
+         for (int q = 0; q < NL; ++q) l[q] = (j0 + q < jend) ? Lr[(size_t)(j0 + q) * ldl] : 0.0;
+         #pragma unroll
+         for (int q = 0; q < NL; ++q) {
+            const int j = (j0 + q < jend) ? j0 + q : j0;
+            #pragma unroll
+            for (int k = 0; k < NR; ++k) acc[k] += l[q] * ys[(size_t)j * NR + k];
+         }
       }
+   }
+   if (h == 1) {
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) part[(size_t)rl * NR + k] = acc[k];
+   }
+   cx.sync();
+   if (h == 0 && active) {
       const int g = sw_row_index(f, r);
       /* rows < nelim are touched by this thread only, rows >= nelim are shared with sibling fronts */
       #pragma unroll
-      for (int k = 0; k < NR; ++k) cx.atomic_add(&x[SW_XI(g, k)], -acc[k]);
+      for (int k = 0; k < NR; ++k) cx.atomic_add(&x[SW_XI(g, k)], -(acc[k] + part[(size_t)rl * NR + k]));
    }
 }
 
@@ -178,59 +202,61 @@ SW_FN int sw_bwd_block(const SolveFront& f, int step) {
    return nblk - 1 - step;
 }
 
-/* ---- backward, G: out(j, k) = sum over the tile's rows r below the block of L(r, kb+j) x(r, k) ---- */
+/* ---- backward, G: acc(j, k) += sum over the tile's rows r below the block of L(r, kb+j) x(r, k) ---- */
+/* SW_GT = 256 threads = 8 warps; warp v owns the columns [32 v, 32 v + 32) of the block, lane l the rows r0 + l + 32 q
+ * (q < 4) of the tile: every load is a coalesced 256-byte row segment of one column, 4 x CG of them in flight per
+ * thread.  The lane sums of CG columns are reduced with shuffles and added to the front's accumulator `acc`
+ * (SWB x NR doubles, zero when the step starts; several tiles add into it: atomics). */
 template <int NR, class Ctx>
-SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const double* x, double* out, double* smem) {
+SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const double* x, double* acc, double* /*smem*/) {
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
    const int kb = b * SWB;
    const int w = sw_min(SWB, f.nelim - kb);
    const int r0 = tileidx * RT;
    if (r0 + RT <= kb + w || r0 >= f.m) return;      // no row of this tile below the block
-   double* tile = smem;                             // [RT][SW_LK]; re-used for the cross-warp reduction
-   constexpr int XLD = sw_xld<NR>();
-   double* xr = smem + (size_t)RT * SW_LK;          // [RT][XLD]
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
-   const int r = r0 + t;
-   const bool active = (r >= kb + w) && (r < f.m);
    const size_t ldl = (size_t)f.ldl;
-   {
-      const int g = active ? sw_row_index(f, r) : 0;
+   double xv[4][NR];
+   bool act[4];
+   #pragma unroll
+   for (int q = 0; q < 4; ++q) {
+      const int r = r0 + lane + 32 * q;
+      act[q] = r >= kb + w && r < f.m;
+      const int g = act[q] ? sw_row_index(f, r) : 0;
       #pragma unroll
-      for (int k = 0; k < NR; ++k) xr[(size_t)t * XLD + k] = active ? x[SW_XI(g, k)] : 0.0;
+      for (int k = 0; k < NR; ++k) xv[q][k] = act[q] ? x[SW_XI(g, k)] : 0.0;
    }
-   for (int jb = 0; jb < w; jb += SSB) {
-      const int wd = sw_min(SSB, w - jb);
-      const double* Lr = f.L + r + (size_t)(kb + jb) * ldl;
-      for (int j = 0; j < SSB; ++j) tile[(size_t)t * SW_LK + j] = (active && j < wd) ? Lr[(size_t)j * ldl] : 0.0;
-      cx.sync();
-      double acc[NR];
+   constexpr int CG = (NR <= 2) ? 8 : 4;           // columns per batch: CG * NR running sums per thread
+   const int c0 = warp * 32;
+   for (int cb = 0; cb < 32 && c0 + cb < w; cb += CG) {
+      double l[CG][4];
       #pragma unroll
-      for (int k = 0; k < NR; ++k) acc[k] = 0.0;
-      for (int i = 0; i < 32; ++i) {
-         const double l = tile[(size_t)(warp * 32 + i) * SW_LK + lane];
+      for (int c = 0; c < CG; ++c) {
+         const bool cin = c0 + cb + c < w;
+         const double* Lc = f.L + (size_t)r0 + lane + (size_t)(kb + c0 + cb + (cin ? c : 0)) * ldl;
          #pragma unroll
-         for (int k = 0; k < NR; ++k) acc[k] += l * xr[(size_t)(warp * 32 + i) * XLD + k];
+         for (int q = 0; q < 4; ++q) l[c][q] = (cin && act[q]) ? Lc[32 * q] : 0.0;
       }
-      cx.sync();
       #pragma unroll
-      for (int k = 0; k < NR; ++k) tile[(size_t)t * SW_LK + k] = acc[k];       // NR <= 32 < SW_LK
-      cx.sync();
-      if (t < SSB) {
+      for (int c = 0; c < CG; ++c) {
          #pragma unroll
          for (int k = 0; k < NR; ++k) {
-            double s = 0.0;
-            for (int q = 0; q < RT / 32; ++q) s += tile[(size_t)(q * 32 + t) * SW_LK + k];
-            out[(size_t)(jb + t) * NR + k] = s;
+            double sum = 0.0;
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) sum += l[c][q] * xv[q][k];
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += cx.shfl_xor(sum, off);
+            /* every lane holds the total; lane (c NR + k) mod 32 adds it */
+            if (lane == ((c * NR + k) & 31) && c0 + cb + c < w) cx.atomic_add(&acc[(size_t)(c0 + cb + c) * NR + k], sum);
          }
       }
-      cx.sync();
    }
 }
 
-/* ---- backward, T: x(block) = L(block, block)^-T (x(block) - sum of the partials) ---- */
+/* ---- backward, T: x(block) = L(block, block)^-T (x(block) - accumulator); the accumulator is cleared ---- */
 template <int NR, bool POSDEF, class Ctx>
-SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const double* pb, double* smem) {
+SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double* pb, double* smem) {
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
    constexpr int XLD = sw_xld<NR>();
@@ -241,15 +267,11 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, const d
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
    const bool acol = t < w;
    const int g = acol ? f.perm[kb + t] - 1 : -1;
-   const int ntile = (f.m + RT - 1) / RT;
-   const int t0 = (kb + w) / RT;                    // first tile that holds a row below the block
    #pragma unroll
    for (int k = 0; k < NR; ++k) {
       double v = 0.0;
-      if (acol) {
-         v = x[SW_XI(g, k)];
-         for (int tt = t0; tt < ntile; ++tt) v -= pb[(size_t)tt * SWB * NR + (size_t)t * NR + k];
-      }
+      if (acol) v = x[SW_XI(g, k)] - pb[(size_t)t * NR + k];      // pb: what the G kernel accumulated for this block
+      pb[(size_t)t * NR + k] = 0.0;                                // ... cleared for the next step
       vs[(size_t)t * XLD + k] = v;
    }
    const size_t ldl = (size_t)f.ldl;

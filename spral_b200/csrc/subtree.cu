@@ -1275,7 +1275,9 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
       if (job == JOB_FWD) S.b_y.ensure(chunk_bytes, s);
       /* levels swept 256 columns at a time (solve_wide.h) */
       auto wide_level = [&](int lev, int nr) {
-         if (!g_solve_wide || N.lvl_steps[lev] < g_solve_wide_min) return false;
+         /* with 16+ right-hand sides the wide kernels (FP64 tensor cores) win on every level; with few, the levels of
+          * small fronts are better off with the 32-column kernels (measured on cfg5: 15.3 vs 16.6 ms, 84 vs 93 ms) */
+         if (!g_solve_wide || N.lvl_steps[lev] < (nr >= 16 ? 1 : g_solve_wide_min)) return false;
          size_t nwork = (size_t)(N.swork_ptr[lev + 1] - N.swork_ptr[lev]);
          return nwork * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
       };

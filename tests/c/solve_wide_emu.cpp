@@ -63,7 +63,7 @@ static double run_case(const Case& c, std::mt19937_64& rng) {
          emu::run_cta(SW_TT, [&](emu::Ctx& cx) { fwd_wide_T<NR, POSDEF>(cx, f, b, x.data(), ywork.data(), smT.data()); });
          for (int t = 0; t < ntile + 1; ++t) {
             std::fill(smG.begin(), smG.end(), std::nan(""));
-            emu::run_cta(RT, [&](emu::Ctx& cx) { fwd_wide_G<NR>(cx, f, t, b, x.data(), ywork.data(), smG.data()); });
+            emu::run_cta(SW_GT, [&](emu::Ctx& cx) { fwd_wide_G<NR>(cx, f, t, b, x.data(), ywork.data(), smG.data()); });
          }
       }
       for (int j = 0; j < nelim; ++j)                                   // k_fwd_flush
@@ -85,13 +85,13 @@ static double run_case(const Case& c, std::mt19937_64& rng) {
             xr[(size_t)idx(j) * NR + k] = s;
          }
       std::vector<double> x = x0;
-      std::vector<double> pbuf((size_t)(ntile + 1) * SWB * NR, std::nan(""));
+      std::vector<double> pbuf((size_t)SWB * NR, 0.0);                  // the front's accumulator: zero when the sweep starts
       std::vector<double> smT(sw_T_smem_doubles<NR>()), smG(sw_bG_smem_doubles<NR>());
       for (int st = 0; st < nblk + 1; ++st) {
          for (int t = 0; t < ntile + 1; ++t) {
             std::fill(smG.begin(), smG.end(), std::nan(""));
-            emu::run_cta(RT, [&](emu::Ctx& cx) {
-               bwd_wide_G<NR>(cx, f, t, st, x.data(), pbuf.data() + (size_t)t * SWB * NR, smG.data()); });
+            emu::run_cta(SW_GT, [&](emu::Ctx& cx) {
+               bwd_wide_G<NR>(cx, f, t, st, x.data(), pbuf.data(), smG.data()); });
          }
          std::fill(smT.begin(), smT.end(), std::nan(""));
          emu::run_cta(SW_TT, [&](emu::Ctx& cx) { bwd_wide_T<NR, POSDEF>(cx, f, st, x.data(), pbuf.data(), smT.data()); });
