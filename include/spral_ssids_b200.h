@@ -247,6 +247,12 @@ struct spral_ssids_b200_analysis* spral_ssids_b200_analyse(
       int* flag);
 void spral_ssids_b200_analysis_free(struct spral_ssids_b200_analysis*);
 
+/* Replaces the subtree partition (akeep%part, exec_loc, contrib_ptr / contrib_idx / contrib_dest of anal.F90:418-454)
+ * by a caller-chosen one: part[0..nparts] = 1-based first nodes (part[nparts] = nnodes + 1), every part connected and
+ * with its last node as only exit.  Returns 0, -1 if invalid. */
+int spral_ssids_b200_analysis_set_partition(struct spral_ssids_b200_analysis*, int nparts, const int* part,
+      const int* exec_loc);
+
 /* Accessors (pointers stay owned by the analysis object). */
 struct spral_ssids_b200_analysis_view {
    int n, nnodes, nparts;

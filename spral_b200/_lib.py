@@ -98,6 +98,7 @@ SYMBOLS = {
         (_vp, [_i, _vp, _vp, _vp, _i, _i, C.c_int64, C.c_float, C.c_float, _ip]),
     "spral_ssids_b200_analysis_free": (None, [_vp]),
     "spral_ssids_b200_analysis_get": (None, [_vp, C.POINTER(AnalysisView)]),
+    "spral_ssids_b200_analysis_set_partition": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "spral_ssids_b200_hungarian_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _ip]),
     "spral_ssids_b200_equilib_scale_sym": (_i, [_i, _vp, _vp, _vp, _vp, _i, _d, _ip]),
     "spral_ssids_b200_match_order_metis": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),

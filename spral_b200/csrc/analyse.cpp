@@ -619,6 +619,41 @@ struct spral_ssids_b200_analysis {
    bool gpu_only = false;
 };
 
+/* contrib_ptr / contrib_idx / contrib_dest of a partition (the tail of find_subtree_partition, anal.F90:418-454):
+ * part p sends its root contribution to slot contrib_idx(p) of the part that holds the parent of its last node.
+ * part / exec_loc are 1-based work arrays (part[1..nparts+1], exec_loc[1..nparts]). */
+static void store_partition(spral_ssids_b200_analysis& A, int nparts, const vec<int>& part, const vec<int>& exec_loc,
+                            const vec<int>& sparent) {
+   const int nnodes = A.nnodes;
+   vec<int> contrib_ptr(nparts + 4, 0), contrib_idx(nparts + 1, 0), contrib_dest(nparts + 1, 0);
+   for (int i = 1; i <= nparts - 1; ++i) {
+      int jn = sparent[part[i + 1] - 1];
+      if (jn > nnodes) continue;
+      int kp = i + 1;
+      while (jn >= part[kp + 1]) kp++;
+      contrib_ptr[kp + 2]++;
+   }
+   contrib_ptr[1] = 1; contrib_ptr[2] = 1;
+   for (int i = 1; i <= nparts; ++i) contrib_ptr[i + 2] = contrib_ptr[i + 1] + contrib_ptr[i + 2];
+   for (int i = 1; i <= nparts - 1; ++i) {
+      int jn = sparent[part[i + 1] - 1];
+      if (jn > nnodes) { contrib_idx[i] = nparts + 1; continue; }
+      int kp = i + 1;
+      while (jn >= part[kp + 1]) kp++;
+      contrib_idx[i] = contrib_ptr[kp + 1];
+      contrib_dest[contrib_idx[i]] = jn;
+      contrib_ptr[kp + 1]++;
+   }
+   contrib_idx[nparts] = nparts + 1;
+
+   A.nparts = nparts;
+   A.part.assign(part.begin() + 1, part.begin() + nparts + 2);
+   A.exec_loc.assign(exec_loc.begin() + 1, exec_loc.begin() + nparts + 1);
+   A.contrib_ptr.assign(contrib_ptr.begin() + 1, contrib_ptr.begin() + nparts + 4);
+   A.contrib_idx.assign(contrib_idx.begin() + 1, contrib_idx.begin() + nparts + 1);
+   A.contrib_dest.assign(contrib_dest.begin() + 1, contrib_dest.begin() + nparts + 1);
+}
+
 /* ---- src/ssids/anal.F90:289-464 find_subtree_partition ---- */
 static void find_subtree_partition(spral_ssids_b200_analysis& A, const vec<int>& sptr,
                                    const vec<int>& sparent, const vec<i64>& rptr,
@@ -684,34 +719,9 @@ static void find_subtree_partition(spral_ssids_b200_analysis& A, const vec<int>&
    part[j + 1] = part[nparts + 1];
    nparts = j;
 
-   vec<int> contrib_ptr(nparts + 4, 0), contrib_idx(nparts + 1, 0), contrib_dest(nparts + 1, 0);
-   for (int i = 1; i <= nparts - 1; ++i) {
-      int jn = sparent[part[i + 1] - 1];
-      if (jn > nnodes) continue;
-      int kp = i + 1;
-      while (jn >= part[kp + 1]) kp++;
-      contrib_ptr[kp + 2]++;
-   }
-   contrib_ptr[1] = 1; contrib_ptr[2] = 1;
-   for (int i = 1; i <= nparts; ++i) contrib_ptr[i + 2] = contrib_ptr[i + 1] + contrib_ptr[i + 2];
-   for (int i = 1; i <= nparts - 1; ++i) {
-      int jn = sparent[part[i + 1] - 1];
-      if (jn > nnodes) { contrib_idx[i] = nparts + 1; continue; }
-      int kp = i + 1;
-      while (jn >= part[kp + 1]) kp++;
-      contrib_idx[i] = contrib_ptr[kp + 1];
-      contrib_dest[contrib_idx[i]] = jn;
-      contrib_ptr[kp + 1]++;
-   }
-   contrib_idx[nparts] = nparts + 1;
-
-   A.nparts = nparts;
-   A.part.assign(part.begin() + 1, part.begin() + nparts + 2);
-   A.exec_loc.assign(exec_loc.begin() + 1, exec_loc.begin() + nparts + 1);
-   A.contrib_ptr.assign(contrib_ptr.begin() + 1, contrib_ptr.begin() + nparts + 4);
-   A.contrib_idx.assign(contrib_idx.begin() + 1, contrib_idx.begin() + nparts + 1);
-   A.contrib_dest.assign(contrib_dest.begin() + 1, contrib_dest.begin() + nparts + 1);
+   store_partition(A, nparts, part, exec_loc, sparent);
 }
+
 
 extern "C" {
 
@@ -836,6 +846,27 @@ struct spral_ssids_b200_analysis* spral_ssids_b200_analyse(
 }
 
 void spral_ssids_b200_analysis_free(struct spral_ssids_b200_analysis* A) { delete A; }
+
+/* Replaces the subtree partition of an analysis (one-process-per-GPU driver: proportional mapping of the top of the
+ * tree, spral_b200/dist.py).  part[0..nparts] are 1-based first nodes (part[0] = 1, part[nparts] = nnodes + 1),
+ * exec_loc[0..nparts-1] the reference's location codes.  A part must be connected with a single exit: only its last
+ * node may have its parent outside.  Returns 0, or -1 when the partition is not valid (the analysis is unchanged). */
+int spral_ssids_b200_analysis_set_partition(struct spral_ssids_b200_analysis* A, int nparts, const int* part_in,
+      const int* exec_loc_in) {
+   if (!A || nparts < 1 || part_in[0] != 1 || part_in[nparts] != A->nnodes + 1) return -1;
+   const int nnodes = A->nnodes;
+   vec<int> sparent(nnodes + 2, 0), part(nparts + 3, 0), exec_loc(nparts + 2, 0);
+   for (int i = 1; i <= nnodes; ++i) sparent[i] = A->sparent[i - 1];
+   for (int p = 1; p <= nparts; ++p) {
+      part[p] = part_in[p - 1]; exec_loc[p] = exec_loc_in[p - 1];
+      if (part_in[p] <= part_in[p - 1]) return -1;
+      for (int i = part_in[p - 1]; i < part_in[p] - 1; ++i)              /* all but the last node stay inside */
+         if (sparent[i] >= part_in[p] || sparent[i] < part_in[p - 1]) return -1;
+   }
+   part[nparts + 1] = part_in[nparts];
+   store_partition(*A, nparts, part, exec_loc, sparent);
+   return 0;
+}
 
 void spral_ssids_b200_analysis_get(const struct spral_ssids_b200_analysis* A,
                                    struct spral_ssids_b200_analysis_view* v) {

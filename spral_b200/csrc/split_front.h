@@ -2,10 +2,12 @@
  * the open panel and the next one, a helper GPU of the same box holds a mirror of the columns further right
  * and applies every trailing update to them.
  *
- * STATUS: compiled only with -DSPRAL_B200_SPLIT (the default build does not contain a line of it) and NOT
- * YET RUN ON GPUS.  The protocol it implements is the one tests/c/dist_front_emu.cpp model-checks (no
- * deadlock, no unordered conflicting accesses, complete updates), in its host-driven form: no kernel ever
- * spins.  The two processes talk through a POSIX shared-memory segment; a flag is raised from a
+ * STATUS: part of the default build, switched on at run time (SPRAL_B200_SPLIT=1, spral_b200/dist.py); runs on
+ * B200s (round 2: cfg5 on 2 GPUs, inertia / delays / backward error equal to the unsplit run).  The far blocks are
+ * dealt round robin over the WORKERS = the owner itself (its blocks stay in its own front and are updated by its
+ * look-ahead bulk stream, as without a split) and the helpers.  The protocol is the one tests/c/dist_front_emu.cpp
+ * model-checks (no deadlock, no unordered conflicting accesses, complete updates), in its host-driven form: no
+ * kernel ever spins.  The two processes talk through a POSIX shared-memory segment; a flag is raised from a
  * cudaLaunchHostFunc callback behind the copy / update it announces and polled by the other host with a
  * time-out.
  *
@@ -38,7 +40,9 @@ struct SplitShm {
                                          // the helper answers 3 -> 0 when it has released the mirror), 4 exit (owner)
    std::atomic<int> error;               // raised by either side: the other gives up
    int m, n, ldl, ld_is_l;               // geometry of the front; ld_is_l: positive definite (L*D == L)
-   int nhelpers, helper_index;           // the far blocks are dealt round robin: block J >= 2 lives on helper (J - 2) % nhelpers
+   int nhelpers, helper_index;           // helpers of this front and this helper's number
+   int nworkers, worker_index;           // the far blocks are dealt round robin over the workers: block J >= 2 belongs to worker
+                                         // (J - 2) % nworkers; worker 0 is the owner itself when it takes a share
    int base;                             // first column of block 0 (a multiple of the update tile): 0, or where the split was re-started
    unsigned char h_L[64], h_LD[64];      // IPC handles of the helper's mirror
    std::atomic<int> ready[SPLIT_MAXP + 4];   // panel k is in the mirror (1) / the split ends here (SPLIT_DRAIN)
@@ -97,14 +101,20 @@ struct SplitOwner {
    bool restart = true;                  // SPRAL_B200_SPLIT_RESTART=0: a drained split stays off for the rest of the front
    bool trace = getenv("SPRAL_B200_TRACE") != nullptr;
    int n_pushed = 0, n_pulled = 0;
+   double t_wait_ms = 0, t_push_ms = 0, t_begin_ms = 0, t_drain_ms = 0;   // host time: waiting for blocks, enqueuing pushes, set-up, drains
    const Front* f = nullptr;             // host copy of its descriptor (owner's pointers)
    int base = 0;                         // block j = columns [base + j PW, base + (j + 1) PW): tile aligned, so that what the
                                          // owner's urgent update touches (whole tile columns) ends where the helpers' columns begin
    int p_first = 0;                      // first column of panel 0 of this split (== base unless re-started off a tile boundary)
+   bool owner_share = true;              // SPRAL_B200_SPLIT_OWNER_SHARE=0: every far block goes to a helper
    int blk(int j) const { return split_block(base, j); }
    int H() const { return (int)links.size(); }
-   Link& link_of(int J) { return links[(J - 2) % H()]; }
-   std::vector<std::pair<std::vector<unsigned char>, void*>> opened;
+   int nworkers() const { return H() + (owner_share ? 1 : 0); }
+   int worker_of(int J) const { return (J - 2) % nworkers(); }
+   bool is_local(int J) const { return owner_share && worker_of(J) == 0; }     // stays in the owner's front
+   Link& link_of(int J) { return links[worker_of(J) - (owner_share ? 1 : 0)]; }
+   /* block of the tile column tj (T = update tile): < 2 for the columns the owner always keeps */
+   int block_of_tile(int tj, int T) const { return tj * T < base ? -1 : (tj * T - base) / PW; }
 
    static std::string segment_name(const char* shm_name, int h) { return std::string(shm_name) + "_" + std::to_string(h); }
    static SplitOwner* create(const char* shm_name, int nhelpers) {
@@ -121,14 +131,19 @@ struct SplitOwner {
       }
       if (const char* e = getenv("SPRAL_B200_SPLIT_TIMEOUT")) o->timeout_s = atof(e);
       if (const char* e = getenv("SPRAL_B200_SPLIT_RESTART")) o->restart = atoi(e) != 0;
+      if (const char* e = getenv("SPRAL_B200_SPLIT_OWNER_SHARE")) o->owner_share = atoi(e) != 0;
       return o;
    }
    ~SplitOwner() {
       for (Link& l : links)
          if (l.sh) { l.sh->phase.store(4, std::memory_order_release); munmap((void*)l.sh, sizeof(SplitShm)); shm_unlink(l.name.c_str()); }
-      for (auto& o : opened) cudaIpcCloseMemHandle(o.second);
    }
-   void* open_handle(const unsigned char* h) {
+   /* mappings of the helpers' mirrors are kept for the life of the process (opening one costs milliseconds; the helper's
+    * allocation cache hands out the same block -- same handle -- for the same front of the next factorisation) */
+   static void* open_handle(const unsigned char* h) {
+      static std::mutex mtx;
+      static std::vector<std::pair<std::vector<unsigned char>, void*>> opened;
+      std::lock_guard<std::mutex> lock(mtx);
       for (auto& o : opened) if (std::memcmp(o.first.data(), h, 64) == 0) return o.second;
       cudaIpcMemHandle_t hh; std::memcpy(&hh, h, sizeof(hh));
       void* p = nullptr;
@@ -141,6 +156,7 @@ struct SplitOwner {
     * front; where a drained split is re-started otherwise).  The far columns are copied on stream `s`, in order behind
     * whatever updated them last.  Returns false (and leaves the front alone) when a helper does not answer. */
    bool begin_front(const Front& fr, bool posdef, cudaStream_t s, int first_col = 0) {
+      const auto tb0 = std::chrono::steady_clock::now();
       const int T = update_tile_size(true);
       const int b = split_round_up(first_col, T);
       if (active || dead || fr.n - b < 4 * PW || (fr.n - b + PW - 1) / PW > SPLIT_MAXP) return false;
@@ -152,6 +168,7 @@ struct SplitOwner {
          sh->drained.store(0);
          sh->m = fr.m; sh->n = fr.n; sh->ldl = fr.ldl; sh->ld_is_l = posdef ? 1 : 0; sh->base = b;
          sh->nhelpers = H(); sh->helper_index = h; links[h].next_k = 0;
+         sh->nworkers = nworkers(); sh->worker_index = h + (owner_share ? 1 : 0);
          sh->phase.store(1, std::memory_order_release);
       }
       for (int h = 0; h < H(); ++h) {
@@ -163,27 +180,35 @@ struct SplitOwner {
       f = &fr; base = b; p_first = first_col;
       /* the far blocks, each to the helper that owns it, rows from its first column down */
       for (int J = 2; blk(J) < fr.n; ++J) {
+         if (is_local(J)) continue;
          const int c0 = blk(J), c1 = std::min(blk(J + 1), fr.n);
          const size_t off = (size_t)c0 + (size_t)c0 * fr.ldl;
          CUDA_TRY(cudaMemcpy2DAsync(link_of(J).mL + off, (size_t)fr.ldl * sizeof(double), fr.L + off, (size_t)fr.ldl * sizeof(double),
                                     (size_t)(fr.m - c0) * sizeof(double), c1 - c0, cudaMemcpyDefault, s));
       }
       active = true; n_pushed = n_pulled = 0;
+      t_begin_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
       if (trace) fprintf(stderr, "[split] front m %d n %d: far columns %d.. on %d helper(s) (panels from column %d)\n", fr.m, fr.n,
                          blk(2), H(), first_col);
       return true;
    }
    /* panel index of the panel that starts at column p0, or -1 when the panels are no longer the split's blocks */
    int panel_of(int p0) const { return (p0 >= p_first && (p0 - p_first) % PW == 0) ? (p0 - p_first) / PW : -1; }
-   bool has_far(int k) const { return blk(k + 2) < f->n; }
+   /* a helper still holds a block >= k + 2 */
+   bool has_far(int k) const {
+      for (int h = 0; h < (int)links.size(); ++h) if (holds_from(h, k + 2)) return true;
+      return false;
+   }
    /* helper h still holds a block >= J0 */
    bool holds_from(int h, int J0) const {
-      for (int J = std::max(2, J0); blk(J) < f->n; ++J) if ((J - 2) % (int)links.size() == h) return true;
+      for (int J = std::max(2, J0); blk(J) < f->n && J < std::max(2, J0) + nworkers(); ++J)
+         if (worker_of(J) == h + (owner_share ? 1 : 0)) return true;
       return false;
    }
    /* Panel k = columns [k0, k1): rows of the far blocks into the mirror of every helper that still holds one, then
     * ready[k] (copy stream). */
    void push_panel(int k, int k0, int k1, cudaStream_t s2) {
+      const auto tp0 = std::chrono::steady_clock::now();
       const int r0 = blk(k + 2);
       const size_t off = (size_t)r0 + (size_t)k0 * f->ldl;
       const size_t pitch = (size_t)f->ldl * sizeof(double), width = (size_t)(f->m - r0) * sizeof(double);
@@ -197,6 +222,7 @@ struct SplitOwner {
          l.next_k = k + 1;
       }
       ++n_pushed;
+      t_push_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
    }
    void pull_block(int J, cudaStream_t s) {
       const int c0 = blk(J), c1 = std::min(blk(J + 1), f->n);
@@ -207,9 +233,12 @@ struct SplitOwner {
    }
    /* Block J comes back (main stream), in order before the urgent update that touches it. */
    void need_block(int J, cudaStream_t s) {
-      if (J < 2 || blk(J) >= f->n) return;
+      if (J < 2 || blk(J) >= f->n || is_local(J)) return;        // a local block is ordered by the bulk stream's events
       SplitShm* sh = link_of(J).sh;
-      if (!split_wait(sh, timeout_s, [&] { return sh->updated[J].load(std::memory_order_acquire) != 0; })) {
+      const auto tw0 = std::chrono::steady_clock::now();
+      const bool okw = split_wait(sh, timeout_s, [&] { return sh->updated[J].load(std::memory_order_acquire) != 0; });
+      t_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+      if (!okw) {
          sh->error.store(1, std::memory_order_release);
          throw std::runtime_error("split front: a helper did not return a block in time");
       }
@@ -218,6 +247,7 @@ struct SplitOwner {
    /* The split ends at panel k (failed pivot, short panel): every block the helpers still hold -- J >= first_block --
     * comes back; they have applied panels 0 .. k-1 to them. */
    void drain(int k, int first_block, cudaStream_t s, cudaStream_t s2) {
+      const auto td0 = std::chrono::steady_clock::now();
       CUDA_TRY(cudaStreamSynchronize(s2));                     // every pushed panel has been announced
       if (trace) fprintf(stderr, "[split] drain at panel %d (%d panels pushed, %d blocks pulled)\n", k, n_pushed, n_pulled);
       for (Link& l : links) l.sh->ready[l.next_k].store(SPLIT_DRAIN, std::memory_order_release);   // where that helper waits
@@ -226,12 +256,14 @@ struct SplitOwner {
             l.sh->error.store(1, std::memory_order_release);
             throw std::runtime_error("split front: a helper did not drain in time");
          }
-      for (int J = std::max(2, first_block); blk(J) < f->n; ++J) pull_block(J, s);
+      for (int J = std::max(2, first_block); blk(J) < f->n; ++J) if (!is_local(J)) pull_block(J, s);
       end_front(s);
+      t_drain_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td0).count();
    }
    void end_front(cudaStream_t s) {
       CUDA_TRY(cudaStreamSynchronize(s));                      // the copies out of the mirrors are done
-      if (trace) fprintf(stderr, "[split] front closed (%d panels pushed, %d blocks pulled)\n", n_pushed, n_pulled);
+      if (trace) fprintf(stderr, "[split] front closed (%d panels pushed, %d blocks pulled); host ms so far: set-up %.1f, pushes %.1f, "
+                         "waiting for blocks %.1f, drains %.1f\n", n_pushed, n_pulled, t_begin_ms, t_push_ms, t_wait_ms, t_drain_ms);
       for (Link& l : links) l.sh->phase.store(3, std::memory_order_release);
       active = false; f = nullptr;
    }
@@ -255,7 +287,7 @@ static int split_helper_serve(const char* shm_name_base, int device, double time
       if (ph == 4) break;
       const int m = sh->m, n = sh->n, ldl = sh->ldl, base = sh->base;
       const bool ld_is_l = sh->ld_is_l != 0;
-      const int Hn = std::max(1, sh->nhelpers), hidx = sh->helper_index;
+      const int Hn = std::max(1, sh->nworkers), hidx = sh->worker_index;      // workers the blocks are dealt to / this one
       const size_t bytes = (size_t)ldl * n * sizeof(double);
       double* mL = (double*)g_pool.alloc(bytes);
       double* mLD = ld_is_l ? mL : (double*)g_pool.alloc(bytes);

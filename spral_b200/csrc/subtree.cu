@@ -400,12 +400,14 @@ struct Numeric {
    int device = 0;                     // copy of S->device: the symbolic object may die first
 #ifdef SPRAL_B200_SPLIT
    SplitOwner* split = nullptr;
+   cudaStream_t stream3 = nullptr;     // pushes of the distributed front's panels to the helpers
 #endif
    ~Numeric() {
       if (!S) return;
       cudaSetDevice(device);
 #ifdef SPRAL_B200_SPLIT
       delete split;
+      if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
 #endif
       if (stream) cudaStreamSynchronize(stream);
       if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
@@ -653,7 +655,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
           * panel (candidates parked at the end) or a new pass ends it */
          if (any_fail || !lookahead || na_all != 1 || split_k < 0 || h0.pend0 != h0.p0 + PW) {
             const int kd = std::max(0, (h0.p0 - N.split->p_first + PW - 1) / PW);      // panels the helper was given: 0 .. kd-1
-            N.split->drain(kd, kd + 1, s, N.stream2);
+            N.split->drain(kd, kd + 1, s, N.stream3);
          } else split_now = true;
       } else if (N.split && N.split->level_ok && N.split->restart && !N.split->dead && !any_fail && lookahead && na_all == 1) {
          /* a drained split starts again behind a clean full panel of the first pass order (sporadic failures must not
@@ -682,12 +684,20 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
             int tj_next = (std::min(h.pend0 + 2 * PW, h.n) - 1) / T;     // last tile column of the panel after next
             bool has_bulk = lookahead && tj_urgent + 1 < nt;
             if (has_bulk) bulk_regs.push_back(make_int4(h.fi, h.p0, h.done, (tj_urgent + 1) * T));
-            for (int tj = h.pend0 / T; tj < nt; ++tj)
+            for (int tj = h.pend0 / T; tj < nt; ++tj) {
+#ifdef SPRAL_B200_SPLIT
+               /* distributed front: the tile columns of the blocks a helper holds are updated there */
+               if (split_now && tj > tj_urgent) {
+                  const int J = N.split->block_of_tile(tj, T);
+                  if (J >= 2 && !N.split->is_local(J)) continue;
+               }
+#endif
                for (int ti = tj; ti < mt; ++ti) {
                   if (has_bulk && tj > tj_next) bulk_b.push_back({(int)bulk_regs.size() - 1, ti, tj});
                   else if (has_bulk && tj > tj_urgent) bulk.push_back({(int)bulk_regs.size() - 1, ti, tj});
                   else outer.push_back({h.fi, ti, tj});
                }
+            }
          }
          if (!posdef && h.pend0 - h.pend > 0 && h.end - h.pend0 > 0) {
             int ntr = (h.m + RT - 1) / RT;
@@ -695,10 +705,6 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          }
       }
       if (err) { if (bulk_pending) cudaStreamSynchronize(N.stream2); return err; }
-#ifdef SPRAL_B200_SPLIT
-      if (split_now) {}                       // the far columns are on the helper whatever their number
-      else
-#endif
       if (lookahead && (int)(bulk.size() + bulk_b.size()) < device_sm_count()) {   // not worth a second stream
          for (const MatTile& t : bulk) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
          for (const MatTile& t : bulk_b) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
@@ -738,9 +744,11 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
 #ifdef SPRAL_B200_SPLIT
       if (split_now) {
          const HostState& h0 = H[act[0]];
-         if (N.split->has_far(split_k)) N.split->push_panel(split_k, h0.p0, h0.done, N.stream2);
-         else N.split->end_front(s);          // nothing is left on the helper
-      } else
+         /* the panel travels on a stream of its own (the host has synchronised the panel; the bulk stream may be
+          * busy with the owner's share of the previous panel for a long time) */
+         if (N.split->has_far(split_k)) N.split->push_panel(split_k, h0.p0, h0.done, N.stream3);
+         else N.split->end_front(s);          // nothing is left on a helper
+      }
 #endif
       if (have_bulk) {
          cudaStream_t s2 = N.stream2;
@@ -838,7 +846,10 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
 #ifdef SPRAL_B200_SPLIT
    /* the segment exists for the whole part, so that the helper -- which arrives when its own parts are done, before
     * this part can end -- always finds it and always sees its end (phase 4 in ~SplitOwner) */
-   if (!S.split_shm.empty()) N.split = SplitOwner::create(S.split_shm.c_str(), S.split_helpers);
+   if (!S.split_shm.empty()) {
+      N.split = SplitOwner::create(S.split_shm.c_str(), S.split_helpers);
+      if (!N.stream3) CUDA_TRY(cudaStreamCreateWithFlags(&N.stream3, cudaStreamNonBlocking));
+   }
 #endif
    Prof prof;
    struct ProfScope { ProfScope(Prof* p) { g_prof = g_profile ? p : nullptr; } ~ProfScope() { g_prof = nullptr; } } prof_scope(&prof);

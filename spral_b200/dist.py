@@ -150,22 +150,156 @@ def assign_ranks(a, world):
     return rank_of
 
 
+def node_flops(a):
+    """Factorisation flops per node without delays: sum_{j < ncol} (m - j)^2 (cpu/factor.hxx:121-124)."""
+    m = (a.rptr[1:] - a.rptr[:-1]).astype(np.float64)
+    nc = (a.sptr[1:] - a.sptr[:-1]).astype(np.float64)
+    # sum_{j=0}^{nc-1} (m-j)^2 = nc m^2 - m nc (nc-1) + (nc-1) nc (2nc-1) / 6
+    return nc * m * m - m * nc * (nc - 1) + (nc - 1) * nc * (2 * nc - 1) / 6.0
+
+
+def proportional_partition(a, world, small=0.02, whole_ok=True):
+    """Proportional mapping of the assembly tree onto `world` ranks (one process per GPU).
+
+    The reference's find_subtree_partition (anal.F90:289-464) cuts subtrees for the GPUs and leaves EVERYTHING
+    above the cut to one "all-region" part -- on the CPU in the reference, on one GPU here -- which for a 3-D
+    problem is most of the work (cfg5: 60 % of the flops above an 8-way cut).  Here the ranks of a node are dealt to
+    its children in proportion to their subtree flops; a subtree that ends up with one rank is a leaf part, and every
+    node that still has several ranks below it becomes a part of its own, run on the rank of its heaviest child (whose
+    contribution block then never travels).  So the level of 6 fronts below the top runs on 6 GPUs, the level of 3 on
+    3, and only the root front is serial (and is the one the distributed top front splits further).
+    Returns (part, rank_of): part = 1-based first nodes (len nparts + 1) in postorder."""
+    nn = a.nnodes
+    par = np.asarray(a.sparent, dtype=np.int64) - 1                # 0-based parent, nn for roots
+    fl = node_flops(a)
+    sub = fl.copy()
+    first = np.arange(nn)                                          # first node of the subtree (postorder: contiguous)
+    children = [[] for _ in range(nn + 1)]
+    for i in range(nn):
+        p = int(par[i]) if par[i] < nn else nn
+        children[p].append(i)
+        if p < nn:
+            sub[p] += sub[i]
+            first[p] = min(first[p], first[i])
+    total = float(fl.sum()) or 1.0
+    parts, ranks_out = [], []
+    load = [0.0] * world                                           # flops dealt to every rank so far (small subtrees)
+
+    def leaf(node, rank):
+        parts.append(int(first[node]) + 1)
+        ranks_out.append(rank)
+        load[rank] += float(sub[node])
+
+    def assign(node, ranks):
+        """Emits the parts of the subtree of `node` in postorder; returns the rank of the part that holds `node`."""
+        if len(ranks) == 1 or not children[node]:
+            leaf(node, ranks[0])
+            return ranks[0]
+        ch = children[node]                                        # increasing index == postorder
+        big = [c for c in ch if sub[c] >= small * total / world * len(ranks) and sub[c] > 0]
+        if len(big) <= 1:                                          # a chain (or one dominant child): nothing to spread here
+            leaf(node, ranks[0])
+            return ranks[0]
+        alloc = {}
+        if len(big) > len(ranks):
+            # more big children than ranks: longest-processing-time packing, one rank per bin -- except for a child
+            # that outweighs a fair share of this node's ranks: it is dealt ALL of them (its own children are then
+            # spread with the loads of its smaller siblings already on the books)
+            order = sorted(big, key=lambda c: -sub[c])
+            fair = (sum(float(sub[c]) for c in big) + float(fl[node]) + sum(load[r] for r in ranks)) / len(ranks)
+            trial = {r: load[r] for r in ranks}
+            for i, c in enumerate(order):                          # what plain packing would give (the node itself goes
+                r = min(ranks, key=lambda q: trial[q])             # where its heaviest child is)
+                trial[r] += float(sub[c]) + (float(fl[node]) if i == 0 else 0.0)
+            whole = order[0] if whole_ok and max(trial.values()) > 1.15 * fair and len(children[order[0]]) > 1 else None
+            bins = {r: load[r] for r in ranks}
+            r0 = min(ranks, key=lambda q: bins[q])                 # takes the chain: this node and the top of `whole`
+            if whole is not None:
+                bins[r0] += float(fl[node]) + float(fl[whole])
+            for c in order:
+                if c == whole:
+                    continue
+                r = min(ranks, key=lambda q: bins[q])
+                alloc[c] = [r]
+                bins[r] += float(sub[c])
+            if whole is not None:
+                alloc[whole] = [r0] + sorted([q for q in ranks if q != r0], key=lambda q: bins[q])
+        else:
+            # integer shares of the ranks for the big children, proportional to their flops, at least one each
+            k = {c: 1 for c in big}
+            for _ in range(len(ranks) - len(big)):
+                c = max(big, key=lambda c: sub[c] / k[c])
+                k[c] += 1
+            pos = 0
+            for c in sorted(big, key=lambda c: -sub[c]):
+                alloc[c] = ranks[pos:pos + k[c]]
+                pos += k[c]
+        top_rank, heaviest = ranks[0], -1.0
+        prebooked = {}
+        for c in ch:                                               # loads of the single-rank siblings count before anybody recurses
+            if c in alloc and len(alloc[c]) == 1:
+                prebooked[c] = float(sub[c])
+                load[alloc[c][0]] += prebooked[c]
+        for c in ch:
+            if c in alloc:
+                if c in prebooked:
+                    load[alloc[c][0]] -= prebooked[c]                  # leaf() books it again
+                r = assign(c, alloc[c])
+            else:                                                  # small subtree (or no rank left): least loaded rank of this node
+                r = min(ranks, key=lambda q: load[q])
+                leaf(c, r)
+            if sub[c] > heaviest:
+                heaviest, top_rank = sub[c], r
+        parts.append(node + 1)
+        ranks_out.append(top_rank)
+        load[top_rank] += float(fl[node])
+        return top_rank
+
+    roots = children[nn]
+    if len(roots) == 1:
+        assign(roots[0], list(range(world)))
+    else:                                                          # a forest: deal the ranks to the trees like children of a virtual root
+        order = sorted(roots, key=lambda c: -sub[c])
+        shares = {c: [] for c in roots}
+        for i, r in enumerate(range(world)):
+            shares[order[i % len(order)] if i < len(order) else max(order, key=lambda c: sub[c] / max(1, len(shares[c])))].append(r)
+        for c in roots:
+            if shares[c]:
+                assign(c, shares[c])
+            else:
+                leaf(c, min(range(world), key=lambda q: load[q]))
+    parts.append(nn + 1)
+    return np.asarray(parts, dtype=np.int32), ranks_out
+
+
 class DistAkeep:
     def __init__(self, analysis, subtrees, rank_of, consumer, children):
         self.analysis, self.subtrees = analysis, subtrees
         self.rank_of, self.consumer, self.children = rank_of, consumer, children
+        # list-scheduling priority of a part: flops on the path from it to the root of the tree ("bottom level").
+        # A rank works through its parts in this order, so what another rank is waiting for comes first
+        # (children always precede their consumers: their bottom level is larger).
+        fl = part_flops(analysis)
+        self.priority = [0.0] * analysis.nparts
+        for p in range(analysis.nparts - 1, -1, -1):
+            q = consumer[p]
+            self.priority[p] = float(fl[p]) + (self.priority[q] if q >= 0 else 0.0)
 
 
-def modelled_critical_path(a, world):
-    """Length of the longest chain of the part schedule when every part costs its
-    flops (normalised to the whole tree) plus a fixed per-part overhead."""
+def modelled_critical_path(a, world, rank_of=None):
+    """Length of the schedule when every part costs its flops (normalised to the whole tree) plus a fixed
+    per-part overhead and every rank works through its parts by decreasing bottom level (DistAkeep.priority)."""
     consumer, children = part_graph(a)
-    rank_of = assign_ranks(a, world)
+    if rank_of is None:
+        rank_of = assign_ranks(a, world)
     fl = part_flops(a)
     tot = max(float(fl.sum()), 1.0)
+    prio = [0.0] * a.nparts
+    for p in range(a.nparts - 1, -1, -1):
+        prio[p] = float(fl[p]) + (prio[consumer[p]] if consumer[p] >= 0 else 0.0)
     fin = [0.0] * a.nparts
     busy = [0.0] * world
-    for p in range(a.nparts):
+    for p in sorted(range(a.nparts), key=lambda p: (-prio[p], p)):
         start = max([fin[c] for c in children[p]] + [busy[rank_of[p]]])
         fin[p] = start + fl[p] / tot + 0.005
         busy[rank_of[p]] = fin[p]
@@ -180,6 +314,21 @@ def analyse(ctx, n, ptr, row, order=None, nemin=32, options=None, tune_partition
     critical path is kept: a finer partition is not always better, every part
     boundary costs the level-set batching across its subtrees."""
     a = Analysis(n, ptr, row, order=order, nemin=nemin, ngpu=ctx.world, **kw)
+    mode = os.environ.get("SPRAL_B200_PARTITION", "proportional")
+    if ctx.world > 1 and tune_partition and mode == "proportional" and a.nnodes > 0:
+        best = None
+        for whole_ok in (False, True):                           # two variants of the mapping: the schedule model picks
+            part, ranks = proportional_partition(a, ctx.world, whole_ok=whole_ok)
+            a.set_partition(part, [r + 2 for r in ranks])
+            cp = modelled_critical_path(a, ctx.world, list(ranks))
+            if best is None or cp < best[0] - 1e-9:
+                best = (cp, part, ranks)
+        _, part, ranks = best
+        a.set_partition(part, [r + 2 for r in ranks])
+        consumer, children = part_graph(a)
+        subtrees = [ctx.engine.symbolic(a, p, ctx.local_rank, options) if ranks[p] == ctx.rank else None
+                    for p in range(a.nparts)]
+        return DistAkeep(a, subtrees, list(ranks), consumer, children)
     if ctx.world > 1 and tune_partition and "max_load_inbalance" not in kw:
         best, best_cp = a, modelled_critical_path(a, ctx.world)
         for mli in (2.0, 3.0):
@@ -461,7 +610,7 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
                   f"factor {1e3*(t_p2-t_p1):.1f} (dev {ctx.engine.device_ms(ns):.1f}), "
                   f"publish {1e3*(t_p3-t_p2):.1f} ms, flops {st.num_flops:.3g}", file=sys.stderr, flush=True)
 
-    mine = [p for p in range(nparts) if ak.rank_of[p] == ctx.rank]
+    mine = sorted((p for p in range(nparts) if ak.rank_of[p] == ctx.rank), key=lambda p: (-ak.priority[p], p))
     split = _split_roles(ctx, ak)                # distributed top front: (shm name, owner rank, helper ranks) or None
     if split and ctx.rank == split[1]:
         _lib.load().spral_ssids_b200_split_enable(ak.subtrees[nparts - 1]._h, split[0].encode(), len(split[2]))
@@ -469,7 +618,7 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
     if not ctx.engine.device_ipc or len(mine) <= 1:
         nthreads = 1
     # independent parts of this rank run concurrently (each on its own stream); tasks are
-    # submitted in postorder, so a parent never starts before its children have started
+    # submitted by decreasing bottom level, so a parent never starts before its children have started
     with ThreadPoolExecutor(max_workers=nthreads) as ex:
         for p in mine:
             futures[p] = ex.submit(run_part, p)
@@ -486,11 +635,12 @@ def factor(ctx, ak, posdef, val, options=None, scaling=None):
 
 
 def _split_roles(ctx, ak):
-    """SPRAL_B200_SPLIT=1 with a library built with -DSPRAL_B200_SPLIT (csrc/split_front.h; opt-in, not run on GPUs
-    yet): the rank that owns the last part (the top of the tree) offloads the far columns of its large fronts to the
-    other ranks (SPRAL_B200_SPLIT_HELPERS caps their number; the far blocks are dealt round robin).  Returns (shared-memory
-    name, owner, [helper ranks]) or None."""
-    if os.environ.get("SPRAL_B200_SPLIT") != "1" or ctx.world < 2 or not ctx.engine.device_ipc:
+    """Distributed top front (csrc/split_front.h; SPRAL_B200_SPLIT=0 turns it off): the rank that owns the last part
+    (the top of the tree) shares the trailing updates of its large fronts with up to SPRAL_B200_SPLIT_HELPERS other ranks
+    (default 3: every helper receives every panel, so the owner's NVLink egress grows with their number -- measured on
+    cfg5: 7 helpers are slower than 3); the far blocks are dealt round robin over the owner and the helpers.
+    Returns (shared-memory name, owner, [helper ranks]) or None."""
+    if os.environ.get("SPRAL_B200_SPLIT", "1") != "1" or ctx.world < 2 or not ctx.engine.device_ipc:
         return None
     lib = _lib.load()
     if not hasattr(lib, "spral_ssids_b200_split_helper_serve"):
@@ -500,7 +650,7 @@ def _split_roles(ctx, ak):
     lib.spral_ssids_b200_split_helper_serve.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int]
     lib.spral_ssids_b200_split_helper_serve.restype = C.c_int
     owner = ak.rank_of[ak.analysis.nparts - 1]
-    nh = max(1, min(ctx.world - 1, int(os.environ.get("SPRAL_B200_SPLIT_HELPERS", str(ctx.world - 1)))))
+    nh = max(1, min(ctx.world - 1, int(os.environ.get("SPRAL_B200_SPLIT_HELPERS", "3"))))
     helpers = [(owner + 1 + i) % ctx.world for i in range(nh)]
     name = f"/spral_b200_split_{os.environ.get('MASTER_PORT', '0')}_{ctx.epoch}"
     return name, owner, helpers

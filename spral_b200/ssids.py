@@ -40,6 +40,21 @@ class Analysis:
             n, _ptr(self.ptr), _ptr(self.row), _ptr(self.order), nemin, -abs(ngpu),
             min_gpu_work, max_load_inbalance, gpu_perf_coeff, C.byref(flag))
         self.flag = flag.value
+        self._load_view()
+
+    def set_partition(self, part, exec_loc):
+        """Replaces the subtree partition (spral_ssids_b200_analysis_set_partition): part = 1-based first nodes,
+        len nparts + 1; exec_loc = the reference's location codes (rank r of an N-GPU job: r + 2)."""
+        part = np.ascontiguousarray(part, dtype=np.int32)
+        loc = np.ascontiguousarray(exec_loc, dtype=np.int32)
+        rc = _lib.load().spral_ssids_b200_analysis_set_partition(self._h, len(loc), _ptr(part), _ptr(loc))
+        if rc != 0:
+            raise ValueError("invalid subtree partition")
+        self._load_view()
+
+    def _load_view(self):
+        lib = _lib.load()
+        n = self.n
         v = AnalysisView()
         lib.spral_ssids_b200_analysis_get(self._h, C.byref(v))
         self.view = v

@@ -102,25 +102,17 @@ def test_distributed_top_front_protocol_model_check():
     assert " 0 failures" in r.stdout and "detected in 0 " not in r.stdout and "/ 0 (" not in r.stdout, r.stdout
 
 
-def test_split_front_variant_compiles_and_default_build_is_untouched():
-    """spral_b200/csrc/split_front.h (distributed top front, `make SPLIT=1`; not run on GPUs yet): the variant compiles
-    for sm_100a, and without the switch the preprocessed subtree.cu does not contain a token of it."""
-    import shutil
-    import pytest
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not found")
+def test_build_without_split_front_has_no_trace_of_it():
+    """spral_b200/csrc/split_front.h (distributed top front) is compiled in by default and switched on at run time;
+    `make NOSPLIT=1` must give a library without a token of it (the preprocessed subtree.cu is checked)."""
     csrc = os.path.join(ROOT, "spral_b200", "csrc")
-    out = os.path.join(ROOT, "build", "tests")
-    os.makedirs(out, exist_ok=True)
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp",
-                           "-I" + os.path.join(ROOT, "include"), "--expt-relaxed-constexpr", "-DSPRAL_B200_SPLIT", "-c",
-                           os.path.join(csrc, "subtree.cu"), "-o", os.path.join(out, "subtree_split.o")])
     pre = subprocess.run(["g++", "-x", "c++", "-E", "-P", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
                           "-I/usr/local/cuda/include", os.path.join(csrc, "subtree.cu")], capture_output=True, text=True)
     assert pre.returncode == 0, pre.stderr[-2000:]
     for token in ("SplitOwner", "SplitShm", "split_now", "split_helper_serve", "shm_open"):
         assert token not in pre.stdout, token
+    with open(os.path.join(csrc, "Makefile")) as fh:
+        assert "-DSPRAL_B200_SPLIT" in fh.read()
 
 
 def test_split_front_host_code_on_a_cuda_mock():
