@@ -331,12 +331,19 @@ k_panel_chain(Front* fronts, const int* __restrict__ flist, int new_panel, Facto
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    double* S = sh.S;
 
-   for (int c = warp; c < CW; c += CH_NT / 32) {
+   for (int c0 = warp; c0 < CW; c0 += 4 * (CH_NT / 32)) {      // four columns (16 independent loads) per thread and round
+      double v[4][CW / 32];
       #pragma unroll
-      for (int i = 0; i < CW / 32; ++i) {
-         const int r = lane + 32 * i;
-         S[c * CLD + r] = (r >= c) ? Lseg[r + (size_t)c * ldl] : 0.0;
-      }
+      for (int q = 0; q < 4; ++q)
+         #pragma unroll
+         for (int i = 0; i < CW / 32; ++i) {
+            const int c = c0 + q * (CH_NT / 32), r = lane + 32 * i;
+            v[q][i] = (r >= c) ? Lseg[r + (size_t)c * ldl] : 0.0;
+         }
+      #pragma unroll
+      for (int q = 0; q < 4; ++q)
+         #pragma unroll
+         for (int i = 0; i < CW / 32; ++i) S[(c0 + q * (CH_NT / 32)) * CLD + lane + 32 * i] = v[q][i];
    }
    if (tid == 0) { sh.fail = 0; sh.status = 0; }
    __syncthreads();
@@ -574,13 +581,25 @@ k_panel_tiles(Front* fronts, const RowTile* work, FactorParams prm) {
    int bad = 0;
    const int rbase = warp * 16;                              // the warp's rows in phases U and S
    for (int jb = 0; jb < CW; jb += PV_BS) {
-      for (int e = tid; e < jb * PV_BS; e += TNT) {
-         const int n = e & 31, k = e >> 5;
-         sh.Bs[k * PBLD + n] = ws->ld11[(jb + n) + (size_t)k * CW];
-      }
-      for (int e = tid; e < PV_BS * PV_BS; e += TNT) {
-         const int c = e & 31, k = e >> 5;
-         sh.Xs[k * PBLD + c] = ws->invl[jb / PV_BS][e];
+      {  /* operands of this step: all loads of a thread first (up to 12 + 4), then the stores */
+         double bv[(CW - PV_BS) * PV_BS / TNT], xv[PV_BS * PV_BS / TNT];
+         #pragma unroll
+         for (int q = 0; q < (CW - PV_BS) * PV_BS / TNT; ++q) {
+            const int e = tid + q * TNT, n = e & 31, k = e >> 5;
+            bv[q] = (e < jb * PV_BS) ? ws->ld11[(jb + n) + (size_t)k * CW] : 0.0;
+         }
+         #pragma unroll
+         for (int q = 0; q < PV_BS * PV_BS / TNT; ++q) xv[q] = ws->invl[jb / PV_BS][tid + q * TNT];
+         #pragma unroll
+         for (int q = 0; q < (CW - PV_BS) * PV_BS / TNT; ++q) {
+            const int e = tid + q * TNT, n = e & 31, k = e >> 5;
+            if (e < jb * PV_BS) sh.Bs[k * PBLD + n] = bv[q];
+         }
+         #pragma unroll
+         for (int q = 0; q < PV_BS * PV_BS / TNT; ++q) {
+            const int e = tid + q * TNT, c = e & 31, k = e >> 5;
+            sh.Xs[k * PBLD + c] = xv[q];
+         }
       }
       if (tid < PV_BS) {
          double v0, v1 = 0.0, v2 = 0.0;
@@ -697,12 +716,19 @@ k_seg_commit(Front* fronts, const RowTile* work) {
    const SegWS* ws = f->sws;
    double* L = f->L;
    const bool diag_cta = (w.tile == p / RT);
+   /* the diagonal block from the workspace to the front: thread t owns row t, 16 columns in flight (a load behind a
+    * store through another pointer would wait for it) */
+   auto write_diag_block = [&]() {
+      for (int c0 = 0; c0 < CW; c0 += 16) {
+         double v[16];
+         #pragma unroll
+         for (int q = 0; q < 16; ++q) v[q] = ws->l11[t + (size_t)(c0 + q) * CW];
+         #pragma unroll
+         for (int q = 0; q < 16; ++q) if (t >= c0 + q) L[(size_t)(p + t) + (size_t)(p + c0 + q) * ldl] = v[q];
+      }
+   };
    if (POSDEF) {                      /* no permutation, no D: only the diagonal block is left to write */
-      if (diag_cta)
-         for (int e = t; e < CW * CW; e += RT) {
-            const int i = e % CW, c = e / CW;
-            if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
-         }
+      if (diag_cta) write_diag_block();
       return;
    }
    if (f->seg_fail) {
@@ -726,7 +752,7 @@ k_seg_commit(Front* fronts, const RowTile* work) {
    __syncthreads();
    if (r0 < p && s_moved) {
       const int cend = min(r0 + RT, p);
-      constexpr int NB = 8;
+      constexpr int NB = 16;
       for (int c0 = r0; c0 < cend; c0 += NB) {
          double v[NB];
          #pragma unroll
@@ -737,10 +763,7 @@ k_seg_commit(Front* fronts, const RowTile* work) {
       }
    }
    if (diag_cta) {
-      for (int e = t; e < CW * CW; e += RT) {
-         const int i = e % CW, c = e / CW;
-         if (i >= c) L[(size_t)(p + i) + (size_t)(p + c) * ldl] = ws->l11[e];
-      }
+      write_diag_block();
       for (int e = t; e < 2 * CW; e += RT) f->D[2 * p + e] = ws->dinv[e];
       s_perm[t] = f->perm[p + src];
       __syncthreads();

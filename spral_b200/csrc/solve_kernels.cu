@@ -424,6 +424,7 @@ struct SolveDevCtx {
    __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
    __device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
    __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
+   __device__ __forceinline__ void mma(double& d0, double& d1, double a, double b) { pv_dmma(d0, d1, a, b); }
 };
 
 template <int NR, bool POSDEF>

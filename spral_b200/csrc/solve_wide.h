@@ -55,8 +55,44 @@ SW_FN int sw_row_index(const SolveFront& f, int i) {
 /* row stride of the right-hand-side blocks in shared memory: not a multiple of 32 doubles (threads that own
  * consecutive rows would all hit one bank with 32 right-hand sides) and even, so that a row stays 16-byte
  * aligned and the broadcast reads of another row's values vectorise */
-template <int NR> constexpr int sw_xld() { return NR == 1 ? 1 : NR + 2; }
-template <int NR> constexpr size_t sw_T_smem_doubles() { return (size_t)SWB * sw_xld<NR>() + (size_t)SSB * SW_LK; }
+template <int NR> constexpr int sw_xld() { return NR == 1 ? 1 : (NR >= 16 ? NR + 4 : NR + 2); }
+/* with 16+ right-hand sides the update of the rows below a sub-block runs on the FP64 tensor cores (cx.mma, m8n8k4 with
+ * M = right-hand side): the 32-column slab of L goes through shared memory, k-major with a stride = 4 mod 16 doubles
+ * (bank-conflict-free fragment loads; so is the stride NR + 4 of the right-hand sides) */
+template <int NR> constexpr bool sw_T_mma() { return NR >= 16; }
+constexpr int SW_LLD = SWB + 4;
+template <int NR> constexpr size_t sw_T_smem_doubles() {
+   return (size_t)SWB * sw_xld<NR>() + (size_t)SSB * SW_LK + (sw_T_mma<NR>() ? (size_t)SSB * SW_LLD : 0);
+}
+
+/* xs(rows of the 8-row groups of this warp that lie in [lo, hi)) -= slab * xs(sub-block rows): the tensor-core form of
+ *   for k: s = xs[t][k]; for j: s -= cur[j] * xs[jb + j][k]
+ * ls[j * SW_LLD + t] = cur[j] of thread t (0 for the threads that do not take part). */
+template <int NR, class Ctx>
+SW_FN void sw_mma_update(Ctx& cx, double* xs, const double* ls, int jb, int lo, int hi) {
+   constexpr int XLD = sw_xld<NR>();
+   const int lane = cx.tid() & 31, warp = cx.tid() >> 5;
+   for (int i = 0; i < 4; ++i) {
+      const int rg = 32 * warp + 8 * i;
+      if (rg + 8 <= lo || rg >= hi) continue;
+      double acc[NR / 8][2];
+      #pragma unroll
+      for (int j = 0; j < NR / 8; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+      #pragma unroll
+      for (int kk = 0; kk < SSB; kk += 4) {
+         const double bfr = ls[(size_t)(kk + (lane & 3)) * SW_LLD + rg + (lane >> 2)];
+         #pragma unroll
+         for (int j = 0; j < NR / 8; ++j) {
+            const double afr = xs[(size_t)(jb + kk + (lane & 3)) * XLD + 8 * j + (lane >> 2)];
+            cx.mma(acc[j][0], acc[j][1], afr, bfr);
+         }
+      }
+      #pragma unroll
+      for (int j = 0; j < NR / 8; ++j)
+         #pragma unroll
+         for (int e = 0; e < 2; ++e) xs[(size_t)(rg + 2 * (lane & 3) + e) * XLD + 8 * j + (lane >> 2)] -= acc[j][e];
+   }
+}
 constexpr int SW_GT = 256;   // threads of a G kernel CTA
 /* forward G: ys [SWB * NR] + the partial sums of the second column half [RT * NR] doubles */
 template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)SWB * NR + (size_t)RT * NR; }
@@ -71,6 +107,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
    constexpr int XLD = sw_xld<NR>();
    double* xs = smem;
    double* lkk = smem + (size_t)SWB * XLD;
+   double* ls = lkk + (size_t)SSB * SW_LK;          // (tensor-core variant only)
    const int w = sw_min(SWB, f.nelim - kb);
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
    const size_t ldl = (size_t)f.ldl;
@@ -95,6 +132,10 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
          for (int j = 0; j < SSB; ++j) lkk[i * SW_LK + j] = (i < wd && j < wd && i >= j) ? cur[j] : 0.0;
       }
       const int jn = jb + SSB;                    // next slab of the rows below this sub-block
+      if (sw_T_mma<NR>()) {
+         #pragma unroll
+         for (int j = 0; j < SSB; ++j) ls[(size_t)j * SW_LLD + t] = (arow && t >= jn) ? cur[j] : 0.0;
+      }
       if (jn < w) {
          const int wdn = sw_min(SSB, w - jn);
          #pragma unroll
@@ -122,7 +163,10 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) xs[(size_t)(jb + lane) * XLD + k] = v[q]; }
       }
       cx.sync();
-      if (arow && t >= jn) {                      // rows of the block below the sub-block
+      if (sw_T_mma<NR>()) {
+         if (jn < w) sw_mma_update<(NR >= 16 ? NR : 16)>(cx, xs, ls, jb, jn, w);
+         cx.sync();                                // the slab is re-written at the top of the next sub-step
+      } else if (arow && t >= jn) {               // rows of the block below the sub-block
          #pragma unroll
          for (int k = 0; k < NR; ++k) {
             double s = xs[(size_t)t * XLD + k];
@@ -262,6 +306,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
    constexpr int XLD = sw_xld<NR>();
    double* vs = smem;
    double* lkk = smem + (size_t)SWB * XLD;
+   double* ls = lkk + (size_t)SSB * SW_LK;          // (tensor-core variant only)
    const int kb = b * SWB;
    const int w = sw_min(SWB, f.nelim - kb);
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
@@ -290,6 +335,10 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
          for (int i = 0; i < SSB; ++i) lkk[i * SW_LK + j] = (i < wd && j < wd && i >= j) ? cur[i] : 0.0;
       }
       const int jp = jb - SSB;                    // rows of the previous sub-block, for the columns up to its end
+      if (sw_T_mma<NR>()) {
+         #pragma unroll
+         for (int i = 0; i < SSB; ++i) ls[(size_t)i * SW_LLD + t] = (acol && t < jb) ? cur[i] : 0.0;
+      }
       if (jp >= 0) {
          #pragma unroll
          for (int i = 0; i < SSB; ++i) nxt[i] = (acol && t < jp + SSB) ? Lcol[jp + i] : 0.0;
@@ -316,7 +365,10 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) vs[(size_t)(jb + lane) * XLD + k] = v[q]; }
       }
       cx.sync();
-      if (acol && t < jb) {                       // columns of the block left of the sub-block
+      if (sw_T_mma<NR>()) {
+         if (jb > 0) sw_mma_update<(NR >= 16 ? NR : 16)>(cx, vs, ls, jb, 0, jb);
+         cx.sync();
+      } else if (acol && t < jb) {                // columns of the block left of the sub-block
          #pragma unroll
          for (int k = 0; k < NR; ++k) {
             double s = vs[(size_t)t * XLD + k];

@@ -55,8 +55,9 @@ static bool g_panel_v2 = true;       // speculative 128-column panel segments (p
                                      // large fronts (SPRAL_B200_PANEL_V2=0: every panel step by step).  Measured on cfg5:
                                      // 376 -> 357 ms together with g_bulk_prio (profiles/r02_ab_variants.md)
 static int g_panel_v2_fronts = 32;
-static int g_ctile_block = 0;        // SPRAL_B200_CTILE_BLOCK=12 (experimental, unmeasured): Schur-complement tiles in
-                                     // SB x SB blocked order for L2 reuse of the operand panels (0 = column by column)
+static int g_ctile_block = 8;        // Schur-complement tiles in SB x SB blocked order for L2 reuse of the operand panels
+                                     // (SPRAL_B200_CTILE_BLOCK=0: column by column).  ncu, largest launch of cfg5: DRAM reads
+                                     // 20.8 -> 11.4 GB, L2 hit rate 59 -> 74 %, same 34.0 ms (profiles/r02_ncu_full_upd_contrib.md)
 static bool g_bulk_prio = true;      // no static SM split: the panel stream has the highest stream priority and the bulk
                                      // update runs one tile per CTA on the lowest, so the panel kernels take SMs as bulk
                                      // tiles retire (SPRAL_B200_BULK_PRIO=0: persistent bulk kernel on SMs - 28)

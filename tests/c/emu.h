@@ -53,6 +53,14 @@ struct Ctx {
       int r = w.xi[(t & 31) ^ off]; pthread_barrier_wait(&w.bar);
       return r;
    }
+   /* mma.sync.m8n8k4 (FP64): lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) .. +1] */
+   void mma(double& d0, double& d1, double a, double bb) {
+      const int lane = t & 31, i = lane >> 2, j0 = 2 * (lane & 3);
+      for (int k = 0; k < 4; ++k) {
+         const double av = shfl(a, i * 4 + k), b0 = shfl(bb, j0 * 4 + k), b1 = shfl(bb, (j0 + 1) * 4 + k);
+         d0 += av * b0; d1 += av * b1;
+      }
+   }
    void atomic_add(double* p, double v) { std::lock_guard<std::mutex> lock(b->atomics); *p += v; }
 };
 
