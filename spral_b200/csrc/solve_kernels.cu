@@ -440,10 +440,10 @@ template <int NR>
 __global__ void __launch_bounds__(SW_GT)
 k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork) {
    extern __shared__ double smem_dyn[];
-   const RowTile w = work[blockIdx.x];
+   const RowTile w = work[blockIdx.x / SW_FSPLIT];
    const SolveFront f = fronts[w.front];
    SolveDevCtx cx;
-   fwd_wide_G<NR>(cx, f, w.tile, blk, x, ywork, smem_dyn);
+   fwd_wide_G<NR>(cx, f, w.tile, blk, (int)(blockIdx.x % SW_FSPLIT), x, ywork, smem_dyn);
 }
 
 template <int NR>
@@ -651,7 +651,7 @@ void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
       }
       for (int b = 0; b < nblk; ++b) {
          k_fwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, b, x, ywork); COUNT_LAUNCH();
-         k_fwd_wide_G<NR><<<nwork, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
+         k_fwd_wide_G<NR><<<nwork * SW_FSPLIT, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
       }
    }
 }
@@ -708,7 +708,7 @@ void launch_fwd_level_wide(const SolveFront* fronts, int first, int count, const
    if (nwork == 0 || nblk == 0 || count == 0) return;
 #define SW_F(NRV) SW_DISPATCH(NRV, (fwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, nblk, x, ywork, s)), \
                                    (fwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, nblk, x, ywork, s)))
-   switch (nr) { SW_F(32); SW_F(16); SW_F(8); SW_F(4); SW_F(2); default: SW_F(1); }
+   switch (nr) { SW_F(64); SW_F(32); SW_F(16); SW_F(8); SW_F(4); SW_F(2); default: SW_F(1); }
 #undef SW_F
 }
 
@@ -717,7 +717,7 @@ void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const
    if (nwork == 0 || nblk == 0 || count == 0) return;
 #define SW_B(NRV) SW_DISPATCH(NRV, (bwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s)), \
                                    (bwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s)))
-   switch (nr) { SW_B(32); SW_B(16); SW_B(8); SW_B(4); SW_B(2); default: SW_B(1); }
+   switch (nr) { SW_B(64); SW_B(32); SW_B(16); SW_B(8); SW_B(4); SW_B(2); default: SW_B(1); }
 #undef SW_B
 }
 #undef SW_DISPATCH
@@ -729,7 +729,8 @@ void configure_solve_kernels() {
 
 /* Largest number of right-hand sides one kernel pass handles. */
 int solve_rhs_chunk(int nrhs) { return nrhs >= 32 ? 32 : nrhs >= 16 ? 16 : nrhs >= 8 ? 8 : nrhs >= 4 ? 4 : nrhs >= 2 ? 2 : 1; }
-int solve_max_chunk() { return 32; }
+/* 64 right-hand sides in one pass exist in the wide kernels only (tensor cores; L is read once instead of twice) */
+int solve_max_chunk() { return 64; }
 
 void launch_fwd_level(const SolveFront* fronts, const RowTile* work, int nwork, int nsteps,
       bool posdef, int nr, double* x, int ldx, double* ywork, cudaStream_t s, unsigned int* bar) {

@@ -95,7 +95,7 @@ SW_FN void sw_mma_update(Ctx& cx, double* xs, const double* ls, int jb, int lo, 
 }
 constexpr int SW_GT = 256;   // threads of a G kernel CTA
 /* forward G: ys [SWB * NR] + the partial sums of the second column half [RT * NR] doubles */
-template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)SWB * NR + (size_t)RT * NR; }
+template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)(SWB / 2) * NR + (size_t)RT * NR; }
 /* backward G: nothing (registers and shuffles only) */
 template <int NR> constexpr size_t sw_bG_smem_doubles() { return 1; }
 
@@ -149,6 +149,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
          double v[NRW];
          #pragma unroll
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? xs[(size_t)(jb + lane) * XLD + k] : 0.0; }
+         #pragma unroll 4
          for (int j = 0; j < wd; ++j) {
             const double l = (lane > j && lane < wd) ? lkk[lane * SW_LK + j] : 0.0;
             const double dj = POSDEF ? lkk[j * SW_LK + j] : 1.0;
@@ -186,20 +187,26 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
 }
 
 /* ---- forward, G: x(rows below the block) -= L(rows, block) * y --------------------- */
-/* SW_GT = 256 threads: thread (row r0 + (t & 127), half h = t >> 7) sums the columns [128 h, 128 h + 128) of its row,
- * 16 or 32 independent loads at a time; the halves meet in shared memory. */
+/* SW_GT = 256 threads per (row tile, column half `ch` of the block): thread (row r0 + (t & 127), quarter h = t >> 7)
+ * sums 64 columns of its row, eight independent loads at a time; the quarters meet in shared memory, the halves in x
+ * (atomics).  Two CTAs per tile: twice as many bytes in flight per SM on the levels that have few tiles. */
+constexpr int SW_FSPLIT = 2;
 template <int NR, class Ctx>
-SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, double* x, const double* ywork, double* smem) {
+SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, int ch, double* x, const double* ywork, double* smem) {
    const int kb = blk * SWB;
    if (kb >= f.nelim) return;
    const int w = sw_min(SWB, f.nelim - kb);
    const int r0 = tile * RT;
    if (r0 + RT <= kb + w || r0 >= f.m) return;
+   constexpr int CH = SWB / SW_FSPLIT;              // columns of this CTA
+   const int c0 = ch * CH;
+   if (c0 >= w) return;
+   const int wc = sw_min(CH, w - c0);
    double* ys = smem;
-   double* part = smem + (size_t)SWB * NR;
+   double* part = smem + (size_t)CH * NR;
    const int t = cx.tid();
-   for (int e = t; e < w; e += SW_GT) {
-      const int g = f.perm[kb + e] - 1;
+   for (int e = t; e < wc; e += SW_GT) {
+      const int g = f.perm[kb + c0 + e] - 1;
       #pragma unroll
       for (int k = 0; k < NR; ++k) ys[(size_t)e * NR + k] = ywork[SW_XI(g, k)];
    }
@@ -212,10 +219,10 @@ SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, double* x
    for (int k = 0; k < NR; ++k) acc[k] = 0.0;
    if (active) {
       const size_t ldl = (size_t)f.ldl;
-      const double* Lr = f.L + r + (size_t)kb * ldl;
-      const int jend = sw_min(w, h * (SWB / 2) + SWB / 2);
-      constexpr int NL = (NR <= 2) ? 32 : 16;      // independent loads in flight per thread
-      for (int j0 = h * (SWB / 2); j0 < jend; j0 += NL) {
+      const double* Lr = f.L + r + (size_t)(kb + c0) * ldl;
+      const int jend = sw_min(wc, h * (CH / 2) + CH / 2);
+      constexpr int NL = 8;                        // independent loads in flight per thread
+      for (int j0 = h * (CH / 2); j0 < jend; j0 += NL) {
          double l[NL];
          #pragma unroll
          for (int q = 0; q < NL; ++q) l[q] = (j0 + q < jend) ? Lr[(size_t)(j0 + q) * ldl] : 0.0;
@@ -234,7 +241,7 @@ SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, double* x
    cx.sync();
    if (h == 0 && active) {
       const int g = sw_row_index(f, r);
-      /* rows < nelim are touched by this thread only, rows >= nelim are shared with sibling fronts */
+      /* several CTAs (column halves, sibling fronts) add into a row of x */
       #pragma unroll
       for (int k = 0; k < NR; ++k) cx.atomic_add(&x[SW_XI(g, k)], -(acc[k] + part[(size_t)rl * NR + k]));
    }
@@ -312,12 +319,16 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
    const bool acol = t < w;
    const int g = acol ? f.perm[kb + t] - 1 : -1;
-   #pragma unroll
-   for (int k = 0; k < NR; ++k) {
-      double v = 0.0;
-      if (acol) v = x[SW_XI(g, k)] - pb[(size_t)t * NR + k];      // pb: what the G kernel accumulated for this block
-      pb[(size_t)t * NR + k] = 0.0;                                // ... cleared for the next step
-      vs[(size_t)t * XLD + k] = v;
+   {  /* pb: what the G kernel accumulated for this block; cleared for the next step.  All loads before the stores
+       * (x and pb are distinct, but the compiler cannot know it and would wait for every store) */
+      double xv[NR], pv[NR];
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) { xv[k] = acol ? x[SW_XI(g, k)] : 0.0; pv[k] = pb[(size_t)t * NR + k]; }
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) {
+         pb[(size_t)t * NR + k] = 0.0;
+         vs[(size_t)t * XLD + k] = acol ? xv[k] - pv[k] : 0.0;
+      }
    }
    const size_t ldl = (size_t)f.ldl;
    const double* Lcol = f.L + (size_t)kb + (size_t)(kb + t) * ldl;     // column kb+t of the block, from row kb
@@ -351,6 +362,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
          double v[NRW];
          #pragma unroll
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? vs[(size_t)(jb + lane) * XLD + k] : 0.0; }
+         #pragma unroll 4
          for (int j = wd - 1; j >= 0; --j) {
             const double l = (lane < j) ? lkk[j * SW_LK + lane] : 0.0;
             const double dj = POSDEF ? lkk[j * SW_LK + j] : 1.0;

@@ -1282,7 +1282,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          dx = (double*)S.b_x.p;
          CUDA_TRY(cudaMemcpyAsync(dx, x, xbytes, cudaMemcpyHostToDevice, s));
       }
-      const int maxnr = std::min(nrhs, solve_max_chunk());
+      const int maxnr = std::min(std::max(nrhs, 1), solve_max_chunk());
       const size_t chunk_bytes = (size_t)S.n * maxnr * sizeof(double);
       if (job == JOB_FWD) S.b_y.ensure(chunk_bytes, s);
       /* levels swept 256 columns at a time (solve_wide.h) */
@@ -1290,14 +1290,15 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          /* with 16+ right-hand sides the wide kernels (FP64 tensor cores) win on every level; with few, the levels of
           * small fronts are better off with the 32-column kernels (measured on cfg5: 15.3 vs 16.6 ms, 84 vs 93 ms) */
          if (!g_solve_wide || N.lvl_steps[lev] < (nr >= 16 ? 1 : g_solve_wide_min)) return false;
-         size_t nwork = (size_t)(N.swork_ptr[lev + 1] - N.swork_ptr[lev]);
-         return nwork * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
+         /* the backward sweep keeps one 256 x nr accumulator per front of the level */
+         size_t nfr = (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]);
+         return nfr * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
       };
       if (job == JOB_DIAG_BWD || job == JOB_BWD) {
-         size_t need = std::max<size_t>(N.max_level_work, 1) * solve_block() * solve_max_chunk() * sizeof(double);
+         size_t need = std::max<size_t>(N.max_level_work, 1) * solve_block() * 32 * sizeof(double);      // 32-column kernels: per tile
          for (int lev = 0; lev < S.nlevels; ++lev)
             if (wide_level(lev, maxnr))
-               need = std::max(need, (size_t)(N.swork_ptr[lev + 1] - N.swork_ptr[lev]) * solve_wide_block() * maxnr * sizeof(double));
+               need = std::max(need, (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]) * solve_wide_block() * maxnr * sizeof(double));
          S.b_pbuf.ensure(need, s);
       }
       double* ywork = (double*)S.b_y.p;
@@ -1305,8 +1306,12 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
       S.b_bar.ensure(256, s);
       unsigned int* bar = g_solve_coop ? (unsigned int*)S.b_bar.p : nullptr;
       S.b_xt.ensure(chunk_bytes, s);
+      /* 64 at a time when every level can be swept by the wide kernels (the 32-column kernels stop at 32) */
+      bool all_wide64 = g_solve_wide != 0;
+      for (int lev = 0; lev < S.nlevels && all_wide64; ++lev)
+         if (N.swork_ptr[lev + 1] > N.swork_ptr[lev] && !wide_level(lev, 64)) all_wide64 = false;
       for (int r0 = 0; r0 < nrhs;) {
-         int nr = solve_rhs_chunk(nrhs - r0);
+         int nr = (nrhs - r0 >= 64 && all_wide64) ? 64 : solve_rhs_chunk(nrhs - r0);
          double* xcol = dx + (size_t)r0 * ldx;
          /* every chunk is swept in the pool's RHS-contiguous buffer: its address is
           * stable, so the (long, launch-latency-bound) kernel sequence of a sweep is

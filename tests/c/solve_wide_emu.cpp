@@ -63,7 +63,8 @@ static double run_case(const Case& c, std::mt19937_64& rng) {
          emu::run_cta(SW_TT, [&](emu::Ctx& cx) { fwd_wide_T<NR, POSDEF>(cx, f, b, x.data(), ywork.data(), smT.data()); });
          for (int t = 0; t < ntile + 1; ++t) {
             std::fill(smG.begin(), smG.end(), std::nan(""));
-            emu::run_cta(SW_GT, [&](emu::Ctx& cx) { fwd_wide_G<NR>(cx, f, t, b, x.data(), ywork.data(), smG.data()); });
+            for (int ch = 0; ch < SW_FSPLIT; ++ch)
+               emu::run_cta(SW_GT, [&](emu::Ctx& cx) { fwd_wide_G<NR>(cx, f, t, b, ch, x.data(), ywork.data(), smG.data()); });
          }
       }
       for (int j = 0; j < nelim; ++j)                                   // k_fwd_flush
