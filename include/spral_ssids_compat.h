@@ -8,10 +8,15 @@
  * spral_b200/csrc/ssids_capi.cpp on top of the subtree ABI
  * (spral_ssids_b200.h) and the restated analyse phase.
  *
- * Not provided (outside the hot path): analyse_coord,
- * analyse_topology, the *_ptr32 variants other than analyse_ptr32, and the
- * scaling algorithms options.scaling = 1..4 (flag -98); a user-supplied scale
- * vector (options.scaling = 0, scale != NULL) is honoured.
+ * All 15 functions of the reference header are provided (analyse, analyse_coord,
+ * analyse_ptr32, analyse_topology -- the topology argument is ignored --, factor,
+ * factor_ptr32, solve, solve1, enquire_posdef, enquire_indef, alter, free*), and
+ * options.scaling = 0 (user vector), 1 (Hungarian), 2 (auction), 3 (from the
+ * matching-based ordering), 4 (equilibration); options.ordering = 0, 1, 2.
+ * Accepted and ignored: options.pivot_method / failed_pivot_method (the engine has
+ * one pivoting strategy: APP inside 32 x 32 blocks with an a-posteriori threshold
+ * test, failed columns retried in later passes, then delayed), nstream,
+ * gpu_perf_coeff, the print units; inform.stat is always 0.
  */
 #ifndef SPRAL_SSIDS_COMPAT_H
 #define SPRAL_SSIDS_COMPAT_H

@@ -334,13 +334,39 @@ def factor(akeep, posdef, val, options=None, scaling=None, device_contrib=True):
     return Fkeep(akeep, posdef, numeric, inform, sc)
 
 
-def solve(fkeep, x, job=0):
+def _sym_matvec(a, val, X):
+    """A X for the lower-triangular CSC pattern of the analysis (1-based ptr / row) and the values given to factor."""
+    n = a.n
+    ptr = np.asarray(a.ptr, dtype=np.int64) - 1
+    row = np.asarray(a.row, dtype=np.int64) - 1
+    col = np.repeat(np.arange(n, dtype=np.int64), np.diff(ptr))
+    v = np.asarray(val, dtype=np.float64)
+    Y = np.zeros_like(X)
+    np.add.at(Y, row, v[:, None] * X[col, :])
+    off = row != col
+    np.add.at(Y, col[off], v[off][:, None] * X[row[off], :])
+    return Y
+
+
+def solve(fkeep, x, job=0, refine=0, val=None):
     """ssids_solve -> inner_solve_cpu (src/ssids/fkeep.F90:234-323).
-    x: (n,) or (n, nrhs) Fortran-ordered; returns the solution (same shape)."""
+    x: (n,) or (n, nrhs) Fortran-ordered; returns the solution (same shape).
+    refine = k (job 0 only; needs `val`, the values that were factorised): k steps of iterative refinement with the
+    same factors, x += solve(b - A x).  With threshold pivoting (u = 0.01) the scaled residual of the reference's CPU
+    engine and of this one is 1e-13 .. 1e-12 on the shifted stencil matrices; one step brings both below 1e-15
+    (DESIGN.md 5).  The reference leaves refinement to the caller (its driver does not refine either)."""
     a = fkeep.akeep.analysis
     x = np.asarray(x, dtype=np.float64)
     if a.n == 0:                      # trivial matrix: nothing to do (src/ssids/ssids.f90:1193)
         return x.copy()
+    if refine and job == 0:
+        if val is None:
+            raise ValueError("solve(refine=k) needs val, the matrix values that were factorised")
+        B = np.asfortranarray(x.reshape(a.n, -1))
+        Xs = solve(fkeep, B, 0)
+        for _ in range(int(refine)):
+            Xs = Xs + solve(fkeep, np.asfortranarray(B - _sym_matvec(a, val, Xs)), 0)
+        return Xs[:, 0] if x.ndim == 1 else Xs
     one = x.ndim == 1
     X = np.asfortranarray(x.reshape(a.n, -1))
     nrhs = X.shape[1]

@@ -545,3 +545,18 @@ def test_random_problems_like_reference_test_random():
             p.close()
         for ns in fk.numeric:
             ns.close()
+
+
+def test_solve_with_refinement_reaches_1e14():
+    """north_star's literal bar (backward error <= 1e-14 in FP64) is not reached by either engine on a shifted
+    stencil matrix with u = 0.01 without refinement (oracle golden 2.0e-12 on cfg3); solve(refine=1) reaches it."""
+    n, ptr, row, val = M.stencil_3d_27pt(24, shift=13.0)
+    ak = sb.analyse(n, ptr, row)
+    fk = sb.factor(ak, False, val)
+    A = M.to_scipy(n, ptr, row, val)
+    rng = np.random.default_rng(4)
+    B = np.asfortranarray(A @ rng.uniform(-1, 1, (n, 3)))
+    X1 = sb.solve(fk, B, refine=1, val=val)
+    assert oracle_ref.backward_error(A, X1, B) <= 1e-14
+    x1 = sb.solve(fk, B[:, 0], refine=2, val=val)
+    assert oracle_ref.backward_error(A, x1, B[:, 0]) <= 1e-14
