@@ -5,7 +5,6 @@ the same library without a helper, bit for bit.  usage: split_check.py n indef|p
 import sys, os, time, threading, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 os.environ.setdefault("OMP_CANCELLATION", "TRUE")
-os.environ["SPRAL_B200_DIAG_V2"] = "1"
 import numpy as np, scipy.sparse as sp
 from spral_b200 import _lib
 _lib.LIB_PATH = os.environ['SPRAL_B200_EMU_LIB']

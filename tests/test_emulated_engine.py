@@ -5,10 +5,9 @@ by loops over the same regions and tiles).  The library is loaded BY TESTS ONLY 
 SPRAL_B200_EMU_LIB); the package knows the CUDA library and nothing else.
 
 This runs the logic of the GPU test files in a GPU-less container: host scheduling, assembly, pivoting kernels, delays,
-solves -- and every opt-in variant -- against the oracle.  It is not a parity claim (parity is measured on the B200,
-`-m gpu`); it is how changes are checked before GPU minutes are spent on them.  The whole of test_gpu_parity.py
-(38 tests without the full-size / device-pointer / C-client ones), test_gpu_widened.py and test_gpu_experimental.py pass
-this way (6 + 6 tests, ~30 min); the CPU suite runs a slice of a couple of minutes."""
+solves -- and the alternative code paths -- against the oracle.  It is not a parity claim (parity is measured on the
+B200, `-m gpu`); it is how changes are checked before GPU minutes are spent on them.  The CPU suite runs a slice of a
+few minutes."""
 import os
 import subprocess
 import sys
@@ -26,7 +25,7 @@ def emu_env():
         pytest.skip("CUDA headers not found")
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "emu", "build_emu.py")], stdout=subprocess.DEVNULL)
     env = dict(os.environ)
-    env.update(SPRAL_B200_EMU_LIB=EMU_LIB, SPRAL_B200_DIAG_V2="1", OMP_CANCELLATION="TRUE")   # 128-fiber diagonal blocks: 8x faster to emulate
+    env.update(SPRAL_B200_EMU_LIB=EMU_LIB, OMP_CANCELLATION="TRUE")
     return env
 
 
@@ -44,11 +43,12 @@ def test_slice_of_the_gpu_parity_suite_on_the_emulator(emu_env):
     assert " passed" in out and "failed" not in out, out[-500:]
 
 
-def test_opt_in_variants_against_the_default_engine_on_the_emulator(emu_env):
-    env = dict(emu_env, SPRAL_B200_EXPERIMENTAL_TESTS="1", SPRAL_B200_DUMP_CASES="dense_391_indef,dense_500_posdef")
-    env.pop("SPRAL_B200_DIAG_V2")            # this file compares DIAG_V2 with the default kernel itself
-    out = _pytest(env, ["tests/test_gpu_experimental.py"], 1500)
-    assert "6 passed" in out, out[-500:]
+def test_alternative_code_paths_against_the_defaults_on_the_emulator(emu_env):
+    """tests/test_gpu_paths.py (step-by-step panels, 32-column solve kernels, scheduling switches against the
+    defaults) on two small dense fronts."""
+    env = dict(emu_env, SPRAL_B200_DUMP_CASES="dense_391_indef")
+    out = _pytest(env, ["tests/test_gpu_paths.py"], 2400)
+    assert "3 passed" in out, out[-500:]
 
 
 @pytest.fixture(scope="module")
@@ -57,10 +57,10 @@ def emu_split_lib(emu_env):
     return os.path.join(ROOT, "build", "emu_split", "libspral_ssids_b200_emu_split.so")
 
 
-@pytest.mark.parametrize("n,kind,helpers,expect", [(1300, "posdef", 1, "4 panels pushed, 4 blocks pulled"), (1300, "indef", 1, "drain at panel"),
-                                                   (2600, "indef", 3, "panels from column 1278")])      # three helpers; drained twice, re-started twice
+@pytest.mark.parametrize("n,kind,helpers,expect", [(1300, "indef", 1, "drain at panel"),
+                                                   (1300, "posdef", 2, "front closed")])      # two helpers + the owner's share
 def test_distributed_top_front_end_to_end_on_the_emulator(emu_env, emu_split_lib, n, kind, helpers, expect):
-    """csrc/split_front.h and its hooks in factor_fronts (`make SPLIT=1`, not run on GPUs yet) with the owner and the helper
+    """csrc/split_front.h and its hooks in factor_fronts with the owner and the helper
     as two threads of one process on the emulator: a front that is split to its end (Cholesky) and one whose split is
     drained by a failed pivot give the factors and solutions of the unsplit run bit for bit."""
     env = dict(emu_env, SPRAL_B200_EMU_LIB=emu_split_lib, SPRAL_B200_TRACE="1")

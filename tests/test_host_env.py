@@ -51,12 +51,19 @@ def test_cpu_baseline_leg_runs_in_its_own_process():
     import oracle_ref
     if not oracle_ref.available():
         pytest.skip("oracle/_ref not built")
-    code = ("import bench, json\n"
-            "print(json.dumps(bench.cpu_reference_factor(12)))")
-    ref = json.loads(_run(code))
+    code = ("import bench, json, argparse, numpy as np\n"
+            "from spral_b200 import matrices as M\n"
+            "from spral_b200.ssids import Analysis\n"
+            "args = argparse.Namespace(workload='cfg5', grid=12, nrhs=4)\n"
+            "n, ptr, row, val = M.stencil_3d_27pt(12, shift=13.0)\n"
+            "a = Analysis(n, ptr, row)\n"
+            "print(json.dumps(bench.cpu_reference_arm(args, a.order)))")
+    ref = json.loads(_run(code).strip().splitlines()[-1])
     cb = ref["cpu_baseline"]
     assert ref["impl"] == "reference" and cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] > 0
     assert ref["e2e"]["h2d_bytes_per_step"] == 0
+    assert "12^3" in ref["config"]["workload"]                       # the SAME workload as the GPU arm (same_config)
+    assert set(cb["solve_seconds"]) == {"1", "4"} and cb["inform"]["matrix_rank"] == 1728
 
 
 def test_trivial_matrix_n0():

@@ -1,6 +1,6 @@
 """Factorises a few fixed matrices on cuda:0 and dumps what identifies the result
 bit for bit (pivot order, D^-1, inform, one solution) to an .npz.  Used by
-tests/test_gpu_experimental.py to compare an opt-in kernel variant (selected
+tests/test_gpu_paths.py to compare an alternative code path (selected
 through the SPRAL_B200_* environment of THIS process) with the default engine."""
 import os
 import sys
