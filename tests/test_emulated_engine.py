@@ -57,8 +57,10 @@ def emu_split_lib(emu_env):
     return os.path.join(ROOT, "build", "emu_split", "libspral_ssids_b200_emu_split.so")
 
 
-@pytest.mark.parametrize("n,kind,helpers,expect", [(1300, "indef", 1, "drain at panel"),
-                                                   (1300, "posdef", 2, "front closed")])      # two helpers + the owner's share
+@pytest.mark.parametrize("n,kind,helpers,expect", [
+    (1300, "indef", 1, "drain at panel"),
+    pytest.param(1300, "posdef", 2, "front closed",           # two helpers + the owner's share
+                 marks=pytest.mark.skipif(os.environ.get("SPRAL_B200_SLOW_TESTS") != "1", reason="2 minutes: set SPRAL_B200_SLOW_TESTS=1"))])
 def test_distributed_top_front_end_to_end_on_the_emulator(emu_env, emu_split_lib, n, kind, helpers, expect):
     """csrc/split_front.h and its hooks in factor_fronts with the owner and the helper
     as two threads of one process on the emulator: a front that is split to its end (Cholesky) and one whose split is
