@@ -427,13 +427,15 @@ struct SolveDevCtx {
    __device__ __forceinline__ void mma(double& d0, double& d1, double a, double b) { pv_dmma(d0, d1, a, b); }
 };
 
-template <int NR, bool POSDEF>
+/* grid = fronts x (NRT / NR) slices of right-hand sides: block b handles front b % count, slice b / count */
+template <int NR, int NRT, bool POSDEF>
 __global__ void __launch_bounds__(SW_TT)
-k_fwd_wide_T(const SolveFront* fronts, int first, int blk, const double* __restrict__ x, double* __restrict__ ywork) {
+k_fwd_wide_T(const SolveFront* fronts, int first, int count, int blk, const double* __restrict__ x, double* __restrict__ ywork) {
    extern __shared__ double smem_dyn[];
-   const SolveFront f = fronts[first + blockIdx.x];
+   const SolveFront f = fronts[first + blockIdx.x % count];
+   const int k0 = (blockIdx.x / count) * NR;
    SolveDevCtx cx;
-   fwd_wide_T<NR, POSDEF>(cx, f, blk, x, ywork, smem_dyn);
+   fwd_wide_T<NR, NRT, POSDEF>(cx, f, blk, x + k0, ywork + k0, smem_dyn);
 }
 
 template <int NR>
@@ -456,14 +458,15 @@ k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int first, int step,
    bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)(w.front - first) * SWB * NR, smem_dyn);
 }
 
-template <int NR, bool POSDEF>
+template <int NR, int NRT, bool POSDEF>
 __global__ void __launch_bounds__(SW_TT)
-k_bwd_wide_T(const SolveFront* fronts, int first, int step, double* __restrict__ x, double* __restrict__ pbuf) {
+k_bwd_wide_T(const SolveFront* fronts, int first, int count, int step, double* __restrict__ x, double* __restrict__ pbuf) {
    extern __shared__ double smem_dyn[];
-   const int fi = first + blockIdx.x;
-   const SolveFront f = fronts[fi];
+   const int fl = blockIdx.x % count;
+   const SolveFront f = fronts[first + fl];
+   const int k0 = (blockIdx.x / count) * NR;
    SolveDevCtx cx;
-   bwd_wide_T<NR, POSDEF>(cx, f, step, x, pbuf + (size_t)blockIdx.x * SWB * NR, smem_dyn);
+   bwd_wide_T<NR, NRT, POSDEF>(cx, f, step, x + k0, pbuf + (size_t)fl * SWB * NRT + k0, smem_dyn);
 }
 
 /* ---- G kernels on the FP64 tensor cores (16 or 32 right-hand sides) ---------------------------------------- */
@@ -625,32 +628,36 @@ k_bwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int first, int s
 }
 
 template <int NR> struct UseMma { static constexpr bool value = (NR >= 16); };
+/* right-hand sides per T CTA: a block of 32 or 64 is solved by 2 or 4 CTAs side by side (the T kernels are one CTA
+ * per front and latency-bound; the SMs are idle while they run) */
+template <int NR> constexpr int t_slice() { return NR > 16 ? 16 : NR; }
 
 template <int NR, bool POSDEF>
 void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork, int nblk,
       double* x, double* ywork, cudaStream_t s) {
    static bool configured = false;
-   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double);
+   constexpr int TS = t_slice<NR>();
+   const size_t smT = sw_T_smem_doubles<TS>() * sizeof(double);
    if constexpr (UseMma<NR>::value) {
       const size_t smG = sg_f_smem_bytes<NR>();
       if (!configured) {
-         cudaFuncSetAttribute(k_fwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+         cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
          cudaFuncSetAttribute(k_fwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
          configured = true;
       }
       for (int b = 0; b < nblk; ++b) {
-         k_fwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, b, x, ywork); COUNT_LAUNCH();
+         k_fwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, b, x, ywork); COUNT_LAUNCH();
          k_fwd_wide_G_mma<NR><<<nwork, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
       }
    } else {
       const size_t smG = sw_fG_smem_doubles<NR>() * sizeof(double);
       if (!configured) {
-         cudaFuncSetAttribute(k_fwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+         cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
          cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
          configured = true;
       }
       for (int b = 0; b < nblk; ++b) {
-         k_fwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, b, x, ywork); COUNT_LAUNCH();
+         k_fwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, b, x, ywork); COUNT_LAUNCH();
          k_fwd_wide_G<NR><<<nwork * SW_FSPLIT, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
       }
    }
@@ -662,9 +669,10 @@ template <int NR, bool POSDEF>
 void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
       const int* wbeg, int nblk, double* x, double* pbuf, cudaStream_t s) {
    static bool configured = false;
-   const size_t smT = sw_T_smem_doubles<NR>() * sizeof(double);
+   constexpr int TS = t_slice<NR>();
+   const size_t smT = sw_T_smem_doubles<TS>() * sizeof(double);
    if (!configured) {
-      cudaFuncSetAttribute(k_bwd_wide_T<NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+      cudaFuncSetAttribute(k_bwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
       if constexpr (UseMma<NR>::value)
          cudaFuncSetAttribute(k_bwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_b_smem_bytes<NR>());
       configured = true;
@@ -677,7 +685,7 @@ void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
          k_bwd_wide_G<NR><<<nwork, SW_GT, 0, s>>>(fronts, work, first, st, x, pbuf);
       }
       COUNT_LAUNCH();
-      k_bwd_wide_T<NR, POSDEF><<<count, SW_TT, smT, s>>>(fronts, first, st, x, pbuf); COUNT_LAUNCH();
+      k_bwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, st, x, pbuf); COUNT_LAUNCH();
    }
 }
 

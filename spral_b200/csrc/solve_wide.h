@@ -100,7 +100,9 @@ template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)(SWB / 
 template <int NR> constexpr size_t sw_bG_smem_doubles() { return 1; }
 
 /* ---- forward, T: y(block) = L(block, block)^-1 x(block); y -> ywork ---------------- */
-template <int NR, bool POSDEF, class Ctx>
+/* NR right-hand sides of the NRT that share a row of x / ywork (the caller offsets the pointers to the first one):
+ * the right-hand sides are independent, so a block of 64 is solved by four CTAs of 16 side by side. */
+template <int NR, int NRT, bool POSDEF, class Ctx>
 SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, double* ywork, double* smem) {
    const int kb = blk * SWB;
    if (kb >= f.nelim) return;
@@ -114,7 +116,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
    const bool arow = t < w;
    const int g = arow ? f.perm[kb + t] - 1 : -1;
    #pragma unroll
-   for (int k = 0; k < NR; ++k) xs[(size_t)t * XLD + k] = arow ? x[SW_XI(g, k)] : 0.0;
+   for (int k = 0; k < NR; ++k) xs[(size_t)t * XLD + k] = arow ? x[(size_t)g * NRT + k] : 0.0;
    const double* Lrow = f.L + (size_t)(kb + t) + (size_t)kb * ldl;     // row kb+t of the block, from column kb
    double cur[SSB], nxt[SSB];
    {
@@ -182,7 +184,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
    cx.sync();
    if (arow) {
       #pragma unroll
-      for (int k = 0; k < NR; ++k) ywork[SW_XI(g, k)] = xs[(size_t)t * XLD + k];
+      for (int k = 0; k < NR; ++k) ywork[(size_t)g * NRT + k] = xs[(size_t)t * XLD + k];
    }
 }
 
@@ -306,7 +308,7 @@ SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const
 }
 
 /* ---- backward, T: x(block) = L(block, block)^-T (x(block) - accumulator); the accumulator is cleared ---- */
-template <int NR, bool POSDEF, class Ctx>
+template <int NR, int NRT, bool POSDEF, class Ctx>
 SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double* pb, double* smem) {
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
@@ -323,10 +325,10 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
        * (x and pb are distinct, but the compiler cannot know it and would wait for every store) */
       double xv[NR], pv[NR];
       #pragma unroll
-      for (int k = 0; k < NR; ++k) { xv[k] = acol ? x[SW_XI(g, k)] : 0.0; pv[k] = pb[(size_t)t * NR + k]; }
+      for (int k = 0; k < NR; ++k) { xv[k] = acol ? x[(size_t)g * NRT + k] : 0.0; pv[k] = pb[(size_t)t * NRT + k]; }
       #pragma unroll
       for (int k = 0; k < NR; ++k) {
-         pb[(size_t)t * NR + k] = 0.0;
+         pb[(size_t)t * NRT + k] = 0.0;
          vs[(size_t)t * XLD + k] = acol ? xv[k] - pv[k] : 0.0;
       }
    }
@@ -395,7 +397,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
    cx.sync();
    if (acol) {
       #pragma unroll
-      for (int k = 0; k < NR; ++k) x[SW_XI(g, k)] = vs[(size_t)t * XLD + k];
+      for (int k = 0; k < NR; ++k) x[(size_t)g * NRT + k] = vs[(size_t)t * XLD + k];
    }
 }
 

@@ -60,7 +60,7 @@ static double run_case(const Case& c, std::mt19937_64& rng) {
       std::vector<double> smT(sw_T_smem_doubles<NR>()), smG(sw_fG_smem_doubles<NR>());
       for (int b = 0; b < nblk + 1; ++b) {                              // one block too many: must be a no-op
          std::fill(smT.begin(), smT.end(), std::nan(""));
-         emu::run_cta(SW_TT, [&](emu::Ctx& cx) { fwd_wide_T<NR, POSDEF>(cx, f, b, x.data(), ywork.data(), smT.data()); });
+         emu::run_cta(SW_TT, [&](emu::Ctx& cx) { fwd_wide_T<NR, NR, POSDEF>(cx, f, b, x.data(), ywork.data(), smT.data()); });
          for (int t = 0; t < ntile + 1; ++t) {
             std::fill(smG.begin(), smG.end(), std::nan(""));
             for (int ch = 0; ch < SW_FSPLIT; ++ch)
@@ -95,7 +95,7 @@ static double run_case(const Case& c, std::mt19937_64& rng) {
                bwd_wide_G<NR>(cx, f, t, st, x.data(), pbuf.data(), smG.data()); });
          }
          std::fill(smT.begin(), smT.end(), std::nan(""));
-         emu::run_cta(SW_TT, [&](emu::Ctx& cx) { bwd_wide_T<NR, POSDEF>(cx, f, st, x.data(), pbuf.data(), smT.data()); });
+         emu::run_cta(SW_TT, [&](emu::Ctx& cx) { bwd_wide_T<NR, NR, POSDEF>(cx, f, st, x.data(), pbuf.data(), smT.data()); });
       }
       for (size_t e = 0; e < x.size(); ++e) {
          double d = std::fabs(x[e] - xr[e]);
