@@ -197,9 +197,37 @@ def proportional_partition(a, world, small=0.02, whole_ok=True):
             return ranks[0]
         ch = children[node]                                        # increasing index == postorder
         big = [c for c in ch if sub[c] >= small * total / world * len(ranks) and sub[c] > 0]
-        if len(big) <= 1:                                          # a chain (or one dominant child): nothing to spread here
+        if not big:
             leaf(node, ranks[0])
             return ranks[0]
+        if len(big) == 1:
+            # a chain: follow it down to the first node that branches (two or more big children).  The subtree of that
+            # node is mapped onto all the ranks; the small subtrees that hang off the chain BEFORE it in postorder are
+            # leaf parts, everything after it -- the other small subtrees and the chain nodes themselves -- is one
+            # part (contiguous, its only exit is `node`).  KKT matrices have such chains near the top of the tree.
+            chain, x = [node], big[0]
+            while True:
+                chx = children[x]
+                bx = [c for c in chx if sub[c] >= small * total / world * len(ranks) and sub[c] > 0]
+                if len(bx) != 1:
+                    break
+                chain.append(x)
+                x = bx[0]
+            if len(children[x]) < 2 or sub[x] < 0.5 * sub[node]:   # nothing worth spreading below the chain
+                leaf(node, ranks[0])
+                return ranks[0]
+            before = []                                            # small subtrees with indices below first[x]
+            for cn in chain:
+                for c in children[cn]:
+                    if c != x and c not in chain and c < first[x]:
+                        before.append(c)
+            for c in sorted(before):
+                leaf(c, min(ranks, key=lambda q: load[q]))
+            r = assign(x, ranks)
+            parts.append(x + 2)                                    # nodes x+1 .. node (1-based first node: x + 2)
+            ranks_out.append(r)
+            load[r] += float(sub[node] - sub[x] - sum(sub[c] for c in before))
+            return r
         alloc = {}
         if len(big) > len(ranks):
             # more big children than ranks: longest-processing-time packing, one rank per bin -- except for a child
