@@ -158,16 +158,29 @@ k_fwd_level_coop(const SolveFront* fronts, const RowTile* work, int nsteps,
    }
 }
 
-/* x(eliminated variables) <- ywork.  Grid = fronts x column chunks (block b: front b % count, chunk b / count): the large fronts are not left to one CTA. */
+/* Right-hand sides handled per thread by the flush / diagonal kernels: a row of x is NR contiguous values; consecutive
+ * threads take consecutive chunks of it (coalesced), every chunk is loaded completely before it is stored (a load behind
+ * a store through the same pointer would wait for it). */
+constexpr int RHS_CHUNK = 8;
+
+/* x(eliminated variables) <- ywork.  Grid = fronts x column chunks (block b: front b % count, chunk b / count): the
+ * large fronts are not left to one CTA. */
 __global__ void __launch_bounds__(256)
 k_fwd_flush(const SolveFront* fronts, int first, int count, int nrhs, double* __restrict__ x, int ldx,
       const double* __restrict__ ywork) {
    const int NR = nrhs;
    const SolveFront f = fronts[first + blockIdx.x % count];
    const int chunk = blockIdx.x / count, nchunk = gridDim.x / count;
-   for (int j = chunk * 256 + threadIdx.x; j < f.nelim; j += nchunk * 256) {
-      int g = f.perm[j] - 1;
-      for (int k = 0; k < nrhs; ++k) x[XI(g, k)] = ywork[XI(g, k)];
+   const int nkc = (nrhs + RHS_CHUNK - 1) / RHS_CHUNK;
+   const int total = f.nelim * nkc;
+   for (int idx = chunk * 256 + threadIdx.x; idx < total; idx += nchunk * 256) {
+      const int j = idx / nkc, k0 = (idx % nkc) * RHS_CHUNK;
+      const int g = f.perm[j] - 1;
+      double v[RHS_CHUNK];
+      #pragma unroll
+      for (int q = 0; q < RHS_CHUNK; ++q) v[q] = (k0 + q < nrhs) ? ywork[XI(g, k0 + q)] : 0.0;
+      #pragma unroll
+      for (int q = 0; q < RHS_CHUNK; ++q) if (k0 + q < nrhs) x[XI(g, k0 + q)] = v[q];
    }
 }
 
@@ -181,20 +194,34 @@ k_diag_solve(const SolveFront* fronts, int first, int count, int nrhs, double* _
    const SolveFront f = fronts[first + blockIdx.x % count];
    const double* d = f.D;
    const int chunk = blockIdx.x / count, nchunk = gridDim.x / count;
-   for (int j = chunk * 256 + threadIdx.x; j < f.nelim; j += nchunk * 256) {
-      double d11 = d[2 * j];
+   const int nkc = (nrhs + RHS_CHUNK - 1) / RHS_CHUNK;
+   const int total = f.nelim * nkc;
+   for (int idx = chunk * 256 + threadIdx.x; idx < total; idx += nchunk * 256) {
+      const int j = idx / nkc, k0 = (idx % nkc) * RHS_CHUNK;
+      const double d11 = d[2 * j];
       if (isinf(d11)) continue;                 // handled by the first column of the pair
-      int g1 = f.perm[j] - 1;
+      const int g1 = f.perm[j] - 1;
       if (j + 1 < f.nelim && isinf(d[2 * j + 2])) {
-         double d21 = d[2 * j + 1], d22 = d[2 * j + 3];
-         int g2 = f.perm[j + 1] - 1;
-         for (int k = 0; k < nrhs; ++k) {
-            double x1 = x[XI(g1, k)], x2 = x[XI(g2, k)];
-            x[XI(g1, k)] = d11 * x1 + d21 * x2;
-            x[XI(g2, k)] = d21 * x1 + d22 * x2;
+         const double d21 = d[2 * j + 1], d22 = d[2 * j + 3];
+         const int g2 = f.perm[j + 1] - 1;
+         double x1[RHS_CHUNK], x2[RHS_CHUNK];
+         #pragma unroll
+         for (int q = 0; q < RHS_CHUNK; ++q) {
+            x1[q] = (k0 + q < nrhs) ? x[XI(g1, k0 + q)] : 0.0;
+            x2[q] = (k0 + q < nrhs) ? x[XI(g2, k0 + q)] : 0.0;
          }
+         #pragma unroll
+         for (int q = 0; q < RHS_CHUNK; ++q)
+            if (k0 + q < nrhs) {
+               x[XI(g1, k0 + q)] = d11 * x1[q] + d21 * x2[q];
+               x[XI(g2, k0 + q)] = d21 * x1[q] + d22 * x2[q];
+            }
       } else {
-         for (int k = 0; k < nrhs; ++k) x[XI(g1, k)] *= d11;
+         double x1[RHS_CHUNK];
+         #pragma unroll
+         for (int q = 0; q < RHS_CHUNK; ++q) x1[q] = (k0 + q < nrhs) ? x[XI(g1, k0 + q)] : 0.0;
+         #pragma unroll
+         for (int q = 0; q < RHS_CHUNK; ++q) if (k0 + q < nrhs) x[XI(g1, k0 + q)] = x1[q] * d11;
       }
    }
 }
@@ -691,18 +718,44 @@ void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
 
 } // namespace
 
-/* x (column-major, ld = ldx, nr columns) <-> xt (n rows of nr contiguous values) */
+/* x (column-major, ld = ldx, nr columns) <-> xt (n rows of nr contiguous values): 32 x 32 tiles through shared memory,
+ * coalesced on both sides.  Grid = ceil(n / 32) x ceil(nr / 32) tiles, flattened. */
 __global__ void __launch_bounds__(256)
 k_transpose_rhs(double* __restrict__ x, int ldx, double* __restrict__ xt, int n, int nr, int to_xt) {
-   int g = blockIdx.x * blockDim.x + threadIdx.x;
-   if (g >= n) return;
-   if (to_xt) for (int k = 0; k < nr; ++k) xt[(size_t)g * nr + k] = x[g + (size_t)k * ldx];
-   else       for (int k = 0; k < nr; ++k) x[g + (size_t)k * ldx] = xt[(size_t)g * nr + k];
+   __shared__ double tile[32][33];
+   const int nkt = (nr + 31) / 32;
+   const int g0 = (blockIdx.x / nkt) * 32, k0 = (blockIdx.x % nkt) * 32;
+   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 8 warps
+   if (to_xt) {
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) {                                  // read x: lanes along g (contiguous)
+         const int k = k0 + ty + 8 * i, g = g0 + tx;
+         tile[ty + 8 * i][tx] = (k < nr && g < n) ? x[g + (size_t)k * ldx] : 0.0;
+      }
+      __syncthreads();
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) {                                  // write xt: lanes along k (contiguous)
+         const int g = g0 + ty + 8 * i, k = k0 + tx;
+         if (g < n && k < nr) xt[(size_t)g * nr + k] = tile[tx][ty + 8 * i];
+      }
+   } else {
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+         const int g = g0 + ty + 8 * i, k = k0 + tx;
+         tile[tx][ty + 8 * i] = (g < n && k < nr) ? xt[(size_t)g * nr + k] : 0.0;
+      }
+      __syncthreads();
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+         const int k = k0 + ty + 8 * i, g = g0 + tx;
+         if (k < nr && g < n) x[g + (size_t)k * ldx] = tile[ty + 8 * i][tx];
+      }
+   }
 }
 
 void launch_transpose_rhs(double* x, int ldx, double* xt, int n, int nr, bool to_xt, cudaStream_t s) {
    if (n == 0) return;
-   k_transpose_rhs<<<(n + 255) / 256, 256, 0, s>>>(x, ldx, xt, n, nr, to_xt ? 1 : 0); COUNT_LAUNCH();
+   k_transpose_rhs<<<((n + 31) / 32) * ((nr + 31) / 32), 256, 0, s>>>(x, ldx, xt, n, nr, to_xt ? 1 : 0); COUNT_LAUNCH();
 }
 
 int solve_block() { return SB; }

@@ -211,6 +211,7 @@ struct Symbolic {
    /* scratch pool shared by the factorisations / solves of this subtree */
    std::mutex mtx;
    Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf, b_xt;
+   Buf b_y2, b_pbuf2, b_xt2;          // second lane of the solves (two chunks of right-hand sides swept concurrently)
    Buf b_bar;                         // arrival counter of the cooperative solve kernels
    Buf b_export[2];                   // packed contribution block handed to another process (IPC), double-buffered
    int export_slot = 0;
@@ -227,7 +228,7 @@ struct Symbolic {
       cudaFree(d_node_of_front);
       b_aval.release(); b_scal.release(); b_cbuf[0].release(); b_cbuf[1].release();
       b_ld.release(); b_bk.release(); b_ws.release(); b_work.release(); b_x.release();
-      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_export[0].release(); b_export[1].release(); b_bar.release(); b_bulk[0].release(); b_bulk[1].release();
+      b_y.release(); b_pbuf.release(); b_retry.release(); b_xt.release(); b_y2.release(); b_pbuf2.release(); b_xt2.release(); b_export[0].release(); b_export[1].release(); b_bar.release(); b_bulk[0].release(); b_bulk[1].release();
       b_segws.release();
    }
 };
@@ -403,6 +404,8 @@ struct Numeric {
    SplitOwner* split = nullptr;
    cudaStream_t stream3 = nullptr;     // pushes of the distributed front's panels to the helpers
 #endif
+   cudaStream_t lane2 = nullptr;       // second lane of the solves
+   cudaEvent_t ev_lane_in = nullptr, ev_lane_out = nullptr;
    ~Numeric() {
       if (!S) return;
       cudaSetDevice(device);
@@ -412,6 +415,9 @@ struct Numeric {
 #endif
       if (stream) cudaStreamSynchronize(stream);
       if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+      if (lane2) { cudaStreamSynchronize(lane2); cudaStreamDestroy(lane2); }
+      if (ev_lane_in) cudaEventDestroy(ev_lane_in);
+      if (ev_lane_out) cudaEventDestroy(ev_lane_out);
       for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
       if (ev_bulk) cudaEventDestroy(ev_bulk);
       if (ev_bulk_all) cudaEventDestroy(ev_bulk_all);
@@ -1301,8 +1307,6 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                need = std::max(need, (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]) * solve_wide_block() * maxnr * sizeof(double));
          S.b_pbuf.ensure(need, s);
       }
-      double* ywork = (double*)S.b_y.p;
-      double* pbuf = (double*)S.b_pbuf.p;
       S.b_bar.ensure(256, s);
       unsigned int* bar = g_solve_coop ? (unsigned int*)S.b_bar.p : nullptr;
       S.b_xt.ensure(chunk_bytes, s);
@@ -1310,13 +1314,42 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
       bool all_wide64 = g_solve_wide != 0;
       for (int lev = 0; lev < S.nlevels && all_wide64; ++lev)
          if (N.swork_ptr[lev + 1] > N.swork_ptr[lev] && !wide_level(lev, 64)) all_wide64 = false;
+      /* Two lanes: the sweeps of two chunks of right-hand sides are independent (separate copies of x, y and the
+       * accumulators; the factors are read-only), so with two or more full chunks two of them run concurrently on two
+       * streams: the one-CTA-per-front T kernels of one lane overlap the G kernels of the other, which a single
+       * sweep cannot do (T(b+1) needs G(b)).  Measured on cfg5: 64 right-hand sides as 2 x 32 on two lanes 54.6 ms
+       * against 52.3 ms as one chunk of 64, so a lane is never narrower than a full chunk.
+       * SPRAL_B200_SOLVE_LANES=1: one lane. */
+      static int lanes_env = -1;
+      if (lanes_env < 0) { const char* e = getenv("SPRAL_B200_SOLVE_LANES"); lanes_env = e ? std::max(1, std::min(2, atoi(e))) : 2; }
+      const int full_chunk = all_wide64 ? 64 : solve_rhs_chunk(nrhs);
+      const int nlanes = (lanes_env == 2 && nrhs >= 2 * full_chunk && nrhs >= 64 && !g_solve_graphs && !bar) ? 2 : 1;
+      cudaStream_t lane_s[2] = {s, s};
+      double* lane_xs[2] = {(double*)S.b_xt.p, nullptr};
+      double* lane_y[2] = {(double*)S.b_y.p, nullptr};
+      double* lane_p[2] = {(double*)S.b_pbuf.p, nullptr};
+      if (nlanes == 2) {
+         if (!N.lane2) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&N.lane2, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&N.ev_lane_in, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&N.ev_lane_out, cudaEventDisableTiming));
+         }
+         lane_s[1] = N.lane2;
+         S.b_xt2.ensure(chunk_bytes, s);
+         if (job == JOB_FWD) S.b_y2.ensure(chunk_bytes, s);
+         if (job == JOB_DIAG_BWD || job == JOB_BWD) S.b_pbuf2.ensure(S.b_pbuf.cap, s);
+         lane_xs[1] = (double*)S.b_xt2.p; lane_y[1] = (double*)S.b_y2.p; lane_p[1] = (double*)S.b_pbuf2.p;
+         CUDA_TRY(cudaEventRecord(N.ev_lane_in, s));              // x is on the device, the buffers exist
+         CUDA_TRY(cudaStreamWaitEvent(N.lane2, N.ev_lane_in, 0));
+      }
+      int lane = 0;
       for (int r0 = 0; r0 < nrhs;) {
          int nr = (nrhs - r0 >= 64 && all_wide64) ? 64 : solve_rhs_chunk(nrhs - r0);
          double* xcol = dx + (size_t)r0 * ldx;
-         /* every chunk is swept in the pool's RHS-contiguous buffer: its address is
-          * stable, so the (long, launch-latency-bound) kernel sequence of a sweep is
-          * captured once into a CUDA graph per (job, chunk width) and replayed */
-         double* xs = (double*)S.b_xt.p;
+         cudaStream_t s = lane_s[lane];                           // (shadows the main stream inside the chunk)
+         double* xs = lane_xs[lane];
+         double* ywork = lane_y[lane];
+         double* pbuf = lane_p[lane];
          launch_transpose_rhs(xcol, ldx, xs, S.n, nr, true, s);
          auto sweep = [&]() {
             if (job == JOB_FWD) {
@@ -1371,6 +1404,11 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          }
          launch_transpose_rhs(xcol, ldx, xs, S.n, nr, false, s);
          r0 += nr;
+         lane = (lane + 1) % nlanes;
+      }
+      if (nlanes == 2) {                                          // join
+         CUDA_TRY(cudaEventRecord(N.ev_lane_out, N.lane2));
+         CUDA_TRY(cudaStreamWaitEvent(s, N.ev_lane_out, 0));
       }
       CUDA_TRY(cudaGetLastError());
       if (host_x) CUDA_TRY(cudaMemcpyAsync(x, dx, xbytes, cudaMemcpyDeviceToHost, s));
