@@ -532,6 +532,17 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
    }
    std::vector<int> snap_host;
    int err = 0;
+   /* SPRAL_B200_TRACE_PANELS=2: a timeline of the level on both streams (events behind every update launch) */
+   struct TlRec { int p0; char what; cudaEvent_t a, b; int tiles; };
+   std::vector<TlRec> tl;
+   cudaEvent_t tl_base = nullptr;
+   const bool timeline = g_trace_panels && big && getenv("SPRAL_B200_TRACE_PANELS")[0] == '2';
+   if (timeline) { cudaEventCreate(&tl_base); cudaStreamSynchronize(N.stream2); cudaStreamSynchronize(s); cudaEventRecord(tl_base, s); }
+   auto tl_open = [&](cudaStream_t st) { cudaEvent_t e = nullptr; if (timeline) { cudaEventCreate(&e); cudaEventRecord(e, st); } return e; };
+   auto tl_close = [&](int p0, char what, cudaEvent_t a, cudaStream_t st, int tiles) {
+      if (!timeline) return;
+      cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tl.push_back({p0, what, a, e, tiles});
+   };
    bool bulk_pending = false;       // a bulk update is (possibly) still running on stream2
    int bulk_parity = 0;
    for (;;) {
@@ -540,6 +551,15 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       for (size_t i = 0; i < H.size(); ++i) if (!H[i].finished) act.push_back((int)i);
       if (act.empty()) {
          if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(s, N.ev_bulk_all, 0));     // join
+         if (timeline) {
+            cudaStreamSynchronize(N.stream2); cudaStreamSynchronize(s);
+            for (auto& r : tl) {
+               float t0 = 0, t1 = 0; cudaEventElapsedTime(&t0, tl_base, r.a); cudaEventElapsedTime(&t1, tl_base, r.b);
+               fprintf(stderr, "[timeline] p0 %5d %c tiles %5d  %9.3f -> %9.3f ms (%.3f)\n", r.p0, r.what, r.tiles, t0, t1, t1 - t0);
+               cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+            }
+            cudaEventDestroy(tl_base);
+         }
          break;
       }
       std::stable_sort(act.begin(), act.end(), [&](int a, int b) {
@@ -608,12 +628,14 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       }
       if (v2) {
          const int nseg = PW / panel_segment_width();
+         cudaEvent_t tle = tl_open(s);
          for (int seg = 0; seg < nseg; ++seg) {
             PROF(PC_DIAG, launch_panel_chain(d_fronts, d_flist, na_all, posdef, seg == 0, prm, s));
             PROF(PC_APPLY, launch_panel_tiles(d_fronts, d_rows, rows_prefix[na_all], posdef, prm, s));
             PROF(PC_COMMIT, launch_seg_commit(d_fronts, d_rows, rows_prefix[na_all], posdef, s));
             if (seg + 1 < nseg) PROF(PC_INNER, launch_update(d_fronts, d_inner, inner_prefix[na_all], UPD_SEG, Ti == 128, s));   // the tile size the list was built with
          }
+         tl_close(H[act[0]].p0, 'C', tle, s, rows_prefix[na_all]);
          take_snapshot();
          int maxrem = 0;
          for (int k = 0; k < na_all; ++k) {
@@ -746,7 +768,9 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       if (!outer.empty()) {
          MatTile* d_outer = upload(bump, outer, s);
          if (g_prof) g_prof->next_tiles = (int)outer.size();
+         cudaEvent_t tle = tl_open(s);
          PROF(PC_OUTER, launch_update(d_fronts, d_outer, (int)outer.size(), UPD_OUTER, big, s));
+         tl_close(H[act[0]].p0, 'U', tle, s, (int)outer.size());
       }
 #ifdef SPRAL_B200_SPLIT
       if (split_now) {
@@ -770,14 +794,18 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          MatTile* d_b = (MatTile*)((char*)bb.p + regs_bytes + a_bytes);
          if (!bulk.empty()) {
             CUDA_TRY(cudaMemcpyAsync(d_a, bulk.data(), bulk.size() * sizeof(MatTile), cudaMemcpyHostToDevice, s2));
+            cudaEvent_t tle = tl_open(s2);
             PROF_ON(PC_OUTER, s2, launch_update(d_fronts, d_a, (int)bulk.size(), UPD_EXPLICIT, big, s2,
                                                  g_bulk_ctas, (const int4*)bb.p));
+            tl_close(H[act[0]].p0, 'A', tle, s2, (int)bulk.size());
          }
          CUDA_TRY(cudaEventRecord(N.ev_bulk, s2));       // the panel after next has all its updates from this panel
          if (!bulk_b.empty()) {
             CUDA_TRY(cudaMemcpyAsync(d_b, bulk_b.data(), bulk_b.size() * sizeof(MatTile), cudaMemcpyHostToDevice, s2));
+            cudaEvent_t tle = tl_open(s2);
             PROF_ON(PC_OUTER, s2, launch_update(d_fronts, d_b, (int)bulk_b.size(), UPD_EXPLICIT, big, s2,
                                                  g_bulk_ctas, (const int4*)bb.p));
+            tl_close(H[act[0]].p0, 'B', tle, s2, (int)bulk_b.size());
          }
          CUDA_TRY(cudaEventRecord(N.ev_bulk_all, s2));
          bulk_pending = true;

@@ -1,0 +1,9 @@
+#!/bin/bash
+# half-tile update kernel (two CTAs per SM) against the one-CTA-per-SM kernel
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+for v in 0 1 2; do
+echo "UPD_HALF=$v: $(SPRAL_B200_UPD_HALF=$v SPRAL_B200_NOPROFILE=1 timeout 600 python tools/profile_factor.py 100 2>&1 | grep '^factor' | cut -c1-60 | tr '\n' ' ')"
+done
+SPRAL_B200_UPD_HALF=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "dense_fronts or doctored or sparse or cfg3" 2>&1 | tail -3
+SPRAL_B200_UPD_HALF=1 SPRAL_B200_NOPROFILE=1 SPRAL_B200_TRACE=1 SPRAL_B200_TRACE_PANELS=2 timeout 600 python tools/profile_factor.py 100 > gpurun_out/timeline25.out 2> gpurun_out/timeline25.log
