@@ -46,12 +46,7 @@ constexpr int NSTAGE = 4;
 #ifndef WS_BK
 #define WS_BK 32
 #endif
-#ifndef HALF_NS
-#define HALF_NS 2
-#endif
-#ifndef HALF_BK
-#define HALF_BK 32
-#endif
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
    return (uint32_t)__cvta_generic_to_shared(p);
@@ -140,29 +135,35 @@ __device__ __forceinline__ Region make_region(const Front* f, int mode, int T) {
 }
 
 /* Epilogue of one warp: thread holds rows r, r+1 of column c for NC x NR
- * 8x8 sub-tiles.  All loads of a column batch are issued before its stores
- * (a load after a possibly-aliasing store would serialise on memory latency). */
+ * 8x8 sub-tiles.  The loads of column batch j + 1 are issued before the stores of batch j (the compiler keeps a
+ * load behind a possibly-aliasing store, so batch after batch would pay one memory latency each). */
+template <int NR>
+__device__ __forceinline__ void load_old(const Region& g, double2 (&old)[NR], int c, int rfirst, int lane) {
+   #pragma unroll
+   for (int i = 0; i < NR; ++i) { old[i].x = 0.0; old[i].y = 0.0; }
+   if (!g.accumulate || c < g.c_lo || c >= g.c_hi) return;
+   const double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
+   #pragma unroll
+   for (int i = 0; i < NR; ++i) {
+      const int r = rfirst + i * 8 + 2 * (lane & 3);
+      const bool v0 = (r >= c) && (r < g.m);
+      const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
+      const double* p = Cc + r;
+      if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) old[i] = *reinterpret_cast<const double2*>(p);
+      else { if (v0) old[i].x = p[0]; if (v1) old[i].y = p[1]; }
+   }
+}
 template <int NC, int NR>
 __device__ __forceinline__ void store_tile(const Region& g, const double (&acc)[NC][NR][2],
       int r0, int c0, int rbase, int cbase, int lane) {
+   double2 old[2][NR];
+   load_old<NR>(g, old[0], c0 + cbase + (lane >> 2), r0 + rbase, lane);
    #pragma unroll
    for (int j = 0; j < NC; ++j) {
       const int c = c0 + cbase + j * 8 + (lane >> 2);
+      if (j + 1 < NC) load_old<NR>(g, old[(j + 1) & 1], c + 8, r0 + rbase, lane);
       if (c < g.c_lo || c >= g.c_hi) continue;
       double* Cc = g.C + (ptrdiff_t)c * (ptrdiff_t)g.ldc;
-      double2 old[NR];
-      #pragma unroll
-      for (int i = 0; i < NR; ++i) {
-         const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
-         const bool v0 = (r >= c) && (r < g.m);
-         const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
-         double* p = Cc + r;
-         old[i].x = 0.0; old[i].y = 0.0;
-         if (g.accumulate) {
-            if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) old[i] = *reinterpret_cast<const double2*>(p);
-            else { if (v0) old[i].x = p[0]; if (v1) old[i].y = p[1]; }
-         }
-      }
       #pragma unroll
       for (int i = 0; i < NR; ++i) {
          const int r = r0 + rbase + i * 8 + 2 * (lane & 3);
@@ -170,7 +171,7 @@ __device__ __forceinline__ void store_tile(const Region& g, const double (&acc)[
          const bool v1 = (r + 1 >= c) && (r + 1 < g.m);
          double* p = Cc + r;
          double2 o;
-         o.x = old[i].x - acc[j][i][0]; o.y = old[i].y - acc[j][i][1];
+         o.x = old[j & 1][i].x - acc[j][i][0]; o.y = old[j & 1][i].y - acc[j][i][1];
          if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) *reinterpret_cast<double2*>(p) = o;
          else { if (v0) p[0] = o.x; if (v1) p[1] = o.y; }
       }
@@ -496,118 +497,6 @@ k_update_ws(Front* fronts, const MatTile* work, int nwork, int mode, const int4*
    }
 }
 
-/* Half-tile variant of k_update_ws: a CTA of 4 consumer warps + the producer warp computes a T x T/2 half of an
- * output tile, and two such CTAs live on an SM (2 x ~100 KB of stages).  The halves of a tile run through their
- * K loops independently, so the epilogue of one CTA (read-modify-write of C: several microseconds in which its
- * warps issue no DMMA) is covered by the main loop of the other one; one warp per SM sub-partition already
- * saturates the FP64 tensor pipe (a DMMA occupies it for 16 cycles).  A K = 256 panel update spends a fifth of
- * a tile's time in prologue and epilogue with one CTA per SM.  Work item 2 i + h is half h of tile i. */
-template <int T, int NS, int BKT>
-__global__ void __launch_bounds__(160, 2)
-k_update_half(Front* fronts, const MatTile* work, int nwork, int mode, const int4* xregs) {
-   constexpr int TC = T / 2;
-   constexpr int LDA_S = T + 4, LDB_S = TC + 4;          // both = 4 mod 16: conflict-free fragment loads
-   constexpr int NWR = 2, NWC = 2, NCONS = 4;
-   constexpr int WTR = T / NWR, WTC = TC / NWC;
-   constexpr int NR = WTR / 8, NC = WTC / 8;
-   constexpr int STAGE_DOUBLES = BKT * (LDA_S + LDB_S);
-
-   extern __shared__ __align__(128) unsigned char smem_raw[];
-   double* tiles = reinterpret_cast<double*>(smem_raw);
-   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_DOUBLES * sizeof(double));
-   uint64_t* empty = full + NS;
-
-   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   if (tid == 0) {
-      for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-   }
-   __syncthreads();
-
-   if (warp == NCONS) {
-      /* ---------------- producer warp ---------------- */
-      int g = 0;
-      for (int item = blockIdx.x; item < 2 * nwork; item += gridDim.x) {
-         TileJob pj;
-         if (!load_job<T, BKT>(fronts, work, item >> 1, mode, pj, xregs)) continue;
-         const int c0 = pj.c0 + (item & 1) * TC;
-         const Region& rg = pj.g;
-         if (c0 + TC <= rg.c_lo || c0 >= rg.c_hi) continue;
-         const int klen = rg.k1 - rg.k0;
-         const int rowsA = min(T, rg.rows_alloc - pj.r0);   // even
-         const int rowsB = min(TC, rg.rows_alloc - c0);
-         for (int chunk = 0; chunk < pj.nchunk; ++chunk, ++g) {
-            const int s = g % NS;
-            if (g >= NS) mbar_wait(&empty[s], (uint32_t)(((g / NS) & 1) ^ 1));
-            const int kc = min(BKT, klen - chunk * BKT);
-            double* st = tiles + (size_t)s * STAGE_DOUBLES;
-            double* stb = st + BKT * LDA_S;
-            const int kc4 = (kc + 3) & ~3;
-            if (kc4 != kc) {              // zero the K tail of both operands
-               for (int col = kc; col < kc4; ++col) {
-                  for (int i = lane; i < T; i += 32) st[col * LDA_S + i] = 0.0;
-                  for (int i = lane; i < TC; i += 32) stb[col * LDB_S + i] = 0.0;
-               }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kc * (rowsA + rowsB) * sizeof(double)));
-            __syncwarp();
-            const double* Ag = rg.A + pj.r0 + (size_t)(rg.k0 + chunk * BKT) * rg.lda;
-            const double* Bg = rg.B + c0 + (size_t)(rg.k0 + chunk * BKT) * rg.ldb;
-            for (int idx = lane; idx < 2 * kc; idx += 32) {
-               int op = idx >= kc;
-               int col = idx - op * kc;
-               if (op) bulk_g2s(stb + col * LDB_S, Bg + (size_t)col * rg.ldb, rowsB * sizeof(double), &full[s]);
-               else    bulk_g2s(st + col * LDA_S, Ag + (size_t)col * rg.lda, rowsA * sizeof(double), &full[s]);
-            }
-         }
-      }
-      return;
-   }
-
-   /* ---------------- consumer warps ---------------- */
-   const int wr = warp % NWR, wc = warp / NWR;
-   const int rbase = wr * WTR, cbase = wc * WTC;
-   int g = 0;
-   for (int item = blockIdx.x; item < 2 * nwork; item += gridDim.x) {
-      TileJob cj;
-      if (!load_job<T, BKT>(fronts, work, item >> 1, mode, cj, xregs)) continue;
-      const Region& rg = cj.g;
-      const int r0 = cj.r0, c0 = cj.c0 + (item & 1) * TC;
-      if (c0 + TC <= rg.c_lo || c0 >= rg.c_hi) continue;
-      const bool warp_active = (r0 + rbase + WTR > c0 + cbase) && (r0 + rbase < rg.m)
-                               && (c0 + cbase < rg.c_hi) && (c0 + cbase + WTC > rg.c_lo);
-      const int klen = rg.k1 - rg.k0;
-      if (warp_active) prefetch_tile<NC, NR>(rg, r0, c0, rbase, cbase, lane);
-      double acc[NC][NR][2];
-      #pragma unroll
-      for (int j = 0; j < NC; ++j)
-         #pragma unroll
-         for (int i = 0; i < NR; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
-
-      for (int chunk = 0; chunk < cj.nchunk; ++chunk, ++g) {
-         const int s = g % NS;
-         mbar_wait(&full[s], (uint32_t)((g / NS) & 1));
-         if (warp_active) {
-            const int kc4 = (min(BKT, klen - chunk * BKT) + 3) & ~3;
-            const double* As = tiles + (size_t)s * STAGE_DOUBLES + (lane & 3) * LDA_S + rbase + (lane >> 2);
-            const double* Bs = tiles + (size_t)s * STAGE_DOUBLES + BKT * LDA_S + (lane & 3) * LDB_S + cbase + (lane >> 2);
-            mma_chunk<NC, NR, BKT, LDA_S, LDB_S>(acc, As, Bs, kc4);
-         }
-         __syncwarp();
-         if (lane == 0) mbar_arrive(&empty[s]);      // this warp is done with stage s
-      }
-
-      if (!warp_active) continue;
-      store_tile<NC, NR>(rg, acc, r0, c0, rbase, cbase, lane);
-   }
-}
-
-template <int T, int NS, int BKT>
-constexpr size_t update_half_smem_bytes() {
-   return (size_t)NS * BKT * (T + 4 + T / 2 + 4) * sizeof(double) + 2 * NS * sizeof(uint64_t);
-}
-
 template <int T, int NS, int BKT = BK>
 constexpr size_t update_smem_bytes() {
    return (size_t)NS * 2 * BKT * (T + 4) * sizeof(double) + 2 * NS * sizeof(uint64_t);
@@ -622,17 +511,10 @@ int update_tile_size(bool big_tiles) { return big_tiles ? 128 : 64; }
 int inner_tile_size(bool big_tiles) { return (big_tiles && getenv("SPRAL_B200_INNER128")) ? 128 : 64; }
 
 static int g_num_sms = 0;
-static int g_upd_half = 1;          // SPRAL_B200_UPD_HALF=0: one 128 x 128 tile per CTA, one CTA per SM (k_update_ws)
 
 void configure_update_kernels() {
    cudaFuncSetAttribute(k_update_ws<128, 2, 4, WS_NS, WS_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                         (int)update_smem_bytes<128, WS_NS, WS_BK>());
-   cudaFuncSetAttribute(k_update_half<128, HALF_NS, HALF_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)update_half_smem_bytes<128, HALF_NS, HALF_BK>());
-   cudaFuncSetAttribute(k_update_half<128, HALF_NS, HALF_BK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-   cudaFuncSetAttribute(k_update_half<128, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_half_smem_bytes<128, 4, 16>());
-   cudaFuncSetAttribute(k_update_half<128, 4, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-   if (const char* e = getenv("SPRAL_B200_UPD_HALF")) g_upd_half = atoi(e);
    cudaFuncSetAttribute(k_update<64, 2, 2, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                         (int)update_smem_bytes<64, NSTAGE>());
    cudaFuncSetAttribute(k_update<64, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -653,14 +535,8 @@ void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mod
       int grid = std::min(nwork, sms * 5);
       k_update<64, 2, 2, 2><<<grid, 128, update_smem_bytes<64, 2>(), s>>>(fronts, work, nwork, (int)mode);
    } else if (big_tiles) {
-      if (g_upd_half) {
-         int grid = max_ctas < 0 ? 2 * nwork : std::min(2 * nwork, 2 * sms);      // max_ctas < 0: one half tile per CTA (not persistent)
-         if (g_upd_half == 2) k_update_half<128, 4, 16><<<grid, 160, update_half_smem_bytes<128, 4, 16>(), s>>>(fronts, work, nwork, (int)mode, xregs);
-         else k_update_half<128, HALF_NS, HALF_BK><<<grid, 160, update_half_smem_bytes<128, HALF_NS, HALF_BK>(), s>>>(fronts, work, nwork, (int)mode, xregs);
-      } else {
       int grid = max_ctas < 0 ? nwork : std::min(nwork, sms);      // max_ctas < 0: one tile per CTA (not persistent)
       k_update_ws<128, 2, 4, WS_NS, WS_BK><<<grid, 384, update_smem_bytes<128, WS_NS, WS_BK>(), s>>>(fronts, work, nwork, (int)mode, xregs);
-      }
    } else {
       int grid = std::min(nwork, sms * 3);
       k_update<64, 2, 2, NSTAGE><<<grid, 128, update_smem_bytes<64, NSTAGE>(), s>>>(fronts, work, nwork, (int)mode);
