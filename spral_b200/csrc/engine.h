@@ -162,9 +162,18 @@ void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowT
 
 /* wide sweeps for levels of large fronts (solve_wide.h; opt-in) */
 int solve_wide_block();
+/* Streams and events of the look-ahead inside a wide sweep: the G work on the rows of the next block stays on the
+ * sweep's stream, the rest runs on the two far streams beside the following T kernels (solve_wide.h: SW_NEAR / SW_FAR).
+ * The backward sweep then needs TWO accumulators per front (pbuf of 2 x count x 256 x nr doubles). */
+struct SolveAux {
+   cudaStream_t far[2] = {nullptr, nullptr};
+   cudaEvent_t evT[4] = {nullptr, nullptr, nullptr, nullptr}, evF[4] = {nullptr, nullptr, nullptr, nullptr};
+   void create();
+   void destroy();
+};
 void launch_fwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s);
+      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s, SolveAux* aux = nullptr);
 void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s);
+      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s, SolveAux* aux = nullptr);
 
 } // namespace b200

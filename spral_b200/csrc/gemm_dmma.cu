@@ -535,7 +535,9 @@ void launch_update(Front* fronts, const MatTile* work, int nwork, UpdateMode mod
       int grid = std::min(nwork, sms * 5);
       k_update<64, 2, 2, 2><<<grid, 128, update_smem_bytes<64, 2>(), s>>>(fronts, work, nwork, (int)mode);
    } else if (big_tiles) {
-      int grid = max_ctas < 0 ? nwork : std::min(nwork, sms);      // max_ctas < 0: one tile per CTA (not persistent)
+      /* max_ctas < 0: one tile per CTA, not persistent (the bulk stream: kernels of the urgent stream get an SM whenever
+       * a CTA retires; 2 .. 6 tiles per CTA measured no faster, tools/gpu_call_r02_31.sh) */
+      int grid = max_ctas < 0 ? nwork : std::min(nwork, sms);
       k_update_ws<128, 2, 4, WS_NS, WS_BK><<<grid, 384, update_smem_bytes<128, WS_NS, WS_BK>(), s>>>(fronts, work, nwork, (int)mode, xregs);
    } else {
       int grid = std::min(nwork, sms * 3);

@@ -467,22 +467,26 @@ k_fwd_wide_T(const SolveFront* fronts, int first, int count, int blk, const doub
 
 template <int NR>
 __global__ void __launch_bounds__(SW_GT)
-k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork) {
+k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork,
+      int part, int first) {
    extern __shared__ double smem_dyn[];
-   const RowTile w = work[blockIdx.x / SW_FSPLIT];
+   /* near launches: two tiles per front of the level, no work list */
+   const RowTile w = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / (2 * SW_FSPLIT), ((int)blockIdx.x / SW_FSPLIT) & 1}
+                                     : work[blockIdx.x / SW_FSPLIT];
    const SolveFront f = fronts[w.front];
    SolveDevCtx cx;
-   fwd_wide_G<NR>(cx, f, w.tile, blk, (int)(blockIdx.x % SW_FSPLIT), x, ywork, smem_dyn);
+   fwd_wide_G<NR>(cx, f, w.tile, blk, (int)(blockIdx.x % SW_FSPLIT), x, ywork, smem_dyn, part);
 }
 
 template <int NR>
 __global__ void __launch_bounds__(SW_GT)
-k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int first, int step, const double* __restrict__ x, double* __restrict__ pbuf) {
+k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int first, int step, const double* __restrict__ x, double* __restrict__ pbuf,
+      int part) {
    extern __shared__ double smem_dyn[];
-   const RowTile w = work[blockIdx.x];
+   const RowTile w = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / 2, (int)blockIdx.x & 1} : work[blockIdx.x];
    const SolveFront f = fronts[w.front];
    SolveDevCtx cx;
-   bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)(w.front - first) * SWB * NR, smem_dyn);
+   bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)(w.front - first) * SWB * NR, smem_dyn, part);
 }
 
 template <int NR, int NRT, bool POSDEF>
@@ -507,11 +511,11 @@ template <int NR> constexpr size_t sg_f_smem_bytes() { return ((size_t)2 * 32 * 
 template <int NR> constexpr size_t sg_b_smem_bytes() { return ((size_t)2 * 32 * SG_LLD + (size_t)RT * sg_xld<NR>()) * sizeof(double); }
 
 struct SgChunk { double2 v[8]; };
-/* chunk c of the tile: columns kb + 32 c .. + 31, rows r0 .. r0 + 127; rows outside [rlo, m) and columns >= kb + w read 0 */
-__device__ __forceinline__ void sg_load(SgChunk& ck, const SolveFront& f, int kb, int w, int r0, int rlo, int c, int tid) {
+/* chunk c of the tile: columns kb + 32 c .. + 31, rows r0 .. r0 + 127; rows outside [rlo, rhi) and columns >= kb + w read 0 */
+__device__ __forceinline__ void sg_load(SgChunk& ck, const SolveFront& f, int kb, int w, int r0, int rlo, int rhi, int c, int tid) {
    const int rr = (tid & 63) * 2, cq = tid >> 6;
    const int r = r0 + rr;
-   const bool a0 = r >= rlo && r < f.m, a1 = r + 1 >= rlo && r + 1 < f.m;
+   const bool a0 = r >= rlo && r < rhi, a1 = r + 1 >= rlo && r + 1 < rhi;
    const size_t ldl = (size_t)f.ldl;
    #pragma unroll
    for (int q = 0; q < 8; ++q) {
@@ -533,15 +537,18 @@ __device__ __forceinline__ void sg_store(const SgChunk& ck, double* Ls, int tid)
 
 template <int NR>
 __global__ void __launch_bounds__(SW_GT)
-k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork) {
+k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork,
+      int part, int first) {
    extern __shared__ __align__(16) double smem_dyn[];
-   const RowTile wk = work[blockIdx.x];
+   const RowTile wk = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / 2, (int)blockIdx.x & 1} : work[blockIdx.x];
    const SolveFront f = fronts[wk.front];
    const int kb = blk * SWB;
    if (kb >= f.nelim) return;
    const int w = min(SWB, f.nelim - kb);
-   const int r0 = wk.tile * RT;
-   if (r0 + RT <= kb + w || r0 >= f.m) return;
+   int rlo, rhi;
+   sw_part_rows(f, kb, w, part, rlo, rhi);
+   const int r0 = (wk.tile + (part == SW_NEAR ? rlo / RT : 0)) * RT;
+   if (r0 + RT <= rlo || r0 >= rhi) return;
    constexpr int YLD = sg_xld<NR>();
    double* Ls = smem_dyn;
    double* ys = smem_dyn + 2 * 32 * SG_LLD;
@@ -553,7 +560,7 @@ k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double*
       for (int k = 0; k < NR; ++k) ys[e * YLD + k] = (g >= 0) ? ywork[XI(g, k)] : 0.0;
    }
    SgChunk ck;
-   sg_load(ck, f, kb, w, r0, kb + w, 0, tid);
+   sg_load(ck, f, kb, w, r0, rlo, rhi, 0, tid);
    sg_store(ck, Ls, tid);
    __syncthreads();
    const int rbase = warp * 16;
@@ -563,7 +570,7 @@ k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double*
       #pragma unroll
       for (int i = 0; i < 2; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
    for (int c = 0; c < nchunk; ++c) {
-      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, kb + w, c + 1, tid);
+      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, rlo, rhi, c + 1, tid);
       const double* Lc = Ls + (c & 1) * 32 * SG_LLD;
       #pragma unroll
       for (int kk = 0; kk < 32; kk += 4) {
@@ -586,7 +593,7 @@ k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double*
       #pragma unroll
       for (int e = 0; e < 2; ++e) {
          const int r = r0 + rbase + i * 8 + 2 * (lane & 3) + e;
-         if (r >= kb + w && r < f.m) {
+         if (r >= rlo && r < rhi) {
             const int g = row_index(f, r);
             #pragma unroll
             for (int j = 0; j < NR / 8; ++j) atomicAdd(&x[XI(g, j * 8 + (lane >> 2))], -acc[j][i][e]);
@@ -597,16 +604,18 @@ k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double*
 template <int NR>
 __global__ void __launch_bounds__(SW_GT)
 k_bwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int first, int step, const double* __restrict__ x,
-      double* __restrict__ pbuf) {
+      double* __restrict__ pbuf, int part) {
    extern __shared__ __align__(16) double smem_dyn[];
-   const RowTile wk = work[blockIdx.x];
+   const RowTile wk = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / 2, (int)blockIdx.x & 1} : work[blockIdx.x];
    const SolveFront f = fronts[wk.front];
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
    const int kb = b * SWB;
    const int w = min(SWB, f.nelim - kb);
-   const int r0 = wk.tile * RT;
-   if (r0 + RT <= kb + w || r0 >= f.m) return;
+   int rlo, rhi;
+   sw_part_rows(f, kb, w, part, rlo, rhi);
+   const int r0 = (wk.tile + (part == SW_NEAR ? rlo / RT : 0)) * RT;
+   if (r0 + RT <= rlo || r0 >= rhi) return;
    constexpr int XLD = sg_xld<NR>();
    double* Ls = smem_dyn;
    double* xs = smem_dyn + 2 * 32 * SG_LLD;
@@ -615,18 +624,18 @@ k_bwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int first, int s
    const int nchunk = (w + 31) / 32;
    for (int e = tid; e < RT; e += SW_GT) {
       const int r = r0 + e;
-      const bool act = r >= kb + w && r < f.m;
+      const bool act = r >= rlo && r < rhi;
       const int g = act ? row_index(f, r) : 0;
       #pragma unroll
       for (int k = 0; k < NR; ++k) xs[e * XLD + k] = act ? x[XI(g, k)] : 0.0;
    }
    SgChunk ck;
-   sg_load(ck, f, kb, w, r0, kb + w, 0, tid);
+   sg_load(ck, f, kb, w, r0, rlo, rhi, 0, tid);
    sg_store(ck, Ls, tid);
    __syncthreads();
    constexpr int NB = NR / 16;               // 8 x 8 output blocks per warp and chunk: (NR / 8 right-hand-side groups) x 4 column groups / 8 warps
    for (int c = 0; c < nchunk; ++c) {
-      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, kb + w, c + 1, tid);
+      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, rlo, rhi, c + 1, tid);
       const double* Lc = Ls + (c & 1) * 32 * SG_LLD;
       double acc[NB][2];
       int jg[NB], cg[NB];
@@ -661,58 +670,102 @@ template <int NR> constexpr int t_slice() { return NR > 16 ? 16 : NR; }
 
 template <int NR, bool POSDEF>
 void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork, int nblk,
-      double* x, double* ywork, cudaStream_t s) {
+      double* x, double* ywork, cudaStream_t s, SolveAux* aux) {
    static bool configured = false;
    constexpr int TS = t_slice<NR>();
+   constexpr bool MMA = UseMma<NR>::value;
    const size_t smT = sw_T_smem_doubles<TS>() * sizeof(double);
-   if constexpr (UseMma<NR>::value) {
-      const size_t smG = sg_f_smem_bytes<NR>();
-      if (!configured) {
-         cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
-         cudaFuncSetAttribute(k_fwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
-         configured = true;
-      }
-      for (int b = 0; b < nblk; ++b) {
-         k_fwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, b, x, ywork); COUNT_LAUNCH();
-         k_fwd_wide_G_mma<NR><<<nwork, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
-      }
-   } else {
-      const size_t smG = sw_fG_smem_doubles<NR>() * sizeof(double);
-      if (!configured) {
-         cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
-         cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
-         configured = true;
-      }
-      for (int b = 0; b < nblk; ++b) {
-         k_fwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, b, x, ywork); COUNT_LAUNCH();
-         k_fwd_wide_G<NR><<<nwork * SW_FSPLIT, SW_GT, smG, s>>>(fronts, work, b, x, ywork); COUNT_LAUNCH();
-      }
+   size_t smG;
+   if constexpr (MMA) smG = sg_f_smem_bytes<NR>(); else smG = sw_fG_smem_doubles<NR>() * sizeof(double);
+   if (!configured) {
+      cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+      if constexpr (MMA) cudaFuncSetAttribute(k_fwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+      else cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+      configured = true;
    }
+   auto G = [&](int b, int part, cudaStream_t st) {
+      if constexpr (MMA) {
+         const int grid = part == SW_NEAR ? 2 * count : nwork;
+         k_fwd_wide_G_mma<NR><<<grid, SW_GT, smG, st>>>(fronts, work, b, x, ywork, part, first);
+      } else {
+         const int grid = (part == SW_NEAR ? 2 * count : nwork) * SW_FSPLIT;
+         k_fwd_wide_G<NR><<<grid, SW_GT, smG, st>>>(fronts, work, b, x, ywork, part, first);
+      }
+      COUNT_LAUNCH();
+   };
+   auto T = [&](int b) {
+      k_fwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, b, x, ywork); COUNT_LAUNCH();
+   };
+   if (!aux || nblk < 2) {
+      for (int b = 0; b < nblk; ++b) { T(b); G(b, SW_ALL, s); }
+      return;
+   }
+   /* T(b) needs the near part of block b - 1 (same stream) and the far parts of the blocks up to b - 2 */
+   for (int b = 0; b < nblk; ++b) {
+      if (b >= 2) cudaStreamWaitEvent(s, aux->evF[(b - 2) & 3], 0);
+      T(b);
+      cudaEventRecord(aux->evT[b & 3], s);
+      cudaStream_t fs = aux->far[b & 1];
+      cudaStreamWaitEvent(fs, aux->evT[b & 3], 0);
+      G(b, SW_FAR, fs);
+      cudaEventRecord(aux->evF[b & 3], fs);
+      G(b, SW_NEAR, s);
+   }
+   cudaStreamWaitEvent(s, aux->evF[(nblk - 2) & 3], 0);
+   cudaStreamWaitEvent(s, aux->evF[(nblk - 1) & 3], 0);
 }
 
-/* pbuf: one SWB x NR accumulator per front of the level, all zero when the sweep of the level starts (the T kernel
- * clears what it consumed) */
+/* pbuf: one SWB x NR accumulator per front of the level (two with look-ahead: blocks alternate between them), all
+ * zero when the sweep of the level starts (the T kernel clears what it consumed) */
 template <int NR, bool POSDEF>
 void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      const int* wbeg, int nblk, double* x, double* pbuf, cudaStream_t s) {
+      const int* wbeg, int nblk, double* x, double* pbuf, cudaStream_t s, SolveAux* aux) {
    static bool configured = false;
    constexpr int TS = t_slice<NR>();
+   constexpr bool MMA = UseMma<NR>::value;
    const size_t smT = sw_T_smem_doubles<TS>() * sizeof(double);
    if (!configured) {
       cudaFuncSetAttribute(k_bwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
-      if constexpr (UseMma<NR>::value)
+      if constexpr (MMA)
          cudaFuncSetAttribute(k_bwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_b_smem_bytes<NR>());
       configured = true;
    }
-   cudaMemsetAsync(pbuf, 0, (size_t)count * SWB * NR * sizeof(double), s);
-   for (int st = 0; st < nblk; ++st) {
-      if constexpr (UseMma<NR>::value) {
-         k_bwd_wide_G_mma<NR><<<nwork, SW_GT, sg_b_smem_bytes<NR>(), s>>>(fronts, work, first, st, x, pbuf);
-      } else {
-         k_bwd_wide_G<NR><<<nwork, SW_GT, 0, s>>>(fronts, work, first, st, x, pbuf);
-      }
+   const size_t accsz = (size_t)count * SWB * NR;
+   auto G = [&](int st, int part, double* acc, cudaStream_t strm) {
+      const int grid = part == SW_NEAR ? 2 * count : nwork;
+      if constexpr (MMA) k_bwd_wide_G_mma<NR><<<grid, SW_GT, sg_b_smem_bytes<NR>(), strm>>>(fronts, work, first, st, x, acc, part);
+      else k_bwd_wide_G<NR><<<grid, SW_GT, 0, strm>>>(fronts, work, first, st, x, acc, part);
       COUNT_LAUNCH();
-      k_bwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, st, x, pbuf); COUNT_LAUNCH();
+   };
+   auto T = [&](int st, double* acc) {
+      k_bwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, st, x, acc); COUNT_LAUNCH();
+   };
+   if (!aux || nblk < 2) {
+      cudaMemsetAsync(pbuf, 0, accsz * sizeof(double), s);
+      for (int st = 0; st < nblk; ++st) { G(st, SW_ALL, pbuf, s); T(st, pbuf); }
+      return;
+   }
+   /* T(st) needs the near part of its block (the rows T(st - 1) has just solved: same stream) and the far part, which
+    * only reads what T(st - 2) and earlier left and therefore runs two steps ahead on the far streams */
+   cudaMemsetAsync(pbuf, 0, 2 * accsz * sizeof(double), s);
+   cudaEventRecord(aux->evT[3], s);
+   for (int st = 0; st < 2; ++st) {
+      cudaStreamWaitEvent(aux->far[st], aux->evT[3], 0);
+      G(st, SW_FAR, pbuf + st * accsz, aux->far[st]);
+      cudaEventRecord(aux->evF[st], aux->far[st]);
+   }
+   for (int st = 0; st < nblk; ++st) {
+      double* acc = pbuf + (st & 1) * accsz;
+      if (st >= 1) G(st, SW_NEAR, acc, s);
+      cudaStreamWaitEvent(s, aux->evF[st & 3], 0);
+      T(st, acc);
+      if (st + 2 < nblk) {
+         cudaEventRecord(aux->evT[st & 3], s);
+         cudaStream_t fs = aux->far[st & 1];
+         cudaStreamWaitEvent(fs, aux->evT[st & 3], 0);
+         G(st + 2, SW_FAR, acc, fs);
+         cudaEventRecord(aux->evF[(st + 2) & 3], fs);
+      }
    }
 }
 
@@ -765,23 +818,39 @@ int solve_wide_block() { return SWB; }
 
 #define SW_DISPATCH(NRV, CALL_T, CALL_F) case NRV: if (posdef) { CALL_T; } else { CALL_F; } break
 void launch_fwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s) {
+      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s, SolveAux* aux) {
    if (nwork == 0 || nblk == 0 || count == 0) return;
-#define SW_F(NRV) SW_DISPATCH(NRV, (fwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, nblk, x, ywork, s)), \
-                                   (fwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, nblk, x, ywork, s)))
+#define SW_F(NRV) SW_DISPATCH(NRV, (fwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, nblk, x, ywork, s, aux)), \
+                                   (fwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, nblk, x, ywork, s, aux)))
    switch (nr) { SW_F(64); SW_F(32); SW_F(16); SW_F(8); SW_F(4); SW_F(2); default: SW_F(1); }
 #undef SW_F
 }
 
 void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s) {
+      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s, SolveAux* aux) {
    if (nwork == 0 || nblk == 0 || count == 0) return;
-#define SW_B(NRV) SW_DISPATCH(NRV, (bwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s)), \
-                                   (bwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s)))
+#define SW_B(NRV) SW_DISPATCH(NRV, (bwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s, aux)), \
+                                   (bwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s, aux)))
    switch (nr) { SW_B(64); SW_B(32); SW_B(16); SW_B(8); SW_B(4); SW_B(2); default: SW_B(1); }
 #undef SW_B
 }
 #undef SW_DISPATCH
+
+void SolveAux::create() {
+   if (far[0]) return;
+   int least = 0, greatest = 0;
+   cudaDeviceGetStreamPriorityRange(&least, &greatest);
+   for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&far[i], cudaStreamNonBlocking, least);
+   for (int i = 0; i < 4; ++i) {
+      cudaEventCreateWithFlags(&evT[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&evF[i], cudaEventDisableTiming);
+   }
+}
+void SolveAux::destroy() {
+   if (!far[0]) return;
+   for (int i = 0; i < 2; ++i) { cudaStreamSynchronize(far[i]); cudaStreamDestroy(far[i]); far[i] = nullptr; }
+   for (int i = 0; i < 4; ++i) { cudaEventDestroy(evT[i]); cudaEventDestroy(evF[i]); }
+}
 
 void configure_solve_kernels() {
    cudaFuncSetAttribute(k_bwd_reduce<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduce_smem<32>());

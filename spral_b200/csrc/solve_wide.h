@@ -93,6 +93,16 @@ SW_FN void sw_mma_update(Ctx& cx, double* xs, const double* ls, int jb, int lo, 
          for (int e = 0; e < 2; ++e) xs[(size_t)(rg + 2 * (lane & 3) + e) * XLD + 8 * j + (lane >> 2)] -= acc[j][e];
    }
 }
+/* Look-ahead (two streams, solve_kernels.cu): the G work of a block is split into the rows of the NEXT block of the
+ * front ("near": the only rows the next T kernel waits for) and the rest ("far": runs beside the following T kernels).
+ * part 0 = all rows below the block, 1 = near, 2 = far; [rlo, rhi) are the rows of the front a G kernel may touch. */
+enum { SW_ALL = 0, SW_NEAR = 1, SW_FAR = 2 };
+SW_FN void sw_part_rows(const SolveFront& f, int kb, int w, int part, int& rlo, int& rhi) {
+   const int below = kb + w;
+   const int ne = below < f.nelim ? sw_min(below + SWB, f.nelim) : below;       // end of the next block's rows
+   rlo = part == SW_FAR ? ne : below;
+   rhi = part == SW_NEAR ? ne : f.m;
+}
 constexpr int SW_GT = 256;   // threads of a G kernel CTA
 /* forward G: ys [SWB * NR] + the partial sums of the second column half [RT * NR] doubles */
 template <int NR> constexpr size_t sw_fG_smem_doubles() { return (size_t)(SWB / 2) * NR + (size_t)RT * NR; }
@@ -194,12 +204,16 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
  * (atomics).  Two CTAs per tile: twice as many bytes in flight per SM on the levels that have few tiles. */
 constexpr int SW_FSPLIT = 2;
 template <int NR, class Ctx>
-SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, int ch, double* x, const double* ywork, double* smem) {
+SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, int ch, double* x, const double* ywork, double* smem,
+      int rpart = SW_ALL) {
    const int kb = blk * SWB;
    if (kb >= f.nelim) return;
    const int w = sw_min(SWB, f.nelim - kb);
+   int rlo, rhi;
+   sw_part_rows(f, kb, w, rpart, rlo, rhi);
+   if (rpart == SW_NEAR) tile += rlo / RT;           // near launches count the tiles from the first row below the block
    const int r0 = tile * RT;
-   if (r0 + RT <= kb + w || r0 >= f.m) return;
+   if (r0 + RT <= rlo || r0 >= rhi) return;
    constexpr int CH = SWB / SW_FSPLIT;              // columns of this CTA
    const int c0 = ch * CH;
    if (c0 >= w) return;
@@ -215,7 +229,7 @@ SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, int ch, d
    cx.sync();
    const int rl = t & (RT - 1), h = t / RT;
    const int r = r0 + rl;
-   const bool active = r >= kb + w && r < f.m;
+   const bool active = r >= rlo && r < rhi;
    double acc[NR];
    #pragma unroll
    for (int k = 0; k < NR; ++k) acc[k] = 0.0;
@@ -261,13 +275,17 @@ SW_FN int sw_bwd_block(const SolveFront& f, int step) {
  * thread.  The lane sums of CG columns are reduced with shuffles and added to the front's accumulator `acc`
  * (SWB x NR doubles, zero when the step starts; several tiles add into it: atomics). */
 template <int NR, class Ctx>
-SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const double* x, double* acc, double* /*smem*/) {
+SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const double* x, double* acc, double* /*smem*/,
+      int part = SW_ALL) {
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
    const int kb = b * SWB;
    const int w = sw_min(SWB, f.nelim - kb);
+   int rlo, rhi;
+   sw_part_rows(f, kb, w, part, rlo, rhi);
+   if (part == SW_NEAR) tileidx += rlo / RT;
    const int r0 = tileidx * RT;
-   if (r0 + RT <= kb + w || r0 >= f.m) return;      // no row of this tile below the block
+   if (r0 + RT <= rlo || r0 >= rhi) return;         // no row of this tile in the part below the block
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
    const size_t ldl = (size_t)f.ldl;
    double xv[4][NR];
@@ -275,7 +293,7 @@ SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const
    #pragma unroll
    for (int q = 0; q < 4; ++q) {
       const int r = r0 + lane + 32 * q;
-      act[q] = r >= kb + w && r < f.m;
+      act[q] = r >= rlo && r < rhi;
       const int g = act[q] ? sw_row_index(f, r) : 0;
       #pragma unroll
       for (int k = 0; k < NR; ++k) xv[q][k] = act[q] ? x[SW_XI(g, k)] : 0.0;

@@ -48,6 +48,7 @@ static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative
 static int g_solve_wide = 1;         // 256-column sweeps (solve_wide.h; SPRAL_B200_SOLVE_WIDE=0: 32-column steps everywhere) on
                                      // levels whose largest front has at least SPRAL_B200_SOLVE_WIDE_MIN (8) 32-column steps
 static int g_solve_wide_min = 8;
+static bool g_solve_lookahead = true; // SPRAL_B200_SOLVE_LOOKAHEAD=0: the wide sweeps on one stream
 static bool g_trace_panels = false;  // SPRAL_B200_TRACE_PANELS=1: per-panel trace lines on stderr (host time between panels)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
 static int g_bulk_ctas = 0;          // SMs given to the overlapped bulk update (SPRAL_B200_BULK_CTAS); < 0: one CTA per tile
@@ -405,6 +406,7 @@ struct Numeric {
    cudaStream_t stream3 = nullptr;     // pushes of the distributed front's panels to the helpers
 #endif
    cudaStream_t lane2 = nullptr;       // second lane of the solves
+   SolveAux solve_aux[2];              // look-ahead streams of the wide sweeps, one set per lane
    cudaEvent_t ev_lane_in = nullptr, ev_lane_out = nullptr;
    ~Numeric() {
       if (!S) return;
@@ -416,6 +418,7 @@ struct Numeric {
       if (stream) cudaStreamSynchronize(stream);
       if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
       if (lane2) { cudaStreamSynchronize(lane2); cudaStreamDestroy(lane2); }
+      solve_aux[0].destroy(); solve_aux[1].destroy();
       if (ev_lane_in) cudaEventDestroy(ev_lane_in);
       if (ev_lane_out) cudaEventDestroy(ev_lane_out);
       for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -868,6 +871,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    if (const char* e = getenv("SPRAL_B200_SOLVE_GRAPHS")) g_solve_graphs = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_COOP")) g_solve_coop = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_WIDE")) g_solve_wide = atoi(e);
+   if (const char* e = getenv("SPRAL_B200_SOLVE_LOOKAHEAD")) g_solve_lookahead = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_WIDE_MIN")) g_solve_wide_min = std::max(1, atoi(e));
    g_bulk_ctas = g_bulk_prio ? -1 : device_sm_count() - 28;
    if (const char* e = getenv("SPRAL_B200_BULK_CTAS")) g_bulk_ctas = atoi(e);
@@ -1305,6 +1309,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
    if (S.nloc == 0 || nrhs == 0) return 0;
    try {
       std::lock_guard<std::mutex> lock(S.mtx);
+      const auto t_solve0 = std::chrono::steady_clock::now();
       CUDA_TRY(cudaSetDevice(S.device));
       cudaStream_t s = N.stream;
       const bool posdef = N.posdef;
@@ -1326,13 +1331,13 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          if (!g_solve_wide || N.lvl_steps[lev] < (nr >= 16 ? 1 : g_solve_wide_min)) return false;
          /* the backward sweep keeps one 256 x nr accumulator per front of the level */
          size_t nfr = (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]);
-         return nfr * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
+         return 2 * nfr * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
       };
       if (job == JOB_DIAG_BWD || job == JOB_BWD) {
          size_t need = std::max<size_t>(N.max_level_work, 1) * solve_block() * 32 * sizeof(double);      // 32-column kernels: per tile
          for (int lev = 0; lev < S.nlevels; ++lev)
             if (wide_level(lev, maxnr))
-               need = std::max(need, (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]) * solve_wide_block() * maxnr * sizeof(double));
+               need = std::max(need, 2 * (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]) * solve_wide_block() * maxnr * sizeof(double));
          S.b_pbuf.ensure(need, s);
       }
       S.b_bar.ensure(256, s);
@@ -1378,6 +1383,8 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          double* xs = lane_xs[lane];
          double* ywork = lane_y[lane];
          double* pbuf = lane_p[lane];
+         SolveAux* aux = nullptr;
+         if (g_solve_lookahead) { aux = &N.solve_aux[lane]; aux->create(); }
          launch_transpose_rhs(xcol, ldx, xs, S.n, nr, true, s);
          auto sweep = [&]() {
             if (job == JOB_FWD) {
@@ -1386,7 +1393,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                   if (wide_level(lev, nr)) {
                      int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
                      launch_fwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev], nwork,
-                           (N.lvl_steps[lev] + 7) / 8, posdef, nr, xs, ywork, s);
+                           (N.lvl_steps[lev] + 7) / 8, posdef, nr, xs, ywork, s, aux);
                   } else
                      launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev], nwork, N.lvl_steps[lev], posdef, nr,
                            xs, ldx, ywork, s, bar);
@@ -1401,7 +1408,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                   if (wide_level(lev, nr))
                      launch_bwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                            N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, (N.lvl_steps[lev] + 7) / 8, posdef, nr,
-                           xs, pbuf, s);
+                           xs, pbuf, s, aux);
                   else
                   launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                         N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
@@ -1440,7 +1447,13 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
       }
       CUDA_TRY(cudaGetLastError());
       if (host_x) CUDA_TRY(cudaMemcpyAsync(x, dx, xbytes, cudaMemcpyDeviceToHost, s));
+      const auto t_enq = std::chrono::steady_clock::now();
       CUDA_TRY(cudaStreamSynchronize(s));
+      if (getenv("SPRAL_B200_TRACE")) {
+         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+         fprintf(stderr, "[solve] job %d nrhs %d: %.2f ms to enqueue, %.2f ms more until the stream drained\n", (int)job, nrhs,
+                 ms(t_solve0, t_enq), ms(t_enq, std::chrono::steady_clock::now()));
+      }
    } catch (const CudaError& e) {
       fprintf(stderr, "spral_ssids_b200: CUDA error %d (%s) in solve\n", (int)e.code, cudaGetErrorString(e.code));
       return SPRAL_SSIDS_ERROR_CUDA_UNKNOWN;
