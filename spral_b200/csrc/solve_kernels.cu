@@ -22,6 +22,9 @@
  *   into a scratch, then one warp per front sums the partials in a fixed
  *   order and solves the transposed diagonal block.
  */
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
 #include "engine.h"
 #include "device_utils.cuh"
 #include "solve_wide.h"
@@ -470,9 +473,7 @@ __global__ void __launch_bounds__(SW_GT)
 k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork,
       int part, int first) {
    extern __shared__ double smem_dyn[];
-   /* near launches: two tiles per front of the level, no work list */
-   const RowTile w = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / (2 * SW_FSPLIT), ((int)blockIdx.x / SW_FSPLIT) & 1}
-                                     : work[blockIdx.x / SW_FSPLIT];
+   const RowTile w = work[blockIdx.x / SW_FSPLIT];
    const SolveFront f = fronts[w.front];
    SolveDevCtx cx;
    fwd_wide_G<NR>(cx, f, w.tile, blk, (int)(blockIdx.x % SW_FSPLIT), x, ywork, smem_dyn, part);
@@ -480,13 +481,25 @@ k_fwd_wide_G(const SolveFront* fronts, const RowTile* work, int blk, double* __r
 
 template <int NR>
 __global__ void __launch_bounds__(SW_GT)
+k_fwd_wide_G_near(const SolveFront* fronts, int first, int blk, double* __restrict__ x, const double* __restrict__ ywork) {
+   extern __shared__ double smem_dyn[];
+   const SolveFront f = fronts[first + (int)blockIdx.x / (2 * SW_NSPLIT)];
+   SolveDevCtx cx;
+   fwd_wide_G<NR, SolveDevCtx, SW_NSPLIT>(cx, f, ((int)blockIdx.x / SW_NSPLIT) & 1, blk, (int)(blockIdx.x % SW_NSPLIT), x, ywork, smem_dyn, SW_NEAR);
+}
+
+constexpr int SW_BNSPLIT = 4;      // CTAs that share a tile in the near launches of the backward sweep and of the tensor-core G kernels
+
+template <int NR>
+__global__ void __launch_bounds__(SW_GT)
 k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int first, int step, const double* __restrict__ x, double* __restrict__ pbuf,
       int part) {
    extern __shared__ double smem_dyn[];
-   const RowTile w = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / 2, (int)blockIdx.x & 1} : work[blockIdx.x];
+   const RowTile w = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / (2 * SW_BNSPLIT), ((int)blockIdx.x / SW_BNSPLIT) & 1} : work[blockIdx.x];
    const SolveFront f = fronts[w.front];
    SolveDevCtx cx;
-   bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)(w.front - first) * SWB * NR, smem_dyn, part);
+   bwd_wide_G<NR>(cx, f, w.tile, step, x, pbuf + (size_t)(w.front - first) * SWB * NR, smem_dyn, part,
+                  part == SW_NEAR ? (int)blockIdx.x % SW_BNSPLIT : 0, part == SW_NEAR ? SW_BNSPLIT : 1);
 }
 
 template <int NR, int NRT, bool POSDEF>
@@ -540,7 +553,8 @@ __global__ void __launch_bounds__(SW_GT)
 k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double* __restrict__ x, const double* __restrict__ ywork,
       int part, int first) {
    extern __shared__ __align__(16) double smem_dyn[];
-   const RowTile wk = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / 2, (int)blockIdx.x & 1} : work[blockIdx.x];
+   /* near launches: two tiles per front of the level (no work list), SW_BNSPLIT CTAs share the 8 column chunks of a tile */
+   const RowTile wk = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / (2 * SW_BNSPLIT), ((int)blockIdx.x / SW_BNSPLIT) & 1} : work[blockIdx.x];
    const SolveFront f = fronts[wk.front];
    const int kb = blk * SWB;
    if (kb >= f.nelim) return;
@@ -554,14 +568,32 @@ k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double*
    double* ys = smem_dyn + 2 * 32 * SG_LLD;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int nchunk = (w + 31) / 32;
-   for (int e = tid; e < nchunk * 32; e += SW_GT) {
-      const int g = (e < w) ? f.perm[kb + e] - 1 : -1;
-      #pragma unroll
-      for (int k = 0; k < NR; ++k) ys[e * YLD + k] = (g >= 0) ? ywork[XI(g, k)] : 0.0;
+   const int cper = part == SW_NEAR ? (SWB / 32) / SW_BNSPLIT : SWB / 32;
+   const int c_begin = part == SW_NEAR ? ((int)blockIdx.x % SW_BNSPLIT) * cper : 0;
+   const int c_end = min(nchunk, c_begin + cper);
+   if (c_begin >= c_end) return;
+   /* the right-hand sides of this CTA's columns: consecutive threads read consecutive values of a row (coalesced) */
+   {
+      constexpr int UN = 8;                                        // loads in flight per thread
+      const int total = (c_end - c_begin) * 32 * NR;
+      for (int base = tid; base < total; base += SW_GT * UN) {
+         double v[UN];
+         #pragma unroll
+         for (int u = 0; u < UN; ++u) {
+            const int idx = base + u * SW_GT;
+            const int e = c_begin * 32 + idx / NR;
+            v[u] = (idx < total && e < w) ? ywork[XI(f.perm[kb + e] - 1, idx % NR)] : 0.0;
+         }
+         #pragma unroll
+         for (int u = 0; u < UN; ++u) {
+            const int idx = base + u * SW_GT;
+            if (idx < total) ys[(c_begin * 32 + idx / NR) * YLD + idx % NR] = v[u];
+         }
+      }
    }
    SgChunk ck;
-   sg_load(ck, f, kb, w, r0, rlo, rhi, 0, tid);
-   sg_store(ck, Ls, tid);
+   sg_load(ck, f, kb, w, r0, rlo, rhi, c_begin, tid);
+   sg_store(ck, Ls + (c_begin & 1) * 32 * SG_LLD, tid);
    __syncthreads();
    const int rbase = warp * 16;
    double acc[NR / 8][2][2];
@@ -569,8 +601,8 @@ k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double*
    for (int j = 0; j < NR / 8; ++j)
       #pragma unroll
       for (int i = 0; i < 2; ++i) { acc[j][i][0] = 0.0; acc[j][i][1] = 0.0; }
-   for (int c = 0; c < nchunk; ++c) {
-      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, rlo, rhi, c + 1, tid);
+   for (int c = c_begin; c < c_end; ++c) {
+      if (c + 1 < c_end) sg_load(ck, f, kb, w, r0, rlo, rhi, c + 1, tid);
       const double* Lc = Ls + (c & 1) * 32 * SG_LLD;
       #pragma unroll
       for (int kk = 0; kk < 32; kk += 4) {
@@ -584,7 +616,7 @@ k_fwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int blk, double*
             #pragma unroll
             for (int i = 0; i < 2; ++i) pv_dmma(acc[j][i][0], acc[j][i][1], afr[j], bfr[i]);
       }
-      if (c + 1 < nchunk) sg_store(ck, Ls + ((c + 1) & 1) * 32 * SG_LLD, tid);
+      if (c + 1 < c_end) sg_store(ck, Ls + ((c + 1) & 1) * 32 * SG_LLD, tid);
       __syncthreads();
    }
    /* acc[j][i][e] = sum for right-hand side 8 j + lane / 4 and row rbase + 8 i + 2 (lane % 4) + e */
@@ -606,7 +638,7 @@ __global__ void __launch_bounds__(SW_GT)
 k_bwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int first, int step, const double* __restrict__ x,
       double* __restrict__ pbuf, int part) {
    extern __shared__ __align__(16) double smem_dyn[];
-   const RowTile wk = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / 2, (int)blockIdx.x & 1} : work[blockIdx.x];
+   const RowTile wk = part == SW_NEAR ? RowTile{first + (int)blockIdx.x / (2 * SW_BNSPLIT), ((int)blockIdx.x / SW_BNSPLIT) & 1} : work[blockIdx.x];
    const SolveFront f = fronts[wk.front];
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
@@ -622,20 +654,34 @@ k_bwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int first, int s
    double* accb = pbuf + (size_t)(wk.front - first) * SWB * NR;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int nchunk = (w + 31) / 32;
-   for (int e = tid; e < RT; e += SW_GT) {
-      const int r = r0 + e;
-      const bool act = r >= rlo && r < rhi;
-      const int g = act ? row_index(f, r) : 0;
-      #pragma unroll
-      for (int k = 0; k < NR; ++k) xs[e * XLD + k] = act ? x[XI(g, k)] : 0.0;
+   const int cper = part == SW_NEAR ? (SWB / 32) / SW_BNSPLIT : SWB / 32;
+   const int c_begin = part == SW_NEAR ? ((int)blockIdx.x % SW_BNSPLIT) * cper : 0;
+   const int c_end = min(nchunk, c_begin + cper);
+   if (c_begin >= c_end) return;
+   {                                                            // coalesced: consecutive threads, consecutive values of a row
+      constexpr int UN = 8;
+      for (int base = tid; base < RT * NR; base += SW_GT * UN) {
+         double v[UN];
+         #pragma unroll
+         for (int u = 0; u < UN; ++u) {
+            const int idx = base + u * SW_GT;
+            const int r = r0 + idx / NR;
+            v[u] = (idx < RT * NR && r >= rlo && r < rhi) ? x[XI(row_index(f, r), idx % NR)] : 0.0;
+         }
+         #pragma unroll
+         for (int u = 0; u < UN; ++u) {
+            const int idx = base + u * SW_GT;
+            if (idx < RT * NR) xs[(idx / NR) * XLD + idx % NR] = v[u];
+         }
+      }
    }
    SgChunk ck;
-   sg_load(ck, f, kb, w, r0, rlo, rhi, 0, tid);
-   sg_store(ck, Ls, tid);
+   sg_load(ck, f, kb, w, r0, rlo, rhi, c_begin, tid);
+   sg_store(ck, Ls + (c_begin & 1) * 32 * SG_LLD, tid);
    __syncthreads();
    constexpr int NB = NR / 16;               // 8 x 8 output blocks per warp and chunk: (NR / 8 right-hand-side groups) x 4 column groups / 8 warps
-   for (int c = 0; c < nchunk; ++c) {
-      if (c + 1 < nchunk) sg_load(ck, f, kb, w, r0, rlo, rhi, c + 1, tid);
+   for (int c = c_begin; c < c_end; ++c) {
+      if (c + 1 < c_end) sg_load(ck, f, kb, w, r0, rlo, rhi, c + 1, tid);
       const double* Lc = Ls + (c & 1) * 32 * SG_LLD;
       double acc[NB][2];
       int jg[NB], cg[NB];
@@ -658,7 +704,7 @@ k_bwd_wide_G_mma(const SolveFront* fronts, const RowTile* work, int first, int s
             const int col = 32 * c + 8 * cg[u] + 2 * (lane & 3) + e;
             if (col < w) atomicAdd(&accb[(size_t)col * NR + 8 * jg[u] + (lane >> 2)], acc[u][e]);
          }
-      if (c + 1 < nchunk) sg_store(ck, Ls + ((c + 1) & 1) * 32 * SG_LLD, tid);
+      if (c + 1 < c_end) sg_store(ck, Ls + ((c + 1) & 1) * 32 * SG_LLD, tid);
       __syncthreads();
    }
 }
@@ -680,16 +726,20 @@ void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
    if (!configured) {
       cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
       if constexpr (MMA) cudaFuncSetAttribute(k_fwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
-      else cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+      else {
+         cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+         cudaFuncSetAttribute(k_fwd_wide_G_near<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
+      }
       configured = true;
    }
    auto G = [&](int b, int part, cudaStream_t st) {
       if constexpr (MMA) {
-         const int grid = part == SW_NEAR ? 2 * count : nwork;
+         const int grid = part == SW_NEAR ? 2 * count * SW_BNSPLIT : nwork;
          k_fwd_wide_G_mma<NR><<<grid, SW_GT, smG, st>>>(fronts, work, b, x, ywork, part, first);
+      } else if (part == SW_NEAR) {
+         k_fwd_wide_G_near<NR><<<2 * count * SW_NSPLIT, SW_GT, smG, st>>>(fronts, first, b, x, ywork);
       } else {
-         const int grid = (part == SW_NEAR ? 2 * count : nwork) * SW_FSPLIT;
-         k_fwd_wide_G<NR><<<grid, SW_GT, smG, st>>>(fronts, work, b, x, ywork, part, first);
+         k_fwd_wide_G<NR><<<nwork * SW_FSPLIT, SW_GT, smG, st>>>(fronts, work, b, x, ywork, part, first);
       }
       COUNT_LAUNCH();
    };
@@ -701,18 +751,37 @@ void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
       return;
    }
    /* T(b) needs the near part of block b - 1 (same stream) and the far parts of the blocks up to b - 2 */
+   static const bool tl = getenv("SPRAL_B200_TRACE_SOLVE") != nullptr;         // timeline of the sweep (events per launch)
+   std::vector<cudaEvent_t> tev;
+   auto mark = [&](cudaStream_t st) { if (tl && nblk >= 16) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+   mark(s);
    for (int b = 0; b < nblk; ++b) {
       if (b >= 2) cudaStreamWaitEvent(s, aux->evF[(b - 2) & 3], 0);
+      mark(s);
       T(b);
+      mark(s);
       cudaEventRecord(aux->evT[b & 3], s);
       cudaStream_t fs = aux->far[b & 1];
       cudaStreamWaitEvent(fs, aux->evT[b & 3], 0);
+      mark(fs);
       G(b, SW_FAR, fs);
+      mark(fs);
       cudaEventRecord(aux->evF[b & 3], fs);
       G(b, SW_NEAR, s);
+      mark(s);
    }
    cudaStreamWaitEvent(s, aux->evF[(nblk - 2) & 3], 0);
    cudaStreamWaitEvent(s, aux->evF[(nblk - 1) & 3], 0);
+   if (!tev.empty()) {
+      cudaStreamSynchronize(s);
+      for (int b = 0; b < nblk; ++b) {
+         float t[5];
+         for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[1 + 5 * b + i]);
+         fprintf(stderr, "[fwd nr %d] block %3d: T %8.1f -> %8.1f us, near -> %8.1f, far %8.1f -> %8.1f\n", NR, b,
+                 1e3 * t[0], 1e3 * t[1], 1e3 * t[4], 1e3 * t[2], 1e3 * t[3]);
+      }
+      for (auto e : tev) cudaEventDestroy(e);
+   }
 }
 
 /* pbuf: one SWB x NR accumulator per front of the level (two with look-ahead: blocks alternate between them), all
@@ -732,7 +801,7 @@ void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
    }
    const size_t accsz = (size_t)count * SWB * NR;
    auto G = [&](int st, int part, double* acc, cudaStream_t strm) {
-      const int grid = part == SW_NEAR ? 2 * count : nwork;
+      const int grid = part == SW_NEAR ? 2 * count * SW_BNSPLIT : nwork;
       if constexpr (MMA) k_bwd_wide_G_mma<NR><<<grid, SW_GT, sg_b_smem_bytes<NR>(), strm>>>(fronts, work, first, st, x, acc, part);
       else k_bwd_wide_G<NR><<<grid, SW_GT, 0, strm>>>(fronts, work, first, st, x, acc, part);
       COUNT_LAUNCH();
@@ -754,11 +823,19 @@ void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
       G(st, SW_FAR, pbuf + st * accsz, aux->far[st]);
       cudaEventRecord(aux->evF[st], aux->far[st]);
    }
+   static const bool tl = getenv("SPRAL_B200_TRACE_SOLVE") != nullptr;
+   std::vector<cudaEvent_t> tev;
+   auto mark = [&](cudaStream_t st) { if (tl && nblk >= 16) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+   mark(s);
    for (int st = 0; st < nblk; ++st) {
       double* acc = pbuf + (st & 1) * accsz;
+      mark(s);
       if (st >= 1) G(st, SW_NEAR, acc, s);
+      mark(s);
       cudaStreamWaitEvent(s, aux->evF[st & 3], 0);
+      mark(s);
       T(st, acc);
+      mark(s);
       if (st + 2 < nblk) {
          cudaEventRecord(aux->evT[st & 3], s);
          cudaStream_t fs = aux->far[st & 1];
@@ -766,6 +843,15 @@ void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
          G(st + 2, SW_FAR, acc, fs);
          cudaEventRecord(aux->evF[(st + 2) & 3], fs);
       }
+   }
+   if (!tev.empty()) {
+      cudaStreamSynchronize(s);
+      for (int st = 0; st < nblk; ++st) {
+         float t[4];
+         for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[1 + 4 * st + i]);
+         fprintf(stderr, "[bwd nr %d] step %3d: near %8.1f -> %8.1f us, T %8.1f -> %8.1f\n", NR, st, 1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3]);
+      }
+      for (auto e : tev) cudaEventDestroy(e);
    }
 }
 

@@ -203,7 +203,10 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
  * sums 64 columns of its row, eight independent loads at a time; the quarters meet in shared memory, the halves in x
  * (atomics).  Two CTAs per tile: twice as many bytes in flight per SM on the levels that have few tiles. */
 constexpr int SW_FSPLIT = 2;
-template <int NR, class Ctx>
+constexpr int SW_NSPLIT = 16;   // column split of the near launches (forward); the backward ones split 4 ways
+/* FS = CTAs that share the block's columns (near launches use SW_NSPLIT: a few tiles on the critical path of the sweep,
+ * each thread then has ONE batch of loads instead of a dependent chain of them) */
+template <int NR, class Ctx, int FS = SW_FSPLIT>
 SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, int ch, double* x, const double* ywork, double* smem,
       int rpart = SW_ALL) {
    const int kb = blk * SWB;
@@ -214,7 +217,7 @@ SW_FN void fwd_wide_G(Ctx& cx, const SolveFront& f, int tile, int blk, int ch, d
    if (rpart == SW_NEAR) tile += rlo / RT;           // near launches count the tiles from the first row below the block
    const int r0 = tile * RT;
    if (r0 + RT <= rlo || r0 >= rhi) return;
-   constexpr int CH = SWB / SW_FSPLIT;              // columns of this CTA
+   constexpr int CH = SWB / FS;                     // columns of this CTA
    const int c0 = ch * CH;
    if (c0 >= w) return;
    const int wc = sw_min(CH, w - c0);
@@ -276,7 +279,7 @@ SW_FN int sw_bwd_block(const SolveFront& f, int step) {
  * (SWB x NR doubles, zero when the step starts; several tiles add into it: atomics). */
 template <int NR, class Ctx>
 SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const double* x, double* acc, double* /*smem*/,
-      int part = SW_ALL) {
+      int part = SW_ALL, int cpart = 0, int ncpart = 1) {
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
    const int kb = b * SWB;
@@ -300,7 +303,8 @@ SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const
    }
    constexpr int CG = (NR <= 2) ? 8 : 4;           // columns per batch: CG * NR running sums per thread
    const int c0 = warp * 32;
-   for (int cb = 0; cb < 32 && c0 + cb < w; cb += CG) {
+   const int cw = 32 / ncpart;                     // near launches: ncpart CTAs share a warp's 32 columns
+   for (int cb = cpart * cw; cb < (cpart + 1) * cw && c0 + cb < w; cb += CG) {
       double l[CG][4];
       #pragma unroll
       for (int c = 0; c < CG; ++c) {

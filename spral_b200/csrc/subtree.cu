@@ -48,6 +48,9 @@ static bool g_solve_coop = false;    // SPRAL_B200_SOLVE_COOP=1: one cooperative
 static int g_solve_wide = 1;         // 256-column sweeps (solve_wide.h; SPRAL_B200_SOLVE_WIDE=0: 32-column steps everywhere) on
                                      // levels whose largest front has at least SPRAL_B200_SOLVE_WIDE_MIN (8) 32-column steps
 static int g_solve_wide_min = 8;
+/* look-ahead inside the wide sweeps only on levels of few, large fronts (two accumulators per front; a level of
+ * thousands of fronts keeps the T kernels busy anyway) */
+constexpr int SOLVE_LOOKAHEAD_MAX_FRONTS = 64;
 static bool g_solve_lookahead = true; // SPRAL_B200_SOLVE_LOOKAHEAD=0: the wide sweeps on one stream
 static bool g_trace_panels = false;  // SPRAL_B200_TRACE_PANELS=1: per-panel trace lines on stderr (host time between panels)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
@@ -1331,13 +1334,15 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
          if (!g_solve_wide || N.lvl_steps[lev] < (nr >= 16 ? 1 : g_solve_wide_min)) return false;
          /* the backward sweep keeps one 256 x nr accumulator per front of the level */
          size_t nfr = (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]);
-         return 2 * nfr * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
+         return (nfr <= SOLVE_LOOKAHEAD_MAX_FRONTS ? 2 : 1) * nfr * solve_wide_block() * nr * sizeof(double) <= ((size_t)1 << 30);
       };
       if (job == JOB_DIAG_BWD || job == JOB_BWD) {
          size_t need = std::max<size_t>(N.max_level_work, 1) * solve_block() * 32 * sizeof(double);      // 32-column kernels: per tile
          for (int lev = 0; lev < S.nlevels; ++lev)
-            if (wide_level(lev, maxnr))
-               need = std::max(need, 2 * (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]) * solve_wide_block() * maxnr * sizeof(double));
+            if (wide_level(lev, maxnr)) {
+               const size_t nfr = (size_t)(S.level_ptr[lev + 1] - S.level_ptr[lev]);
+               need = std::max(need, (nfr <= SOLVE_LOOKAHEAD_MAX_FRONTS ? 2 : 1) * nfr * solve_wide_block() * maxnr * sizeof(double));
+            }
          S.b_pbuf.ensure(need, s);
       }
       S.b_bar.ensure(256, s);
@@ -1393,7 +1398,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                   if (wide_level(lev, nr)) {
                      int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
                      launch_fwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev], nwork,
-                           (N.lvl_steps[lev] + 7) / 8, posdef, nr, xs, ywork, s, aux);
+                           (N.lvl_steps[lev] + 7) / 8, posdef, nr, xs, ywork, s, f1 - f0 <= SOLVE_LOOKAHEAD_MAX_FRONTS ? aux : nullptr);
                   } else
                      launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev], nwork, N.lvl_steps[lev], posdef, nr,
                            xs, ldx, ywork, s, bar);
@@ -1408,7 +1413,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                   if (wide_level(lev, nr))
                      launch_bwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                            N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, (N.lvl_steps[lev] + 7) / 8, posdef, nr,
-                           xs, pbuf, s, aux);
+                           xs, pbuf, s, f1 - f0 <= SOLVE_LOOKAHEAD_MAX_FRONTS ? aux : nullptr);
                   else
                   launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                         N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
