@@ -44,11 +44,11 @@ def test_slice_of_the_gpu_parity_suite_on_the_emulator(emu_env):
 
 
 def test_alternative_code_paths_against_the_defaults_on_the_emulator(emu_env):
-    """tests/test_gpu_paths.py (step-by-step panels, 32-column solve kernels, scheduling switches against the
-    defaults) on two small dense fronts."""
+    """tests/test_gpu_paths.py (step-by-step panels, 32-column solve kernels, scheduling switches, sweeps without
+    look-ahead against the defaults) on a small dense front."""
     env = dict(emu_env, SPRAL_B200_DUMP_CASES="dense_391_indef")
     out = _pytest(env, ["tests/test_gpu_paths.py"], 2400)
-    assert "3 passed" in out, out[-500:]
+    assert "4 passed" in out, out[-500:]
 
 
 @pytest.fixture(scope="module")

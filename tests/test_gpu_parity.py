@@ -147,6 +147,19 @@ def test_dense_fronts(n):
     _check(lambda: _dense(A), False, 2, order=order)
 
 
+@pytest.mark.parametrize("nrhs", [16, 33, 64, 130])
+def test_many_right_hand_sides(nrhs):
+    """16+ right-hand sides take the tensor-core solve kernels (one pass per 16, 32 or 64), 128+ two concurrent lanes
+    of 64; on a front of three 256-column blocks and on a tree of several levels, with the look-ahead inside the
+    sweeps.  The reference solves them one at a time (gpu/subtree.f90:570-579); every column is checked against the
+    oracle's solution through the backward error of the whole block."""
+    rng = np.random.default_rng(nrhs)
+    A = _sym(rng, 700)
+    _check(lambda: _dense(A), False, nrhs, order=np.arange(1, 701, dtype=np.int32))
+    _check(lambda: M.stencil_3d_27pt(20, shift=13.0), False, nrhs)
+    _check(lambda: M.laplacian_3d_7pt(24), True, nrhs)
+
+
 @pytest.mark.parametrize("kind,n", [("smalllead", 64), ("smalllead", 300), ("smalllead", 600),
                                     ("saddle", 100), ("saddle", 300), ("saddle", 600),
                                     ("arrow", 200), ("arrow", 700)])

@@ -52,6 +52,7 @@ def main(out):
         rng = np.random.default_rng(11)
         X5 = sb.solve(fk, np.asfortranarray(A @ rng.uniform(-1, 1, (n, 5))))      # chunks of 4 + 1 right-hand sides
         res[name + "/x5"] = X5
+        res[name + "/x20"] = sb.solve(fk, np.asfortranarray(A @ rng.uniform(-1, 1, (n, 20))))      # 16 (tensor cores) + 4
         g = fk.inform
         res[name + "/d"] = d
         if piv is not None:
