@@ -164,7 +164,8 @@ void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowT
 int solve_wide_block();
 /* Streams and events of the look-ahead inside a wide sweep: the G work on the rows of the next block stays on the
  * sweep's stream, the rest runs on the two far streams beside the following T kernels (solve_wide.h: SW_NEAR / SW_FAR).
- * The backward sweep then needs TWO accumulators per front (pbuf of 2 x count x 256 x nr doubles). */
+ * The backward sweep then needs TWO accumulators per front (pbuf of 2 x count x 256 x nr doubles).
+ * half: no front of the level eliminates more than 128 columns (the T kernels then keep 128 rows in shared memory). */
 struct SolveAux {
    cudaStream_t far[2] = {nullptr, nullptr};
    cudaEvent_t evT[4] = {nullptr, nullptr, nullptr, nullptr}, evF[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -172,8 +173,8 @@ struct SolveAux {
    void destroy();
 };
 void launch_fwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s, SolveAux* aux = nullptr);
+      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s, SolveAux* aux = nullptr, bool half = false);
 void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s, SolveAux* aux = nullptr);
+      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s, SolveAux* aux = nullptr, bool half = false);
 
 } // namespace b200

@@ -458,14 +458,14 @@ struct SolveDevCtx {
 };
 
 /* grid = fronts x (NRT / NR) slices of right-hand sides: block b handles front b % count, slice b / count */
-template <int NR, int NRT, bool POSDEF>
-__global__ void __launch_bounds__(SW_TT)
+template <int NR, int NRT, bool POSDEF, int HB = SWB>
+__global__ void __launch_bounds__(HB < SW_TT ? HB : SW_TT)
 k_fwd_wide_T(const SolveFront* fronts, int first, int count, int blk, const double* __restrict__ x, double* __restrict__ ywork) {
    extern __shared__ double smem_dyn[];
    const SolveFront f = fronts[first + blockIdx.x % count];
    const int k0 = (blockIdx.x / count) * NR;
    SolveDevCtx cx;
-   fwd_wide_T<NR, NRT, POSDEF>(cx, f, blk, x + k0, ywork + k0, smem_dyn);
+   fwd_wide_T_h<NR, NRT, POSDEF, HB>(cx, f, blk, x + k0, ywork + k0, smem_dyn);
 }
 
 template <int NR>
@@ -502,15 +502,15 @@ k_bwd_wide_G(const SolveFront* fronts, const RowTile* work, int first, int step,
                   part == SW_NEAR ? (int)blockIdx.x % SW_BNSPLIT : 0, part == SW_NEAR ? SW_BNSPLIT : 1);
 }
 
-template <int NR, int NRT, bool POSDEF>
-__global__ void __launch_bounds__(SW_TT)
+template <int NR, int NRT, bool POSDEF, int HB = SWB>
+__global__ void __launch_bounds__(HB < SW_TT ? HB : SW_TT)
 k_bwd_wide_T(const SolveFront* fronts, int first, int count, int step, double* __restrict__ x, double* __restrict__ pbuf) {
    extern __shared__ double smem_dyn[];
    const int fl = blockIdx.x % count;
    const SolveFront f = fronts[first + fl];
    const int k0 = (blockIdx.x / count) * NR;
    SolveDevCtx cx;
-   bwd_wide_T<NR, NRT, POSDEF>(cx, f, step, x + k0, pbuf + (size_t)fl * SWB * NRT + k0, smem_dyn);
+   bwd_wide_T_h<NR, NRT, POSDEF, HB>(cx, f, step, x + k0, pbuf + (size_t)fl * SWB * NRT + k0, smem_dyn);
 }
 
 /* ---- G kernels on the FP64 tensor cores (16 or 32 right-hand sides) ---------------------------------------- */
@@ -716,8 +716,11 @@ template <int NR> constexpr int t_slice() { return NR > 16 ? 16 : NR; }
 
 template <int NR, bool POSDEF>
 void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork, int nblk,
-      double* x, double* ywork, cudaStream_t s, SolveAux* aux) {
-   static bool configured = false;
+      double* x, double* ywork, cudaStream_t s, SolveAux* aux, bool half) {
+   static bool configured_dev[64] = {false};       // function attributes are per device
+   int dev_ = 0;
+   cudaGetDevice(&dev_);
+   bool& configured = configured_dev[dev_ & 63];
    constexpr int TS = t_slice<NR>();
    constexpr bool MMA = UseMma<NR>::value;
    const size_t smT = sw_T_smem_doubles<TS>() * sizeof(double);
@@ -725,6 +728,8 @@ void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
    if constexpr (MMA) smG = sg_f_smem_bytes<NR>(); else smG = sw_fG_smem_doubles<NR>() * sizeof(double);
    if (!configured) {
       cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+      if constexpr (MMA) cudaFuncSetAttribute(k_fwd_wide_T<TS, NR, POSDEF, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sw_T_smem_doubles<TS, 128>() * sizeof(double)));
       if constexpr (MMA) cudaFuncSetAttribute(k_fwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
       else {
          cudaFuncSetAttribute(k_fwd_wide_G<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smG);
@@ -744,6 +749,14 @@ void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
       COUNT_LAUNCH();
    };
    auto T = [&](int b) {
+      if constexpr (MMA) {
+         if (half) {          // every front of the level eliminates at most 128 columns: three T CTAs per SM
+            const size_t smTh = sw_T_smem_doubles<TS, 128>() * sizeof(double);
+            k_fwd_wide_T<TS, NR, POSDEF, 128><<<count * (NR / TS), 128, smTh, s>>>(fronts, first, count, b, x, ywork);
+            COUNT_LAUNCH();
+            return;
+         }
+      }
       k_fwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, b, x, ywork); COUNT_LAUNCH();
    };
    if (!aux || nblk < 2) {
@@ -788,13 +801,18 @@ void fwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
  * zero when the sweep of the level starts (the T kernel clears what it consumed) */
 template <int NR, bool POSDEF>
 void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      const int* wbeg, int nblk, double* x, double* pbuf, cudaStream_t s, SolveAux* aux) {
-   static bool configured = false;
+      const int* wbeg, int nblk, double* x, double* pbuf, cudaStream_t s, SolveAux* aux, bool half) {
+   static bool configured_dev[64] = {false};       // function attributes are per device
+   int dev_ = 0;
+   cudaGetDevice(&dev_);
+   bool& configured = configured_dev[dev_ & 63];
    constexpr int TS = t_slice<NR>();
    constexpr bool MMA = UseMma<NR>::value;
    const size_t smT = sw_T_smem_doubles<TS>() * sizeof(double);
    if (!configured) {
       cudaFuncSetAttribute(k_bwd_wide_T<TS, NR, POSDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+      if constexpr (MMA) cudaFuncSetAttribute(k_bwd_wide_T<TS, NR, POSDEF, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sw_T_smem_doubles<TS, 128>() * sizeof(double)));
       if constexpr (MMA)
          cudaFuncSetAttribute(k_bwd_wide_G_mma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_b_smem_bytes<NR>());
       configured = true;
@@ -807,6 +825,14 @@ void bwd_level_wide_t(const SolveFront* fronts, int first, int count, const RowT
       COUNT_LAUNCH();
    };
    auto T = [&](int st, double* acc) {
+      if constexpr (MMA) {
+         if (half) {
+            const size_t smTh = sw_T_smem_doubles<TS, 128>() * sizeof(double);
+            k_bwd_wide_T<TS, NR, POSDEF, 128><<<count * (NR / TS), 128, smTh, s>>>(fronts, first, count, st, x, acc);
+            COUNT_LAUNCH();
+            return;
+         }
+      }
       k_bwd_wide_T<TS, NR, POSDEF><<<count * (NR / TS), SW_TT, smT, s>>>(fronts, first, count, st, x, acc); COUNT_LAUNCH();
    };
    if (!aux || nblk < 2) {
@@ -904,19 +930,19 @@ int solve_wide_block() { return SWB; }
 
 #define SW_DISPATCH(NRV, CALL_T, CALL_F) case NRV: if (posdef) { CALL_T; } else { CALL_F; } break
 void launch_fwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s, SolveAux* aux) {
+      int nblk, bool posdef, int nr, double* x, double* ywork, cudaStream_t s, SolveAux* aux, bool half) {
    if (nwork == 0 || nblk == 0 || count == 0) return;
-#define SW_F(NRV) SW_DISPATCH(NRV, (fwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, nblk, x, ywork, s, aux)), \
-                                   (fwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, nblk, x, ywork, s, aux)))
+#define SW_F(NRV) SW_DISPATCH(NRV, (fwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, nblk, x, ywork, s, aux, half)), \
+                                   (fwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, nblk, x, ywork, s, aux, half)))
    switch (nr) { SW_F(64); SW_F(32); SW_F(16); SW_F(8); SW_F(4); SW_F(2); default: SW_F(1); }
 #undef SW_F
 }
 
 void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const RowTile* work, int nwork,
-      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s, SolveAux* aux) {
+      const int* wbeg, int nblk, bool posdef, int nr, double* x, double* pbuf, cudaStream_t s, SolveAux* aux, bool half) {
    if (nwork == 0 || nblk == 0 || count == 0) return;
-#define SW_B(NRV) SW_DISPATCH(NRV, (bwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s, aux)), \
-                                   (bwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s, aux)))
+#define SW_B(NRV) SW_DISPATCH(NRV, (bwd_level_wide_t<NRV, true>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s, aux, half)), \
+                                   (bwd_level_wide_t<NRV, false>(fronts, first, count, work, nwork, wbeg, nblk, x, pbuf, s, aux, half)))
    switch (nr) { SW_B(64); SW_B(32); SW_B(16); SW_B(8); SW_B(4); SW_B(2); default: SW_B(1); }
 #undef SW_B
 }

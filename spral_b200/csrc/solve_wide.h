@@ -60,15 +60,18 @@ template <int NR> constexpr int sw_xld() { return NR == 1 ? 1 : (NR >= 16 ? NR +
  * M = right-hand side): the 32-column slab of L goes through shared memory, k-major with a stride = 4 mod 16 doubles
  * (bank-conflict-free fragment loads; so is the stride NR + 4 of the right-hand sides) */
 template <int NR> constexpr bool sw_T_mma() { return NR >= 16; }
+/* HB = rows of the block a T CTA keeps in shared memory: SWB, or 128 on the levels whose fronts eliminate at most 128
+ * columns (one block; the CTA then has 128 threads): 62 KB instead of 116 KB of shared memory with 16 right-hand sides
+ * and half the registers, three CTAs per SM instead of one -- those levels have thousands of fronts */
 constexpr int SW_LLD = SWB + 4;
-template <int NR> constexpr size_t sw_T_smem_doubles() {
-   return (size_t)SWB * sw_xld<NR>() + (size_t)SSB * SW_LK + (sw_T_mma<NR>() ? (size_t)SSB * SW_LLD : 0);
+template <int NR, int HB = SWB> constexpr size_t sw_T_smem_doubles() {
+   return (size_t)HB * sw_xld<NR>() + (size_t)SSB * SW_LK + (sw_T_mma<NR>() ? (size_t)SSB * (HB + 4) : 0);
 }
 
 /* xs(rows of the 8-row groups of this warp that lie in [lo, hi)) -= slab * xs(sub-block rows): the tensor-core form of
  *   for k: s = xs[t][k]; for j: s -= cur[j] * xs[jb + j][k]
- * ls[j * SW_LLD + t] = cur[j] of thread t (0 for the threads that do not take part). */
-template <int NR, class Ctx>
+ * ls[j * LLD + t] = cur[j] of thread t (0 for the threads that do not take part). */
+template <int NR, int LLD, class Ctx>
 SW_FN void sw_mma_update(Ctx& cx, double* xs, const double* ls, int jb, int lo, int hi) {
    constexpr int XLD = sw_xld<NR>();
    const int lane = cx.tid() & 31, warp = cx.tid() >> 5;
@@ -80,7 +83,7 @@ SW_FN void sw_mma_update(Ctx& cx, double* xs, const double* ls, int jb, int lo, 
       for (int j = 0; j < NR / 8; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
       #pragma unroll
       for (int kk = 0; kk < SSB; kk += 4) {
-         const double bfr = ls[(size_t)(kk + (lane & 3)) * SW_LLD + rg + (lane >> 2)];
+         const double bfr = ls[(size_t)(kk + (lane & 3)) * LLD + rg + (lane >> 2)];
          #pragma unroll
          for (int j = 0; j < NR / 8; ++j) {
             const double afr = xs[(size_t)(jb + kk + (lane & 3)) * XLD + 8 * j + (lane >> 2)];
@@ -112,21 +115,24 @@ template <int NR> constexpr size_t sw_bG_smem_doubles() { return 1; }
 /* ---- forward, T: y(block) = L(block, block)^-1 x(block); y -> ywork ---------------- */
 /* NR right-hand sides of the NRT that share a row of x / ywork (the caller offsets the pointers to the first one):
  * the right-hand sides are independent, so a block of 64 is solved by four CTAs of 16 side by side. */
-template <int NR, int NRT, bool POSDEF, class Ctx>
-SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, double* ywork, double* smem) {
+template <int NR, int NRT, bool POSDEF, int HB, class Ctx>
+SW_FN void fwd_wide_T_h(Ctx& cx, const SolveFront& f, int blk, const double* x, double* ywork, double* smem) {
    const int kb = blk * SWB;
    if (kb >= f.nelim) return;
    constexpr int XLD = sw_xld<NR>();
+   constexpr int LLD = HB + 4;
    double* xs = smem;
-   double* lkk = smem + (size_t)SWB * XLD;
+   double* lkk = smem + (size_t)HB * XLD;
    double* ls = lkk + (size_t)SSB * SW_LK;          // (tensor-core variant only)
    const int w = sw_min(SWB, f.nelim - kb);
    const int t = cx.tid(), lane = t & 31, warp = t >> 5;
    const size_t ldl = (size_t)f.ldl;
    const bool arow = t < w;
    const int g = arow ? f.perm[kb + t] - 1 : -1;
-   #pragma unroll
-   for (int k = 0; k < NR; ++k) xs[(size_t)t * XLD + k] = arow ? x[(size_t)g * NRT + k] : 0.0;
+   if (t < HB) {
+      #pragma unroll
+      for (int k = 0; k < NR; ++k) xs[(size_t)t * XLD + k] = arow ? x[(size_t)g * NRT + k] : 0.0;
+   }
    const double* Lrow = f.L + (size_t)(kb + t) + (size_t)kb * ldl;     // row kb+t of the block, from column kb
    double cur[SSB], nxt[SSB];
    {
@@ -134,7 +140,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
       #pragma unroll
       for (int j = 0; j < SSB; ++j) cur[j] = (arow && j < wd0) ? Lrow[(size_t)j * ldl] : 0.0;
    }
-   constexpr int NWARP = SW_TT / 32;
+   constexpr int NWARP = (HB < SW_TT ? HB : SW_TT) / 32;      // the CTA has min(HB, 256) threads
    constexpr int NRW = (NR + NWARP - 1) / NWARP;
    for (int jb = 0; jb < w; jb += SSB) {
       const int wd = sw_min(SSB, w - jb);
@@ -146,7 +152,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
       const int jn = jb + SSB;                    // next slab of the rows below this sub-block
       if (sw_T_mma<NR>()) {
          #pragma unroll
-         for (int j = 0; j < SSB; ++j) ls[(size_t)j * SW_LLD + t] = (arow && t >= jn) ? cur[j] : 0.0;
+         for (int j = 0; j < SSB; ++j) if (t < HB) ls[(size_t)j * LLD + t] = (arow && t >= jn) ? cur[j] : 0.0;
       }
       if (jn < w) {
          const int wdn = sw_min(SSB, w - jn);
@@ -177,7 +183,7 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
       }
       cx.sync();
       if (sw_T_mma<NR>()) {
-         if (jn < w) sw_mma_update<(NR >= 16 ? NR : 16)>(cx, xs, ls, jb, jn, w);
+         if (jn < w) sw_mma_update<(NR >= 16 ? NR : 16), LLD>(cx, xs, ls, jb, jn, w);
          cx.sync();                                // the slab is re-written at the top of the next sub-step
       } else if (arow && t >= jn) {               // rows of the block below the sub-block
          #pragma unroll
@@ -196,6 +202,10 @@ SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, do
       #pragma unroll
       for (int k = 0; k < NR; ++k) ywork[(size_t)g * NRT + k] = xs[(size_t)t * XLD + k];
    }
+}
+template <int NR, int NRT, bool POSDEF, class Ctx>
+SW_FN void fwd_wide_T(Ctx& cx, const SolveFront& f, int blk, const double* x, double* ywork, double* smem) {
+   fwd_wide_T_h<NR, NRT, POSDEF, SWB>(cx, f, blk, x, ywork, smem);
 }
 
 /* ---- forward, G: x(rows below the block) -= L(rows, block) * y --------------------- */
@@ -330,13 +340,14 @@ SW_FN void bwd_wide_G(Ctx& cx, const SolveFront& f, int tileidx, int step, const
 }
 
 /* ---- backward, T: x(block) = L(block, block)^-T (x(block) - accumulator); the accumulator is cleared ---- */
-template <int NR, int NRT, bool POSDEF, class Ctx>
-SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double* pb, double* smem) {
+template <int NR, int NRT, bool POSDEF, int HB, class Ctx>
+SW_FN void bwd_wide_T_h(Ctx& cx, const SolveFront& f, int step, double* x, double* pb, double* smem) {
    const int b = sw_bwd_block(f, step);
    if (b < 0) return;
    constexpr int XLD = sw_xld<NR>();
+   constexpr int LLD = HB + 4;
    double* vs = smem;
-   double* lkk = smem + (size_t)SWB * XLD;
+   double* lkk = smem + (size_t)HB * XLD;
    double* ls = lkk + (size_t)SSB * SW_LK;          // (tensor-core variant only)
    const int kb = b * SWB;
    const int w = sw_min(SWB, f.nelim - kb);
@@ -351,7 +362,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
       #pragma unroll
       for (int k = 0; k < NR; ++k) {
          pb[(size_t)t * NRT + k] = 0.0;
-         vs[(size_t)t * XLD + k] = acol ? xv[k] - pv[k] : 0.0;
+         if (t < HB) vs[(size_t)t * XLD + k] = acol ? xv[k] - pv[k] : 0.0;
       }
    }
    const size_t ldl = (size_t)f.ldl;
@@ -360,7 +371,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
    double cur[SSB], nxt[SSB];
    #pragma unroll
    for (int i = 0; i < SSB; ++i) cur[i] = (acol && t < jbl + SSB && jbl + i < w) ? Lcol[jbl + i] : 0.0;
-   constexpr int NWARP = SW_TT / 32;
+   constexpr int NWARP = (HB < SW_TT ? HB : SW_TT) / 32;      // the CTA has min(HB, 256) threads
    constexpr int NRW = (NR + NWARP - 1) / NWARP;
    for (int jb = jbl; jb >= 0; jb -= SSB) {
       const int wd = sw_min(SSB, w - jb);
@@ -372,7 +383,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
       const int jp = jb - SSB;                    // rows of the previous sub-block, for the columns up to its end
       if (sw_T_mma<NR>()) {
          #pragma unroll
-         for (int i = 0; i < SSB; ++i) ls[(size_t)i * SW_LLD + t] = (acol && t < jb) ? cur[i] : 0.0;
+         for (int i = 0; i < SSB; ++i) if (t < HB) ls[(size_t)i * LLD + t] = (acol && t < jb) ? cur[i] : 0.0;
       }
       if (jp >= 0) {
          #pragma unroll
@@ -402,7 +413,7 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
       }
       cx.sync();
       if (sw_T_mma<NR>()) {
-         if (jb > 0) sw_mma_update<(NR >= 16 ? NR : 16)>(cx, vs, ls, jb, 0, jb);
+         if (jb > 0) sw_mma_update<(NR >= 16 ? NR : 16), LLD>(cx, vs, ls, jb, 0, jb);
          cx.sync();
       } else if (acol && t < jb) {                // columns of the block left of the sub-block
          #pragma unroll
@@ -421,6 +432,10 @@ SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double*
       #pragma unroll
       for (int k = 0; k < NR; ++k) x[(size_t)g * NRT + k] = vs[(size_t)t * XLD + k];
    }
+}
+template <int NR, int NRT, bool POSDEF, class Ctx>
+SW_FN void bwd_wide_T(Ctx& cx, const SolveFront& f, int step, double* x, double* pb, double* smem) {
+   bwd_wide_T_h<NR, NRT, POSDEF, SWB>(cx, f, step, x, pb, smem);
 }
 
 } // namespace b200

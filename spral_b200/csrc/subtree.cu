@@ -1398,7 +1398,8 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                   if (wide_level(lev, nr)) {
                      int f0 = S.level_ptr[lev] - 1, f1 = S.level_ptr[lev + 1] - 1;
                      launch_fwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev], nwork,
-                           (N.lvl_steps[lev] + 7) / 8, posdef, nr, xs, ywork, s, f1 - f0 <= SOLVE_LOOKAHEAD_MAX_FRONTS ? aux : nullptr);
+                           (N.lvl_steps[lev] + 7) / 8, posdef, nr, xs, ywork, s, f1 - f0 <= SOLVE_LOOKAHEAD_MAX_FRONTS ? aux : nullptr,
+                           N.lvl_steps[lev] <= 4);
                   } else
                      launch_fwd_level(N.d_sfronts, N.d_swork + N.swork_ptr[lev], nwork, N.lvl_steps[lev], posdef, nr,
                            xs, ldx, ywork, s, bar);
@@ -1413,7 +1414,7 @@ static int solve_subtree(const Numeric& Nc, SolveJob job, int nrhs, double* x, i
                   if (wide_level(lev, nr))
                      launch_bwd_level_wide(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                            N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, (N.lvl_steps[lev] + 7) / 8, posdef, nr,
-                           xs, pbuf, s, f1 - f0 <= SOLVE_LOOKAHEAD_MAX_FRONTS ? aux : nullptr);
+                           xs, pbuf, s, f1 - f0 <= SOLVE_LOOKAHEAD_MAX_FRONTS ? aux : nullptr, N.lvl_steps[lev] <= 4);
                   else
                   launch_bwd_level(N.d_sfronts, f0, f1 - f0, N.d_swork + N.swork_ptr[lev],
                         N.swork_ptr[lev + 1] - N.swork_ptr[lev], N.d_wbeg, N.lvl_steps[lev], posdef, nr,
