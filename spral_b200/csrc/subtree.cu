@@ -673,11 +673,16 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       std::vector<int4> bulk_regs;          // {front, k0, k1, c_lo} of every front in the bulk lists
       std::vector<RowTile> swap_rows;
       bool any_fail = false;
+      std::vector<char> failed(na_all, 0);
       for (int k = 0; k < na_all; ++k) {
          const int* sn = &snap_host[(size_t)k * 8];
-         if (sn[6] >= 0 && H[act[k]].pend0 - sn[2] > 0) any_fail = true;
+         if (sn[6] >= 0 && H[act[k]].pend0 - sn[2] > 0) { failed[k] = 1; any_fail = true; }
       }
+      /* look-ahead is decided front by front: on a level of several fronts one failed pivot must not put the whole
+       * trailing update of every other front on the main stream (the fronts are independent; a front with a failed
+       * pivot gets its full update and its swaps in order, behind the whole bulk backlog) */
       const bool lookahead = big && !any_fail && g_lookahead;
+      const bool la_level = big && g_lookahead;
 #ifdef SPRAL_B200_SPLIT
       /* distributed top front (split_front.h; protocol: tests/c/dist_front_emu.cpp): while the split is active the far
        * columns live on the helper; the first panel with a failed pivot brings them back and ends it */
@@ -717,7 +722,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
             /* last tile column that holds a column of the next panel */
             int tj_urgent = (std::min(h.pend0 + PW, h.n) - 1) / T;
             int tj_next = (std::min(h.pend0 + 2 * PW, h.n) - 1) / T;     // last tile column of the panel after next
-            bool has_bulk = lookahead && tj_urgent + 1 < nt;
+            bool has_bulk = la_level && !failed[k] && tj_urgent + 1 < nt;
             if (has_bulk) bulk_regs.push_back(make_int4(h.fi, h.p0, h.done, (tj_urgent + 1) * T));
             for (int tj = h.pend0 / T; tj < nt; ++tj) {
 #ifdef SPRAL_B200_SPLIT
@@ -740,7 +745,7 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
          }
       }
       if (err) { if (bulk_pending) cudaStreamSynchronize(N.stream2); return err; }
-      if (lookahead && (int)(bulk.size() + bulk_b.size()) < device_sm_count()) {   // not worth a second stream
+      if (la_level && (int)(bulk.size() + bulk_b.size()) < device_sm_count()) {   // not worth a second stream
          for (const MatTile& t : bulk) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
          for (const MatTile& t : bulk_b) outer.push_back({bulk_regs[t.front].x, t.ti, t.tj});
          bulk.clear(); bulk_b.clear();
