@@ -189,6 +189,20 @@ struct Bump {
 /* Symbolic subtree                                                          */
 /* ------------------------------------------------------------------------ */
 
+/* grow-only pinned host buffer */
+struct PinnedInts {
+   int* p = nullptr; size_t cap = 0;
+   int* ensure(size_t n) {
+      if (n > cap) {
+         if (p) cudaFreeHost(p);
+         cap = std::max<size_t>(2 * n, 1 << 16);
+         if (cudaMallocHost((void**)&p, cap * sizeof(int)) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); throw std::bad_alloc(); }
+      }
+      return p;
+   }
+   ~PinnedInts() { if (p) cudaFreeHost(p); }
+};
+
 struct Symbolic {
    int device = 0, n = 0, sa = 0, en = 0, nloc = 0;
    spral_ssids_b200_options options;
@@ -216,6 +230,7 @@ struct Symbolic {
    std::mutex mtx;
    Buf b_aval, b_scal, b_cbuf[2], b_ld, b_bk, b_ws, b_work, b_retry, b_x, b_y, b_pbuf, b_xt;
    Buf b_y2, b_pbuf2, b_xt2;          // second lane of the solves (two chunks of right-hand sides swept concurrently)
+   PinnedInts snap_pinned;            // per-panel snapshot of the pivoting state (D2H)
    Buf b_bar;                         // arrival counter of the cooperative solve kernels
    Buf b_export[2];                   // packed contribution block handed to another process (IPC), double-buffered
    int export_slot = 0;
@@ -536,7 +551,10 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       h.finished = (f.n == 0);
       h.p0 = 0; h.pend0 = std::min(PW, f.n); h.pend = h.pend0;     // advance_state() opens the same panel
    }
-   std::vector<int> snap_host;
+   /* the snapshot lands in pinned memory (a pageable destination makes the copy synchronous and slower); the buffer
+    * belongs to the symbolic subtree, so it is allocated once, not per factorisation or thread */
+   PinnedInts& snap_pinned = N.S->snap_pinned;
+   int* snap_host = nullptr;
    int err = 0;
    /* SPRAL_B200_TRACE_PANELS=2: a timeline of the level on both streams (events behind every update launch) */
    struct TlRec { int p0; char what; cudaEvent_t a, b; int tiles; };
@@ -613,8 +631,8 @@ static int factor_fronts(Numeric& N, Front* d_fronts, const std::vector<Front>& 
       const auto t_panel0 = std::chrono::steady_clock::now();
       auto take_snapshot = [&]() {
          launch_snapshot(d_fronts, d_flist, na_all, d_snap, s);
-         snap_host.resize((size_t)na_all * 8);
-         CUDA_TRY(cudaMemcpyAsync(snap_host.data(), d_snap, snap_host.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+         snap_host = snap_pinned.ensure((size_t)na_all * 8);
+         CUDA_TRY(cudaMemcpyAsync(snap_host, d_snap, (size_t)na_all * 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
          auto ts0 = std::chrono::steady_clock::now();
          CUDA_TRY(cudaStreamSynchronize(s));
          const double dtw = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();

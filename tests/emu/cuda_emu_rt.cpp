@@ -151,6 +151,8 @@ const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
 /* "Device" memory: malloc, or -- SPRAL_B200_EMU_SHM=1 -- POSIX shared memory, so that an IPC handle (which then carries
  * the segment's name) can be opened by ANOTHER process: the one-process-per-GPU paths run as real processes on the CPU. */
 static bool shm_mode() { static int v = -1; if (v < 0) v = getenv("SPRAL_B200_EMU_SHM") ? 1 : 0; return v == 1; }
+cudaError_t cudaMallocHost(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t bytes) {
    if (!bytes) bytes = 1;
    void* q = nullptr;
