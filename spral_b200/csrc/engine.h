@@ -162,6 +162,8 @@ void launch_bwd_level(const SolveFront* fronts, int first, int count, const RowT
 
 /* wide sweeps for levels of large fronts (solve_wide.h; opt-in) */
 int solve_wide_block();
+/* inverses of the 32 x 32 diagonal blocks of the fronts that carry SolveFront::Linv; work = {front, block} */
+void launch_build_linv(const SolveFront* fronts, const int2* work, int nwork, bool posdef, cudaStream_t s);
 /* Streams and events of the look-ahead inside a wide sweep: the G work on the rows of the next block stays on the
  * sweep's stream, the rest runs on the two far streams beside the following T kernels (solve_wide.h: SW_NEAR / SW_FAR).
  * The backward sweep then needs TWO accumulators per front (pbuf of 2 x count x 256 x nr doubles).

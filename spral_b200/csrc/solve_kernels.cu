@@ -451,6 +451,7 @@ void bwd_level(const SolveFront* fronts, int first, int count, const RowTile* wo
 struct SolveDevCtx {
    __device__ __forceinline__ int tid() const { return threadIdx.x; }
    __device__ __forceinline__ void sync() { __syncthreads(); }
+   __device__ __forceinline__ void sync_warp() { __syncwarp(); }
    __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
    __device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
    __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
@@ -947,6 +948,54 @@ void launch_bwd_level_wide(const SolveFront* fronts, int first, int count, const
 #undef SW_B
 }
 #undef SW_DISPATCH
+
+/* Inverses of the 32 x 32 diagonal blocks of L for the fronts that carry SolveFront::Linv: one warp per block, lane j
+ * solves L x = e_j by substitution (column j of the inverse), the block is written row-major.  Unit diagonal for
+ * L D L^T, the stored diagonal for Cholesky; rows and columns past nelim are identity.  An entry beyond LINV_LIMIT (or
+ * not finite) marks the whole front: the explicit inverse is only as accurate as the block is well conditioned, and
+ * the threshold test bounds the entries of L (by 1 / u), not of its inverse. */
+constexpr double LINV_LIMIT = 1e4;
+template <bool POSDEF>
+__global__ void __launch_bounds__(32)
+k_build_linv(const SolveFront* fronts, const int2* work) {
+   __shared__ double Lb[32][33];
+   __shared__ double X[32][33];
+   const int2 w = work[blockIdx.x];
+   const SolveFront f = fronts[w.x];
+   const int lane = threadIdx.x;
+   const int c0 = w.y * 32;
+   const int wd = min(32, f.nelim - c0);
+   for (int j = 0; j < 32; ++j) {                        // lane = row
+      double v = 0.0;
+      if (lane < wd && j < wd && lane >= j) v = f.L[(size_t)(c0 + lane) + (size_t)(c0 + j) * (size_t)f.ldl];
+      if (lane == j && (!POSDEF || lane >= wd)) v = 1.0;
+      Lb[lane][j] = v;
+   }
+   __syncwarp();
+   const int j = lane;                                   // lane = column of the inverse
+   bool bad = false;
+   for (int i = 0; i < 32; ++i) {
+      double x = 0.0;
+      if (i >= j) {
+         double sum = (i == j) ? 1.0 : 0.0;
+         for (int k = j; k < i; ++k) sum -= Lb[i][k] * X[k][j];
+         x = sum / Lb[i][i];
+      }
+      X[i][j] = x;
+      if (!(fabs(x) <= LINV_LIMIT)) bad = true;
+   }
+   __syncwarp();
+   double* out = const_cast<double*>(f.Linv) + (size_t)w.y * 1024;
+   for (int i = 0; i < 32; ++i) out[i * 32 + lane] = X[i][lane];
+   if (__ballot_sync(0xffffffffu, bad) != 0u && lane == 0) *const_cast<int*>(f.linv_bad) = 1;
+}
+
+void launch_build_linv(const SolveFront* fronts, const int2* work, int nwork, bool posdef, cudaStream_t s) {
+   if (nwork == 0) return;
+   if (posdef) k_build_linv<true><<<nwork, 32, 0, s>>>(fronts, work);
+   else k_build_linv<false><<<nwork, 32, 0, s>>>(fronts, work);
+   COUNT_LAUNCH();
+}
 
 void SolveAux::create() {
    if (far[0]) return;

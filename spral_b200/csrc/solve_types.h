@@ -13,6 +13,10 @@ struct RowTile { int front; int tile; };
 struct SolveFront {
    const double* L; const double* D; const int* perm; const int* rows;
    int ldl, m, n, n0, m0, nelim;
+   /* fronts of the wide sweeps' critical path (256+ eliminated columns): the inverses of the 32 x 32 diagonal blocks of
+    * L, block b at Linv + 1024 b, row-major, zero above the diagonal (k_build_linv); *linv_bad != 0: an inverse came out
+    * large or not finite, the T kernels then substitute as they do for the fronts without inverses (Linv == nullptr) */
+   const double* Linv = nullptr; const int* linv_bad = nullptr;
 };
 
 } // namespace b200

@@ -134,6 +134,14 @@ SW_FN void fwd_wide_T_h(Ctx& cx, const SolveFront& f, int blk, const double* x, 
       for (int k = 0; k < NR; ++k) xs[(size_t)t * XLD + k] = arow ? x[(size_t)g * NRT + k] : 0.0;
    }
    const double* Lrow = f.L + (size_t)(kb + t) + (size_t)kb * ldl;     // row kb+t of the block, from column kb
+   /* inverse diagonal blocks (solve_types.h): the 32-step substitution of a sub-block becomes a 32-term product.  Four
+    * entries of the block per thread (256 threads) or eight (128), loaded one sub-step ahead. */
+   constexpr int TT = HB < SW_TT ? HB : SW_TT, IPT = SSB * SSB / TT;
+   const bool use_inv = f.Linv != nullptr && *f.linv_bad == 0;
+   const double* inv_blk = use_inv ? f.Linv + (size_t)(kb / SSB) * (SSB * SSB) + (size_t)t * IPT : nullptr;
+   double icur[IPT], inxt[IPT];
+   #pragma unroll
+   for (int q = 0; q < IPT; ++q) icur[q] = use_inv ? inv_blk[q] : 0.0;
    double cur[SSB], nxt[SSB];
    {
       const int wd0 = sw_min(SSB, w);
@@ -144,12 +152,19 @@ SW_FN void fwd_wide_T_h(Ctx& cx, const SolveFront& f, int blk, const double* x, 
    constexpr int NRW = (NR + NWARP - 1) / NWARP;
    for (int jb = 0; jb < w; jb += SSB) {
       const int wd = sw_min(SSB, w - jb);
-      if (t >= jb && t < jb + SSB) {              // the rows of the sub-block publish its diagonal block
+      if (use_inv) {                               // everybody publishes its entries of the inverse block
+         #pragma unroll
+         for (int q = 0; q < IPT; ++q) { const int e = t * IPT + q; lkk[(e / SSB) * SW_LK + e % SSB] = icur[q]; }
+      } else if (t >= jb && t < jb + SSB) {        // the rows of the sub-block publish its diagonal block
          const int i = t - jb;
          #pragma unroll
          for (int j = 0; j < SSB; ++j) lkk[i * SW_LK + j] = (i < wd && j < wd && i >= j) ? cur[j] : 0.0;
       }
       const int jn = jb + SSB;                    // next slab of the rows below this sub-block
+      if (use_inv && jn < w) {
+         #pragma unroll
+         for (int q = 0; q < IPT; ++q) inxt[q] = inv_blk[(size_t)(jn / SSB) * (SSB * SSB) + q];
+      }
       if (sw_T_mma<NR>()) {
          #pragma unroll
          for (int j = 0; j < SSB; ++j) if (t < HB) ls[(size_t)j * LLD + t] = (arow && t >= jn) ? cur[j] : 0.0;
@@ -165,6 +180,24 @@ SW_FN void fwd_wide_T_h(Ctx& cx, const SolveFront& f, int blk, const double* x, 
       cx.sync();
       {  /* forward substitution: lanes are the rows of the sub-block, the right-hand sides are dealt to the warps */
          double v[NRW];
+         if (use_inv) {                            // y = Linv_bb r: four partial sums per right-hand side
+            #pragma unroll
+            for (int q = 0; q < NRW; ++q) {
+               const int k = warp * NRW + q;
+               double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+               if (k < NR) {
+                  #pragma unroll
+                  for (int j = 0; j < SSB; j += 4) {
+                     s0 += lkk[lane * SW_LK + j] * xs[(size_t)(jb + j) * XLD + k];
+                     s1 += lkk[lane * SW_LK + j + 1] * xs[(size_t)(jb + j + 1) * XLD + k];
+                     s2 += lkk[lane * SW_LK + j + 2] * xs[(size_t)(jb + j + 2) * XLD + k];
+                     s3 += lkk[lane * SW_LK + j + 3] * xs[(size_t)(jb + j + 3) * XLD + k];
+                  }
+               }
+               v[q] = (s0 + s1) + (s2 + s3);
+            }
+            cx.sync_warp();                        // every lane has read the old values of the sub-block's rows
+         } else {
          #pragma unroll
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? xs[(size_t)(jb + lane) * XLD + k] : 0.0; }
          #pragma unroll 4
@@ -177,6 +210,7 @@ SW_FN void fwd_wide_T_h(Ctx& cx, const SolveFront& f, int blk, const double* x, 
                if (POSDEF) { yj /= dj; if (lane == j) v[q] = yj; }
                v[q] -= l * yj;
             }
+         }
          }
          #pragma unroll
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) xs[(size_t)(jb + lane) * XLD + k] = v[q]; }
@@ -196,6 +230,8 @@ SW_FN void fwd_wide_T_h(Ctx& cx, const SolveFront& f, int blk, const double* x, 
       }
       #pragma unroll
       for (int j = 0; j < SSB; ++j) cur[j] = nxt[j];
+      #pragma unroll
+      for (int q = 0; q < IPT; ++q) icur[q] = inxt[q];
    }
    cx.sync();
    if (arow) {
@@ -368,6 +404,12 @@ SW_FN void bwd_wide_T_h(Ctx& cx, const SolveFront& f, int step, double* x, doubl
    const size_t ldl = (size_t)f.ldl;
    const double* Lcol = f.L + (size_t)kb + (size_t)(kb + t) * ldl;     // column kb+t of the block, from row kb
    const int jbl = ((w - 1) / SSB) * SSB;           // last sub-block: the first one to be solved
+   constexpr int TT = HB < SW_TT ? HB : SW_TT, IPT = SSB * SSB / TT;      // inverse diagonal blocks: see fwd_wide_T_h
+   const bool use_inv = f.Linv != nullptr && *f.linv_bad == 0;
+   const double* inv_blk = use_inv ? f.Linv + (size_t)(kb / SSB) * (SSB * SSB) + (size_t)t * IPT : nullptr;
+   double icur[IPT], inxt[IPT];
+   #pragma unroll
+   for (int q = 0; q < IPT; ++q) icur[q] = use_inv ? inv_blk[(size_t)(jbl / SSB) * (SSB * SSB) + q] : 0.0;
    double cur[SSB], nxt[SSB];
    #pragma unroll
    for (int i = 0; i < SSB; ++i) cur[i] = (acol && t < jbl + SSB && jbl + i < w) ? Lcol[jbl + i] : 0.0;
@@ -375,12 +417,19 @@ SW_FN void bwd_wide_T_h(Ctx& cx, const SolveFront& f, int step, double* x, doubl
    constexpr int NRW = (NR + NWARP - 1) / NWARP;
    for (int jb = jbl; jb >= 0; jb -= SSB) {
       const int wd = sw_min(SSB, w - jb);
-      if (t >= jb && t < jb + SSB) {              // the columns of the sub-block publish its diagonal block
+      if (use_inv) {
+         #pragma unroll
+         for (int q = 0; q < IPT; ++q) { const int e = t * IPT + q; lkk[(e / SSB) * SW_LK + e % SSB] = icur[q]; }
+      } else if (t >= jb && t < jb + SSB) {       // the columns of the sub-block publish its diagonal block
          const int j = t - jb;
          #pragma unroll
          for (int i = 0; i < SSB; ++i) lkk[i * SW_LK + j] = (i < wd && j < wd && i >= j) ? cur[i] : 0.0;
       }
       const int jp = jb - SSB;                    // rows of the previous sub-block, for the columns up to its end
+      if (use_inv && jp >= 0) {
+         #pragma unroll
+         for (int q = 0; q < IPT; ++q) inxt[q] = inv_blk[(size_t)(jp / SSB) * (SSB * SSB) + q];
+      }
       if (sw_T_mma<NR>()) {
          #pragma unroll
          for (int i = 0; i < SSB; ++i) if (t < HB) ls[(size_t)i * LLD + t] = (acol && t < jb) ? cur[i] : 0.0;
@@ -395,6 +444,24 @@ SW_FN void bwd_wide_T_h(Ctx& cx, const SolveFront& f, int step, double* x, doubl
       cx.sync();
       {  /* transposed substitution: lanes are the columns of the sub-block */
          double v[NRW];
+         if (use_inv) {                            // z = Linv_bb^T r
+            #pragma unroll
+            for (int q = 0; q < NRW; ++q) {
+               const int k = warp * NRW + q;
+               double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+               if (k < NR) {
+                  #pragma unroll
+                  for (int i = 0; i < SSB; i += 4) {
+                     s0 += lkk[i * SW_LK + lane] * vs[(size_t)(jb + i) * XLD + k];
+                     s1 += lkk[(i + 1) * SW_LK + lane] * vs[(size_t)(jb + i + 1) * XLD + k];
+                     s2 += lkk[(i + 2) * SW_LK + lane] * vs[(size_t)(jb + i + 2) * XLD + k];
+                     s3 += lkk[(i + 3) * SW_LK + lane] * vs[(size_t)(jb + i + 3) * XLD + k];
+                  }
+               }
+               v[q] = (s0 + s1) + (s2 + s3);
+            }
+            cx.sync_warp();
+         } else {
          #pragma unroll
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; v[q] = (k < NR) ? vs[(size_t)(jb + lane) * XLD + k] : 0.0; }
          #pragma unroll 4
@@ -407,6 +474,7 @@ SW_FN void bwd_wide_T_h(Ctx& cx, const SolveFront& f, int step, double* x, doubl
                if (POSDEF) { zj /= dj; if (lane == j) v[q] = zj; }
                v[q] -= l * zj;
             }
+         }
          }
          #pragma unroll
          for (int q = 0; q < NRW; ++q) { const int k = warp * NRW + q; if (k < NR) vs[(size_t)(jb + lane) * XLD + k] = v[q]; }
@@ -426,6 +494,8 @@ SW_FN void bwd_wide_T_h(Ctx& cx, const SolveFront& f, int step, double* x, doubl
       }
       #pragma unroll
       for (int i = 0; i < SSB; ++i) cur[i] = nxt[i];
+      #pragma unroll
+      for (int q = 0; q < IPT; ++q) icur[q] = inxt[q];
    }
    cx.sync();
    if (acol) {

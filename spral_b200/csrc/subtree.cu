@@ -51,6 +51,10 @@ static int g_solve_wide_min = 8;
 /* look-ahead inside the wide sweeps only on levels of few, large fronts (two accumulators per front; a level of
  * thousands of fronts keeps the T kernels busy anyway) */
 constexpr int SOLVE_LOOKAHEAD_MAX_FRONTS = 64;
+/* fronts with at least this many eliminated columns get the inverses of their 32 x 32 diagonal blocks (8 KB per 32
+ * columns; cfg5: 46 fronts, 23 MB); SPRAL_B200_SOLVE_LINV=0: none */
+constexpr int SOLVE_LINV_MIN_COLS = 256;
+static bool g_solve_linv = true;
 static bool g_solve_lookahead = true; // SPRAL_B200_SOLVE_LOOKAHEAD=0: the wide sweeps on one stream
 static bool g_trace_panels = false;  // SPRAL_B200_TRACE_PANELS=1: per-panel trace lines on stderr (host time between panels)
 static bool g_lookahead = true;      // SPRAL_B200_LOOKAHEAD=0 disables the two-stream panel look-ahead
@@ -398,6 +402,7 @@ struct Numeric {
    Front* d_fronts = nullptr;          // level order
    std::vector<Front> h_fronts;
    SolveFront* d_sfronts = nullptr;
+   double* d_linv = nullptr; int* d_linv_bad = nullptr;       // inverse diagonal blocks of the large fronts (solves)
    RowTile* d_swork = nullptr; int* d_wbeg = nullptr;
    std::vector<int> swork_ptr, lvl_steps;
    size_t max_level_work = 0;
@@ -447,6 +452,8 @@ struct Numeric {
       for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
       for (void* p : chunks) g_pool.release(p);
       for (void* p : ext_allocs) g_pool.release(p);
+      if (d_linv) g_pool.release(d_linv);
+      if (d_linv_bad) g_pool.release(d_linv_bad);
       g_pool.release(d_fronts); g_pool.release(d_sfronts); g_pool.release(d_swork); g_pool.release(d_wbeg);
       g_pool.release(d_export);
       if (stream) cudaStreamDestroy(stream);
@@ -898,6 +905,7 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
    if (const char* e = getenv("SPRAL_B200_SOLVE_COOP")) g_solve_coop = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_WIDE")) g_solve_wide = atoi(e);
    if (const char* e = getenv("SPRAL_B200_SOLVE_LOOKAHEAD")) g_solve_lookahead = atoi(e) != 0;
+   if (const char* e = getenv("SPRAL_B200_SOLVE_LINV")) g_solve_linv = atoi(e) != 0;
    if (const char* e = getenv("SPRAL_B200_SOLVE_WIDE_MIN")) g_solve_wide_min = std::max(1, atoi(e));
    g_bulk_ctas = g_bulk_prio ? -1 : device_sm_count() - 28;
    if (const char* e = getenv("SPRAL_B200_BULK_CTAS")) g_bulk_ctas = atoi(e);
@@ -1292,13 +1300,40 @@ static void factor_subtree(Numeric& N, const double* aval_in, const double* scal
          N.max_level_work = std::max(N.max_level_work, sw.size() - (size_t)N.swork_ptr[lev]);
       }
       N.swork_ptr[S.nlevels] = (int)sw.size();
+      /* inverse diagonal blocks for the fronts whose T kernels are the critical path of a sweep (solve_types.h) */
+      std::vector<int2> lwork;
+      if (g_solve_linv) {
+         size_t nb_total = 0;
+         for (int fi = 0; fi < nloc; ++fi) if (sf[fi].nelim >= SOLVE_LINV_MIN_COLS) nb_total += (size_t)(sf[fi].nelim + 31) / 32;
+         if (nb_total > 0) {
+            N.d_linv = (double*)g_pool.alloc(nb_total * 1024 * sizeof(double));
+            N.d_linv_bad = (int*)g_pool.alloc(nloc * sizeof(int));
+            CUDA_TRY(cudaMemsetAsync(N.d_linv_bad, 0, nloc * sizeof(int), s));
+            size_t off = 0;
+            for (int fi = 0; fi < nloc; ++fi) {
+               if (sf[fi].nelim < SOLVE_LINV_MIN_COLS) continue;
+               const int nb = (sf[fi].nelim + 31) / 32;
+               sf[fi].Linv = N.d_linv + off * 1024;
+               sf[fi].linv_bad = N.d_linv_bad + fi;
+               for (int b = 0; b < nb; ++b) lwork.push_back(make_int2(fi, b));
+               off += (size_t)nb;
+            }
+         }
+      }
       N.d_sfronts = (SolveFront*)g_pool.alloc(nloc * sizeof(SolveFront));
       N.d_swork = (RowTile*)g_pool.alloc(std::max<size_t>(sw.size(), 1) * sizeof(RowTile));
       N.d_wbeg = (int*)g_pool.alloc(nloc * sizeof(int));
       CUDA_TRY(cudaMemcpyAsync(N.d_sfronts, sf.data(), nloc * sizeof(SolveFront), cudaMemcpyHostToDevice, s));
       if (!sw.empty()) CUDA_TRY(cudaMemcpyAsync(N.d_swork, sw.data(), sw.size() * sizeof(RowTile), cudaMemcpyHostToDevice, s));
       CUDA_TRY(cudaMemcpyAsync(N.d_wbeg, wbeg.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, s));
+      int2* d_lwork = nullptr;
+      if (!lwork.empty()) {
+         d_lwork = (int2*)g_pool.alloc(lwork.size() * sizeof(int2));
+         CUDA_TRY(cudaMemcpyAsync(d_lwork, lwork.data(), lwork.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+         launch_build_linv(N.d_sfronts, d_lwork, (int)lwork.size(), posdef, s);
+      }
       CUDA_TRY(cudaStreamSynchronize(s));
+      if (d_lwork) g_pool.release(d_lwork);
    }
 #ifdef SPRAL_B200_SPLIT
    delete N.split; N.split = nullptr;          // phase 4: the helper leaves its service loop

@@ -35,6 +35,7 @@ struct Ctx {
    Block* b; int t;
    int tid() const { return t; }
    void sync() { pthread_barrier_wait(&b->bar); }
+   void sync_warp() { pthread_barrier_wait(&b->warps[t >> 5].bar); }
    double shfl(double v, int src) {
       auto& w = b->warps[t >> 5];
       w.xd[t & 31] = v; pthread_barrier_wait(&w.bar);
