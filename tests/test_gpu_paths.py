@@ -19,7 +19,7 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 SWITCHES = ("SPRAL_B200_PANEL_V2", "SPRAL_B200_BULK_PRIO", "SPRAL_B200_CTILE_BLOCK", "SPRAL_B200_SOLVE_WIDE",
-            "SPRAL_B200_SOLVE_WIDE_MIN", "SPRAL_B200_LOOKAHEAD", "SPRAL_B200_SOLVE_LOOKAHEAD", "SPRAL_B200_SOLVE_LANES")
+            "SPRAL_B200_SOLVE_WIDE_MIN", "SPRAL_B200_LOOKAHEAD", "SPRAL_B200_SOLVE_LOOKAHEAD", "SPRAL_B200_SOLVE_LANES", "SPRAL_B200_SOLVE_LINV")
 CASES = "dense_600_indef,dense_500_posdef,stencil27_36_indef,lap3d_24_posdef,kkt_3000"
 
 
@@ -73,6 +73,8 @@ def test_scheduling_switches_do_not_change_results(tmp_path, baseline):
 
 
 def test_sweeps_without_look_ahead_agree(tmp_path, baseline):
-    """One stream per sweep (no near / far split of the G work, one accumulator per front) and one lane."""
-    got = _dump(tmp_path, "nola", SPRAL_B200_SOLVE_LOOKAHEAD="0", SPRAL_B200_SOLVE_LANES="1", SPRAL_B200_SOLVE_WIDE_MIN="1")
+    """One stream per sweep (no near / far split of the G work, one accumulator per front), one lane, substitution
+    instead of the inverse diagonal blocks."""
+    got = _dump(tmp_path, "nola", SPRAL_B200_SOLVE_LOOKAHEAD="0", SPRAL_B200_SOLVE_LANES="1", SPRAL_B200_SOLVE_WIDE_MIN="1",
+                SPRAL_B200_SOLVE_LINV="0")
     _compare(baseline, got, same_factor=True)
