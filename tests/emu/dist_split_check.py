@@ -20,7 +20,7 @@ def _worker(rank, world, port, grid, kind, logdir, q):
         log = open(os.path.join(logdir, f"rank{rank}.log"), "w")
         os.dup2(log.fileno(), 2)
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2", OMP_CANCELLATION="TRUE",
-                          SPRAL_B200_EMU_SHM="1", SPRAL_B200_DIAG_V2="1", SPRAL_B200_SPLIT="1", SPRAL_B200_TRACE="1",
+                          SPRAL_B200_EMU_SHM="1", SPRAL_B200_SPLIT="1", SPRAL_B200_TRACE="1",
                           SPRAL_B200_SPLIT_TIMEOUT="120")
         for p in (ROOT, os.path.join(ROOT, "tests")):
             if p not in sys.path:

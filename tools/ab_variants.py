@@ -16,8 +16,6 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ENV = {
     "base": {},
-    "diag_v2": {"SPRAL_B200_DIAG_V2": "1"},
-    "diag1": {"SPRAL_B200_DIAG": "1"},               # the thread-per-entry diagonal-block kernel of round 1
     "bulk100": {"SPRAL_B200_BULK_CTAS": "100"},
     "bulk132": {"SPRAL_B200_BULK_CTAS": "132"},
     "v2f64": {"SPRAL_B200_PANEL_V2_FRONTS": "64"},
@@ -28,6 +26,8 @@ ENV = {
     "ctile8": {"SPRAL_B200_CTILE_BLOCK": "8"},       # 16 operand panels of 5.4 MB (K = 5243) stay inside the 126 MB L2
     "bulk84": {"SPRAL_B200_BULK_CTAS": "84"},        # more SMs left for the panel kernels (PANEL_V2 tiles: 1 CTA / SM)
     "solve_wide": {"SPRAL_B200_SOLVE_WIDE": "1"},
+    "solve_nolookahead": {"SPRAL_B200_SOLVE_LOOKAHEAD": "0"},
+    "solve_nolinv": {"SPRAL_B200_SOLVE_LINV": "0"},
 }
 DEFAULT = ["base", "diag1", "panel_v2", "panel_v2+bulk_prio", "panel_v2+bulk100", "panel_v2+bulk132", "panel_v2+v2f8",
            "panel_v2+bulk_prio+solve_wide"]
