@@ -53,12 +53,11 @@ def test_alternative_code_paths_against_the_defaults_on_the_emulator(emu_env):
 
 def test_solve_paths_of_many_right_hand_sides_and_large_fronts_on_the_emulator(emu_env):
     """tests/emu/solve_check.py: tensor-core G kernels, look-ahead inside a sweep, inverse diagonal blocks (L D L^T and
-    Cholesky), half-height T kernels, chunks of 64 + 16 + 4 right-hand sides -- with the defaults and with the
-    look-ahead and the inverse blocks switched off."""
-    for extra in ({}, {"SPRAL_B200_SOLVE_LINV": "0", "SPRAL_B200_SOLVE_LOOKAHEAD": "0", "SPRAL_B200_SOLVE_LANES": "1"}):
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "solve_check.py")], env=dict(emu_env, **extra),
-                           capture_output=True, text=True, timeout=900)
-        assert r.returncode == 0 and r.stdout.count(" OK") == 5, r.stdout[-2000:] + r.stderr[-2000:]
+    Cholesky), half-height T kernels, chunks of 64 + 16 + 4 right-hand sides (the switched-off variants are compared
+    by tests/test_gpu_paths.py, on the emulator above and on the GPU)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "solve_check.py")], env=emu_env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.count(" OK") == 5, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.fixture(scope="module")
